@@ -1,0 +1,304 @@
+/*
+ * sparkl_abi.h — C ABI of libsparkl_b200.so, the B200-native replacement of sparkl's GPU MPM substep.
+ *
+ * Every struct below is the byte image of a `#[repr(C)]` type of the reference (dimforge/sparkl 0.4.0, 3D/f32);
+ * the reference file:line it mirrors is cited next to it, and the layout is pinned by static asserts.
+ * Every entry point replaces one piece of the reference's Rust host API for `CudaMpmPipeline::step`
+ * (src/cuda/cuda_mpm_pipeline.rs:262-659); the piece is cited at the declaration.  The Rust-side binding
+ * a sparkl maintainer would add is in INTEGRATION.md (and rust_shim/).
+ *
+ * Conventions: all functions return 0 (SPK_OK) on success, a negative SPK_E* code for API misuse, or a
+ * positive cudaError_t value for CUDA failures (mirrors `CudaResult<T>`).  Handles own all device memory;
+ * callers own host arrays.  One caller thread per context at a time (same as `&mut SingleGpuMpmContext`).
+ * There is NO CPU fallback: every compute entry point fails with a CUDA error if no sm_100 device exists.
+ */
+#ifndef SPARKL_ABI_H
+#define SPARKL_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPK_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- error codes */
+#define SPK_OK 0
+#define SPK_EINVAL (-1)       /* bad argument (replaces the reference's assert panics, cuda_particle_set.rs:40-59) */
+#define SPK_EUNSUPPORTED (-2) /* feature outside the hot-path scope (e.g. heightfield colliders) */
+#define SPK_ESTATE (-3)       /* call sequence error (e.g. stage call before sort) */
+#define SPK_EOVERFLOW (-4)    /* u32 particle/block limits exceeded (cuda_sparse_grid.rs:197,332) */
+
+/* ---------------------------------------------------------------- particle PODs
+ * src_core/dynamics/particle.rs:14-219 (one device array per struct in the reference, cuda_particle_set.rs:12-19) */
+typedef struct SpkParticlePosition { float point[3]; } SpkParticlePosition;         /* particle.rs:17-20  */
+typedef struct SpkParticleVelocity { float vector[3]; } SpkParticleVelocity;        /* particle.rs:54-57  */
+typedef struct SpkParticleVolume {                                                   /* particle.rs:65-72  */
+    float mass;
+    float volume0;
+    float radius0;
+    float deformation_gradient[9]; /* column-major (nalgebra Matrix3) */
+    float plastic_deformation_gradient_det;
+} SpkParticleVolume;
+typedef struct SpkParticleStatus {                                                   /* particle.rs:119-127 */
+    uint8_t failed;
+    uint8_t is_static;
+    uint8_t kinematic_vel_enabled;
+    uint8_t _pad0;
+    float kinematic_vel[3];
+    uint64_t model_index;
+} SpkParticleStatus;
+typedef struct SpkParticlePhase { float phase; float psi_pos; } SpkParticlePhase;   /* particle.rs:144-148 */
+typedef struct SpkParticleData {                                                     /* particle.rs:201-208 */
+    float nacc_alpha;
+    float plastic_hardening;
+    float elastic_hardening;
+    float log_vol_gain;
+} SpkParticleData;
+
+/* ---------------------------------------------------------------- solver parameters
+ * src_core/dynamics/solver/solver_parameters.rs:17-68 */
+enum { SPK_BOUNDARY_STICK = 0, SPK_BOUNDARY_FRICTION = 1, SPK_BOUNDARY_FRICTION_Z_UP = 2, SPK_BOUNDARY_NONE = 3 };
+enum { SPK_DAMAGE_CDMPM = 0, SPK_DAMAGE_EIGENEROSION = 1, SPK_DAMAGE_MODIFIED_EIGENEROSION = 2, SPK_DAMAGE_NONE = 3 };
+typedef struct SpkSolverParameters {
+    float dt;                  /* default 1/60 */
+    float max_substep_dt;      /* default FLT_MAX */
+    uint32_t max_num_substeps; /* default 1000 */
+    uint32_t boundary_handling; /* ignored on the GPU path (per-collider instead), kept for layout */
+    uint32_t damage_model;      /* passed to g2p2g but unused there (g2p2g.rs:190) */
+    uint8_t force_fluids_volume_recomputation;   /* ignored by the CUDA pipeline */
+    uint8_t enable_boundary_particle_projection; /* ignored (particle_updater.rs:204 is `if false`) */
+    uint8_t stop_after_one_substep;
+    uint8_t _pad0;
+    uint32_t simulation_dofs;   /* ignored by the CUDA pipeline */
+} SpkSolverParameters;
+
+/* ---------------------------------------------------------------- material models
+ * GpuParticleModel, 96 bytes: src_kernels/gpu_particle_model.rs:7-13.  Byte image of the Rust enums
+ * (tags/offsets recovered from the shipped PTX).  The DevicePointer<ParticleData> slots
+ * are ignored by this library: per-particle ParticleData is owned by the context (spk_particles_upload). */
+enum { SPK_CONSTITUTIVE_COROTATED = 0, SPK_CONSTITUTIVE_NEO_HOOKEAN = 1, SPK_CONSTITUTIVE_MONAGHAN = 2, SPK_CONSTITUTIVE_CUSTOM = 3 };
+enum { SPK_PLASTIC_DRUCKER_PRAGER = 0, SPK_PLASTIC_NACC = 1, SPK_PLASTIC_RANKINE = 2, SPK_PLASTIC_SNOW = 3, SPK_PLASTIC_CUSTOM = 4, SPK_PLASTIC_NONE = 5 };
+enum { SPK_FAILURE_MAXIMUM_STRESS = 0, SPK_FAILURE_CUSTOM = 1, SPK_FAILURE_NONE = 2 };
+
+typedef struct SpkCorotatedLinearElasticity { /* elasticity_corotated_linear.rs:12-17 */
+    uint8_t split_stress_on_failure; uint8_t _pad[3];
+    float cfl_coeff; float lambda; float mu;
+} SpkCorotatedLinearElasticity;
+typedef struct SpkNeoHookeanElasticity { float cfl_coeff; float lambda; float mu; } SpkNeoHookeanElasticity; /* elasticity_neo_hookean.rs:11-15 */
+typedef struct SpkMonaghanSphEos { float pressure0; uint32_t gamma; float viscosity; float max_neg_pressure; } SpkMonaghanSphEos; /* eos_monaghan_sph.rs:11-16 */
+typedef struct SpkDruckerPragerPlasticity { /* plasticity_drucker_prager.rs:10-19 */
+    float h0, h1, h2, h3, lambda, mu;
+    uint8_t only_active_when_failed; uint8_t _pad[3];
+    float volume_correction;
+} SpkDruckerPragerPlasticity;
+typedef struct SpkNaccPlasticity { /* plasticity_nacc.rs:12-19 */
+    float mu, kappa;
+    uint8_t hardening_enabled; uint8_t _pad[3];
+    float hardening_factor, cohesion, friction;
+} SpkNaccPlasticity;
+typedef struct SpkRankinePlasticity { float mu, lambda, tensile_strength, softening_rate; } SpkRankinePlasticity; /* plasticity_rankine.rs:11-16 */
+typedef struct SpkSnowPlasticity { float min_epsilon, max_epsilon, hardening_coeff; } SpkSnowPlasticity;         /* plasticity_snow.rs:11-15 */
+typedef struct SpkMaximumStressFailure { float max_principal_stress, max_shear_stress; } SpkMaximumStressFailure; /* failure_maximum_stress.rs:7-10 */
+
+typedef struct SpkGpuParticleModel {
+    /* GpuConstitutiveModel: src_kernels/gpu_constitutive_model.rs:12-17 */
+    uint32_t constitutive_tag; uint32_t _pad0;
+    union {
+        struct { SpkCorotatedLinearElasticity m; uint64_t data_ptr; } corotated;
+        struct { SpkNeoHookeanElasticity m; uint32_t _p; uint64_t data_ptr; } neo_hookean;
+        struct { SpkMonaghanSphEos m; } monaghan;
+        struct { uint32_t id; } custom;
+        uint8_t _bytes[24];
+    } constitutive;
+    /* Option<GpuPlasticModel>: src_kernels/gpu_plastic_model.rs:12-18, None encoded as tag 5 */
+    uint32_t plastic_tag; uint32_t _pad1;
+    union {
+        struct { SpkDruckerPragerPlasticity m; uint64_t data_ptr; } drucker_prager;
+        struct { SpkNaccPlasticity m; uint64_t data_ptr; } nacc;
+        struct { SpkRankinePlasticity m; uint64_t data_ptr; } rankine;
+        struct { SpkSnowPlasticity m; uint32_t _p; uint64_t data_ptr; } snow;
+        struct { uint32_t id; } custom;
+        uint8_t _bytes[40];
+    } plastic;
+    /* Option<CoreFailureModel>: src_core/dynamics/models/failure_model.rs:8-11, None encoded as tag 2 */
+    uint32_t failure_tag;
+    union {
+        SpkMaximumStressFailure maximum_stress;
+        uint32_t custom_id;
+    } failure;
+    uint32_t _pad2;
+} SpkGpuParticleModel;
+
+/* ---------------------------------------------------------------- colliders
+ * GpuCollider, 336 bytes: src_kernels/gpu_collider.rs:203-212 (offsets from the PTX).
+ * Scope: Cuboid (tag 0).  HeightField/TriMesh/Polyline are SURVEY §8(f) "next" rows -> SPK_EUNSUPPORTED. */
+enum { SPK_SHAPE_CUBOID = 0, SPK_SHAPE_HEIGHTFIELD = 1, SPK_SHAPE_TRIMESH = 2, SPK_SHAPE_POLYLINE = 3 };
+typedef struct SpkGpuCollider {
+    uint32_t shape_tag; uint32_t _pad0;
+    union {
+        struct { float half_extents[3]; } cuboid;
+        uint8_t _bytes[288];
+    } shape;
+    float rotation[4];    /* unit quaternion, nalgebra coordinate order (i, j, k, w) */
+    float translation[3];
+    float friction;
+    float penalty_stiffness;
+    uint32_t grid_boundary_handling; /* SPK_BOUNDARY_* */
+} SpkGpuCollider;
+
+/* ---------------------------------------------------------------- sparse grid read-back images
+ * Used by the parity tests and by hosts that inspect the grid; internal device storage is SoA. */
+typedef struct SpkActiveBlockHeader { /* src_kernels/cuda/sort.rs:29-38 */
+    uint64_t virtual_id;  /* BlockVirtualId: x | y<<21 | z<<42, origin 2^20 (gpu_grid.rs:73-120) */
+    uint32_t first_particle;
+    uint32_t num_particles;
+    uint32_t halo_state;  /* bit0 IS_HALO, bit1 HAS_HALO_NEIGHBOR (sort.rs:15-27) */
+    uint32_t _pad0;
+} SpkActiveBlockHeader;
+typedef struct SpkDispatchBlock2ActiveBlock { uint32_t active_block_id; uint32_t first_particle; } SpkDispatchBlock2ActiveBlock; /* gpu_grid.rs:166-172 */
+enum { SPK_PROJ_NOT_COMPUTED = 0, SPK_PROJ_INSIDE = 1, SPK_PROJ_OUTSIDE = 2, SPK_PROJ_TOO_FAR = 3 };
+typedef struct SpkGpuGridNode { /* src_kernels/gpu_grid.rs:443-459, 72 bytes */
+    float mass;
+    float momentum_velocity[3];
+    float psi_momentum_velocity;
+    float psi_mass;
+    float prev_mass;
+    uint32_t _pad0;
+    uint64_t projection_status_tag;     /* SPK_PROJ_* */
+    uint64_t projection_status_payload; /* collider index for Inside/Outside */
+    float collision_normal[3];
+    float projection_scaled_dir[3];
+} SpkGpuGridNode;
+
+/* ---------------------------------------------------------------- timings
+ * CudaDeviceTimings / CudaSubstepTimings (cuda_mpm_pipeline.rs:28-85), milliseconds from CUDA events,
+ * accumulated over the substeps of one spk_step call. */
+typedef struct SpkStepTimings {
+    uint32_t num_substeps;
+    float last_dt;
+    float grid_resize_and_sort_ms;
+    float reset_grid_ms;
+    float estimate_timestep_ms;
+    float g2p2g_ms;
+    float grid_update_ms;
+    float total_ms;
+    uint32_t num_active_blocks;   /* of the last substep */
+    uint32_t num_dispatch_blocks; /* of the last substep */
+    uint32_t g2p2g_launches;
+    uint32_t kernel_launches;     /* all kernels launched by this call */
+} SpkStepTimings;
+
+typedef struct SpkSortInfo {
+    uint32_t num_active_blocks;
+    uint32_t num_dispatch_blocks;
+    uint32_t num_dispatch_halo_blocks;
+    uint32_t hashmap_capacity;
+} SpkSortInfo;
+
+#if defined(__cplusplus)
+static_assert(sizeof(SpkParticlePosition) == 12, "ParticlePosition");
+static_assert(sizeof(SpkParticleVelocity) == 12, "ParticleVelocity");
+static_assert(sizeof(SpkParticleVolume) == 52, "ParticleVolume");
+static_assert(sizeof(SpkParticleStatus) == 24 && offsetof(SpkParticleStatus, kinematic_vel) == 4 &&
+              offsetof(SpkParticleStatus, model_index) == 16, "ParticleStatus");
+static_assert(sizeof(SpkParticlePhase) == 8, "ParticlePhase");
+static_assert(sizeof(SpkParticleData) == 16, "ParticleData");
+static_assert(sizeof(SpkSolverParameters) == 28 && offsetof(SpkSolverParameters, simulation_dofs) == 24, "SolverParameters");
+static_assert(sizeof(SpkGpuParticleModel) == 96, "GpuParticleModel");
+static_assert(offsetof(SpkGpuParticleModel, constitutive) == 8, "constitutive payload @8");
+static_assert(offsetof(SpkGpuParticleModel, plastic_tag) == 32 && offsetof(SpkGpuParticleModel, plastic) == 40, "plastic @32/@40");
+static_assert(offsetof(SpkGpuParticleModel, failure_tag) == 80 && offsetof(SpkGpuParticleModel, failure) == 84, "failure @80/@84");
+static_assert(sizeof(SpkGpuCollider) == 336 && offsetof(SpkGpuCollider, rotation) == 296 &&
+              offsetof(SpkGpuCollider, translation) == 312 && offsetof(SpkGpuCollider, friction) == 324 &&
+              offsetof(SpkGpuCollider, grid_boundary_handling) == 332, "GpuCollider");
+static_assert(sizeof(SpkActiveBlockHeader) == 24, "ActiveBlockHeader");
+static_assert(sizeof(SpkGpuGridNode) == 72 && offsetof(SpkGpuGridNode, projection_status_tag) == 32 &&
+              offsetof(SpkGpuGridNode, collision_normal) == 48 && offsetof(SpkGpuGridNode, projection_scaled_dir) == 60, "GpuGridNode");
+#endif
+
+/* ================================================================ entry points */
+typedef struct spk_ctx spk_ctx;
+
+/* which-selectors of spk_particles_read */
+enum { SPK_ATTR_POSITION = 0, SPK_ATTR_VELOCITY = 1, SPK_ATTR_STATUS = 2, SPK_ATTR_VOLUME = 3, SPK_ATTR_PHASE = 4,
+       SPK_ATTR_DATA = 5, SPK_ATTR_SORTED_IDS = 6 };
+
+int spk_abi_version(void);
+const char* spk_error_string(int code);
+
+/* Context + 2 streams + CudaSparseGrid::with_capacity (testbed_plugin.rs:191-236, cuda_sparse_grid.rs:53-90). */
+int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ctx** out);
+int spk_ctx_destroy(spk_ctx* ctx);
+int spk_ctx_cell_width(const spk_ctx* ctx, float* out);          /* CudaSparseGrid::cell_width, cuda_sparse_grid.rs:92 */
+int spk_ctx_synchronize(spk_ctx* ctx);
+
+/* CudaParticleSet::from_particles + SharedCudaVec<ParticleData>::from_slice (cuda_particle_set.rs:32-71,
+ * testbed_plugin.rs:208-217).  Replaces the whole set.  `data` may be NULL (ParticleData::default()). */
+int spk_particles_upload(spk_ctx* ctx, const SpkParticleStatus* status, const SpkParticlePosition* pos,
+                         const SpkParticleVelocity* vel, const SpkParticleVolume* volume,
+                         const SpkParticlePhase* phase, const SpkParticleData* data, size_t n);
+/* CudaParticleSet::append (cuda_particle_set.rs:137-177). */
+int spk_particles_append(spk_ctx* ctx, const SpkParticleStatus* status, const SpkParticlePosition* pos,
+                         const SpkParticleVelocity* vel, const SpkParticleVolume* volume,
+                         const SpkParticlePhase* phase, const SpkParticleData* data, size_t n);
+/* CudaParticleSet::remove_range (cuda_particle_set.rs:123-131): removes ids [begin, end); later ids shift down. */
+int spk_particles_remove_range(spk_ctx* ctx, size_t begin, size_t end);
+/* CudaParticleSet::len (cuda_particle_set.rs:73). */
+int spk_particles_len(const spk_ctx* ctx, size_t* out);
+/* CudaParticleSet::read_* (cuda_particle_set.rs:93-119): copies attribute `which` of the first n particles,
+ * indexed by the caller's particle id (upload order), in the reference's struct layout, into host memory. */
+int spk_particles_read(spk_ctx* ctx, int which, void* dst, size_t n);
+
+/* CudaParticleModelSet::from_models / ensure_models_are_uploaded (cuda_particle_model_set.rs:27-84). */
+int spk_models_upload(spk_ctx* ctx, const SpkGpuParticleModel* models, size_t n);
+/* CudaColliderSet::from_collider_set after the rapier->GpuCollider conversion (cuda_collider_set.rs:45-126). */
+int spk_colliders_upload(spk_ctx* ctx, const SpkGpuCollider* colliders, size_t n);
+
+/* CudaMpmPipeline::step (cuda_mpm_pipeline.rs:262-659): advances all contexts by params->dt with adaptive
+ * substeps; writes the simulated time (params.dt - remaining) to *simulated_time_out.  nctx must be 1 per
+ * process (one process per GPU; multi-GPU runs use the stage calls below plus the halo calls). */
+int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float gravity[3],
+             SpkStepTimings* timings_or_null, float* simulated_time_out);
+
+/* ---- stage-level calls: the pieces step_generic sequences, exposed so that (a) the parity tests can compare
+ * each stage with the oracle and (b) the multi-process pipeline can interleave the halo exchange. */
+/* reset of the frame's dt accumulator: timestep_length.copy_from(from_sec(params.dt)) (cuda_mpm_pipeline.rs:294-299) */
+int spk_frame_begin(spk_ctx* ctx, const SpkSolverParameters* params);
+/* CudaSparseGrid::launch_sort (cuda_sparse_grid.rs:147-489): K1,K2,K5-K12 of SURVEY §2.2 */
+int spk_stage_sort(spk_ctx* ctx, SpkSortInfo* info_or_null);
+/* reset_grid + copy_grid_projection_data (cuda_mpm_pipeline.rs:371-376): K13,K14 */
+int spk_stage_reset_grid(spk_ctx* ctx);
+/* estimate_timestep_length + read-back (cuda_mpm_pipeline.rs:381-398): K15. Returns into_sec(dt_acc). */
+int spk_stage_estimate_dt(spk_ctx* ctx, float min_dt, float max_dt, float* dt_out);
+/* raw dt accumulator (GpuTimestepLength, gpu_timestep.rs:8-26) for the multi-process min-reduction */
+int spk_dt_acc_get(spk_ctx* ctx, uint64_t* out);
+int spk_dt_acc_set(spk_ctx* ctx, uint64_t value);
+/* g2p2g (cuda_mpm_pipeline.rs:479-498): K16, all dispatch blocks (halo or not) */
+int spk_stage_g2p2g(spk_ctx* ctx, float dt, uint32_t damage_model);
+/* grid_update + swap_buffers (cuda_mpm_pipeline.rs:536-558): K19 */
+int spk_stage_grid_update(spk_ctx* ctx, float dt, const float gravity[3]);
+
+/* ---- halo exchange for multi-process runs (replaces K3,K4,K17,K18 and the D2D copies,
+ * cuda_sparse_grid.rs:256-322, cuda_mpm_pipeline.rs:407-533).  Keys travel as u64 virtual ids; payload is the
+ * 6 summed floats per node (mass, momentum xyz, psi_momentum, psi_mass) = 1536 B per block. */
+int spk_halo_active_keys(spk_ctx* ctx, uint64_t* dev_keys_out, uint32_t capacity, uint32_t* count_out); /* device buffer */
+int spk_halo_tag(spk_ctx* ctx, const uint64_t* dev_remote_keys, uint32_t n_remote, uint32_t* num_halo_out);
+int spk_halo_pack(spk_ctx* ctx, uint64_t* dev_keys_out, float* dev_payload_out, uint32_t capacity, uint32_t* count_out);
+int spk_halo_merge(spk_ctx* ctx, const uint64_t* dev_keys, const float* dev_payload, uint32_t n_blocks);
+
+/* ---- read-back of the sparse grid in the reference's layouts (parity tests; ≙ the commented-out
+ * check_active_blocks, cuda_sparse_grid.rs:491-652).  which_grid: 0 = curr, 1 = next. */
+int spk_grid_num_active_blocks(spk_ctx* ctx, int which_grid, uint32_t* out);
+int spk_grid_read_headers(spk_ctx* ctx, int which_grid, SpkActiveBlockHeader* dst, uint32_t n);
+int spk_grid_read_nodes(spk_ctx* ctx, int which_grid, SpkGpuGridNode* dst, uint32_t n_blocks); /* 64 nodes per block */
+int spk_grid_read_dispatch(spk_ctx* ctx, SpkDispatchBlock2ActiveBlock* dst, uint32_t n);
+/* raw device pointers for zero-copy wrappers (torch / NCCL plumbing); valid until the next upload/append */
+int spk_device_ptr(spk_ctx* ctx, int which /* SPK_ATTR_* */, void** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARKL_ABI_H */

@@ -1,0 +1,110 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY — imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; never by sparkl_b200/."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from sparkl_b200 import abi
+from sparkl_b200.engine import Engine, declare
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "mpm_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        declare(_LIB, "orc_")
+        _LIB.orc_create.argtypes = [C.c_float]
+        _LIB.orc_create.restype = C.c_void_p
+        _LIB.orc_destroy.argtypes = [C.c_void_p]
+        _LIB.orc_step.argtypes = [C.c_void_p, C.POINTER(abi.SolverParameters), C.POINTER(C.c_float * 3),
+                                  C.POINTER(abi.StepTimings), C.POINTER(C.c_float)]
+        _LIB.orc_step.restype = C.c_int
+        _LIB.orc_set_threads.argtypes = [C.c_int]
+        _LIB.orc_set_threads.restype = C.c_int
+        _LIB.orc_block_key_of_point.argtypes = [C.c_void_p, C.c_float]
+        _LIB.orc_block_key_of_point.restype = C.c_uint64
+        _LIB.orc_dt_from_sec.argtypes = [C.c_float]
+        _LIB.orc_dt_from_sec.restype = C.c_uint64
+        _LIB.orc_dt_into_sec.argtypes = [C.c_uint64]
+        _LIB.orc_dt_into_sec.restype = C.c_float
+    return _LIB
+
+
+class OracleEngine(Engine):
+    def __init__(self, cell_width: float):
+        l = lib()
+        super().__init__(l, "orc_", C.c_void_p(l.orc_create(cell_width)))
+        self.cell_width = cell_width
+
+    def __del__(self):
+        try:
+            self._lib.orc_destroy(self._h)
+        except Exception:
+            pass
+
+    def step(self, params: abi.SolverParameters, gravity):
+        g = (C.c_float * 3)(*gravity)
+        t = abi.StepTimings()
+        sim = C.c_float()
+        rc = self._lib.orc_step(self._h, C.byref(params), C.byref(g), C.byref(t), C.byref(sim))
+        if rc:
+            raise abi.SparklError(rc, "orc_step")
+        return sim.value, t
+
+
+def set_threads(n: int) -> int:
+    return lib().orc_set_threads(n)
+
+
+def svd3(F: np.ndarray):
+    """F: 3x3 row-major numpy -> (U, s, Vt) as computed by the oracle's nalgebra stand-in."""
+    l = lib()
+    f = np.ascontiguousarray(F.T, dtype=np.float32)  # column-major image
+    u, s, vt = np.zeros(9, np.float32), np.zeros(3, np.float32), np.zeros(9, np.float32)
+    l.orc_svd3(f.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), vt.ctypes.data_as(C.c_void_p))
+    return u.reshape(3, 3).T, s, vt.reshape(3, 3).T
+
+
+def block_key_of_point(p, cell_width: float) -> int:
+    a = np.asarray(p, np.float32)
+    return lib().orc_block_key_of_point(a.ctypes.data_as(C.c_void_p), cell_width)
+
+
+def kirchhoff_stress(model: abi.ParticleModel, F: np.ndarray, phase=1.0, hardening=1.0, jp=1.0, mass=1.0, volume0=1.0, vel_grad=None):
+    l = lib()
+    m = np.frombuffer(model.to_gpu_model(), np.uint8).copy()
+    d = np.zeros(1, abi.DATA); d["elastic_hardening"] = hardening; d["plastic_hardening"] = 1.0
+    v = np.zeros(1, abi.VOLUME)
+    v["mass"], v["volume0"], v["plastic_deformation_gradient_det"] = mass, volume0, jp
+    v["deformation_gradient"] = np.asarray(F, np.float32).T.reshape(9)
+    g = np.zeros(9, np.float32) if vel_grad is None else np.asarray(vel_grad, np.float32).T.reshape(9).copy()
+    out = np.zeros(9, np.float32)
+    l.orc_kirchhoff_stress(m.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.c_float(phase),
+                           g.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out.reshape(3, 3).T
+
+
+def plastic_update(model: abi.ParticleModel, F: np.ndarray, data: np.ndarray, jp=1.0, phase=1.0):
+    l = lib()
+    m = np.frombuffer(model.to_gpu_model(), np.uint8).copy()
+    v = np.zeros(1, abi.VOLUME)
+    v["mass"], v["volume0"], v["plastic_deformation_gradient_det"] = 1.0, 1.0, jp
+    v["deformation_gradient"] = np.asarray(F, np.float32).T.reshape(9)
+    d = data.copy()
+    l.orc_plastic_update(m.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.c_float(phase))
+    return v["deformation_gradient"][0].reshape(3, 3).T.copy(), float(v["plastic_deformation_gradient_det"][0]), d

@@ -1,0 +1,166 @@
+"""ctypes plumbing shared by the product library (prefix `spk_`) and the test oracle (prefix `orc_`).
+
+Both expose the same stage-level C entry points (include/sparkl_abi.h); `Engine` turns them into numpy-level
+calls.  Nothing here computes: it only marshals arrays across the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+_vp = C.c_void_p
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+def declare(lib, prefix: str):
+    """Declare argtypes/restype for every entry point the Engine uses."""
+    sig = {
+        "particles_upload": [_vp] * 7 + [C.c_size_t],
+        "particles_len": [_vp, C.POINTER(C.c_size_t)],
+        "particles_read": [_vp, C.c_int, _vp, C.c_size_t],
+        "models_upload": [_vp, _vp, C.c_size_t],
+        "colliders_upload": [_vp, _vp, C.c_size_t],
+        "frame_begin": [_vp, C.POINTER(abi.SolverParameters)],
+        "stage_sort": [_vp, C.POINTER(abi.SortInfo)],
+        "stage_reset_grid": [_vp],
+        "stage_estimate_dt": [_vp, C.c_float, C.c_float, C.POINTER(C.c_float)],
+        "dt_acc_get": [_vp, C.POINTER(C.c_uint64)],
+        "dt_acc_set": [_vp, C.c_uint64],
+        "stage_g2p2g": [_vp, C.c_float, C.c_uint32],
+        "stage_grid_update": [_vp, C.c_float, C.POINTER(C.c_float * 3)],
+        "grid_num_active_blocks": [_vp, C.c_int, C.POINTER(C.c_uint32)],
+        "grid_read_headers": [_vp, C.c_int, _vp, C.c_uint32],
+        "grid_read_nodes": [_vp, C.c_int, _vp, C.c_uint32],
+        "grid_read_dispatch": [_vp, _vp, C.c_uint32],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, prefix + name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+
+
+class Engine:
+    """One simulation context behind a C ABI (`spk_ctx*` or `orc_ctx*`)."""
+
+    def __init__(self, lib, prefix: str, handle, error_string=None):
+        self._lib, self._prefix, self._h = lib, prefix, handle
+        self._err = error_string
+
+    def _call(self, name, *args):
+        rc = getattr(self._lib, self._prefix + name)(self._h, *args)
+        if rc != 0:
+            what = self._err(rc) if self._err else name
+            raise abi.SparklError(rc, f"{self._prefix}{name}: {what}")
+
+    # ---- particles ------------------------------------------------------------------------------------------
+    def upload(self, pc: abi.ParticleComponents):
+        arrs = [np.ascontiguousarray(a) for a in (pc.status, pc.position, pc.velocity, pc.volume, pc.phase, pc.data)]
+        for a, dt in zip(arrs, (abi.STATUS, abi.POSITION, abi.VELOCITY, abi.VOLUME, abi.PHASE, abi.DATA)):
+            if a.dtype != dt:
+                raise abi.SparklError(abi.EINVAL, "attribute dtype mismatch")
+        n = len(arrs[0])
+        if any(len(a) != n for a in arrs):  # the reference asserts equal lengths (cuda_particle_set.rs:40-59)
+            raise abi.SparklError(abi.EINVAL, "All attribute buffer must have the same length.")
+        self._call("particles_upload", *[_ptr(a) for a in arrs], n)
+
+    def __len__(self):
+        n = C.c_size_t()
+        self._call("particles_len", C.byref(n))
+        return n.value
+
+    def read(self, which: int, n: int | None = None) -> np.ndarray:
+        n = len(self) if n is None else n
+        out = np.zeros(n, abi.ATTR_DTYPES[which])
+        if n:
+            self._call("particles_read", which, _ptr(out), n)
+        return out
+
+    def read_all(self) -> abi.ParticleComponents:
+        pc = abi.ParticleComponents(0)
+        pc.position, pc.velocity = self.read(abi.ATTR_POSITION), self.read(abi.ATTR_VELOCITY)
+        pc.status, pc.volume = self.read(abi.ATTR_STATUS), self.read(abi.ATTR_VOLUME)
+        pc.phase, pc.data = self.read(abi.ATTR_PHASE), self.read(abi.ATTR_DATA)
+        return pc
+
+    def models_upload(self, models):
+        packed = abi.pack_models(models)
+        self._call("models_upload", _ptr(packed), len(models))
+
+    def colliders_upload(self, colliders):
+        packed = abi.pack_colliders(colliders)
+        self._call("colliders_upload", _ptr(packed), len(colliders))
+
+    # ---- stages ---------------------------------------------------------------------------------------------
+    def frame_begin(self, params: abi.SolverParameters):
+        self._call("frame_begin", C.byref(params))
+
+    def stage_sort(self) -> abi.SortInfo:
+        info = abi.SortInfo()
+        self._call("stage_sort", C.byref(info))
+        return info
+
+    def stage_reset_grid(self):
+        self._call("stage_reset_grid")
+
+    def stage_estimate_dt(self, min_dt: float, max_dt: float) -> float:
+        out = C.c_float()
+        self._call("stage_estimate_dt", min_dt, max_dt, C.byref(out))
+        return out.value
+
+    def dt_acc(self) -> int:
+        out = C.c_uint64()
+        self._call("dt_acc_get", C.byref(out))
+        return out.value
+
+    def set_dt_acc(self, v: int):
+        self._call("dt_acc_set", v)
+
+    def stage_g2p2g(self, dt: float, damage_model: int = abi.DamageModel.NONE):
+        self._call("stage_g2p2g", dt, damage_model)
+
+    def stage_grid_update(self, dt: float, gravity):
+        g = (C.c_float * 3)(*gravity)
+        self._call("stage_grid_update", dt, C.byref(g))
+
+    def substep(self, params: abi.SolverParameters, gravity, remaining: float) -> float:
+        """One iteration of the `while remaining_time > 0` loop of cuda_mpm_pipeline.rs:322-638."""
+        min_dt = np.float32(params.dt) / np.float32(params.max_num_substeps)
+        info = self.stage_sort()
+        self.stage_reset_grid()
+        dt = self.stage_estimate_dt(float(min_dt), float(min(np.float32(remaining), np.float32(params.max_substep_dt))))
+        if info.num_dispatch_blocks > 0:
+            self.stage_g2p2g(dt, params.damage_model)
+        self.stage_grid_update(dt, gravity)
+        return dt
+
+    # ---- grid read-back -------------------------------------------------------------------------------------
+    def num_active_blocks(self, which_grid: int) -> int:
+        out = C.c_uint32()
+        self._call("grid_num_active_blocks", which_grid, C.byref(out))
+        return out.value
+
+    def grid_headers(self, which_grid: int) -> np.ndarray:
+        n = self.num_active_blocks(which_grid)
+        out = np.zeros(n, abi.ACTIVE_BLOCK_HEADER)
+        if n:
+            self._call("grid_read_headers", which_grid, _ptr(out), n)
+        return out
+
+    def grid_nodes(self, which_grid: int) -> np.ndarray:
+        n = self.num_active_blocks(which_grid)
+        out = np.zeros((n, 64), abi.GRID_NODE)
+        if n:
+            self._call("grid_read_nodes", which_grid, _ptr(out), n)
+        return out
+
+    def dispatch(self, n: int) -> np.ndarray:
+        out = np.zeros(n, abi.DISPATCH)
+        if n:
+            self._call("grid_read_dispatch", _ptr(out), n)
+        return out

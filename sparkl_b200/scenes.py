@@ -1,0 +1,130 @@
+"""Deterministic synthetic restatements of the reference's example scenes.
+
+Every generator returns a `Scene`: lattice particles built by `abi.cube_particles` (examples3d/helper.rs:6-40,
+randomize = false), the model list, cuboid colliders, gravity and `SolverParameters::default()` with dt = 1/60.
+Sizes are parameters so the same scene serves the parity tests (thousands of particles) and the benchmark
+(millions).  No RNG is used unless `jitter` is requested (numpy PCG64, seed stated by the caller).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi
+from .abi import (BoundaryHandling, CorotatedLinearElasticity, CuboidCollider, DruckerPragerPlasticity, MonaghanSphEos,
+                  NeoHookeanElasticity, ParticleComponents, ParticleModel, SolverParameters, cube_particles)
+
+
+@dataclass
+class Scene:
+    name: str
+    cell_width: float
+    particles: ParticleComponents
+    models: list
+    colliders: list
+    gravity: tuple = (0.0, -9.81, 0.0)
+    params: SolverParameters = field(default_factory=SolverParameters)
+
+    @property
+    def num_particles(self):
+        return len(self.particles)
+
+
+def box_colliders(lo, hi, thickness=2.0, friction=0.5, handling=BoundaryHandling.Friction, walls=True):
+    """Cuboid floor (top at lo.y) and optionally 4 walls around [lo, hi] — the cuboid stand-in for the reference's
+    heightfield ground (examples3d/sand3.rs:23-38), see SURVEY §8d."""
+    lo, hi = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
+    cx, cz = (lo[0] + hi[0]) / 2, (lo[2] + hi[2]) / 2
+    hx, hz = (hi[0] - lo[0]) / 2 + thickness, (hi[2] - lo[2]) / 2 + thickness
+    hy = (hi[1] - lo[1]) / 2 + thickness
+    cy = (lo[1] + hi[1]) / 2
+    out = [CuboidCollider((hx, thickness / 2, hz), (cx, lo[1] - thickness / 2, cz), friction=friction, grid_boundary_handling=handling)]
+    if walls:
+        out += [
+            CuboidCollider((thickness / 2, hy, hz), (lo[0] - thickness / 2, cy, cz), friction=friction, grid_boundary_handling=handling),
+            CuboidCollider((thickness / 2, hy, hz), (hi[0] + thickness / 2, cy, cz), friction=friction, grid_boundary_handling=handling),
+            CuboidCollider((hx, hy, thickness / 2), (cx, cy, lo[2] - thickness / 2), friction=friction, grid_boundary_handling=handling),
+            CuboidCollider((hx, hy, thickness / 2), (cx, cy, hi[2] + thickness / 2), friction=friction, grid_boundary_handling=handling),
+        ]
+    return out
+
+
+def sand3(ni=100, nj=50, nk=50, x_offset=0.0, with_colliders=True) -> Scene:
+    """examples3d/sand3.rs:40-75: an upper Drucker-Prager sand lattice stacked on a corotated elastic lattice,
+    E = 1e7, nu = 0.2, h = 0.2, r = h/4, rho0 = 2700.  Reference size is (100, 50, 50) x 2 = 500k particles;
+    the 4M benchmark configuration is (200, 100, 100) x 2."""
+    E, NU = 1.0e7, 0.2
+    h = 0.2
+    r = np.float32(h) / np.float32(4.0)
+    models = [ParticleModel.with_plasticity(CorotatedLinearElasticity(E, NU), DruckerPragerPlasticity(E, NU)),
+              ParticleModel(CorotatedLinearElasticity(E, NU))]
+    y0 = np.float32(h) * np.float32(3.0) + np.float32(2.0)
+    upper = cube_particles((x_offset, y0 + r * np.float32(2.0) * np.float32(nj), 0.0), ni, nj, nk, 0, r, 2700.0)
+    lower = cube_particles((x_offset, y0, 0.0), ni, nj, nk, 1, r, 2700.0)
+    pc = ParticleComponents.concatenate([upper, lower])
+    cols = []
+    if with_colliders:
+        ext = 2.0 * float(r)
+        cols = box_colliders((x_offset - 4.0, 2.0, -4.0), (x_offset + ni * ext + 4.0, 2.0 + 2 * nj * ext + 8.0, nk * ext + 4.0))
+    return Scene("sand3", h, pc, models, cols)
+
+
+def fluids3(ni=38, nj=20, nk=20, with_colliders=True) -> Scene:
+    """examples3d/fluids3.rs:17-38: Monaghan weakly-compressible fluid, radius 0.1, h = 0.8 (64 particles per cell
+    at rest), rho0 = 1000.  The reference has no collider; the dam-break variant adds a cuboid floor and walls."""
+    h = 0.8
+    r = 0.1
+    models = [ParticleModel(MonaghanSphEos(1.0e6, 7, 1.01e-3))]
+    pc = cube_particles((1.6, 1.6, 1.6), ni, nj, nk, 0, r, 1000.0)
+    cols = []
+    if with_colliders:
+        cols = box_colliders((0.8, 0.8, 0.8), (1.6 + ni * 0.2 * 2.0, 1.6 + nj * 0.2 * 3.0, 1.6 + nk * 0.2 + 0.8))
+    return Scene("fluids3", h, pc, models, cols)
+
+
+def cube_through_sand3(ni=100, nj=50, nk=50, nc=25) -> Scene:
+    """examples3d/cube_through_sand3.rs:51-75: a Drucker-Prager sand lattice hit by a block of kinematic particles
+    (kinematic_vel = (10, 0, 0)); the "cube" is particles, not an SDF body."""
+    E, NU = 1.0e7, 0.2
+    h = 0.2
+    r = np.float32(h) / np.float32(4.0)
+    models = [ParticleModel.with_plasticity(CorotatedLinearElasticity(E, NU), DruckerPragerPlasticity(E, NU)),
+              ParticleModel(CorotatedLinearElasticity(E, NU))]
+    y0 = np.float32(h) * np.float32(3.0) + np.float32(2.0)
+    sand = cube_particles((0.0, y0, 0.0), ni, nj, nk, 0, r, 2700.0)
+    ext = 2.0 * float(r)
+    block = cube_particles((-nc * ext - 1.0, y0, (nk - nc) * ext / 2), nc, nc, nc, 1, r, 2700.0)
+    block.status["kinematic_vel_enabled"] = 1
+    block.status["kinematic_vel"] = np.array([10.0, 0.0, 0.0], np.float32)
+    pc = ParticleComponents.concatenate([sand, block])
+    cols = box_colliders((-nc * ext - 6.0, 2.0, -4.0), (ni * ext + 4.0, 2.0 + nj * ext + 8.0, nk * ext + 4.0))
+    return Scene("cube_through_sand3", h, pc, models, cols)
+
+
+def neo_hookean_block(ni=40, nj=40, nk=20, x_offset=0.0, with_floor=True) -> Scene:
+    """The synthetic uniform-density Neo-Hookean block of BASELINE.json configs[4] (per-GPU slab 400x400x200 at
+    full size): spacing h/2, h = 0.2, E = 1e6, nu = 0.3, with a small sinusoidal initial displacement (initial
+    velocities are discarded by the reference's first substep)."""
+    h = 0.2
+    r = np.float32(h) / np.float32(4.0)
+    models = [ParticleModel(NeoHookeanElasticity(1.0e6, 0.3))]
+    pc = cube_particles((x_offset, 2.6, 0.0), ni, nj, nk, 0, r, 1000.0)
+    p = pc.position["point"]
+    p[:, 1] += (np.float32(0.01) * np.sin(p[:, 0] * np.float32(3.0))).astype(np.float32)
+    cols = []
+    if with_floor:
+        ext = 2.0 * float(r)
+        cols = box_colliders((x_offset - 4.0, 2.0, -4.0), (x_offset + ni * ext + 4.0, 2.0 + nj * ext + 8.0, nk * ext + 4.0), walls=False)
+    return Scene("neo_hookean_block", h, pc, models, cols)
+
+
+def jitter(scene: Scene, amplitude: float, seed: int = 42) -> Scene:
+    """Uniform position jitter (numpy PCG64(seed)); NOT the reference's un-vendored oorandom stream."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p = scene.particles.position["point"]
+    p += rng.uniform(-amplitude, amplitude, p.shape).astype(np.float32)
+    return scene
+
+
+SCENES = {"sand3": sand3, "fluids3": fluids3, "cube_through_sand3": cube_through_sand3, "neo_hookean_block": neo_hookean_block}
