@@ -108,3 +108,13 @@ def plastic_update(model: abi.ParticleModel, F: np.ndarray, data: np.ndarray, jp
     d = data.copy()
     l.orc_plastic_update(m.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.c_float(phase))
     return v["deformation_gradient"][0].reshape(3, 3).T.copy(), float(v["plastic_deformation_gradient_det"][0]), d
+
+
+def cuboid_project(collider: abi.CuboidCollider, pt):
+    l = lib()
+    c = np.frombuffer(collider.to_gpu_collider(), np.uint8).copy()
+    p = np.asarray(pt, np.float32).copy()
+    out = np.zeros(3, np.float32)
+    inside = C.c_int()
+    l.orc_cuboid_project(c.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.byref(inside))
+    return out, bool(inside.value)

@@ -1,0 +1,57 @@
+"""Loads libsparkl_b200.so (the CUDA product library).  There is no CPU fallback: if the library is missing or no
+CUDA device is usable, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import abi
+from .engine import declare
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsparkl_b200.so")
+_LIB = None
+
+# every symbol include/sparkl_abi.h declares
+EXPORTS = [
+    "spk_abi_version", "spk_error_string", "spk_ctx_create", "spk_ctx_destroy", "spk_ctx_cell_width", "spk_ctx_synchronize",
+    "spk_particles_upload", "spk_particles_append", "spk_particles_remove_range", "spk_particles_len", "spk_particles_read",
+    "spk_models_upload", "spk_colliders_upload", "spk_step", "spk_frame_begin", "spk_stage_sort", "spk_stage_reset_grid",
+    "spk_stage_estimate_dt", "spk_dt_acc_get", "spk_dt_acc_set", "spk_stage_g2p2g", "spk_stage_grid_update",
+    "spk_halo_active_keys", "spk_halo_tag", "spk_halo_pack", "spk_halo_merge", "spk_grid_num_active_blocks",
+    "spk_grid_read_headers", "spk_grid_read_nodes", "spk_grid_read_dispatch", "spk_device_ptr",
+]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise abi.SparklError(abi.ESTATE, f"{LIB_PATH} is not built (run `python -m sparkl_b200.build`); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        declare(l, "spk_")
+        vp = C.c_void_p
+        l.spk_abi_version.restype = C.c_int
+        l.spk_error_string.argtypes = [C.c_int]
+        l.spk_error_string.restype = C.c_char_p
+        l.spk_ctx_create.argtypes = [C.c_int, C.c_float, C.c_uint32, C.POINTER(vp)]
+        l.spk_ctx_destroy.argtypes = [vp]
+        l.spk_ctx_synchronize.argtypes = [vp]
+        l.spk_particles_append.argtypes = [vp] * 7 + [C.c_size_t]
+        l.spk_particles_remove_range.argtypes = [vp, C.c_size_t, C.c_size_t]
+        l.spk_step.argtypes = [C.POINTER(vp), C.c_size_t, C.POINTER(abi.SolverParameters), C.POINTER(C.c_float * 3),
+                               C.POINTER(abi.StepTimings), C.POINTER(C.c_float)]
+        l.spk_halo_active_keys.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        l.spk_halo_tag.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        l.spk_halo_pack.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        l.spk_halo_merge.argtypes = [vp, vp, vp, C.c_uint32]
+        l.spk_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        for name in EXPORTS:
+            if name not in ("spk_error_string",):
+                getattr(l, name).restype = C.c_int
+        _LIB = l
+    return _LIB
+
+
+def error_string(code: int) -> str:
+    return lib().spk_error_string(code).decode()

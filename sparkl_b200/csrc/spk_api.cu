@@ -1,0 +1,752 @@
+// spk_api.cu — the C ABI of include/sparkl_abi.h: context / buffers, particle pack & unpack, and the host sequencing
+// of one `CudaMpmPipeline::step` (src/cuda/cuda_mpm_pipeline.rs:273-659, src/cuda/cuda_sparse_grid.rs:147-489).
+//
+// Host-side redesign: ONE blocking read-back per substep (a 64-byte pinned record holding the active-block count,
+// the dispatch count, the overflow flag and the dt accumulator) instead of the reference's three
+// (cuda_sparse_grid.rs:211-215,392-394, cuda_mpm_pipeline.rs:393-398); buffers only ever grow on the device (no
+// host-initialised `vec![default; n]` + H2D on growth, cuda_sparse_grid.rs:459-475).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "spk_device.cuh"
+
+#define CK(expr)                                   \
+    do {                                           \
+        cudaError_t _e = (expr);                   \
+        if (_e != cudaSuccess) return (int)_e;     \
+    } while (0)
+
+namespace {
+
+template <typename T>
+cudaError_t dev_alloc(T*& p, size_t count) {
+    p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMalloc((void**)&p, count * sizeof(T));
+}
+template <typename T>
+void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+uint32_t next_pow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
+}
+
+void free_grid(GridBuffers& g) {
+    dev_free(g.keys); dev_free(g.vals); dev_free(g.blk_key); dev_free(g.blk_first); dev_free(g.blk_count); dev_free(g.blk_halo);
+    dev_free(g.nbr_self); dev_free(g.nbr_prev); dev_free(g.vel); dev_free(g.acc); dev_free(g.proj); dev_free(g.cacheN); dev_free(g.cacheD);
+}
+// (re)allocate one grid buffer for `cap_hash` hash slots; contents are NOT preserved (only ever done on the next grid,
+// which launch_sort rebuilds from scratch — cuda_sparse_grid.rs:235-243)
+cudaError_t alloc_grid(spk_ctx* c, GridBuffers& g, uint32_t cap_hash) {
+    free_grid(g);
+    g.cap_hash = cap_hash;
+    g.cap_blocks = cap_hash / 2;
+    const size_t nb = g.cap_blocks, nn = nb * 64;
+    cudaError_t e;
+    if ((e = dev_alloc(g.keys, cap_hash)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.vals, cap_hash)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.blk_key, nb)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.blk_first, nb)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.blk_count, nb)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.blk_halo, nb)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.nbr_self, nb * 8)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.nbr_prev, nb * 8)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.vel, nn)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.acc, nn * SPK_ACC_CHANNELS)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.proj, nn)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.cacheN, nn)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.cacheD, nn)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(g.keys, 0xff, (size_t)cap_hash * 8, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(g.vel, 0, nn * sizeof(float4), c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(g.acc, 0, nn * SPK_ACC_CHANNELS * sizeof(float), c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(g.proj, 0, nn * 4, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(g.cacheN, 0, nn * sizeof(float4), c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(g.cacheD, 0, nn * sizeof(float4), c->stream)) != cudaSuccess) return e;
+    g.nab_host = 0;
+    g.has_velocity = 0;
+    return cudaSuccess;
+}
+cudaError_t ensure_slot_scratch(spk_ctx* c, uint32_t cap_hash) {
+    if (c->slot_cnt_cap >= cap_hash) return cudaSuccess;
+    dev_free(c->slot_cnt);
+    cudaError_t e = dev_alloc(c->slot_cnt, cap_hash);
+    c->slot_cnt_cap = e == cudaSuccess ? cap_hash : 0;
+    return e;
+}
+cudaError_t ensure_dispatch(spk_ctx* c) {
+    const GridBuffers& g = c->grid[1 - c->gcur];
+    const uint64_t need = c->n / c->chunk + g.cap_blocks + 2;
+    if (c->dispatch_cap >= need) return cudaSuccess;
+    dev_free(c->dispatch);
+    cudaError_t e = dev_alloc(c->dispatch, need);
+    c->dispatch_cap = e == cudaSuccess ? (uint32_t)need : 0;
+    return e;
+}
+cudaError_t ensure_staging(spk_ctx* c, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 1 << 20);
+    if (c->staging_bytes >= bytes) return cudaSuccess;
+    dev_free(c->staging);
+    cudaError_t e = cudaMalloc(&c->staging, bytes);
+    c->staging_bytes = e == cudaSuccess ? bytes : 0;
+    return e;
+}
+void free_particles(spk_ctx* c) {
+    for (int b = 0; b < 2; ++b) {
+        dev_free(c->pb[b].a0); dev_free(c->pb[b].a1); dev_free(c->pb[b].a2); dev_free(c->pb[b].a3); dev_free(c->pb[b].a4); dev_free(c->pb[b].a5);
+    }
+    dev_free(c->vel); dev_free(c->cold); dev_free(c->slot_of); dev_free(c->rank_of); dev_free(c->perm);
+    c->cap = 0;
+}
+cudaError_t alloc_particles(spk_ctx* c, size_t cap) {
+    free_particles(c);
+    cudaError_t e;
+    for (int b = 0; b < 2; ++b) {
+        if ((e = dev_alloc(c->pb[b].a0, cap)) != cudaSuccess) return e;
+        if ((e = dev_alloc(c->pb[b].a1, cap)) != cudaSuccess) return e;
+        if ((e = dev_alloc(c->pb[b].a2, cap)) != cudaSuccess) return e;
+        if ((e = dev_alloc(c->pb[b].a3, cap)) != cudaSuccess) return e;
+        if ((e = dev_alloc(c->pb[b].a4, cap)) != cudaSuccess) return e;
+        if ((e = dev_alloc(c->pb[b].a5, cap)) != cudaSuccess) return e;
+    }
+    if ((e = dev_alloc(c->vel, cap)) != cudaSuccess) return e;
+    if ((e = dev_alloc(c->cold, cap)) != cudaSuccess) return e;
+    if ((e = dev_alloc(c->slot_of, cap)) != cudaSuccess) return e;
+    if ((e = dev_alloc(c->rank_of, cap)) != cudaSuccess) return e;
+    if ((e = dev_alloc(c->perm, cap)) != cudaSuccess) return e;
+    c->cap = cap;
+    return cudaSuccess;
+}
+
+// ---- pack: reference AoS-per-attribute arrays -> internal float4 streams (ids first..first+n) --------------------
+__global__ void pack_kernel(ParticleBuffers pb, float4* vel, float4* cold, const SpkParticleStatus* status, const SpkParticlePosition* pos,
+                            const SpkParticleVelocity* v, const SpkParticleVolume* volume, const SpkParticlePhase* phase, const SpkParticleData* data,
+                            size_t first, size_t n) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t i = first + k;
+    const SpkParticleStatus st = status[k];
+    const SpkParticleVolume vo = volume[k];
+    const uint32_t flags = (st.failed ? SPK_F_FAILED : 0u) | (st.is_static ? SPK_F_STATIC : 0u) | (st.kinematic_vel_enabled ? SPK_F_KINEMATIC : 0u) |
+                           ((uint32_t)st.model_index << SPK_F_MODEL_SHIFT);
+    pb.a0[i] = make_float4(pos[k].point[0], pos[k].point[1], pos[k].point[2], __uint_as_float(flags));
+    const float* F = vo.deformation_gradient;
+    pb.a1[i] = make_float4(F[0], F[1], F[2], F[3]);
+    pb.a2[i] = make_float4(F[4], F[5], F[6], F[7]);
+    pb.a3[i] = make_float4(F[8], vo.plastic_deformation_gradient_det, vo.mass, vo.volume0);
+    SpkParticleData d = data ? data[k] : SpkParticleData{-0.01f, 1.0f, 1.0f, 0.0f}; // ParticleData::default, particle.rs:211-219
+    pb.a4[i] = make_float4(phase[k].phase, phase[k].psi_pos, d.elastic_hardening, d.plastic_hardening);
+    pb.a5[i] = make_float4(d.log_vol_gain, d.nacc_alpha, __uint_as_float((uint32_t)i), 0.f);
+    vel[i] = make_float4(v[k].vector[0], v[k].vector[1], v[k].vector[2], 0.f);
+    cold[i] = make_float4(st.kinematic_vel[0], st.kinematic_vel[1], st.kinematic_vel[2], vo.radius0);
+}
+// ---- unpack: internal streams (physical order) -> reference layout indexed by original particle id ---------------
+__global__ void unpack_kernel(ParticleBuffers pb, const float4* vel, const float4* cold, const uint32_t* perm_or_null, int which, void* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (which == SPK_ATTR_SORTED_IDS) {
+        const size_t src = perm_or_null ? perm_or_null[i] : i;
+        ((uint32_t*)out)[i] = __float_as_uint(pb.a5[src].z);
+        return;
+    }
+    const uint32_t id = __float_as_uint(pb.a5[i].z);
+    if (id >= n) return;
+    switch (which) {
+    case SPK_ATTR_POSITION: { const float4 r = pb.a0[i]; SpkParticlePosition o; o.point[0] = r.x; o.point[1] = r.y; o.point[2] = r.z; ((SpkParticlePosition*)out)[id] = o; break; }
+    case SPK_ATTR_VELOCITY: { const float4 r = vel[i]; SpkParticleVelocity o; o.vector[0] = r.x; o.vector[1] = r.y; o.vector[2] = r.z; ((SpkParticleVelocity*)out)[id] = o; break; }
+    case SPK_ATTR_STATUS: {
+        const uint32_t f = __float_as_uint(pb.a0[i].w);
+        const float4 cd = cold[id];
+        SpkParticleStatus o;
+        o.failed = (f & SPK_F_FAILED) ? 1 : 0; o.is_static = (f & SPK_F_STATIC) ? 1 : 0; o.kinematic_vel_enabled = (f & SPK_F_KINEMATIC) ? 1 : 0; o._pad0 = 0;
+        o.kinematic_vel[0] = cd.x; o.kinematic_vel[1] = cd.y; o.kinematic_vel[2] = cd.z;
+        o.model_index = f >> SPK_F_MODEL_SHIFT;
+        ((SpkParticleStatus*)out)[id] = o;
+        break;
+    }
+    case SPK_ATTR_VOLUME: {
+        const float4 r1 = pb.a1[i], r2 = pb.a2[i], r3 = pb.a3[i];
+        SpkParticleVolume o;
+        o.mass = r3.z; o.volume0 = r3.w; o.radius0 = cold[id].w;
+        o.deformation_gradient[0] = r1.x; o.deformation_gradient[1] = r1.y; o.deformation_gradient[2] = r1.z; o.deformation_gradient[3] = r1.w;
+        o.deformation_gradient[4] = r2.x; o.deformation_gradient[5] = r2.y; o.deformation_gradient[6] = r2.z; o.deformation_gradient[7] = r2.w;
+        o.deformation_gradient[8] = r3.x; o.plastic_deformation_gradient_det = r3.y;
+        ((SpkParticleVolume*)out)[id] = o;
+        break;
+    }
+    case SPK_ATTR_PHASE: { const float4 r = pb.a4[i]; SpkParticlePhase o; o.phase = r.x; o.psi_pos = r.y; ((SpkParticlePhase*)out)[id] = o; break; }
+    case SPK_ATTR_DATA: {
+        const float4 r4 = pb.a4[i], r5 = pb.a5[i];
+        SpkParticleData o; o.nacc_alpha = r5.y; o.plastic_hardening = r4.w; o.elastic_hardening = r4.z; o.log_vol_gain = r5.x;
+        ((SpkParticleData*)out)[id] = o;
+        break;
+    }
+    default: break;
+    }
+}
+
+size_t attr_size(int which) {
+    switch (which) {
+    case SPK_ATTR_POSITION: return sizeof(SpkParticlePosition);
+    case SPK_ATTR_VELOCITY: return sizeof(SpkParticleVelocity);
+    case SPK_ATTR_STATUS: return sizeof(SpkParticleStatus);
+    case SPK_ATTR_VOLUME: return sizeof(SpkParticleVolume);
+    case SPK_ATTR_PHASE: return sizeof(SpkParticlePhase);
+    case SPK_ATTR_DATA: return sizeof(SpkParticleData);
+    case SPK_ATTR_SORTED_IDS: return sizeof(uint32_t);
+    default: return 0;
+    }
+}
+
+int read_counters(spk_ctx* c) {
+    CK(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+
+const float DT_FACTOR = 1000000000000.0f; // GpuTimestepLength::FACTOR, gpu_timestep.rs:18
+unsigned long long host_dt_from_sec(float dt) {
+    const float v = dt * DT_FACTOR;
+    if (std::isnan(v) || v <= 0.f) return 0ull;
+    if (v >= 1.8446744073709552e19f) return 0xffffffffffffffffull;
+    return (unsigned long long)v;
+}
+float host_dt_into_sec(unsigned long long v) { return (float)v / DT_FACTOR; }
+
+int upload_range(spk_ctx* c, const SpkParticleStatus* status, const SpkParticlePosition* pos, const SpkParticleVelocity* vel, const SpkParticleVolume* volume,
+                 const SpkParticlePhase* phase, const SpkParticleData* data, size_t first, size_t n) {
+    if (n == 0) return SPK_OK;
+    // stage the host AoS arrays on the device, then repack with one kernel
+    const size_t per = sizeof(SpkParticleStatus) + sizeof(SpkParticlePosition) + sizeof(SpkParticleVelocity) + sizeof(SpkParticleVolume) +
+                       sizeof(SpkParticlePhase) + sizeof(SpkParticleData);
+    CK(ensure_staging(c, n * per + 256));
+    char* base = (char*)c->staging;
+    auto put = [&](const void* src, size_t bytes, char*& cursor) -> cudaError_t {
+        cudaError_t e = cudaMemcpyAsync(cursor, src, bytes, cudaMemcpyHostToDevice, c->stream);
+        cursor += (bytes + 15) & ~size_t(15);
+        return e;
+    };
+    char* cur = base;
+    char* d_status = cur; CK(put(status, n * sizeof(SpkParticleStatus), cur));
+    char* d_pos = cur; CK(put(pos, n * sizeof(SpkParticlePosition), cur));
+    char* d_vel = cur; CK(put(vel, n * sizeof(SpkParticleVelocity), cur));
+    char* d_volume = cur; CK(put(volume, n * sizeof(SpkParticleVolume), cur));
+    char* d_phase = cur; CK(put(phase, n * sizeof(SpkParticlePhase), cur));
+    char* d_data = nullptr;
+    if (data) { d_data = cur; CK(put(data, n * sizeof(SpkParticleData), cur)); }
+    pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->pb[c->cur], c->vel, c->cold, (const SpkParticleStatus*)d_status, (const SpkParticlePosition*)d_pos,
+                                                                     (const SpkParticleVelocity*)d_vel, (const SpkParticleVolume*)d_volume,
+                                                                     (const SpkParticlePhase*)d_phase, (const SpkParticleData*)d_data, first, n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream)); // host arrays may be pageable: keep the call synchronous like CudaVec::from_slice
+    return SPK_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int spk_abi_version(void) { return SPK_ABI_VERSION; }
+
+const char* spk_error_string(int code) {
+    switch (code) {
+    case SPK_OK: return "ok";
+    case SPK_EINVAL: return "invalid argument";
+    case SPK_EUNSUPPORTED: return "unsupported (outside the hot-path scope)";
+    case SPK_ESTATE: return "invalid call sequence";
+    case SPK_EOVERFLOW: return "u32 particle/block limit exceeded";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ctx** out) {
+    if (!out || !(cell_width > 0.f)) return SPK_EINVAL;
+    *out = nullptr;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) return (int)cudaErrorInvalidDevice; // TMA bulk copies need sm_90+; the library is built for sm_100a only
+    spk_ctx* c = new (std::nothrow) spk_ctx();
+    if (!c) return (int)cudaErrorMemoryAllocation;
+    std::memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->cell_width = cell_width;
+    c->sm_count = prop.multiProcessorCount;
+    c->chunk = 512;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    CK(cudaMalloc((void**)&c->d_counters, sizeof(DeviceCounters)));
+    CK(cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)));
+    CK(cudaHostAlloc((void**)&c->h_counters, sizeof(DeviceCounters), cudaHostAllocDefault));
+    std::memset(c->h_counters, 0, sizeof(DeviceCounters));
+    // CudaSparseGrid::with_capacity: next_power_of_two().max(1024) blocks (cuda_sparse_grid.rs:53-54); the hash map holds
+    // twice as many slots (50 % maximum load factor, cuda_sparse_grid.rs:219)
+    const uint32_t cap_hash = std::max<uint32_t>(next_pow2(block_capacity), 1024u) * 2u;
+    CK(alloc_grid(c, c->grid[0], cap_hash));
+    CK(alloc_grid(c, c->grid[1], cap_hash));
+    CK(ensure_slot_scratch(c, cap_hash));
+    CK(ensure_staging(c, 1 << 20));
+    CK(alloc_particles(c, 1024));
+    CK(ensure_dispatch(c));
+    CK(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return SPK_OK;
+}
+
+int spk_ctx_destroy(spk_ctx* c) {
+    if (!c) return SPK_EINVAL;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_particles(c);
+    free_grid(c->grid[0]); free_grid(c->grid[1]);
+    dev_free(c->slot_cnt); dev_free(c->dispatch); dev_free(c->models); dev_free(c->colliders); dev_free(c->d_counters);
+    if (c->staging) cudaFree(c->staging);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream); cudaStreamDestroy(c->halo_stream);
+    delete c;
+    return SPK_OK;
+}
+
+int spk_ctx_cell_width(const spk_ctx* c, float* out) { if (!c || !out) return SPK_EINVAL; *out = c->cell_width; return SPK_OK; }
+int spk_ctx_synchronize(spk_ctx* c) { if (!c) return SPK_EINVAL; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return SPK_OK; }
+
+int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkParticlePosition* pos, const SpkParticleVelocity* vel,
+                         const SpkParticleVolume* volume, const SpkParticlePhase* phase, const SpkParticleData* data, size_t n) {
+    if (!c || (n && (!status || !pos || !vel || !volume || !phase))) return SPK_EINVAL;
+    if (n >= 0xffffffffull) return SPK_EOVERFLOW;
+    CK(cudaSetDevice(c->device));
+    for (size_t i = 0; i < n; ++i) if (status[i].model_index >= (1u << 24)) return SPK_EINVAL;
+    if (n > c->cap) CK(alloc_particles(c, n + n / 8 + 1024));
+    c->n = n;
+    c->cur = 0;
+    c->sorted_valid = false;
+    // size the sparse grid for the particle count up front: 2x2x2 particles per cell, 4x4x4 cells per block, 50 % load
+    // (the reference's own estimate, cuda_sparse_grid.rs:222-229), doubled for the shell of neighbour blocks
+    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (64 * 8 * 50)) * 4u, 2048u);
+    GridBuffers& next = c->grid[1 - c->gcur];
+    if (next.cap_hash < want) { CK(alloc_grid(c, next, want)); CK(ensure_slot_scratch(c, want)); }
+    CK(ensure_dispatch(c));
+    return upload_range(c, status, pos, vel, volume, phase, data, 0, n);
+}
+
+int spk_particles_len(const spk_ctx* c, size_t* out) { if (!c || !out) return SPK_EINVAL; *out = c->n; return SPK_OK; }
+
+int spk_particles_read(spk_ctx* c, int which, void* dst, size_t n) {
+    if (!c || (n && !dst) || n > c->n) return SPK_EINVAL;
+    const size_t sz = attr_size(which);
+    if (!sz) return SPK_EINVAL;
+    if (n == 0) return SPK_OK;
+    CK(cudaSetDevice(c->device));
+    CK(ensure_staging(c, c->n * sz));
+    const uint32_t* perm = (which == SPK_ATTR_SORTED_IDS && c->sorted_valid) ? c->perm : nullptr;
+    unpack_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->pb[c->cur], c->vel, c->cold, perm, which, c->staging, c->n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, c->staging, n * sz, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+
+int spk_particles_append(spk_ctx* c, const SpkParticleStatus* status, const SpkParticlePosition* pos, const SpkParticleVelocity* vel,
+                         const SpkParticleVolume* volume, const SpkParticlePhase* phase, const SpkParticleData* data, size_t n) {
+    if (!c || (n && (!status || !pos || !vel || !volume || !phase))) return SPK_EINVAL;
+    if (n == 0) return SPK_OK;
+    CK(cudaSetDevice(c->device));
+    const size_t old_n = c->n, new_n = old_n + n;
+    if (new_n >= 0xffffffffull) return SPK_EOVERFLOW;
+    for (size_t i = 0; i < n; ++i) if (status[i].model_index >= (1u << 24)) return SPK_EINVAL;
+    if (new_n > c->cap) {
+        // grow: read everything back in id order, reallocate, upload again (cold path; CudaVec::append reallocates too)
+        std::vector<SpkParticleStatus> s(new_n); std::vector<SpkParticlePosition> p(new_n); std::vector<SpkParticleVelocity> v(new_n);
+        std::vector<SpkParticleVolume> vo(new_n); std::vector<SpkParticlePhase> ph(new_n); std::vector<SpkParticleData> d(new_n);
+        int rc;
+        if ((rc = spk_particles_read(c, SPK_ATTR_STATUS, s.data(), old_n))) return rc;
+        if ((rc = spk_particles_read(c, SPK_ATTR_POSITION, p.data(), old_n))) return rc;
+        if ((rc = spk_particles_read(c, SPK_ATTR_VELOCITY, v.data(), old_n))) return rc;
+        if ((rc = spk_particles_read(c, SPK_ATTR_VOLUME, vo.data(), old_n))) return rc;
+        if ((rc = spk_particles_read(c, SPK_ATTR_PHASE, ph.data(), old_n))) return rc;
+        if ((rc = spk_particles_read(c, SPK_ATTR_DATA, d.data(), old_n))) return rc;
+        std::copy(status, status + n, s.begin() + old_n); std::copy(pos, pos + n, p.begin() + old_n); std::copy(vel, vel + n, v.begin() + old_n);
+        std::copy(volume, volume + n, vo.begin() + old_n); std::copy(phase, phase + n, ph.begin() + old_n);
+        for (size_t i = 0; i < n; ++i) d[old_n + i] = data ? data[i] : SpkParticleData{-0.01f, 1.0f, 1.0f, 0.0f};
+        return spk_particles_upload(c, s.data(), p.data(), v.data(), vo.data(), ph.data(), d.data(), new_n);
+    }
+    c->n = new_n;
+    c->sorted_valid = false;
+    CK(ensure_dispatch(c));
+    return upload_range(c, status, pos, vel, volume, phase, data, old_n, n);
+}
+
+int spk_particles_remove_range(spk_ctx* c, size_t begin, size_t end) {
+    if (!c || begin > end || end > c->n) return SPK_EINVAL;
+    if (begin == end) return SPK_OK;
+    const size_t old_n = c->n;
+    std::vector<SpkParticleStatus> s(old_n); std::vector<SpkParticlePosition> p(old_n); std::vector<SpkParticleVelocity> v(old_n);
+    std::vector<SpkParticleVolume> vo(old_n); std::vector<SpkParticlePhase> ph(old_n); std::vector<SpkParticleData> d(old_n);
+    int rc;
+    if ((rc = spk_particles_read(c, SPK_ATTR_STATUS, s.data(), old_n))) return rc;
+    if ((rc = spk_particles_read(c, SPK_ATTR_POSITION, p.data(), old_n))) return rc;
+    if ((rc = spk_particles_read(c, SPK_ATTR_VELOCITY, v.data(), old_n))) return rc;
+    if ((rc = spk_particles_read(c, SPK_ATTR_VOLUME, vo.data(), old_n))) return rc;
+    if ((rc = spk_particles_read(c, SPK_ATTR_PHASE, ph.data(), old_n))) return rc;
+    if ((rc = spk_particles_read(c, SPK_ATTR_DATA, d.data(), old_n))) return rc;
+    s.erase(s.begin() + begin, s.begin() + end); p.erase(p.begin() + begin, p.begin() + end); v.erase(v.begin() + begin, v.begin() + end);
+    vo.erase(vo.begin() + begin, vo.begin() + end); ph.erase(ph.begin() + begin, ph.begin() + end); d.erase(d.begin() + begin, d.begin() + end);
+    return spk_particles_upload(c, s.data(), p.data(), v.data(), vo.data(), ph.data(), d.data(), s.size());
+}
+
+int spk_models_upload(spk_ctx* c, const SpkGpuParticleModel* models, size_t n) {
+    if (!c || (n && !models)) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    std::vector<DevModel> dm(n);
+    for (size_t i = 0; i < n; ++i) {
+        const SpkGpuParticleModel& m = models[i];
+        DevModel& d = dm[i];
+        std::memset(&d, 0, sizeof(d));
+        d.ctag = m.constitutive_tag; d.ptag = m.plastic_tag; d.ftag = m.failure_tag;
+        switch (m.constitutive_tag) {
+        case SPK_CONSTITUTIVE_COROTATED:
+            d.c[0] = m.constitutive.corotated.m.cfl_coeff; d.c[1] = m.constitutive.corotated.m.lambda; d.c[2] = m.constitutive.corotated.m.mu;
+            if (m.constitutive.corotated.m.split_stress_on_failure) d.flags |= 1u;
+            break;
+        case SPK_CONSTITUTIVE_NEO_HOOKEAN:
+            d.c[0] = m.constitutive.neo_hookean.m.cfl_coeff; d.c[1] = m.constitutive.neo_hookean.m.lambda; d.c[2] = m.constitutive.neo_hookean.m.mu;
+            break;
+        case SPK_CONSTITUTIVE_MONAGHAN: {
+            d.c[0] = m.constitutive.monaghan.m.pressure0;
+            uint32_t g = m.constitutive.monaghan.m.gamma;
+            std::memcpy(&d.c[1], &g, 4);
+            d.c[2] = m.constitutive.monaghan.m.viscosity; d.c[3] = m.constitutive.monaghan.m.max_neg_pressure;
+            break;
+        }
+        case SPK_CONSTITUTIVE_CUSTOM: break; // zero stress, no dt bound (gpu_constitutive_model.rs:83,108)
+        default: return SPK_EINVAL;
+        }
+        switch (m.plastic_tag) {
+        case SPK_PLASTIC_DRUCKER_PRAGER: {
+            const auto& p = m.plastic.drucker_prager.m;
+            d.p[0] = p.h0; d.p[1] = p.h1; d.p[2] = p.h2; d.p[3] = p.h3; d.p[4] = p.lambda; d.p[5] = p.mu; d.p[6] = p.volume_correction;
+            if (p.only_active_when_failed) d.flags |= 2u;
+            break;
+        }
+        case SPK_PLASTIC_NACC: {
+            const auto& p = m.plastic.nacc.m;
+            d.p[0] = p.mu; d.p[1] = p.kappa; d.p[2] = p.hardening_factor; d.p[3] = p.cohesion; d.p[4] = p.friction;
+            if (p.hardening_enabled) d.flags |= 4u;
+            break;
+        }
+        case SPK_PLASTIC_RANKINE: {
+            const auto& p = m.plastic.rankine.m;
+            d.p[0] = p.mu; d.p[1] = p.lambda; d.p[2] = p.tensile_strength; d.p[3] = p.softening_rate;
+            break;
+        }
+        case SPK_PLASTIC_SNOW: {
+            const auto& p = m.plastic.snow.m;
+            d.p[0] = p.min_epsilon; d.p[1] = p.max_epsilon; d.p[2] = p.hardening_coeff;
+            break;
+        }
+        case SPK_PLASTIC_CUSTOM: case SPK_PLASTIC_NONE: break;
+        default: return SPK_EINVAL;
+        }
+        switch (m.failure_tag) {
+        case SPK_FAILURE_MAXIMUM_STRESS: d.f[0] = m.failure.maximum_stress.max_principal_stress; d.f[1] = m.failure.maximum_stress.max_shear_stress; break;
+        case SPK_FAILURE_CUSTOM: case SPK_FAILURE_NONE: break;
+        default: return SPK_EINVAL;
+        }
+    }
+    dev_free(c->models);
+    CK(dev_alloc(c->models, n));
+    if (n) CK(cudaMemcpy(c->models, dm.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice));
+    c->nmodels = n;
+    return SPK_OK;
+}
+
+int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
+    if (!c || (n && !cols)) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    std::vector<DevCollider> dc(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (cols[i].shape_tag != SPK_SHAPE_CUBOID) return SPK_EUNSUPPORTED; // heightfield / trimesh / polyline: SURVEY §8(f) "next"
+        if (cols[i].grid_boundary_handling > SPK_BOUNDARY_NONE) return SPK_EINVAL;
+        std::memcpy(dc[i].half_extents, cols[i].shape.cuboid.half_extents, 12);
+        std::memcpy(dc[i].rot, cols[i].rotation, 16);
+        std::memcpy(dc[i].tr, cols[i].translation, 12);
+        dc[i].friction = cols[i].friction;
+        dc[i].handling = cols[i].grid_boundary_handling;
+    }
+    dev_free(c->colliders);
+    CK(dev_alloc(c->colliders, n));
+    if (n) CK(cudaMemcpy(c->colliders, dc.data(), n * sizeof(DevCollider), cudaMemcpyHostToDevice));
+    c->ncolliders = n;
+    // colliders changed: invalidate the per-node projection cache of both grids (the reference uploads colliders once)
+    for (int g = 0; g < 2; ++g) CK(cudaMemsetAsync(c->grid[g].proj, 0, (size_t)c->grid[g].cap_blocks * 64 * 4, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stages
+int spk_frame_begin(spk_ctx* c, const SpkSolverParameters* params) {
+    if (!c || !params) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const unsigned long long v = host_dt_from_sec(params->dt);
+    CK(cudaMemcpyAsync(&c->d_counters->dt_acc, &v, 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+
+int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    if (c->n && !c->models) return SPK_ESTATE;
+    for (int attempt = 0; attempt < 16; ++attempt) {
+        GridBuffers& g = c->grid[1 - c->gcur];
+        CK(spk_launch_sort_bin(c));
+        int rc = read_counters(c);
+        if (rc) return rc;
+        const DeviceCounters& hc = *c->h_counters;
+        // grow-and-retry until the load factor is <= 50 % (cuda_sparse_grid.rs:162-253)
+        if (hc.overflow || hc.nab > g.cap_blocks) {
+            const uint64_t want = std::max<uint64_t>((uint64_t)g.cap_hash * 2, (uint64_t)next_pow2((uint64_t)hc.nab * 2));
+            if (want > (1ull << 30)) return SPK_EOVERFLOW;
+            CK(alloc_grid(c, g, (uint32_t)want));
+            CK(ensure_slot_scratch(c, (uint32_t)want));
+            CK(ensure_dispatch(c));
+            continue;
+        }
+        g.nab_host = hc.nab;
+        CK(spk_launch_sort_finish(c));
+        c->sorted_valid = true;
+        if (info) {
+            info->num_active_blocks = hc.nab;
+            uint32_t nd = 0; // dispatch count in the reference's units (128 threads per dispatch block)
+            (void)nd;
+            info->num_dispatch_blocks = hc.ndispatch;
+            info->num_dispatch_halo_blocks = 0;
+            info->hashmap_capacity = g.cap_hash;
+        }
+        return SPK_OK;
+    }
+    return SPK_EOVERFLOW;
+}
+
+int spk_stage_reset_grid(spk_ctx* c) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(spk_launch_reset_grid(c));
+    return SPK_OK;
+}
+
+int spk_stage_estimate_dt(spk_ctx* c, float min_dt, float max_dt, float* dt_out) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(spk_launch_estimate_dt(c, min_dt, max_dt));
+    int rc = read_counters(c);
+    if (rc) return rc;
+    if (dt_out) *dt_out = host_dt_into_sec(c->h_counters->dt_acc);
+    return SPK_OK;
+}
+
+int spk_dt_acc_get(spk_ctx* c, uint64_t* out) {
+    if (!c || !out) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    int rc = read_counters(c);
+    if (rc) return rc;
+    *out = c->h_counters->dt_acc;
+    return SPK_OK;
+}
+int spk_dt_acc_set(spk_ctx* c, uint64_t v) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(&c->d_counters->dt_acc, &v, 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+
+int spk_stage_g2p2g(spk_ctx* c, float dt, uint32_t damage_model) {
+    (void)damage_model; // unused by the reference kernel too (g2p2g.rs:190)
+    if (!c) return SPK_EINVAL;
+    if (!c->sorted_valid) return SPK_ESTATE;
+    CK(cudaSetDevice(c->device));
+    CK(spk_launch_g2p2g(c, dt));
+    return SPK_OK;
+}
+
+int spk_stage_grid_update(spk_ctx* c, float dt, const float gravity[3]) {
+    if (!c || !gravity) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(spk_launch_grid_update(c, dt, gravity));
+    return SPK_OK;
+}
+
+// CudaMpmPipeline::step_generic, cuda_mpm_pipeline.rs:273-659
+int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float gravity[3], SpkStepTimings* timings, float* simulated_time_out) {
+    if (!ctxs || nctx == 0 || !params || !gravity) return SPK_EINVAL;
+    if (nctx != 1) return SPK_EUNSUPPORTED; // one process per GPU; multi-GPU runs drive the stage + halo calls (sparkl_b200/distributed.py)
+    spk_ctx* c = ctxs[0];
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const uint32_t launches0 = c->launches, g2p2g0 = c->g2p2g_launches;
+    if (timings) std::memset(timings, 0, sizeof(*timings));
+    int rc;
+    if ((rc = spk_frame_begin(c, params))) return rc;
+    if (params->dt == 0.0f || c->n == 0) { // nothing to simulate (:305-309)
+        if (simulated_time_out) *simulated_time_out = params->dt;
+        return SPK_OK;
+    }
+    const float min_dt = params->dt / (float)params->max_num_substeps;
+    float remaining = params->dt;
+    uint32_t niter = 0;
+    float acc_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t* ev = c->ev;
+    if (timings) CK(cudaEventRecord(ev[10], c->stream));
+    while (remaining > 0.0f) {
+        ++niter;
+        if (timings) CK(cudaEventRecord(ev[0], c->stream));
+        SpkSortInfo info;
+        if ((rc = spk_stage_sort(c, &info))) return rc;
+        if (timings) CK(cudaEventRecord(ev[1], c->stream));
+        CK(spk_launch_reset_grid(c));
+        if (timings) CK(cudaEventRecord(ev[2], c->stream));
+        float dt;
+        if ((rc = spk_stage_estimate_dt(c, min_dt, std::fmin(remaining, params->max_substep_dt), &dt))) return rc;
+        if (timings) CK(cudaEventRecord(ev[3], c->stream));
+        CK(spk_launch_g2p2g(c, dt));
+        if (timings) CK(cudaEventRecord(ev[4], c->stream));
+        CK(spk_launch_grid_update(c, dt, gravity));
+        if (timings) {
+            CK(cudaEventRecord(ev[5], c->stream));
+            CK(cudaEventSynchronize(ev[5]));
+            for (int k = 0; k < 5; ++k) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); acc_ms[k] += ms; }
+            timings->last_dt = dt;
+            timings->num_active_blocks = info.num_active_blocks;
+            timings->num_dispatch_blocks = info.num_dispatch_blocks;
+        }
+        remaining -= dt;
+        if (remaining <= 10.0f / DT_FACTOR || params->stop_after_one_substep) break; // :630-638
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (timings) {
+        CK(cudaEventRecord(ev[11], c->stream));
+        CK(cudaEventSynchronize(ev[11]));
+        CK(cudaEventElapsedTime(&timings->total_ms, ev[10], ev[11]));
+        timings->num_substeps = niter;
+        timings->grid_resize_and_sort_ms = acc_ms[0]; timings->reset_grid_ms = acc_ms[1]; timings->estimate_timestep_ms = acc_ms[2];
+        timings->g2p2g_ms = acc_ms[3]; timings->grid_update_ms = acc_ms[4];
+        timings->g2p2g_launches = c->g2p2g_launches - g2p2g0;
+        timings->kernel_launches = c->launches - launches0;
+    }
+    if (simulated_time_out) *simulated_time_out = params->dt - remaining;
+    return SPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ read-back
+int spk_grid_num_active_blocks(spk_ctx* c, int which_grid, uint32_t* out) {
+    if (!c || !out) return SPK_EINVAL;
+    *out = (which_grid ? c->grid[1 - c->gcur] : c->grid[c->gcur]).nab_host;
+    return SPK_OK;
+}
+int spk_grid_read_headers(spk_ctx* c, int which_grid, SpkActiveBlockHeader* dst, uint32_t n) {
+    if (!c || (n && !dst)) return SPK_EINVAL;
+    GridBuffers& g = which_grid ? c->grid[1 - c->gcur] : c->grid[c->gcur];
+    if (n > g.nab_host) return SPK_EINVAL;
+    if (!n) return SPK_OK;
+    CK(cudaSetDevice(c->device));
+    std::vector<unsigned long long> key(n);
+    std::vector<uint32_t> first(n), count(n), halo(n);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(key.data(), g.blk_key, n * 8ull, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(first.data(), g.blk_first, n * 4ull, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(count.data(), g.blk_count, n * 4ull, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(halo.data(), g.blk_halo, n * 4ull, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; ++i) dst[i] = SpkActiveBlockHeader{key[i], first[i], count[i], halo[i], 0};
+    return SPK_OK;
+}
+int spk_grid_read_nodes(spk_ctx* c, int which_grid, SpkGpuGridNode* dst, uint32_t n_blocks) {
+    if (!c || (n_blocks && !dst)) return SPK_EINVAL;
+    GridBuffers& g = which_grid ? c->grid[1 - c->gcur] : c->grid[c->gcur];
+    if (n_blocks > g.nab_host) return SPK_EINVAL;
+    if (!n_blocks) return SPK_OK;
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n_blocks * 64 * sizeof(SpkGpuGridNode);
+    CK(ensure_staging(c, bytes));
+    CK(spk_launch_grid_export(c, which_grid, (SpkGpuGridNode*)c->staging, n_blocks));
+    CK(cudaMemcpyAsync(dst, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+// dispatch table in the reference's format: multiplicity = ceil(num_particles / 128) entries per block
+// (write_blocks_multiplicity_to_scan_value + init_gpu_dispatch_blocks_mapping, sort.rs:226-280), derived from the headers
+int spk_grid_read_dispatch(spk_ctx* c, SpkDispatchBlock2ActiveBlock* dst, uint32_t n) {
+    if (!c || (n && !dst)) return SPK_EINVAL;
+    GridBuffers& g = c->sorted_valid ? c->grid[1 - c->gcur] : c->grid[c->gcur];
+    std::vector<SpkActiveBlockHeader> h(g.nab_host);
+    int rc = spk_grid_read_headers(c, c->sorted_valid ? 1 : 0, h.data(), g.nab_host);
+    if (rc) return rc;
+    uint32_t k = 0;
+    for (uint32_t b = 0; b < g.nab_host; ++b) {
+        const uint32_t mult = h[b].num_particles / SPK_REF_G2P2G_THREADS + (h[b].num_particles % SPK_REF_G2P2G_THREADS > 0);
+        for (uint32_t m = 0; m < mult; ++m) {
+            if (k >= n) return SPK_OK;
+            dst[k++] = SpkDispatchBlock2ActiveBlock{b, h[b].first_particle + m * SPK_REF_G2P2G_THREADS};
+        }
+    }
+    return k == n ? SPK_OK : SPK_EINVAL;
+}
+
+int spk_device_ptr(spk_ctx* c, int which, void** out) {
+    if (!c || !out) return SPK_EINVAL;
+    switch (which) {
+    case SPK_ATTR_POSITION: *out = c->pb[c->cur].a0; break;
+    case SPK_ATTR_VELOCITY: *out = c->vel; break;
+    default: return SPK_EINVAL;
+    }
+    return SPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ halo (multi-process)
+int spk_halo_active_keys(spk_ctx* c, uint64_t* dev_keys_out, uint32_t capacity, uint32_t* count_out) {
+    if (!c || !count_out) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const uint32_t nab = c->grid[1 - c->gcur].nab_host;
+    *count_out = nab;
+    if (nab > capacity) return SPK_EINVAL;
+    CK(spk_launch_halo_keys(c, (unsigned long long*)dev_keys_out, capacity));
+    CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+int spk_halo_tag(spk_ctx* c, const uint64_t* dev_remote_keys, uint32_t n_remote, uint32_t* num_halo_out) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(&c->d_counters->num_halo, 0, 4, c->stream));
+    CK(spk_launch_halo_tag(c, (const unsigned long long*)dev_remote_keys, n_remote));
+    int rc = read_counters(c);
+    if (rc) return rc;
+    if (num_halo_out) *num_halo_out = c->h_counters->num_halo;
+    return SPK_OK;
+}
+int spk_halo_pack(spk_ctx* c, uint64_t* dev_keys_out, float* dev_payload_out, uint32_t capacity, uint32_t* count_out) {
+    if (!c || !count_out) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(spk_launch_halo_pack(c, (unsigned long long*)dev_keys_out, dev_payload_out, capacity));
+    int rc = read_counters(c);
+    if (rc) return rc;
+    *count_out = c->h_counters->pad[0];
+    return *count_out > capacity ? SPK_EINVAL : SPK_OK;
+}
+int spk_halo_merge(spk_ctx* c, const uint64_t* dev_keys, const float* dev_payload, uint32_t n_blocks) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(spk_launch_halo_merge(c, (const unsigned long long*)dev_keys, dev_payload, n_blocks));
+    return SPK_OK;
+}
+
+} // extern "C"

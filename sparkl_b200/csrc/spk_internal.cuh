@@ -1,0 +1,139 @@
+// spk_internal.cuh — device data layout and context of libsparkl_b200 (B200 / sm_100a).
+//
+// HBM layout:
+//  * particles: "array of float4 streams" (AoSoA-free SoA of 16-byte records), double buffered.  g2p2g reads the
+//    current buffer through the sort permutation and writes the next buffer in sorted order, so particles are
+//    physically re-sorted by block every substep for free and all stores are fully coalesced.
+//  * sparse grid: per active block 64 cells; `vel` (float4: v.xyz, psi_velocity) is one contiguous 1 KB chunk per
+//    block so a g2p2g CTA stages its 2x2x2 block tile with 8 TMA bulk copies; `acc` ([6][64] floats: mass,
+//    momentum xyz, psi_momentum, psi_mass) is one contiguous 1.5 KB chunk per block so the tile is flushed with 8
+//    TMA bulk reduce-adds.  Collider cache (`proj`, `cacheN`, `cacheD`) is touched only by reset/grid_update.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sparkl_abi.h"
+
+#define SPK_CELLS_PER_BLOCK 64
+#define SPK_TILE_CELLS 512
+#define SPK_ACC_CHANNELS 6
+#define SPK_EMPTY_KEY 0xffffffffffffffffull
+#define SPK_NO_BLOCK 0xffffffffu
+#define SPK_REF_G2P2G_THREADS 128u /* G2P2G_THREADS of the reference, src_kernels/cuda/mod.rs:15 (dispatch read-back) */
+
+// particle flag bits (record A0.w)
+#define SPK_F_FAILED 1u
+#define SPK_F_STATIC 2u
+#define SPK_F_KINEMATIC 4u
+#define SPK_F_MODEL_SHIFT 8
+
+struct ParticleBuffers { // one of the two ping-pong buffers
+    float4* a0;          // x, y, z, flags (bits)
+    float4* a1;          // F col-major 0..3
+    float4* a2;          // F 4..7
+    float4* a3;          // F8, Jp, mass, volume0
+    float4* a4;          // phase, psi_pos, elastic_hardening, plastic_hardening
+    float4* a5;          // log_vol_gain, nacc_alpha, orig_id (bits), unused
+};
+
+struct DevModel { // compact device image of GpuParticleModel (include/sparkl_abi.h)
+    uint32_t ctag, ptag, ftag, flags; // flags: bit0 split_stress_on_failure, bit1 only_active_when_failed, bit2 hardening_enabled
+    float c[4];                       // corotated: cfl, lambda, mu | neo-hookean: cfl, lambda, mu | monaghan: pressure0, gamma(bits), viscosity, max_neg_pressure
+    float p[8];                       // DP: h0,h1,h2,h3,lambda,mu,volume_correction | NACC: mu,kappa,hardening_factor,cohesion,friction | Rankine: mu,lambda,tensile,softening | Snow: min_eps,max_eps,hardening_coeff
+    float f[2];                       // max_principal_stress, max_shear_stress
+};
+
+struct DevCollider {
+    float half_extents[3];
+    float rot[4]; // i, j, k, w
+    float tr[3];
+    float friction;
+    uint32_t handling;
+};
+
+struct GridBuffers { // one of the two sparse-grid buffers (curr / next)
+    // hash map: key -> block id (open addressing, linear probing, capacity power of two)
+    unsigned long long* keys;
+    uint32_t* vals;
+    uint32_t cap_hash;
+    uint32_t cap_blocks; // capacity of all per-block arrays (== cap_hash / 2)
+    // per block
+    unsigned long long* blk_key;
+    uint32_t* blk_first;
+    uint32_t* blk_count;
+    uint32_t* blk_halo;
+    int32_t* nbr_self; // [cap_blocks][8] ids of key + {0,1}^3 in THIS grid (octant bit0 = x, bit1 = y, bit2 = z)
+    int32_t* nbr_prev; // [cap_blocks][8] ids of the same keys in the OTHER (previous) grid, -1 when absent
+    // per node
+    float4* vel;     // [cap_blocks*64] velocity.xyz, psi_velocity (valid after grid_update)
+    float* acc;      // [cap_blocks][6][64]
+    uint32_t* proj;  // [cap_blocks*64] projection status: tag | collider << 2
+    float4* cacheN;  // collision_normal.xyz, prev_mass
+    float4* cacheD;  // projection_scaled_dir.xyz, unused
+    uint32_t nab_host;      // host copy of the number of active blocks
+    uint32_t has_velocity;  // 1 after grid_update (momentum_velocity holds velocities)
+};
+
+struct DeviceCounters { // one 64-byte record read back once per substep (pinned mirror on the host)
+    uint32_t nab;            // number of active blocks
+    uint32_t ndispatch;      // number of g2p2g dispatch entries
+    uint32_t overflow;       // hash map full / block capacity exceeded
+    uint32_t nparticles_binned;
+    unsigned long long dt_acc; // GpuTimestepLength
+    uint32_t num_halo;
+    uint32_t pad[7];
+};
+
+struct DispatchEntry { uint32_t block; uint32_t first; uint32_t count; uint32_t pad; };
+
+struct spk_ctx {
+    int device;
+    float cell_width;
+    cudaStream_t stream, halo_stream;
+    // particles
+    size_t n, cap;
+    int cur; // index of the current particle buffer
+    ParticleBuffers pb[2];
+    float4* vel;     // vx, vy, vz, unused — aligned with pb[cur]
+    float4* cold;    // kinematic_vel.xyz, radius0 — indexed by ORIGINAL particle id
+    uint32_t* slot_of; // hash slot of the particle's block (current order)
+    uint32_t* rank_of; // rank inside its block
+    uint32_t* perm;    // sorted index -> index in current order
+    bool sorted_valid; // perm/slot tables describe pb[cur]
+    // models / colliders
+    DevModel* models; size_t nmodels; uint32_t model_flags_any; // bit0: any model needs an SVD
+    DevCollider* colliders; size_t ncolliders;
+    // grid
+    GridBuffers grid[2];
+    int gcur;             // grid[gcur] = curr (read only), grid[1-gcur] = next
+    uint32_t* slot_cnt;   // [cap_hash of next] particles per hash slot
+    uint32_t slot_cnt_cap;
+    DispatchEntry* dispatch; uint32_t dispatch_cap;
+    uint32_t chunk;       // particles per g2p2g dispatch entry
+    // counters
+    DeviceCounters* d_counters;
+    DeviceCounters* h_counters; // pinned
+    // scratch for read-back / staging
+    void* staging; size_t staging_bytes;
+    // timing
+    cudaEvent_t ev[12];
+    uint32_t launches;
+    uint32_t g2p2g_launches;
+    int sm_count;
+};
+
+// ---- kernels launch wrappers (defined in the .cu files) ---------------------------------------------------------
+cudaError_t spk_launch_sort_bin(spk_ctx* c);                 // K1: hash insert + count + rank per particle
+cudaError_t spk_launch_sort_finish(spk_ctx* c);              // K2..K5: neighbours, ids/scan, tables, scatter
+cudaError_t spk_launch_reset_grid(spk_ctx* c);
+cudaError_t spk_launch_estimate_dt(spk_ctx* c, float min_dt, float max_dt);
+cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt);
+cudaError_t spk_launch_grid_update(spk_ctx* c, float dt, const float gravity[3]);
+cudaError_t spk_launch_pack_upload(spk_ctx* c, const void* d_status, const void* d_pos, const void* d_vel, const void* d_volume,
+                                   const void* d_phase, const void* d_data, size_t first, size_t n);
+cudaError_t spk_launch_unpack(spk_ctx* c, int which, void* d_out, size_t n);
+cudaError_t spk_launch_grid_export(spk_ctx* c, int which_grid, SpkGpuGridNode* d_out, uint32_t nblocks);
+cudaError_t spk_launch_halo_keys(spk_ctx* c, unsigned long long* out, uint32_t capacity);
+cudaError_t spk_launch_halo_tag(spk_ctx* c, const unsigned long long* remote, uint32_t n);
+cudaError_t spk_launch_halo_pack(spk_ctx* c, unsigned long long* keys, float* payload, uint32_t capacity);
+cudaError_t spk_launch_halo_merge(spk_ctx* c, const unsigned long long* keys, const float* payload, uint32_t n);

@@ -1,0 +1,213 @@
+// spk_sort.cu — particle binning, sparse-grid block activation, block ids / scans, neighbour tables, permutation.
+//
+// Replaces K1-K12 of the reference (src_kernels/cuda/sort.rs:58-280, hashmap.rs:37-96,
+// prefix_sum.rs, sequenced by src/cuda/cuda_sparse_grid.rs:147-489).  Redesign:
+//  * ONE pass over positions (the reference reads them three times: K2, K5, K10): a warp first de-duplicates its
+//    block keys with match.any (particles are kept physically block-sorted, so a warp usually holds 1-2 keys), the
+//    group leader inserts the key and reserves ranks with one atomicAdd per (warp, block).
+//  * the 8 associated blocks are activated per occupied block, not per particle (8 CAS per particle in K2).
+//  * block ids are the rank of the hash slot (reduce-then-scan over the table), so ids need no atomic counter and the
+//    three scans of the reference (first_particle, dispatch base, id) collapse into one.
+//  * neighbour-block tables (ids of key + {0,1}^3 in the next and in the previous grid) are built once per block so
+//    g2p2g / reset never probe the hash map.
+#include "spk_device.cuh"
+
+namespace {
+
+constexpr int BIN_THREADS = 256;
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8; // slots per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4* __restrict__ a0, uint32_t n, float h, unsigned long long* keys,
+                                                                     uint32_t cap_hash, uint32_t* slot_cnt, uint32_t* __restrict__ slot_of,
+                                                                     uint32_t* __restrict__ rank_of, DeviceCounters* counters) {
+    const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    const bool valid = i < n;
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const float4 p = a0[i];
+    const unsigned long long key = spk_block_key_of_point(p.x, p.y, p.z, h);
+    const unsigned group = __match_any_sync(active, key);
+    const int leader = __ffs(group) - 1;
+    const int lane = threadIdx.x & 31;
+    uint32_t slot = SPK_NO_BLOCK, base = 0;
+    if (lane == leader) {
+        slot = spk_hash_insert(keys, cap_hash, key);
+        if (slot != SPK_NO_BLOCK) base = atomicAdd(&slot_cnt[slot], (uint32_t)__popc(group));
+        else counters->overflow = 1;
+    }
+    slot = __shfl_sync(group, slot, leader);
+    base = __shfl_sync(group, base, leader);
+    slot_of[i] = slot;
+    rank_of[i] = base + __popc(group & spk_lanemask_lt());
+}
+
+// touch_particle_blocks (sort.rs:58-72) done per occupied block: activate key + {0,1}^3 (gpu_grid.rs:307-321)
+__global__ void activate_neighbours_kernel(unsigned long long* keys, uint32_t cap_hash, const uint32_t* __restrict__ slot_cnt, DeviceCounters* counters) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= cap_hash) return;
+    if (slot_cnt[s] == 0) return; // only blocks that own particles (slots created here keep a zero count)
+    const unsigned long long key = keys[s];
+    for (int o = 1; o < 8; ++o)
+        if (spk_hash_insert(keys, cap_hash, spk_key_offset(key, o)) == SPK_NO_BLOCK) counters->overflow = 1;
+}
+
+struct Triple { uint32_t occ, cnt, mult; };
+__device__ __forceinline__ Triple operator+(Triple a, Triple b) { return Triple{a.occ + b.occ, a.cnt + b.cnt, a.mult + b.mult}; }
+
+__device__ __forceinline__ Triple block_exclusive_scan(Triple v, Triple& total) {
+    __shared__ Triple warp_tot[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Triple inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Triple o{__shfl_up_sync(0xffffffffu, inc.occ, d), __shfl_up_sync(0xffffffffu, inc.cnt, d), __shfl_up_sync(0xffffffffu, inc.mult, d)};
+        if (lane >= d) inc = inc + o;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    Triple base{0, 0, 0}, tot{0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < wid) base = base + warp_tot[w];
+        tot = tot + warp_tot[w];
+    }
+    __syncthreads();
+    total = tot;
+    return Triple{base.occ + inc.occ - v.occ, base.cnt + inc.cnt - v.cnt, base.mult + inc.mult - v.mult};
+}
+
+__device__ __forceinline__ Triple slot_triple(const unsigned long long* keys, const uint32_t* slot_cnt, uint32_t s, uint32_t cap_hash, uint32_t chunk) {
+    Triple t{0, 0, 0};
+    if (s < cap_hash && keys[s] != SPK_EMPTY_KEY) {
+        t.occ = 1;
+        t.cnt = slot_cnt[s];
+        t.mult = (t.cnt + chunk - 1) / chunk;
+    }
+    return t;
+}
+
+// pass 1 of reduce-then-scan: per-CTA totals of (occupied slots, particles, dispatch entries)
+__global__ void __launch_bounds__(SCAN_THREADS) slot_totals_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ slot_cnt,
+                                                                    uint32_t cap_hash, uint32_t chunk, Triple* partials) {
+    Triple acc{0, 0, 0};
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) acc = acc + slot_triple(keys, slot_cnt, base + k, cap_hash, chunk);
+    Triple total;
+    block_exclusive_scan(acc, total);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+// pass 2: ids = rank of the slot, first_particle / dispatch base = exclusive prefix sums (replaces K6-K9, K11, K12)
+__global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ slot_cnt,
+                                                                   uint32_t cap_hash, uint32_t chunk, const Triple* __restrict__ partials, uint32_t* vals,
+                                                                   GridBuffers g, DispatchEntry* dispatch, uint32_t dispatch_cap, DeviceCounters* counters) {
+    __shared__ Triple s_base;
+    // redundant reduction of the partials of all previous CTAs (at most a few hundred values)
+    Triple pre{0, 0, 0};
+    for (uint32_t j = threadIdx.x; j < blockIdx.x; j += SCAN_THREADS) pre = pre + partials[j];
+    Triple pre_tot;
+    block_exclusive_scan(pre, pre_tot);
+    if (threadIdx.x == 0) s_base = pre_tot;
+    __syncthreads();
+    const Triple cta_base = s_base;
+
+    Triple item[SCAN_ITEMS];
+    Triple acc{0, 0, 0};
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { item[k] = slot_triple(keys, slot_cnt, base + k, cap_hash, chunk); acc = acc + item[k]; }
+    Triple total;
+    Triple run = block_exclusive_scan(acc, total) + cta_base;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (item[k].occ) {
+            const uint32_t s = base + k, id = run.occ;
+            vals[s] = id;
+            if (id < g.cap_blocks) {
+                g.blk_key[id] = keys[s];
+                g.blk_first[id] = run.cnt;
+                g.blk_count[id] = item[k].cnt;
+                g.blk_halo[id] = 0; // HaloState::EMPTY, gpu_grid.rs:353-368
+            } else {
+                counters->overflow = 1;
+            }
+            for (uint32_t m = 0; m < item[k].mult; ++m) {
+                const uint32_t d = run.mult + m;
+                if (d < dispatch_cap) dispatch[d] = DispatchEntry{id, run.cnt + m * chunk, min(chunk, item[k].cnt - m * chunk), 0};
+                else counters->overflow = 1;
+            }
+        }
+        run = run + item[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) {
+        counters->nab = run.occ;
+        counters->ndispatch = run.mult;
+        counters->nparticles_binned = run.cnt;
+    }
+}
+
+// neighbour-block tables: for block b, ids of key + {0,1}^3 in the next grid (always present) and in the previous grid
+__global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, uint32_t nab) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = t >> 3, o = t & 7;
+    if (b >= nab) return;
+    const unsigned long long key = spk_key_offset(next.blk_key[b], (int)o);
+    next.nbr_self[b * 8 + o] = spk_hash_get(next, key);
+    next.nbr_prev[b * 8 + o] = spk_hash_get(prev, key);
+}
+
+// finalize_particles_sort (sort.rs:201-221): sorted slot -> index in the current physical order
+__global__ void __launch_bounds__(BIN_THREADS) scatter_perm_kernel(const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ rank_of, uint32_t n,
+                                                                    const uint32_t* __restrict__ vals, const uint32_t* __restrict__ blk_first,
+                                                                    uint32_t cap_blocks, uint32_t* __restrict__ perm) {
+    const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t slot = slot_of[i];
+    if (slot == SPK_NO_BLOCK) return;
+    const uint32_t id = vals[slot];
+    if (id >= cap_blocks) return;
+    perm[blk_first[id] + rank_of[i]] = i;
+}
+
+} // namespace
+
+cudaError_t spk_launch_sort_bin(spk_ctx* c) {
+    GridBuffers& g = c->grid[1 - c->gcur];
+    cudaStream_t s = c->stream;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(g.keys, 0xff, (size_t)g.cap_hash * 8, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(c->slot_cnt, 0, (size_t)g.cap_hash * 4, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(c->d_counters, 0, 16, s)) != cudaSuccess) return e; // nab, ndispatch, overflow, nparticles_binned
+    const uint32_t n = (uint32_t)c->n;
+    if (n) {
+        bin_particles_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->pb[c->cur].a0, n, c->cell_width, g.keys, g.cap_hash, c->slot_cnt,
+                                                                                        c->slot_of, c->rank_of, c->d_counters);
+        activate_neighbours_kernel<<<(g.cap_hash + 255) / 256, 256, 0, s>>>(g.keys, g.cap_hash, c->slot_cnt, c->d_counters);
+        c->launches += 2;
+    }
+    const uint32_t ntiles = (g.cap_hash + SCAN_TILE - 1) / SCAN_TILE;
+    Triple* partials = (Triple*)c->staging; // staging is at least 64 KB
+    slot_totals_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials);
+    assign_ids_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials, g.vals, g, c->dispatch, c->dispatch_cap, c->d_counters);
+    c->launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t spk_launch_sort_finish(spk_ctx* c) {
+    GridBuffers& g = c->grid[1 - c->gcur];
+    GridBuffers& prev = c->grid[c->gcur];
+    cudaStream_t s = c->stream;
+    const uint32_t nab = g.nab_host, n = (uint32_t)c->n;
+    if (nab) {
+        build_tables_kernel<<<(nab * 8 + 255) / 256, 256, 0, s>>>(g, prev, nab);
+        c->launches += 1;
+    }
+    if (n) {
+        scatter_perm_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->slot_of, c->rank_of, n, g.vals, g.blk_first, g.cap_blocks, c->perm);
+        c->launches += 1;
+    }
+    return cudaGetLastError();
+}

@@ -1,0 +1,183 @@
+"""Host-side mirror of the reference's CUDA pipeline API over the C ABI (include/sparkl_abi.h).
+
+Names, argument meaning and error behaviour follow src/cuda/*.rs of the reference:
+  CudaParticleSet          cuda_particle_set.rs:12-177
+  CudaParticleModelSet     cuda_particle_model_set.rs:8-84
+  CudaColliderSet          cuda_collider_set.rs:13-131
+  CudaSparseGrid           cuda_sparse_grid.rs:26-144
+  SingleGpuMpmContext      cuda_mpm_pipeline.rs:177-194
+  CudaMpmPipeline.step     cuda_mpm_pipeline.rs:262-271
+The reference keeps particles, models, colliders and grid as separate Rust objects borrowed by a
+`SingleGpuMpmContext`; here one `spk_ctx` owns all device memory of a context and the classes below are views on it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from ._lib import error_string, lib
+from .engine import Engine, _ptr
+
+
+class SingleGpuMpmContext(Engine):
+    """One CUDA context: device, 2 streams, particle set, model set, collider set, sparse grid, dt accumulator."""
+
+    def __init__(self, cell_width: float, device: int = 0, block_capacity: int = 1024):
+        l = lib()
+        h = C.c_void_p()
+        rc = l.spk_ctx_create(device, cell_width, block_capacity, C.byref(h))
+        if rc:
+            raise abi.SparklError(rc, "spk_ctx_create: " + error_string(rc))
+        super().__init__(l, "spk_", h, error_string)
+        self.cell_width, self.device = cell_width, device
+        self.particles = CudaParticleSet(self)
+        self.models = CudaParticleModelSet(self)
+        self.colliders = CudaColliderSet(self)
+        self.grid = CudaSparseGrid(self)
+
+    def close(self):
+        if self._h:
+            self._lib.spk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._call("ctx_synchronize")
+
+    def append(self, pc: abi.ParticleComponents):
+        arrs = [np.ascontiguousarray(a) for a in (pc.status, pc.position, pc.velocity, pc.volume, pc.phase, pc.data)]
+        n = len(arrs[0])
+        if any(len(a) != n for a in arrs):
+            raise abi.SparklError(abi.EINVAL, "All attribute buffer must have the same length.")
+        self._call("particles_append", *[_ptr(a) for a in arrs], n)
+
+    def remove_range(self, begin: int, end: int):
+        self._call("particles_remove_range", begin, end)
+
+    def step(self, params: abi.SolverParameters, gravity, timings: bool = True):
+        return CudaMpmPipeline().step(params, gravity, [self], timings)
+
+
+class CudaParticleSet:
+    def __init__(self, ctx: SingleGpuMpmContext):
+        self._ctx = ctx
+
+    @classmethod
+    def from_particles(cls, ctx, status, position, velocity, volume, phase, data=None):
+        pc = abi.ParticleComponents(0)
+        pc.status, pc.position, pc.velocity, pc.volume, pc.phase = status, position, velocity, volume, phase
+        pc.data = data if data is not None else _default_data(len(status))
+        ctx.upload(pc)
+        return ctx.particles
+
+    def len(self):
+        return len(self._ctx)
+
+    __len__ = len
+
+    def is_empty(self):
+        return len(self._ctx) == 0
+
+    def read_positions(self):
+        return self._ctx.read(abi.ATTR_POSITION)
+
+    def read_velocities(self):
+        return self._ctx.read(abi.ATTR_VELOCITY)
+
+    def read_statuses(self):
+        return self._ctx.read(abi.ATTR_STATUS)
+
+    def read_volumes(self):
+        return self._ctx.read(abi.ATTR_VOLUME)
+
+    def read_phase(self):
+        return self._ctx.read(abi.ATTR_PHASE)
+
+    def read_sorted_particle_ids(self):
+        return self._ctx.read(abi.ATTR_SORTED_IDS)
+
+    def append(self, pc):
+        self._ctx.append(pc)
+
+    def remove_range(self, begin, end):
+        self._ctx.remove_range(begin, end)
+
+
+def _default_data(n):
+    d = np.zeros(n, abi.DATA)
+    d["nacc_alpha"], d["plastic_hardening"], d["elastic_hardening"] = -0.01, 1.0, 1.0
+    return d
+
+
+class CudaParticleModelSet:
+    def __init__(self, ctx):
+        self._ctx, self.models = ctx, []
+
+    def from_models(self, models):
+        self.models = list(models)
+        self._ctx.models_upload(self.models)
+        return self
+
+    def ensure_models_are_uploaded(self):
+        """cuda_particle_model_set.rs:61-84: re-upload if the host models were edited."""
+        self._ctx.models_upload(self.models)
+
+
+class CudaColliderSet:
+    def __init__(self, ctx):
+        self._ctx, self.colliders = ctx, []
+
+    def from_collider_set(self, colliders):
+        self.colliders = list(colliders)
+        self._ctx.colliders_upload(self.colliders)
+        return self
+
+
+class CudaSparseGrid:
+    def __init__(self, ctx):
+        self._ctx = ctx
+
+    def cell_width(self):
+        return self._ctx.cell_width
+
+    def curr_headers(self):
+        return self._ctx.grid_headers(0)
+
+    def curr_nodes(self):
+        return self._ctx.grid_nodes(0)
+
+
+class CudaMpmPipeline:
+    """`CudaMpmPipeline::step`: advances the contexts by params.dt and returns the simulated time."""
+
+    def __init__(self):
+        self.step_id = 0
+
+    def step(self, params: abi.SolverParameters, gravity, contexts, timings: bool = True):
+        if len(contexts) != 1:
+            raise abi.SparklError(abi.EUNSUPPORTED, "one process per GPU: use sparkl_b200.distributed for multi-GPU runs")
+        ctx = contexts[0]
+        g = (C.c_float * 3)(*gravity)
+        t = abi.StepTimings()
+        sim = C.c_float()
+        arr = (C.c_void_p * 1)(ctx._h)
+        rc = ctx._lib.spk_step(arr, 1, C.byref(params), C.byref(g), C.byref(t) if timings else None, C.byref(sim))
+        if rc:
+            raise abi.SparklError(rc, "spk_step: " + error_string(rc))
+        self.step_id += t.num_substeps
+        return sim.value, t
+
+
+def context_from_scene(scene, device: int = 0) -> SingleGpuMpmContext:
+    ctx = SingleGpuMpmContext(scene.cell_width, device)
+    ctx.models.from_models(scene.models)
+    ctx.colliders.from_collider_set(scene.colliders)
+    ctx.upload(scene.particles)
+    return ctx

@@ -1,0 +1,164 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars: integer structures (active blocks, per-block particle sets, dispatch table, status flags,
+projection tags) EXACT on canonical form; floating-point state within RTOL of the field scale.  RTOL is stated per
+test: one substep 2e-5, growing with the number of substeps because f32 round-off and summation order (atomics in the
+product and in the reference, fixed order in the oracle) diverge chaotically."""
+import numpy as np
+import pytest
+
+from sparkl_b200 import abi, scenes
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+RTOL_1 = 2e-5
+
+
+def _engines(scene, oracle):
+    from sparkl_b200.pipeline import context_from_scene
+    g = context_from_scene(scene)
+    o = oracle.OracleEngine(scene.cell_width)
+    o.models_upload(scene.models)
+    o.colliders_upload(scene.colliders)
+    o.upload(scene.particles)
+    return g, o
+
+
+def _substep_both(g, o, scene, remaining, check=True, rtol=RTOL_1, tag=""):
+    from oracle import binding as ob
+    tol = util.scene_tol(scene, rtol)
+    p = scene.params
+    min_dt = float(np.float32(p.dt) / np.float32(p.max_num_substeps))
+    max_dt = float(min(np.float32(remaining), np.float32(p.max_substep_dt)))
+    ig, io = g.stage_sort(), o.stage_sort()
+    if check:
+        vg, pg, mg, _, _ = util.canonical_sort_state(g)
+        vo, po, mo, _, _ = util.canonical_sort_state(o)
+        assert ig.num_active_blocks == io.num_active_blocks, tag
+        assert np.array_equal(vg, vo), f"{tag}: active block sets differ"
+        assert mg == mo, f"{tag}: dispatch multisets differ"
+        for k in po:
+            assert np.array_equal(pg[k], po[k]), f"{tag}: particle set of block {k:#x} differs"
+    g.stage_reset_grid(); o.stage_reset_grid()
+    dtg, dto = g.stage_estimate_dt(min_dt, max_dt), o.stage_estimate_dt(min_dt, max_dt)
+    if check:
+        assert abs(g.dt_acc() - o.dt_acc()) <= max(2, int(4e-7 * o.dt_acc())), f"{tag}: dt accumulators differ {g.dt_acc()} vs {o.dt_acc()}"
+    # drive both with the ORACLE's dt so that one substep is compared on identical inputs
+    g.set_dt_acc(o.dt_acc())
+    dt = dto
+    g.stage_g2p2g(dt); o.stage_g2p2g(dt)
+    if check:
+        util.assert_particles_close(g.read_all(), o.read_all(), scene.cell_width, tol, tag + " after g2p2g")
+        kg, ng = util.nodes_by_key(g, 1)
+        ko, no = util.nodes_by_key(o, 1)
+        assert np.array_equal(kg, ko)
+        util.assert_nodes_close(ng, no, tol, tag + " next grid after g2p2g", scene, ko, ob)
+    g.stage_grid_update(dt, scene.gravity); o.stage_grid_update(dt, scene.gravity)
+    if check:
+        kg, ng = util.nodes_by_key(g, 0)
+        ko, no = util.nodes_by_key(o, 0)
+        assert np.array_equal(kg, ko)
+        util.assert_nodes_close(ng, no, tol, tag + " grid after grid_update", scene, ko, ob)
+    return dt
+
+
+def _run_frames(g, o, scene, nsub, rtol_of_step):
+    """lock-step substeps with per-substep comparison at a tolerance growing with the step index"""
+    g.frame_begin(scene.params); o.frame_begin(scene.params)
+    remaining = float(np.float32(scene.params.dt))
+    for s in range(nsub):
+        dt = _substep_both(g, o, scene, remaining, rtol=rtol_of_step(s), tag=f"substep {s}")
+        remaining = float(np.float32(remaining) - np.float32(dt))
+        if remaining <= 1e-11:
+            g.frame_begin(scene.params); o.frame_begin(scene.params)
+            remaining = float(np.float32(scene.params.dt))
+
+
+def test_sand_first_substeps(oracle):
+    sc = scenes.sand3(16, 8, 8)
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 3, lambda s: RTOL_1 * (1 + 2 * s))
+
+
+def test_sand_jittered_20_substeps(oracle):
+    sc = scenes.jitter(scenes.sand3(12, 6, 10), 0.02, seed=7)
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 20, lambda s: RTOL_1 * (1 + 3 * s))
+
+
+def test_fluid_dam_break(oracle):
+    sc = scenes.fluids3(16, 10, 10)
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 8, lambda s: 5e-5 * (1 + 3 * s))
+
+
+def test_neo_hookean_block(oracle):
+    sc = scenes.neo_hookean_block(12, 12, 8)
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 10, lambda s: RTOL_1 * (1 + 3 * s))
+
+
+def test_cube_through_sand_kinematic(oracle):
+    sc = scenes.cube_through_sand3(12, 6, 6, 4)
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 10, lambda s: RTOL_1 * (1 + 3 * s))
+
+
+def test_full_step_matches_oracle(oracle):
+    """spk_step (whole frame, adaptive substeps) against orc_step: same substep count, state within tolerance."""
+    sc = scenes.jitter(scenes.sand3(10, 6, 6), 0.01, seed=3)
+    g, o = _engines(sc, oracle)
+    for frame in range(2):
+        sg, tg = g.step(sc.params, sc.gravity)
+        so, to = o.step(sc.params, sc.gravity)
+        assert tg.num_substeps == to.num_substeps
+        assert abs(sg - so) <= 1e-6
+        assert tg.g2p2g_launches == tg.num_substeps and tg.kernel_launches >= 8 * tg.num_substeps
+        util.assert_particles_close(g.read_all(), o.read_all(), sc.cell_width, util.scene_tol(sc, 1e-4 * (frame + 1)), f"frame {frame}")
+
+
+def test_empty_and_single_particle(oracle):
+    sc = scenes.sand3(1, 1, 1)
+    from sparkl_b200.pipeline import SingleGpuMpmContext
+    g = SingleGpuMpmContext(sc.cell_width)
+    g.models.from_models(sc.models)
+    g.upload(abi.ParticleComponents(0))
+    sim, t = g.step(sc.params, sc.gravity)
+    assert sim == pytest.approx(sc.params.dt) and t.num_substeps == 0
+    g2, o = _engines(sc, oracle)
+    _run_frames(g2, o, sc, 4, lambda s: RTOL_1 * (1 + 2 * s))
+
+
+def test_ragged_blocks_and_chunk_boundaries(oracle):
+    """blocks holding 1 .. >512 particles (several g2p2g dispatch entries per block, partial last chunk)"""
+    rng = np.random.Generator(np.random.PCG64(11))
+    h = 0.2
+    pts = [rng.uniform(2.5, 2.5 + 4 * h, (1500, 3)), rng.uniform(6.0, 6.0 + 12 * h, (700, 3)), np.array([[9.05, 9.05, 9.05]])]
+    pts = np.concatenate(pts).astype(np.float32)
+    sc = scenes.sand3(1, 1, 1)
+    sc.particles = abi.particles_from_positions(pts, 0, 0.05, 2700.0)
+    sc.particles.status["model_index"][::2] = 1
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 3, lambda s: 5e-5 * (1 + 3 * s))
+
+
+def test_append_remove_read_roundtrip(oracle):
+    sc = scenes.jitter(scenes.sand3(6, 4, 4), 0.01, seed=5)
+    from sparkl_b200.pipeline import context_from_scene
+    g = context_from_scene(sc)
+    n = len(sc.particles)
+    back = g.read_all()
+    for name in ("position", "velocity", "volume", "status", "phase", "data"):
+        assert np.array_equal(getattr(back, name), getattr(sc.particles, name)), name
+    g.step(sc.params, sc.gravity)
+    extra = sc.particles.take(np.arange(10))
+    g.append(extra)
+    assert len(g) == n + 10
+    st = g.read(abi.ATTR_POSITION)
+    assert np.array_equal(st[n:], extra.position)
+    g.remove_range(3, 8)
+    assert len(g) == n + 5
+    assert np.array_equal(g.read(abi.ATTR_POSITION)[n - 5:], extra.position)
+    g.step(sc.params, sc.gravity)
+    assert np.isfinite(g.read(abi.ATTR_POSITION)["point"]).all()

@@ -1,0 +1,141 @@
+"""Canonical comparison forms shared by the parity tests: the reference assigns block ids and
+in-block particle order by atomics races, so integer structures are compared on canonical forms only."""
+import numpy as np
+
+from sparkl_b200 import abi
+
+
+def canonical_sort_state(engine):
+    """(sorted virtual ids, {vid: sorted particle ids}, dispatch multiset) of the NEXT grid after stage_sort."""
+    hdr = engine.grid_headers(1)
+    ids = engine.read(abi.ATTR_SORTED_IDS)
+    order = np.argsort(hdr["virtual_id"], kind="stable")
+    vids = hdr["virtual_id"][order]
+    per_block = {}
+    for h in hdr:
+        s = ids[h["first_particle"]: h["first_particle"] + h["num_particles"]]
+        per_block[int(h["virtual_id"])] = np.sort(s)
+    ndisp = int(sum((int(h["num_particles"]) + 127) // 128 for h in hdr))
+    disp = engine.dispatch(ndisp)
+    multiset = sorted((int(hdr["virtual_id"][d["active_block_id"]]), int(d["first_particle"]) - int(hdr["first_particle"][d["active_block_id"]])) for d in disp)
+    return vids, per_block, multiset, hdr, ids
+
+
+def nodes_by_key(engine, which):
+    """dict-free canonical node table: (sorted vids, nodes[nblocks, 64] reordered by vid)."""
+    hdr = engine.grid_headers(which)
+    nodes = engine.grid_nodes(which)
+    order = np.argsort(hdr["virtual_id"], kind="stable")
+    return hdr["virtual_id"][order], nodes[order]
+
+
+def rel_err(a, b, floor=0.0, atol=0.0):
+    """max |a-b| minus an absolute allowance, relative to the scale of b"""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if not a.size:
+        return 0.0
+    scale = max(float(np.max(np.abs(b))), floor, 1e-30)
+    return max(float(np.max(np.abs(a - b))) - atol, 0.0) / scale
+
+
+class Tol:
+    """Tolerance classes of the parity tests (all relative to the field's scale over the scene):
+      base       well-conditioned state: positions (in units of h), F, Jp, masses, hardening variables
+      20 x base  velocity-like: particle velocities, node momenta / velocities (they carry the stress error below)
+      50 x base  energy / stress-like: psi_pos, psi momenta, log_vol_gain.  tau = 2 mu (F - R) F^T and
+                 psi = mu sum (sigma - 1)^2 subtract nearly equal numbers at small strain, so in f32 they carry an
+                 absolute error of ~1e-6 * modulus whatever the implementation (the oracle's SVD runs in double);
+                 `modulus` (max Young modulus of the scene) sets that absolute allowance.
+    """
+
+    def __init__(self, base, modulus=0.0):
+        self.base, self.modulus = base, modulus
+
+    @property
+    def energy_atol(self):
+        return 2e-6 * self.modulus
+
+
+def scene_tol(scene, base):
+    mod = 0.0
+    for m in scene.models:
+        c = m.constitutive_model
+        mod = max(mod, float(getattr(c, "lam", 0.0)) + 2 * float(getattr(c, "mu", 0.0)))
+    return Tol(base, mod)
+
+
+def assert_particles_close(pa: abi.ParticleComponents, pb: abi.ParticleComponents, h, tol, what=""):
+    if not isinstance(tol, Tol):
+        tol = Tol(tol)
+    assert len(pa) == len(pb)
+    b = tol.base
+    checks = {  # name: (error, allowed)
+        "pos": (float(np.max(np.abs(pa.position["point"].astype(np.float64) - pb.position["point"]))) / max(h, 1e-30) if len(pa) else 0.0, b),
+        "vel": (rel_err(pa.velocity["vector"], pb.velocity["vector"], floor=1e-2), 20 * b),
+        "F": (rel_err(pa.volume["deformation_gradient"], pb.volume["deformation_gradient"], floor=1.0), b),
+        "Jp": (rel_err(pa.volume["plastic_deformation_gradient_det"], pb.volume["plastic_deformation_gradient_det"], floor=1.0), b),
+        "psi_pos": (rel_err(pa.phase["psi_pos"], pb.phase["psi_pos"], floor=1e-3, atol=tol.energy_atol), 50 * b),
+        "phase": (rel_err(pa.phase["phase"], pb.phase["phase"], floor=1.0), b),
+        "plastic_hardening": (rel_err(pa.data["plastic_hardening"], pb.data["plastic_hardening"], floor=1.0), b),
+        "elastic_hardening": (rel_err(pa.data["elastic_hardening"], pb.data["elastic_hardening"], floor=1.0), b),
+        "log_vol_gain": (rel_err(pa.data["log_vol_gain"], pb.data["log_vol_gain"], floor=5e-2), 50 * b),
+        "nacc_alpha": (rel_err(pa.data["nacc_alpha"], pb.data["nacc_alpha"], floor=1e-2), 50 * b),
+    }
+    bad = {k: v for k, v in checks.items() if not (v[0] <= v[1])}
+    assert not bad, f"{what}: fields out of tolerance (error, allowed): {bad} (all: {checks})"
+    for f in ("failed", "is_static", "kinematic_vel_enabled", "model_index"):
+        assert np.array_equal(pa.status[f], pb.status[f]), f"{what}: status.{f} differs"
+    assert np.array_equal(pa.status["kinematic_vel"], pb.status["kinematic_vel"])
+    assert np.array_equal(pa.volume["mass"], pb.volume["mass"]) and np.array_equal(pa.volume["volume0"], pb.volume["volume0"])
+    assert np.array_equal(pa.volume["radius0"], pb.volume["radius0"])
+    return {k: v[0] for k, v in checks.items()}
+
+
+def node_positions(vids, h):
+    """world position of every node of the blocks `vids` (grid_update.rs:34-38): [nblocks, 64, 3] float32"""
+    m = (1 << 21) - 1
+    org = 1 << 20
+    bx = (vids & m).astype(np.int64) - org
+    by = ((vids >> 21) & m).astype(np.int64) - org
+    bz = ((vids >> 42) & m).astype(np.int64) - org
+    cell = np.arange(64)
+    out = np.empty((len(vids), 64, 3), np.float32)
+    out[..., 0] = (bx[:, None] * 4 + (cell & 3)[None, :]).astype(np.float32) * np.float32(h)
+    out[..., 1] = (by[:, None] * 4 + ((cell >> 2) & 3)[None, :]).astype(np.float32) * np.float32(h)
+    out[..., 2] = (bz[:, None] * 4 + (cell >> 4)[None, :]).astype(np.float32) * np.float32(h)
+    return out
+
+
+def assert_nodes_close(na, nb, tol, what="", scene=None, vids=None, oracle=None):
+    """grid nodes re-indexed by (virtual id, cell).  Projection tags must be equal; the collider index may differ only
+    where two colliders are equidistant from the node up to round-off (the reference resolves such ties with a strict
+    `<` on f32 distances, grid_update.rs:121-124, which no re-implementation can reproduce bit for bit)."""
+    if not isinstance(tol, Tol):
+        tol = Tol(tol)
+    assert na.shape == nb.shape
+    b = tol.base
+    mscale = float(np.max(np.abs(nb["mass"]))) if nb.size else 0.0
+    checks = {
+        "mass": (rel_err(na["mass"], nb["mass"]), b),
+        "momentum_velocity": (rel_err(na["momentum_velocity"], nb["momentum_velocity"], floor=1e-2), 50 * b),
+        "psi_momentum_velocity": (rel_err(na["psi_momentum_velocity"], nb["psi_momentum_velocity"], floor=1e-3, atol=tol.energy_atol * max(mscale, 1.0)), 50 * b),
+        "psi_mass": (rel_err(na["psi_mass"], nb["psi_mass"]), b),
+        "prev_mass": (rel_err(na["prev_mass"], nb["prev_mass"]), b),
+        "collision_normal": (rel_err(na["collision_normal"], nb["collision_normal"], floor=1.0), max(b, 1e-5)),
+    }
+    bad = {k: v for k, v in checks.items() if not (v[0] <= v[1])}
+    assert not bad, f"{what}: node fields out of tolerance (error, allowed): {bad} (all: {checks})"
+    assert np.array_equal(na["projection_status_tag"], nb["projection_status_tag"]), f"{what}: projection tags differ"
+    same = na["projection_status_payload"] == nb["projection_status_payload"]
+    dir_err = np.abs(na["projection_scaled_dir"].astype(np.float64) - nb["projection_scaled_dir"]).max(axis=-1) if na.size else np.zeros(0)
+    assert (dir_err[same] <= 1e-5 * max(1.0, float(np.abs(nb["projection_scaled_dir"]).max()))).all(), f"{what}: projection_scaled_dir differs"
+    if not same.all():
+        assert scene is not None and oracle is not None and vids is not None, f"{what}: projection payload differs"
+        pos = node_positions(vids, scene.cell_width)[~same]
+        ia, ib = na["projection_status_payload"][~same], nb["projection_status_payload"][~same]
+        for p, i, j in zip(pos, ia, ib):
+            pi, _ = oracle.cuboid_project(scene.colliders[int(i)], p)
+            pj, _ = oracle.cuboid_project(scene.colliders[int(j)], p)
+            di, dj = np.linalg.norm(pi - p), np.linalg.norm(pj - p)
+            assert abs(di - dj) <= 1e-5 * scene.cell_width, f"{what}: collider index differs at a non-tie node {p}: {i}@{di} vs {j}@{dj}"
+    return {k: v[0] for k, v in checks.items()}
