@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py — particle-substeps/s of the 3D sand workload (BASELINE.json metric) + G2P2G HBM roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+ours:      one "step" = one MPM substep (sort -> reset -> dt -> fused G2P2G -> grid update) of the sand3 scene
+           (examples3d/sand3.rs scaled to 4M particles per GPU: BASELINE.json configs[2]) through the C ABI
+           (spk_step with stop_after_one_substep).  N > 1: x-slabs of 4M particles per rank with halo exchange (weak).
+reference: the CPU arm — the oracle port of the reference algorithm (oracle/mpm_oracle.cpp, OpenMP, all host cores) on
+           a bounded sample of the same scene; the reference's Rust CPU path cannot be built here (no cargo/rustc).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_substeps_per_sec"
+UNIT = "particle-substeps/s"
+# algorithmic bytes per particle-substep of the fused G2P2G kernel, sand (SURVEY.md §8d / DESIGN.md §5):
+# particle records R112 + W108 + ParticleData R16+W16 = 252, plus grid (72 R + 24 W) * 64 / 512 = 12
+A_G2P2G_SAND = 264.0
+FULL = (200, 100, 100)       # per-GPU lattice (x2 stacked) = 4,000,000 particles
+CPU_SAMPLE = (50, 25, 25)    # bounded CPU sample of the same scene = 62,500 particles
+
+
+def _peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def build_scene(rank, world, dims):
+    from sparkl_b200 import scenes
+    ni, nj, nk = dims
+    ext = float(np.float32(0.2) / np.float32(4.0)) * 2.0
+    # slabs side by side along x; one floor + outer walls for the whole domain, identical on every rank
+    sc = scenes.sand3(ni, nj, nk, x_offset=rank * ni * ext, with_colliders=False)
+    sc.colliders = scenes.box_colliders((-4.0, 2.0, -4.0), (world * ni * ext + 4.0, 2.0 + 2 * nj * ext + 8.0, nk * ext + 4.0))
+    return sc
+
+
+def cpu_baseline(steps, warmup, dims=CPU_SAMPLE):
+    """the oracle port timed on the host cores (all threads) on a bounded sample of the workload"""
+    from oracle import binding as ob
+    from sparkl_b200 import abi
+    threads = ob.set_threads(0)
+    sc = build_scene(0, 1, dims)
+    e = ob.OracleEngine(sc.cell_width)
+    e.models_upload(sc.models); e.colliders_upload(sc.colliders); e.upload(sc.particles)
+    p = abi.SolverParameters(stop_after_one_substep=1)
+    for _ in range(warmup):
+        e.step(p, sc.gravity)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        _, t = e.step(p, sc.gravity)
+        n += t.num_substeps
+    dt = time.perf_counter() - t0
+    return {"value": sc.num_particles * n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"sand3 lattice {dims[0]}x{dims[1]}x{dims[2]} x2 = {sc.num_particles} particles, {n} substeps, oracle/mpm_oracle.cpp (OpenMP)"}, dt / max(n, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, ms = cpu_baseline(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "sand3 (examples3d/sand3.rs) Drucker-Prager sand on corotated block, CPU arm on a bounded sample", "sample": base["sample"]},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def pinned_like(arr):
+    import torch
+    t = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
+    out = t.numpy().view(arr.dtype).reshape(arr.shape)
+    out[...] = arr
+    return out, t
+
+
+def run_ours(args):
+    import torch
+    from sparkl_b200 import abi
+    from sparkl_b200.pipeline import context_from_scene
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims = tuple(args.dims) if args.dims else FULL
+    sc = build_scene(rank, world, dims)
+    npart = sc.num_particles
+    ctx = context_from_scene(sc, device=local)
+    stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=torch.device("cuda", local))
+    params = abi.SolverParameters(stop_after_one_substep=1)
+    pipe = None
+    if world > 1:
+        from sparkl_b200.distributed import DistributedMpmPipeline
+        pipe = DistributedMpmPipeline(ctx, dist, torch.device("cuda", local))
+
+    def one_substep():
+        if pipe is None:
+            return ctx.step(params, sc.gravity)[1]
+        pipe.step(params, sc.gravity)
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_substep()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g2p2g_ms = launches = 0.0
+    stage_ms = np.zeros(5)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        t = one_substep()
+        if t is not None:
+            g2p2g_ms += t.g2p2g_ms
+            launches += t.kernel_launches
+            stage_ms += [t.grid_resize_and_sort_ms, t.reset_grid_ms, t.estimate_timestep_ms, t.g2p2g_ms, t.grid_update_ms]
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.finish() if sampler else None
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = npart * world * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers: upload (pinned H2D) -> one frame -> read back pos/vel/phase
+    e2e = None
+    if world == 1:
+        host = sc.particles
+        pins = [pinned_like(a) for a in (host.status, host.position, host.velocity, host.volume, host.phase, host.data)]
+        pc = abi.ParticleComponents(0)
+        pc.status, pc.position, pc.velocity, pc.volume, pc.phase, pc.data = [p[0] for p in pins]
+        frame = abi.SolverParameters()
+        h2d = sum(p[0].nbytes for p in pins)
+        d2h = npart * (12 + 12 + 8)
+        subs = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_frames):
+            ctx.upload(pc)
+            _, t = ctx.step(frame, sc.gravity, timings=False)
+            ctx.read(abi.ATTR_POSITION); ctx.read(abi.ATTR_VELOCITY); ctx.read(abi.ATTR_PHASE)
+            subs += 1
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        # substeps per frame: dt = 1/60 at the CFL step of this scene
+        _, t = ctx.step(frame, sc.gravity)
+        per_frame = t.num_substeps
+        e2e = {"value": npart * per_frame * args.e2e_frames / wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "step": f"spk_particles_upload (pinned host) + spk_step(dt=1/60: {per_frame} substeps) + spk_particles_read(pos, vel, phase)",
+               "frames": args.e2e_frames, "ms_per_frame": wall * 1e3 / args.e2e_frames}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = _peaks()
+    roof = None
+    if world == 1 and g2p2g_ms > 0:
+        achieved = A_G2P2G_SAND * npart * args.steps / (g2p2g_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "g2p2g_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": _ncu_traffic(), "peak_source": peak_src, "bytes_per_particle_substep": A_G2P2G_SAND,
+                "kernel_ms_per_launch": g2p2g_ms / args.steps,
+                "stage_ms_per_substep": dict(zip(["sort", "reset_grid", "estimate_dt", "g2p2g", "grid_update"], (stage_ms / args.steps).round(4).tolist()))}
+    base = None
+    if world == 1 and not args.no_cpu_baseline:
+        base, _ = cpu_baseline(2, 1)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"sand3 (examples3d/sand3.rs scaled): 2 stacked lattices {dims[0]}x{dims[1]}x{dims[2]} per GPU = {npart} particles/GPU, h=0.2, "
+                                   "Drucker-Prager sand over corotated block, cuboid floor+walls", "particles_per_gpu": npart,
+                       "parallelism": f"x-slabs x{world}, halo exchange" if world > 1 else "single GPU", "l2": "inputs larger than L2 (particle state ~0.8 GB per GPU)"},
+            "clocks": clocks, "gpu_launches": int(launches) if launches else None, "e2e": e2e, "roofline": roof, "cpu_baseline": base}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _ncu_traffic():
+    """dram bytes per g2p2g launch from the committed ncu summary of the same command (profiles/), if present"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "g2p2g_ncu_summary.json")))
+        return float(d["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dims", type=int, nargs=3, default=None, help="per-GPU lattice (default 200 100 100)")
+    ap.add_argument("--e2e-frames", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -234,6 +234,9 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
 int spk_ctx_destroy(spk_ctx* ctx);
 int spk_ctx_cell_width(const spk_ctx* ctx, float* out);          /* CudaSparseGrid::cell_width, cuda_sparse_grid.rs:92 */
 int spk_ctx_synchronize(spk_ctx* ctx);
+/* the context's main stream (`SingleGpuMpmContext::stream`, cuda_mpm_pipeline.rs:179) as a cudaStream_t, so hosts can
+ * record their own events / order their own copies against the pipeline */
+int spk_ctx_stream(spk_ctx* ctx, void** cuda_stream_out);
 
 /* CudaParticleSet::from_particles + SharedCudaVec<ParticleData>::from_slice (cuda_particle_set.rs:32-71,
  * testbed_plugin.rs:208-217).  Replaces the whole set.  `data` may be NULL (ParticleData::default()). */

@@ -34,6 +34,13 @@ def lib():
         _LIB.orc_step.argtypes = [C.c_void_p, C.POINTER(abi.SolverParameters), C.POINTER(C.c_float * 3),
                                   C.POINTER(abi.StepTimings), C.POINTER(C.c_float)]
         _LIB.orc_step.restype = C.c_int
+        vp = C.c_void_p
+        _LIB.orc_halo_active_keys.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        _LIB.orc_halo_tag.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        _LIB.orc_halo_pack.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        _LIB.orc_halo_merge.argtypes = [vp, vp, vp, C.c_uint32]
+        for nme in ("orc_halo_active_keys", "orc_halo_tag", "orc_halo_pack", "orc_halo_merge"):
+            getattr(_LIB, nme).restype = C.c_int
         _LIB.orc_set_threads.argtypes = [C.c_int]
         _LIB.orc_set_threads.restype = C.c_int
         _LIB.orc_block_key_of_point.argtypes = [C.c_void_p, C.c_float]
@@ -50,6 +57,7 @@ class OracleEngine(Engine):
         l = lib()
         super().__init__(l, "orc_", C.c_void_p(l.orc_create(cell_width)))
         self.cell_width = cell_width
+        self.device = -1
 
     def __del__(self):
         try:

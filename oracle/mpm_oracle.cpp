@@ -1151,6 +1151,63 @@ int orc_grid_read_dispatch(orc_ctx* c, SpkDispatchBlock2ActiveBlock* dst, uint32
     return SPK_OK;
 }
 
+// ---- halo exchange (multi-process path), same contract as spk_halo_* with HOST pointers; lets the world_size-2 gloo
+// tests drive sparkl_b200.distributed on CPU.  tag_halo_blocks / copy_halo_to_staging / merge_halo_blocks,
+// src_kernels/cuda/sort.rs:74-164.
+int orc_halo_active_keys(orc_ctx* c, uint64_t* keys_out, uint32_t capacity, uint32_t* count_out) {
+    Grid& g = c->next_grid();
+    *count_out = (uint32_t)g.headers.size();
+    if (g.headers.size() > capacity) return SPK_EINVAL;
+    for (size_t i = 0; i < g.headers.size(); ++i) keys_out[i] = g.headers[i].virtual_id;
+    return SPK_OK;
+}
+int orc_halo_tag(orc_ctx* c, const uint64_t* remote_keys, uint32_t n_remote, uint32_t* num_halo_out) {
+    Grid& g = c->next_grid();
+    uint32_t nh = 0;
+    for (uint32_t i = 0; i < n_remote; ++i) {
+        int b = g.find(remote_keys[i]);
+        if (b >= 0 && !(g.headers[b].halo_state & 1u)) { g.headers[b].halo_state |= 1u; ++nh; }
+    }
+    if (num_halo_out) *num_halo_out = nh;
+    return SPK_OK;
+}
+int orc_halo_pack(orc_ctx* c, uint64_t* keys_out, float* payload_out, uint32_t capacity, uint32_t* count_out) {
+    Grid& g = c->next_grid();
+    uint32_t k = 0;
+    for (size_t b = 0; b < g.headers.size(); ++b) {
+        if (!(g.headers[b].halo_state & 1u)) continue;
+        if (k >= capacity) return SPK_EINVAL;
+        keys_out[k] = g.headers[b].virtual_id;
+        float* dst = payload_out + (size_t)k * 384;
+        for (int cell = 0; cell < 64; ++cell) {
+            const SpkGpuGridNode& nd = g.nodes[b * 64 + cell];
+            dst[0 * 64 + cell] = nd.mass; dst[1 * 64 + cell] = nd.momentum_velocity[0]; dst[2 * 64 + cell] = nd.momentum_velocity[1];
+            dst[3 * 64 + cell] = nd.momentum_velocity[2]; dst[4 * 64 + cell] = nd.psi_momentum_velocity; dst[5 * 64 + cell] = nd.psi_mass;
+        }
+        ++k;
+    }
+    *count_out = k;
+    return SPK_OK;
+}
+int orc_halo_merge(orc_ctx* c, const uint64_t* keys, const float* payload, uint32_t n_blocks) {
+    Grid& g = c->next_grid();
+    for (uint32_t k = 0; k < n_blocks; ++k) {
+        int b = g.find(keys[k]);
+        if (b < 0) continue;
+        const float* src = payload + (size_t)k * 384;
+        for (int cell = 0; cell < 64; ++cell) {
+            SpkGpuGridNode& nd = g.nodes[(size_t)b * 64 + cell];
+            nd.mass = red_add(nd.mass, src[0 * 64 + cell]);
+            nd.momentum_velocity[0] = red_add(nd.momentum_velocity[0], src[1 * 64 + cell]);
+            nd.momentum_velocity[1] = red_add(nd.momentum_velocity[1], src[2 * 64 + cell]);
+            nd.momentum_velocity[2] = red_add(nd.momentum_velocity[2], src[3 * 64 + cell]);
+            nd.psi_momentum_velocity = red_add(nd.psi_momentum_velocity, src[4 * 64 + cell]);
+            nd.psi_mass = red_add(nd.psi_mass, src[5 * 64 + cell]);
+        }
+    }
+    return SPK_OK;
+}
+
 // ---- unit hooks used by tests/ (known-answer checks of the building blocks)
 void orc_svd3(const float* f_colmajor, float* u, float* s, float* vt) {
     M3 F; std::memcpy(F.m, f_colmajor, 36);

@@ -14,7 +14,7 @@ _LIB = None
 
 # every symbol include/sparkl_abi.h declares
 EXPORTS = [
-    "spk_abi_version", "spk_error_string", "spk_ctx_create", "spk_ctx_destroy", "spk_ctx_cell_width", "spk_ctx_synchronize",
+    "spk_abi_version", "spk_error_string", "spk_ctx_create", "spk_ctx_destroy", "spk_ctx_cell_width", "spk_ctx_synchronize", "spk_ctx_stream",
     "spk_particles_upload", "spk_particles_append", "spk_particles_remove_range", "spk_particles_len", "spk_particles_read",
     "spk_models_upload", "spk_colliders_upload", "spk_step", "spk_frame_begin", "spk_stage_sort", "spk_stage_reset_grid",
     "spk_stage_estimate_dt", "spk_dt_acc_get", "spk_dt_acc_set", "spk_stage_g2p2g", "spk_stage_grid_update",
@@ -37,6 +37,7 @@ def lib():
         l.spk_ctx_create.argtypes = [C.c_int, C.c_float, C.c_uint32, C.POINTER(vp)]
         l.spk_ctx_destroy.argtypes = [vp]
         l.spk_ctx_synchronize.argtypes = [vp]
+        l.spk_ctx_stream.argtypes = [vp, C.POINTER(vp)]
         l.spk_particles_append.argtypes = [vp] * 7 + [C.c_size_t]
         l.spk_particles_remove_range.argtypes = [vp, C.c_size_t, C.c_size_t]
         l.spk_step.argtypes = [C.POINTER(vp), C.c_size_t, C.POINTER(abi.SolverParameters), C.POINTER(C.c_float * 3),

@@ -318,6 +318,7 @@ int spk_ctx_destroy(spk_ctx* c) {
 }
 
 int spk_ctx_cell_width(const spk_ctx* c, float* out) { if (!c || !out) return SPK_EINVAL; *out = c->cell_width; return SPK_OK; }
+int spk_ctx_stream(spk_ctx* c, void** out) { if (!c || !out) return SPK_EINVAL; *out = (void*)c->stream; return SPK_OK; }
 int spk_ctx_synchronize(spk_ctx* c) { if (!c) return SPK_EINVAL; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return SPK_OK; }
 
 int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkParticlePosition* pos, const SpkParticleVelocity* vel,
@@ -527,8 +528,6 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
         c->sorted_valid = true;
         if (info) {
             info->num_active_blocks = hc.nab;
-            uint32_t nd = 0; // dispatch count in the reference's units (128 threads per dispatch block)
-            (void)nd;
             info->num_dispatch_blocks = hc.ndispatch;
             info->num_dispatch_halo_blocks = 0;
             info->hashmap_capacity = g.cap_hash;

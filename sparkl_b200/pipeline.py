@@ -51,6 +51,12 @@ class SingleGpuMpmContext(Engine):
     def synchronize(self):
         self._call("ctx_synchronize")
 
+    def cuda_stream(self) -> int:
+        """raw cudaStream_t of the context's main stream"""
+        out = C.c_void_p()
+        self._call("ctx_stream", C.byref(out))
+        return out.value or 0
+
     def append(self, pc: abi.ParticleComponents):
         arrs = [np.ascontiguousarray(a) for a in (pc.status, pc.position, pc.velocity, pc.volume, pc.phase, pc.data)]
         n = len(arrs[0])
