@@ -126,3 +126,62 @@ def cuboid_project(collider: abi.CuboidCollider, pt):
     inside = C.c_int()
     l.orc_cuboid_project(c.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.byref(inside))
     return out, bool(inside.value)
+
+
+# ------------------------------------------------------------------------------------------------ oracle-A
+_REF = None
+REF_CUBIN = os.path.join(_HERE, "_ref", "sparkl3d-kernels.cubin")
+REF_LIB = os.path.join(_HERE, "_ref", "libref_harness.so")
+
+
+def ref_available() -> bool:
+    """the reference's own GPU kernels (assembled from its shipped PTX by `make -C oracle ref`) + a CUDA driver"""
+    if not (os.path.exists(REF_CUBIN) and os.path.exists(REF_LIB)):
+        return False
+    try:
+        return bool(ref_lib().ref_available())
+    except OSError:
+        return False
+
+
+def ref_lib():
+    global _REF
+    if _REF is None:
+        _REF = C.CDLL(REF_LIB)
+        declare(_REF, "ref_")
+        vp = C.c_void_p
+        _REF.ref_available.restype = C.c_int
+        _REF.ref_create.argtypes = [C.c_int, C.c_float, C.c_char_p, C.POINTER(vp)]
+        _REF.ref_create.restype = C.c_int
+        _REF.ref_destroy.argtypes = [vp]
+        _REF.ref_step.argtypes = [vp, C.POINTER(abi.SolverParameters), C.POINTER(C.c_float * 3), C.POINTER(abi.StepTimings), C.POINTER(C.c_float)]
+        _REF.ref_step.restype = C.c_int
+    return _REF
+
+
+class RefEngine(Engine):
+    """The reference's unmodified GPU kernels driven by oracle/ref_harness.cpp (oracle-A)."""
+
+    def __init__(self, cell_width: float, device: int = 0):
+        l = ref_lib()
+        h = C.c_void_p()
+        rc = l.ref_create(device, cell_width, REF_CUBIN.encode(), C.byref(h))
+        if rc:
+            raise abi.SparklError(rc, "ref_create")
+        super().__init__(l, "ref_", h)
+        self.cell_width, self.device = cell_width, device
+
+    def __del__(self):
+        try:
+            self._lib.ref_destroy(self._h)
+        except Exception:
+            pass
+
+    def step(self, params: abi.SolverParameters, gravity):
+        g = (C.c_float * 3)(*gravity)
+        t = abi.StepTimings()
+        sim = C.c_float()
+        rc = self._lib.ref_step(self._h, C.byref(params), C.byref(g), C.byref(t), C.byref(sim))
+        if rc:
+            raise abi.SparklError(rc, "ref_step")
+        return sim.value, t

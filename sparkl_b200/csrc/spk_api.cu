@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -280,7 +281,9 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     c->device = device;
     c->cell_width = cell_width;
     c->sm_count = prop.multiProcessorCount;
-    c->chunk = 512;
+    c->chunk = 256; // == threads per g2p2g CTA (spk_g2p2g.cu)
+    c->g2p2g_mode = 1;
+    if (const char* m = getenv("SPK_G2P2G_MODE")) c->g2p2g_mode = atoi(m) ? 1 : 0; // A/B switch for profiling
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
@@ -335,7 +338,9 @@ int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkP
     // (the reference's own estimate, cuda_sparse_grid.rs:222-229), doubled for the shell of neighbour blocks
     const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (64 * 8 * 50)) * 4u, 2048u);
     GridBuffers& next = c->grid[1 - c->gcur];
+    GridBuffers& curr = c->grid[c->gcur];
     if (next.cap_hash < want) { CK(alloc_grid(c, next, want)); CK(ensure_slot_scratch(c, want)); }
+    if (curr.cap_hash < want && curr.nab_host == 0) CK(alloc_grid(c, curr, want)); // empty: nothing to preserve
     CK(ensure_dispatch(c));
     return upload_range(c, status, pos, vel, volume, phase, data, 0, n);
 }
@@ -516,7 +521,9 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
         const DeviceCounters& hc = *c->h_counters;
         // grow-and-retry until the load factor is <= 50 % (cuda_sparse_grid.rs:162-253)
         if (hc.overflow || hc.nab > g.cap_blocks) {
-            const uint64_t want = std::max<uint64_t>((uint64_t)g.cap_hash * 2, (uint64_t)next_pow2((uint64_t)hc.nab * 2));
+            // jump straight to the size the particle count suggests (the reference's estimate, cuda_sparse_grid.rs:222-233)
+            const uint64_t estimate = (uint64_t)next_pow2((uint64_t)c->n * 100 / (64 * 8 * 50)) * 4u;
+            const uint64_t want = std::max<uint64_t>({(uint64_t)g.cap_hash * 2, (uint64_t)next_pow2((uint64_t)hc.nab * 4), std::min<uint64_t>(estimate, 1ull << 26)});
             if (want > (1ull << 30)) return SPK_EOVERFLOW;
             CK(alloc_grid(c, g, (uint32_t)want));
             CK(ensure_slot_scratch(c, (uint32_t)want));

@@ -47,7 +47,10 @@ __device__ __forceinline__ uint32_t spk_hash(unsigned long long key, uint32_t ma
 __device__ __forceinline__ uint32_t spk_hash_insert(unsigned long long* keys, uint32_t cap, unsigned long long key) {
     const uint32_t mask = cap - 1;
     uint32_t slot = spk_hash(key, mask);
-    for (uint32_t probe = 0; probe < cap; ++probe) {
+    // a probe sequence this long only happens when the table is (nearly) full: report overflow, the host grows the
+    // table and re-runs the sort (cuda_sparse_grid.rs:162-253) instead of crawling through a saturated table
+    const uint32_t max_probes = cap < 512u ? cap : 512u;
+    for (uint32_t probe = 0; probe < max_probes; ++probe) {
         unsigned long long prev = keys[slot];
         if (prev == key) return slot;
         if (prev == SPK_EMPTY_KEY) {
@@ -71,7 +74,7 @@ __device__ __forceinline__ uint32_t spk_hash_find_slot(const unsigned long long*
     return SPK_NO_BLOCK;
 }
 __device__ __forceinline__ int32_t spk_hash_get(const GridBuffers& g, unsigned long long key) {
-    if (g.nab_host == 0 && g.cap_hash == 0) return -1;
+    if (g.cap_hash == 0) return -1;
     uint32_t slot = spk_hash_find_slot(g.keys, g.cap_hash, key);
     return slot == SPK_NO_BLOCK ? -1 : (int32_t)g.vals[slot];
 }

@@ -110,6 +110,7 @@ struct spk_ctx {
     uint32_t slot_cnt_cap;
     DispatchEntry* dispatch; uint32_t dispatch_cap;
     uint32_t chunk;       // particles per g2p2g dispatch entry
+    int g2p2g_mode;       // 0: per-particle shared atomics, 1: cell-binned register accumulation (default)
     // counters
     DeviceCounters* d_counters;
     DeviceCounters* h_counters; // pinned

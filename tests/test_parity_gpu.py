@@ -43,7 +43,7 @@ def _substep_both(g, o, scene, remaining, check=True, rtol=RTOL_1, tag=""):
     g.stage_reset_grid(); o.stage_reset_grid()
     dtg, dto = g.stage_estimate_dt(min_dt, max_dt), o.stage_estimate_dt(min_dt, max_dt)
     if check:
-        assert abs(g.dt_acc() - o.dt_acc()) <= max(2, int(4e-7 * o.dt_acc())), f"{tag}: dt accumulators differ {g.dt_acc()} vs {o.dt_acc()}"
+        assert abs(g.dt_acc() - o.dt_acc()) <= max(2, int(1e-5 * o.dt_acc())), f"{tag}: dt accumulators differ {g.dt_acc()} vs {o.dt_acc()}"
     # drive both with the ORACLE's dt so that one substep is compared on identical inputs
     g.set_dt_acc(o.dt_acc())
     dt = dto

@@ -115,10 +115,18 @@ def assert_nodes_close(na, nb, tol, what="", scene=None, vids=None, oracle=None)
     assert na.shape == nb.shape
     b = tol.base
     mscale = float(np.max(np.abs(nb["mass"]))) if nb.size else 0.0
+    # a node whose mass is within rounding of the f32 underflow threshold is flushed to zero by one implementation and
+    # not by the other (the reference flushes at every `red.add`): its velocity is 0 on one side and finite on the other,
+    # and it weighs < 1e-20 of a regular node in every particle update.  Compare momenta / velocities on massive nodes.
+    massive = (nb["mass"] > 1e-20 * mscale) & (na["mass"] > 1e-20 * mscale)
+    mv_a = np.where(massive[..., None], na["momentum_velocity"], 0.0)
+    mv_b = np.where(massive[..., None], nb["momentum_velocity"], 0.0)
+    pv_a = np.where(massive, na["psi_momentum_velocity"], 0.0)
+    pv_b = np.where(massive, nb["psi_momentum_velocity"], 0.0)
     checks = {
         "mass": (rel_err(na["mass"], nb["mass"]), b),
-        "momentum_velocity": (rel_err(na["momentum_velocity"], nb["momentum_velocity"], floor=1e-2), 50 * b),
-        "psi_momentum_velocity": (rel_err(na["psi_momentum_velocity"], nb["psi_momentum_velocity"], floor=1e-3, atol=tol.energy_atol * max(mscale, 1.0)), 50 * b),
+        "momentum_velocity": (rel_err(mv_a, mv_b, floor=1e-2), 50 * b),
+        "psi_momentum_velocity": (rel_err(pv_a, pv_b, floor=1e-3, atol=tol.energy_atol * max(mscale, 1.0)), 50 * b),
         "psi_mass": (rel_err(na["psi_mass"], nb["psi_mass"]), b),
         "prev_mass": (rel_err(na["prev_mass"], nb["prev_mass"]), b),
         "collision_normal": (rel_err(na["collision_normal"], nb["collision_normal"], floor=1.0), max(b, 1e-5)),
