@@ -116,7 +116,9 @@ def neo_hookean_block(ni=40, nj=40, nk=20, x_offset=0.0, with_floor=True) -> Sce
     if with_floor:
         ext = 2.0 * float(r)
         cols = box_colliders((x_offset - 4.0, 2.0, -4.0), (x_offset + ni * ext + 4.0, 2.0 + nj * ext + 8.0, nk * ext + 4.0), walls=False)
-    return Scene("neo_hookean_block", h, pc, models, cols)
+    # The reference's Neo-Hookean dt bound is evaluated with cell_width and hardening swapped: it
+    # returns ~0.03 s here, far above the stable step (~0.5 h / c = 2.7e-3 s), so the scene caps the substep explicitly.
+    return Scene("neo_hookean_block", h, pc, models, cols, params=SolverParameters(max_substep_dt=1.5e-3))
 
 
 def jitter(scene: Scene, amplitude: float, seed: int = 42) -> Scene:

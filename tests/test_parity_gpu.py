@@ -33,13 +33,10 @@ def _substep_both(g, o, scene, remaining, check=True, rtol=RTOL_1, tag=""):
     max_dt = float(min(np.float32(remaining), np.float32(p.max_substep_dt)))
     ig, io = g.stage_sort(), o.stage_sort()
     if check:
-        vg, pg, mg, _, _ = util.canonical_sort_state(g)
-        vo, po, mo, _, _ = util.canonical_sort_state(o)
-        assert ig.num_active_blocks == io.num_active_blocks, tag
-        assert np.array_equal(vg, vo), f"{tag}: active block sets differ"
-        assert mg == mo, f"{tag}: dispatch multisets differ"
-        for k in po:
-            assert np.array_equal(pg[k], po[k]), f"{tag}: particle set of block {k:#x} differs"
+        boundary = util.boundary_particles(o.read(abi.ATTR_POSITION)["point"], scene.cell_width)
+        util.assert_membership_equal(util.canonical_sort_state(g), util.canonical_sort_state(o), boundary, tag)
+        if not boundary.any():
+            assert ig.num_active_blocks == io.num_active_blocks, tag
     g.stage_reset_grid(); o.stage_reset_grid()
     dtg, dto = g.stage_estimate_dt(min_dt, max_dt), o.stage_estimate_dt(min_dt, max_dt)
     if check:
@@ -50,16 +47,10 @@ def _substep_both(g, o, scene, remaining, check=True, rtol=RTOL_1, tag=""):
     g.stage_g2p2g(dt); o.stage_g2p2g(dt)
     if check:
         util.assert_particles_close(g.read_all(), o.read_all(), scene.cell_width, tol, tag + " after g2p2g")
-        kg, ng = util.nodes_by_key(g, 1)
-        ko, no = util.nodes_by_key(o, 1)
-        assert np.array_equal(kg, ko)
-        util.assert_nodes_close(ng, no, tol, tag + " next grid after g2p2g", scene, ko, ob)
+        util.assert_grids_close(g, o, 1, tol, tag + " next grid after g2p2g", scene, ob)
     g.stage_grid_update(dt, scene.gravity); o.stage_grid_update(dt, scene.gravity)
     if check:
-        kg, ng = util.nodes_by_key(g, 0)
-        ko, no = util.nodes_by_key(o, 0)
-        assert np.array_equal(kg, ko)
-        util.assert_nodes_close(ng, no, tol, tag + " grid after grid_update", scene, ko, ob)
+        util.assert_grids_close(g, o, 0, tol, tag + " grid after grid_update", scene, ob, velocity_field=True)
     return dt
 
 
@@ -94,7 +85,7 @@ def test_fluid_dam_break(oracle):
 
 
 def test_neo_hookean_block(oracle):
-    sc = scenes.neo_hookean_block(12, 12, 8)
+    sc = scenes.jitter(scenes.neo_hookean_block(12, 12, 8), 0.002, seed=4)
     g, o = _engines(sc, oracle)
     _run_frames(g, o, sc, 10, lambda s: RTOL_1 * (1 + 3 * s))
 
