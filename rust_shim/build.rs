@@ -1,0 +1,31 @@
+// build.rs a sparkl maintainer would add to crates/sparkl3d (feature "cuda-b200"): compiles the hand-written sm_100a
+// kernels + the C ABI with nvcc and links them, replacing crates-ptx/ (rustc_codegen_nvvm) and resources/*.ptx.
+// NOT compiled in this repository's environment (no cargo/rustc in the image); kept as the reference-side binding.
+use std::{env, path::PathBuf, process::Command};
+
+fn main() {
+    let csrc = PathBuf::from(env::var("SPARKL_B200_CSRC").unwrap_or_else(|_| "../sparkl_b200/csrc".into()));
+    let out = PathBuf::from(env::var("OUT_DIR").unwrap());
+    let sources = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu"];
+    let mut objects = vec![];
+    for s in sources {
+        let obj = out.join(s.replace(".cu", ".o"));
+        let status = Command::new("nvcc")
+            .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-c"])
+            .arg(csrc.join(s))
+            .arg("-o")
+            .arg(&obj)
+            .status()
+            .expect("nvcc not found");
+        assert!(status.success(), "nvcc failed on {s}");
+        objects.push(obj);
+        println!("cargo:rerun-if-changed={}", csrc.join(s).display());
+    }
+    let lib = out.join("libsparkl_b200.a");
+    assert!(Command::new("ar").arg("crs").arg(&lib).args(&objects).status().unwrap().success());
+    println!("cargo:rustc-link-search=native={}", out.display());
+    println!("cargo:rustc-link-lib=static=sparkl_b200");
+    println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
+    println!("cargo:rustc-link-lib=cudart");
+    println!("cargo:rustc-link-lib=stdc++");
+}

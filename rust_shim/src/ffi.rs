@@ -1,0 +1,91 @@
+//! `extern "C"` declarations of include/sparkl_abi.h and the drop-in replacement of `src/cuda/cuda_mpm_pipeline.rs`.
+//! The `#[repr(C)]` types are sparkl's own (`sparkl_core::dynamics::*`, `kernels::GpuParticleModel`, `GpuCollider`):
+//! the C ABI takes their byte images unchanged.  NOT compiled here (no Rust toolchain in the image).
+use crate::core::dynamics::solver::SolverParameters;
+use crate::core::prelude::{ParticleData, ParticlePhase, ParticlePosition, ParticleStatus, ParticleVelocity, ParticleVolume};
+use crate::kernels::{GpuCollider, GpuParticleModel};
+use crate::math::{Real, Vector};
+use std::os::raw::{c_int, c_void};
+
+#[repr(C)]
+pub struct SpkCtx { _private: [u8; 0] }
+
+#[repr(C)]
+#[derive(Default, Copy, Clone, Debug)]
+pub struct SpkStepTimings { // ≙ CudaDeviceTimings, cuda_mpm_pipeline.rs:56-85
+    pub num_substeps: u32, pub last_dt: f32, pub grid_resize_and_sort_ms: f32, pub reset_grid_ms: f32, pub estimate_timestep_ms: f32,
+    pub g2p2g_ms: f32, pub grid_update_ms: f32, pub total_ms: f32, pub num_active_blocks: u32, pub num_dispatch_blocks: u32,
+    pub g2p2g_launches: u32, pub kernel_launches: u32,
+}
+
+extern "C" {
+    pub fn spk_ctx_create(device: c_int, cell_width: f32, block_capacity: u32, out: *mut *mut SpkCtx) -> c_int;
+    pub fn spk_ctx_destroy(ctx: *mut SpkCtx) -> c_int;
+    pub fn spk_particles_upload(ctx: *mut SpkCtx, status: *const ParticleStatus, pos: *const ParticlePosition, vel: *const ParticleVelocity,
+                                volume: *const ParticleVolume, phase: *const ParticlePhase, data: *const ParticleData, n: usize) -> c_int;
+    pub fn spk_particles_append(ctx: *mut SpkCtx, status: *const ParticleStatus, pos: *const ParticlePosition, vel: *const ParticleVelocity,
+                                volume: *const ParticleVolume, phase: *const ParticlePhase, data: *const ParticleData, n: usize) -> c_int;
+    pub fn spk_particles_remove_range(ctx: *mut SpkCtx, begin: usize, end: usize) -> c_int;
+    pub fn spk_particles_len(ctx: *const SpkCtx, out: *mut usize) -> c_int;
+    pub fn spk_particles_read(ctx: *mut SpkCtx, which: c_int, dst: *mut c_void, n: usize) -> c_int;
+    pub fn spk_models_upload(ctx: *mut SpkCtx, models: *const GpuParticleModel, n: usize) -> c_int;
+    pub fn spk_colliders_upload(ctx: *mut SpkCtx, colliders: *const GpuCollider, n: usize) -> c_int;
+    pub fn spk_step(ctxs: *mut *mut SpkCtx, nctx: usize, params: *const SolverParameters, gravity: *const f32,
+                    timings: *mut SpkStepTimings, simulated_time_out: *mut f32) -> c_int;
+}
+
+/// `CudaResult`-shaped error: positive = cudaError_t, negative = SPK_E* (API misuse).
+#[derive(Debug, Copy, Clone, PartialEq, Eq)]
+pub struct SpkError(pub i32);
+fn ck(rc: c_int) -> Result<(), SpkError> { if rc == 0 { Ok(()) } else { Err(SpkError(rc)) } }
+
+/// Owns what `SingleGpuMpmContext` borrows in the reference: context, streams, particles, models, colliders, grid.
+pub struct B200MpmContext { raw: *mut SpkCtx }
+
+impl B200MpmContext {
+    pub fn new(device: i32, cell_width: Real) -> Result<Self, SpkError> {
+        let mut raw = std::ptr::null_mut();
+        ck(unsafe { spk_ctx_create(device, cell_width, 1024, &mut raw) })?; // CudaSparseGrid::new(cell_width)
+        Ok(Self { raw })
+    }
+    /// ≙ CudaParticleSet::from_particles + SharedCudaVec::<ParticleData>::from_slice (testbed_plugin.rs:208-217)
+    pub fn set_particles(&mut self, c: &crate::cuda::ParticleComponents) -> Result<(), SpkError> {
+        assert_eq!(c.status.len(), c.position.len(), "All attribute buffer must have the same length.");
+        ck(unsafe { spk_particles_upload(self.raw, c.status.as_ptr(), c.position.as_ptr(), c.velocity.as_ptr(), c.volume.as_ptr(),
+                                         c.phase.as_ptr(), c.data.as_ptr(), c.status.len()) })
+    }
+    /// ≙ CudaParticleModelSet::from_models / ensure_models_are_uploaded; the DevicePointer slots may be null.
+    pub fn set_models(&mut self, models: &[GpuParticleModel]) -> Result<(), SpkError> {
+        ck(unsafe { spk_models_upload(self.raw, models.as_ptr(), models.len()) })
+    }
+    /// ≙ CudaColliderSet::from_collider_set after the rapier → GpuCollider conversion (Cuboid shapes).
+    pub fn set_colliders(&mut self, colliders: &[GpuCollider]) -> Result<(), SpkError> {
+        ck(unsafe { spk_colliders_upload(self.raw, colliders.as_ptr(), colliders.len()) })
+    }
+    pub fn read_positions(&mut self) -> Result<Vec<ParticlePosition>, SpkError> {
+        let mut n = 0usize;
+        ck(unsafe { spk_particles_len(self.raw, &mut n) })?;
+        let mut out = vec![ParticlePosition::default(); n];
+        ck(unsafe { spk_particles_read(self.raw, 0, out.as_mut_ptr() as *mut c_void, n) })?;
+        Ok(out)
+    }
+}
+impl Drop for B200MpmContext { fn drop(&mut self) { unsafe { spk_ctx_destroy(self.raw); } } }
+
+/// Drop-in for `CudaMpmPipeline` (cuda_mpm_pipeline.rs:144-271).
+#[derive(Default)]
+pub struct B200MpmPipeline { pub step_id: u64 }
+
+impl B200MpmPipeline {
+    pub fn new() -> Self { Self { step_id: 0 } }
+    /// Same contract as `CudaMpmPipeline::step`: advances by `params.dt` with adaptive substeps, returns the simulated time.
+    pub fn step(&mut self, timings: Option<&mut SpkStepTimings>, params: &SolverParameters, gravity: &Vector<Real>,
+                contexts: &mut [B200MpmContext]) -> Result<f32, SpkError> {
+        let mut raw: Vec<*mut SpkCtx> = contexts.iter().map(|c| c.raw).collect();
+        let mut simulated = 0.0f32;
+        let t = timings.map(|t| t as *mut _).unwrap_or(std::ptr::null_mut());
+        ck(unsafe { spk_step(raw.as_mut_ptr(), raw.len(), params, gravity.as_ptr(), t, &mut simulated) })?;
+        if !t.is_null() { self.step_id += unsafe { (*t).num_substeps } as u64; }
+        Ok(simulated)
+    }
+}
