@@ -14,7 +14,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # IEEE division / sqrt and no flush-to-zero are REQUIRED: block membership depends on div.rn + round-half-away
 # (SURVEY.md §3.3), so no --use_fast_math.
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-         "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+         "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"] + os.environ.get("SPK_NVCC_DEFS", "").split()
 
 
 def _stale(target, deps):

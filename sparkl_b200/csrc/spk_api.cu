@@ -210,6 +210,7 @@ size_t attr_size(int which) {
 int read_counters(spk_ctx* c) {
     CK(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    c->counters_fresh = true;
     return SPK_OK;
 }
 
@@ -281,7 +282,7 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     c->device = device;
     c->cell_width = cell_width;
     c->sm_count = prop.multiProcessorCount;
-    c->chunk = 256; // == threads per g2p2g CTA (spk_g2p2g.cu)
+    c->chunk = SPK_G2P2G_CHUNK;
     c->g2p2g_mode = 1;
     if (const char* m = getenv("SPK_G2P2G_MODE")) c->g2p2g_mode = atoi(m) ? 1 : 0; // A/B switch for profiling
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -291,6 +292,7 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     CK(cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)));
     CK(cudaHostAlloc((void**)&c->h_counters, sizeof(DeviceCounters), cudaHostAllocDefault));
     std::memset(c->h_counters, 0, sizeof(DeviceCounters));
+    CK(cudaHostAlloc((void**)&c->h_upload, 64, cudaHostAllocDefault));
     // CudaSparseGrid::with_capacity: next_power_of_two().max(1024) blocks (cuda_sparse_grid.rs:53-54); the hash map holds
     // twice as many slots (50 % maximum load factor, cuda_sparse_grid.rs:219)
     const uint32_t cap_hash = std::max<uint32_t>(next_pow2(block_capacity), 1024u) * 2u;
@@ -314,6 +316,7 @@ int spk_ctx_destroy(spk_ctx* c) {
     dev_free(c->slot_cnt); dev_free(c->dispatch); dev_free(c->models); dev_free(c->colliders); dev_free(c->d_counters);
     if (c->staging) cudaFree(c->staging);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_upload) cudaFreeHost(c->h_upload);
     for (auto& e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream); cudaStreamDestroy(c->halo_stream);
     delete c;
@@ -334,6 +337,7 @@ int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkP
     c->n = n;
     c->cur = 0;
     c->sorted_valid = false;
+    c->dt_cache_valid = false;
     // size the sparse grid for the particle count up front: 2x2x2 particles per cell, 4x4x4 cells per block, 50 % load
     // (the reference's own estimate, cuda_sparse_grid.rs:222-229), doubled for the shell of neighbour blocks
     const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (64 * 8 * 50)) * 4u, 2048u);
@@ -388,6 +392,7 @@ int spk_particles_append(spk_ctx* c, const SpkParticleStatus* status, const SpkP
     }
     c->n = new_n;
     c->sorted_valid = false;
+    c->dt_cache_valid = false;
     CK(ensure_dispatch(c));
     return upload_range(c, status, pos, vel, volume, phase, data, old_n, n);
 }
@@ -473,6 +478,7 @@ int spk_models_upload(spk_ctx* c, const SpkGpuParticleModel* models, size_t n) {
     CK(dev_alloc(c->models, n));
     if (n) CK(cudaMemcpy(c->models, dm.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice));
     c->nmodels = n;
+    c->dt_cache_valid = false; // the cached CFL candidate was computed with the previous models
     return SPK_OK;
 }
 
@@ -502,10 +508,7 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
 // ------------------------------------------------------------------------------------------------ stages
 int spk_frame_begin(spk_ctx* c, const SpkSolverParameters* params) {
     if (!c || !params) return SPK_EINVAL;
-    CK(cudaSetDevice(c->device));
-    const unsigned long long v = host_dt_from_sec(params->dt);
-    CK(cudaMemcpyAsync(&c->d_counters->dt_acc, &v, 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    c->dt_acc_host = host_dt_from_sec(params->dt); // timestep_length.copy_from(from_sec(params.dt)), cuda_mpm_pipeline.rs:294-299
     return SPK_OK;
 }
 
@@ -554,26 +557,37 @@ int spk_stage_reset_grid(spk_ctx* c) {
 int spk_stage_estimate_dt(spk_ctx* c, float min_dt, float max_dt, float* dt_out) {
     if (!c) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));
-    CK(spk_launch_estimate_dt(c, min_dt, max_dt));
-    int rc = read_counters(c);
-    if (rc) return rc;
-    if (dt_out) *dt_out = host_dt_into_sec(c->h_counters->dt_acc);
+    if (c->dt_cache_valid) {
+        // K15 was fused into the previous g2p2g (the particle state has not changed since): the reduced un-clamped
+        // candidate arrived with the counters record; apply timestep.rs:87-112 to it.  min / clamp / fixed-point
+        // conversion are monotone, so min_p f(c_p) == f(min_p c_p), bit for bit.
+        if (!c->counters_fresh) { int rc = read_counters(c); if (rc) return rc; }
+        const uint32_t bits = c->h_counters->dt_raw_bits;
+        if (bits < SPK_DT_RAW_NONE) { // at least one non-failed particle
+            float raw;
+            std::memcpy(&raw, &bits, 4);
+            float d = std::fmin(max_dt, raw);
+            if (d < min_dt && max_dt > min_dt) d = min_dt;
+            c->dt_acc_host = std::min(c->dt_acc_host, host_dt_from_sec(d));
+        }
+    } else {
+        CK(spk_launch_estimate_dt(c, min_dt, max_dt));
+        int rc = read_counters(c);
+        if (rc) return rc;
+        if (c->n) c->dt_acc_host = c->h_counters->dt_acc;
+    }
+    if (dt_out) *dt_out = host_dt_into_sec(c->dt_acc_host);
     return SPK_OK;
 }
 
 int spk_dt_acc_get(spk_ctx* c, uint64_t* out) {
     if (!c || !out) return SPK_EINVAL;
-    CK(cudaSetDevice(c->device));
-    int rc = read_counters(c);
-    if (rc) return rc;
-    *out = c->h_counters->dt_acc;
+    *out = c->dt_acc_host;
     return SPK_OK;
 }
 int spk_dt_acc_set(spk_ctx* c, uint64_t v) {
     if (!c) return SPK_EINVAL;
-    CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(&c->d_counters->dt_acc, &v, 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    c->dt_acc_host = v;
     return SPK_OK;
 }
 

@@ -15,8 +15,11 @@
 
 namespace {
 
+#ifndef SPK_G2P2G_MIN_CTAS
+#define SPK_G2P2G_MIN_CTAS 3
+#endif
 constexpr int G2P2G_THREADS = 256;
-constexpr int G2P2G_CHUNK = 256;   // particles per dispatch entry == threads per CTA (one particle per thread)
+constexpr int G2P2G_CHUNK = SPK_G2P2G_CHUNK;
 constexpr int NBINS = 216;         // 6x6x6 possible stencil-base cells of a block's particles after advection
 constexpr int PAY_FLOATS = 28;     // staged P2G payload per particle (7 float4)
 
@@ -33,6 +36,7 @@ struct G2P2GParams {
     const float4* prev_vel; // previous grid velocities [block][64]
     float h, dt;
     uint32_t ndispatch;
+    uint32_t* dt_raw_bits; // CFL candidate of the NEXT substep (fused K15)
 };
 
 // shared memory carve-up (dynamic)
@@ -98,7 +102,7 @@ __device__ __forceinline__ void quad_weights(float x, float w[3]) {
 //         touching the tile: shared float atomics drop from 162 per particle to 162 per occupied cell, with no
 //         same-address conflicts inside a group.
 template <int MODE>
-__global__ void __launch_bounds__(G2P2G_THREADS, 2) g2p2g_kernel(const G2P2GParams P) {
+__global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kernel(const G2P2GParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     float4* s_vel = reinterpret_cast<float4*>(smem + SM_VEL);
     float* s_acc = reinterpret_cast<float*>(smem + SM_ACC);
@@ -110,6 +114,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, 2) g2p2g_kernel(const G2P2GPara
     int* s_nbr_self = reinterpret_cast<int*>(smem + SM_MISC + 8);
     int* s_nbr_prev = reinterpret_cast<int*>(smem + SM_MISC + 40);
     int* s_nnz = reinterpret_cast<int*>(smem + SM_MISC + 72);
+    unsigned* s_dtmin = reinterpret_cast<unsigned*>(smem + SM_MISC + 76);
 
     const int tid = threadIdx.x;
     const DispatchEntry ent = P.dispatch[blockIdx.x];
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, 2) g2p2g_kernel(const G2P2GPara
         s_nbr_self[tid] = P.nbr_self[ent.block * 8 + tid];
         s_nbr_prev[tid] = P.nbr_prev[ent.block * 8 + tid];
     }
-    if (tid == 0) mbar_init(s_bar, 1);
+    if (tid == 0) { mbar_init(s_bar, 1); *s_dtmin = SPK_DT_RAW_NONE; }
     for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64; i += G2P2G_THREADS) s_acc[i] = 0.f;
     if (MODE == 1 && tid < 224) s_bin_cnt[tid] = 0;
     __syncthreads();
@@ -301,6 +306,19 @@ __global__ void __launch_bounds__(G2P2G_THREADS, 2) g2p2g_kernel(const G2P2GPara
         }
     }
 
+    // ---- fused K15 (timestep.rs:38-113): un-clamped dt candidate of this particle for the NEXT substep; the clamps and the
+    // fixed-point conversion are monotone, so they are applied once to the reduced value (spk_stage_estimate_dt)
+    {
+        unsigned cand_bits = SPK_DT_RAW_NONE;
+        if (has_particle && !(p.flags & SPK_F_FAILED)) {
+            const DevModel& model = P.models[p.flags >> SPK_F_MODEL_SHIFT];
+            const float cand = particle_dt_candidate(model, h, p.mass, p.volume0, p.F.m[0], p.elastic_hardening, vel[0], vel[1], vel[2]);
+            cand_bits = __float_as_uint(fminf(fmaxf(cand, 0.f), 1.0e30f)); // NaN -> 1e30 (Rust f32::min ignores NaN)
+        }
+        cand_bits = __reduce_min_sync(0xffffffffu, cand_bits);
+        if ((tid & 31) == 0 && cand_bits < SPK_DT_RAW_NONE) atomicMin(s_dtmin, cand_bits);
+    }
+
     // ---- P2G preparation with the UPDATED position (g2p2g.rs:280-309)
     float ref2[3], w2[3][3];
     int t2[3] = {0, 0, 0};
@@ -471,6 +489,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, 2) g2p2g_kernel(const G2P2GPara
             const int nid = s_nbr_self[o];
             if (nid >= 0) tma_reduce_add_f32_1d(P.acc + (size_t)nid * (SPK_ACC_CHANNELS * 64), &s_acc[o * SPK_ACC_CHANNELS * 64], SPK_ACC_CHANNELS * 64 * 4);
         }
+        if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(P.dt_raw_bits, *s_dtmin);
         tma_commit_and_wait_read();
     }
 }
@@ -536,6 +555,8 @@ cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) {
     P.h = c->cell_width;
     P.dt = dt;
     P.ndispatch = nd;
+    P.dt_raw_bits = &c->d_counters->dt_raw_bits;
+    { cudaError_t e = cudaMemsetAsync(&c->d_counters->dt_raw_bits, 0x7f, 4, c->stream); if (e != cudaSuccess) return e; }
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(g2p2g_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
@@ -548,6 +569,8 @@ cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) {
     c->g2p2g_launches += 1;
     c->cur = 1 - c->cur; // the next buffer now holds the particles, physically in sorted order
     c->sorted_valid = false;
+    c->dt_cache_valid = true;
+    c->counters_fresh = false;
     return cudaGetLastError();
 }
 
@@ -558,6 +581,9 @@ cudaError_t spk_launch_estimate_dt(spk_ctx* c, float min_dt, float max_dt) {
     int blocks = (int)((n + DT_THREADS - 1) / DT_THREADS);
     const int maxb = c->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
+    *c->h_upload = c->dt_acc_host;
+    { cudaError_t e = cudaMemcpyAsync(&c->d_counters->dt_acc, c->h_upload, 8, cudaMemcpyHostToDevice, c->stream); if (e != cudaSuccess) return e; }
+    c->counters_fresh = false;
     estimate_dt_kernel<<<blocks, DT_THREADS, 0, c->stream>>>(pb.a0, pb.a1, pb.a3, pb.a4, c->vel, n, c->models, c->cell_width, min_dt, max_dt, c->d_counters);
     c->launches += 1;
     return cudaGetLastError();

@@ -298,15 +298,17 @@ cudaError_t spk_launch_halo_keys(spk_ctx* c, unsigned long long* out, uint32_t c
 cudaError_t spk_launch_halo_tag(spk_ctx* c, const unsigned long long* remote, uint32_t n) {
     GridBuffers& g = c->grid[1 - c->gcur];
     if (!n) return cudaSuccess;
+    c->counters_fresh = false;
     halo_tag_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(g, remote, n, c->d_counters);
     c->launches += 1;
     return cudaGetLastError();
 }
 cudaError_t spk_launch_halo_pack(spk_ctx* c, unsigned long long* keys, float* payload, uint32_t capacity) {
     GridBuffers& g = c->grid[1 - c->gcur];
-    cudaError_t e = cudaMemsetAsync(&c->d_counters->pad[0], 0, 4, c->stream);
+    cudaError_t e = cudaMemsetAsync(&c->d_counters->halo_cursor, 0, 4, c->stream);
     if (e != cudaSuccess || !g.nab_host) return e;
-    halo_pack_kernel<<<g.nab_host, 64, 0, c->stream>>>(g, g.nab_host, keys, payload, capacity, &c->d_counters->pad[0]);
+    c->counters_fresh = false;
+    halo_pack_kernel<<<g.nab_host, 64, 0, c->stream>>>(g, g.nab_host, keys, payload, capacity, &c->d_counters->halo_cursor);
     c->launches += 1;
     return cudaGetLastError();
 }

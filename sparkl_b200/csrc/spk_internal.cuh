@@ -19,6 +19,9 @@
 #define SPK_ACC_CHANNELS 6
 #define SPK_EMPTY_KEY 0xffffffffffffffffull
 #define SPK_NO_BLOCK 0xffffffffu
+#ifndef SPK_G2P2G_CHUNK
+#define SPK_G2P2G_CHUNK 256 /* particles per g2p2g dispatch entry == threads per CTA */
+#endif
 #define SPK_REF_G2P2G_THREADS 128u /* G2P2G_THREADS of the reference, src_kernels/cuda/mod.rs:15 (dispatch read-back) */
 
 // particle flag bits (record A0.w)
@@ -81,8 +84,12 @@ struct DeviceCounters { // one 64-byte record read back once per substep (pinned
     uint32_t nparticles_binned;
     unsigned long long dt_acc; // GpuTimestepLength
     uint32_t num_halo;
-    uint32_t pad[7];
+    uint32_t halo_cursor;
+    uint32_t dt_raw_bits;    // min over non-failed particles of the un-clamped dt candidate (float bits), written by g2p2g's
+                             // epilogue for the NEXT substep; >= SPK_DT_RAW_NONE when no particle contributed
+    uint32_t pad[5];
 };
+#define SPK_DT_RAW_NONE 0x7f7f7f7fu /* memset pattern; valid candidates are capped at 1e30f */
 
 struct DispatchEntry { uint32_t block; uint32_t first; uint32_t count; uint32_t pad; };
 
@@ -100,6 +107,8 @@ struct spk_ctx {
     uint32_t* rank_of; // rank inside its block
     uint32_t* perm;    // sorted index -> index in current order
     bool sorted_valid; // perm/slot tables describe pb[cur]
+    bool dt_cache_valid; // d_counters->dt_raw_bits describes pb[cur] (set by g2p2g, cleared by any particle/model edit)
+    unsigned long long dt_acc_host; // GpuTimestepLength accumulator (host-authoritative)
     // models / colliders
     DevModel* models; size_t nmodels; uint32_t model_flags_any; // bit0: any model needs an SVD
     DevCollider* colliders; size_t ncolliders;
@@ -114,6 +123,8 @@ struct spk_ctx {
     // counters
     DeviceCounters* d_counters;
     DeviceCounters* h_counters; // pinned
+    unsigned long long* h_upload; // pinned 8-byte staging for dt_acc -> device
+    bool counters_fresh;         // h_counters was read after the last kernel that writes d_counters
     // scratch for read-back / staging
     void* staging; size_t staging_bytes;
     // timing

@@ -181,6 +181,7 @@ cudaError_t spk_launch_sort_bin(spk_ctx* c) {
     if ((e = cudaMemsetAsync(g.keys, 0xff, (size_t)g.cap_hash * 8, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(c->slot_cnt, 0, (size_t)g.cap_hash * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(c->d_counters, 0, 16, s)) != cudaSuccess) return e; // nab, ndispatch, overflow, nparticles_binned
+    c->counters_fresh = false;
     const uint32_t n = (uint32_t)c->n;
     if (n) {
         bin_particles_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->pb[c->cur].a0, n, c->cell_width, g.keys, g.cap_hash, c->slot_cnt,
