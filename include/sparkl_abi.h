@@ -286,11 +286,16 @@ int spk_stage_grid_update(spk_ctx* ctx, float dt, const float gravity[3]);
 
 /* ---- halo exchange for multi-process runs (replaces K3,K4,K17,K18 and the D2D copies,
  * cuda_sparse_grid.rs:256-322, cuda_mpm_pipeline.rs:407-533).  Keys travel as u64 virtual ids; payload is the
- * 6 summed floats per node (mass, momentum xyz, psi_momentum, psi_mass) = 1536 B per block. */
-int spk_halo_active_keys(spk_ctx* ctx, uint64_t* dev_keys_out, uint32_t capacity, uint32_t* count_out); /* device buffer */
-int spk_halo_tag(spk_ctx* ctx, const uint64_t* dev_remote_keys, uint32_t n_remote, uint32_t* num_halo_out);
-int spk_halo_pack(spk_ctx* ctx, uint64_t* dev_keys_out, float* dev_payload_out, uint32_t capacity, uint32_t* count_out);
-int spk_halo_merge(spk_ctx* ctx, const uint64_t* dev_keys, const float* dev_payload, uint32_t n_blocks);
+ * 6 summed floats per node (mass, momentum xyz, psi_momentum, psi_mass) = 1536 B per block.  All buffers are DEVICE
+ * pointers owned by the caller; every call is asynchronous on the context's stream except spk_halo_count.  Buffers
+ * have a fixed capacity agreed between ranks and are padded with the EMPTY key (u64::MAX), which tag/merge skip, so
+ * they can be all-gathered without exchanging lengths first. */
+int spk_halo_begin(spk_ctx* ctx);                                                     /* num_halo_blocks <- 0 */
+int spk_halo_active_keys(spk_ctx* ctx, uint64_t* dev_keys_out, uint32_t capacity);    /* next grid's block keys, padded */
+int spk_halo_tag(spk_ctx* ctx, const uint64_t* dev_remote_keys, uint32_t n_remote);   /* tag_halo_blocks, sort.rs:74-96 */
+int spk_halo_count(spk_ctx* ctx, uint32_t* num_halo_out);                             /* blocking read of num_halo_blocks */
+int spk_halo_pack(spk_ctx* ctx, uint64_t* dev_keys_out, float* dev_payload_out, uint32_t capacity); /* copy_halo_to_staging */
+int spk_halo_merge(spk_ctx* ctx, const uint64_t* dev_keys, const float* dev_payload, uint32_t n_blocks); /* merge_halo_blocks */
 
 /* ---- read-back of the sparse grid in the reference's layouts (parity tests; ≙ the commented-out
  * check_active_blocks, cuda_sparse_grid.rs:491-652).  which_grid: 0 = curr, 1 = next. */

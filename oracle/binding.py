@@ -35,11 +35,13 @@ def lib():
                                   C.POINTER(abi.StepTimings), C.POINTER(C.c_float)]
         _LIB.orc_step.restype = C.c_int
         vp = C.c_void_p
-        _LIB.orc_halo_active_keys.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
-        _LIB.orc_halo_tag.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
-        _LIB.orc_halo_pack.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        _LIB.orc_halo_begin.argtypes = [vp]
+        _LIB.orc_halo_active_keys.argtypes = [vp, vp, C.c_uint32]
+        _LIB.orc_halo_tag.argtypes = [vp, vp, C.c_uint32]
+        _LIB.orc_halo_count.argtypes = [vp, C.POINTER(C.c_uint32)]
+        _LIB.orc_halo_pack.argtypes = [vp, vp, vp, C.c_uint32]
         _LIB.orc_halo_merge.argtypes = [vp, vp, vp, C.c_uint32]
-        for nme in ("orc_halo_active_keys", "orc_halo_tag", "orc_halo_pack", "orc_halo_merge"):
+        for nme in ("orc_halo_begin", "orc_halo_active_keys", "orc_halo_tag", "orc_halo_count", "orc_halo_pack", "orc_halo_merge"):
             getattr(_LIB, nme).restype = C.c_int
         _LIB.orc_set_threads.argtypes = [C.c_int]
         _LIB.orc_set_threads.restype = C.c_int

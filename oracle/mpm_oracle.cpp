@@ -270,6 +270,7 @@ struct orc_ctx {
     int curr = 0; // grids[curr] = read-only previous grid, grids[1-curr] = next
     std::vector<SpkDispatchBlock2ActiveBlock> dispatch;
     uint64_t dt_acc = 0; // GpuTimestepLength
+    uint32_t num_halo = 0;
     Grid& curr_grid() { return grids[curr]; }
     Grid& next_grid() { return grids[1 - curr]; }
 };
@@ -1154,29 +1155,30 @@ int orc_grid_read_dispatch(orc_ctx* c, SpkDispatchBlock2ActiveBlock* dst, uint32
 // ---- halo exchange (multi-process path), same contract as spk_halo_* with HOST pointers; lets the world_size-2 gloo
 // tests drive sparkl_b200.distributed on CPU.  tag_halo_blocks / copy_halo_to_staging / merge_halo_blocks,
 // src_kernels/cuda/sort.rs:74-164.
-int orc_halo_active_keys(orc_ctx* c, uint64_t* keys_out, uint32_t capacity, uint32_t* count_out) {
+int orc_halo_begin(orc_ctx* c) { c->num_halo = 0; return SPK_OK; }
+int orc_halo_active_keys(orc_ctx* c, uint64_t* keys_out, uint32_t capacity) {
     Grid& g = c->next_grid();
-    *count_out = (uint32_t)g.headers.size();
-    if (g.headers.size() > capacity) return SPK_EINVAL;
-    for (size_t i = 0; i < g.headers.size(); ++i) keys_out[i] = g.headers[i].virtual_id;
+    if (g.headers.size() > capacity) return SPK_EOVERFLOW;
+    for (uint32_t i = 0; i < capacity; ++i) keys_out[i] = i < g.headers.size() ? g.headers[i].virtual_id : UINT64_MAX;
     return SPK_OK;
 }
-int orc_halo_tag(orc_ctx* c, const uint64_t* remote_keys, uint32_t n_remote, uint32_t* num_halo_out) {
+int orc_halo_tag(orc_ctx* c, const uint64_t* remote_keys, uint32_t n_remote) {
     Grid& g = c->next_grid();
-    uint32_t nh = 0;
     for (uint32_t i = 0; i < n_remote; ++i) {
+        if (remote_keys[i] == UINT64_MAX) continue;
         int b = g.find(remote_keys[i]);
-        if (b >= 0 && !(g.headers[b].halo_state & 1u)) { g.headers[b].halo_state |= 1u; ++nh; }
+        if (b >= 0 && !(g.headers[b].halo_state & 1u)) { g.headers[b].halo_state |= 1u; ++c->num_halo; }
     }
-    if (num_halo_out) *num_halo_out = nh;
     return SPK_OK;
 }
-int orc_halo_pack(orc_ctx* c, uint64_t* keys_out, float* payload_out, uint32_t capacity, uint32_t* count_out) {
+int orc_halo_count(orc_ctx* c, uint32_t* out) { *out = c->num_halo; return SPK_OK; }
+int orc_halo_pack(orc_ctx* c, uint64_t* keys_out, float* payload_out, uint32_t capacity) {
     Grid& g = c->next_grid();
     uint32_t k = 0;
+    for (uint32_t i = 0; i < capacity; ++i) keys_out[i] = UINT64_MAX;
     for (size_t b = 0; b < g.headers.size(); ++b) {
         if (!(g.headers[b].halo_state & 1u)) continue;
-        if (k >= capacity) return SPK_EINVAL;
+        if (k >= capacity) return SPK_EOVERFLOW;
         keys_out[k] = g.headers[b].virtual_id;
         float* dst = payload_out + (size_t)k * 384;
         for (int cell = 0; cell < 64; ++cell) {
@@ -1186,12 +1188,12 @@ int orc_halo_pack(orc_ctx* c, uint64_t* keys_out, float* payload_out, uint32_t c
         }
         ++k;
     }
-    *count_out = k;
     return SPK_OK;
 }
 int orc_halo_merge(orc_ctx* c, const uint64_t* keys, const float* payload, uint32_t n_blocks) {
     Grid& g = c->next_grid();
     for (uint32_t k = 0; k < n_blocks; ++k) {
+        if (keys[k] == UINT64_MAX) continue;
         int b = g.find(keys[k]);
         if (b < 0) continue;
         const float* src = payload + (size_t)k * 384;

@@ -18,7 +18,7 @@ EXPORTS = [
     "spk_particles_upload", "spk_particles_append", "spk_particles_remove_range", "spk_particles_len", "spk_particles_read",
     "spk_models_upload", "spk_colliders_upload", "spk_step", "spk_frame_begin", "spk_stage_sort", "spk_stage_reset_grid",
     "spk_stage_estimate_dt", "spk_dt_acc_get", "spk_dt_acc_set", "spk_stage_g2p2g", "spk_stage_grid_update",
-    "spk_halo_active_keys", "spk_halo_tag", "spk_halo_pack", "spk_halo_merge", "spk_grid_num_active_blocks",
+    "spk_halo_begin", "spk_halo_active_keys", "spk_halo_tag", "spk_halo_count", "spk_halo_pack", "spk_halo_merge", "spk_grid_num_active_blocks",
     "spk_grid_read_headers", "spk_grid_read_nodes", "spk_grid_read_dispatch", "spk_device_ptr",
 ]
 
@@ -42,9 +42,11 @@ def lib():
         l.spk_particles_remove_range.argtypes = [vp, C.c_size_t, C.c_size_t]
         l.spk_step.argtypes = [C.POINTER(vp), C.c_size_t, C.POINTER(abi.SolverParameters), C.POINTER(C.c_float * 3),
                                C.POINTER(abi.StepTimings), C.POINTER(C.c_float)]
-        l.spk_halo_active_keys.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
-        l.spk_halo_tag.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
-        l.spk_halo_pack.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        l.spk_halo_begin.argtypes = [vp]
+        l.spk_halo_active_keys.argtypes = [vp, vp, C.c_uint32]
+        l.spk_halo_tag.argtypes = [vp, vp, C.c_uint32]
+        l.spk_halo_count.argtypes = [vp, C.POINTER(C.c_uint32)]
+        l.spk_halo_pack.argtypes = [vp, vp, vp, C.c_uint32]
         l.spk_halo_merge.argtypes = [vp, vp, vp, C.c_uint32]
         l.spk_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
         for name in EXPORTS:

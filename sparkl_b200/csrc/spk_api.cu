@@ -733,34 +733,38 @@ int spk_device_ptr(spk_ctx* c, int which, void** out) {
 }
 
 // ------------------------------------------------------------------------------------------------ halo (multi-process)
-int spk_halo_active_keys(spk_ctx* c, uint64_t* dev_keys_out, uint32_t capacity, uint32_t* count_out) {
-    if (!c || !count_out) return SPK_EINVAL;
-    CK(cudaSetDevice(c->device));
-    const uint32_t nab = c->grid[1 - c->gcur].nab_host;
-    *count_out = nab;
-    if (nab > capacity) return SPK_EINVAL;
-    CK(spk_launch_halo_keys(c, (unsigned long long*)dev_keys_out, capacity));
-    CK(cudaStreamSynchronize(c->stream));
-    return SPK_OK;
-}
-int spk_halo_tag(spk_ctx* c, const uint64_t* dev_remote_keys, uint32_t n_remote, uint32_t* num_halo_out) {
+int spk_halo_begin(spk_ctx* c) {
     if (!c) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(&c->d_counters->num_halo, 0, 4, c->stream));
-    CK(spk_launch_halo_tag(c, (const unsigned long long*)dev_remote_keys, n_remote));
-    int rc = read_counters(c);
-    if (rc) return rc;
-    if (num_halo_out) *num_halo_out = c->h_counters->num_halo;
     return SPK_OK;
 }
-int spk_halo_pack(spk_ctx* c, uint64_t* dev_keys_out, float* dev_payload_out, uint32_t capacity, uint32_t* count_out) {
-    if (!c || !count_out) return SPK_EINVAL;
+int spk_halo_active_keys(spk_ctx* c, uint64_t* dev_keys_out, uint32_t capacity) {
+    if (!c || (capacity && !dev_keys_out)) return SPK_EINVAL;
+    if (c->grid[1 - c->gcur].nab_host > capacity) return SPK_EOVERFLOW;
     CK(cudaSetDevice(c->device));
-    CK(spk_launch_halo_pack(c, (unsigned long long*)dev_keys_out, dev_payload_out, capacity));
+    CK(spk_launch_halo_keys(c, (unsigned long long*)dev_keys_out, capacity));
+    return SPK_OK;
+}
+int spk_halo_tag(spk_ctx* c, const uint64_t* dev_remote_keys, uint32_t n_remote) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(spk_launch_halo_tag(c, (const unsigned long long*)dev_remote_keys, n_remote));
+    return SPK_OK;
+}
+int spk_halo_count(spk_ctx* c, uint32_t* num_halo_out) {
+    if (!c || !num_halo_out) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
     int rc = read_counters(c);
     if (rc) return rc;
-    *count_out = c->h_counters->pad[0];
-    return *count_out > capacity ? SPK_EINVAL : SPK_OK;
+    *num_halo_out = c->h_counters->num_halo;
+    return SPK_OK;
+}
+int spk_halo_pack(spk_ctx* c, uint64_t* dev_keys_out, float* dev_payload_out, uint32_t capacity) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(spk_launch_halo_pack(c, (unsigned long long*)dev_keys_out, dev_payload_out, capacity));
+    return SPK_OK;
 }
 int spk_halo_merge(spk_ctx* c, const uint64_t* dev_keys, const float* dev_payload, uint32_t n_blocks) {
     if (!c) return SPK_EINVAL;

@@ -223,12 +223,13 @@ __global__ void grid_export_kernel(GridBuffers g, uint32_t nblocks, SpkGpuGridNo
 // ---- halo path (one process per GPU) -----------------------------------------------------------------------------
 __global__ void halo_keys_kernel(GridBuffers g, uint32_t nab, unsigned long long* out, uint32_t capacity) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nab && b < capacity) out[b] = g.blk_key[b];
+    if (b < capacity) out[b] = b < nab ? g.blk_key[b] : SPK_EMPTY_KEY;
 }
 // tag_halo_blocks (sort.rs:74-96): a remote active block that is also active here becomes IS_HALO
 __global__ void halo_tag_kernel(GridBuffers g, const unsigned long long* __restrict__ remote, uint32_t n, DeviceCounters* counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (remote[i] == SPK_EMPTY_KEY) return; // padding
     const int32_t b = spk_hash_get(g, remote[i]);
     if (b >= 0 && atomicExch(&g.blk_halo[b], 1u) == 0u) atomicAdd(&counters->num_halo, 1u);
 }
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(64) halo_pack_kernel(GridBuffers g, uint32_t n
 }
 // merge_halo_blocks (sort.rs:142-164)
 __global__ void __launch_bounds__(64) halo_merge_kernel(GridBuffers g, const unsigned long long* __restrict__ keys, const float* __restrict__ payload) {
+    if (keys[blockIdx.x] == SPK_EMPTY_KEY) return; // padding
     const int32_t b = spk_hash_get(g, keys[blockIdx.x]);
     if (b < 0) return;
     float* acc = g.acc + (size_t)b * (SPK_ACC_CHANNELS * 64);
@@ -290,8 +292,8 @@ cudaError_t spk_launch_grid_export(spk_ctx* c, int which_grid, SpkGpuGridNode* d
 
 cudaError_t spk_launch_halo_keys(spk_ctx* c, unsigned long long* out, uint32_t capacity) {
     GridBuffers& g = c->grid[1 - c->gcur];
-    if (!g.nab_host) return cudaSuccess;
-    halo_keys_kernel<<<(g.nab_host + 255) / 256, 256, 0, c->stream>>>(g, g.nab_host, out, capacity);
+    if (!capacity) return cudaSuccess;
+    halo_keys_kernel<<<(capacity + 255) / 256, 256, 0, c->stream>>>(g, g.nab_host, out, capacity);
     c->launches += 1;
     return cudaGetLastError();
 }
@@ -306,6 +308,7 @@ cudaError_t spk_launch_halo_tag(spk_ctx* c, const unsigned long long* remote, ui
 cudaError_t spk_launch_halo_pack(spk_ctx* c, unsigned long long* keys, float* payload, uint32_t capacity) {
     GridBuffers& g = c->grid[1 - c->gcur];
     cudaError_t e = cudaMemsetAsync(&c->d_counters->halo_cursor, 0, 4, c->stream);
+    if (e == cudaSuccess && capacity) e = cudaMemsetAsync(keys, 0xff, (size_t)capacity * 8, c->stream); // EMPTY padding
     if (e != cudaSuccess || !g.nab_host) return e;
     c->counters_fresh = false;
     halo_pack_kernel<<<g.nab_host, 64, 0, c->stream>>>(g, g.nab_host, keys, payload, capacity, &c->d_counters->halo_cursor);

@@ -8,12 +8,19 @@ on shared blocks, and dt is the minimum over ranks.  Because a shared block ends
 activated it, the result does not depend on how particles are partitioned — the bench partitions the domain into
 x-slabs so that only slab faces are shared.
 
-Differences with the reference: the payload is the 6 summed floats per node (1536 B per block instead of the 4616-byte
-`HaloBlockData`), the dt minimum is an all-reduce on the u64 accumulator instead of a host loop, and ranks are
-processes, so the exchange goes through `torch.distributed` collectives on device buffers.
+Differences with the reference:
+  * payload = the 6 summed floats per node (1536 B per block instead of the 4616-byte `HaloBlockData`);
+  * fixed-capacity buffers padded with the EMPTY key are all-gathered, so no lengths travel and the exchange needs no
+    host round trip; the reference reads counts back and issues one `cuMemcpyDtoDAsync` per pair of devices;
+  * ONE small all-reduce per substep carries the global dt minimum and the global halo-block maximum (which sizes the
+    payload exchange identically on every rank); the reference loops over devices on the host (:393-398);
+  * everything is enqueued on the context's own stream (torch ops run under `ExternalStream(ctx stream)`), so the
+    collectives are stream-ordered with the kernels: 3 host synchronisations per substep in total
+    (sort counters, halo count, all-reduce result).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -21,111 +28,106 @@ import numpy as np
 from . import abi
 
 BLOCK_PAYLOAD_FLOATS = 6 * 64
-
-
-class HaloExchange:
-    """Backend-agnostic exchange of (keys, payload) between ranks.  Works on torch tensors; with NCCL the tensors are
-    CUDA tensors handed to the library as raw device pointers, with gloo (CPU tests) the same protocol runs on host
-    tensors against a `HaloPeer` implementation."""
-
-    def __init__(self, dist, device):
-        import torch
-        self.torch, self.dist, self.device = torch, dist, device
-        self.world, self.rank = dist.get_world_size(), dist.get_rank()
-
-    def all_gather_varlen(self, t, count: int):
-        """all-gather the first `count` rows of `t` from every rank -> (concatenated rows of the OTHER ranks, counts)"""
-        torch, dist = self.torch, self.dist
-        counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
-        mine = torch.tensor([count], dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(counts, mine) if hasattr(dist, "all_gather_into_tensor") and self.device.type == "cuda" else self._gather_counts(counts, mine)
-        counts_h = counts.cpu().tolist()
-        mx = max(max(counts_h), 1)
-        row = t.shape[1:] if t.dim() > 1 else ()
-        send = torch.zeros((mx,) + tuple(row), dtype=t.dtype, device=self.device)
-        if count:
-            send[:count] = t[:count]
-        recv = [torch.empty_like(send) for _ in range(self.world)]
-        dist.all_gather(recv, send)
-        others = [recv[r][:counts_h[r]] for r in range(self.world) if r != self.rank and counts_h[r] > 0]
-        if others:
-            return torch.cat(others, dim=0), counts_h
-        return send[:0], counts_h
-
-    def _gather_counts(self, counts, mine):
-        lst = [self.torch.zeros_like(mine) for _ in range(self.world)]
-        self.dist.all_gather(lst, mine)
-        counts.copy_(self.torch.cat(lst))
-
-    def all_reduce_min_u64(self, value: int) -> int:
-        torch, dist = self.torch, self.dist
-        # u64 min through two i64-safe halves (NCCL has no u64 min in torch): dt_acc < 2^63 always (dt * 1e12)
-        t = torch.tensor([min(value, (1 << 63) - 1)], dtype=torch.int64, device=self.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        return int(t.item())
+EMPTY = -1  # u64::MAX viewed as int64
 
 
 class DistributedMpmPipeline:
     """`CudaMpmPipeline::step` over several single-GPU contexts living in different processes."""
 
-    def __init__(self, ctx, dist=None, device=None):
+    def __init__(self, ctx, dist=None, device=None, key_capacity: int = 1 << 17):
         import torch
         import torch.distributed as tdist
-        self.ctx = ctx
+        self.torch, self.ctx = torch, ctx
         self.dist = dist or tdist
         self.device = device if device is not None else torch.device("cuda", ctx.device)
-        self.x = HaloExchange(self.dist, self.device)
-        self.torch = torch
-        self._keys = torch.zeros(1024, dtype=torch.int64, device=self.device)
-        self._hkeys = torch.zeros(256, dtype=torch.int64, device=self.device)
-        self._hpay = torch.zeros((256, BLOCK_PAYLOAD_FLOATS), dtype=torch.float32, device=self.device)
+        self.world, self.rank = self.dist.get_world_size(), self.dist.get_rank()
+        self.cuda = self.device.type == "cuda"
+        self.stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=self.device) if self.cuda else None
+        self.key_cap = int(key_capacity)  # agreed capacity of the active-key exchange (blocks per rank)
+        z = lambda *shape, dt: torch.zeros(shape, dtype=dt, device=self.device)
+        self._keys = z(self.key_cap, dt=torch.int64)
+        self._allkeys = z(self.world, self.key_cap, dt=torch.int64)
+        self._halo_cap = 0
+        self._hk = self._hp = self._allhk = self._allhp = None
+        self._red = z(2, dt=torch.int64)
+        self._red_host = torch.zeros(2, dtype=torch.int64).pin_memory() if self.cuda else torch.zeros(2, dtype=torch.int64)
         self.halo_blocks_last = 0
         self.halo_bytes_last = 0
 
-    def _ensure(self, name, n, cols=None):
-        t = getattr(self, name)
-        if t.shape[0] < n:
-            shape = (int(n * 1.5) + 64,) + ((cols,) if cols else ())
-            setattr(self, name, self.torch.zeros(shape, dtype=t.dtype, device=self.device))
-        return getattr(self, name)
+    # ---- helpers ------------------------------------------------------------------------------------------------
+    def _scope(self):
+        return self.torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()
 
+    def _all_gather(self, out2d, inp):
+        if self.cuda:
+            self.dist.all_gather_into_tensor(out2d.view(-1, *inp.shape[1:]) if inp.dim() > 1 else out2d.view(-1), inp)
+        else:
+            lst = [out2d[r] for r in range(self.world)]
+            self.dist.all_gather(lst, inp)
+
+    def _ensure_halo(self, cap):
+        if cap == self._halo_cap:
+            return
+        torch = self.torch
+        self._halo_cap = cap
+        self._hk = torch.zeros(cap, dtype=torch.int64, device=self.device)
+        self._hp = torch.zeros((cap, BLOCK_PAYLOAD_FLOATS), dtype=torch.float32, device=self.device)
+        self._allhk = torch.zeros((self.world, cap), dtype=torch.int64, device=self.device)
+        self._allhp = torch.zeros((self.world, cap, BLOCK_PAYLOAD_FLOATS), dtype=torch.float32, device=self.device)
+
+    def _others(self, t2d):
+        """the two contiguous row ranges of a [world, ...] buffer that belong to the OTHER ranks"""
+        out = []
+        if self.rank > 0:
+            out.append(t2d[: self.rank])
+        if self.rank + 1 < self.world:
+            out.append(t2d[self.rank + 1:])
+        return out
+
+    # ---- one substep --------------------------------------------------------------------------------------------
     def substep(self, params: abi.SolverParameters, gravity, remaining: float) -> float:
-        ctx, l, h = self.ctx, self.ctx._lib, self.ctx._h
-        vp = C.c_void_p
-        info = ctx.stage_sort()
-        # ---- halo tagging: all-gather of active block keys (cuda_sparse_grid.rs:256-322)
-        nab = info.num_active_blocks
-        keys = self._ensure("_keys", nab)
-        cnt = C.c_uint32()
-        ctx._call("halo_active_keys", vp(keys.data_ptr()), keys.shape[0], C.byref(cnt))
-        remote, _ = self.x.all_gather_varlen(keys, nab)
-        nh = C.c_uint32()
-        remote = remote.contiguous()
-        ctx._call("halo_tag", vp(remote.data_ptr()) if remote.numel() else vp(0), int(remote.shape[0]), C.byref(nh))
-        ctx.stage_reset_grid()
-        # ---- dt: local candidate, global min (cuda_mpm_pipeline.rs:393-398)
-        min_dt = float(np.float32(params.dt) / np.float32(params.max_num_substeps))
-        max_dt = float(min(np.float32(remaining), np.float32(params.max_substep_dt)))
-        ctx.stage_estimate_dt(min_dt, max_dt)
-        acc = self.x.all_reduce_min_u64(ctx.dt_acc())
-        ctx.set_dt_acc(acc)
-        dt = float(np.float32(acc) / np.float32(1.0e12))
-        # ---- transfers + halo accumulate (cuda_mpm_pipeline.rs:407-533)
-        if info.num_dispatch_blocks > 0:
-            ctx.stage_g2p2g(dt, params.damage_model)
-        nhalo = nh.value
-        hk = self._ensure("_hkeys", nhalo)
-        hp = self._ensure("_hpay", nhalo, BLOCK_PAYLOAD_FLOATS)
-        got = C.c_uint32()
-        ctx._call("halo_pack", vp(hk.data_ptr()), vp(hp.data_ptr()), hk.shape[0], C.byref(got))
-        rk, _ = self.x.all_gather_varlen(hk, got.value)
-        rp, _ = self.x.all_gather_varlen(hp, got.value)
-        rk, rp = rk.contiguous(), rp.contiguous()
-        if rk.shape[0]:
-            ctx._call("halo_merge", vp(rk.data_ptr()), vp(rp.data_ptr()), int(rk.shape[0]))
-        self.halo_blocks_last = int(got.value)
-        self.halo_bytes_last = int(got.value) * (8 + 4 * BLOCK_PAYLOAD_FLOATS)
-        ctx.stage_grid_update(dt, gravity)
+        ctx, vp = self.ctx, C.c_void_p
+        with self._scope():
+            info = ctx.stage_sort()                                            # host sync 1 (counters)
+            if info.num_active_blocks > self.key_cap:
+                raise abi.SparklError(abi.EOVERFLOW, f"{info.num_active_blocks} active blocks exceed the key exchange capacity {self.key_cap}")
+            # ---- halo tagging: all-gather of active block keys (cuda_sparse_grid.rs:256-322)
+            ctx._call("halo_begin")
+            ctx._call("halo_active_keys", vp(self._keys.data_ptr()), self.key_cap)
+            self._all_gather(self._allkeys, self._keys)
+            for part in self._others(self._allkeys):
+                ctx._call("halo_tag", vp(part.data_ptr()), int(part.numel()))
+            ctx.stage_reset_grid()
+            # ---- dt: local candidate, then ONE all-reduce for (global dt min, global max halo count)
+            min_dt = float(np.float32(params.dt) / np.float32(params.max_num_substeps))
+            max_dt = float(min(np.float32(remaining), np.float32(params.max_substep_dt)))
+            ctx.stage_estimate_dt(min_dt, max_dt)
+            nh = C.c_uint32()
+            ctx._call("halo_count", C.byref(nh))                               # host sync 2
+            self._red_host[0] = min(ctx.dt_acc(), (1 << 63) - 1)
+            self._red_host[1] = -int(nh.value)
+            self._red.copy_(self._red_host, non_blocking=True)
+            self.dist.all_reduce(self._red, op=self.dist.ReduceOp.MIN)
+            red = self._red.cpu() if self.cuda else self._red                  # host sync 3
+            acc, max_halo = int(red[0]), -int(red[1])
+            ctx.set_dt_acc(acc)
+            dt = float(np.float32(acc) / np.float32(1.0e12))
+            # ---- transfers, then halo accumulate (cuda_mpm_pipeline.rs:407-533)
+            if info.num_dispatch_blocks > 0:
+                ctx.stage_g2p2g(dt, params.damage_model)
+            if max_halo > 0:
+                cap = (max_halo + 255) // 256 * 256
+                self._ensure_halo(cap)
+                hk, hp = self._hk[:cap], self._hp[:cap]
+                ctx._call("halo_pack", vp(hk.data_ptr()), vp(hp.data_ptr()), cap)
+                allhk, allhp = self._allhk, self._allhp
+                self._all_gather(allhk, hk)
+                self._all_gather(allhp, hp)
+                for pk, pp in zip(self._others(allhk), self._others(allhp)):
+                    ctx._call("halo_merge", vp(pk.data_ptr()), vp(pp.data_ptr()), int(pk.numel()))
+            self.halo_blocks_last = int(nh.value)
+            self.halo_bytes_last = int(nh.value) * (8 + 4 * BLOCK_PAYLOAD_FLOATS)
+            ctx.stage_grid_update(dt, gravity)
         return dt
 
     def step(self, params: abi.SolverParameters, gravity):
