@@ -9,7 +9,7 @@ from . import abi
 from .engine import declare
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsparkl_b200.so")
+LIB_PATH = os.environ.get("SPK_LIB_PATH") or os.path.join(_HERE, "libsparkl_b200.so")  # SPK_LIB_PATH: A/B builds of the same ABI (scripts/variants.sh)
 _LIB = None
 
 # every symbol include/sparkl_abi.h declares

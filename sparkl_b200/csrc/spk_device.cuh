@@ -26,6 +26,15 @@ __device__ __forceinline__ long long spk_assoc_cell(float p, float h) {
     if (q != q) return 0;
     return __float2ll_rz(q); // saturates on overflow
 }
+// x / h, correctly rounded, from the correctly rounded reciprocal y = RN(1 / h) (Markstein: q0 = x y, r = x - q0 h exactly
+// by FMA, q = q0 + r y).  Bit-identical to div.rn.f32 over 4e9 random operands and the cell widths of every scene
+// (scripts/check_div.c); operands outside the safe exponent range take the IEEE division.  3 instructions instead of ~12.
+__device__ __forceinline__ float spk_div_h(float x, float h, float inv_h) {
+    const float q0 = x * inv_h;
+    const float q = fmaf(fmaf(-q0, h, x), inv_h, q0);
+    const float ax = fabsf(x);
+    return (ax < 1.0e30f && ax > 1.0e-30f) ? q : __fdiv_rn(x, h);
+}
 // block_associated_to_point, gpu_grid.rs:271-279: ((cell - 2 + 2^22) as usize) / 4 per axis
 __device__ __forceinline__ unsigned long long spk_block_coord(long long cell) {
     return (unsigned long long)(cell - 2 + SPK_PACK_ORIGIN * 4) / 4ull;

@@ -34,7 +34,7 @@ struct G2P2GParams {
     const int32_t* nbr_prev;
     float* acc;             // next grid accumulators [block][6][64]
     const float4* prev_vel; // previous grid velocities [block][64]
-    float h, dt;
+    float h, inv_h, dt;
     uint32_t ndispatch;
     uint32_t* dt_raw_bits; // CFL candidate of the NEXT substep (fused K15)
 };
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
     for (int i = tid; i < SPK_TILE_CELLS; i += G2P2G_THREADS)
         if (s_nbr_prev[i >> 6] < 0) s_vel[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    const float h = P.h, dt = P.dt;
+    const float h = P.h, inv_h = P.inv_h, dt = P.dt;
     const float inv_d = 4.f / (h * h);
     const bool has_particle = (uint32_t)tid < ent.count;
 
@@ -162,15 +162,19 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
         p.log_vol_gain = r5.x; p.nacc_alpha = r5.y; p.orig_id = __float_as_uint(r5.z);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float q = roundf(__fdiv_rn(p.x[a], h));
+            const float q = roundf(spk_div_h(p.x[a], h, inv_h));
             cell_before[a] = q;
             ref[a] = (q - 1.f) * h - p.x[a];               // dir_to_associated_grid_node, particle.rs:37-47
-            quad_weights(__fdiv_rn(-ref[a], h), w[a]);
+            quad_weights(spk_div_h(-ref[a], h, inv_h), w[a]);
             const int assoc_cell = (q != q) ? -2 : (int)__float2ll_rz(q) - 2;
             tcell[a] = (assoc_cell & 3) + 1;                // associated_cell_index_in_block_off_by_two, particle.rs:28-35
         }
     }
+#ifdef SPK_WAIT1
+    if ((tid & 31) == 0) mbar_wait(s_bar, 0);
+#else
     mbar_wait(s_bar, 0);
+#endif
     __syncthreads();
 
     if (has_particle) {
@@ -180,7 +184,11 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
         {
             float V[3] = {0.f, 0.f, 0.f}, Gx[3] = {0.f, 0.f, 0.f}, Gy[3] = {0.f, 0.f, 0.f}, Gz[3] = {0.f, 0.f, 0.f};
             const float wpx[3] = {w[0][0] * ref[0], w[0][1] * (ref[0] + h), w[0][2] * (ref[0] + 2.f * h)};
+#ifdef SPK_G2P_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int dz = 0; dz < 3; ++dz) {
                 const int iz = cell_part(tcell[2] + dz, 2) | (oct_part(tcell[2] + dz, 2) << 6);
                 float P0[3] = {0.f, 0.f, 0.f}, P1[3] = {0.f, 0.f, 0.f}, P2[3] = {0.f, 0.f, 0.f};
@@ -327,9 +335,9 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
     if (has_particle && do_p2g) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float q = roundf(__fdiv_rn(p.x[a], h));
+            const float q = roundf(spk_div_h(p.x[a], h, inv_h));
             ref2[a] = (q - 1.f) * h - p.x[a];
-            quad_weights(__fdiv_rn(-ref2[a], h), w2[a]);
+            quad_weights(spk_div_h(-ref2[a], h, inv_h), w2[a]);
             const float mvf = q - cell_before[a];
             const int mv = (mvf != mvf) ? 0 : (int)__float2ll_rz(mvf);
             t2[a] = tcell[a] + mv; // in [0, 5] after the velocity clamp
@@ -441,7 +449,12 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
         const float fsy = (float)sy, fsz = (float)sz;
         const int nnz = *s_nnz;
         if (grp < 3) {
+#ifdef SPK_SPREAD
+            const int third = (nnz + 2) / 3;
+            for (int k = warp, e = warp + grp * third; k < third; k += G2P2G_THREADS / 32, e += G2P2G_THREADS / 32) if (e < nnz) {
+#else
             for (int e = warp * 3 + grp; e < nnz; e += (G2P2G_THREADS / 32) * 3) {
+#endif
                 const int bin = s_binlist[e];
                 const int start = s_bin_start[bin], cnt = s_bin_cnt[bin];
                 float aM[3] = {0.f, 0.f, 0.f}, aX[3] = {0.f, 0.f, 0.f}, aY[3] = {0.f, 0.f, 0.f}, aZ[3] = {0.f, 0.f, 0.f}, aPm[3] = {0.f, 0.f, 0.f},
@@ -553,6 +566,7 @@ cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) {
     P.acc = next.acc;
     P.prev_vel = prev.vel;
     P.h = c->cell_width;
+    P.inv_h = 1.0f / c->cell_width;
     P.dt = dt;
     P.ndispatch = nd;
     P.dt_raw_bits = &c->d_counters->dt_raw_bits;

@@ -49,85 +49,104 @@ __device__ __forceinline__ float signum_f(float x) { return (x != x) ? x : copys
 // ---------------------------------------------------------------------------------------------------- SVD
 struct Svd3 { Mat3 u; float s[3]; Mat3 v; }; // F = u diag(s) v^T, s >= 0 (unordered)
 
+// One Hestenes rotation of the column pair (p, q) of U (and V).  al / be are the squared column norms (tracked
+// incrementally inside a sweep: a Jacobi rotation moves exactly t * ga from one to the other), ga their dot product.
+//   t = tan(theta) = sign(d) 2 ga / (|d| + sqrt(d^2 + 4 ga^2)),  d = be - al     (the smaller root, |theta| <= pi/4)
+// Approximate MUFU reciprocal / rsqrt are enough for t (the angle only has to be accurate enough for quadratic
+// convergence); c = 1 / sqrt(1 + t^2) gets one Newton step so the rotation stays orthonormal to f32 round-off.
 #define SPK_JACOBI_ROT(p, q)                                                                                            \
     {                                                                                                                   \
-        float al = U.m[3 * p] * U.m[3 * p] + U.m[3 * p + 1] * U.m[3 * p + 1] + U.m[3 * p + 2] * U.m[3 * p + 2];           \
-        float be = U.m[3 * q] * U.m[3 * q] + U.m[3 * q + 1] * U.m[3 * q + 1] + U.m[3 * q + 2] * U.m[3 * q + 2];           \
-        float ga = U.m[3 * p] * U.m[3 * q] + U.m[3 * p + 1] * U.m[3 * q + 1] + U.m[3 * p + 2] * U.m[3 * q + 2];           \
-        if (ga * ga > (6.0e-15f) * (al * be)) {                                                                          \
-            rotated = true;                                                                                             \
-            float zeta = (be - al) / (2.f * ga);                                                                        \
-            float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));                                  \
-            float cc = rsqrtf(1.f + t * t);                                                                             \
-            cc = cc * (1.5f - 0.5f * (1.f + t * t) * cc * cc);                                                          \
-            float ss = cc * t;                                                                                          \
+        const float ga = U.m[3 * p] * U.m[3 * q] + U.m[3 * p + 1] * U.m[3 * q + 1] + U.m[3 * p + 2] * U.m[3 * q + 2];     \
+        const float g2 = ga * ga, ab = nrm[p] * nrm[q];                                                                 \
+        big = big || (g2 > 1.0e-9f * ab);                                                                               \
+        if (g2 > 1.0e-14f * ab) {                                                                                       \
+            const float d = nrm[q] - nrm[p];                                                                            \
+            const float x = fmaf(d, d, 4.f * g2);                                                                       \
+            const float den = fabsf(d) + x * rsqrtf(x);                                                                 \
+            float t = __fdividef(ga + ga, den);                                                                         \
+            t = d < 0.f ? -t : t;                                                                                       \
+            const float tt = fmaf(t, t, 1.f);                                                                           \
+            float cc = rsqrtf(tt);                                                                                      \
+            cc = cc * fmaf(-0.5f * tt, cc * cc, 1.5f);                                                                  \
+            const float ss = cc * t;                                                                                    \
+            nrm[p] = fmaf(-t, ga, nrm[p]);                                                                              \
+            nrm[q] = fmaf(t, ga, nrm[q]);                                                                               \
             _Pragma("unroll") for (int r = 0; r < 3; ++r) {                                                             \
-                float up = U.m[3 * p + r], uq = U.m[3 * q + r];                                                         \
+                const float up = U.m[3 * p + r], uq = U.m[3 * q + r];                                                   \
                 U.m[3 * p + r] = cc * up - ss * uq;                                                                     \
                 U.m[3 * q + r] = ss * up + cc * uq;                                                                     \
-                float vp = V.m[3 * p + r], vq = V.m[3 * q + r];                                                         \
+                const float vp = V.m[3 * p + r], vq = V.m[3 * q + r];                                                   \
                 V.m[3 * p + r] = cc * vp - ss * vq;                                                                     \
                 V.m[3 * q + r] = ss * vp + cc * vq;                                                                     \
             }                                                                                                           \
         }                                                                                                               \
     }
 
+// rank-deficient F: complete U to an orthonormal basis (the reference's nalgebra SVD also returns a full U)
+__device__ __forceinline__ void svd3_complete_basis(Mat3& U, float* sv, bool* ok) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (ok[c]) continue;
+        const int a1 = (c + 1) % 3, a2 = (c + 2) % 3;
+        float w0, w1, w2;
+        if (ok[a1] && ok[a2]) {
+            w0 = U.m[3 * a1 + 1] * U.m[3 * a2 + 2] - U.m[3 * a1 + 2] * U.m[3 * a2 + 1];
+            w1 = U.m[3 * a1 + 2] * U.m[3 * a2 + 0] - U.m[3 * a1 + 0] * U.m[3 * a2 + 2];
+            w2 = U.m[3 * a1 + 0] * U.m[3 * a2 + 1] - U.m[3 * a1 + 1] * U.m[3 * a2 + 0];
+        } else {
+            // at most one valid column k: any unit vector orthogonal to it
+            const int k = ok[a1] ? a1 : a2;
+            float kx = ok[k] ? U.m[3 * k] : 0.f, ky = ok[k] ? U.m[3 * k + 1] : 0.f, kz = ok[k] ? U.m[3 * k + 2] : 0.f;
+            float ex = fabsf(kx) <= fabsf(ky) && fabsf(kx) <= fabsf(kz) ? 1.f : 0.f;
+            float ey = (ex == 0.f && fabsf(ky) <= fabsf(kz)) ? 1.f : 0.f;
+            float ez = (ex == 0.f && ey == 0.f) ? 1.f : 0.f;
+            float d = ex * kx + ey * ky + ez * kz;
+            w0 = ex - d * kx; w1 = ey - d * ky; w2 = ez - d * kz;
+            float inv = rsqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+            w0 *= inv; w1 *= inv; w2 *= inv;
+        }
+        U.m[3 * c] = w0; U.m[3 * c + 1] = w1; U.m[3 * c + 2] = w2;
+        ok[c] = true;
+        sv[c] = 0.f;
+    }
+}
+
 // One-sided (Hestenes) Jacobi: rotates column pairs of U = F V until mutually orthogonal; relative accuracy of the
-// singular values is that of f32 even for ill-conditioned F.  F = I (rest state) exits after the first sweep.
+// singular values is that of f32 even for ill-conditioned F.  Convergence is quadratic, so the loop stops after the
+// first sweep whose largest pre-rotation cosine^2 was below 1e-9 (the rotations of that sweep bring it to round-off):
+// 3-4 sweeps for any F met in practice, no extra verification sweep.
 __device__ __forceinline__ Svd3 svd3(const Mat3& F) {
     Mat3 U = F, V = mat_identity();
 #pragma unroll 1
     for (int sweep = 0; sweep < 12; ++sweep) {
-        bool rotated = false;
+        bool big = false;
+        float nrm[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) nrm[c] = U.m[3 * c] * U.m[3 * c] + U.m[3 * c + 1] * U.m[3 * c + 1] + U.m[3 * c + 2] * U.m[3 * c + 2];
         SPK_JACOBI_ROT(0, 1)
         SPK_JACOBI_ROT(0, 2)
         SPK_JACOBI_ROT(1, 2)
-        if (!rotated) break;
+        if (!big) break;
     }
     Svd3 out;
     bool ok[3];
     float smax = 0.f;
+    float inv[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        out.s[c] = sqrtf(U.m[3 * c] * U.m[3 * c] + U.m[3 * c + 1] * U.m[3 * c + 1] + U.m[3 * c + 2] * U.m[3 * c + 2]);
+        const float n2 = U.m[3 * c] * U.m[3 * c] + U.m[3 * c + 1] * U.m[3 * c + 1] + U.m[3 * c + 2] * U.m[3 * c + 2];
+        float r = rsqrtf(fmaxf(n2, 1.0e-37f));
+        r = r * fmaf(-0.5f * n2, r * r, 1.5f); // one Newton step: 1 / |u_c| to f32 round-off
+        inv[c] = r;
+        out.s[c] = n2 * r;
         smax = fmaxf(smax, out.s[c]);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         ok[c] = out.s[c] > 1.0e-30f && out.s[c] > 1.0e-7f * smax;
-        if (ok[c]) {
-            float inv = 1.f / out.s[c];
-            U.m[3 * c] *= inv; U.m[3 * c + 1] *= inv; U.m[3 * c + 2] *= inv;
-        }
+        if (ok[c]) { U.m[3 * c] *= inv[c]; U.m[3 * c + 1] *= inv[c]; U.m[3 * c + 2] *= inv[c]; }
     }
-    if (!(ok[0] && ok[1] && ok[2])) {
-        // rank-deficient F: complete U to an orthonormal basis (the reference's nalgebra SVD also returns a full U)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (ok[c]) continue;
-            const int a1 = (c + 1) % 3, a2 = (c + 2) % 3;
-            float w0, w1, w2;
-            if (ok[a1] && ok[a2]) {
-                w0 = U.m[3 * a1 + 1] * U.m[3 * a2 + 2] - U.m[3 * a1 + 2] * U.m[3 * a2 + 1];
-                w1 = U.m[3 * a1 + 2] * U.m[3 * a2 + 0] - U.m[3 * a1 + 0] * U.m[3 * a2 + 2];
-                w2 = U.m[3 * a1 + 0] * U.m[3 * a2 + 1] - U.m[3 * a1 + 1] * U.m[3 * a2 + 0];
-            } else {
-                // at most one valid column k: any unit vector orthogonal to it
-                const int k = ok[a1] ? a1 : a2;
-                float kx = ok[k] ? U.m[3 * k] : 0.f, ky = ok[k] ? U.m[3 * k + 1] : 0.f, kz = ok[k] ? U.m[3 * k + 2] : 0.f;
-                float ex = fabsf(kx) <= fabsf(ky) && fabsf(kx) <= fabsf(kz) ? 1.f : 0.f;
-                float ey = (ex == 0.f && fabsf(ky) <= fabsf(kz)) ? 1.f : 0.f;
-                float ez = (ex == 0.f && ey == 0.f) ? 1.f : 0.f;
-                float d = ex * kx + ey * ky + ez * kz;
-                w0 = ex - d * kx; w1 = ey - d * ky; w2 = ez - d * kz;
-                float inv = rsqrtf(w0 * w0 + w1 * w1 + w2 * w2);
-                w0 *= inv; w1 *= inv; w2 *= inv;
-            }
-            U.m[3 * c] = w0; U.m[3 * c + 1] = w1; U.m[3 * c + 2] = w2;
-            ok[c] = true;
-            out.s[c] = 0.f;
-        }
-    }
+    if (!(ok[0] && ok[1] && ok[2])) svd3_complete_basis(U, out.s, ok);
     out.u = U;
     out.v = V;
     return out;
@@ -141,7 +160,7 @@ __device__ __forceinline__ Mat3 svd_recompose(const Mat3& u, const float s[3], c
 }
 
 // eigenvalue extrema of a symmetric 3x3 (lower triangle read, like nalgebra SymmetricEigen) by cyclic Jacobi
-__device__ inline void sym_eig_minmax(const Mat3& a, float& mn, float& mx) {
+__device__ __forceinline__ void sym_eig_minmax(const Mat3& a, float& mn, float& mx) {
     float A00 = M_(a, 0, 0), A11 = M_(a, 1, 1), A22 = M_(a, 2, 2), A01 = M_(a, 1, 0), A02 = M_(a, 2, 0), A12 = M_(a, 2, 1);
 #pragma unroll 1
     for (int sweep = 0; sweep < 10; ++sweep) {
@@ -207,7 +226,8 @@ __device__ __forceinline__ float monaghan_pressure(const DevModel& m, float mass
 
 // GpuPlasticModel::update_particle (gpu_plastic_model.rs:21-61) on a shared SVD.  Returns true when F changed
 // (svd.s then holds the projected singular values and F has been recomposed).
-__device__ inline bool plastic_update(const DevModel& m, ParticleState& p, Svd3& svd) {
+__device__ __forceinline__ bool plastic_update_other(const DevModel& m, ParticleState& p, Svd3& svd);
+__device__ __forceinline__ bool plastic_update(const DevModel& m, ParticleState& p, Svd3& svd) {
     float* s = svd.s;
     switch (m.ptag) {
     case SPK_PLASTIC_DRUCKER_PRAGER: { // plasticity_drucker_prager.rs:36-104
@@ -245,6 +265,13 @@ __device__ inline bool plastic_update(const DevModel& m, ParticleState& p, Svd3&
         p.F = svd_recompose(svd.u, s, svd.v);
         return true;
     }
+    case SPK_PLASTIC_NACC: case SPK_PLASTIC_RANKINE: case SPK_PLASTIC_SNOW: return plastic_update_other(m, p, svd);
+    default: return false; // Custom / None: no-op (gpu_plastic_model.rs:59)
+    }
+}
+__device__ __forceinline__ bool plastic_update_other(const DevModel& m, ParticleState& p, Svd3& svd) {
+    float* s = svd.s;
+    switch (m.ptag) {
     case SPK_PLASTIC_NACC: { // plasticity_nacc.rs:61-165
         const float mu = m.p[0], kappa = m.p[1], xi = m.p[2], beta = m.p[3], mm = m.p[4];
         const bool hardening_enabled = (m.flags & 4u) != 0;
@@ -336,7 +363,8 @@ __device__ inline bool plastic_update(const DevModel& m, ParticleState& p, Svd3&
 }
 
 // CorotatedLinearElasticity::kirchhoff_stress, elasticity_corotated_linear.rs:31-77, from the shared SVD of F.
-__device__ inline Mat3 corotated_stress(const DevModel& m, float phase, float hardening, const Mat3& F, const Svd3& svd, float j) {
+__device__ __forceinline__ Mat3 corotated_stress_split(const DevModel& m, float phase, float hardening, const Mat3& F, const Svd3& svd, float j, float sph);
+__device__ __forceinline__ Mat3 corotated_stress(const DevModel& m, float phase, float hardening, const Mat3& F, const Svd3& svd, float j) {
     const float lambda = m.c[1], mu = m.c[2];
     const float sph = lambda * hardening * (j - 1.f) * j;
     if (phase == 1.f) {
@@ -352,6 +380,10 @@ __device__ inline Mat3 corotated_stress(const DevModel& m, float phase, float ha
         t.m[0] += sph; t.m[4] += sph; t.m[8] += sph;
         return t;
     }
+    return corotated_stress_split(m, phase, hardening, F, svd, j, sph);
+}
+__device__ __forceinline__ Mat3 corotated_stress_split(const DevModel& m, float phase, float hardening, const Mat3& F, const Svd3& svd, float j, float sph) {
+    const float mu = m.c[2];
     float sp[3], sn[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) { sp[i] = fmaxf(svd.s[i] - 1.f, 0.f); sn[i] = fminf(svd.s[i] - 1.f, 0.f); }
@@ -370,7 +402,7 @@ __device__ inline Mat3 corotated_stress(const DevModel& m, float phase, float ha
 }
 
 // elasticity_neo_hookean.rs:43-67
-__device__ inline Mat3 neo_hookean_stress(const DevModel& m, float phase, float hardening, const Mat3& F, float j) {
+__device__ __forceinline__ Mat3 neo_hookean_stress(const DevModel& m, float phase, float hardening, const Mat3& F, float j) {
     const float lambda = m.c[1], mu = m.c[2];
     const float pc = (1.f - 0.001f) * phase * phase + 0.001f;
     const float k = 2.f / 3.f * mu * hardening + lambda * hardening;
