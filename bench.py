@@ -166,8 +166,12 @@ def run_ours(args):
     params = abi.SolverParameters(stop_after_one_substep=1)
     pipe = None
     if world > 1:
-        from sparkl_b200.distributed import DistributedMpmPipeline
-        pipe = DistributedMpmPipeline(ctx, dist, torch.device("cuda", local))
+        if args.halo == "nvlink":  # device-initiated NVLink peer-memory exchange inside spk_step (spk_dist.cu)
+            from sparkl_b200.distributed import NvlinkMpmPipeline
+            NvlinkMpmPipeline(ctx, dist)
+        else:                      # the portable torch.distributed (NCCL) protocol, kept for A/B
+            from sparkl_b200.distributed import DistributedMpmPipeline
+            pipe = DistributedMpmPipeline(ctx, dist, torch.device("cuda", local))
 
     def one_substep():
         if pipe is None:
@@ -259,7 +263,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"sand3 (examples3d/sand3.rs scaled): 2 stacked lattices {dims[0]}x{dims[1]}x{dims[2]} per GPU = {npart} particles/GPU, h=0.2, "
                                    "Drucker-Prager sand over corotated block, cuboid floor+walls", "particles_per_gpu": npart,
-                       "parallelism": f"x-slabs x{world}, halo exchange" if world > 1 else "single GPU", "l2": "inputs larger than L2 (particle state ~0.8 GB per GPU)"},
+                       "parallelism": f"x-slabs x{world}, halo accumulate over {'NVLink peer memory (device-initiated)' if args.halo == 'nvlink' else 'NCCL all-gather'}" if world > 1 else "single GPU", "l2": "inputs larger than L2 (particle state ~0.8 GB per GPU)"},
             "clocks": clocks, "gpu_launches": int(launches) if launches else None, "e2e": e2e, "roofline": roof, "cpu_baseline": base,
             "reference_gpu": ref_gpu}
     print(json.dumps(line), flush=True)
@@ -287,6 +291,7 @@ def main():
     ap.add_argument("--settle", type=int, default=120, help="untimed substeps run before the warm-up to load the material")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own GPU kernels (oracle/_ref)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="nvlink", choices=["nvlink", "nccl"], help="multi-GPU halo exchange: NVLink peer memory inside spk_step, or NCCL collectives")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -297,6 +297,18 @@ int spk_halo_count(spk_ctx* ctx, uint32_t* num_halo_out);                       
 int spk_halo_pack(spk_ctx* ctx, uint64_t* dev_keys_out, float* dev_payload_out, uint32_t capacity); /* copy_halo_to_staging */
 int spk_halo_merge(spk_ctx* ctx, const uint64_t* dev_keys, const float* dev_payload, uint32_t n_blocks); /* merge_halo_blocks */
 
+/* ---- multi-GPU over NVLink peer memory, one process per GPU (replaces the gather of active block headers,
+ * src/cuda/cuda_sparse_grid.rs:256-322; K3/K4/K17/K18, src_kernels/cuda/sort.rs:74-164; the per-pair cuMemcpyDtoDAsync
+ * and the host dt minimum, src/cuda/cuda_mpm_pipeline.rs:393-398,458-472,512-532).  Every rank exports one descriptor,
+ * the caller all-gathers them with whatever transport it has (MPI, torch.distributed, a file) and attaches; from then on
+ * spk_step() runs the exchange itself with device-initiated NVLink loads / atomics and two device-side barriers per
+ * substep.  Collective: every rank must make the same sequence of spk_step / upload calls; each rank must own particles. */
+typedef struct SpkDistDescriptor { unsigned char opaque[128]; } SpkDistDescriptor;
+int spk_dist_export(spk_ctx* ctx, SpkDistDescriptor* out);   /* after the particle upload, before the first step */
+int spk_dist_attach(spk_ctx* ctx, uint32_t rank, uint32_t world, const SpkDistDescriptor* all_ranks /* [world] */);
+int spk_dist_detach(spk_ctx* ctx);
+int spk_dist_info(spk_ctx* ctx, uint32_t* num_halo_blocks, uint32_t* barrier_epoch);
+
 /* ---- read-back of the sparse grid in the reference's layouts (parity tests; ≙ the commented-out
  * check_active_blocks, cuda_sparse_grid.rs:491-652).  which_grid: 0 = curr, 1 = next. */
 int spk_grid_num_active_blocks(spk_ctx* ctx, int which_grid, uint32_t* out);

@@ -6,7 +6,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sparkl_b200 import abi, scenes
 from sparkl_b200.pipeline import context_from_scene
-from sparkl_b200.distributed import DistributedMpmPipeline
+from sparkl_b200.distributed import DistributedMpmPipeline, NvlinkMpmPipeline
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -17,11 +17,19 @@ edges = np.linspace(x.min(), x.max() + 1e-3, world + 1)
 mine = np.nonzero((x >= edges[rank]) & (x < edges[rank + 1]))[0]
 part = scenes.Scene(sc.name, sc.cell_width, sc.particles.take(mine), sc.models, sc.colliders, sc.gravity, sc.params)
 ctx = context_from_scene(part, device=local)
-pipe = DistributedMpmPipeline(ctx, dist, torch.device("cuda", local))
+mode = sys.argv[1] if len(sys.argv) > 1 else "nvlink"
 nsub = 0
-for _ in range(2):
-    sim, n = pipe.step(sc.params, sc.gravity)
-    nsub += n
+if mode == "nvlink":
+    pipe = NvlinkMpmPipeline(ctx, dist)
+    for _ in range(2):
+        sim, t = pipe.step(sc.params, sc.gravity)
+        nsub += t.num_substeps
+    pipe.halo_blocks_last = pipe.halo_blocks()
+else:
+    pipe = DistributedMpmPipeline(ctx, dist, torch.device("cuda", local))
+    for _ in range(2):
+        sim, n = pipe.step(sc.params, sc.gravity)
+        nsub += n
 pos = torch.zeros((len(sc.particles), 3), dtype=torch.float32, device="cuda")
 pos[torch.from_numpy(mine).cuda()] = torch.from_numpy(ctx.read(abi.ATTR_POSITION)["point"].copy()).cuda()
 dist.all_reduce(pos)
@@ -33,5 +41,5 @@ if rank == 0:
         nref += t.num_substeps
     want = ref.read(abi.ATTR_POSITION)["point"]
     err = np.abs(pos.cpu().numpy() - want).max() / sc.cell_width
-    print(f"multi-gpu check: world={world} substeps {nsub} vs {nref}, halo blocks {pipe.halo_blocks_last}, max |dx|/h = {err:.3e}", "OK" if err < 1e-4 and nsub == nref else "FAIL", flush=True)
+    print(f"multi-gpu check [{mode}]: world={world} substeps {nsub} vs {nref}, halo blocks {pipe.halo_blocks_last}, max |dx|/h = {err:.3e}", "OK" if err < 1e-4 and nsub == nref else "FAIL", flush=True)
 dist.destroy_process_group()

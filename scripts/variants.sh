@@ -7,7 +7,7 @@ mkdir -p build/variants
 if [ "$1" = build ]; then
   name=$2; shift 2
   objs=""
-  for f in spk_api spk_sort spk_g2p2g spk_grid; do
+  for f in spk_api spk_sort spk_g2p2g spk_grid spk_dist; do
     /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c sparkl_b200/csrc/$f.cu -o build/variants/${name}_$f.o &
     objs="$objs build/variants/${name}_$f.o"
   done

@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu"]
+SOURCES = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu", "spk_dist.cu"]
 HEADERS = ["spk_internal.cuh", "spk_device.cuh", "spk_math.cuh", "../../include/sparkl_abi.h"]
 LIB = os.path.join(HERE, "libsparkl_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

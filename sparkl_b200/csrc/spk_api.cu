@@ -42,6 +42,7 @@ uint32_t next_pow2(uint64_t v) {
 }
 
 void free_grid(GridBuffers& g) {
+    if (g.external_hash) { g.keys = nullptr; g.vals = nullptr; g.external_hash = 0; } // owned by the multi-GPU arena
     dev_free(g.keys); dev_free(g.vals); dev_free(g.blk_key); dev_free(g.blk_first); dev_free(g.blk_count); dev_free(g.blk_halo);
     dev_free(g.nbr_self); dev_free(g.nbr_prev); dev_free(g.vel); dev_free(g.acc); dev_free(g.proj); dev_free(g.cacheN); dev_free(g.cacheD);
 }
@@ -53,8 +54,14 @@ cudaError_t alloc_grid(spk_ctx* c, GridBuffers& g, uint32_t cap_hash) {
     g.cap_blocks = cap_hash / 2;
     const size_t nb = g.cap_blocks, nn = nb * 64;
     cudaError_t e;
-    if ((e = dev_alloc(g.keys, cap_hash)) != cudaSuccess) return e;
-    if ((e = dev_alloc(g.vals, cap_hash)) != cudaSuccess) return e;
+    if (c->dist_arena) {
+        // multi-GPU: the hash table lives in the arena shared with the peers and cannot move or grow
+        if (!spk_dist_grid_storage(c, (int)(&g - c->grid), cap_hash, &g.keys, &g.vals)) return cudaErrorMemoryAllocation;
+        g.external_hash = 1;
+    } else {
+        if ((e = dev_alloc(g.keys, cap_hash)) != cudaSuccess) return e;
+        if ((e = dev_alloc(g.vals, cap_hash)) != cudaSuccess) return e;
+    }
     if ((e = dev_alloc(g.blk_key, nb)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.blk_first, nb)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.blk_count, nb)) != cudaSuccess) return e;
@@ -254,6 +261,17 @@ int upload_range(spk_ctx* c, const SpkParticleStatus* status, const SpkParticleP
 
 } // namespace
 
+int spk_dist_realloc_grids(spk_ctx* c, uint32_t cap_hash) {
+    for (int g = 0; g < 2; ++g) CK(alloc_grid(c, c->grid[g], cap_hash));
+    CK(ensure_slot_scratch(c, cap_hash));
+    CK(ensure_dispatch(c));
+    c->gcur = 0;
+    c->sorted_valid = false;
+    c->dt_cache_valid = false;
+    CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+
 extern "C" {
 
 int spk_abi_version(void) { return SPK_ABI_VERSION; }
@@ -311,10 +329,14 @@ int spk_ctx_destroy(spk_ctx* c) {
     if (!c) return SPK_EINVAL;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    spk_dist_detach(c);
+    if (c->dist_arena) { c->grid[0].external_hash = c->grid[1].external_hash = 1; }
     free_particles(c);
     free_grid(c->grid[0]); free_grid(c->grid[1]);
     dev_free(c->slot_cnt); dev_free(c->dispatch); dev_free(c->models); dev_free(c->colliders); dev_free(c->d_counters);
     if (c->staging) cudaFree(c->staging);
+    if (c->dist_arena) cudaFree(c->dist_arena);
+    if (c->dist_peer_ids) cudaFree(c->dist_peer_ids);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_upload) cudaFreeHost(c->h_upload);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -523,6 +545,7 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
         if (rc) return rc;
         const DeviceCounters& hc = *c->h_counters;
         // grow-and-retry until the load factor is <= 50 % (cuda_sparse_grid.rs:162-253)
+        if ((hc.overflow || hc.nab > g.cap_blocks) && c->dist_arena) return SPK_EOVERFLOW; // the shared arena cannot grow
         if (hc.overflow || hc.nab > g.cap_blocks) {
             // jump straight to the size the particle count suggests (the reference's estimate, cuda_sparse_grid.rs:222-233)
             const uint64_t estimate = (uint64_t)next_pow2((uint64_t)c->n * 100 / (64 * 8 * 50)) * 4u;
@@ -572,6 +595,7 @@ int spk_stage_estimate_dt(spk_ctx* c, float min_dt, float max_dt, float* dt_out)
         }
     } else {
         CK(spk_launch_estimate_dt(c, min_dt, max_dt));
+        if (spk_dist_active(c)) CK(spk_dist_launch_barrier(c, 2)); // dt_acc <- min over the ranks
         int rc = read_counters(c);
         if (rc) return rc;
         if (c->n) c->dt_acc_host = c->h_counters->dt_acc;
@@ -618,6 +642,8 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
     if (timings) std::memset(timings, 0, sizeof(*timings));
     int rc;
     if ((rc = spk_frame_begin(c, params))) return rc;
+    const bool dist = spk_dist_active(c);
+    if (dist && c->n == 0) return SPK_ESTATE; // every rank takes part in the device-side barriers
     if (params->dt == 0.0f || c->n == 0) { // nothing to simulate (:305-309)
         if (simulated_time_out) *simulated_time_out = params->dt;
         return SPK_OK;
@@ -638,9 +664,18 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
         if (timings) CK(cudaEventRecord(ev[2], c->stream));
         float dt;
         if ((rc = spk_stage_estimate_dt(c, min_dt, std::fmin(remaining, params->max_substep_dt), &dt))) return rc;
+        if (dist) { // every rank has built its hash table and zeroed its grid: find the blocks shared with the peers
+            CK(spk_dist_launch_barrier(c, 0));
+            CK(spk_dist_launch_detect(c));
+        }
         if (timings) CK(cudaEventRecord(ev[3], c->stream));
         CK(spk_launch_g2p2g(c, dt));
         if (timings) CK(cudaEventRecord(ev[4], c->stream));
+        if (dist) { // NVLink red.add of the shared blocks into the peers, barrier (+ global dt minimum), fold what arrived
+            CK(spk_dist_launch_push(c));
+            CK(spk_dist_launch_barrier(c, 1));
+            CK(spk_dist_launch_merge(c));
+        }
         CK(spk_launch_grid_update(c, dt, gravity));
         if (timings) {
             CK(cudaEventRecord(ev[5], c->stream));

@@ -1,0 +1,291 @@
+// spk_dist.cu — multi-GPU halo accumulation over NVLink peer memory, one process per GPU.
+//
+// Replaces the reference's multi-GPU machinery: the host-side gather of every device's active block
+// headers (src/cuda/cuda_sparse_grid.rs:256-322), K3/K4 halo tagging, K17 `copy_halo_to_staging`, one
+// cuMemcpyDtoDAsync per device pair (src/cuda/cuda_mpm_pipeline.rs:458-472), K18 `merge_halo_blocks` and the host loop
+// that takes the dt minimum (:393-398).  Semantics are unchanged: a block active on several ranks ends the substep with
+// the full sum on every one of them, dt is the minimum over ranks.
+//
+// B200 design: every rank shares ONE device arena with its peers through CUDA IPC (mapped over NVLink / NVSwitch):
+//     [mailbox | hash keys, hash vals, halo accumulators (hacc) of grid buffer 0 | the same for grid buffer 1]
+// and all cross-GPU traffic is device-initiated:
+//   * detect : every rank probes its peers' hash tables directly (P2P loads) for its own active block keys — no key
+//              lists travel, no host round trip; the result is a per-block table of the peer's block ids.
+//   * push   : after G2P2G a rank adds the accumulators of its shared blocks straight into the peers' `hacc` arrays with
+//              NVLink atomics (red.add.f32), addressed by the peer's own block ids — no pack / staging / unpack.
+//   * merge  : each rank folds its `hacc` into its grid and clears it.
+//   * barrier: a one-CTA kernel writes an epoch flag (+ the dt candidate) into every peer's mailbox and spins on its own
+//              mailbox; two per substep.  The dt minimum rides on the second one.
+// The host never blocks for the exchange: the only read-back per substep is the 64-byte counter record of the sort.
+#include <cstdio>
+#include <cstring>
+
+#include "spk_device.cuh"
+
+#define CK(expr)                               \
+    do {                                       \
+        cudaError_t _e = (expr);               \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+namespace {
+
+constexpr size_t MAILBOX_BYTES = 4096;
+constexpr size_t ALIGN = 1024;
+__host__ __device__ inline size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
+// arena layout as a function of the hash capacity (identical arithmetic on the owner and on every peer)
+__host__ __device__ inline size_t arena_grid_bytes(uint32_t cap_hash) {
+    return align_up((size_t)cap_hash * 8) + align_up((size_t)cap_hash * 4) + align_up((size_t)(cap_hash / 2) * SPK_ACC_CHANNELS * 64 * 4);
+}
+__host__ __device__ inline size_t arena_bytes(uint32_t cap_hash) { return MAILBOX_BYTES + 2 * arena_grid_bytes(cap_hash); }
+__host__ __device__ inline DistGridView arena_grid(char* base, uint32_t cap_hash, int g) {
+    char* p = base + MAILBOX_BYTES + (size_t)g * arena_grid_bytes(cap_hash);
+    DistGridView v;
+    v.keys = reinterpret_cast<unsigned long long*>(p);
+    p += align_up((size_t)cap_hash * 8);
+    v.vals = reinterpret_cast<uint32_t*>(p);
+    p += align_up((size_t)cap_hash * 4);
+    v.hacc = reinterpret_cast<float*>(p);
+    return v;
+}
+
+struct DescriptorWire { // what travels in SpkDistDescriptor (opaque to the caller)
+    cudaIpcMemHandle_t handle;
+    uint32_t cap_hash;
+    uint32_t device;
+    unsigned long long bytes;
+    uint32_t magic;
+};
+static_assert(sizeof(DescriptorWire) <= sizeof(SpkDistDescriptor), "descriptor too small");
+constexpr uint32_t MAGIC = 0x53504b44u; // "SPKD"
+
+__device__ __forceinline__ void st_sys_u32(volatile uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Cross-GPU barrier + small all-to-all of one 64-bit value.  One CTA; thread p talks to peer p.
+//   mode 0: plain barrier, publishes `gnext` (which grid buffer is this rank's next grid)
+//   mode 1: additionally min-reduces counters->dt_raw_bits over the ranks (fused CFL reduction of g2p2g)
+//   mode 2: additionally min-reduces counters->dt_acc over the ranks (stand-alone estimate_dt kernel)
+__global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext, int mode, DeviceCounters* counters) {
+    const uint32_t p = threadIdx.x;
+    const uint32_t slot = epoch & 1u;
+    unsigned long long mine = 0;
+    if (mode == 1) mine = counters->dt_raw_bits;
+    else if (mode == 2) mine = counters->dt_acc;
+    __shared__ unsigned long long s_val[SPK_MAX_RANKS];
+    if (p < d.world) {
+        s_val[p] = mine;
+        if (p != d.rank) {
+            DistMailbox* remote = d.peer_mailbox[p];
+            remote->val[slot][d.rank] = mine;
+            remote->gnext[slot][d.rank] = gnext;
+            __threadfence_system(); // payload (and everything this rank wrote before, incl. NVLink atomics) before the flag
+            st_sys_u32(&remote->flag[d.rank], epoch);
+            const long long t0 = clock64();
+            while ((int)(ld_sys_u32(&d.mailbox->flag[p]) - epoch) < 0) {
+                if (clock64() - t0 > 6000000000ll) { counters->overflow = 0x100u + p; break; } // ~3 s: a peer died; never hang the GPU
+                __nanosleep(64);
+            }
+            __threadfence_system();
+            s_val[p] = __ldcv(&d.mailbox->val[slot][p]);
+        }
+    }
+    __syncthreads();
+    if (p == 0 && mode != 0) {
+        unsigned long long m = s_val[0];
+        for (uint32_t r = 1; r < d.world; ++r) m = s_val[r] < m ? s_val[r] : m;
+        if (mode == 1) counters->dt_raw_bits = (uint32_t)m;
+        else counters->dt_acc = m;
+    }
+}
+
+// For every active block of this rank and every peer: the peer's id of the same block key (probe of the peer's hash
+// table over NVLink), -1 when the peer does not hold it.  Shared blocks are tagged IS_HALO (tag_halo_blocks, sort.rs:74-96).
+__global__ void __launch_bounds__(256) dist_detect_kernel(DistState d, GridBuffers next, uint32_t nab, uint32_t epoch, int32_t* peer_ids, DeviceCounters* counters) {
+    const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t b = t / d.world, p = t % d.world;
+    if (b >= nab) return;
+    int32_t id = -1;
+    if (p != d.rank) {
+        const uint32_t g = __ldcv(&d.mailbox->gnext[epoch & 1u][p]) & 1u;
+        const unsigned long long* keys = d.peer_grid[p][g].keys;
+        const uint32_t cap = d.peer_cap_hash[p], mask = cap - 1;
+        const unsigned long long key = next.blk_key[b];
+        // GridHashMap::get (hashmap.rs:72-87) on the PEER's table: volatile loads, never served from a stale L1 line
+        uint32_t slot = spk_hash(key, mask);
+        for (uint32_t probe = 0; probe < cap; ++probe) {
+            const unsigned long long k = __ldcv(&keys[slot]);
+            if (k == key) { id = (int32_t)__ldcv(&d.peer_grid[p][g].vals[slot]); break; }
+            if (k == SPK_EMPTY_KEY) break;
+            slot = (slot + 1) & mask;
+        }
+        if ((uint32_t)id >= cap / 2) id = -1;
+        if (id >= 0 && atomicExch(&next.blk_halo[b], 1u) == 0u) atomicAdd(&counters->num_halo, 1u);
+    }
+    peer_ids[(size_t)b * d.world + p] = id;
+}
+
+// One CTA per active block; shared blocks add their six accumulated channels into each holder's `hacc` (NVLink red.add).
+__global__ void __launch_bounds__(128) dist_push_kernel(DistState d, GridBuffers next, uint32_t nab, uint32_t epoch, const int32_t* __restrict__ peer_ids) {
+    const uint32_t b = blockIdx.x;
+    if (b >= nab || !(next.blk_halo[b] & 1u)) return;
+    const float* acc = next.acc + (size_t)b * (SPK_ACC_CHANNELS * 64);
+    float v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = acc[threadIdx.x + k * 128];
+    for (uint32_t p = 0; p < d.world; ++p) {
+        const int32_t id = peer_ids[(size_t)b * d.world + p];
+        if (id < 0) continue;
+        const uint32_t g = __ldcv(&d.mailbox->gnext[epoch & 1u][p]) & 1u;
+        float* dst = d.peer_grid[p][g].hacc + (size_t)id * (SPK_ACC_CHANNELS * 64);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (v[k] != 0.f) atomicAdd(dst + threadIdx.x + k * 128, v[k]);
+    }
+    __threadfence_system();
+}
+
+// merge_halo_blocks (sort.rs:142-164): fold what the peers pushed into this rank's grid, clear the staging for the next use
+__global__ void __launch_bounds__(128) dist_merge_kernel(GridBuffers next, uint32_t nab, float* hacc) {
+    const uint32_t b = blockIdx.x;
+    if (b >= nab || !(next.blk_halo[b] & 1u)) return;
+    float* acc = next.acc + (size_t)b * (SPK_ACC_CHANNELS * 64);
+    float* h = hacc + (size_t)b * (SPK_ACC_CHANNELS * 64);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t i = threadIdx.x + k * 128;
+        acc[i] += __ldcg(&h[i]);
+        h[i] = 0.f;
+    }
+}
+
+} // namespace
+
+bool spk_dist_active(const spk_ctx* c) { return c->dist.world > 1; }
+
+// hash keys / vals of grid buffer `g` live in the shared arena once spk_dist_export has run
+bool spk_dist_grid_storage(spk_ctx* c, int g, uint32_t cap_hash, unsigned long long** keys, uint32_t** vals) {
+    if (!c->dist_arena || cap_hash != c->dist_cap_hash) return false;
+    DistGridView v = arena_grid(c->dist_arena, c->dist_cap_hash, g);
+    *keys = v.keys;
+    *vals = v.vals;
+    return true;
+}
+
+cudaError_t spk_dist_launch_barrier(spk_ctx* c, int mode) {
+    DistState& d = c->dist;
+    d.epoch += 1;
+    dist_barrier_kernel<<<1, SPK_MAX_RANKS, 0, c->stream>>>(d, d.epoch, (uint32_t)(1 - c->gcur), mode, c->d_counters);
+    c->launches += 1;
+    c->counters_fresh = false;
+    return cudaGetLastError();
+}
+cudaError_t spk_dist_launch_detect(spk_ctx* c) {
+    DistState& d = c->dist;
+    GridBuffers& next = c->grid[1 - c->gcur];
+    const uint32_t nab = next.nab_host;
+    cudaError_t e = cudaMemsetAsync(&c->d_counters->num_halo, 0, 4, c->stream);
+    if (e != cudaSuccess || !nab) return e;
+    dist_detect_kernel<<<(nab * d.world + 255) / 256, 256, 0, c->stream>>>(d, next, nab, d.epoch, c->dist_peer_ids, c->d_counters);
+    c->launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t spk_dist_launch_push(spk_ctx* c) {
+    DistState& d = c->dist;
+    GridBuffers& next = c->grid[1 - c->gcur];
+    if (!next.nab_host) return cudaSuccess;
+    dist_push_kernel<<<next.nab_host, 128, 0, c->stream>>>(d, next, next.nab_host, d.epoch, c->dist_peer_ids);
+    c->launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t spk_dist_launch_merge(spk_ctx* c) {
+    GridBuffers& next = c->grid[1 - c->gcur];
+    if (!next.nab_host) return cudaSuccess;
+    dist_merge_kernel<<<next.nab_host, 128, 0, c->stream>>>(next, next.nab_host, arena_grid(c->dist_arena, c->dist_cap_hash, 1 - c->gcur).hacc);
+    c->launches += 1;
+    return cudaGetLastError();
+}
+
+extern "C" {
+
+int spk_dist_export(spk_ctx* c, SpkDistDescriptor* out) {
+    if (!c || !out) return SPK_EINVAL;
+    if (c->dist_arena) return SPK_ESTATE;
+    CK(cudaSetDevice(c->device));
+    // the shared arena has a fixed capacity: size it generously from what the particle count suggested (growth of the hash
+    // map would move it and invalidate the peers' mappings, so in distributed runs an overflow is an error instead)
+    const uint32_t cap = std::max(c->grid[0].cap_hash, c->grid[1].cap_hash) * 2u;
+    const size_t bytes = arena_bytes(cap);
+    char* arena = nullptr;
+    CK(cudaMalloc((void**)&arena, bytes));
+    CK(cudaMemsetAsync(arena, 0, bytes, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->dist_arena = arena;
+    c->dist_cap_hash = cap;
+    c->dist_arena_bytes = bytes;
+    // both grid buffers move their hash tables into the arena (their contents are rebuilt by the next sort)
+    int rc = spk_dist_realloc_grids(c, cap);
+    if (rc) return rc;
+    CK(cudaMalloc((void**)&c->dist_peer_ids, (size_t)(cap / 2) * SPK_MAX_RANKS * sizeof(int32_t)));
+    DescriptorWire w;
+    std::memset(&w, 0, sizeof(w));
+    CK(cudaIpcGetMemHandle(&w.handle, arena));
+    w.cap_hash = cap;
+    w.device = (uint32_t)c->device;
+    w.bytes = bytes;
+    w.magic = MAGIC;
+    std::memset(out, 0, sizeof(*out));
+    std::memcpy(out, &w, sizeof(w));
+    return SPK_OK;
+}
+
+int spk_dist_attach(spk_ctx* c, uint32_t rank, uint32_t world, const SpkDistDescriptor* all) {
+    if (!c || !all || world < 1 || world > SPK_MAX_RANKS || rank >= world) return SPK_EINVAL;
+    if (!c->dist_arena || c->dist.world) return SPK_ESTATE;
+    CK(cudaSetDevice(c->device));
+    DistState d;
+    std::memset(&d, 0, sizeof(d));
+    d.rank = rank;
+    d.world = world;
+    d.mailbox = reinterpret_cast<DistMailbox*>(c->dist_arena);
+    for (uint32_t p = 0; p < world; ++p) {
+        DescriptorWire w;
+        std::memcpy(&w, &all[p], sizeof(w));
+        if (w.magic != MAGIC) return SPK_EINVAL;
+        char* base = c->dist_arena;
+        if (p != rank) {
+            void* mapped = nullptr;
+            CK(cudaIpcOpenMemHandle(&mapped, w.handle, cudaIpcMemLazyEnablePeerAccess));
+            base = (char*)mapped;
+            c->dist_mapped[p] = mapped;
+        }
+        d.peer_mailbox[p] = reinterpret_cast<DistMailbox*>(base);
+        d.peer_cap_hash[p] = w.cap_hash;
+        for (int g = 0; g < 2; ++g) d.peer_grid[p][g] = arena_grid(base, w.cap_hash, g);
+    }
+    c->dist = d;
+    return SPK_OK;
+}
+
+int spk_dist_detach(spk_ctx* c) {
+    if (!c) return SPK_EINVAL;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (uint32_t p = 0; p < SPK_MAX_RANKS; ++p)
+        if (c->dist_mapped[p]) { cudaIpcCloseMemHandle(c->dist_mapped[p]); c->dist_mapped[p] = nullptr; }
+    std::memset(&c->dist, 0, sizeof(c->dist));
+    return SPK_OK;
+}
+
+int spk_dist_info(spk_ctx* c, uint32_t* num_halo_blocks, uint32_t* epoch) {
+    if (!c) return SPK_EINVAL;
+    if (num_halo_blocks) *num_halo_blocks = c->h_counters->num_halo;
+    if (epoch) *epoch = c->dist.epoch;
+    return SPK_OK;
+}
+
+} // extern "C"

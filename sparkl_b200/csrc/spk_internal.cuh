@@ -73,6 +73,7 @@ struct GridBuffers { // one of the two sparse-grid buffers (curr / next)
     uint32_t* proj;  // [cap_blocks*64] projection status: tag | collider << 2
     float4* cacheN;  // collision_normal.xyz, prev_mass
     float4* cacheD;  // projection_scaled_dir.xyz, unused
+    uint32_t external_hash; // keys / vals live in the shared multi-GPU arena (not owned by this struct)
     uint32_t nab_host;      // host copy of the number of active blocks
     uint32_t has_velocity;  // 1 after grid_update (momentum_velocity holds velocities)
 };
@@ -92,6 +93,22 @@ struct DeviceCounters { // one 64-byte record read back once per substep (pinned
 #define SPK_DT_RAW_NONE 0x7f7f7f7fu /* memset pattern; valid candidates are capped at 1e30f */
 
 struct DispatchEntry { uint32_t block; uint32_t first; uint32_t count; uint32_t pad; };
+
+// ---- multi-GPU over NVLink peer memory (spk_dist.cu) ---------------------------------------------------------------
+#define SPK_MAX_RANKS 16
+struct DistMailbox { // first 4 KB of every rank's shared arena; written by the peers
+    volatile uint32_t flag[SPK_MAX_RANKS];        // flag[p]: last barrier epoch signalled by rank p
+    uint32_t gnext[2][SPK_MAX_RANKS];             // [epoch & 1][p]: which grid buffer is rank p's next grid
+    unsigned long long val[2][SPK_MAX_RANKS];     // [epoch & 1][p]: rank p's dt candidate
+};
+struct DistGridView { unsigned long long* keys; uint32_t* vals; float* hacc; }; // one grid buffer's shared arrays
+struct DistState {   // passed by value to the kernels
+    uint32_t rank, world, epoch, pad;
+    DistMailbox* mailbox;                          // this rank's
+    DistMailbox* peer_mailbox[SPK_MAX_RANKS];      // peer-mapped
+    DistGridView peer_grid[SPK_MAX_RANKS][2];      // peer-mapped (entry [rank] = this rank's own)
+    uint32_t peer_cap_hash[SPK_MAX_RANKS];
+};
 
 struct spk_ctx {
     int device;
@@ -127,6 +144,11 @@ struct spk_ctx {
     bool counters_fresh;         // h_counters was read after the last kernel that writes d_counters
     // scratch for read-back / staging
     void* staging; size_t staging_bytes;
+    // multi-GPU (all zero / null in single-GPU runs)
+    DistState dist;
+    char* dist_arena; size_t dist_arena_bytes; uint32_t dist_cap_hash;
+    int32_t* dist_peer_ids;              // [cap_blocks][world]: the peer's id of each of this rank's active blocks, -1 if absent
+    void* dist_mapped[SPK_MAX_RANKS];    // cudaIpcOpenMemHandle results (to close)
     // timing
     cudaEvent_t ev[12];
     uint32_t launches;
@@ -149,3 +171,11 @@ cudaError_t spk_launch_halo_keys(spk_ctx* c, unsigned long long* out, uint32_t c
 cudaError_t spk_launch_halo_tag(spk_ctx* c, const unsigned long long* remote, uint32_t n);
 cudaError_t spk_launch_halo_pack(spk_ctx* c, unsigned long long* keys, float* payload, uint32_t capacity);
 cudaError_t spk_launch_halo_merge(spk_ctx* c, const unsigned long long* keys, const float* payload, uint32_t n);
+// spk_dist.cu
+bool spk_dist_active(const spk_ctx* c);
+bool spk_dist_grid_storage(spk_ctx* c, int g, uint32_t cap_hash, unsigned long long** keys, uint32_t** vals);
+int spk_dist_realloc_grids(spk_ctx* c, uint32_t cap_hash); // defined in spk_api.cu
+cudaError_t spk_dist_launch_barrier(spk_ctx* c, int mode); // 0 barrier, 1 + min of dt_raw_bits, 2 + min of dt_acc
+cudaError_t spk_dist_launch_detect(spk_ctx* c);
+cudaError_t spk_dist_launch_push(spk_ctx* c);
+cudaError_t spk_dist_launch_merge(spk_ctx* c);

@@ -144,3 +144,35 @@ class DistributedMpmPipeline:
             if remaining <= np.float32(10.0) / np.float32(1.0e12) or params.stop_after_one_substep:
                 break
         return float(np.float32(params.dt) - remaining), n
+
+
+class NvlinkMpmPipeline:
+    """The product multi-GPU path: halo accumulation and the dt minimum run inside `spk_step` with device-initiated NVLink
+    loads / atomics on peer memory (sparkl_b200/csrc/spk_dist.cu).  torch.distributed is used ONCE, to all-gather the
+    128-byte IPC descriptors; no collective runs in the substep loop.  Every rank must own particles and make the same
+    sequence of step calls."""
+
+    def __init__(self, ctx, dist=None):
+        import torch.distributed as tdist
+        self.ctx, self.dist = ctx, dist or tdist
+        self.world, self.rank = self.dist.get_world_size(), self.dist.get_rank()
+        desc = (C.c_ubyte * 128)()
+        ctx._call("dist_export", C.cast(desc, C.c_void_p))
+        mine = bytes(desc)
+        every = [None] * self.world
+        self.dist.all_gather_object(every, mine)
+        blob = (C.c_ubyte * (128 * self.world)).from_buffer_copy(b"".join(every))
+        ctx._call("dist_attach", self.rank, self.world, C.cast(blob, C.c_void_p))
+        self.dist.barrier()  # every rank has mapped every arena before the first device-side barrier
+
+    def step(self, params: abi.SolverParameters, gravity, timings: bool = True):
+        """one frame; returns (simulated_time, StepTimings) like SingleGpuMpmContext.step"""
+        return self.ctx.step(params, gravity, timings)
+
+    def halo_blocks(self) -> int:
+        n, e = C.c_uint32(), C.c_uint32()
+        self.ctx._call("dist_info", C.byref(n), C.byref(e))
+        return n.value
+
+    def close(self):
+        self.ctx._call("dist_detach")
