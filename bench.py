@@ -31,7 +31,7 @@ UNIT = "particle-substeps/s"
 # particle records R112 + W108 + ParticleData R16+W16 = 252, plus grid (72 R + 24 W) * 64 / 512 = 12
 A_G2P2G_SAND = 264.0
 FULL = (200, 100, 100)       # per-GPU lattice (x2 stacked) = 4,000,000 particles
-CPU_SAMPLE = (50, 25, 25)    # bounded CPU sample of the same scene = 62,500 particles
+CPU_SAMPLE = (100, 50, 50)   # bounded CPU sample = the reference's own sand3 size (examples3d/sand3.rs:51-71): 500,000 particles
 
 
 def _peaks():
@@ -43,32 +43,52 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    """samples SM clocks / throttle reasons during the timed region: NVML in-process (1 kHz) when available, else nvidia-smi"""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.sm, self.mx, self.mask, self._halt = index, [], [], 0, threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._halt.is_set():
             try:
+                if self.nvml is not None:
+                    self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)))
+                    try:
+                        self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self._halt.wait(0.001)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                for (name, bit), v in zip(self.REASONS.items(), r[2:6]):
+                    if v.lower().startswith("active"):
+                        self.mask |= bit
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def finish(self):
         self._halt.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+        reasons = sorted(n for n, bit in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": reasons,
+                "samples": len(self.sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_scene(rank, world, dims):
@@ -215,30 +235,35 @@ def run_ours(args):
     value = npart * world * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers: upload (pinned H2D) -> one frame -> read back pos/vel/phase
+    # into pinned host buffers; every rank does it for its own slab, the frame time is the max over ranks
     e2e = None
-    if world == 1:
+    if args.e2e_frames > 0:
         host = sc.particles
         pins = [pinned_like(a) for a in (host.status, host.position, host.velocity, host.volume, host.phase, host.data)]
         pc = abi.ParticleComponents(0)
         pc.status, pc.position, pc.velocity, pc.volume, pc.phase, pc.data = [p[0] for p in pins]
+        outs = {w: pinned_like(np.empty(npart, abi.ATTR_DTYPES[w])) for w in (abi.ATTR_POSITION, abi.ATTR_VELOCITY, abi.ATTR_PHASE)}
         frame = abi.SolverParameters()
         h2d = sum(p[0].nbytes for p in pins)
-        d2h = npart * (12 + 12 + 8)
+        d2h = sum(o[0].nbytes for o in outs.values())
         subs = 0
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_frames):
             ctx.upload(pc)
-            _, t = ctx.step(frame, sc.gravity, timings=False)
-            ctx.read(abi.ATTR_POSITION); ctx.read(abi.ATTR_VELOCITY); ctx.read(abi.ATTR_PHASE)
-            subs += 1
-        torch.cuda.synchronize()
+            _, t = ctx.step(frame, sc.gravity)
+            subs += t.num_substeps
+            for w, o in outs.items():
+                ctx.read(w, out=o[0])
+        barrier()
         wall = time.perf_counter() - t0
-        # substeps per frame: dt = 1/60 at the CFL step of this scene
-        _, t = ctx.step(frame, sc.gravity)
-        per_frame = t.num_substeps
-        e2e = {"value": npart * per_frame * args.e2e_frames / wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "step": f"spk_particles_upload (pinned host) + spk_step(dt=1/60: {per_frame} substeps) + spk_particles_read(pos, vel, phase)",
+        if world > 1:
+            tt = torch.tensor([wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            wall = float(tt.item())
+        e2e = {"value": npart * world * subs / wall, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "step": f"per rank: spk_particles_upload (pinned host, all 6 attributes) + spk_step(dt=1/60: {subs // args.e2e_frames} substeps) + "
+                       "spk_particles_read(pos, vel, phase) into pinned host buffers",
                "frames": args.e2e_frames, "ms_per_frame": wall * 1e3 / args.e2e_frames}
 
     if rank != 0:
@@ -255,7 +280,7 @@ def run_ours(args):
                 "stage_ms_per_substep": dict(zip(["sort", "reset_grid", "estimate_dt", "g2p2g", "grid_update"], (stage_ms / args.steps).round(4).tolist()))}
     base = None
     if world == 1 and not args.no_cpu_baseline:
-        base, _ = cpu_baseline(2, 1)
+        base, _ = cpu_baseline(12, 1)  # ~10-20 s of host time
     ref_gpu = None
     if world == 1 and not args.no_ref_gpu:
         ref_gpu = reference_gpu(sc, args.settle, min(args.steps, 10))

@@ -9,8 +9,16 @@ from sparkl_b200.pipeline import context_from_scene
 from sparkl_b200.distributed import DistributedMpmPipeline, NvlinkMpmPipeline
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+# SPK_CHECK_ONE_GPU=1: every rank on cuda:0 (time-sliced), gloo for the descriptor exchange — lets the single-GPU test tier
+# exercise the peer-memory path (tests/test_nvlink_gpu.py)
+one_gpu = os.environ.get("SPK_CHECK_ONE_GPU") == "1"
+if one_gpu:
+    local = 0
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if one_gpu:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 sc = scenes.jitter(scenes.sand3(24, 8, 8), 0.02, seed=9)
 x = sc.particles.position["point"][:, 0]
 edges = np.linspace(x.min(), x.max() + 1e-3, world + 1)
@@ -30,8 +38,9 @@ else:
     for _ in range(2):
         sim, n = pipe.step(sc.params, sc.gravity)
         nsub += n
-pos = torch.zeros((len(sc.particles), 3), dtype=torch.float32, device="cuda")
-pos[torch.from_numpy(mine).cuda()] = torch.from_numpy(ctx.read(abi.ATTR_POSITION)["point"].copy()).cuda()
+dev = "cpu" if one_gpu else "cuda"
+pos = torch.zeros((len(sc.particles), 3), dtype=torch.float32, device=dev)
+pos[torch.from_numpy(mine).to(dev)] = torch.from_numpy(ctx.read(abi.ATTR_POSITION)["point"].copy()).to(dev)
 dist.all_reduce(pos)
 if rank == 0:
     ref = context_from_scene(sc, device=local)

@@ -137,11 +137,12 @@ cudaError_t alloc_particles(spk_ctx* c, size_t cap) {
 // ---- pack: reference AoS-per-attribute arrays -> internal float4 streams (ids first..first+n) --------------------
 __global__ void pack_kernel(ParticleBuffers pb, float4* vel, float4* cold, const SpkParticleStatus* status, const SpkParticlePosition* pos,
                             const SpkParticleVelocity* v, const SpkParticleVolume* volume, const SpkParticlePhase* phase, const SpkParticleData* data,
-                            size_t first, size_t n) {
+                            size_t first, size_t n, uint32_t* bad_flag) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const size_t i = first + k;
     const SpkParticleStatus st = status[k];
+    if (st.model_index >= (1u << 24)) *bad_flag = 1u; // the flags word keeps 24 bits of model index
     const SpkParticleVolume vo = volume[k];
     const uint32_t flags = (st.failed ? SPK_F_FAILED : 0u) | (st.is_static ? SPK_F_STATIC : 0u) | (st.kinematic_vel_enabled ? SPK_F_KINEMATIC : 0u) |
                            ((uint32_t)st.model_index << SPK_F_MODEL_SHIFT);
@@ -253,9 +254,15 @@ int upload_range(spk_ctx* c, const SpkParticleStatus* status, const SpkParticleP
     if (data) { d_data = cur; CK(put(data, n * sizeof(SpkParticleData), cur)); }
     pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->pb[c->cur], c->vel, c->cold, (const SpkParticleStatus*)d_status, (const SpkParticlePosition*)d_pos,
                                                                      (const SpkParticleVelocity*)d_vel, (const SpkParticleVolume*)d_volume,
-                                                                     (const SpkParticlePhase*)d_phase, (const SpkParticleData*)d_data, first, n);
+                                                                     (const SpkParticlePhase*)d_phase, (const SpkParticleData*)d_data, first, n, &c->d_counters->pad[0]);
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_upload + 1, &c->d_counters->pad[0], 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream)); // host arrays may be pageable: keep the call synchronous like CudaVec::from_slice
+    if (*(uint32_t*)(c->h_upload + 1)) { // a model index does not fit (validated on the device: no host pass over the arrays)
+        CK(cudaMemsetAsync(&c->d_counters->pad[0], 0, 4, c->stream));
+        c->n = first;
+        return SPK_EINVAL;
+    }
     return SPK_OK;
 }
 
@@ -354,7 +361,6 @@ int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkP
     if (!c || (n && (!status || !pos || !vel || !volume || !phase))) return SPK_EINVAL;
     if (n >= 0xffffffffull) return SPK_EOVERFLOW;
     CK(cudaSetDevice(c->device));
-    for (size_t i = 0; i < n; ++i) if (status[i].model_index >= (1u << 24)) return SPK_EINVAL;
     if (n > c->cap) CK(alloc_particles(c, n + n / 8 + 1024));
     c->n = n;
     c->cur = 0;
@@ -395,7 +401,6 @@ int spk_particles_append(spk_ctx* c, const SpkParticleStatus* status, const SpkP
     CK(cudaSetDevice(c->device));
     const size_t old_n = c->n, new_n = old_n + n;
     if (new_n >= 0xffffffffull) return SPK_EOVERFLOW;
-    for (size_t i = 0; i < n; ++i) if (status[i].model_index >= (1u << 24)) return SPK_EINVAL;
     if (new_n > c->cap) {
         // grow: read everything back in id order, reallocate, upload again (cold path; CudaVec::append reallocates too)
         std::vector<SpkParticleStatus> s(new_n); std::vector<SpkParticlePosition> p(new_n); std::vector<SpkParticleVelocity> v(new_n);

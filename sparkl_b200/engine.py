@@ -74,9 +74,14 @@ class Engine:
         self._call("particles_len", C.byref(n))
         return n.value
 
-    def read(self, which: int, n: int | None = None) -> np.ndarray:
+    def read(self, which: int, n: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        """read one attribute back in particle-id order; `out` may be a caller-owned (e.g. pinned) buffer of the attribute's
+        dtype, which makes the device->host copy run at full PCIe rate (the testbed's frame read-back, testbed_plugin.rs:533-588)"""
         n = len(self) if n is None else n
-        out = np.zeros(n, abi.ATTR_DTYPES[which])
+        if out is None:
+            out = np.empty(n, abi.ATTR_DTYPES[which])
+        elif out.dtype != abi.ATTR_DTYPES[which] or len(out) < n or not out.flags.c_contiguous:
+            raise abi.SparklError(abi.EINVAL, "output buffer has the wrong dtype / length")
         if n:
             self._call("particles_read", which, _ptr(out), n)
         return out

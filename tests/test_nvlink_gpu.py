@@ -1,0 +1,24 @@
+"""The multi-GPU product path (sparkl_b200/csrc/spk_dist.cu: CUDA-IPC arena, device-side barriers, peer hash probes,
+red.add halo push) on the single-GPU test tier: two processes share cuda:0 (time-sliced), map each other's arena through
+CUDA IPC exactly as they would across NVLink, and must reproduce the single-context result (scripts/check_multi_gpu.py).
+The 2/4/8-GPU runs of the same script are recorded in profiles/."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_ranks_peer_memory_path_matches_single_context():
+    env = dict(os.environ, SPK_CHECK_ONE_GPU="1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(ROOT, "scripts", "check_multi_gpu.py"), "nvlink"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    line = [l for l in out.splitlines() if "multi-gpu check" in l]
+    assert line and line[-1].rstrip().endswith("OK"), out[-3000:]
+    assert "halo blocks 0," not in line[-1], "the two slabs must share blocks"
