@@ -27,6 +27,12 @@ CASES = {
     "fluids3": ("fluids3", (12, 8, 8), 0.01, 12, 8, (0, 3, 7)),
     "neo_hookean_block": ("neo_hookean_block", (10, 10, 6), 0.002, 13, 8, (0, 3, 7)),
     "cube_through_sand3": ("cube_through_sand3", (10, 5, 6, 4), 0.02, 14, 8, (0, 3, 7)),
+    # the plasticity / failure models no example scene reaches (pre-strained block, scenes.model_block)
+    "nacc": ("model_block", ("nacc", 8, 8, 6), 0.01, 15, 8, (0, 3, 7)),
+    "rankine": ("model_block", ("rankine", 8, 8, 6), 0.01, 16, 8, (0, 3, 7)),
+    "snow": ("model_block", ("snow", 8, 8, 6), 0.01, 17, 8, (0, 3, 7)),
+    "failure": ("model_block", ("failure", 8, 8, 6), 0.01, 18, 8, (0, 3, 7)),
+    "failure_split": ("model_block", ("failure_split", 8, 8, 6), 0.01, 19, 8, (0, 3, 7)),
 }
 
 

@@ -121,6 +121,39 @@ def neo_hookean_block(ni=40, nj=40, nk=20, x_offset=0.0, with_floor=True) -> Sce
     return Scene("neo_hookean_block", h, pc, models, cols, params=SolverParameters(max_substep_dt=1.5e-3))
 
 
+def model_block(kind: str, ni=8, nj=8, nk=6, seed: int = 21) -> Scene:
+    """A small pre-strained block dropped on a cuboid floor for the plasticity / failure models the example scenes of
+    scenes.py do not reach: `kind` in nacc | rankine | snow | failure | failure_split.  Model parameters follow the
+    reference's 2D examples (examples2d/basic2.rs:43-46,91-94, examples2d/elasticity2.rs:68-71, l_panel2.rs:49-52).
+    Every particle starts with a seeded random deformation gradient (stretch up to +-8 %, small shear) so the return
+    mappings and the failure criterion fire from the first substep on."""
+    from .abi import MaximumStressFailure, NaccPlasticity, RankinePlasticity, SnowPlasticity
+    E, NU = 1.0e6, 0.3
+    h = 0.2
+    r = np.float32(h) / np.float32(4.0)
+    if kind == "nacc":
+        model = ParticleModel.with_plasticity(NeoHookeanElasticity(E, NU), NaccPlasticity(E, NU, 0.04, True, 3.0, np.radians(40.0)))
+    elif kind == "rankine":
+        model = ParticleModel.with_plasticity(CorotatedLinearElasticity(E, NU), RankinePlasticity(E, NU, 1.0e2, 5.0))
+    elif kind == "snow":
+        model = ParticleModel.with_plasticity(CorotatedLinearElasticity(E, NU), SnowPlasticity())
+    elif kind in ("failure", "failure_split"):
+        c = CorotatedLinearElasticity(E, NU)
+        c.split_stress_on_failure = kind == "failure_split"
+        model = ParticleModel(c, None, MaximumStressFailure(2.0e4, 3.0e38))
+    else:
+        raise ValueError(kind)
+    pc = cube_particles((0.0, 2.6, 0.0), ni, nj, nk, 0, r, 1000.0)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = len(pc)
+    F = np.tile(np.eye(3, dtype=np.float32), (n, 1, 1)) + rng.uniform(-0.08, 0.08, (n, 3, 3)).astype(np.float32) * np.array(
+        [[1.0, 0.3, 0.3], [0.3, 1.0, 0.3], [0.3, 0.3, 1.0]], np.float32)
+    pc.volume["deformation_gradient"] = F.transpose(0, 2, 1).reshape(n, 9)  # column-major like nalgebra
+    ext = 2.0 * float(r)
+    cols = box_colliders((-4.0, 2.0, -4.0), (ni * ext + 4.0, 2.0 + nj * ext + 8.0, nk * ext + 4.0), walls=False)
+    return Scene("model_block_" + kind, h, pc, [model], cols, params=SolverParameters(max_substep_dt=1.0e-3))
+
+
 def jitter(scene: Scene, amplitude: float, seed: int = 42) -> Scene:
     """Uniform position jitter (numpy PCG64(seed)); NOT the reference's un-vendored oorandom stream."""
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -129,4 +162,5 @@ def jitter(scene: Scene, amplitude: float, seed: int = 42) -> Scene:
     return scene
 
 
-SCENES = {"sand3": sand3, "fluids3": fluids3, "cube_through_sand3": cube_through_sand3, "neo_hookean_block": neo_hookean_block}
+SCENES = {"sand3": sand3, "fluids3": fluids3, "cube_through_sand3": cube_through_sand3, "neo_hookean_block": neo_hookean_block,
+          "model_block": model_block}

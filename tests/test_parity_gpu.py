@@ -90,6 +90,13 @@ def test_neo_hookean_block(oracle):
     _run_frames(g, o, sc, 10, lambda s: RTOL_1 * (1 + 3 * s))
 
 
+@pytest.mark.parametrize("kind", ["nacc", "rankine", "snow", "failure", "failure_split"])
+def test_other_plasticity_and_failure_models(oracle, kind):
+    sc = scenes.jitter(scenes.model_block(kind), 0.01, seed=3)
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 8, lambda s: 5e-5 * (1 + 3 * s))
+
+
 def test_cube_through_sand_kinematic(oracle):
     sc = scenes.cube_through_sand3(12, 6, 6, 4)
     g, o = _engines(sc, oracle)

@@ -32,7 +32,7 @@ def _three(scene, ob):
     return engines
 
 
-def _lockstep(scene, ob, nsub, base, growth=3.0):
+def _lockstep(scene, ob, nsub, base, growth=3.0, robust=False):
     E = _three(scene, ob)
     p = scene.params
     for e in E.values():
@@ -64,15 +64,22 @@ def _lockstep(scene, ob, nsub, base, growth=3.0):
             e.stage_g2p2g(dt)
         pr = E["reference"].read_all()
         for k in ("product", "oracle"):
-            errs = util.assert_particles_close(E[k].read_all(), pr, scene.cell_width, tol, f"substep {s} {k} vs reference, particles after g2p2g")
+            if robust:  # Snow / Rankine: the reference's own f32 SVD noise dominates (tests/util.py: ROBUST_MODELS)
+                errs = util.assert_particles_close_robust(E[k].read_all(), pr, scene.cell_width, f"substep {s} {k} vs reference, particles after g2p2g")
+            else:
+                errs = util.assert_particles_close(E[k].read_all(), pr, scene.cell_width, tol, f"substep {s} {k} vs reference, particles after g2p2g")
             for f, v in errs.items():
                 worst[(k, f)] = max(worst.get((k, f), 0.0), v)
+        if robust:  # the product must still match the (f64-SVD) oracle tightly on the same substep
+            util.assert_particles_close(E["product"].read_all(), E["oracle"].read_all(), scene.cell_width, tol, f"substep {s} product vs oracle")
         for k in ("product", "oracle"):
-            util.assert_grids_close(E[k], E["reference"], 1, tol, f"substep {s} {k} vs reference, next grid after g2p2g", scene, ob)
+            if not robust:
+                util.assert_grids_close(E[k], E["reference"], 1, tol, f"substep {s} {k} vs reference, next grid after g2p2g", scene, ob)
         for e in E.values():
             e.stage_grid_update(dt, scene.gravity)
         for k in ("product", "oracle"):
-            util.assert_grids_close(E[k], E["reference"], 0, tol, f"substep {s} {k} vs reference, grid after grid_update", scene, ob, velocity_field=True)
+            if not robust:
+                util.assert_grids_close(E[k], E["reference"], 0, tol, f"substep {s} {k} vs reference, grid after grid_update", scene, ob, velocity_field=True)
         remaining = np.float32(remaining - np.float32(dt))
         if remaining <= 1e-11:
             for e in E.values():
@@ -96,6 +103,13 @@ def test_neo_hookean_against_reference_kernels(ref):
 
 def test_kinematic_block_against_reference_kernels(ref):
     _lockstep(scenes.jitter(scenes.cube_through_sand3(12, 6, 6, 4), 0.02, seed=6), ref, 8, 2e-5)
+
+
+@pytest.mark.parametrize("kind", ["nacc", "rankine", "snow", "failure", "failure_split"])
+def test_other_models_against_reference_kernels(ref, kind):
+    """NACC / Rankine / Snow return mappings and the maximum-stress failure criterion (with and without the split
+    stress), on a pre-strained block: product and oracle in lock-step with the reference's own kernels"""
+    _lockstep(scenes.jitter(scenes.model_block(kind), 0.01, seed=3), ref, 8, 5e-5, robust=kind in util.ROBUST_MODELS)
 
 
 def _run_frames(engine, sc, frames):
