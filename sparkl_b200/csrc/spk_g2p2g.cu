@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
         if (has_particle && !(p.flags & SPK_F_FAILED)) {
             const DevModel& model = P.models[p.flags >> SPK_F_MODEL_SHIFT];
             const float cand = particle_dt_candidate(model, h, p.mass, p.volume0, p.F.m[0], p.elastic_hardening, vel[0], vel[1], vel[2]);
-            cand_bits = __float_as_uint(fminf(fmaxf(cand, 0.f), 1.0e30f)); // NaN -> 1e30 (Rust f32::min ignores NaN)
+            cand_bits = __float_as_uint(cand != cand ? 1.0e30f : fminf(fmaxf(cand, 0.f), 1.0e30f)); // NaN imposes no bound (Rust f32::min ignores NaN)
         }
         cand_bits = __reduce_min_sync(0xffffffffu, cand_bits);
         if ((tid & 31) == 0 && cand_bits < SPK_DT_RAW_NONE) atomicMin(s_dtmin, cand_bits);
