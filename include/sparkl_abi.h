@@ -134,12 +134,22 @@ typedef struct SpkGpuParticleModel {
 
 /* ---------------------------------------------------------------- colliders
  * GpuCollider, 336 bytes: src_kernels/gpu_collider.rs:203-212 (offsets from the PTX).
- * Scope: Cuboid (tag 0).  HeightField/TriMesh/Polyline are SURVEY §8(f) "next" rows -> SPK_EUNSUPPORTED. */
+ * Scope: Cuboid (tag 0) and HeightField (tag 1).  TriMesh / Polyline are SURVEY §8(f) "next" rows -> SPK_EUNSUPPORTED.
+ * The reference's HeightField payload is parry's `CudaHeightFieldPtr` (device pointers of ITS CUDA context,
+ * src_kernels/gpu_collider.rs:14-18, src/cuda/cuda_collider_set.rs:71-86); here the payload carries a HOST description of
+ * the same rapier `HeightField` (heights matrix + scale) and the library owns the device copy. */
 enum { SPK_SHAPE_CUBOID = 0, SPK_SHAPE_HEIGHTFIELD = 1, SPK_SHAPE_TRIMESH = 2, SPK_SHAPE_POLYLINE = 3 };
 typedef struct SpkGpuCollider {
     uint32_t shape_tag; uint32_t _pad0;
     union {
         struct { float half_extents[3]; } cuboid;
+        struct {                      /* parry3d HeightField::new(heights, scale) + GpuColliderShape::HeightField flags */
+            const float* heights;     /* HOST pointer, column-major nrows x ncols (nalgebra DMatrix): rows <-> z, columns <-> x */
+            uint32_t nrows, ncols;    /* number of height samples per axis (>= 2); the field spans [-scale/2, scale/2] in x and z */
+            float scale[3];
+            uint8_t bellow_heightfield_is_solid; /* always true in cuda_collider_set.rs:77 */
+            uint8_t flip_interior;
+        } heightfield;
         uint8_t _bytes[288];
     } shape;
     float rotation[4];    /* unit quaternion, nalgebra coordinate order (i, j, k, w) */

@@ -130,6 +130,18 @@ def cuboid_project(collider: abi.CuboidCollider, pt):
     return out, bool(inside.value)
 
 
+def collider_project(collider, pt, max_dist):
+    """GpuColliderShape::project_point_with_max_dist as restated by the oracle: (point, is_inside) or None"""
+    l = lib()
+    l.orc_collider_project.restype = C.c_int
+    c = np.frombuffer(collider.to_gpu_collider(), np.uint8).copy()
+    p = np.asarray(pt, np.float32).copy()
+    out = np.zeros(3, np.float32)
+    inside = C.c_int()
+    found = l.orc_collider_project(c.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), C.c_float(max_dist), out.ctypes.data_as(C.c_void_p), C.byref(inside))
+    return (out, bool(inside.value)) if found else None
+
+
 # ------------------------------------------------------------------------------------------------ oracle-A
 _REF = None
 REF_CUBIN = os.path.join(_HERE, "_ref", "sparkl3d-kernels.cubin")

@@ -266,6 +266,7 @@ struct orc_ctx {
     std::vector<uint32_t> sorted_ids;
     std::vector<SpkGpuParticleModel> models;
     std::vector<SpkGpuCollider> colliders;
+    std::vector<std::vector<float>> collider_data; // owned copies of the heightfield matrices the colliders point to
     Grid grids[2];
     int curr = 0; // grids[curr] = read-only previous grid, grids[1-curr] = next
     std::vector<SpkDispatchBlock2ActiveBlock> dispatch;
@@ -727,19 +728,88 @@ static Projection cuboid_project_point(const SpkGpuCollider& c, V3 pt) {
     out.point = quat_rotate(c.rotation, out.point) + tr;
     return out;
 }
-static bool collider_project(const SpkGpuCollider& c, V3 pt, Projection& out) {
+// Triangle::project_local_point (parry3d 0.13 point_triangle.rs): closest point by Voronoi regions (Ericson 5.1.5)
+static V3 triangle_closest_point(V3 p, V3 a, V3 b, V3 c) {
+    V3 ab = b - a, ac = c - a, ap = p - a;
+    Real d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0 && d2 <= 0) return a;
+    V3 bp = p - b;
+    Real d3 = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3 >= 0 && d4 <= d3) return b;
+    Real vc = d1 * d4 - d3 * d2;
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) return a + ab * (d1 / (d1 - d3));
+    V3 cp = p - c;
+    Real d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0 && d5 <= d6) return c;
+    Real vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) return a + ac * (d2 / (d2 - d6));
+    Real va = d3 * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) return b + (c - b) * ((d4 - d3) / ((d4 - d3) + (d5 - d6)));
+    Real denom = 1.0f / (va + vb + vc);
+    return a + ab * (vb * denom) + ac * (vc * denom);
+}
+// GenericHeightField::project_local_point_with_max_dist over map_elements_in_local_aabb (parry3d 0.13 point_heightfield.rs,
+// heightfield3.rs; the crate is not under /root/reference: restated from its published algorithm), then the inside test
+// of GpuColliderShape::project_point_with_max_dist (src_kernels/gpu_collider.rs:73-99)
+static bool heightfield_project_point(const SpkGpuCollider& c, V3 pt, Real max_dist, Projection& out) {
+    const auto& hf = c.shape.heightfield;
+    float qinv[4] = {-c.rotation[0], -c.rotation[1], -c.rotation[2], c.rotation[3]};
+    V3 tr = v3(c.translation[0], c.translation[1], c.translation[2]);
+    V3 lp = quat_rotate(qinv, pt - tr);
+    const int cells_x = (int)hf.ncols - 1, cells_z = (int)hf.nrows - 1;
+    const Real cw = 1.0f / (Real)cells_x, ch = 1.0f / (Real)cells_z;
+    V3 rmn = v3((lp.x - max_dist) / hf.scale[0], (lp.y - max_dist) / hf.scale[1], (lp.z - max_dist) / hf.scale[2]);
+    V3 rmx = v3((lp.x + max_dist) / hf.scale[0], (lp.y + max_dist) / hf.scale[1], (lp.z + max_dist) / hf.scale[2]);
+    if (rmx.x <= -0.5f || rmx.z <= -0.5f || rmn.x >= 0.5f || rmn.z >= 0.5f) return false;
+    auto clampf = [](Real v, Real lo, Real hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    const int min_x = (int)clampf(std::floor((rmn.x + 0.5f) / cw), 0.0f, (Real)(cells_x - 1));
+    const int min_z = (int)clampf(std::floor((rmn.z + 0.5f) / ch), 0.0f, (Real)(cells_z - 1));
+    const int max_x = (int)clampf(std::ceil((rmx.x + 0.5f) / cw), 0.0f, (Real)cells_x);
+    const int max_z = (int)clampf(std::ceil((rmx.z + 0.5f) / ch), 0.0f, (Real)cells_z);
+    Real sq_smallest = FLT_MAX;
+    bool found = false;
+    V3 best = v3(0, 0, 0);
+    for (int j = min_x; j < max_x; ++j)
+        for (int i = min_z; i < max_z; ++i) {
+            Real z0 = -0.5f + ch * (Real)i, z1 = -0.5f + ch * (Real)(i + 1), x0 = -0.5f + cw * (Real)j, x1 = -0.5f + cw * (Real)(j + 1);
+            Real y00 = hf.heights[i + (size_t)j * hf.nrows], y10 = hf.heights[i + 1 + (size_t)j * hf.nrows];
+            Real y01 = hf.heights[i + (size_t)(j + 1) * hf.nrows], y11 = hf.heights[i + 1 + (size_t)(j + 1) * hf.nrows];
+            if ((y00 > rmx.y && y10 > rmx.y && y01 > rmx.y && y11 > rmx.y) || (y00 < rmn.y && y10 < rmn.y && y01 < rmn.y && y11 < rmn.y)) continue;
+            V3 p00 = v3(x0 * hf.scale[0], y00 * hf.scale[1], z0 * hf.scale[2]), p10 = v3(x0 * hf.scale[0], y10 * hf.scale[1], z1 * hf.scale[2]);
+            V3 p01 = v3(x1 * hf.scale[0], y01 * hf.scale[1], z0 * hf.scale[2]), p11 = v3(x1 * hf.scale[0], y11 * hf.scale[1], z1 * hf.scale[2]);
+            for (int t = 0; t < 2; ++t) {
+                V3 q = t == 0 ? triangle_closest_point(lp, p00, p10, p01) : triangle_closest_point(lp, p10, p11, p01);
+                Real sq = norm_squared(lp - q);
+                if (sq < sq_smallest) {
+                    sq_smallest = sq;
+                    if (std::sqrt(sq) <= max_dist) { best = q; found = true; }
+                }
+            }
+        }
+    if (!found) return false;
+    if (hf.bellow_heightfield_is_solid) {
+        bool in_footprint = lp.x >= -0.5f * hf.scale[0] && lp.x <= 0.5f * hf.scale[0] && lp.z >= -0.5f * hf.scale[2] && lp.z <= 0.5f * hf.scale[2];
+        out.is_inside = in_footprint && (hf.flip_interior ? lp.y >= best.y : lp.y <= best.y);
+    } else {
+        out.is_inside = best.x == lp.x && best.y == lp.y && best.z == lp.z;
+    }
+    out.point = quat_rotate(c.rotation, best) + tr;
+    return true;
+}
+static bool collider_project(const SpkGpuCollider& c, V3 pt, Real max_dist, Projection& out) {
+    if (c.shape_tag == SPK_SHAPE_HEIGHTFIELD) return heightfield_project_point(c, pt, max_dist, out);
     if (c.shape_tag != SPK_SHAPE_CUBOID) return false;
     out = cuboid_project_point(c, pt);
     return true;
 }
 // sdf, grid_update.rs:54-71
-static bool sdf(const orc_ctx& ctx, V3 q, Real& out) {
+static bool sdf(const orc_ctx& ctx, V3 q, Real max_dist, Real& out) {
     bool any = false;
     Real best = 0;
     for (const auto& c : ctx.colliders) {
         if (c.grid_boundary_handling == SPK_BOUNDARY_NONE) continue;
         Projection p;
-        if (!collider_project(c, q, p)) continue;
+        if (!collider_project(c, q, max_dist, p)) continue;
         Real d = norm(p.point - q) * (p.is_inside ? -1.0f : 1.0f);
         if (!any || d < best) { best = d; any = true; } // min_by keeps the first of equal elements
     }
@@ -754,7 +824,7 @@ static V3 sdf_gradient(const orc_ctx& ctx, Real h, V3 q) {
         V3 off = v3(0, 0, 0);
         off[a] = 1.0f * (h * FACTOR);
         Real sp, sn;
-        bool hp = sdf(ctx, q + off, sp), hn = sdf(ctx, q + (-off), sn);
+        bool hp = sdf(ctx, q + off, h * 2.0f, sp), hn = sdf(ctx, q + (-off), h * 2.0f, sn);
         g[a] = (hp && hn) ? (sp - sn) / h / FACTOR / 2.0f : 0.0f;
     }
     Real n = norm(g);
@@ -775,7 +845,7 @@ static void update_single_cell(const orc_ctx& ctx, Real dt, SpkGpuGridNode& cell
             const auto& c = ctx.colliders[i];
             if (c.grid_boundary_handling == SPK_BOUNDARY_NONE) continue;
             Projection p;
-            if (!collider_project(c, cell_pos, p)) continue;
+            if (!collider_project(c, cell_pos, h * 2.0f, p)) continue; // max_dist = cell_width * 2 (grid_update.rs:118)
             V3 dir = cell_pos - p.point;
             Real dist = norm(dir);
             if (dist < (have ? best_dist : FLT_MAX)) { have = true; best_dir = dir; best_dist = dist; best_inside = p.is_inside; best_id = i; }
@@ -887,8 +957,16 @@ int orc_particles_read(orc_ctx* c, int which, void* dst, size_t n) {
 }
 int orc_models_upload(orc_ctx* c, const SpkGpuParticleModel* models, size_t n) { c->models.assign(models, models + n); return SPK_OK; }
 int orc_colliders_upload(orc_ctx* c, const SpkGpuCollider* cols, size_t n) {
-    for (size_t i = 0; i < n; ++i) if (cols[i].shape_tag != SPK_SHAPE_CUBOID) return SPK_EUNSUPPORTED;
+    for (size_t i = 0; i < n; ++i) if (cols[i].shape_tag != SPK_SHAPE_CUBOID && cols[i].shape_tag != SPK_SHAPE_HEIGHTFIELD) return SPK_EUNSUPPORTED;
     c->colliders.assign(cols, cols + n);
+    c->collider_data.assign(n, {});
+    for (size_t i = 0; i < n; ++i)
+        if (cols[i].shape_tag == SPK_SHAPE_HEIGHTFIELD) { // keep an owned copy of the heights matrix
+            const auto& hf = cols[i].shape.heightfield;
+            if (!hf.heights || hf.nrows < 2 || hf.ncols < 2) return SPK_EINVAL;
+            c->collider_data[i].assign(hf.heights, hf.heights + (size_t)hf.nrows * hf.ncols);
+            c->colliders[i].shape.heightfield.heights = c->collider_data[i].data();
+        }
     return SPK_OK;
 }
 
@@ -1226,6 +1304,13 @@ void orc_kirchhoff_stress(const SpkGpuParticleModel* m, const SpkParticleData* d
     std::memcpy(out9, s.m, 36);
 }
 void orc_plastic_update(const SpkGpuParticleModel* m, SpkParticleData* d, SpkParticleVolume* vol, float phase) { model_plastic_update(*m, *d, *vol, phase); }
+int orc_collider_project(const SpkGpuCollider* c, const float* pt, float max_dist, float* out_pt, int* inside) {
+    Projection p;
+    if (!collider_project(*c, v3(pt[0], pt[1], pt[2]), max_dist, p)) return 0;
+    out_pt[0] = p.point.x; out_pt[1] = p.point.y; out_pt[2] = p.point.z;
+    *inside = p.is_inside ? 1 : 0;
+    return 1;
+}
 void orc_cuboid_project(const SpkGpuCollider* c, const float* pt, float* out_pt, int* inside) {
     Projection p = cuboid_project_point(*c, v3(pt[0], pt[1], pt[2]));
     out_pt[0] = p.point.x; out_pt[1] = p.point.y; out_pt[2] = p.point.z; *inside = p.is_inside;

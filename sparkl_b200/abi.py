@@ -277,6 +277,35 @@ class CuboidCollider:
         return bytes(buf)
 
 
+class HeightFieldCollider:
+    """A rapier `ColliderBuilder::heightfield(heights, scale)` + `CudaColliderOptions` -> 336-byte GpuCollider image with the
+    HeightField payload of include/sparkl_abi.h (a HOST pointer to the column-major heights matrix; rows <-> z, columns
+    <-> x; the field spans [-scale/2, scale/2] in x and z, parry3d heightfield3.rs).  Keep the object alive until the upload."""
+
+    def __init__(self, heights, scale, translation=(0, 0, 0), rotation=(0, 0, 0, 1), friction=0.5, penalty_stiffness=0.0,
+                 grid_boundary_handling=BoundaryHandling.Friction, flip_interior=False):
+        h = np.asarray(heights, np.float32)
+        assert h.ndim == 2 and h.shape[0] >= 2 and h.shape[1] >= 2
+        self.nrows, self.ncols = h.shape
+        self.heights = np.asfortranarray(h)  # nalgebra DMatrix storage
+        self.scale, self.translation, self.rotation = tuple(scale), translation, rotation
+        self.friction, self.penalty_stiffness, self.grid_boundary_handling = friction, penalty_stiffness, grid_boundary_handling
+        self.flip_interior = flip_interior
+
+    def to_gpu_collider(self) -> bytes:
+        buf = bytearray(336)
+        np.frombuffer(buf, "<u4", 1, 0)[0] = 1
+        np.frombuffer(buf, "<u8", 1, 8)[0] = self.heights.ctypes.data
+        np.frombuffer(buf, "<u4", 2, 16)[:] = [self.nrows, self.ncols]
+        np.frombuffer(buf, "<f4", 3, 24)[:] = self.scale
+        np.frombuffer(buf, "u1", 2, 36)[:] = [1, int(self.flip_interior)]  # bellow_heightfield_is_solid: cuda_collider_set.rs:77
+        np.frombuffer(buf, "<f4", 4, 296)[:] = self.rotation
+        np.frombuffer(buf, "<f4", 3, 312)[:] = self.translation
+        np.frombuffer(buf, "<f4", 2, 324)[:] = [self.friction, self.penalty_stiffness]
+        np.frombuffer(buf, "<u4", 1, 332)[0] = self.grid_boundary_handling
+        return bytes(buf)
+
+
 def pack_colliders(colliders) -> np.ndarray:
     out = np.zeros((len(colliders), 336), dtype=np.uint8)
     for i, c in enumerate(colliders):

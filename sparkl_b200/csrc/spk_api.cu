@@ -340,7 +340,7 @@ int spk_ctx_destroy(spk_ctx* c) {
     if (c->dist_arena) { c->grid[0].external_hash = c->grid[1].external_hash = 1; }
     free_particles(c);
     free_grid(c->grid[0]); free_grid(c->grid[1]);
-    dev_free(c->slot_cnt); dev_free(c->dispatch); dev_free(c->models); dev_free(c->colliders); dev_free(c->d_counters);
+    dev_free(c->slot_cnt); dev_free(c->dispatch); dev_free(c->models); dev_free(c->colliders); dev_free(c->collider_data); dev_free(c->d_counters);
     if (c->staging) cudaFree(c->staging);
     if (c->dist_arena) cudaFree(c->dist_arena);
     if (c->dist_peer_ids) cudaFree(c->dist_peer_ids);
@@ -513,17 +513,39 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
     if (!c || (n && !cols)) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));
     std::vector<DevCollider> dc(n);
+    std::vector<float> data; // all heightfield matrices back to back
+    std::vector<size_t> data_off(n, 0);
     for (size_t i = 0; i < n; ++i) {
-        if (cols[i].shape_tag != SPK_SHAPE_CUBOID) return SPK_EUNSUPPORTED; // heightfield / trimesh / polyline: SURVEY §8(f) "next"
+        DevCollider& d = dc[i];
+        std::memset(&d, 0, sizeof(d));
         if (cols[i].grid_boundary_handling > SPK_BOUNDARY_NONE) return SPK_EINVAL;
-        std::memcpy(dc[i].half_extents, cols[i].shape.cuboid.half_extents, 12);
-        std::memcpy(dc[i].rot, cols[i].rotation, 16);
-        std::memcpy(dc[i].tr, cols[i].translation, 12);
-        dc[i].friction = cols[i].friction;
-        dc[i].handling = cols[i].grid_boundary_handling;
+        d.shape = cols[i].shape_tag;
+        if (cols[i].shape_tag == SPK_SHAPE_CUBOID) {
+            std::memcpy(d.half_extents, cols[i].shape.cuboid.half_extents, 12);
+        } else if (cols[i].shape_tag == SPK_SHAPE_HEIGHTFIELD) {
+            const auto& hf = cols[i].shape.heightfield;
+            if (!hf.heights || hf.nrows < 2 || hf.ncols < 2) return SPK_EINVAL; // HeightField::new asserts > 1 samples per axis
+            d.nrows = hf.nrows; d.ncols = hf.ncols;
+            std::memcpy(d.scale, hf.scale, 12);
+            d.hf_flags = (hf.bellow_heightfield_is_solid ? 1u : 0u) | (hf.flip_interior ? 2u : 0u);
+            data_off[i] = data.size();
+            data.insert(data.end(), hf.heights, hf.heights + (size_t)hf.nrows * hf.ncols);
+        } else {
+            return SPK_EUNSUPPORTED; // trimesh / polyline: SURVEY §8(f) "next"
+        }
+        std::memcpy(d.rot, cols[i].rotation, 16);
+        std::memcpy(d.tr, cols[i].translation, 12);
+        d.friction = cols[i].friction;
+        d.handling = cols[i].grid_boundary_handling;
     }
+    CK(cudaStreamSynchronize(c->stream));
     dev_free(c->colliders);
+    dev_free(c->collider_data);
     CK(dev_alloc(c->colliders, n));
+    CK(dev_alloc(c->collider_data, data.size()));
+    if (!data.empty()) CK(cudaMemcpy(c->collider_data, data.data(), data.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < n; ++i)
+        if (dc[i].shape == SPK_SHAPE_HEIGHTFIELD) dc[i].heights = c->collider_data + data_off[i];
     if (n) CK(cudaMemcpy(c->colliders, dc.data(), n * sizeof(DevCollider), cudaMemcpyHostToDevice));
     c->ncolliders = n;
     // colliders changed: invalidate the per-node projection cache of both grids (the reference uploads colliders once)

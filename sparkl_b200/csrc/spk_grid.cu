@@ -79,14 +79,103 @@ __device__ inline void cuboid_project(const DevCollider& c, Vec3 pt, Vec3& out, 
     const Vec3 w = quat_rotate(c.rot, Vec3{r[0], r[1], r[2]});
     out = Vec3{w.x + c.tr[0], w.y + c.tr[1], w.z + c.tr[2]};
 }
+// ---- heightfield projection: parry3d 0.13 `GenericHeightField::project_local_point_with_max_dist` (point_heightfield.rs)
+// over `map_elements_in_local_aabb` (heightfield3.rs), restated; then the inside test of
+// GpuColliderShape::project_point_with_max_dist (src_kernels/gpu_collider.rs:73-99).
+// Closest point on a triangle: Ericson, Real-Time Collision Detection 5.1.5 (the Voronoi-region walk parry uses).
+__device__ __forceinline__ Vec3 v_sub(Vec3 a, Vec3 b) { return Vec3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ float v_dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ inline Vec3 closest_point_on_triangle(Vec3 p, Vec3 a, Vec3 b, Vec3 c) {
+    const Vec3 ab = v_sub(b, a), ac = v_sub(c, a), ap = v_sub(p, a);
+    const float d1 = v_dot(ab, ap), d2 = v_dot(ac, ap);
+    if (d1 <= 0.f && d2 <= 0.f) return a;
+    const Vec3 bp = v_sub(p, b);
+    const float d3 = v_dot(ab, bp), d4 = v_dot(ac, bp);
+    if (d3 >= 0.f && d4 <= d3) return b;
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
+        const float v = d1 / (d1 - d3);
+        return Vec3{a.x + v * ab.x, a.y + v * ab.y, a.z + v * ab.z};
+    }
+    const Vec3 cp = v_sub(p, c);
+    const float d5 = v_dot(ab, cp), d6 = v_dot(ac, cp);
+    if (d6 >= 0.f && d5 <= d6) return c;
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
+        const float w = d2 / (d2 - d6);
+        return Vec3{a.x + w * ac.x, a.y + w * ac.y, a.z + w * ac.z};
+    }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        return Vec3{b.x + w * (c.x - b.x), b.y + w * (c.y - b.y), b.z + w * (c.z - b.z)};
+    }
+    const float denom = 1.f / (va + vb + vc);
+    const float v = vb * denom, w = vc * denom;
+    return Vec3{a.x + ab.x * v + ac.x * w, a.y + ab.y * v + ac.y * w, a.z + ab.z * v + ac.z * w};
+}
+__device__ inline bool heightfield_project(const DevCollider& c, Vec3 pt, float max_dist, Vec3& out, bool& inside) {
+    const float qinv[4] = {-c.rot[0], -c.rot[1], -c.rot[2], c.rot[3]};
+    const Vec3 lp = quat_rotate(qinv, Vec3{pt.x - c.tr[0], pt.y - c.tr[1], pt.z - c.tr[2]});
+    const int cells_x = (int)c.ncols - 1, cells_z = (int)c.nrows - 1; // HeightField::ncols() / nrows(): number of CELLS
+    const float cw = 1.f / (float)cells_x, ch = 1.f / (float)cells_z; // unit_cell_width / unit_cell_height
+    const float rminx = (lp.x - max_dist) / c.scale[0], rminy = (lp.y - max_dist) / c.scale[1], rminz = (lp.z - max_dist) / c.scale[2];
+    const float rmaxx = (lp.x + max_dist) / c.scale[0], rmaxy = (lp.y + max_dist) / c.scale[1], rmaxz = (lp.z + max_dist) / c.scale[2];
+    if (rmaxx <= -0.5f || rmaxz <= -0.5f || rminx >= 0.5f || rminz >= 0.5f) return false; // outside of the heightfield bounds
+    // quantize_floor / quantize_ceil (heightfield3.rs)
+    const int min_x = (int)fminf(fmaxf(floorf((rminx + 0.5f) / cw), 0.f), (float)(cells_x - 1));
+    const int min_z = (int)fminf(fmaxf(floorf((rminz + 0.5f) / ch), 0.f), (float)(cells_z - 1));
+    const int max_x = (int)fminf(fmaxf(ceilf((rmaxx + 0.5f) / cw), 0.f), (float)cells_x);
+    const int max_z = (int)fminf(fmaxf(ceilf((rmaxz + 0.5f) / ch), 0.f), (float)cells_z);
+    float sq_smallest = FLT_MAX;
+    bool found = false;
+    Vec3 best{0.f, 0.f, 0.f};
+    for (int j = min_x; j < max_x; ++j) {
+        for (int i = min_z; i < max_z; ++i) {
+            const float z0 = -0.5f + ch * (float)i, z1 = -0.5f + ch * (float)(i + 1);
+            const float x0 = -0.5f + cw * (float)j, x1 = -0.5f + cw * (float)(j + 1);
+            const float y00 = c.heights[i + (size_t)j * c.nrows], y10 = c.heights[i + 1 + (size_t)j * c.nrows];
+            const float y01 = c.heights[i + (size_t)(j + 1) * c.nrows], y11 = c.heights[i + 1 + (size_t)(j + 1) * c.nrows];
+            if ((y00 > rmaxy && y10 > rmaxy && y01 > rmaxy && y11 > rmaxy) || (y00 < rminy && y10 < rminy && y01 < rminy && y11 < rminy)) continue;
+            const Vec3 p00{x0 * c.scale[0], y00 * c.scale[1], z0 * c.scale[2]}, p10{x0 * c.scale[0], y10 * c.scale[1], z1 * c.scale[2]};
+            const Vec3 p01{x1 * c.scale[0], y01 * c.scale[1], z0 * c.scale[2]}, p11{x1 * c.scale[0], y11 * c.scale[1], z1 * c.scale[2]};
+#pragma unroll
+            for (int t = 0; t < 2; ++t) { // default cell status: triangles (p00, p10, p01) and (p10, p11, p01)
+                const Vec3 q = t == 0 ? closest_point_on_triangle(lp, p00, p10, p01) : closest_point_on_triangle(lp, p10, p11, p01);
+                const Vec3 d = v_sub(lp, q);
+                const float sq = v_dot(d, d);
+                if (sq < sq_smallest) {
+                    sq_smallest = sq;
+                    if (sqrtf(sq) <= max_dist) { best = q; found = true; }
+                }
+            }
+        }
+    }
+    if (!found) return false;
+    if (c.hf_flags & 1u) { // bellow_heightfield_is_solid: inside = within the x/z footprint and on the solid side of the surface
+        const bool in_footprint = lp.x >= -0.5f * c.scale[0] && lp.x <= 0.5f * c.scale[0] && lp.z >= -0.5f * c.scale[2] && lp.z <= 0.5f * c.scale[2];
+        inside = in_footprint && ((c.hf_flags & 2u) ? lp.y >= best.y : lp.y <= best.y);
+    } else {
+        inside = best.x == lp.x && best.y == lp.y && best.z == lp.z;
+    }
+    const Vec3 w = quat_rotate(c.rot, best);
+    out = Vec3{w.x + c.tr[0], w.y + c.tr[1], w.z + c.tr[2]};
+    return true;
+}
+// GpuColliderShape::project_point_with_max_dist, gpu_collider.rs:42-103 (solid = false)
+__device__ __forceinline__ bool collider_project(const DevCollider& c, Vec3 pt, float max_dist, Vec3& out, bool& inside) {
+    if (c.shape == SPK_SHAPE_HEIGHTFIELD) return heightfield_project(c, pt, max_dist, out, inside);
+    cuboid_project(c, pt, out, inside);
+    return true;
+}
 // sdf, grid_update.rs:54-71
-__device__ inline bool sdf(const DevCollider* cols, uint32_t ncol, Vec3 q, float& out) {
+__device__ inline bool sdf(const DevCollider* cols, uint32_t ncol, Vec3 q, float max_dist, float& out) {
     bool any = false;
     float best = 0.f;
     for (uint32_t i = 0; i < ncol; ++i) {
         if (cols[i].handling == SPK_BOUNDARY_NONE) continue;
         Vec3 p; bool inside;
-        cuboid_project(cols[i], q, p, inside);
+        if (!collider_project(cols[i], q, max_dist, p, inside)) continue;
         const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
         const float d = sqrtf(dx * dx + dy * dy + dz * dz) * (inside ? -1.f : 1.f);
         if (!any || d < best) { best = d; any = true; }
@@ -128,7 +217,7 @@ __global__ void __launch_bounds__(256) grid_update_kernel(GridBuffers g, uint32_
         for (uint32_t i = 0; i < ncol; ++i) {
             if (cols[i].handling == SPK_BOUNDARY_NONE) continue;
             Vec3 p; bool inside;
-            cuboid_project(cols[i], pos, p, inside);
+            if (!collider_project(cols[i], pos, h * 2.f, p, inside)) continue; // max_dist = cell_width * 2, grid_update.rs:118
             const Vec3 dir{pos.x - p.x, pos.y - p.y, pos.z - p.z};
             const float dist = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
             if (dist < (have ? best_dist : FLT_MAX)) { have = true; best_dist = dist; best_dir = dir; best_inside = inside; best_id = i; }
@@ -147,7 +236,7 @@ __global__ void __launch_bounds__(256) grid_update_kernel(GridBuffers g, uint32_
             Vec3 qp = pos, qn = pos;
             if (a == 0) { qp.x += off; qn.x += -off; } else if (a == 1) { qp.y += off; qn.y += -off; } else { qp.z += off; qn.z += -off; }
             float sp, sn;
-            const bool hp = sdf(cols, ncol, qp, sp), hn = sdf(cols, ncol, qn, sn);
+            const bool hp = sdf(cols, ncol, qp, h * 2.f, sp), hn = sdf(cols, ncol, qn, h * 2.f, sn);
             grad[a] = (hp && hn) ? (sp - sn) / h / 0.1f / 2.f : 0.f;
         }
         const float gn = sqrtf(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]);

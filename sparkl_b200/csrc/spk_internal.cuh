@@ -52,6 +52,11 @@ struct DevCollider {
     float tr[3];
     float friction;
     uint32_t handling;
+    uint32_t shape;       // SPK_SHAPE_CUBOID / SPK_SHAPE_HEIGHTFIELD
+    uint32_t nrows, ncols; // heightfield: height samples along z / x
+    const float* heights; // heightfield: device copy, column-major nrows x ncols
+    float scale[3];
+    uint32_t hf_flags;    // bit0 bellow_heightfield_is_solid, bit1 flip_interior
 };
 
 struct GridBuffers { // one of the two sparse-grid buffers (curr / next)
@@ -129,6 +134,7 @@ struct spk_ctx {
     // models / colliders
     DevModel* models; size_t nmodels; uint32_t model_flags_any; // bit0: any model needs an SVD
     DevCollider* colliders; size_t ncolliders;
+    float* collider_data; // device copies of the heightfield matrices, one allocation
     // grid
     GridBuffers grid[2];
     int gcur;             // grid[gcur] = curr (read only), grid[1-gcur] = next

@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import abi
-from .abi import (BoundaryHandling, CorotatedLinearElasticity, CuboidCollider, DruckerPragerPlasticity, MonaghanSphEos,
+from .abi import (BoundaryHandling, CorotatedLinearElasticity, CuboidCollider, HeightFieldCollider, DruckerPragerPlasticity, MonaghanSphEos,
                   NeoHookeanElasticity, ParticleComponents, ParticleModel, SolverParameters, cube_particles)
 
 
@@ -50,7 +50,17 @@ def box_colliders(lo, hi, thickness=2.0, friction=0.5, handling=BoundaryHandling
     return out
 
 
-def sand3(ni=100, nj=50, nk=50, x_offset=0.0, with_colliders=True) -> Scene:
+def sand3_heightfield_ground(friction=0.5, handling=BoundaryHandling.Friction) -> HeightFieldCollider:
+    """the ground of examples3d/sand3.rs:23-38 and cube_through_sand3.rs:26-38: a 41 x 41 heightfield, heights[(i, j)] =
+    -sin(i pi / 40), scale (40, 10, 40), translated by (0, 10, 0): a trough along x whose bottom (y = 0) is at z = 0"""
+    n = 40
+    i = np.arange(n + 1, dtype=np.float32)
+    col = -np.sin(i * np.float32(np.pi) / np.float32(n)).astype(np.float32)
+    heights = np.repeat(col[:, None], n + 1, axis=1)
+    return HeightFieldCollider(heights, (40.0, 10.0, 40.0), translation=(0.0, 10.0, 0.0), friction=friction, grid_boundary_handling=handling)
+
+
+def sand3(ni=100, nj=50, nk=50, x_offset=0.0, with_colliders=True, ground="cuboid", y0=None) -> Scene:
     """examples3d/sand3.rs:40-75: an upper Drucker-Prager sand lattice stacked on a corotated elastic lattice,
     E = 1e7, nu = 0.2, h = 0.2, r = h/4, rho0 = 2700.  Reference size is (100, 50, 50) x 2 = 500k particles;
     the 4M benchmark configuration is (200, 100, 100) x 2."""
@@ -59,12 +69,14 @@ def sand3(ni=100, nj=50, nk=50, x_offset=0.0, with_colliders=True) -> Scene:
     r = np.float32(h) / np.float32(4.0)
     models = [ParticleModel.with_plasticity(CorotatedLinearElasticity(E, NU), DruckerPragerPlasticity(E, NU)),
               ParticleModel(CorotatedLinearElasticity(E, NU))]
-    y0 = np.float32(h) * np.float32(3.0) + np.float32(2.0)
+    y0 = np.float32(h) * np.float32(3.0) + np.float32(2.0) if y0 is None else np.float32(y0)
     upper = cube_particles((x_offset, y0 + r * np.float32(2.0) * np.float32(nj), 0.0), ni, nj, nk, 0, r, 2700.0)
     lower = cube_particles((x_offset, y0, 0.0), ni, nj, nk, 1, r, 2700.0)
     pc = ParticleComponents.concatenate([upper, lower])
     cols = []
-    if with_colliders:
+    if with_colliders and ground == "heightfield":  # the reference scene's own ground
+        cols = [sand3_heightfield_ground()]
+    elif with_colliders:
         ext = 2.0 * float(r)
         cols = box_colliders((x_offset - 4.0, 2.0, -4.0), (x_offset + ni * ext + 4.0, 2.0 + 2 * nj * ext + 8.0, nk * ext + 4.0))
     return Scene("sand3", h, pc, models, cols)

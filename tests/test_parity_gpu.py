@@ -97,6 +97,25 @@ def test_other_plasticity_and_failure_models(oracle, kind):
     _run_frames(g, o, sc, 8, lambda s: 5e-5 * (1 + 3 * s))
 
 
+def test_sand_on_heightfield_ground(oracle):
+    """the reference scenes' own ground (examples3d/sand3.rs:23-38): HeightField collider, §8f-1"""
+    sc = scenes.jitter(scenes.sand3(10, 5, 8, ground="heightfield", y0=0.45), 0.02, seed=5)
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 10, lambda s: RTOL_1 * (1 + 3 * s))
+    tags = np.bincount(g.grid_nodes(0)["projection_status_tag"].ravel().astype(int), minlength=4)
+    assert tags[1] > 0 and tags[2] > 0 and tags[3] > 0  # inside / outside / too far all occur
+
+
+def test_unsupported_collider_shapes_are_rejected():
+    from sparkl_b200.pipeline import SingleGpuMpmContext
+    g = SingleGpuMpmContext(0.2)
+    img = np.zeros((1, 336), np.uint8)
+    for tag in (2, 3):  # TriMesh, Polyline: SURVEY §8f "next"
+        img[0, 0] = tag
+        rc = g._lib.spk_colliders_upload(g._h, img.ctypes.data, 1)
+        assert rc == abi.EUNSUPPORTED
+
+
 def test_cube_through_sand_kinematic(oracle):
     sc = scenes.cube_through_sand3(12, 6, 6, 4)
     g, o = _engines(sc, oracle)

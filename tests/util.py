@@ -169,7 +169,9 @@ def assert_nodes_close(na, nb, tol, what="", scene=None, vids=None, oracle=None,
         "psi_momentum_velocity": (rel_err(pv_a, pv_b, floor=1e-3, atol=tol.energy_atol * max(mscale, 1.0)), 50 * b),
         "psi_mass": (rel_err(na["psi_mass"], nb["psi_mass"]), b),
         "prev_mass": (rel_err(na["prev_mass"], nb["prev_mass"]), b),
-        "collision_normal": (rel_err(na["collision_normal"], nb["collision_normal"], floor=1.0), max(b, 1e-5)),
+        # the normal is a central difference of the SDF over +-0.1 h (grid_update.rs:74-94): f32 round-off of the projected
+        # points (~1e-7 * |x|) is amplified by 1 / (0.2 h), i.e. a few 1e-5 for coordinates of order 10
+        "collision_normal": (rel_err(na["collision_normal"], nb["collision_normal"], floor=1.0), max(b, 1e-4)),
     }
     bad = {k: v for k, v in checks.items() if not (v[0] <= v[1])}
     assert not bad, f"{what}: node fields out of tolerance (error, allowed): {bad} (all: {checks})"
