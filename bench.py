@@ -42,53 +42,56 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-class ClockSampler(threading.Thread):
-    """samples SM clocks / throttle reasons during the timed region: NVML in-process (1 kHz) when available, else nvidia-smi"""
+_SAMPLER_SRC = r"""
+import sys, time
+idx = int(sys.argv[1])
+try:
+    import pynvml as N
+    N.nvmlInit(); h = N.nvmlDeviceGetHandleByIndex(idx)
+    print("max", N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM), flush=True)
+    while True:
+        try: m = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception: m = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        print(time.time(), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), int(m), flush=True)
+        time.sleep(0.005)
+except Exception as e:
+    print("err", e, flush=True)
+"""
+
+
+class ClockSampler:
+    """samples SM clocks / throttle reasons during the timed region from a SEPARATE process (NVML, 200 Hz): an in-process
+    poller competes with the launching thread for the GIL and the driver lock and was measured to slow the multi-GPU step"""
 
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.sm, self.mx, self.mask, self._halt = index, [], [], 0, threading.Event()
-        self.nvml = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
-            self.nvml = pynvml
-        except Exception:
-            self.nvml = None
+        self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.t0 = self.t1 = None
 
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self._halt.is_set():
-            try:
-                if self.nvml is not None:
-                    self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)))
-                    try:
-                        self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                    except Exception:
-                        self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                    self._halt.wait(0.001)
-                    continue
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                r = [x.strip() for x in out.split(",")]
-                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
-                for (name, bit), v in zip(self.REASONS.items(), r[2:6]):
-                    if v.lower().startswith("active"):
-                        self.mask |= bit
-            except Exception:
-                pass
-            self._halt.wait(0.05)
+    def start(self):
+        self.t0 = time.time()
 
     def finish(self):
-        self._halt.set()
-        self.join(timeout=6)
-        reasons = sorted(n for n, bit in self.REASONS.items() if self.mask & bit)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": reasons,
-                "samples": len(self.sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+        self.t1 = time.time()
+        time.sleep(0.02)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, mask = [], None, 0
+        for line in out.splitlines():
+            f = line.split()
+            if len(f) == 2 and f[0] == "max":
+                mx = float(f[1])
+            elif len(f) == 3:
+                t = float(f[0])
+                if self.t0 <= t <= self.t1:
+                    sm.append(float(f[1])); mask |= int(f[2])
+        reasons = sorted(n for n, bit in self.REASONS.items() if mask & bit)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "source": "nvml (separate process)"}
 
 
 def build_scene(rank, world, dims):
@@ -194,8 +197,8 @@ def run_ours(args):
             pipe = DistributedMpmPipeline(ctx, dist, torch.device("cuda", local))
 
     def one_substep():
-        if pipe is None:
-            return ctx.step(params, sc.gravity)[1]
+        if pipe is None:  # per-stage event timings (one extra event sync per substep) only where they are reported: N = 1
+            return ctx.step(params, sc.gravity, timings=(world == 1))[1]
         pipe.step(params, sc.gravity)
         return None
 
@@ -204,6 +207,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None  # started early: its process is up by the time the timed region begins
     # bring the scene into a loaded state first (material compressing under gravity, F != I): the rest lattice makes the
     # per-particle SVD converge in one sweep and would flatter the kernel.  Untimed, not part of the warm-up contract.
     for _ in range(args.settle):
@@ -211,7 +215,6 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         one_substep()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -220,7 +223,7 @@ def run_ours(args):
     ev0.record(stream)
     for _ in range(args.steps):
         t = one_substep()
-        if t is not None:
+        if t is not None and world == 1:
             g2p2g_ms += t.g2p2g_ms
             launches += t.kernel_launches
             stage_ms += [t.grid_resize_and_sort_ms, t.reset_grid_ms, t.estimate_timestep_ms, t.g2p2g_ms, t.grid_update_ms]

@@ -344,6 +344,7 @@ int spk_ctx_destroy(spk_ctx* c) {
     if (c->staging) cudaFree(c->staging);
     if (c->dist_arena) cudaFree(c->dist_arena);
     if (c->dist_peer_ids) cudaFree(c->dist_peer_ids);
+    if (c->dist_push_ptrs) cudaFree(c->dist_push_ptrs);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_upload) cudaFreeHost(c->h_upload);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -699,7 +700,7 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
         CK(spk_launch_g2p2g(c, dt));
         if (timings) CK(cudaEventRecord(ev[4], c->stream));
         if (dist) { // NVLink red.add of the shared blocks into the peers, barrier (+ global dt minimum), fold what arrived
-            CK(spk_dist_launch_push(c));
+            if (!c->dist_fused_push) CK(spk_dist_launch_push(c)); // default: pushed by g2p2g's own flush
             CK(spk_dist_launch_barrier(c, 1));
             CK(spk_dist_launch_merge(c));
         }

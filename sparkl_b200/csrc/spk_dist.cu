@@ -18,6 +18,7 @@
 //              mailbox; two per substep.  The dt minimum rides on the second one.
 // The host never blocks for the exchange: the only read-back per substep is the 64-byte counter record of the sort.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "spk_device.cuh"
@@ -105,8 +106,11 @@ __global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext,
 
 // For every active block of this rank and every peer: the peer's id of the same block key (probe of the peer's hash
 // table over NVLink), -1 when the peer does not hold it.  Shared blocks are tagged IS_HALO (tag_halo_blocks, sort.rs:74-96).
-__global__ void __launch_bounds__(256) dist_detect_kernel(DistState d, GridBuffers next, uint32_t nab, uint32_t epoch, int32_t* peer_ids, DeviceCounters* counters) {
+__global__ void __launch_bounds__(256) dist_detect_kernel(DistState d, GridBuffers next, uint32_t nab, uint32_t epoch, int32_t* peer_ids, float** push_ptrs,
+                                                          DeviceCounters* counters) {
     const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    if (t < d.world) // where each rank's halo accumulator of THIS substep lives (for the push fused into g2p2g's flush)
+        push_ptrs[t] = t == d.rank ? nullptr : d.peer_grid[t][__ldcv(&d.mailbox->gnext[epoch & 1u][t]) & 1u].hacc;
     const uint32_t b = t / d.world, p = t % d.world;
     if (b >= nab) return;
     int32_t id = -1;
@@ -190,7 +194,7 @@ cudaError_t spk_dist_launch_detect(spk_ctx* c) {
     const uint32_t nab = next.nab_host;
     cudaError_t e = cudaMemsetAsync(&c->d_counters->num_halo, 0, 4, c->stream);
     if (e != cudaSuccess || !nab) return e;
-    dist_detect_kernel<<<(nab * d.world + 255) / 256, 256, 0, c->stream>>>(d, next, nab, d.epoch, c->dist_peer_ids, c->d_counters);
+    dist_detect_kernel<<<(nab * d.world + 255) / 256, 256, 0, c->stream>>>(d, next, nab, d.epoch, c->dist_peer_ids, c->dist_push_ptrs, c->d_counters);
     c->launches += 1;
     return cudaGetLastError();
 }
@@ -231,6 +235,10 @@ int spk_dist_export(spk_ctx* c, SpkDistDescriptor* out) {
     int rc = spk_dist_realloc_grids(c, cap);
     if (rc) return rc;
     CK(cudaMalloc((void**)&c->dist_peer_ids, (size_t)(cap / 2) * SPK_MAX_RANKS * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&c->dist_push_ptrs, SPK_MAX_RANKS * sizeof(float*)));
+    CK(cudaMemset(c->dist_push_ptrs, 0, SPK_MAX_RANKS * sizeof(float*)));
+    c->dist_fused_push = 1;
+    if (const char* m = getenv("SPK_DIST_PUSH")) c->dist_fused_push = std::strcmp(m, "kernel") != 0; // A/B: separate push kernel
     DescriptorWire w;
     std::memset(&w, 0, sizeof(w));
     CK(cudaIpcGetMemHandle(&w.handle, arena));

@@ -37,6 +37,11 @@ struct G2P2GParams {
     float h, inv_h, dt;
     uint32_t ndispatch;
     uint32_t* dt_raw_bits; // CFL candidate of the NEXT substep (fused K15)
+    // multi-GPU (world == 0: single GPU): shared blocks are ALSO reduced into every holder's halo accumulator over NVLink
+    uint32_t world;
+    const uint32_t* blk_halo;   // [block] bit0: active on another rank too (spk_dist.cu: dist_detect_kernel)
+    const int32_t* peer_ids;    // [block][world] the peer's id of the block, -1 if absent
+    float* const* peer_hacc;    // [world] peer-mapped `hacc` of each rank's next grid
 };
 
 // shared memory carve-up (dynamic)
@@ -502,8 +507,30 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
             const int nid = s_nbr_self[o];
             if (nid >= 0) tma_reduce_add_f32_1d(P.acc + (size_t)nid * (SPK_ACC_CHANNELS * 64), &s_acc[o * SPK_ACC_CHANNELS * 64], SPK_ACC_CHANNELS * 64 * 4);
         }
+        // fused halo push (multi-GPU): the same tile chunks are bulk-reduced straight into the peers' halo accumulators,
+        // addressed by the peer's own block ids — the transfer rides on NVLink while other CTAs still compute
+        bool pushed = false;
+        if (P.world > 1) {
+            for (int o = 0; o < 8; ++o) {
+                const int nid = s_nbr_self[o];
+                if (nid < 0 || !(P.blk_halo[nid] & 1u)) continue;
+                for (uint32_t r = 0; r < P.world; ++r) {
+                    const int32_t pid = P.peer_ids[(size_t)nid * P.world + r];
+                    if (pid >= 0) {
+                        tma_reduce_add_f32_1d(P.peer_hacc[r] + (size_t)pid * (SPK_ACC_CHANNELS * 64), &s_acc[o * SPK_ACC_CHANNELS * 64], SPK_ACC_CHANNELS * 64 * 4);
+                        pushed = true;
+                    }
+                }
+            }
+        }
         if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(P.dt_raw_bits, *s_dtmin);
-        tma_commit_and_wait_read();
+        if (pushed) { // remote reductions must be complete (not only read out of shared memory) before this CTA retires
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __threadfence_system();
+        } else {
+            tma_commit_and_wait_read();
+        }
     }
 }
 
@@ -570,6 +597,10 @@ cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) {
     P.dt = dt;
     P.ndispatch = nd;
     P.dt_raw_bits = &c->d_counters->dt_raw_bits;
+    P.world = (c->dist.world > 1 && c->dist_fused_push) ? c->dist.world : 0;
+    P.blk_halo = next.blk_halo;
+    P.peer_ids = c->dist_peer_ids;
+    P.peer_hacc = c->dist_push_ptrs;
     { cudaError_t e = cudaMemsetAsync(&c->d_counters->dt_raw_bits, 0x7f, 4, c->stream); if (e != cudaSuccess) return e; }
     static bool configured = false;
     if (!configured) {

@@ -155,6 +155,8 @@ struct spk_ctx {
     char* dist_arena; size_t dist_arena_bytes; uint32_t dist_cap_hash;
     int32_t* dist_peer_ids;              // [cap_blocks][world]: the peer's id of each of this rank's active blocks, -1 if absent
     void* dist_mapped[SPK_MAX_RANKS];    // cudaIpcOpenMemHandle results (to close)
+    float** dist_push_ptrs;              // [SPK_MAX_RANKS] device array: peer-mapped hacc of every rank's next grid (written by detect)
+    int dist_fused_push;                 // 1: g2p2g's flush pushes shared blocks itself (default); 0: separate push kernel (A/B)
     // timing
     cudaEvent_t ev[12];
     uint32_t launches;
