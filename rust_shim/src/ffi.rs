@@ -32,6 +32,26 @@ extern "C" {
     pub fn spk_colliders_upload(ctx: *mut SpkCtx, colliders: *const GpuCollider, n: usize) -> c_int;
     pub fn spk_step(ctxs: *mut *mut SpkCtx, nctx: usize, params: *const SolverParameters, gravity: *const f32,
                     timings: *mut SpkStepTimings, simulated_time_out: *mut f32) -> c_int;
+    // multi-GPU over NVLink peer memory, one process per GPU (sparkl_b200/csrc/spk_dist.cu)
+    pub fn spk_dist_export(ctx: *mut SpkCtx, out: *mut SpkDistDescriptor) -> c_int;
+    pub fn spk_dist_attach(ctx: *mut SpkCtx, rank: u32, world: u32, all_ranks: *const SpkDistDescriptor) -> c_int;
+    pub fn spk_dist_detach(ctx: *mut SpkCtx) -> c_int;
+}
+
+/// Opaque 128-byte blob (CUDA IPC handle of the rank's shared arena + its capacity); all-gather it with the host's transport.
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct SpkDistDescriptor { pub opaque: [u8; 128] }
+
+/// The HeightField payload of the 336-byte collider image (include/sparkl_abi.h): a HOST description of rapier's
+/// `HeightField` instead of parry's `CudaHeightFieldPtr` (which holds device pointers of cust's context).
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct SpkHeightFieldPayload {
+    pub heights: *const f32, // column-major DMatrix storage: `heightfield.heights().as_slice().as_ptr()`
+    pub nrows: u32, pub ncols: u32,
+    pub scale: [f32; 3],
+    pub bellow_heightfield_is_solid: u8, pub flip_interior: u8,
 }
 
 /// `CudaResult`-shaped error: positive = cudaError_t, negative = SPK_E* (API misuse).
@@ -58,7 +78,10 @@ impl B200MpmContext {
     pub fn set_models(&mut self, models: &[GpuParticleModel]) -> Result<(), SpkError> {
         ck(unsafe { spk_models_upload(self.raw, models.as_ptr(), models.len()) })
     }
-    /// ≙ CudaColliderSet::from_collider_set after the rapier → GpuCollider conversion (Cuboid shapes).
+    /// ≙ CudaColliderSet::from_collider_set after the rapier → GpuCollider conversion.  Cuboid images pass unchanged; for a
+    /// heightfield write tag 1 at offset 0 and a `SpkHeightFieldPayload` at offset 8 of the 336-byte image
+    /// (`cuda_collider_set.rs:71-86` builds a `CudaHeightFieldPtr` there instead); pose / friction / boundary handling stay
+    /// at their offsets.  TriMesh / Polyline are rejected with SPK_EUNSUPPORTED.
     pub fn set_colliders(&mut self, colliders: &[GpuCollider]) -> Result<(), SpkError> {
         ck(unsafe { spk_colliders_upload(self.raw, colliders.as_ptr(), colliders.len()) })
     }
@@ -68,6 +91,18 @@ impl B200MpmContext {
         let mut out = vec![ParticlePosition::default(); n];
         ck(unsafe { spk_particles_read(self.raw, 0, out.as_mut_ptr() as *mut c_void, n) })?;
         Ok(out)
+    }
+}
+impl B200MpmContext {
+    /// Multi-GPU, one process per GPU: call on every rank after `set_particles`, all-gather the descriptors (MPI, files, ...),
+    /// then `dist_attach`.  Afterwards `B200MpmPipeline::step` runs the halo accumulation and the dt minimum itself over NVLink.
+    pub fn dist_export(&mut self) -> Result<SpkDistDescriptor, SpkError> {
+        let mut d = SpkDistDescriptor { opaque: [0; 128] };
+        ck(unsafe { spk_dist_export(self.raw, &mut d) })?;
+        Ok(d)
+    }
+    pub fn dist_attach(&mut self, rank: u32, all_ranks: &[SpkDistDescriptor]) -> Result<(), SpkError> {
+        ck(unsafe { spk_dist_attach(self.raw, rank, all_ranks.len() as u32, all_ranks.as_ptr()) })
     }
 }
 impl Drop for B200MpmContext { fn drop(&mut self) { unsafe { spk_ctx_destroy(self.raw); } } }

@@ -175,11 +175,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
             tcell[a] = (assoc_cell & 3) + 1;                // associated_cell_index_in_block_off_by_two, particle.rs:28-35
         }
     }
-#ifdef SPK_WAIT1
-    if ((tid & 31) == 0) mbar_wait(s_bar, 0);
-#else
     mbar_wait(s_bar, 0);
-#endif
     __syncthreads();
 
     if (has_particle) {
@@ -189,11 +185,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
         {
             float V[3] = {0.f, 0.f, 0.f}, Gx[3] = {0.f, 0.f, 0.f}, Gy[3] = {0.f, 0.f, 0.f}, Gz[3] = {0.f, 0.f, 0.f};
             const float wpx[3] = {w[0][0] * ref[0], w[0][1] * (ref[0] + h), w[0][2] * (ref[0] + 2.f * h)};
-#ifdef SPK_G2P_ROLL
-#pragma unroll 1
-#else
 #pragma unroll
-#endif
             for (int dz = 0; dz < 3; ++dz) {
                 const int iz = cell_part(tcell[2] + dz, 2) | (oct_part(tcell[2] + dz, 2) << 6);
                 float P0[3] = {0.f, 0.f, 0.f}, P1[3] = {0.f, 0.f, 0.f}, P2[3] = {0.f, 0.f, 0.f};
@@ -454,12 +446,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
         const float fsy = (float)sy, fsz = (float)sz;
         const int nnz = *s_nnz;
         if (grp < 3) {
-#ifdef SPK_SPREAD
-            const int third = (nnz + 2) / 3;
-            for (int k = warp, e = warp + grp * third; k < third; k += G2P2G_THREADS / 32, e += G2P2G_THREADS / 32) if (e < nnz) {
-#else
             for (int e = warp * 3 + grp; e < nnz; e += (G2P2G_THREADS / 32) * 3) {
-#endif
                 const int bin = s_binlist[e];
                 const int start = s_bin_start[bin], cnt = s_bin_cnt[bin];
                 float aM[3] = {0.f, 0.f, 0.f}, aX[3] = {0.f, 0.f, 0.f}, aY[3] = {0.f, 0.f, 0.f}, aZ[3] = {0.f, 0.f, 0.f}, aPm[3] = {0.f, 0.f, 0.f},
