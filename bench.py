@@ -269,6 +269,32 @@ def run_ours(args):
                        "spk_particles_read(pos, vel, phase) into pinned host buffers",
                "frames": args.e2e_frames, "ms_per_frame": wall * 1e3 / args.e2e_frames}
 
+    # ---- the reference testbed's frame loop (testbed_plugin.rs:490-588): step one frame, read pos / vel / phase back; no
+    # re-upload.  Blocking reads vs spk_particles_read_async (the copy of frame k overlaps frame k + 1)
+    frame_loop = None
+    if world == 1 and args.e2e_frames > 0:
+        frame_loop = {}
+        for mode in ("blocking", "async"):
+            subs = 0
+            for it in range(1 + max(4, args.e2e_frames * 2)):
+                if it == 1:  # the first frame warms up (async staging buffers are allocated on first use)
+                    ctx.read_wait()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    subs = 0
+                _, t = ctx.step(frame, sc.gravity)
+                subs += t.num_substeps
+                for w, o in outs.items():
+                    if mode == "async":
+                        ctx.read_async(w, o[0])
+                    else:
+                        ctx.read(w, out=o[0])
+            ctx.read_wait()
+            torch.cuda.synchronize()
+            frame_loop[mode] = npart * subs / (time.perf_counter() - t0)
+        frame_loop["unit"] = UNIT
+        frame_loop["what"] = "spk_step(dt=1/60) + read-back of pos, vel, phase into pinned buffers per frame, no re-upload"
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -293,7 +319,7 @@ def run_ours(args):
                                    "Drucker-Prager sand over corotated block, cuboid floor+walls", "particles_per_gpu": npart,
                        "parallelism": f"x-slabs x{world}, halo accumulate over {'NVLink peer memory (device-initiated)' if args.halo == 'nvlink' else 'NCCL all-gather'}" if world > 1 else "single GPU", "l2": "inputs larger than L2 (particle state ~0.8 GB per GPU)"},
             "clocks": clocks, "gpu_launches": int(launches) if launches else None, "e2e": e2e, "roofline": roof, "cpu_baseline": base,
-            "reference_gpu": ref_gpu}
+            "reference_gpu": ref_gpu, "frame_loop": frame_loop}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -264,6 +264,14 @@ int spk_particles_len(const spk_ctx* ctx, size_t* out);
 /* CudaParticleSet::read_* (cuda_particle_set.rs:93-119): copies attribute `which` of the first n particles,
  * indexed by the caller's particle id (upload order), in the reference's struct layout, into host memory. */
 int spk_particles_read(spk_ctx* ctx, int which, void* dst, size_t n);
+/* Asynchronous frame read-back (the testbed reads positions / velocities / phases back after every frame with blocking
+ * copies, src/bin/.../testbed_plugin.rs:533-588): the attribute is unpacked into its own device staging buffer on the
+ * context stream and copied to `dst` on a separate copy stream; the call returns at once and the next spk_step can be
+ * enqueued immediately, so the device->host transfer overlaps the following frame.  `dst` should be pinned host memory and
+ * must stay valid until spk_particles_read_wait, which blocks until every outstanding read has landed.  One read per
+ * attribute may be in flight (a second one of the same attribute waits for the first). */
+int spk_particles_read_async(spk_ctx* ctx, int which, void* dst, size_t n);
+int spk_particles_read_wait(spk_ctx* ctx);
 
 /* CudaParticleModelSet::from_models / ensure_models_are_uploaded (cuda_particle_model_set.rs:27-84). */
 int spk_models_upload(spk_ctx* ctx, const SpkGpuParticleModel* models, size_t n);

@@ -215,8 +215,17 @@ size_t attr_size(int which) {
     }
 }
 
+// the 64-byte counter record reaches the host through MAPPED pinned memory written by a one-warp kernel, not through a DMA
+// copy: a copy would queue on the device-to-host copy engine behind any bulk read-back in flight
+// (spk_particles_read_async) and stall the substep loop until that transfer ends
+__global__ void publish_counters_kernel(const DeviceCounters* __restrict__ src, DeviceCounters* dst_mapped) {
+    reinterpret_cast<uint32_t*>(dst_mapped)[threadIdx.x] = reinterpret_cast<const uint32_t*>(src)[threadIdx.x];
+    __threadfence_system();
+}
 int read_counters(spk_ctx* c) {
-    CK(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, c->stream));
+    static_assert(sizeof(DeviceCounters) % 4 == 0 && sizeof(DeviceCounters) <= 128, "one warp copies the record");
+    publish_counters_kernel<<<1, sizeof(DeviceCounters) / 4, 0, c->stream>>>(c->d_counters, c->h_counters_dev);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     c->counters_fresh = true;
     return SPK_OK;
@@ -315,8 +324,9 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     CK(cudaMalloc((void**)&c->d_counters, sizeof(DeviceCounters)));
     CK(cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)));
-    CK(cudaHostAlloc((void**)&c->h_counters, sizeof(DeviceCounters), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&c->h_counters, sizeof(DeviceCounters), cudaHostAllocMapped));
     std::memset(c->h_counters, 0, sizeof(DeviceCounters));
+    CK(cudaHostGetDevicePointer((void**)&c->h_counters_dev, c->h_counters, 0));
     CK(cudaHostAlloc((void**)&c->h_upload, 64, cudaHostAllocDefault));
     // CudaSparseGrid::with_capacity: next_power_of_two().max(1024) blocks (cuda_sparse_grid.rs:53-54); the hash map holds
     // twice as many slots (50 % maximum load factor, cuda_sparse_grid.rs:219)
@@ -342,6 +352,11 @@ int spk_ctx_destroy(spk_ctx* c) {
     free_grid(c->grid[0]); free_grid(c->grid[1]);
     dev_free(c->slot_cnt); dev_free(c->dispatch); dev_free(c->models); dev_free(c->colliders); dev_free(c->collider_data); dev_free(c->d_counters);
     if (c->staging) cudaFree(c->staging);
+    cudaStreamSynchronize(c->halo_stream);
+    for (int k = 0; k < 8; ++k) {
+        if (c->async_buf[k]) cudaFree(c->async_buf[k]);
+        if (c->async_ready[k]) { cudaEventDestroy(c->async_ready[k]); cudaEventDestroy(c->async_done[k]); }
+    }
     if (c->dist_arena) cudaFree(c->dist_arena);
     if (c->dist_peer_ids) cudaFree(c->dist_peer_ids);
     if (c->dist_push_ptrs) cudaFree(c->dist_push_ptrs);
@@ -392,6 +407,45 @@ int spk_particles_read(spk_ctx* c, int which, void* dst, size_t n) {
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, c->staging, n * sz, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+
+int spk_particles_read_async(spk_ctx* c, int which, void* dst, size_t n) {
+    if (!c || (n && !dst) || n > c->n || which < 0 || which >= 8) return SPK_EINVAL;
+    const size_t sz = attr_size(which);
+    if (!sz) return SPK_EINVAL;
+    if (n == 0) return SPK_OK;
+    CK(cudaSetDevice(c->device));
+    if (!c->async_ready[which]) {
+        CK(cudaEventCreateWithFlags(&c->async_ready[which], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->async_done[which], cudaEventDisableTiming));
+    }
+    if (c->async_bytes[which] < c->n * sz) {
+        if (c->async_inflight[which]) CK(cudaEventSynchronize(c->async_done[which]));
+        if (c->async_buf[which]) cudaFree(c->async_buf[which]);
+        c->async_buf[which] = nullptr;
+        c->async_bytes[which] = 0;
+        CK(cudaMalloc(&c->async_buf[which], c->n * sz));
+        c->async_bytes[which] = c->n * sz;
+    }
+    // the previous copy out of this staging buffer must have finished before it is overwritten
+    if (c->async_inflight[which]) CK(cudaStreamWaitEvent(c->stream, c->async_done[which], 0));
+    const uint32_t* perm = (which == SPK_ATTR_SORTED_IDS && c->sorted_valid) ? c->perm : nullptr;
+    unpack_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->pb[c->cur], c->vel, c->cold, perm, which, c->async_buf[which], c->n);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->async_ready[which], c->stream));
+    CK(cudaStreamWaitEvent(c->halo_stream, c->async_ready[which], 0));
+    CK(cudaMemcpyAsync(dst, c->async_buf[which], n * sz, cudaMemcpyDeviceToHost, c->halo_stream));
+    CK(cudaEventRecord(c->async_done[which], c->halo_stream));
+    c->async_inflight[which] = true;
+    return SPK_OK;
+}
+
+int spk_particles_read_wait(spk_ctx* c) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->halo_stream));
+    for (auto& f : c->async_inflight) f = false;
     return SPK_OK;
 }
 

@@ -145,11 +145,15 @@ struct spk_ctx {
     int g2p2g_mode;       // 0: per-particle shared atomics, 1: cell-binned register accumulation (default)
     // counters
     DeviceCounters* d_counters;
-    DeviceCounters* h_counters; // pinned
+    DeviceCounters* h_counters; // pinned, mapped
+    DeviceCounters* h_counters_dev; // device address of h_counters
     unsigned long long* h_upload; // pinned 8-byte staging for dt_acc -> device
     bool counters_fresh;         // h_counters was read after the last kernel that writes d_counters
     // scratch for read-back / staging
     void* staging; size_t staging_bytes;
+    // asynchronous read-back: one device staging buffer + two events per attribute; copies run on halo_stream
+    void* async_buf[8]; size_t async_bytes[8];
+    cudaEvent_t async_ready[8], async_done[8]; bool async_inflight[8];
     // multi-GPU (all zero / null in single-GPU runs)
     DistState dist;
     char* dist_arena; size_t dist_arena_bytes; uint32_t dist_cap_hash;

@@ -70,6 +70,17 @@ class SingleGpuMpmContext(Engine):
     def step(self, params: abi.SolverParameters, gravity, timings: bool = True):
         return CudaMpmPipeline().step(params, gravity, [self], timings)
 
+    def read_async(self, which: int, out: np.ndarray):
+        """enqueue the read-back of one attribute into `out` (pinned memory for real overlap) and return at once; the next
+        step can be issued immediately.  `read_wait()` blocks until every outstanding read has landed."""
+        n = len(self)
+        if out.dtype != abi.ATTR_DTYPES[which] or len(out) < n or not out.flags.c_contiguous:
+            raise abi.SparklError(abi.EINVAL, "output buffer has the wrong dtype / length")
+        self._call("particles_read_async", which, _ptr(out), n)
+
+    def read_wait(self):
+        self._call("particles_read_wait")
+
 
 class CudaParticleSet:
     def __init__(self, ctx: SingleGpuMpmContext):

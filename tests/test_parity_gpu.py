@@ -160,6 +160,31 @@ def test_ragged_blocks_and_chunk_boundaries(oracle):
     _run_frames(g, o, sc, 3, lambda s: 5e-5 * (1 + 3 * s))
 
 
+def test_async_readback_matches_blocking_reads():
+    """spk_particles_read_async / _wait (the testbed's per-frame read-back, §8f-2): same bytes as the blocking reads, several
+    attributes in flight, frames enqueued back to back"""
+    from sparkl_b200.pipeline import context_from_scene
+    sc = scenes.jitter(scenes.sand3(12, 6, 8), 0.02, seed=8)
+    g = context_from_scene(sc)
+    n = len(sc.particles)
+    for frame in range(3):
+        g.step(sc.params, sc.gravity)
+        outs = {w: np.empty(n, abi.ATTR_DTYPES[w]) for w in (abi.ATTR_POSITION, abi.ATTR_VELOCITY, abi.ATTR_PHASE, abi.ATTR_VOLUME)}
+        for w, o in outs.items():
+            g.read_async(w, o)
+        if frame < 2:
+            g.read_wait()
+            for w, o in outs.items():
+                assert np.array_equal(o, g.read(w)), (frame, w)
+        else:  # enqueue the next frame before waiting: the copies must hold the state of THIS frame
+            want = {w: g.read(w) for w in outs}
+            g.read_async(abi.ATTR_POSITION, outs[abi.ATTR_POSITION])  # a second read of the same attribute queues behind the first
+            g.step(sc.params, sc.gravity)
+            g.read_wait()
+            for w, o in outs.items():
+                assert np.array_equal(o, want[w]), (frame, w)
+
+
 def test_append_remove_read_roundtrip(oracle):
     sc = scenes.jitter(scenes.sand3(6, 4, 4), 0.01, seed=5)
     from sparkl_b200.pipeline import context_from_scene
