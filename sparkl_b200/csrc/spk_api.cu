@@ -387,6 +387,7 @@ int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkP
     const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (64 * 8 * 50)) * 4u, 2048u);
     GridBuffers& next = c->grid[1 - c->gcur];
     GridBuffers& curr = c->grid[c->gcur];
+    if (c->dist_arena && want > c->dist_cap_hash) return SPK_EOVERFLOW; // the arena shared with the peers cannot grow
     if (next.cap_hash < want) { CK(alloc_grid(c, next, want)); CK(ensure_slot_scratch(c, want)); }
     if (curr.cap_hash < want && curr.nab_host == 0) CK(alloc_grid(c, curr, want)); // empty: nothing to preserve
     CK(ensure_dispatch(c));

@@ -589,11 +589,11 @@ cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) {
     P.peer_ids = c->dist_peer_ids;
     P.peer_hacc = c->dist_push_ptrs;
     { cudaError_t e = cudaMemsetAsync(&c->d_counters->dt_raw_bits, 0x7f, 4, c->stream); if (e != cudaSuccess) return e; }
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(g2p2g_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        cudaFuncSetAttribute(g2p2g_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        configured = true;
+    if (!c->g2p2g_configured) { // a function attribute is per device: once per context, not once per process
+        cudaError_t e = cudaFuncSetAttribute(g2p2g_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        if (e != cudaSuccess) return e;
+        c->g2p2g_configured = true;
     }
     if (c->g2p2g_mode == 0) g2p2g_kernel<0><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
     else g2p2g_kernel<1><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);

@@ -143,6 +143,7 @@ struct spk_ctx {
     DispatchEntry* dispatch; uint32_t dispatch_cap;
     uint32_t chunk;       // particles per g2p2g dispatch entry
     int g2p2g_mode;       // 0: per-particle shared atomics, 1: cell-binned register accumulation (default)
+    bool g2p2g_configured; // the >48 KB dynamic shared memory opt-in was set on this context's device
     // counters
     DeviceCounters* d_counters;
     DeviceCounters* h_counters; // pinned, mapped
