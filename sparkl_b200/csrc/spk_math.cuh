@@ -95,8 +95,11 @@ __device__ __forceinline__ void svd3_complete_basis(Mat3& U, float* sv, bool* ok
             w2 = U.m[3 * a1 + 0] * U.m[3 * a2 + 1] - U.m[3 * a1 + 1] * U.m[3 * a2 + 0];
         } else {
             // at most one valid column k: any unit vector orthogonal to it
-            const int k = ok[a1] ? a1 : a2;
-            float kx = ok[k] ? U.m[3 * k] : 0.f, ky = ok[k] ? U.m[3 * k + 1] : 0.f, kz = ok[k] ? U.m[3 * k + 2] : 0.f;
+            // (selects on compile-time indices only: a run-time column index would force U into local memory on the hot path too)
+            const bool use1 = ok[a1], use2 = !ok[a1] && ok[a2];
+            const float kx = use1 ? U.m[3 * a1] : (use2 ? U.m[3 * a2] : 0.f);
+            const float ky = use1 ? U.m[3 * a1 + 1] : (use2 ? U.m[3 * a2 + 1] : 0.f);
+            const float kz = use1 ? U.m[3 * a1 + 2] : (use2 ? U.m[3 * a2 + 2] : 0.f);
             float ex = fabsf(kx) <= fabsf(ky) && fabsf(kx) <= fabsf(kz) ? 1.f : 0.f;
             float ey = (ex == 0.f && fabsf(ky) <= fabsf(kz)) ? 1.f : 0.f;
             float ez = (ex == 0.f && ey == 0.f) ? 1.f : 0.f;

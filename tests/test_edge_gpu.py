@@ -1,0 +1,74 @@
+"""Edge cases of the hot path on the GPU, product vs oracle: sparse-grid hash-map growth (grow-and-retry,
+cuda_sparse_grid.rs:162-253), negative / far / NaN coordinates (block keys saturate like Rust's `as i64`), failed and static
+particles (particle_updater.rs:155-165, 240-243), a model table with unused entries."""
+import numpy as np
+import pytest
+
+from sparkl_b200 import abi, scenes
+from tests import util
+from tests.test_parity_gpu import _engines, _run_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene_from_points(pts, model_index=0):
+    sc = scenes.sand3(1, 1, 1)
+    sc.particles = abi.particles_from_positions(np.asarray(pts, np.float32), model_index, 0.05, 2700.0)
+    return sc
+
+
+def test_hash_map_grows_when_blocks_outnumber_the_estimate(oracle):
+    """3 000 isolated particles -> ~24 000 active blocks against an initial capacity of 1 024: several grow-and-retry rounds"""
+    rng = np.random.Generator(np.random.PCG64(5))
+    g3 = np.stack(np.meshgrid(np.arange(15), np.arange(14), np.arange(15), indexing="ij"), -1).reshape(-1, 3)[:3000]
+    pts = 3.0 + g3 * 1.7 + rng.uniform(-0.05, 0.05, (3000, 3))
+    sc = _scene_from_points(pts)
+    sc.colliders = []
+    g, o = _engines(sc, oracle)
+    ig, io = g.stage_sort(), o.stage_sort()
+    assert ig.num_active_blocks == io.num_active_blocks and ig.num_active_blocks > 20000
+    assert ig.hashmap_capacity >= 2 * ig.num_active_blocks
+    util.assert_membership_equal(util.canonical_sort_state(g), util.canonical_sort_state(o), util.boundary_particles(pts, sc.cell_width), "after growth")
+    g2, o2 = _engines(sc, oracle)
+    _run_frames(g2, o2, sc, 3, lambda s: 2e-5 * (1 + 3 * s))
+
+
+def test_negative_far_and_nan_coordinates(oracle):
+    pts = np.array([[-3.33, -0.01, -7.9], [-3.31, -0.02, -7.92], [1.0e4, 2.0, 3.0], [-2.0e4, 5.0, 1.0e4], [0.1, 0.1, 0.1], [0.3, 0.1, 0.1]], np.float32)
+    sc = _scene_from_points(pts)
+    sc.colliders = []
+    g, o = _engines(sc, oracle)
+    ig, io = g.stage_sort(), o.stage_sort()
+    assert ig.num_active_blocks == io.num_active_blocks
+    util.assert_membership_equal(util.canonical_sort_state(g), util.canonical_sort_state(o), np.zeros(len(pts), bool), "negative / far coordinates")
+    # a NaN coordinate saturates to cell 0 (Rust `as i64`): same block on both sides, nothing else is disturbed
+    pts2 = pts.copy()
+    pts2[4, 1] = np.nan
+    sc2 = _scene_from_points(pts2)
+    sc2.colliders = []
+    g2, o2 = _engines(sc2, oracle)
+    g2.stage_sort(); o2.stage_sort()
+    cg, co = util.canonical_sort_state(g2), util.canonical_sort_state(o2)
+    assert np.array_equal(cg[0], co[0]) and all(np.array_equal(cg[1][k], co[1][k]) for k in co[1])
+
+
+def test_failed_and_static_particles(oracle):
+    sc = scenes.jitter(scenes.sand3(8, 4, 6), 0.02, seed=12)
+    n = len(sc.particles)
+    sc.particles.status["failed"][::7] = 1
+    sc.particles.status["is_static"][3::11] = 1
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 6, lambda s: 2e-5 * (1 + 3 * s))
+    st = g.read(abi.ATTR_STATUS)
+    assert st["failed"][::7].all() and np.array_equal(st["is_static"], sc.particles.status["is_static"])
+    v = g.read(abi.ATTR_VELOCITY)["vector"]
+    assert not v[3::11][sc.particles.status["failed"][3::11] == 0].any(), "static particles keep a zero velocity"
+    assert n == len(g)
+
+
+def test_model_table_with_unused_entries(oracle):
+    sc = scenes.jitter(scenes.sand3(6, 4, 4), 0.02, seed=13)
+    sc.models = sc.models + [abi.ParticleModel(abi.NeoHookeanElasticity(1.0e6, 0.3)), abi.ParticleModel(abi.MonaghanSphEos(1.0e6, 7, 1.0e-3))]
+    sc.particles.status["model_index"][::5] = 2  # a few Neo-Hookean particles inside the sand
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 4, lambda s: 2e-5 * (1 + 3 * s))
