@@ -280,7 +280,10 @@ int spk_colliders_upload(spk_ctx* ctx, const SpkGpuCollider* colliders, size_t n
 
 /* CudaMpmPipeline::step (cuda_mpm_pipeline.rs:262-659): advances all contexts by params->dt with adaptive
  * substeps; writes the simulated time (params.dt - remaining) to *simulated_time_out.  nctx must be 1 per
- * process (one process per GPU; multi-GPU runs use the stage calls below plus the halo calls). */
+ * process (one process per GPU; multi-GPU runs attach the contexts with spk_dist_* and then call spk_step on every rank).
+ * With timings_or_null == NULL the call returns once the frame is ENQUEUED (every substep still reads its 64-byte counter
+ * record back, so only the tail of the last substep is outstanding): consecutive frames then run back to back on the GPU.
+ * All other entry points are ordered on the context's stream; spk_ctx_synchronize() waits for completion. */
 int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float gravity[3],
              SpkStepTimings* timings_or_null, float* simulated_time_out);
 
@@ -335,6 +338,11 @@ int spk_grid_read_nodes(spk_ctx* ctx, int which_grid, SpkGpuGridNode* dst, uint3
 int spk_grid_read_dispatch(spk_ctx* ctx, SpkDispatchBlock2ActiveBlock* dst, uint32_t n);
 /* raw device pointers for zero-copy wrappers (torch / NCCL plumbing); valid until the next upload/append */
 int spk_device_ptr(spk_ctx* ctx, int which /* SPK_ATTR_* */, void** out);
+/* Kernel timing without perturbing the run (≙ the g2p2g field of CudaDeviceTimings, cuda_mpm_pipeline.rs:56-85, which the
+ * reference fills with blocking event reads): with `enable` != 0 every following g2p2g launch is bracketed by a pair of CUDA
+ * events recorded on the context's stream WITHOUT synchronising (up to 256 launches); each call returns the summed duration
+ * and the number of launches recorded since the previous call, and resets the ring. */
+int spk_g2p2g_time(spk_ctx* ctx, int enable, float* total_ms_out, uint32_t* launches_out);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ EXPORTS = [
     "spk_models_upload", "spk_colliders_upload", "spk_step", "spk_frame_begin", "spk_stage_sort", "spk_stage_reset_grid",
     "spk_stage_estimate_dt", "spk_dt_acc_get", "spk_dt_acc_set", "spk_stage_g2p2g", "spk_stage_grid_update",
     "spk_halo_begin", "spk_halo_active_keys", "spk_halo_tag", "spk_halo_count", "spk_halo_pack", "spk_halo_merge", "spk_grid_num_active_blocks",
-    "spk_grid_read_headers", "spk_grid_read_nodes", "spk_grid_read_dispatch", "spk_device_ptr",
+    "spk_grid_read_headers", "spk_grid_read_nodes", "spk_grid_read_dispatch", "spk_device_ptr", "spk_g2p2g_time",
     "spk_dist_export", "spk_dist_attach", "spk_dist_detach", "spk_dist_info",
 ]
 
@@ -53,6 +53,7 @@ def lib():
         l.spk_halo_pack.argtypes = [vp, vp, vp, C.c_uint32]
         l.spk_halo_merge.argtypes = [vp, vp, vp, C.c_uint32]
         l.spk_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        l.spk_g2p2g_time.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
         l.spk_dist_export.argtypes = [vp, vp]
         l.spk_dist_attach.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
         l.spk_dist_detach.argtypes = [vp]

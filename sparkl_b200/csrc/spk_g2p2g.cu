@@ -595,8 +595,11 @@ cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) {
         if (e != cudaSuccess) return e;
         c->g2p2g_configured = true;
     }
+    const bool timed = c->kev_on && c->kev_count < 256;
+    if (timed) cudaEventRecord(c->kev[2 * c->kev_count], c->stream);
     if (c->g2p2g_mode == 0) g2p2g_kernel<0><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
     else g2p2g_kernel<1><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
+    if (timed) { cudaEventRecord(c->kev[2 * c->kev_count + 1], c->stream); c->kev_count += 1; }
     c->launches += 1;
     c->g2p2g_launches += 1;
     c->cur = 1 - c->cur; // the next buffer now holds the particles, physically in sorted order

@@ -164,6 +164,9 @@ struct spk_ctx {
     int dist_fused_push;                 // 1: g2p2g's flush pushes shared blocks itself (default); 0: separate push kernel (A/B)
     // timing
     cudaEvent_t ev[12];
+    cudaEvent_t ev_counters;
+    // ring of event pairs around every g2p2g launch (recorded without synchronising; read by spk_g2p2g_time)
+    cudaEvent_t kev[2 * 256]; uint32_t kev_count; bool kev_on; // recorded right after the counter record has been published to the host
     uint32_t launches;
     uint32_t g2p2g_launches;
     int sm_count;

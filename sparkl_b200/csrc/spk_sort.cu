@@ -150,10 +150,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned
 }
 
 // neighbour-block tables: for block b, ids of key + {0,1}^3 in the next grid (always present) and in the previous grid
-__global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, uint32_t nab) {
+// (launched for the grid's block CAPACITY before the host has read the block count back, so that the read-back overlaps this
+// kernel and scatter_perm_kernel; the true count comes from the device-side record)
+__global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, const DeviceCounters* __restrict__ counters) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t b = t >> 3, o = t & 7;
-    if (b >= nab) return;
+    if (b >= counters->nab || b >= next.cap_blocks) return;
     const unsigned long long key = spk_key_offset(next.blk_key[b], (int)o);
     next.nbr_self[b * 8 + o] = spk_hash_get(next, key);
     next.nbr_prev[b * 8 + o] = spk_hash_get(prev, key);
@@ -201,9 +203,9 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c) {
     GridBuffers& g = c->grid[1 - c->gcur];
     GridBuffers& prev = c->grid[c->gcur];
     cudaStream_t s = c->stream;
-    const uint32_t nab = g.nab_host, n = (uint32_t)c->n;
-    if (nab) {
-        build_tables_kernel<<<(nab * 8 + 255) / 256, 256, 0, s>>>(g, prev, nab);
+    const uint32_t n = (uint32_t)c->n;
+    {
+        build_tables_kernel<<<(g.cap_blocks * 8 + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters);
         c->launches += 1;
     }
     if (n) {

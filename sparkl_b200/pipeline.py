@@ -81,6 +81,13 @@ class SingleGpuMpmContext(Engine):
     def read_wait(self):
         self._call("particles_read_wait")
 
+    def g2p2g_time(self, enable: bool = True):
+        """(summed g2p2g kernel time in ms, launches) since the previous call, measured with CUDA events recorded on the
+        context's stream without synchronising; `enable` arms / disarms the recording for the launches that follow"""
+        ms, n = C.c_float(), C.c_uint32()
+        self._call("g2p2g_time", int(enable), C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
 
 class CudaParticleSet:
     def __init__(self, ctx: SingleGpuMpmContext):
