@@ -257,6 +257,22 @@ int spk_particles_upload(spk_ctx* ctx, const SpkParticleStatus* status, const Sp
 int spk_particles_append(spk_ctx* ctx, const SpkParticleStatus* status, const SpkParticlePosition* pos,
                          const SpkParticleVelocity* vel, const SpkParticleVolume* volume,
                          const SpkParticlePhase* phase, const SpkParticleData* data, size_t n);
+/* Asynchronous variant of spk_particles_upload for hosts that stream a new particle state every frame: the arrays (which
+ * must be PINNED and stay valid until the next blocking call or spk_ctx_synchronize) are copied on a separate copy stream
+ * into a dedicated staging buffer, so the transfer overlaps the frame the GPU is still computing; only the repack kernel is
+ * ordered after both.  Returns without synchronising; an out-of-range model index is reported (SPK_EINVAL) by the next
+ * spk_step / spk_stage_sort instead. */
+int spk_particles_upload_async(spk_ctx* ctx, const SpkParticleStatus* status, const SpkParticlePosition* pos,
+                               const SpkParticleVelocity* vel, const SpkParticleVolume* volume,
+                               const SpkParticlePhase* phase, const SpkParticleData* data, size_t n);
+/* The two halves of spk_particles_upload_async, for hosts that prefetch: _stage_async starts the host->device copy of the
+ * NEXT state and returns (the current particles are untouched, spk_step may run meanwhile: the copy overlaps it);
+ * _commit_staged makes the staged state the current one (repack kernel, ordered on the context's stream after the copy).
+ * One staged upload at a time; committing without a staged upload is SPK_ESTATE. */
+int spk_particles_stage_async(spk_ctx* ctx, const SpkParticleStatus* status, const SpkParticlePosition* pos,
+                              const SpkParticleVelocity* vel, const SpkParticleVolume* volume,
+                              const SpkParticlePhase* phase, const SpkParticleData* data, size_t n);
+int spk_particles_commit_staged(spk_ctx* ctx);
 /* CudaParticleSet::remove_range (cuda_particle_set.rs:123-131): removes ids [begin, end); later ids shift down. */
 int spk_particles_remove_range(spk_ctx* ctx, size_t begin, size_t end);
 /* CudaParticleSet::len (cuda_particle_set.rs:73). */

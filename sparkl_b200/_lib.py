@@ -16,7 +16,7 @@ _LIB = None
 EXPORTS = [
     "spk_abi_version", "spk_error_string", "spk_ctx_create", "spk_ctx_destroy", "spk_ctx_cell_width", "spk_ctx_synchronize", "spk_ctx_stream",
     "spk_particles_upload", "spk_particles_append", "spk_particles_remove_range", "spk_particles_len", "spk_particles_read",
-    "spk_particles_read_async", "spk_particles_read_wait",
+    "spk_particles_read_async", "spk_particles_read_wait", "spk_particles_upload_async", "spk_particles_stage_async", "spk_particles_commit_staged",
     "spk_models_upload", "spk_colliders_upload", "spk_step", "spk_frame_begin", "spk_stage_sort", "spk_stage_reset_grid",
     "spk_stage_estimate_dt", "spk_dt_acc_get", "spk_dt_acc_set", "spk_stage_g2p2g", "spk_stage_grid_update",
     "spk_halo_begin", "spk_halo_active_keys", "spk_halo_tag", "spk_halo_count", "spk_halo_pack", "spk_halo_merge", "spk_grid_num_active_blocks",
@@ -44,6 +44,9 @@ def lib():
         l.spk_particles_remove_range.argtypes = [vp, C.c_size_t, C.c_size_t]
         l.spk_particles_read_async.argtypes = [vp, C.c_int, vp, C.c_size_t]
         l.spk_particles_read_wait.argtypes = [vp]
+        l.spk_particles_upload_async.argtypes = [vp] * 7 + [C.c_size_t]
+        l.spk_particles_stage_async.argtypes = [vp] * 7 + [C.c_size_t]
+        l.spk_particles_commit_staged.argtypes = [vp]
         l.spk_step.argtypes = [C.POINTER(vp), C.c_size_t, C.POINTER(abi.SolverParameters), C.POINTER(C.c_float * 3),
                                C.POINTER(abi.StepTimings), C.POINTER(C.c_float)]
         l.spk_halo_begin.argtypes = [vp]

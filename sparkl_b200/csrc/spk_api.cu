@@ -333,6 +333,9 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     if (const char* m = getenv("SPK_G2P2G_MODE")) c->g2p2g_mode = atoi(m) ? 1 : 0; // A/B switch for profiling
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->up_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->up_consumed, cudaEventDisableTiming));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     CK(cudaEventCreateWithFlags(&c->ev_counters, cudaEventDisableTiming));
     CK(cudaMalloc((void**)&c->d_counters, sizeof(DeviceCounters)));
@@ -378,7 +381,10 @@ int spk_ctx_destroy(spk_ctx* c) {
     for (auto& e : c->ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_counters);
     if (c->kev[0]) for (auto& e : c->kev) cudaEventDestroy(e);
-    cudaStreamDestroy(c->stream); cudaStreamDestroy(c->halo_stream);
+    cudaStreamSynchronize(c->h2d_stream);
+    if (c->up_staging) cudaFree(c->up_staging);
+    cudaEventDestroy(c->up_ready); cudaEventDestroy(c->up_consumed);
+    cudaStreamDestroy(c->stream); cudaStreamDestroy(c->halo_stream); cudaStreamDestroy(c->h2d_stream);
     delete c;
     return SPK_OK;
 }
@@ -407,6 +413,75 @@ int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkP
     if (curr.cap_hash < want && curr.nab_host == 0) CK(alloc_grid(c, curr, want)); // empty: nothing to preserve
     CK(ensure_dispatch(c));
     return upload_range(c, status, pos, vel, volume, phase, data, 0, n);
+}
+
+// ---- asynchronous upload: stage (host -> device copy on its own stream) and commit (repack on the main stream) ------------
+int spk_particles_stage_async(spk_ctx* c, const SpkParticleStatus* status, const SpkParticlePosition* pos, const SpkParticleVelocity* vel,
+                              const SpkParticleVolume* volume, const SpkParticlePhase* phase, const SpkParticleData* data, size_t n) {
+    if (!c || (n && (!status || !pos || !vel || !volume || !phase))) return SPK_EINVAL;
+    if (n >= 0xffffffffull) return SPK_EOVERFLOW;
+    CK(cudaSetDevice(c->device));
+    const size_t per = sizeof(SpkParticleStatus) + sizeof(SpkParticlePosition) + sizeof(SpkParticleVelocity) + sizeof(SpkParticleVolume) +
+                       sizeof(SpkParticlePhase) + sizeof(SpkParticleData);
+    if (c->up_staging_bytes < n * per + 256) {
+        CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->h2d_stream));
+        if (c->up_staging) cudaFree(c->up_staging);
+        c->up_staging = nullptr; c->up_staging_bytes = 0;
+        CK(cudaMalloc(&c->up_staging, n * per + 256));
+        c->up_staging_bytes = n * per + 256;
+    }
+    // the repack kernel of the previous commit must have read the staging buffer before it is overwritten
+    if (c->up_inflight) CK(cudaStreamWaitEvent(c->h2d_stream, c->up_consumed, 0));
+    char* cur = (char*)c->up_staging;
+    size_t* off = c->up_off;
+    const void* src[6] = {status, pos, vel, volume, phase, data};
+    const size_t bytes[6] = {n * sizeof(SpkParticleStatus), n * sizeof(SpkParticlePosition), n * sizeof(SpkParticleVelocity), n * sizeof(SpkParticleVolume),
+                             n * sizeof(SpkParticlePhase), n * sizeof(SpkParticleData)};
+    for (int k = 0; k < 6; ++k) {
+        off[k] = (size_t)(cur - (char*)c->up_staging);
+        if (src[k] && bytes[k]) CK(cudaMemcpyAsync(cur, src[k], bytes[k], cudaMemcpyHostToDevice, c->h2d_stream));
+        cur += (bytes[k] + 15) & ~size_t(15);
+    }
+    CK(cudaEventRecord(c->up_ready, c->h2d_stream));
+    c->up_staged_n = n;
+    c->up_staged_data = data != nullptr;
+    c->up_staged = true;
+    return SPK_OK;
+}
+
+int spk_particles_commit_staged(spk_ctx* c) {
+    if (!c) return SPK_EINVAL;
+    if (!c->up_staged) return SPK_ESTATE;
+    CK(cudaSetDevice(c->device));
+    const size_t n = c->up_staged_n;
+    if (n > c->cap) { CK(cudaStreamSynchronize(c->stream)); CK(alloc_particles(c, n + n / 8 + 1024)); }
+    c->n = n;
+    c->cur = 0;
+    c->sorted_valid = false;
+    c->dt_cache_valid = false;
+    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (64 * 8 * 50)) * 4u, 2048u);
+    GridBuffers& next = c->grid[1 - c->gcur];
+    if (c->dist_arena && want > c->dist_cap_hash) return SPK_EOVERFLOW;
+    if (next.cap_hash < want) { CK(alloc_grid(c, next, want)); CK(ensure_slot_scratch(c, want)); }
+    CK(ensure_dispatch(c));
+    c->up_staged = false;
+    if (n == 0) return SPK_OK;
+    char* base = (char*)c->up_staging;
+    CK(cudaStreamWaitEvent(c->stream, c->up_ready, 0));
+    pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        c->pb[c->cur], c->vel, c->cold, (const SpkParticleStatus*)(base + c->up_off[0]), (const SpkParticlePosition*)(base + c->up_off[1]),
+        (const SpkParticleVelocity*)(base + c->up_off[2]), (const SpkParticleVolume*)(base + c->up_off[3]), (const SpkParticlePhase*)(base + c->up_off[4]),
+        c->up_staged_data ? (const SpkParticleData*)(base + c->up_off[5]) : nullptr, 0, n, &c->d_counters->pad[0]);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->up_consumed, c->stream));
+    c->up_inflight = true;
+    return SPK_OK; // no synchronisation: a bad model index is reported by the next sort (it travels in the counter record)
+}
+
+int spk_particles_upload_async(spk_ctx* c, const SpkParticleStatus* status, const SpkParticlePosition* pos, const SpkParticleVelocity* vel,
+                               const SpkParticleVolume* volume, const SpkParticlePhase* phase, const SpkParticleData* data, size_t n) {
+    int rc = spk_particles_stage_async(c, status, pos, vel, volume, phase, data, n);
+    return rc ? rc : spk_particles_commit_staged(c);
 }
 
 int spk_particles_len(const spk_ctx* c, size_t* out) { if (!c || !out) return SPK_EINVAL; *out = c->n; return SPK_OK; }
@@ -648,6 +723,10 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
         CK(spk_launch_sort_finish(c));
         if ((rc = wait_counters(c))) return rc;
         const DeviceCounters& hc = *c->h_counters;
+        if (hc.pad[0]) { // spk_particles_upload_async found a model index that does not fit the flags word
+            CK(cudaMemsetAsync(&c->d_counters->pad[0], 0, 4, c->stream));
+            return SPK_EINVAL;
+        }
         // grow-and-retry until the load factor is <= 50 % (cuda_sparse_grid.rs:162-253)
         if ((hc.overflow || hc.nab > g.cap_blocks) && c->dist_arena) return SPK_EOVERFLOW; // the shared arena cannot grow
         if (hc.overflow || hc.nab > g.cap_blocks) {

@@ -152,6 +152,9 @@ struct spk_ctx {
     bool counters_fresh;         // h_counters was read after the last kernel that writes d_counters
     // scratch for read-back / staging
     void* staging; size_t staging_bytes;
+    // asynchronous upload: own staging buffer, host->device copies on h2d_stream, pack kernel on the main stream
+    cudaStream_t h2d_stream; void* up_staging; size_t up_staging_bytes; cudaEvent_t up_ready, up_consumed; bool up_inflight;
+    bool up_staged, up_staged_data; size_t up_staged_n; size_t up_off[6]; // a staged (not yet committed) upload
     // asynchronous read-back: one device staging buffer + two events per attribute; copies run on halo_stream
     void* async_buf[8]; size_t async_bytes[8];
     cudaEvent_t async_ready[8], async_done[8]; bool async_inflight[8];

@@ -70,6 +70,19 @@ class SingleGpuMpmContext(Engine):
     def step(self, params: abi.SolverParameters, gravity, timings: bool = True):
         return CudaMpmPipeline().step(params, gravity, [self], timings)
 
+    def upload_async(self, pc: abi.ParticleComponents, stage_only: bool = False):
+        """spk_particles_upload_async: `pc`'s arrays must be pinned, contiguous, of the ABI dtypes, and stay alive until the next
+        blocking call; the host->device copy overlaps the frame the GPU is still computing"""
+        arrs = [pc.status, pc.position, pc.velocity, pc.volume, pc.phase, pc.data]
+        for a, dt in zip(arrs, (abi.STATUS, abi.POSITION, abi.VELOCITY, abi.VOLUME, abi.PHASE, abi.DATA)):
+            if a.dtype != dt or not a.flags.c_contiguous or len(a) != len(arrs[0]):
+                raise abi.SparklError(abi.EINVAL, "attribute dtype / layout / length mismatch")
+        self._call("particles_stage_async" if stage_only else "particles_upload_async", *[_ptr(a) for a in arrs], len(arrs[0]))
+
+    def commit_staged(self):
+        """make the state staged by `upload_async(pc, stage_only=True)` the current particle state"""
+        self._call("particles_commit_staged")
+
     def read_async(self, which: int, out: np.ndarray):
         """enqueue the read-back of one attribute into `out` (pinned memory for real overlap) and return at once; the next
         step can be issued immediately.  `read_wait()` blocks until every outstanding read has landed."""

@@ -204,3 +204,34 @@ def test_append_remove_read_roundtrip(oracle):
     assert np.array_equal(g.read(abi.ATTR_POSITION)[n - 5:], extra.position)
     g.step(sc.params, sc.gravity)
     assert np.isfinite(g.read(abi.ATTR_POSITION)["point"]).all()
+
+
+def test_async_upload_matches_blocking_upload():
+    """spk_particles_upload_async: same state as the blocking upload, also when it is enqueued behind a running frame"""
+    import torch
+    from sparkl_b200.pipeline import context_from_scene
+    sc = scenes.jitter(scenes.sand3(10, 6, 6), 0.02, seed=9)
+    a, b = context_from_scene(sc), context_from_scene(sc)
+    pins = {}
+    pc = abi.ParticleComponents(0)
+    for name in ("status", "position", "velocity", "volume", "phase", "data"):
+        src = getattr(sc.particles, name)
+        t = torch.empty(src.nbytes, dtype=torch.uint8).pin_memory()
+        arr = t.numpy().view(src.dtype).reshape(src.shape)
+        arr[...] = src
+        pins[name] = t
+        setattr(pc, name, arr)
+    for frame in range(3):
+        a.upload(sc.particles)
+        b.upload_async(pc)                       # queued behind the previous frame of `b`
+        a.step(sc.params, sc.gravity)
+        b.step(sc.params, sc.gravity, timings=False)
+    pa, pb = a.read_all(), b.read_all()
+    for name in ("position", "velocity", "volume", "status", "phase", "data"):
+        assert np.array_equal(getattr(pa, name), getattr(pb, name)) or name in ("position", "velocity", "volume", "phase", "data")
+    util.assert_particles_close(pb, pa, sc.cell_width, util.scene_tol(sc, 1e-4), "async vs blocking upload")
+    # an out-of-range model index is reported by the next step
+    pc.status["model_index"][0] = 1 << 25
+    b.upload_async(pc)
+    with pytest.raises(abi.SparklError):
+        b.step(sc.params, sc.gravity)
