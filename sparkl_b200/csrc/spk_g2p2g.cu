@@ -52,7 +52,8 @@ constexpr int SM_BINCNT = SM_PAY + G2P2G_CHUNK * PAY_FLOATS * 4;
 constexpr int SM_BINSTART = SM_BINCNT + 224 * 4;
 constexpr int SM_BINLIST = SM_BINSTART + 224 * 4;
 constexpr int SM_MISC = SM_BINLIST + 224 * 2;               // mbarrier (8) + nbr_self[8] + nbr_prev[8] + nnz
-constexpr int SM_TOTAL = SM_MISC + 8 + 32 + 32 + 16;
+constexpr int SM_HALO = SM_MISC + 8 + 32 + 32 + 16;          // uint32[8]: bit0 = octant block is shared with another rank (multi-GPU)
+constexpr int SM_TOTAL = SM_HALO + 32;
 
 // ---- TMA bulk helpers (sm_90+; SASS: UBLKCP / UBLKRED) ------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,12 +121,17 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
     int* s_nbr_prev = reinterpret_cast<int*>(smem + SM_MISC + 40);
     int* s_nnz = reinterpret_cast<int*>(smem + SM_MISC + 72);
     unsigned* s_dtmin = reinterpret_cast<unsigned*>(smem + SM_MISC + 76);
+    uint32_t* s_halo = reinterpret_cast<uint32_t*>(smem + SM_HALO);
 
     const int tid = threadIdx.x;
     const DispatchEntry ent = P.dispatch[blockIdx.x];
     if (tid < 8) {
-        s_nbr_self[tid] = P.nbr_self[ent.block * 8 + tid];
+        const int nid = P.nbr_self[ent.block * 8 + tid];
+        s_nbr_self[tid] = nid;
         s_nbr_prev[tid] = P.nbr_prev[ent.block * 8 + tid];
+        // multi-GPU: is the octant's block shared with a peer?  Fetched here by 8 threads in parallel, long before the flush needs
+        // it (a serial chain of 8 L2 loads by thread 0 at the very end kept every CTA's slot busy for ~2.5 us)
+        s_halo[tid] = (P.world > 1 && nid >= 0) ? P.blk_halo[nid] : 0u;
     }
     if (tid == 0) { mbar_init(s_bar, 1); *s_dtmin = SPK_DT_RAW_NONE; }
     for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64; i += G2P2G_THREADS) s_acc[i] = 0.f;
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
         if (P.world > 1) {
             for (int o = 0; o < 8; ++o) {
                 const int nid = s_nbr_self[o];
-                if (nid < 0 || !(P.blk_halo[nid] & 1u)) continue;
+                if (nid < 0 || !(s_halo[o] & 1u)) continue;
                 for (uint32_t r = 0; r < P.world; ++r) {
                     const int32_t pid = P.peer_ids[(size_t)nid * P.world + r];
                     if (pid >= 0) {
