@@ -134,7 +134,7 @@ typedef struct SpkGpuParticleModel {
 
 /* ---------------------------------------------------------------- colliders
  * GpuCollider, 336 bytes: src_kernels/gpu_collider.rs:203-212 (offsets from the PTX).
- * Scope: Cuboid (tag 0) and HeightField (tag 1).  TriMesh / Polyline are SURVEY §8(f) "next" rows -> SPK_EUNSUPPORTED.
+ * Scope: Cuboid (tag 0), HeightField (tag 1) and Polyline (tag 3).  TriMesh is a SURVEY §8(f) "next" row -> SPK_EUNSUPPORTED.
  * The reference's HeightField payload is parry's `CudaHeightFieldPtr` (device pointers of ITS CUDA context,
  * src_kernels/gpu_collider.rs:14-18, src/cuda/cuda_collider_set.rs:71-86); here the payload carries a HOST description of
  * the same rapier `HeightField` (heights matrix + scale) and the library owns the device copy. */
@@ -150,6 +150,11 @@ typedef struct SpkGpuCollider {
             uint8_t bellow_heightfield_is_solid; /* always true in cuda_collider_set.rs:77 */
             uint8_t flip_interior;
         } heightfield;
+        struct {                      /* GpuColliderShape::Polyline (src_kernels/gpu_collider.rs:24-27,105-201): a closed polygon */
+            const float* vertices;    /* HOST pointer, num_vertices x (x, y, z); segment i joins vertex i and (i + 1) % n */
+            uint32_t num_vertices;
+            uint8_t flip_interior;
+        } polyline;
         uint8_t _bytes[288];
     } shape;
     float rotation[4];    /* unit quaternion, nalgebra coordinate order (i, j, k, w) */

@@ -796,8 +796,53 @@ static bool heightfield_project_point(const SpkGpuCollider& c, V3 pt, Real max_d
     out.point = quat_rotate(c.rotation, best) + tr;
     return true;
 }
+// polyline_project_point, src_kernels/gpu_collider.rs:105-201 (dim3), with parry3d's Segment::project_local_point_and_get_location
+// and Segment::planar_normal(2) restated
+static bool polyline_project_point(const SpkGpuCollider& c, V3 point, Projection& out) {
+    const auto& pl = c.shape.polyline;
+    const int n = (int)pl.num_vertices;
+    if (n == 0) return false;
+    float qinv[4] = {-c.rotation[0], -c.rotation[1], -c.rotation[2], c.rotation[3]};
+    V3 tr = v3(c.translation[0], c.translation[1], c.translation[2]);
+    V3 local_point = quat_rotate(qinv, point - tr);
+    auto vertex = [&](int i) { return v3(pl.vertices[3 * i], pl.vertices[3 * i + 1], pl.vertices[3 * i + 2]); };
+    struct Best { V3 proj; int loc; Real dist; int id; V3 a, b; bool is_inside; } best{};
+    bool have = false;
+    for (int i = 0; i < n; ++i) { // 1) the closest segment (:118-138)
+        V3 a = vertex(i), b = vertex((i + 1) % n);
+        V3 ab = b - a, ap = local_point - a;
+        Real ab_ap = dot(ab, ap), sqnab = dot(ab, ab);
+        V3 q; int loc;
+        if (ab_ap <= 0) { q = a; loc = 0; }
+        else if (ab_ap >= sqnab) { q = b; loc = 1; }
+        else { q = a + ab * (ab_ap / sqnab); loc = 2; }
+        Real dist = norm(local_point - q);
+        if (!have || dist < best.dist) { best = Best{q, loc, dist, i, a, b, q.x == local_point.x && q.y == local_point.y && q.z == local_point.z}; have = true; }
+    }
+    // 2) inside / outside (:140-186)
+    V3 dir = best.b - best.a;
+    Real nn = std::sqrt(dir.y * dir.y + dir.x * dir.x);
+    if (nn > FLT_EPSILON) {
+        V3 normal1 = v3(dir.y / nn, -dir.x / nn, 0);
+        Real side = dot(point - best.proj, normal1); // WORLD point minus LOCAL projection, as in the reference
+        if (best.loc == 2) best.is_inside = side <= 0;
+        else {
+            V3 dir2;
+            if (best.loc == 0) { int adj = best.id == 0 ? n - 1 : best.id - 1; dir2 = -(vertex((adj + 1) % n) - vertex(adj)); }
+            else { int adj = (best.id + 1) % n; dir2 = vertex((adj + 1) % n) - vertex(adj); }
+            Real d = dot(normal1, dir2), threshold = 1.0e-3f * norm(dir2);
+            best.is_inside = std::fabs(d) > threshold ? d >= 0 : side <= 0;
+        }
+    }
+    best.proj.z = local_point.z; // :190-193
+    if (pl.flip_interior) best.is_inside = !best.is_inside;
+    out.is_inside = best.is_inside;
+    out.point = quat_rotate(c.rotation, best.proj) + tr;
+    return true;
+}
 static bool collider_project(const SpkGpuCollider& c, V3 pt, Real max_dist, Projection& out) {
     if (c.shape_tag == SPK_SHAPE_HEIGHTFIELD) return heightfield_project_point(c, pt, max_dist, out);
+    if (c.shape_tag == SPK_SHAPE_POLYLINE) return polyline_project_point(c, pt, out);
     if (c.shape_tag != SPK_SHAPE_CUBOID) return false;
     out = cuboid_project_point(c, pt);
     return true;
@@ -957,7 +1002,8 @@ int orc_particles_read(orc_ctx* c, int which, void* dst, size_t n) {
 }
 int orc_models_upload(orc_ctx* c, const SpkGpuParticleModel* models, size_t n) { c->models.assign(models, models + n); return SPK_OK; }
 int orc_colliders_upload(orc_ctx* c, const SpkGpuCollider* cols, size_t n) {
-    for (size_t i = 0; i < n; ++i) if (cols[i].shape_tag != SPK_SHAPE_CUBOID && cols[i].shape_tag != SPK_SHAPE_HEIGHTFIELD) return SPK_EUNSUPPORTED;
+    for (size_t i = 0; i < n; ++i)
+        if (cols[i].shape_tag != SPK_SHAPE_CUBOID && cols[i].shape_tag != SPK_SHAPE_HEIGHTFIELD && cols[i].shape_tag != SPK_SHAPE_POLYLINE) return SPK_EUNSUPPORTED;
     c->colliders.assign(cols, cols + n);
     c->collider_data.assign(n, {});
     for (size_t i = 0; i < n; ++i)
@@ -966,6 +1012,11 @@ int orc_colliders_upload(orc_ctx* c, const SpkGpuCollider* cols, size_t n) {
             if (!hf.heights || hf.nrows < 2 || hf.ncols < 2) return SPK_EINVAL;
             c->collider_data[i].assign(hf.heights, hf.heights + (size_t)hf.nrows * hf.ncols);
             c->colliders[i].shape.heightfield.heights = c->collider_data[i].data();
+        } else if (cols[i].shape_tag == SPK_SHAPE_POLYLINE) {
+            const auto& pl = cols[i].shape.polyline;
+            if (pl.num_vertices && !pl.vertices) return SPK_EINVAL;
+            c->collider_data[i].assign(pl.vertices, pl.vertices + (size_t)pl.num_vertices * 3);
+            c->colliders[i].shape.polyline.vertices = c->collider_data[i].data();
         }
     return SPK_OK;
 }

@@ -81,7 +81,8 @@ impl B200MpmContext {
     /// ≙ CudaColliderSet::from_collider_set after the rapier → GpuCollider conversion.  Cuboid images pass unchanged; for a
     /// heightfield write tag 1 at offset 0 and a `SpkHeightFieldPayload` at offset 8 of the 336-byte image
     /// (`cuda_collider_set.rs:71-86` builds a `CudaHeightFieldPtr` there instead); pose / friction / boundary handling stay
-    /// at their offsets.  TriMesh / Polyline are rejected with SPK_EUNSUPPORTED.
+    /// at their offsets.  Polyline: tag 3, then { vertices: *const f32 (n x 3, host), num_vertices: u32, flip_interior: u8 } at
+    /// offset 8.  TriMesh is rejected with SPK_EUNSUPPORTED.
     pub fn set_colliders(&mut self, colliders: &[GpuCollider]) -> Result<(), SpkError> {
         ck(unsafe { spk_colliders_upload(self.raw, colliders.as_ptr(), colliders.len()) })
     }

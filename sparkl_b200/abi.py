@@ -306,6 +306,34 @@ class HeightFieldCollider:
         return bytes(buf)
 
 
+class PolylineCollider:
+    """A rapier polyline collider (closed polygon in the xy plane, extruded along z in 3D) -> 336-byte GpuCollider image with
+    the Polyline payload of include/sparkl_abi.h (HOST pointer to the n x 3 vertices).  Counter-clockwise = solid interior
+    (parry's Polyline::project_local_point_assuming_solid_interior_ccw).  Keep the object alive until the upload."""
+
+    def __init__(self, vertices, translation=(0, 0, 0), rotation=(0, 0, 0, 1), friction=0.5, penalty_stiffness=0.0,
+                 grid_boundary_handling=BoundaryHandling.Friction, flip_interior=False):
+        v = np.ascontiguousarray(np.asarray(vertices, np.float32))
+        if v.ndim == 2 and v.shape[1] == 2:
+            v = np.ascontiguousarray(np.concatenate([v, np.zeros((len(v), 1), np.float32)], axis=1))
+        assert v.ndim == 2 and v.shape[1] == 3
+        self.vertices, self.translation, self.rotation = v, translation, rotation
+        self.friction, self.penalty_stiffness, self.grid_boundary_handling = friction, penalty_stiffness, grid_boundary_handling
+        self.flip_interior = flip_interior
+
+    def to_gpu_collider(self) -> bytes:
+        buf = bytearray(336)
+        np.frombuffer(buf, "<u4", 1, 0)[0] = 3
+        np.frombuffer(buf, "<u8", 1, 8)[0] = self.vertices.ctypes.data
+        np.frombuffer(buf, "<u4", 1, 16)[0] = len(self.vertices)
+        np.frombuffer(buf, "u1", 1, 20)[0] = int(self.flip_interior)
+        np.frombuffer(buf, "<f4", 4, 296)[:] = self.rotation
+        np.frombuffer(buf, "<f4", 3, 312)[:] = self.translation
+        np.frombuffer(buf, "<f4", 2, 324)[:] = [self.friction, self.penalty_stiffness]
+        np.frombuffer(buf, "<u4", 1, 332)[0] = self.grid_boundary_handling
+        return bytes(buf)
+
+
 def pack_colliders(colliders) -> np.ndarray:
     out = np.zeros((len(colliders), 336), dtype=np.uint8)
     for i, c in enumerate(colliders):

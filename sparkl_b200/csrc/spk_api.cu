@@ -676,8 +676,15 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
             d.hf_flags = (hf.bellow_heightfield_is_solid ? 1u : 0u) | (hf.flip_interior ? 2u : 0u);
             data_off[i] = data.size();
             data.insert(data.end(), hf.heights, hf.heights + (size_t)hf.nrows * hf.ncols);
+        } else if (cols[i].shape_tag == SPK_SHAPE_POLYLINE) {
+            const auto& pl = cols[i].shape.polyline;
+            if (pl.num_vertices && !pl.vertices) return SPK_EINVAL;
+            d.nrows = pl.num_vertices; // number of vertices
+            d.hf_flags = pl.flip_interior ? 2u : 0u;
+            data_off[i] = data.size();
+            data.insert(data.end(), pl.vertices, pl.vertices + (size_t)pl.num_vertices * 3);
         } else {
-            return SPK_EUNSUPPORTED; // trimesh / polyline: SURVEY §8(f) "next"
+            return SPK_EUNSUPPORTED; // trimesh: SURVEY §8(f) "next"
         }
         std::memcpy(d.rot, cols[i].rotation, 16);
         std::memcpy(d.tr, cols[i].translation, 12);
@@ -691,7 +698,7 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
     CK(dev_alloc(c->collider_data, data.size()));
     if (!data.empty()) CK(cudaMemcpy(c->collider_data, data.data(), data.size() * sizeof(float), cudaMemcpyHostToDevice));
     for (size_t i = 0; i < n; ++i)
-        if (dc[i].shape == SPK_SHAPE_HEIGHTFIELD) dc[i].heights = c->collider_data + data_off[i];
+        if (dc[i].shape == SPK_SHAPE_HEIGHTFIELD || dc[i].shape == SPK_SHAPE_POLYLINE) dc[i].heights = c->collider_data + data_off[i];
     if (n) CK(cudaMemcpy(c->colliders, dc.data(), n * sizeof(DevCollider), cudaMemcpyHostToDevice));
     c->ncolliders = n;
     // colliders changed: invalidate the per-node projection cache of both grids (the reference uploads colliders once)

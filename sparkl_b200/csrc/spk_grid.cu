@@ -162,9 +162,65 @@ __device__ inline bool heightfield_project(const DevCollider& c, Vec3 pt, float 
     out = Vec3{w.x + c.tr[0], w.y + c.tr[1], w.z + c.tr[2]};
     return true;
 }
+// polyline_project_point, src_kernels/gpu_collider.rs:105-201 (dim3): closest segment of the closed polygon (full 3D distance,
+// first of equal distances wins), inside / outside from the segment's normal in the xy plane (`planar_normal(2)`), with the
+// vertex rule of parry's Polyline::project_local_point_assuming_solid_interior_ccw; the projection keeps the query's z.
+// Quirk kept: the inside tests subtract the LOCAL projection from the WORLD point (gpu_collider.rs:176,181).
+__device__ inline bool polyline_project(const DevCollider& c, Vec3 pt, Vec3& out, bool& inside) {
+    const int n = (int)c.nrows;
+    if (n == 0) return false;
+    const float qinv[4] = {-c.rot[0], -c.rot[1], -c.rot[2], c.rot[3]};
+    const Vec3 lp = quat_rotate(qinv, Vec3{pt.x - c.tr[0], pt.y - c.tr[1], pt.z - c.tr[2]});
+    const float* v = c.heights;
+    float best_dist = FLT_MAX;
+    Vec3 best{0.f, 0.f, 0.f}, sa{0.f, 0.f, 0.f}, sb{0.f, 0.f, 0.f};
+    int best_id = 0, best_loc = 2; // 0 / 1: on vertex a / b, 2: on the edge
+    bool best_eq = false;
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1) % n;
+        const Vec3 a{v[3 * i], v[3 * i + 1], v[3 * i + 2]}, b{v[3 * j], v[3 * j + 1], v[3 * j + 2]};
+        const Vec3 ab = v_sub(b, a), ap = v_sub(lp, a);
+        const float ab_ap = v_dot(ab, ap), sqnab = v_dot(ab, ab);
+        Vec3 q; int loc;
+        if (ab_ap <= 0.f) { q = a; loc = 0; }
+        else if (ab_ap >= sqnab) { q = b; loc = 1; }
+        else { const float u = ab_ap / sqnab; q = Vec3{a.x + ab.x * u, a.y + ab.y * u, a.z + ab.z * u}; loc = 2; }
+        const Vec3 d = v_sub(lp, q);
+        const float dist = sqrtf(v_dot(d, d));
+        if (i == 0 || dist < best_dist) { best_dist = dist; best = q; best_id = i; best_loc = loc; sa = a; sb = b; best_eq = q.x == lp.x && q.y == lp.y && q.z == lp.z; }
+    }
+    inside = best_eq;
+    const Vec3 dir = v_sub(sb, sa);
+    const float nn = sqrtf(dir.y * dir.y + dir.x * dir.x);
+    if (nn > FLT_EPSILON) { // planar_normal(2) = normalize((dir.y, -dir.x, 0))
+        const Vec3 nrm{dir.y / nn, -dir.x / nn, 0.f};
+        const float side = (pt.x - best.x) * nrm.x + (pt.y - best.y) * nrm.y + (pt.z - best.z) * nrm.z;
+        if (best_loc == 2) {
+            inside = side <= 0.f;
+        } else {
+            Vec3 dir2;
+            if (best_loc == 0) { // previous segment, reversed
+                const int adj = best_id == 0 ? n - 1 : best_id - 1, aj = (adj + 1) % n;
+                dir2 = Vec3{-(v[3 * aj] - v[3 * adj]), -(v[3 * aj + 1] - v[3 * adj + 1]), -(v[3 * aj + 2] - v[3 * adj + 2])};
+            } else {
+                const int adj = (best_id + 1) % n, aj = (adj + 1) % n;
+                dir2 = Vec3{v[3 * aj] - v[3 * adj], v[3 * aj + 1] - v[3 * adj + 1], v[3 * aj + 2] - v[3 * adj + 2]};
+            }
+            const float dot = v_dot(nrm, dir2);
+            const float threshold = 1.0e-3f * sqrtf(v_dot(dir2, dir2));
+            inside = fabsf(dot) > threshold ? dot >= 0.f : side <= 0.f;
+        }
+    }
+    best.z = lp.z;
+    if (c.hf_flags & 2u) inside = !inside;
+    const Vec3 w = quat_rotate(c.rot, best);
+    out = Vec3{w.x + c.tr[0], w.y + c.tr[1], w.z + c.tr[2]};
+    return true;
+}
 // GpuColliderShape::project_point_with_max_dist, gpu_collider.rs:42-103 (solid = false)
 __device__ __forceinline__ bool collider_project(const DevCollider& c, Vec3 pt, float max_dist, Vec3& out, bool& inside) {
     if (c.shape == SPK_SHAPE_HEIGHTFIELD) return heightfield_project(c, pt, max_dist, out, inside);
+    if (c.shape == SPK_SHAPE_POLYLINE) return polyline_project(c, pt, out, inside);
     cuboid_project(c, pt, out, inside);
     return true;
 }

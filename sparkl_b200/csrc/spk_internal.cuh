@@ -53,8 +53,8 @@ struct DevCollider {
     float friction;
     uint32_t handling;
     uint32_t shape;       // SPK_SHAPE_CUBOID / SPK_SHAPE_HEIGHTFIELD
-    uint32_t nrows, ncols; // heightfield: height samples along z / x
-    const float* heights; // heightfield: device copy, column-major nrows x ncols
+    uint32_t nrows, ncols; // heightfield: height samples along z / x; polyline: nrows = number of vertices
+    const float* heights; // heightfield: device copy, column-major nrows x ncols; polyline: vertices (x, y, z)
     float scale[3];
     uint32_t hf_flags;    // bit0 bellow_heightfield_is_solid, bit1 flip_interior
 };

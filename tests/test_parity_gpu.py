@@ -106,11 +106,20 @@ def test_sand_on_heightfield_ground(oracle):
     assert tags[1] > 0 and tags[2] > 0 and tags[3] > 0  # inside / outside / too far all occur
 
 
+def test_sand_in_a_polyline_trough(oracle):
+    """Polyline collider (gpu_collider.rs:105-201), §8f-1"""
+    sc = scenes.jitter(scenes.sand3(8, 4, 6, with_colliders=False, y0=0.5), 0.02, seed=6)
+    trough = np.array([[-1, 0.3], [-1, 6], [-1.5, 6], [-1.5, -0.5], [3.5, -0.5], [3.5, 6], [3, 6], [3, 0.3]], np.float32)  # counter-clockwise: the U-shaped wall is the solid
+    sc.colliders = [abi.PolylineCollider(trough)]
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 10, lambda s: RTOL_1 * (1 + 3 * s))
+
+
 def test_unsupported_collider_shapes_are_rejected():
     from sparkl_b200.pipeline import SingleGpuMpmContext
     g = SingleGpuMpmContext(0.2)
     img = np.zeros((1, 336), np.uint8)
-    for tag in (2, 3):  # TriMesh, Polyline: SURVEY §8f "next"
+    for tag in (2,):  # TriMesh: SURVEY §8f "next"
         img[0, 0] = tag
         rc = g._lib.spk_colliders_upload(g._h, img.ctypes.data, 1)
         assert rc == abi.EUNSUPPORTED
