@@ -24,6 +24,17 @@ extern "C" {
 
 #define SPK_ABI_VERSION 1
 
+/* Dimension of the build.  Like the reference (crates sparkl2d / sparkl3d compiled from one source tree with the `dim2` /
+ * `dim3` features, src_kernels/lib.rs:12-20), the library is built twice from the same sources: libsparkl_b200.so
+ * (SPK_DIM == 3, the default) and libsparkl_b200_2d.so (-DSPK_DIM=2).  Both export the same entry points; the structs whose
+ * Rust definition holds a `Vector<Real>` / `Point<Real>` / `Matrix<Real>` change size with the dimension. */
+#ifndef SPK_DIM
+#define SPK_DIM 3
+#endif
+#if SPK_DIM != 2 && SPK_DIM != 3
+#error "SPK_DIM must be 2 or 3"
+#endif
+
 /* ---------------------------------------------------------------- error codes */
 #define SPK_OK 0
 #define SPK_EINVAL (-1)       /* bad argument (replaces the reference's assert panics, cuda_particle_set.rs:40-59) */
@@ -33,13 +44,13 @@ extern "C" {
 
 /* ---------------------------------------------------------------- particle PODs
  * src_core/dynamics/particle.rs:14-219 (one device array per struct in the reference, cuda_particle_set.rs:12-19) */
-typedef struct SpkParticlePosition { float point[3]; } SpkParticlePosition;         /* particle.rs:17-20  */
-typedef struct SpkParticleVelocity { float vector[3]; } SpkParticleVelocity;        /* particle.rs:54-57  */
+typedef struct SpkParticlePosition { float point[SPK_DIM]; } SpkParticlePosition;   /* particle.rs:17-20  */
+typedef struct SpkParticleVelocity { float vector[SPK_DIM]; } SpkParticleVelocity;  /* particle.rs:54-57  */
 typedef struct SpkParticleVolume {                                                   /* particle.rs:65-72  */
     float mass;
     float volume0;
     float radius0;
-    float deformation_gradient[9]; /* column-major (nalgebra Matrix3) */
+    float deformation_gradient[SPK_DIM * SPK_DIM]; /* column-major (nalgebra Matrix3 / Matrix2) */
     float plastic_deformation_gradient_det;
 } SpkParticleVolume;
 typedef struct SpkParticleStatus {                                                   /* particle.rs:119-127 */
@@ -47,7 +58,10 @@ typedef struct SpkParticleStatus {                                              
     uint8_t is_static;
     uint8_t kinematic_vel_enabled;
     uint8_t _pad0;
-    float kinematic_vel[3];
+    float kinematic_vel[SPK_DIM];
+#if SPK_DIM == 2
+    uint32_t _pad1;       /* usize alignment */
+#endif
     uint64_t model_index;
 } SpkParticleStatus;
 typedef struct SpkParticlePhase { float phase; float psi_pos; } SpkParticlePhase;   /* particle.rs:144-148 */
@@ -139,6 +153,7 @@ typedef struct SpkGpuParticleModel {
  * src_kernels/gpu_collider.rs:14-18, src/cuda/cuda_collider_set.rs:71-86); here the payload carries a HOST description of
  * the same rapier `HeightField` (heights matrix + scale) and the library owns the device copy. */
 enum { SPK_SHAPE_CUBOID = 0, SPK_SHAPE_HEIGHTFIELD = 1, SPK_SHAPE_TRIMESH = 2, SPK_SHAPE_POLYLINE = 3 };
+#if SPK_DIM == 3
 typedef struct SpkGpuCollider {
     uint32_t shape_tag; uint32_t _pad0;
     union {
@@ -163,11 +178,35 @@ typedef struct SpkGpuCollider {
     float penalty_stiffness;
     uint32_t grid_boundary_handling; /* SPK_BOUNDARY_* */
 } SpkGpuCollider;
+#else
+/* dim2 GpuCollider (same Rust definition, src_kernels/gpu_collider.rs:203-212, with parry2d shapes and an Isometry2).
+ * Cuboid (tag 0) and Polyline (tag 3); HeightField / TriMesh -> SPK_EUNSUPPORTED.  The byte image of the reference's dim2 enum
+ * depends on parry2d's CUDA pointer types and was NOT recovered from sparkl2d-kernels.ptx: this layout is this library's own
+ * (field order and meaning as in the Rust struct; the polyline payload is a HOST description like the 3D one). */
+typedef struct SpkGpuCollider {
+    uint32_t shape_tag; uint32_t _pad0;
+    union {
+        struct { float half_extents[2]; } cuboid;
+        struct {
+            const float* vertices;    /* HOST pointer, num_vertices x (x, y); segment i joins vertex i and (i + 1) % n */
+            uint32_t num_vertices;
+            uint8_t flip_interior;
+        } polyline;
+        uint8_t _bytes[32];
+    } shape;
+    float rotation[2];    /* unit complex (re, im) = (cos, sin), nalgebra UnitComplex */
+    float translation[2];
+    float friction;
+    float penalty_stiffness;
+    uint32_t grid_boundary_handling; /* SPK_BOUNDARY_*; Friction and FrictionZUp act the same in 2D (grid_update.rs:159-160) */
+    uint32_t _pad1;
+} SpkGpuCollider;
+#endif
 
 /* ---------------------------------------------------------------- sparse grid read-back images
  * Used by the parity tests and by hosts that inspect the grid; internal device storage is SoA. */
 typedef struct SpkActiveBlockHeader { /* src_kernels/cuda/sort.rs:29-38 */
-    uint64_t virtual_id;  /* BlockVirtualId: x | y<<21 | z<<42, origin 2^20 (gpu_grid.rs:73-120) */
+    uint64_t virtual_id;  /* BlockVirtualId: x | y<<21 | z<<42, origin 2^20; dim2: x | y<<32, origin 2^31 (gpu_grid.rs:73-120) */
     uint32_t first_particle;
     uint32_t num_particles;
     uint32_t halo_state;  /* bit0 IS_HALO, bit1 HAS_HALO_NEIGHBOR (sort.rs:15-27) */
@@ -175,17 +214,19 @@ typedef struct SpkActiveBlockHeader { /* src_kernels/cuda/sort.rs:29-38 */
 } SpkActiveBlockHeader;
 typedef struct SpkDispatchBlock2ActiveBlock { uint32_t active_block_id; uint32_t first_particle; } SpkDispatchBlock2ActiveBlock; /* gpu_grid.rs:166-172 */
 enum { SPK_PROJ_NOT_COMPUTED = 0, SPK_PROJ_INSIDE = 1, SPK_PROJ_OUTSIDE = 2, SPK_PROJ_TOO_FAR = 3 };
-typedef struct SpkGpuGridNode { /* src_kernels/gpu_grid.rs:443-459, 72 bytes */
+typedef struct SpkGpuGridNode { /* src_kernels/gpu_grid.rs:443-459, 72 bytes (dim2: 56 bytes) */
     float mass;
-    float momentum_velocity[3];
+    float momentum_velocity[SPK_DIM];
     float psi_momentum_velocity;
     float psi_mass;
     float prev_mass;
+#if SPK_DIM == 3
     uint32_t _pad0;
+#endif
     uint64_t projection_status_tag;     /* SPK_PROJ_* */
     uint64_t projection_status_payload; /* collider index for Inside/Outside */
-    float collision_normal[3];
-    float projection_scaled_dir[3];
+    float collision_normal[SPK_DIM];
+    float projection_scaled_dir[SPK_DIM];
 } SpkGpuGridNode;
 
 /* ---------------------------------------------------------------- timings
@@ -214,9 +255,24 @@ typedef struct SpkSortInfo {
 } SpkSortInfo;
 
 #if defined(__cplusplus)
+#if SPK_DIM == 3
 static_assert(sizeof(SpkParticlePosition) == 12, "ParticlePosition");
 static_assert(sizeof(SpkParticleVelocity) == 12, "ParticleVelocity");
 static_assert(sizeof(SpkParticleVolume) == 52, "ParticleVolume");
+static_assert(sizeof(SpkGpuCollider) == 336 && offsetof(SpkGpuCollider, rotation) == 296 &&
+              offsetof(SpkGpuCollider, translation) == 312 && offsetof(SpkGpuCollider, friction) == 324 &&
+              offsetof(SpkGpuCollider, grid_boundary_handling) == 332, "GpuCollider");
+static_assert(sizeof(SpkGpuGridNode) == 72 && offsetof(SpkGpuGridNode, projection_status_tag) == 32 &&
+              offsetof(SpkGpuGridNode, collision_normal) == 48 && offsetof(SpkGpuGridNode, projection_scaled_dir) == 60, "GpuGridNode");
+#else
+static_assert(sizeof(SpkParticlePosition) == 8, "ParticlePosition (dim2)");
+static_assert(sizeof(SpkParticleVelocity) == 8, "ParticleVelocity (dim2)");
+static_assert(sizeof(SpkParticleVolume) == 32, "ParticleVolume (dim2)");
+static_assert(sizeof(SpkGpuCollider) == 72 && offsetof(SpkGpuCollider, rotation) == 40 && offsetof(SpkGpuCollider, translation) == 48 &&
+              offsetof(SpkGpuCollider, friction) == 56 && offsetof(SpkGpuCollider, grid_boundary_handling) == 64, "GpuCollider (dim2)");
+static_assert(sizeof(SpkGpuGridNode) == 56 && offsetof(SpkGpuGridNode, projection_status_tag) == 24 &&
+              offsetof(SpkGpuGridNode, collision_normal) == 40 && offsetof(SpkGpuGridNode, projection_scaled_dir) == 48, "GpuGridNode (dim2)");
+#endif
 static_assert(sizeof(SpkParticleStatus) == 24 && offsetof(SpkParticleStatus, kinematic_vel) == 4 &&
               offsetof(SpkParticleStatus, model_index) == 16, "ParticleStatus");
 static_assert(sizeof(SpkParticlePhase) == 8, "ParticlePhase");
@@ -226,12 +282,7 @@ static_assert(sizeof(SpkGpuParticleModel) == 96, "GpuParticleModel");
 static_assert(offsetof(SpkGpuParticleModel, constitutive) == 8, "constitutive payload @8");
 static_assert(offsetof(SpkGpuParticleModel, plastic_tag) == 32 && offsetof(SpkGpuParticleModel, plastic) == 40, "plastic @32/@40");
 static_assert(offsetof(SpkGpuParticleModel, failure_tag) == 80 && offsetof(SpkGpuParticleModel, failure) == 84, "failure @80/@84");
-static_assert(sizeof(SpkGpuCollider) == 336 && offsetof(SpkGpuCollider, rotation) == 296 &&
-              offsetof(SpkGpuCollider, translation) == 312 && offsetof(SpkGpuCollider, friction) == 324 &&
-              offsetof(SpkGpuCollider, grid_boundary_handling) == 332, "GpuCollider");
 static_assert(sizeof(SpkActiveBlockHeader) == 24, "ActiveBlockHeader");
-static_assert(sizeof(SpkGpuGridNode) == 72 && offsetof(SpkGpuGridNode, projection_status_tag) == 32 &&
-              offsetof(SpkGpuGridNode, collision_normal) == 48 && offsetof(SpkGpuGridNode, projection_scaled_dir) == 60, "GpuGridNode");
 #endif
 
 /* ================================================================ entry points */
@@ -305,7 +356,7 @@ int spk_colliders_upload(spk_ctx* ctx, const SpkGpuCollider* colliders, size_t n
  * With timings_or_null == NULL the call returns once the frame is ENQUEUED (every substep still reads its 64-byte counter
  * record back, so only the tail of the last substep is outstanding): consecutive frames then run back to back on the GPU.
  * All other entry points are ordered on the context's stream; spk_ctx_synchronize() waits for completion. */
-int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float gravity[3],
+int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float gravity[SPK_DIM],
              SpkStepTimings* timings_or_null, float* simulated_time_out);
 
 /* ---- stage-level calls: the pieces step_generic sequences, exposed so that (a) the parity tests can compare
@@ -324,7 +375,7 @@ int spk_dt_acc_set(spk_ctx* ctx, uint64_t value);
 /* g2p2g (cuda_mpm_pipeline.rs:479-498): K16, all dispatch blocks (halo or not) */
 int spk_stage_g2p2g(spk_ctx* ctx, float dt, uint32_t damage_model);
 /* grid_update + swap_buffers (cuda_mpm_pipeline.rs:536-558): K19 */
-int spk_stage_grid_update(spk_ctx* ctx, float dt, const float gravity[3]);
+int spk_stage_grid_update(spk_ctx* ctx, float dt, const float gravity[SPK_DIM]);
 
 /* ---- halo exchange for multi-process runs (replaces K3,K4,K17,K18 and the D2D copies,
  * cuda_sparse_grid.rs:256-322, cuda_mpm_pipeline.rs:407-533).  Keys travel as u64 virtual ids; payload is the
@@ -355,7 +406,7 @@ int spk_dist_info(spk_ctx* ctx, uint32_t* num_halo_blocks, uint32_t* barrier_epo
  * check_active_blocks, cuda_sparse_grid.rs:491-652).  which_grid: 0 = curr, 1 = next. */
 int spk_grid_num_active_blocks(spk_ctx* ctx, int which_grid, uint32_t* out);
 int spk_grid_read_headers(spk_ctx* ctx, int which_grid, SpkActiveBlockHeader* dst, uint32_t n);
-int spk_grid_read_nodes(spk_ctx* ctx, int which_grid, SpkGpuGridNode* dst, uint32_t n_blocks); /* 64 nodes per block */
+int spk_grid_read_nodes(spk_ctx* ctx, int which_grid, SpkGpuGridNode* dst, uint32_t n_blocks); /* 64 (dim2: 16) nodes per block */
 int spk_grid_read_dispatch(spk_ctx* ctx, SpkDispatchBlock2ActiveBlock* dst, uint32_t n);
 /* raw device pointers for zero-copy wrappers (torch / NCCL plumbing); valid until the next upload/append */
 int spk_device_ptr(spk_ctx* ctx, int which /* SPK_ATTR_* */, void** out);

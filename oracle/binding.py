@@ -142,6 +142,111 @@ def collider_project(collider, pt, max_dist):
     return (out, bool(inside.value)) if found else None
 
 
+# ------------------------------------------------------------------------------------------------ dim2 oracle
+_LIB2D = None
+
+
+def build2d(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle2d.so")
+    src = os.path.join(_HERE, "mpm_oracle2d.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle2d.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib2d():
+    """oracle/liboracle2d.so: the dim2 restatement (mpm_oracle2d.cpp), same `orc_*` entry points with the dim2 struct layouts"""
+    global _LIB2D
+    if _LIB2D is None:
+        l = C.CDLL(build2d())
+        declare(l, "orc_")
+        l.orc_create.argtypes = [C.c_float]
+        l.orc_create.restype = C.c_void_p
+        l.orc_destroy.argtypes = [C.c_void_p]
+        l.orc_step.argtypes = [C.c_void_p, C.POINTER(abi.SolverParameters), C.POINTER(C.c_float * 3), C.POINTER(abi.StepTimings), C.POINTER(C.c_float)]
+        l.orc_step.restype = C.c_int
+        l.orc_block_key_of_point.argtypes = [C.c_void_p, C.c_float]
+        l.orc_block_key_of_point.restype = C.c_uint64
+        l.orc_collider_project.restype = C.c_int
+        _LIB2D = l
+    return _LIB2D
+
+
+class OracleEngine2D(Engine):
+    def __init__(self, cell_width: float):
+        from sparkl_b200 import abi2d
+        l = lib2d()
+        super().__init__(l, "orc_", C.c_void_p(l.orc_create(cell_width)), types=abi2d)
+        self.cell_width = cell_width
+        self.device = -1
+
+    def __del__(self):
+        try:
+            self._lib.orc_destroy(self._h)
+        except Exception:
+            pass
+
+    def step(self, params: abi.SolverParameters, gravity):
+        g = (C.c_float * 3)(*gravity)
+        t = abi.StepTimings()
+        sim = C.c_float()
+        rc = self._lib.orc_step(self._h, C.byref(params), C.byref(g), C.byref(t), C.byref(sim))
+        if rc:
+            raise abi.SparklError(rc, "orc_step")
+        return sim.value, t
+
+
+def svd2(F: np.ndarray):
+    """F: 2x2 row-major numpy -> (U, s, Vt) of the dim2 oracle's closed-form nalgebra stand-in"""
+    l = lib2d()
+    f = np.ascontiguousarray(F.T, dtype=np.float32)
+    u, s, vt = np.zeros(4, np.float32), np.zeros(2, np.float32), np.zeros(4, np.float32)
+    l.orc_svd2(f.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), vt.ctypes.data_as(C.c_void_p))
+    return u.reshape(2, 2).T, s, vt.reshape(2, 2).T
+
+
+def block_key_of_point2d(p, cell_width: float) -> int:
+    a = np.asarray(p, np.float32)
+    return lib2d().orc_block_key_of_point(a.ctypes.data_as(C.c_void_p), cell_width)
+
+
+def kirchhoff_stress2d(model, F: np.ndarray, phase=1.0, hardening=1.0, jp=1.0, mass=1.0, volume0=1.0, vel_grad=None):
+    from sparkl_b200 import abi2d
+    l = lib2d()
+    m = np.frombuffer(model.to_gpu_model(), np.uint8).copy()
+    d = np.zeros(1, abi2d.DATA); d["elastic_hardening"] = hardening; d["plastic_hardening"] = 1.0
+    v = np.zeros(1, abi2d.VOLUME)
+    v["mass"], v["volume0"], v["plastic_deformation_gradient_det"] = mass, volume0, jp
+    v["deformation_gradient"] = np.asarray(F, np.float32).T.reshape(4)
+    g = np.zeros(4, np.float32) if vel_grad is None else np.asarray(vel_grad, np.float32).T.reshape(4).copy()
+    out = np.zeros(4, np.float32)
+    l.orc_kirchhoff_stress(m.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.c_float(phase),
+                           g.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out.reshape(2, 2).T
+
+
+def plastic_update2d(model, F: np.ndarray, data: np.ndarray, jp=1.0, phase=1.0):
+    from sparkl_b200 import abi2d
+    l = lib2d()
+    m = np.frombuffer(model.to_gpu_model(), np.uint8).copy()
+    v = np.zeros(1, abi2d.VOLUME)
+    v["mass"], v["volume0"], v["plastic_deformation_gradient_det"] = 1.0, 1.0, jp
+    v["deformation_gradient"] = np.asarray(F, np.float32).T.reshape(4)
+    d = data.copy()
+    l.orc_plastic_update(m.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.c_float(phase))
+    return v["deformation_gradient"][0].reshape(2, 2).T.copy(), float(v["plastic_deformation_gradient_det"][0]), d
+
+
+def collider_project2d(collider, pt, max_dist):
+    l = lib2d()
+    c = np.frombuffer(collider.to_gpu_collider(), np.uint8).copy()
+    p = np.asarray(pt, np.float32).copy()
+    out = np.zeros(2, np.float32)
+    inside = C.c_int()
+    found = l.orc_collider_project(c.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), C.c_float(max_dist), out.ctypes.data_as(C.c_void_p), C.byref(inside))
+    return (out, bool(inside.value)) if found else None
+
+
 # ------------------------------------------------------------------------------------------------ oracle-A
 _REF = None
 REF_CUBIN = os.path.join(_HERE, "_ref", "sparkl3d-kernels.cubin")

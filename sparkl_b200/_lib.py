@@ -10,7 +10,9 @@ from .engine import declare
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPK_LIB_PATH") or os.path.join(_HERE, "libsparkl_b200.so")  # SPK_LIB_PATH: A/B builds of the same ABI (scripts/variants.sh)
+LIB2D_PATH = os.environ.get("SPK_LIB2D_PATH") or os.path.join(_HERE, "libsparkl_b200_2d.so")  # the -DSPK_DIM=2 build (same entry points)
 _LIB = None
+_LIBS = {}
 
 # every symbol include/sparkl_abi.h declares
 EXPORTS = [
@@ -25,12 +27,17 @@ EXPORTS = [
 ]
 
 
-def lib():
+def lib(dim: int = 3):
+    """the product library of the given dimension (3: libsparkl_b200.so, 2: libsparkl_b200_2d.so — one source tree, two builds,
+    like the reference's sparkl3d / sparkl2d crates)"""
     global _LIB
-    if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise abi.SparklError(abi.ESTATE, f"{LIB_PATH} is not built (run `python -m sparkl_b200.build`); there is no CPU fallback")
-        l = C.CDLL(LIB_PATH)
+    if dim not in (2, 3):
+        raise abi.SparklError(abi.EINVAL, "dim must be 2 or 3")
+    if dim not in _LIBS:
+        path = LIB_PATH if dim == 3 else LIB2D_PATH
+        if not os.path.exists(path):
+            raise abi.SparklError(abi.ESTATE, f"{path} is not built (run `python -m sparkl_b200.build`); there is no CPU fallback")
+        l = C.CDLL(path)
         declare(l, "spk_")
         vp = C.c_void_p
         l.spk_abi_version.restype = C.c_int
@@ -64,9 +71,11 @@ def lib():
         for name in EXPORTS:
             if name not in ("spk_error_string",):
                 getattr(l, name).restype = C.c_int
-        _LIB = l
-    return _LIB
+        _LIBS[dim] = l
+        if dim == 3:
+            _LIB = l
+    return _LIBS[dim]
 
 
-def error_string(code: int) -> str:
-    return lib().spk_error_string(code).decode()
+def error_string(code: int, dim: int = 3) -> str:
+    return lib(dim).spk_error_string(code).decode()

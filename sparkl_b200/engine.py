@@ -46,11 +46,13 @@ def declare(lib, prefix: str):
 
 
 class Engine:
-    """One simulation context behind a C ABI (`spk_ctx*` or `orc_ctx*`)."""
+    """One simulation context behind a C ABI (`spk_ctx*` or `orc_ctx*`).  `types` is the module holding the byte images of the
+    build's dimension-dependent structs: abi (3D, default) or abi2d (the -DSPK_DIM=2 libraries)."""
 
-    def __init__(self, lib, prefix: str, handle, error_string=None):
+    def __init__(self, lib, prefix: str, handle, error_string=None, types=abi):
         self._lib, self._prefix, self._h = lib, prefix, handle
         self._err = error_string
+        self.T = types
 
     def _call(self, name, *args):
         rc = getattr(self._lib, self._prefix + name)(self._h, *args)
@@ -60,8 +62,9 @@ class Engine:
 
     # ---- particles ------------------------------------------------------------------------------------------
     def upload(self, pc: abi.ParticleComponents):
+        T = self.T
         arrs = [np.ascontiguousarray(a) for a in (pc.status, pc.position, pc.velocity, pc.volume, pc.phase, pc.data)]
-        for a, dt in zip(arrs, (abi.STATUS, abi.POSITION, abi.VELOCITY, abi.VOLUME, abi.PHASE, abi.DATA)):
+        for a, dt in zip(arrs, (T.STATUS, T.POSITION, T.VELOCITY, T.VOLUME, T.PHASE, T.DATA)):
             if a.dtype != dt:
                 raise abi.SparklError(abi.EINVAL, "attribute dtype mismatch")
         n = len(arrs[0])
@@ -79,15 +82,15 @@ class Engine:
         dtype, which makes the device->host copy run at full PCIe rate (the testbed's frame read-back, testbed_plugin.rs:533-588)"""
         n = len(self) if n is None else n
         if out is None:
-            out = np.empty(n, abi.ATTR_DTYPES[which])
-        elif out.dtype != abi.ATTR_DTYPES[which] or len(out) < n or not out.flags.c_contiguous:
+            out = np.empty(n, self.T.ATTR_DTYPES[which])
+        elif out.dtype != self.T.ATTR_DTYPES[which] or len(out) < n or not out.flags.c_contiguous:
             raise abi.SparklError(abi.EINVAL, "output buffer has the wrong dtype / length")
         if n:
             self._call("particles_read", which, _ptr(out), n)
         return out
 
     def read_all(self) -> abi.ParticleComponents:
-        pc = abi.ParticleComponents(0)
+        pc = self.T.ParticleComponents(0)
         pc.position, pc.velocity = self.read(abi.ATTR_POSITION), self.read(abi.ATTR_VELOCITY)
         pc.status, pc.volume = self.read(abi.ATTR_STATUS), self.read(abi.ATTR_VOLUME)
         pc.phase, pc.data = self.read(abi.ATTR_PHASE), self.read(abi.ATTR_DATA)
@@ -98,7 +101,7 @@ class Engine:
         self._call("models_upload", _ptr(packed), len(models))
 
     def colliders_upload(self, colliders):
-        packed = abi.pack_colliders(colliders)
+        packed = self.T.pack_colliders(colliders)
         self._call("colliders_upload", _ptr(packed), len(colliders))
 
     # ---- stages ---------------------------------------------------------------------------------------------
@@ -159,7 +162,7 @@ class Engine:
 
     def grid_nodes(self, which_grid: int) -> np.ndarray:
         n = self.num_active_blocks(which_grid)
-        out = np.zeros((n, 64), abi.GRID_NODE)
+        out = np.zeros((n, getattr(self.T, "CELLS_PER_BLOCK", 64)), self.T.GRID_NODE)
         if n:
             self._call("grid_read_nodes", which_grid, _ptr(out), n)
         return out
