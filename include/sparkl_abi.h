@@ -293,6 +293,7 @@ enum { SPK_ATTR_POSITION = 0, SPK_ATTR_VELOCITY = 1, SPK_ATTR_STATUS = 2, SPK_AT
        SPK_ATTR_DATA = 5, SPK_ATTR_SORTED_IDS = 6 };
 
 int spk_abi_version(void);
+int spk_dim(void);                /* SPK_DIM of the loaded library: 3 (libsparkl_b200.so) or 2 (libsparkl_b200_2d.so) */
 const char* spk_error_string(int code);
 
 /* Context + 2 streams + CudaSparseGrid::with_capacity (testbed_plugin.rs:191-236, cuda_sparse_grid.rs:53-90). */

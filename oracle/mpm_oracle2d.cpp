@@ -114,9 +114,10 @@ static inline Real powi(Real a, int b) { // compiler-rt __powisf2
 static inline Real inv_exact(Real e) { return e == 0.0f ? 0.0f : 1.0f / e; } // src_core/utils/physics.rs:7-14
 
 // ------------------------------------------------------------------------------------------------ SVD / eigen (2x2, closed form)
-// Stand-in for nalgebra 0.32.1 `svd_unordered(true, true)` on a Matrix2: F = R(theta) diag(s) R(-phi) from the polar angles
-// (E, F, G, H decomposition), in double.  Singular values are made non-negative by flipping the matching row of V^T, so U and
-// V^T are orthogonal (not necessarily rotations) exactly like nalgebra's output; only U f(S) V^T products are consumed.
+// Stand-in for nalgebra 0.32.1 `svd_unordered(true, true)` on a Matrix2.  Since 0.31 nalgebra special-cases 2x2 matrices
+// (linalg/svd2.rs `svd_ordered2`): the closed form F = R(phi) diag(sx, sy) R(theta) from the E/F/G/H half-sums, singular values
+// returned as (sx, |sy|) with sx >= |sy| — i.e. DESCENDING — and the sign of sy folded into the second row of V^T.  Restated
+// here in double.  The order matters for exactly one consumer: Rankine's `idx = [0, 1, DIM - 1]` sort (plasticity_rankine.rs:47).
 struct Svd2 { M2 u; V2 s; M2 vt; };
 static Svd2 svd_unordered(const M2& a) {
     const double A = a(0, 0), B = a(0, 1), C = a(1, 0), D = a(1, 1);

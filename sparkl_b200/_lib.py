@@ -16,7 +16,7 @@ _LIBS = {}
 
 # every symbol include/sparkl_abi.h declares
 EXPORTS = [
-    "spk_abi_version", "spk_error_string", "spk_ctx_create", "spk_ctx_destroy", "spk_ctx_cell_width", "spk_ctx_synchronize", "spk_ctx_stream",
+    "spk_abi_version", "spk_dim", "spk_error_string", "spk_ctx_create", "spk_ctx_destroy", "spk_ctx_cell_width", "spk_ctx_synchronize", "spk_ctx_stream",
     "spk_particles_upload", "spk_particles_append", "spk_particles_remove_range", "spk_particles_len", "spk_particles_read",
     "spk_particles_read_async", "spk_particles_read_wait", "spk_particles_upload_async", "spk_particles_stage_async", "spk_particles_commit_staged",
     "spk_models_upload", "spk_colliders_upload", "spk_step", "spk_frame_begin", "spk_stage_sort", "spk_stage_reset_grid",

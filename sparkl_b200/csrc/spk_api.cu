@@ -35,6 +35,8 @@ void dev_free(T*& p) {
     if (p) cudaFree(p);
     p = nullptr;
 }
+// particles per cell of the reference's own grid-size estimate: 2^DIM (cuda_sparse_grid.rs:222-229)
+#define SPK_PARTICLES_PER_CELL (1 << SPK_DIM)
 uint32_t next_pow2(uint64_t v) {
     uint64_t p = 1;
     while (p < v) p <<= 1;
@@ -52,7 +54,7 @@ cudaError_t alloc_grid(spk_ctx* c, GridBuffers& g, uint32_t cap_hash) {
     free_grid(g);
     g.cap_hash = cap_hash;
     g.cap_blocks = cap_hash / 2;
-    const size_t nb = g.cap_blocks, nn = nb * 64;
+    const size_t nb = g.cap_blocks, nn = nb * SPK_CELLS_PER_BLOCK;
     cudaError_t e;
     if (c->dist_arena) {
         // multi-GPU: the hash table lives in the arena shared with the peers and cannot move or grow
@@ -66,8 +68,8 @@ cudaError_t alloc_grid(spk_ctx* c, GridBuffers& g, uint32_t cap_hash) {
     if ((e = dev_alloc(g.blk_first, nb)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.blk_count, nb)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.blk_halo, nb)) != cudaSuccess) return e;
-    if ((e = dev_alloc(g.nbr_self, nb * 8)) != cudaSuccess) return e;
-    if ((e = dev_alloc(g.nbr_prev, nb * 8)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.nbr_self, nb * SPK_NBR)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.nbr_prev, nb * SPK_NBR)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.vel, nn)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.acc, nn * SPK_ACC_CHANNELS)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.proj, nn)) != cudaSuccess) return e;
@@ -146,16 +148,28 @@ __global__ void pack_kernel(ParticleBuffers pb, float4* vel, float4* cold, const
     const SpkParticleVolume vo = volume[k];
     const uint32_t flags = (st.failed ? SPK_F_FAILED : 0u) | (st.is_static ? SPK_F_STATIC : 0u) | (st.kinematic_vel_enabled ? SPK_F_KINEMATIC : 0u) |
                            ((uint32_t)st.model_index << SPK_F_MODEL_SHIFT);
-    pb.a0[i] = make_float4(pos[k].point[0], pos[k].point[1], pos[k].point[2], __uint_as_float(flags));
     const float* F = vo.deformation_gradient;
+#if SPK_DIM == 3
+    pb.a0[i] = make_float4(pos[k].point[0], pos[k].point[1], pos[k].point[2], __uint_as_float(flags));
     pb.a1[i] = make_float4(F[0], F[1], F[2], F[3]);
     pb.a2[i] = make_float4(F[4], F[5], F[6], F[7]);
     pb.a3[i] = make_float4(F[8], vo.plastic_deformation_gradient_det, vo.mass, vo.volume0);
+#else // dim2: a1 holds the whole column-major 2x2 F, a2 is unused
+    pb.a0[i] = make_float4(pos[k].point[0], pos[k].point[1], 0.f, __uint_as_float(flags));
+    pb.a1[i] = make_float4(F[0], F[1], F[2], F[3]);
+    pb.a2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pb.a3[i] = make_float4(0.f, vo.plastic_deformation_gradient_det, vo.mass, vo.volume0);
+#endif
     SpkParticleData d = data ? data[k] : SpkParticleData{-0.01f, 1.0f, 1.0f, 0.0f}; // ParticleData::default, particle.rs:211-219
     pb.a4[i] = make_float4(phase[k].phase, phase[k].psi_pos, d.elastic_hardening, d.plastic_hardening);
     pb.a5[i] = make_float4(d.log_vol_gain, d.nacc_alpha, __uint_as_float((uint32_t)i), 0.f);
+#if SPK_DIM == 3
     vel[i] = make_float4(v[k].vector[0], v[k].vector[1], v[k].vector[2], 0.f);
     cold[i] = make_float4(st.kinematic_vel[0], st.kinematic_vel[1], st.kinematic_vel[2], vo.radius0);
+#else
+    vel[i] = make_float4(v[k].vector[0], v[k].vector[1], 0.f, 0.f);
+    cold[i] = make_float4(st.kinematic_vel[0], st.kinematic_vel[1], 0.f, vo.radius0);
+#endif
 }
 // ---- unpack: internal streams (physical order) -> reference layout indexed by original particle id ---------------
 __global__ void unpack_kernel(ParticleBuffers pb, const float4* vel, const float4* cold, const uint32_t* perm_or_null, int which, void* out, size_t n) {
@@ -169,14 +183,24 @@ __global__ void unpack_kernel(ParticleBuffers pb, const float4* vel, const float
     const uint32_t id = __float_as_uint(pb.a5[i].z);
     if (id >= n) return;
     switch (which) {
+#if SPK_DIM == 3
     case SPK_ATTR_POSITION: { const float4 r = pb.a0[i]; SpkParticlePosition o; o.point[0] = r.x; o.point[1] = r.y; o.point[2] = r.z; ((SpkParticlePosition*)out)[id] = o; break; }
     case SPK_ATTR_VELOCITY: { const float4 r = vel[i]; SpkParticleVelocity o; o.vector[0] = r.x; o.vector[1] = r.y; o.vector[2] = r.z; ((SpkParticleVelocity*)out)[id] = o; break; }
+#else
+    case SPK_ATTR_POSITION: { const float4 r = pb.a0[i]; SpkParticlePosition o; o.point[0] = r.x; o.point[1] = r.y; ((SpkParticlePosition*)out)[id] = o; break; }
+    case SPK_ATTR_VELOCITY: { const float4 r = vel[i]; SpkParticleVelocity o; o.vector[0] = r.x; o.vector[1] = r.y; ((SpkParticleVelocity*)out)[id] = o; break; }
+#endif
     case SPK_ATTR_STATUS: {
         const uint32_t f = __float_as_uint(pb.a0[i].w);
         const float4 cd = cold[id];
         SpkParticleStatus o;
         o.failed = (f & SPK_F_FAILED) ? 1 : 0; o.is_static = (f & SPK_F_STATIC) ? 1 : 0; o.kinematic_vel_enabled = (f & SPK_F_KINEMATIC) ? 1 : 0; o._pad0 = 0;
-        o.kinematic_vel[0] = cd.x; o.kinematic_vel[1] = cd.y; o.kinematic_vel[2] = cd.z;
+        o.kinematic_vel[0] = cd.x; o.kinematic_vel[1] = cd.y;
+#if SPK_DIM == 3
+        o.kinematic_vel[2] = cd.z;
+#else
+        o._pad1 = 0;
+#endif
         o.model_index = f >> SPK_F_MODEL_SHIFT;
         ((SpkParticleStatus*)out)[id] = o;
         break;
@@ -186,8 +210,13 @@ __global__ void unpack_kernel(ParticleBuffers pb, const float4* vel, const float
         SpkParticleVolume o;
         o.mass = r3.z; o.volume0 = r3.w; o.radius0 = cold[id].w;
         o.deformation_gradient[0] = r1.x; o.deformation_gradient[1] = r1.y; o.deformation_gradient[2] = r1.z; o.deformation_gradient[3] = r1.w;
+#if SPK_DIM == 3
         o.deformation_gradient[4] = r2.x; o.deformation_gradient[5] = r2.y; o.deformation_gradient[6] = r2.z; o.deformation_gradient[7] = r2.w;
-        o.deformation_gradient[8] = r3.x; o.plastic_deformation_gradient_det = r3.y;
+        o.deformation_gradient[8] = r3.x;
+#else
+        (void)r2;
+#endif
+        o.plastic_deformation_gradient_det = r3.y;
         ((SpkParticleVolume*)out)[id] = o;
         break;
     }
@@ -303,6 +332,7 @@ int spk_dist_realloc_grids(spk_ctx* c, uint32_t cap_hash) {
 extern "C" {
 
 int spk_abi_version(void) { return SPK_ABI_VERSION; }
+int spk_dim(void) { return SPK_DIM; }
 
 const char* spk_error_string(int code) {
     switch (code) {
@@ -405,7 +435,7 @@ int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkP
     c->dt_cache_valid = false;
     // size the sparse grid for the particle count up front: 2x2x2 particles per cell, 4x4x4 cells per block, 50 % load
     // (the reference's own estimate, cuda_sparse_grid.rs:222-229), doubled for the shell of neighbour blocks
-    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (64 * 8 * 50)) * 4u, 2048u);
+    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (SPK_CELLS_PER_BLOCK * SPK_PARTICLES_PER_CELL * 50)) * 4u, 2048u);
     GridBuffers& next = c->grid[1 - c->gcur];
     GridBuffers& curr = c->grid[c->gcur];
     if (c->dist_arena && want > c->dist_cap_hash) return SPK_EOVERFLOW; // the arena shared with the peers cannot grow
@@ -459,7 +489,7 @@ int spk_particles_commit_staged(spk_ctx* c) {
     c->cur = 0;
     c->sorted_valid = false;
     c->dt_cache_valid = false;
-    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (64 * 8 * 50)) * 4u, 2048u);
+    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (SPK_CELLS_PER_BLOCK * SPK_PARTICLES_PER_CELL * 50)) * 4u, 2048u);
     GridBuffers& next = c->grid[1 - c->gcur];
     if (c->dist_arena && want > c->dist_cap_hash) return SPK_EOVERFLOW;
     if (next.cap_hash < want) { CK(alloc_grid(c, next, want)); CK(ensure_slot_scratch(c, want)); }
@@ -666,6 +696,22 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
         std::memset(&d, 0, sizeof(d));
         if (cols[i].grid_boundary_handling > SPK_BOUNDARY_NONE) return SPK_EINVAL;
         d.shape = cols[i].shape_tag;
+#if SPK_DIM == 2
+        if (cols[i].shape_tag == SPK_SHAPE_CUBOID) {
+            std::memcpy(d.half_extents, cols[i].shape.cuboid.half_extents, 8);
+        } else if (cols[i].shape_tag == SPK_SHAPE_POLYLINE) {
+            const auto& pl = cols[i].shape.polyline;
+            if (pl.num_vertices && !pl.vertices) return SPK_EINVAL;
+            d.nrows = pl.num_vertices;
+            d.hf_flags = pl.flip_interior ? 2u : 0u;
+            data_off[i] = data.size();
+            data.insert(data.end(), pl.vertices, pl.vertices + (size_t)pl.num_vertices * 2);
+        } else {
+            return SPK_EUNSUPPORTED; // heightfield / trimesh are not built in dim2
+        }
+        std::memcpy(d.rot, cols[i].rotation, 8);
+        std::memcpy(d.tr, cols[i].translation, 8);
+#else
         if (cols[i].shape_tag == SPK_SHAPE_CUBOID) {
             std::memcpy(d.half_extents, cols[i].shape.cuboid.half_extents, 12);
         } else if (cols[i].shape_tag == SPK_SHAPE_HEIGHTFIELD) {
@@ -688,6 +734,7 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
         }
         std::memcpy(d.rot, cols[i].rotation, 16);
         std::memcpy(d.tr, cols[i].translation, 12);
+#endif
         d.friction = cols[i].friction;
         d.handling = cols[i].grid_boundary_handling;
     }
@@ -702,7 +749,7 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
     if (n) CK(cudaMemcpy(c->colliders, dc.data(), n * sizeof(DevCollider), cudaMemcpyHostToDevice));
     c->ncolliders = n;
     // colliders changed: invalidate the per-node projection cache of both grids (the reference uploads colliders once)
-    for (int g = 0; g < 2; ++g) CK(cudaMemsetAsync(c->grid[g].proj, 0, (size_t)c->grid[g].cap_blocks * 64 * 4, c->stream));
+    for (int g = 0; g < 2; ++g) CK(cudaMemsetAsync(c->grid[g].proj, 0, (size_t)c->grid[g].cap_blocks * SPK_CELLS_PER_BLOCK * 4, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return SPK_OK;
 }
@@ -738,7 +785,7 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
         if ((hc.overflow || hc.nab > g.cap_blocks) && c->dist_arena) return SPK_EOVERFLOW; // the shared arena cannot grow
         if (hc.overflow || hc.nab > g.cap_blocks) {
             // jump straight to the size the particle count suggests (the reference's estimate, cuda_sparse_grid.rs:222-233)
-            const uint64_t estimate = (uint64_t)next_pow2((uint64_t)c->n * 100 / (64 * 8 * 50)) * 4u;
+            const uint64_t estimate = (uint64_t)next_pow2((uint64_t)c->n * 100 / (SPK_CELLS_PER_BLOCK * SPK_PARTICLES_PER_CELL * 50)) * 4u;
             const uint64_t want = std::max<uint64_t>({(uint64_t)g.cap_hash * 2, (uint64_t)next_pow2((uint64_t)hc.nab * 4), std::min<uint64_t>(estimate, 1ull << 26)});
             if (want > (1ull << 30)) return SPK_EOVERFLOW;
             CK(alloc_grid(c, g, (uint32_t)want));
@@ -813,7 +860,7 @@ int spk_stage_g2p2g(spk_ctx* c, float dt, uint32_t damage_model) {
     return SPK_OK;
 }
 
-int spk_stage_grid_update(spk_ctx* c, float dt, const float gravity[3]) {
+int spk_stage_grid_update(spk_ctx* c, float dt, const float gravity[SPK_DIM]) {
     if (!c || !gravity) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));
     CK(spk_launch_grid_update(c, dt, gravity));
@@ -821,7 +868,7 @@ int spk_stage_grid_update(spk_ctx* c, float dt, const float gravity[3]) {
 }
 
 // CudaMpmPipeline::step_generic, cuda_mpm_pipeline.rs:273-659
-int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float gravity[3], SpkStepTimings* timings, float* simulated_time_out) {
+int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float gravity[SPK_DIM], SpkStepTimings* timings, float* simulated_time_out) {
     if (!ctxs || nctx == 0 || !params || !gravity) return SPK_EINVAL;
     if (nctx != 1) return SPK_EUNSUPPORTED; // one process per GPU; multi-GPU runs drive the stage + halo calls (sparkl_b200/distributed.py)
     spk_ctx* c = ctxs[0];
@@ -922,7 +969,7 @@ int spk_grid_read_nodes(spk_ctx* c, int which_grid, SpkGpuGridNode* dst, uint32_
     if (n_blocks > g.nab_host) return SPK_EINVAL;
     if (!n_blocks) return SPK_OK;
     CK(cudaSetDevice(c->device));
-    const size_t bytes = (size_t)n_blocks * 64 * sizeof(SpkGpuGridNode);
+    const size_t bytes = (size_t)n_blocks * SPK_CELLS_PER_BLOCK * sizeof(SpkGpuGridNode);
     CK(ensure_staging(c, bytes));
     CK(spk_launch_grid_export(c, which_grid, (SpkGpuGridNode*)c->staging, n_blocks));
     CK(cudaMemcpyAsync(dst, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));

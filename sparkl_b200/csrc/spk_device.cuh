@@ -2,6 +2,7 @@
 #pragma once
 #include "spk_internal.cuh"
 
+#if SPK_DIM == 3
 #define SPK_PACK_ORIGIN 0x00100000ll
 #define SPK_KEY_MASK 0x1fffffull
 
@@ -18,6 +19,24 @@ __device__ __forceinline__ unsigned long long spk_key_offset(unsigned long long 
     spk_unpack_key(k, x, y, z);
     return spk_pack_key(x + (o & 1), y + ((o >> 1) & 1), z + ((o >> 2) & 1));
 }
+#else
+#define SPK_PACK_ORIGIN 0x80000000ll
+#define SPK_KEY_MASK 0xffffffffull
+
+// BlockVirtualId::pack / unpack (dim2) — src_kernels/gpu_grid.rs:90-94,106-109 (32 bits per axis, x | y<<32, origin 2^31)
+__host__ __device__ __forceinline__ unsigned long long spk_pack_key(unsigned long long x, unsigned long long y) {
+    return (x & SPK_KEY_MASK) | ((y & SPK_KEY_MASK) << 32);
+}
+__host__ __device__ __forceinline__ void spk_unpack_key(unsigned long long k, unsigned long long& x, unsigned long long& y) {
+    x = k & SPK_KEY_MASK; y = (k >> 32) & SPK_KEY_MASK;
+}
+// key of block (b + o), o in {0,1}^2 encoded bit0 = x, bit1 = y
+__device__ __forceinline__ unsigned long long spk_key_offset(unsigned long long k, int o) {
+    unsigned long long x, y;
+    spk_unpack_key(k, x, y);
+    return spk_pack_key(x + (o & 1), y + ((o >> 1) & 1));
+}
+#endif
 
 // Associated cell of a coordinate: round(p / h) with IEEE division and round-half-away (Rust f32::round), saturating
 // cast to i64 with NaN -> 0 (gpu_grid.rs:273, PTX: div.rn.f32 + trunc(x + copysign(0.5, x)) + cvt.rzi.s64.f32).
@@ -39,9 +58,15 @@ __device__ __forceinline__ float spk_div_h(float x, float h, float inv_h) {
 __device__ __forceinline__ unsigned long long spk_block_coord(long long cell) {
     return (unsigned long long)(cell - 2 + SPK_PACK_ORIGIN * 4) / 4ull;
 }
+#if SPK_DIM == 3
 __device__ __forceinline__ unsigned long long spk_block_key_of_point(float x, float y, float z, float h) {
     return spk_pack_key(spk_block_coord(spk_assoc_cell(x, h)), spk_block_coord(spk_assoc_cell(y, h)), spk_block_coord(spk_assoc_cell(z, h)));
 }
+#else
+__device__ __forceinline__ unsigned long long spk_block_key_of_point(float x, float y, float /*unused*/, float h) {
+    return spk_pack_key(spk_block_coord(spk_assoc_cell(x, h)), spk_block_coord(spk_assoc_cell(y, h)));
+}
+#endif
 
 // 64-bit finaliser hash (same family as hashmap.rs:7-14; only set semantics of the map are observable)
 __device__ __forceinline__ uint32_t spk_hash(unsigned long long key, uint32_t mask) {

@@ -17,6 +17,23 @@
 //   * barrier: a one-CTA kernel writes an epoch flag (+ the dt candidate) into every peer's mailbox and spins on its own
 //              mailbox; two per substep.  The dt minimum rides on the second one.
 // The host never blocks for the exchange: the only read-back per substep is the 64-byte counter record of the sort.
+#include "spk_internal.cuh"
+#if SPK_DIM == 2
+// dim2 build: the NVLink peer-memory path is not built (the 2D scenes of the reference are single-GPU sized); the entry points
+// exist so both libraries export the same symbols, and fail loudly.
+bool spk_dist_active(const spk_ctx*) { return false; }
+bool spk_dist_grid_storage(spk_ctx*, int, uint32_t, unsigned long long**, uint32_t**) { return false; }
+cudaError_t spk_dist_launch_barrier(spk_ctx*, int) { return cudaErrorNotSupported; }
+cudaError_t spk_dist_launch_detect(spk_ctx*) { return cudaErrorNotSupported; }
+cudaError_t spk_dist_launch_push(spk_ctx*) { return cudaErrorNotSupported; }
+cudaError_t spk_dist_launch_merge(spk_ctx*) { return cudaErrorNotSupported; }
+extern "C" {
+int spk_dist_export(spk_ctx*, SpkDistDescriptor*) { return SPK_EUNSUPPORTED; }
+int spk_dist_attach(spk_ctx*, uint32_t, uint32_t, const SpkDistDescriptor*) { return SPK_EUNSUPPORTED; }
+int spk_dist_detach(spk_ctx* c) { return c ? SPK_OK : SPK_EINVAL; }
+int spk_dist_info(spk_ctx*, uint32_t*, uint32_t*) { return SPK_EUNSUPPORTED; }
+}
+#else
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -297,3 +314,5 @@ int spk_dist_info(spk_ctx* c, uint32_t* num_halo_blocks, uint32_t* epoch) {
 }
 
 } // extern "C"
+
+#endif // SPK_DIM

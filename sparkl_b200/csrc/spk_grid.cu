@@ -416,7 +416,7 @@ cudaError_t spk_launch_reset_grid(spk_ctx* c) {
     return cudaGetLastError();
 }
 
-cudaError_t spk_launch_grid_update(spk_ctx* c, float dt, const float gravity[3]) {
+cudaError_t spk_launch_grid_update(spk_ctx* c, float dt, const float gravity[SPK_DIM]) {
     GridBuffers& next = c->grid[1 - c->gcur];
     const uint32_t nab = next.nab_host;
     if (nab) {

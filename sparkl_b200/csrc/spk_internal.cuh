@@ -14,15 +14,34 @@
 
 #include "../../include/sparkl_abi.h"
 
+// SPK_DIM (include/sparkl_abi.h) selects the build: 3 -> libsparkl_b200.so, 2 -> libsparkl_b200_2d.so.  Host sequencing, hash
+// map, scans and particle streams are shared; the block shape (4^DIM cells, 2^DIM associated blocks) and the kernels that walk
+// the stencil (spk_g2p2g*.cu, spk_grid*.cu) are per dimension, like the reference's `dim2` / `dim3` features.
+#if SPK_DIM == 3
 #define SPK_CELLS_PER_BLOCK 64
 #define SPK_TILE_CELLS 512
+#define SPK_NBR 8 /* NUM_ASSOC_BLOCKS, src_kernels/gpu_grid.rs:13-16 */
+#define SPK_NBR_SHIFT 3
+#define SPK_CELL_SHIFT 6
+#define SPK_REF_G2P2G_THREADS 128u /* G2P2G_THREADS of the reference, src_kernels/cuda/mod.rs:15 (dispatch read-back) */
+#else
+#define SPK_CELLS_PER_BLOCK 16
+#define SPK_TILE_CELLS 64
+#define SPK_NBR 4
+#define SPK_NBR_SHIFT 2
+#define SPK_CELL_SHIFT 4
+#define SPK_REF_G2P2G_THREADS 64u /* dim2: src_kernels/cuda/mod.rs:12-13 */
+#endif
 #define SPK_ACC_CHANNELS 6
 #define SPK_EMPTY_KEY 0xffffffffffffffffull
 #define SPK_NO_BLOCK 0xffffffffu
 #ifndef SPK_G2P2G_CHUNK
+#if SPK_DIM == 3
 #define SPK_G2P2G_CHUNK 256 /* particles per g2p2g dispatch entry == threads per CTA */
+#else
+#define SPK_G2P2G_CHUNK 128 /* dim2: a 4x4-cell block holds ~64 particles at rest */
 #endif
-#define SPK_REF_G2P2G_THREADS 128u /* G2P2G_THREADS of the reference, src_kernels/cuda/mod.rs:15 (dispatch read-back) */
+#endif
 
 // particle flag bits (record A0.w)
 #define SPK_F_FAILED 1u
@@ -48,7 +67,7 @@ struct DevModel { // compact device image of GpuParticleModel (include/sparkl_ab
 
 struct DevCollider {
     float half_extents[3];
-    float rot[4]; // i, j, k, w
+    float rot[4]; // i, j, k, w (dim2: re, im of the unit complex, rest unused)
     float tr[3];
     float friction;
     uint32_t handling;
@@ -181,7 +200,7 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c);              // K2..K5: neighbou
 cudaError_t spk_launch_reset_grid(spk_ctx* c);
 cudaError_t spk_launch_estimate_dt(spk_ctx* c, float min_dt, float max_dt);
 cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt);
-cudaError_t spk_launch_grid_update(spk_ctx* c, float dt, const float gravity[3]);
+cudaError_t spk_launch_grid_update(spk_ctx* c, float dt, const float gravity[SPK_DIM]);
 cudaError_t spk_launch_pack_upload(spk_ctx* c, const void* d_status, const void* d_pos, const void* d_vel, const void* d_volume,
                                    const void* d_phase, const void* d_data, size_t first, size_t n);
 cudaError_t spk_launch_unpack(spk_ctx* c, int which, void* d_out, size_t n);

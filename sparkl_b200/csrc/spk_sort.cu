@@ -49,7 +49,7 @@ __global__ void activate_neighbours_kernel(unsigned long long* keys, uint32_t ca
     if (s >= cap_hash) return;
     if (slot_cnt[s] == 0) return; // only blocks that own particles (slots created here keep a zero count)
     const unsigned long long key = keys[s];
-    for (int o = 1; o < 8; ++o)
+    for (int o = 1; o < SPK_NBR; ++o)
         if (spk_hash_insert(keys, cap_hash, spk_key_offset(key, o)) == SPK_NO_BLOCK) counters->overflow = 1;
 }
 
@@ -154,11 +154,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned
 // kernel and scatter_perm_kernel; the true count comes from the device-side record)
 __global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, const DeviceCounters* __restrict__ counters) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t b = t >> 3, o = t & 7;
+    const uint32_t b = t >> SPK_NBR_SHIFT, o = t & (SPK_NBR - 1);
     if (b >= counters->nab || b >= next.cap_blocks) return;
     const unsigned long long key = spk_key_offset(next.blk_key[b], (int)o);
-    next.nbr_self[b * 8 + o] = spk_hash_get(next, key);
-    next.nbr_prev[b * 8 + o] = spk_hash_get(prev, key);
+    next.nbr_self[b * SPK_NBR + o] = spk_hash_get(next, key);
+    next.nbr_prev[b * SPK_NBR + o] = spk_hash_get(prev, key);
 }
 
 // finalize_particles_sort (sort.rs:201-221): sorted slot -> index in the current physical order
@@ -205,7 +205,7 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c) {
     cudaStream_t s = c->stream;
     const uint32_t n = (uint32_t)c->n;
     {
-        build_tables_kernel<<<(g.cap_blocks * 8 + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters);
+        build_tables_kernel<<<(g.cap_blocks * SPK_NBR + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters);
         c->launches += 1;
     }
     if (n) {

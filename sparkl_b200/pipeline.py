@@ -24,14 +24,19 @@ from .engine import Engine, _ptr
 class SingleGpuMpmContext(Engine):
     """One CUDA context: device, 2 streams, particle set, model set, collider set, sparse grid, dt accumulator."""
 
-    def __init__(self, cell_width: float, device: int = 0, block_capacity: int = 1024):
-        l = lib()
+    def __init__(self, cell_width: float, device: int = 0, block_capacity: int = 1024, dim: int = 3):
+        """`dim` selects the library: 3 = libsparkl_b200.so (crate sparkl3d), 2 = libsparkl_b200_2d.so (crate sparkl2d)"""
+        l = lib(dim)
         h = C.c_void_p()
         rc = l.spk_ctx_create(device, cell_width, block_capacity, C.byref(h))
         if rc:
-            raise abi.SparklError(rc, "spk_ctx_create: " + error_string(rc))
-        super().__init__(l, "spk_", h, error_string)
-        self.cell_width, self.device = cell_width, device
+            raise abi.SparklError(rc, "spk_ctx_create: " + error_string(rc, dim))
+        if dim == 2:
+            from . import abi2d as types
+        else:
+            types = abi
+        super().__init__(l, "spk_", h, lambda code: error_string(code, dim), types)
+        self.cell_width, self.device, self.dim = cell_width, device, dim
         self.particles = CudaParticleSet(self)
         self.models = CudaParticleModelSet(self)
         self.colliders = CudaColliderSet(self)
@@ -74,7 +79,8 @@ class SingleGpuMpmContext(Engine):
         """spk_particles_upload_async: `pc`'s arrays must be pinned, contiguous, of the ABI dtypes, and stay alive until the next
         blocking call; the host->device copy overlaps the frame the GPU is still computing"""
         arrs = [pc.status, pc.position, pc.velocity, pc.volume, pc.phase, pc.data]
-        for a, dt in zip(arrs, (abi.STATUS, abi.POSITION, abi.VELOCITY, abi.VOLUME, abi.PHASE, abi.DATA)):
+        T = self.T
+        for a, dt in zip(arrs, (T.STATUS, T.POSITION, T.VELOCITY, T.VOLUME, T.PHASE, T.DATA)):
             if a.dtype != dt or not a.flags.c_contiguous or len(a) != len(arrs[0]):
                 raise abi.SparklError(abi.EINVAL, "attribute dtype / layout / length mismatch")
         self._call("particles_stage_async" if stage_only else "particles_upload_async", *[_ptr(a) for a in arrs], len(arrs[0]))
@@ -87,7 +93,7 @@ class SingleGpuMpmContext(Engine):
         """enqueue the read-back of one attribute into `out` (pinned memory for real overlap) and return at once; the next
         step can be issued immediately.  `read_wait()` blocks until every outstanding read has landed."""
         n = len(self)
-        if out.dtype != abi.ATTR_DTYPES[which] or len(out) < n or not out.flags.c_contiguous:
+        if out.dtype != self.T.ATTR_DTYPES[which] or len(out) < n or not out.flags.c_contiguous:
             raise abi.SparklError(abi.EINVAL, "output buffer has the wrong dtype / length")
         self._call("particles_read_async", which, _ptr(out), n)
 
@@ -207,13 +213,14 @@ class CudaMpmPipeline:
         arr = (C.c_void_p * 1)(ctx._h)
         rc = ctx._lib.spk_step(arr, 1, C.byref(params), C.byref(g), C.byref(t) if timings else None, C.byref(sim))
         if rc:
-            raise abi.SparklError(rc, "spk_step: " + error_string(rc))
+            raise abi.SparklError(rc, "spk_step: " + error_string(rc, getattr(ctx, "dim", 3)))
         self.step_id += t.num_substeps
         return sim.value, t
 
 
 def context_from_scene(scene, device: int = 0) -> SingleGpuMpmContext:
-    ctx = SingleGpuMpmContext(scene.cell_width, device)
+    dim = scene.particles.position.dtype["point"].shape[0]  # the scene's particle layout decides which library runs it
+    ctx = SingleGpuMpmContext(scene.cell_width, device, dim=dim)
     ctx.models.from_models(scene.models)
     ctx.colliders.from_collider_set(scene.colliders)
     ctx.upload(scene.particles)

@@ -15,7 +15,8 @@ def canonical_sort_state(engine):
     for h in hdr:
         s = ids[h["first_particle"]: h["first_particle"] + h["num_particles"]]
         per_block[int(h["virtual_id"])] = np.sort(s)
-    ndisp = int(sum((int(h["num_particles"]) + 127) // 128 for h in hdr))
+    per = getattr(getattr(engine, "T", abi), "REF_G2P2G_THREADS", 128)  # G2P2G_THREADS of the reference: 128 (dim3) / 64 (dim2)
+    ndisp = int(sum((int(h["num_particles"]) + per - 1) // per for h in hdr))
     disp = engine.dispatch(ndisp)
     multiset = sorted((int(hdr["virtual_id"][d["active_block_id"]]), int(d["first_particle"]) - int(hdr["first_particle"][d["active_block_id"]])) for d in disp)
     return vids, per_block, multiset, hdr, ids
@@ -127,8 +128,16 @@ def assert_particles_close_robust(pa, pb, h, what=""):
     return out
 
 
-def node_positions(vids, h):
-    """world position of every node of the blocks `vids` (grid_update.rs:34-38): [nblocks, 64, 3] float32"""
+def node_positions(vids, h, dim=3):
+    """world position of every node of the blocks `vids` (grid_update.rs:34-38): [nblocks, 64, 3] float32 (dim2: [nblocks, 16, 2])"""
+    if dim == 2:
+        bx = (vids & np.uint64(0xFFFFFFFF)).astype(np.int64) - (1 << 31)
+        by = (vids >> np.uint64(32)).astype(np.int64) - (1 << 31)
+        cell = np.arange(16)
+        out = np.empty((len(vids), 16, 2), np.float32)
+        out[..., 0] = (bx[:, None] * 4 + (cell & 3)[None, :]).astype(np.float32) * np.float32(h)
+        out[..., 1] = (by[:, None] * 4 + (cell >> 2)[None, :]).astype(np.float32) * np.float32(h)
+        return out
     m = (1 << 21) - 1
     org = 1 << 20
     bx = (vids & m).astype(np.int64) - org
@@ -181,11 +190,13 @@ def assert_nodes_close(na, nb, tol, what="", scene=None, vids=None, oracle=None,
     assert (dir_err[same] <= 1e-5 * max(1.0, float(np.abs(nb["projection_scaled_dir"]).max()))).all(), f"{what}: projection_scaled_dir differs"
     if not same.all():
         assert scene is not None and oracle is not None and vids is not None, f"{what}: projection payload differs"
-        pos = node_positions(vids, scene.cell_width)[~same]
+        dim = na["momentum_velocity"].shape[-1]
+        pos = node_positions(vids, scene.cell_width, dim)[~same]
         ia, ib = na["projection_status_payload"][~same], nb["projection_status_payload"][~same]
+        project = oracle.cuboid_project if dim == 3 else (lambda c, q: oracle.collider_project2d(c, q, 2 * scene.cell_width))
         for p, i, j in zip(pos, ia, ib):
-            pi, _ = oracle.cuboid_project(scene.colliders[int(i)], p)
-            pj, _ = oracle.cuboid_project(scene.colliders[int(j)], p)
+            pi, _ = project(scene.colliders[int(i)], p)
+            pj, _ = project(scene.colliders[int(j)], p)
             di, dj = np.linalg.norm(pi - p), np.linalg.norm(pj - p)
             assert abs(di - dj) <= 1e-5 * scene.cell_width, f"{what}: collider index differs at a non-tie node {p}: {i}@{di} vs {j}@{dj}"
     return {k: v[0] for k, v in checks.items()}
