@@ -68,6 +68,7 @@ __device__ __forceinline__ unsigned long long spk_block_key_of_point(float x, fl
 }
 #endif
 
+#ifdef __CUDACC__ // hash map + warp helpers: device only (the arithmetic helpers above are also host-compiled by tests/host/)
 // 64-bit finaliser hash (same family as hashmap.rs:7-14; only set semantics of the map are observable)
 __device__ __forceinline__ uint32_t spk_hash(unsigned long long key, uint32_t mask) {
     key ^= key >> 33;
@@ -118,3 +119,4 @@ __device__ __forceinline__ uint32_t spk_lanemask_lt() {
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+#endif // __CUDACC__

@@ -344,50 +344,13 @@ def test_stop_after_one_substep_and_zero_dt_dim2():
 # ---------------------------------------------------------------------------------------------- the DEVICE math, compiled for the host
 # sparkl_b200/csrc/spk_math2d.cuh is what the dim2 CUDA kernel inlines (one shared SVD, DevModel parameter blocks).  It is compiled
 # here with g++ (tests/host/math2d_host.cpp) and compared with the oracle, so the kernel's arithmetic is checked without a GPU.
-DEVMODEL = np.dtype([("ctag", "<u4"), ("ptag", "<u4"), ("ftag", "<u4"), ("flags", "<u4"), ("c", "<f4", (4,)), ("p", "<f4", (8,)), ("f", "<f4", (2,))])
-
-
-def _devmodel(model: abi.ParticleModel) -> np.ndarray:
-    """mirror of spk_models_upload (sparkl_b200/csrc/spk_api.cu): SpkGpuParticleModel -> DevModel"""
-    d = np.zeros(1, DEVMODEL)
-    c, p, f = model.constitutive_model, model.plastic_model, model.failure_model
-    d["ctag"], d["ptag"], d["ftag"] = c.tag, 5 if p is None else p.tag, 2 if f is None else f.tag
-    if c.tag == 0:
-        d["c"][0, :3] = [c.cfl_coeff, c.lam, c.mu]
-        d["flags"] |= 1 if c.split_stress_on_failure else 0
-    elif c.tag == 1:
-        d["c"][0, :3] = [c.cfl_coeff, c.lam, c.mu]
-    elif c.tag == 2:
-        d["c"][0] = [c.pressure0, np.array([c.gamma], "<u4").view("<f4")[0], c.viscosity, c.max_neg_pressure]
-    if p is not None and p.tag == 0:
-        d["p"][0, :7] = [p.h0, p.h1, p.h2, p.h3, p.lam, p.mu, p.volume_correction]
-        d["flags"] |= 2 if p.only_active_when_failed else 0
-    elif p is not None and p.tag == 1:
-        d["p"][0, :5] = [p.mu, p.kappa, p.hardening_factor, p.cohesion, p.friction]
-        d["flags"] |= 4 if p.hardening_enabled else 0
-    elif p is not None and p.tag == 2:
-        d["p"][0, :4] = [p.mu, p.lam, p.tensile_strength, p.softening_rate]
-    elif p is not None and p.tag == 3:
-        d["p"][0, :3] = [p.min_epsilon, p.max_epsilon, p.hardening_coeff]
-    if f is not None:
-        d["f"][0] = [f.max_principal_stress, f.max_shear_stress]
-    return d
+from tests.host.emu2d import DEVMODEL, devmodel as _devmodel  # noqa: E402
 
 
 @pytest.fixture(scope="module")
 def hostmath():
-    src = os.path.join(ROOT, "tests", "host", "math2d_host.cpp")
-    out = os.path.join(ROOT, "tests", "host", "libmath2d_host.so")
-    hdr = os.path.join(ROOT, "sparkl_b200", "csrc", "spk_math2d.cuh")
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + cuda_inc, "-o", out, src])
-    l = C.CDLL(out)
-    assert l.hm_sizeof_devmodel() == DEVMODEL.itemsize
-    l.hm_dt_candidate.restype = C.c_float
-    l.hm_dt_candidate.argtypes = [C.c_void_p] + [C.c_float] * 7
-    l.hm_stress.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
-    return l
+    from tests.host.emu2d import math_lib
+    return math_lib()
 
 
 def _vp(a):
@@ -498,3 +461,64 @@ def test_device_math_eigen_extrema(hostmath):
         sym = np.array([[a[0, 0], a[1, 0]], [a[1, 0], a[1, 1]]], np.float64)
         ev = np.linalg.eigvalsh(sym)
         assert abs(mn.value - ev[0]) <= 1e-5 * max(1, np.abs(ev).max()) and abs(mx.value - ev[1]) <= 1e-5 * max(1, np.abs(ev).max())
+
+
+# ---------------------------------------------------------------------------------------------- the DEVICE kernels, emulated on the host
+# tests/host/kernels2d_host.cpp compiles the product's dim2 kernel sources (G2P2G particle body, reset, grid update with colliders,
+# export) with g++; tests/host/emu2d.py adds the numpy restatement of the sort and of the host sequencing.  The bodies of the GPU
+# parity tests (tests/test_dim2_gpu.py) are then run with that emulation in place of the CUDA context: same comparisons, same
+# tolerances, no GPU.  What this leaves to the GPU run: the launch glue (TMA staging / bulk-reduce flush, barriers, dispatch
+# indexing) and the CUDA sort kernels, which the dim2 library shares with the GPU-verified 3D build.
+def _host_engines(scene):
+    from tests.host.emu2d import Emu2D
+    g = Emu2D(scene.cell_width)
+    g.models_upload(scene.models)
+    g.colliders_upload(scene.colliders)
+    g.upload(scene.particles)
+    return g, _oracle(scene)
+
+
+@pytest.fixture()
+def gpu_test_bodies(monkeypatch):
+    import tests.test_dim2_gpu as T
+    monkeypatch.setattr(T, "_engines", _host_engines)
+    return T
+
+
+def test_device_kernels_on_host_elasticity2(gpu_test_bodies):
+    gpu_test_bodies.test_elasticity2_lockstep()
+    gpu_test_bodies.test_elasticity2_on_the_ground()
+
+
+@pytest.mark.parametrize("kind", ["corotated", "neo_hookean", "fluid", "sand", "nacc", "failure", "failure_split"])
+def test_device_kernels_on_host_models(gpu_test_bodies, kind):
+    gpu_test_bodies.test_model_block2_lockstep(kind)
+
+
+@pytest.mark.parametrize("kind", ["rankine", "snow"])
+def test_device_kernels_on_host_clamping_models(gpu_test_bodies, kind):
+    gpu_test_bodies.test_model_block2_lockstep_clamping_models(kind)
+
+
+def test_device_kernels_on_host_fluid_and_polyline(gpu_test_bodies):
+    gpu_test_bodies.test_fluids2_dam_break_lockstep()
+    gpu_test_bodies.test_polyline_trough_dim2()
+
+
+def test_device_kernels_on_host_roundtrip_and_kinematic():
+    """pack / unpack mirror + kinematic and static particles through the emulated kernel"""
+    sc = scenes2d.jitter(scenes2d.model_block2("corotated", 10, 8), 0.01, seed=5)
+    sc.particles.status["kinematic_vel_enabled"][:10] = 1
+    sc.particles.status["kinematic_vel"][:10] = (0.5, 0.25)
+    sc.particles.status["is_static"][10:20] = 1
+    sc.particles.status["failed"][20:24] = 1
+    g, o = _host_engines(sc)
+    back = g.read_all()
+    for name in ("position", "velocity", "volume", "status", "phase", "data"):
+        assert np.array_equal(getattr(back, name), getattr(sc.particles, name)), name
+    import tests.test_dim2_gpu as T
+    g.frame_begin(sc.params); o.frame_begin(sc.params)
+    rem = float(f32(sc.params.dt))
+    for s in range(4):
+        rem -= T._substep_both(g, o, sc, rem, T.RTOL_1 * (1 + 3 * s), f"substep {s}")
+    assert np.array_equal(g.read(abi.ATTR_STATUS)["failed"], o.read(abi.ATTR_STATUS)["failed"])
