@@ -304,3 +304,64 @@ class RefEngine(Engine):
         if rc:
             raise abi.SparklError(rc, "ref_step")
         return sim.value, t
+
+
+# ------------------------------------------------------------------------------------------------ oracle-A, dim2
+_REF2D = None
+REF2D_CUBIN = os.path.join(_HERE, "_ref", "sparkl2d-kernels.cubin")
+REF2D_LIB = os.path.join(_HERE, "_ref", "libref_harness2d.so")
+
+
+def ref2d_available() -> bool:
+    """the reference's own dim2 GPU kernels (resources/sparkl2d-kernels.ptx assembled by `make -C oracle ref`) + a CUDA driver"""
+    if not (os.path.exists(REF2D_CUBIN) and os.path.exists(REF2D_LIB)):
+        return False
+    try:
+        return bool(ref2d_lib().ref_available())
+    except OSError:
+        return False
+
+
+def ref2d_lib():
+    global _REF2D
+    if _REF2D is None:
+        _REF2D = C.CDLL(REF2D_LIB)
+        declare(_REF2D, "ref_")
+        vp = C.c_void_p
+        _REF2D.ref_available.restype = C.c_int
+        _REF2D.ref_create.argtypes = [C.c_int, C.c_float, C.c_char_p, C.POINTER(vp)]
+        _REF2D.ref_create.restype = C.c_int
+        _REF2D.ref_destroy.argtypes = [vp]
+        _REF2D.ref_step.argtypes = [vp, C.POINTER(abi.SolverParameters), C.POINTER(C.c_float * 3), C.POINTER(abi.StepTimings), C.POINTER(C.c_float)]
+        _REF2D.ref_step.restype = C.c_int
+    return _REF2D
+
+
+class RefEngine2D(Engine):
+    """The reference's unmodified dim2 GPU kernels driven by the -DSPK_DIM=2 build of oracle/ref_harness.cpp.  Collider-free
+    scenes only (colliders_upload with a non-empty list raises EUNSUPPORTED)."""
+
+    def __init__(self, cell_width: float, device: int = 0):
+        from sparkl_b200 import abi2d
+        l = ref2d_lib()
+        h = C.c_void_p()
+        rc = l.ref_create(device, cell_width, REF2D_CUBIN.encode(), C.byref(h))
+        if rc:
+            raise abi.SparklError(rc, "ref_create (dim2)")
+        super().__init__(l, "ref_", h, types=abi2d)
+        self.cell_width, self.device = cell_width, device
+
+    def __del__(self):
+        try:
+            self._lib.ref_destroy(self._h)
+        except Exception:
+            pass
+
+    def step(self, params: abi.SolverParameters, gravity):
+        g = (C.c_float * 3)(*gravity)
+        t = abi.StepTimings()
+        sim = C.c_float()
+        rc = self._lib.ref_step(self._h, C.byref(params), C.byref(g), C.byref(t), C.byref(sim))
+        if rc:
+            raise abi.SparklError(rc, "ref_step (dim2)")
+        return sim.value, t

@@ -26,6 +26,22 @@
 
 #include "../include/sparkl_abi.h"
 
+// The same file builds the dim2 harness (-DSPK_DIM=2 -> oracle/_ref/libref_harness2d.so driving resources/sparkl2d-kernels.ptx):
+// the kernels take the same parameter blocks in both dimensions (checked against the .entry declarations of both PTX files);
+// what changes is the block shape (4x4 threads, 16 nodes of 56 bytes per block), G2P2G_THREADS (64, src_kernels/cuda/mod.rs:12-13),
+// the particle struct sizes and the 8-byte gravity vector.  The dim2 GpuCollider byte image was not recovered, so the dim2
+// harness only runs collider-free scenes.
+#if SPK_DIM == 2
+#define REF_CELLS 16u
+#define REF_BLOCK_Z 1u
+#define REF_G2P2G_THREADS 64u
+#else
+#define REF_CELLS 64u
+#define REF_BLOCK_Z 4u
+#define REF_G2P2G_THREADS 128u
+#endif
+#define REF_NODE_BYTES sizeof(SpkGpuGridNode)
+
 namespace {
 
 struct Driver {
@@ -112,7 +128,7 @@ struct ref_ctx {
         std::memset(&b, 0, sizeof(b));
         b.cell_width = cell_width; b.buffer = g.buffer.p; b.active_blocks = g.active_blocks.p; b.num_active_blocks = num_active_blocks.p;
         b.entries = g.hashmap.p; b.capacity = g.block_capacity; b.dispatch = dispatch.p; b.dispatch_halo = dispatch_halo.p;
-        b.capacity_nodes = (uint64_t)g.block_capacity * 64; // cuda_sparse_grid.rs:116,133
+        b.capacity_nodes = (uint64_t)g.block_capacity * REF_CELLS; // cuda_sparse_grid.rs:116,133
         return b;
     }
 };
@@ -212,7 +228,7 @@ int upload_models(ref_ctx* c) {
 }
 int alloc_grid_data(ref_ctx* c, GridData& g, uint32_t block_capacity) { // CudaSparseGrid::with_capacity, cuda_sparse_grid.rs:53-90
     g.block_capacity = block_capacity;
-    if (int r = g.buffer.ensure((size_t)block_capacity * 64 * 72, true)) return r; // GpuGridNode::default() == all-zero bytes
+    if (int r = g.buffer.ensure((size_t)block_capacity * REF_CELLS * REF_NODE_BYTES, true)) return r; // GpuGridNode::default() == all-zero bytes
     if (int r = g.active_blocks.ensure((size_t)block_capacity * 24, true)) return r;
     if (int r = g.hashmap.ensure((size_t)block_capacity * 16, true)) return r;
     return reset_hashmap(c, g);
@@ -290,7 +306,8 @@ int ref_particles_upload(ref_ctx* c, const SpkParticleStatus* status, const SpkP
     if (!c) return SPK_EINVAL;
     CU(D.p_cuCtxSetCurrent(c->ctx));
     c->n = n;
-    struct { DevBuf* b; const void* src; size_t sz; } items[] = {{&c->status, status, 24}, {&c->pos, pos, 12}, {&c->vel, vel, 12}, {&c->volume, volume, 52},
+    struct { DevBuf* b; const void* src; size_t sz; } items[] = {{&c->status, status, sizeof(SpkParticleStatus)}, {&c->pos, pos, sizeof(SpkParticlePosition)},
+                                                                   {&c->vel, vel, sizeof(SpkParticleVelocity)}, {&c->volume, volume, sizeof(SpkParticleVolume)},
                                                                    {&c->phase, phase, 8}, {&c->data, data, 16}};
     std::vector<SpkParticleData> dflt;
     if (!data) { dflt.assign(n, SpkParticleData{-0.01f, 1.0f, 1.0f, 0.0f}); items[5].src = dflt.data(); }
@@ -307,10 +324,10 @@ int ref_particles_read(ref_ctx* c, int which, void* dst, size_t n) {
     CU(D.p_cuCtxSetCurrent(c->ctx));
     DevBuf* b; size_t sz;
     switch (which) {
-    case SPK_ATTR_POSITION: b = &c->pos; sz = 12; break;
-    case SPK_ATTR_VELOCITY: b = &c->vel; sz = 12; break;
-    case SPK_ATTR_STATUS: b = &c->status; sz = 24; break;
-    case SPK_ATTR_VOLUME: b = &c->volume; sz = 52; break;
+    case SPK_ATTR_POSITION: b = &c->pos; sz = sizeof(SpkParticlePosition); break;
+    case SPK_ATTR_VELOCITY: b = &c->vel; sz = sizeof(SpkParticleVelocity); break;
+    case SPK_ATTR_STATUS: b = &c->status; sz = sizeof(SpkParticleStatus); break;
+    case SPK_ATTR_VOLUME: b = &c->volume; sz = sizeof(SpkParticleVolume); break;
     case SPK_ATTR_PHASE: b = &c->phase; sz = 8; break;
     case SPK_ATTR_DATA: b = &c->data; sz = 16; break;
     case SPK_ATTR_SORTED_IDS: b = &c->sorted_ids; sz = 4; break;
@@ -329,9 +346,12 @@ int ref_models_upload(ref_ctx* c, const SpkGpuParticleModel* models, size_t n) {
 int ref_colliders_upload(ref_ctx* c, const SpkGpuCollider* cols, size_t n) {
     if (!c) return SPK_EINVAL;
     CU(D.p_cuCtxSetCurrent(c->ctx));
+#if SPK_DIM == 2
+    if (n) return SPK_EUNSUPPORTED; // the byte image of the dim2 GpuCollider was not recovered: collider-free scenes only
+#endif
     for (size_t i = 0; i < n; ++i) if (cols[i].shape_tag != SPK_SHAPE_CUBOID) return SPK_EUNSUPPORTED; // parry device layouts are not vendored
-    if (int r = c->d_colliders.ensure(std::max<size_t>(n, 1) * 336, true)) return r;
-    if (n) CU(D.p_cuMemcpyHtoD_v2(c->d_colliders.p, cols, n * 336));
+    if (int r = c->d_colliders.ensure(std::max<size_t>(n, 1) * sizeof(SpkGpuCollider), true)) return r;
+    if (n) CU(D.p_cuMemcpyHtoD_v2(c->d_colliders.p, cols, n * sizeof(SpkGpuCollider)));
     c->ncolliders = n;
     return SPK_OK;
 }
@@ -360,7 +380,7 @@ int ref_stage_sort(ref_ctx* c, SpkSortInfo* info) {
         CU(D.p_cuCtxSynchronize());
         CU(D.p_cuMemcpyDtoH_v2(&nab, c->num_active_blocks.p, 4));
         if ((uint64_t)nab > (uint64_t)g.block_capacity * 50 / 100) { // MAX_HASHMAP_LOAD_FACTOR, cuda_sparse_grid.rs:219-222
-            size_t estimated = std::max<size_t>(next_pow2((c->n * 100) / (64 * 8 * 50)), c->cur().block_capacity);
+            size_t estimated = std::max<size_t>(next_pow2((c->n * 100) / (REF_CELLS * (1u << SPK_DIM) * 50)), c->cur().block_capacity); // 4^DIM * 2^DIM * load factor
             size_t new_capacity = std::max<size_t>(estimated, (size_t)g.block_capacity * 2);
             g.active_blocks.release(); g.hashmap.release();
             if (int r = g.active_blocks.ensure(new_capacity * 24, true)) return r;
@@ -374,7 +394,7 @@ int ref_stage_sort(ref_ctx* c, SpkSortInfo* info) {
     g.nab = nab;
     GpuGridBlob next = c->blob(g);
     CUdeviceptr scan = c->scan_values.p, halo_scan = c->halo_scan_values.p, sorted = c->sorted_ids.p;
-    uint32_t ngroups = particles_len / nthreads + 1, nbg = nab / nthreads + 1, tpb = 128;
+    uint32_t ngroups = particles_len / nthreads + 1, nbg = nab / nthreads + 1, tpb = REF_G2P2G_THREADS;
     { void* a[] = {&pos, &particles_len, &next}; if (int r = launch(c, c->k_count, ngroups, nthreads, 1, 1, a)) return r; }
     { void* a[] = {&next, &scan}; if (int r = launch(c, c->k_copy_len, nbg, nthreads, 1, 1, a)) return r; }
     if (int r = scan_launch(c, scan, nab)) return r;
@@ -390,10 +410,10 @@ int ref_stage_sort(ref_ctx* c, SpkSortInfo* info) {
     }
     next = c->blob(g);
     if (nab) { void* a[] = {&next, &scan, &halo_scan, &tpb}; if (int r = launch(c, c->k_dispatch, nab, 32, 1, 1, a)) return r; }
-    const size_t desired = (size_t)nab * 64;
-    if (g.buffer.bytes / 72 < desired) { // grown buffers are initialised with default nodes (cuda_sparse_grid.rs:455-461)
+    const size_t desired = (size_t)nab * REF_CELLS;
+    if (g.buffer.bytes / REF_NODE_BYTES < desired) { // grown buffers are initialised with default nodes (cuda_sparse_grid.rs:455-461)
         g.buffer.release();
-        if (int r = g.buffer.ensure(desired * 72, true)) return r;
+        if (int r = g.buffer.ensure(desired * REF_NODE_BYTES, true)) return r;
     }
     if (info) { info->num_active_blocks = nab; info->num_dispatch_blocks = c->num_dispatch_blocks; info->num_dispatch_halo_blocks = 0; info->hashmap_capacity = g.block_capacity; }
     return SPK_OK;
@@ -404,8 +424,8 @@ int ref_stage_reset_grid(ref_ctx* c) { // cuda_mpm_pipeline.rs:371-376
     GridData& g = c->nxt();
     if (!g.nab) return SPK_OK;
     GpuGridBlob next = c->blob(g), curr = c->blob(c->cur());
-    { void* a[] = {&next}; if (int r = launch(c, c->k_reset_grid, g.nab, 4, 4, 4, a)) return r; }
-    { void* a[] = {&curr, &next}; if (int r = launch(c, c->k_copy_proj, g.nab, 4, 4, 4, a)) return r; }
+    { void* a[] = {&next}; if (int r = launch(c, c->k_reset_grid, g.nab, 4, 4, REF_BLOCK_Z, a)) return r; }
+    { void* a[] = {&curr, &next}; if (int r = launch(c, c->k_copy_proj, g.nab, 4, 4, REF_BLOCK_Z, a)) return r; }
     return SPK_OK;
 }
 
@@ -434,26 +454,26 @@ int ref_stage_g2p2g(ref_ctx* c, float dt, uint32_t damage_model) { // cuda_parti
     GpuGridBlob curr = c->blob(c->cur()), next = c->blob(c->nxt());
     uint8_t halo = 0;
     void* a[] = {&dt, &cols, &ncol, &status, &pos, &vel, &volume, &phase, &sorted, &models, &curr, &next, &damage_model, &halo};
-    return launch(c, c->k_g2p2g, c->num_dispatch_blocks, 128, 1, 1, a);
+    return launch(c, c->k_g2p2g, c->num_dispatch_blocks, REF_G2P2G_THREADS, 1, 1, a);
 }
 
-int ref_stage_grid_update(ref_ctx* c, float dt, const float gravity[3]) { // cuda_mpm_pipeline.rs:536-558
+int ref_stage_grid_update(ref_ctx* c, float dt, const float gravity[SPK_DIM]) { // cuda_mpm_pipeline.rs:536-558
     CU(D.p_cuCtxSetCurrent(c->ctx));
     GridData& g = c->nxt();
     if (g.nab) {
         GpuGridBlob next = c->blob(g);
         CUdeviceptr cols = c->d_colliders.p;
         uint64_t ncol = c->ncolliders;
-        float grav[3] = {gravity[0], gravity[1], gravity[2]};
+        float grav[3] = {gravity[0], gravity[1], SPK_DIM == 3 ? gravity[SPK_DIM - 1] : 0.f}; // Vector<Real> by value: 12 bytes (dim2: 8)
         void* a[] = {&dt, &next, &cols, &ncol, grav};
-        if (int r = launch(c, c->k_grid_update, g.nab, 4, 4, 4, a)) return r;
+        if (int r = launch(c, c->k_grid_update, g.nab, 4, 4, REF_BLOCK_Z, a)) return r;
     }
     c->curr = 1 - c->curr; // swap_buffers
     return SPK_OK;
 }
 
 // CudaMpmPipeline::step_generic (one context) with the reference's own per-phase event timers (CudaDeviceTimings)
-int ref_step(ref_ctx* c, const SpkSolverParameters* params, const float gravity[3], SpkStepTimings* t, float* simulated_time_out) {
+int ref_step(ref_ctx* c, const SpkSolverParameters* params, const float gravity[SPK_DIM], SpkStepTimings* t, float* simulated_time_out) {
     if (!c || !params) return SPK_EINVAL;
     CU(D.p_cuCtxSetCurrent(c->ctx));
     if (t) std::memset(t, 0, sizeof(*t));
@@ -512,7 +532,7 @@ int ref_grid_read_nodes(ref_ctx* c, int which, SpkGpuGridNode* dst, uint32_t n_b
     GridData& g = which ? c->nxt() : c->cur();
     if (n_blocks > g.nab) return SPK_EINVAL;
     CU(D.p_cuCtxSynchronize());
-    if (n_blocks) CU(D.p_cuMemcpyDtoH_v2(dst, g.buffer.p, (size_t)n_blocks * 64 * 72));
+    if (n_blocks) CU(D.p_cuMemcpyDtoH_v2(dst, g.buffer.p, (size_t)n_blocks * REF_CELLS * REF_NODE_BYTES));
     return SPK_OK;
 }
 int ref_grid_read_dispatch(ref_ctx* c, SpkDispatchBlock2ActiveBlock* dst, uint32_t n) {

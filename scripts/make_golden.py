@@ -19,7 +19,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from sparkl_b200 import abi, scenes  # noqa: E402
+from sparkl_b200 import abi, scenes, scenes2d  # noqa: E402
 
 # name -> (generator, args, jitter amplitude, seed, substeps, recorded substeps)
 CASES = {
@@ -36,7 +36,41 @@ CASES = {
 }
 
 
+# dim2 cases (reference: resources/sparkl2d-kernels.ptx through the -DSPK_DIM=2 harness).  All collider-free: the byte image of
+# the dim2 GpuCollider was not recovered (include/sparkl_abi.h), so the dim2 harness cannot upload colliders.
+CASES_2D = {
+    "elasticity2": ("elasticity2", (2, 0.3, False), 0.002, 31, 8, (0, 3, 7)),   # BASELINE.json configs[0] (pre-strained, see build_case)
+    "fluids2": ("fluids2", (24, 16, False), 0.002, 32, 8, (0, 3, 7)),
+    "corotated2": ("model_block2", ("corotated", 14, 12), 0.01, 33, 8, (0, 3, 7)),
+    "neo_hookean2": ("model_block2", ("neo_hookean", 14, 12), 0.01, 34, 8, (0, 3, 7)),
+    "sand2": ("model_block2", ("sand", 14, 12), 0.01, 35, 8, (0, 3, 7)),
+    "nacc2": ("model_block2", ("nacc", 14, 12), 0.01, 36, 8, (0, 3, 7)),
+    "rankine2": ("model_block2", ("rankine", 14, 12), 0.01, 37, 8, (0, 3, 7)),
+    "snow2": ("model_block2", ("snow", 14, 12), 0.01, 38, 8, (0, 3, 7)),
+    "failure2": ("model_block2", ("failure", 14, 12), 0.01, 39, 8, (0, 3, 7)),
+    "failure_split2": ("model_block2", ("failure_split", 14, 12), 0.01, 40, 8, (0, 3, 7)),
+}
+
+
+def case_dim(name):
+    return 2 if name in CASES_2D else 3
+
+
 def build_case(name):
+    if name in CASES_2D:
+        gen, args, amp, seed, nsub, rec = CASES_2D[name]
+        sc = scenes2d.jitter(scenes2d.SCENES[gen](*args), amp, seed=seed)
+        sc.colliders = []
+        if name == "elasticity2":  # free-falling stars would only exercise advection: pre-strain them so corotated + Rankine act
+            rng = np.random.Generator(np.random.PCG64(seed + 100))
+            n = len(sc.particles)
+            F = np.tile(np.eye(2, dtype=np.float32), (n, 1, 1)) + rng.uniform(-0.05, 0.05, (n, 2, 2)).astype(np.float32) * np.array(
+                [[1.0, 0.3], [0.3, 1.0]], np.float32)
+            sc.particles.volume["deformation_gradient"] = F.transpose(0, 2, 1).reshape(n, 4)
+        if name == "fluids2":  # a free-falling block at J = 1 feels no pressure: start from a seeded volume ratio J = 1 -+ 2 %
+            rng = np.random.Generator(np.random.PCG64(seed + 100))
+            sc.particles.volume["deformation_gradient"][:, 0] = (1.0 + rng.uniform(-0.02, 0.02, len(sc.particles))).astype(np.float32)
+        return sc, nsub, rec
     gen, args, amp, seed, nsub, rec = CASES[name]
     sc = scenes.jitter(scenes.SCENES[gen](*args), amp, seed=seed)
     return sc, nsub, rec
@@ -54,19 +88,27 @@ def record_particles(out, s, pc):
 
 def main():
     from oracle import binding as ob
-    outdir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden")
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    outdir = args[0] if args else os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
-    assert ob.ref_available(), "oracle/_ref not built or no CUDA device"
-    for name in CASES:
+    names = list(CASES_2D) if "--dim2" in sys.argv else (list(CASES) + list(CASES_2D) if "--all" in sys.argv else list(CASES))
+    for name in names:
         sc, nsub, rec = build_case(name)
-        e = ob.RefEngine(sc.cell_width)
+        table = CASES_2D if name in CASES_2D else CASES
+        if case_dim(name) == 2:
+            assert ob.ref2d_available(), "oracle/_ref (dim2) not built or no CUDA device"
+            e = ob.RefEngine2D(sc.cell_width)
+        else:
+            assert ob.ref_available(), "oracle/_ref not built or no CUDA device"
+            e = ob.RefEngine(sc.cell_width)
         e.models_upload(sc.models); e.colliders_upload(sc.colliders); e.upload(sc.particles)
         p = sc.params
         e.frame_begin(p)
         remaining = np.float32(p.dt)
         min_dt = float(np.float32(p.dt) / np.float32(p.max_num_substeps))
-        out = {"meta": np.array(json.dumps({"case": name, "generator": CASES[name][0], "args": CASES[name][1], "jitter": CASES[name][2], "seed": CASES[name][3],
-                                             "nsub": nsub, "recorded": list(rec), "what": "reference sparkl3d-kernels.ptx on B200 (oracle/_ref)"})),
+        out = {"meta": np.array(json.dumps({"case": name, "generator": table[name][0], "args": table[name][1], "jitter": table[name][2], "seed": table[name][3],
+                                             "nsub": nsub, "recorded": list(rec), "dim": case_dim(name),
+                                             "what": f"reference sparkl{case_dim(name)}d-kernels.ptx on B200 (oracle/_ref)"})),
                "pos_init": sc.particles.position["point"].copy()}
         dts, accs = [], []
         for s in range(nsub):

@@ -184,7 +184,13 @@ def assert_nodes_close(na, nb, tol, what="", scene=None, vids=None, oracle=None,
     }
     bad = {k: v for k, v in checks.items() if not (v[0] <= v[1])}
     assert not bad, f"{what}: node fields out of tolerance (error, allowed): {bad} (all: {checks})"
-    assert np.array_equal(na["projection_status_tag"], nb["projection_status_tag"]), f"{what}: projection tags differ"
+    if not np.array_equal(na["projection_status_tag"], nb["projection_status_tag"]):
+        diff = na["projection_status_tag"] != nb["projection_status_tag"]
+        where = ""
+        if vids is not None and scene is not None:
+            pos = node_positions(vids, scene.cell_width, na["momentum_velocity"].shape[-1])[diff]
+            where = f"; first nodes {pos[:4].tolist()} tags {na['projection_status_tag'][diff][:4].tolist()} vs {nb['projection_status_tag'][diff][:4].tolist()}"
+        raise AssertionError(f"{what}: projection tags differ on {int(diff.sum())} of {diff.size} nodes{where}")
     same = na["projection_status_payload"] == nb["projection_status_payload"]
     dir_err = np.abs(na["projection_scaled_dir"].astype(np.float64) - nb["projection_scaled_dir"]).max(axis=-1) if na.size else np.zeros(0)
     assert (dir_err[same] <= 1e-5 * max(1.0, float(np.abs(nb["projection_scaled_dir"]).max()))).all(), f"{what}: projection_scaled_dir differs"
@@ -255,7 +261,7 @@ def golden_cases():
 
 def golden_particles(fx, s, template: abi.ParticleComponents) -> abi.ParticleComponents:
     """ParticleComponents holding the reference kernels' state after substep `s` (immutable fields from the scene)"""
-    pc = abi.ParticleComponents(len(template))
+    pc = type(template)(len(template))  # abi.ParticleComponents or abi2d.ParticleComponents
     for name in ("status", "position", "velocity", "volume", "phase", "data"):
         setattr(pc, name, getattr(template, name).copy())
     pc.position["point"] = fx[f"pos_{s}"]
@@ -269,11 +275,12 @@ def golden_particles(fx, s, template: abi.ParticleComponents) -> abi.ParticleCom
     return pc
 
 
-def run_against_golden(make_engine, case, base=2e-5, growth=3.0):
+def run_against_golden(make_engine, case, base=2e-5, growth=3.0, dt_rtol=1e-5):
     """Drives `make_engine(scene)` in lock-step with the committed outputs of the reference's own GPU kernels
     (tests/golden/<case>.npz, generated by scripts/make_golden.py on a B200): same initial state, the reference's dt at
     every substep; active block set + per-block particle counts exact (up to particles on a rounding boundary), dt
-    accumulator within 1e-5, particle state within Tol at the recorded substeps, final grid mass / velocity / tags."""
+    accumulator within 1e-5 (`dt_rtol`; looser for the dim2 fluid whose single-particle bound is a 0/0 at J = 1, see
+    tests/test_dim2_gpu.py), particle state within Tol at the recorded substeps, final grid mass / velocity / tags."""
     import json
     import os
     from scripts.make_golden import build_case
@@ -301,7 +308,7 @@ def run_against_golden(make_engine, case, base=2e-5, growth=3.0):
         e.stage_reset_grid()
         e.stage_estimate_dt(min_dt, float(min(remaining, np.float32(p.max_substep_dt))))
         acc, ref_acc = e.dt_acc(), int(fx["dt_accs"][s])
-        assert abs(acc - ref_acc) <= max(2, int(1e-5 * ref_acc)), f"{case} substep {s}: dt accumulator {acc} vs reference {ref_acc}"
+        assert abs(acc - ref_acc) <= max(2, int(dt_rtol * ref_acc)), f"{case} substep {s}: dt accumulator {acc} vs reference {ref_acc}"
         e.set_dt_acc(ref_acc)
         dt = float(fx["dts"][s])
         e.stage_g2p2g(dt)
@@ -335,7 +342,7 @@ def run_against_golden(make_engine, case, base=2e-5, growth=3.0):
     if not np.array_equal(tag, rtag):
         # legal only where two colliders are equidistant from the node up to round-off (strict `<` on f32 distances,
         # grid_update.rs:121-124): e.g. a node 0.8 inside one wall and 0.8 outside the next one
-        pos = node_positions(common, sc.cell_width)[tag != rtag]
+        pos = node_positions(common, sc.cell_width, nodes["momentum_velocity"].shape[-1])[tag != rtag]
         for pt in pos:
             d = np.sort([_axis_aligned_cuboid_distance(c, pt) for c in sc.colliders])
             assert len(d) >= 2 and abs(d[0] - d[1]) <= 1e-5 * sc.cell_width, f"{case}: projection tag differs at a non-tie node {pt}"
