@@ -12,11 +12,14 @@
 // `determinant`) and parry2d 0.13.0 (`Cuboid::project_point`, `Segment::normal`).  Only U·f(Σ)·Vᵀ products and eigenvalue
 // extrema are consumed, so the 2x2 SVD / eigen-decomposition are computed in closed form in double and rounded to f32.
 //
-// PARITY STATUS: **parity unpinned**.  The reference holds no golden vectors for this path and its dim2 kernels
-// (resources/sparkl2d-kernels.ptx) have not been run against this file; what pins it is (a) that every dimension-independent
-// formula is shared with the 3D oracle, which IS pinned against the reference's own 3D kernels, (b) known-answer tests of the
-// dimension-dependent pieces (keys, stencil, 2x2 SVD, DIM-dependent constants) and (c) conservation / symmetry properties
-// (tests/test_dim2_cpu.py).
+// PARITY STATUS: pinned against the reference itself on collider-free scenes.  The reference holds no golden vectors for this
+// path; its dim2 kernels (resources/sparkl2d-kernels.ptx, assembled for sm_100a and driven by the -DSPK_DIM=2 build of
+// oracle/ref_harness.cpp) were run on a B200 on ten seeded scenes (every constitutive / plastic / failure model) and their outputs
+// are committed as tests/golden/*2.npz: this file reproduces them to ~1e-6 relative (tests/test_golden_cpu.py), and product, oracle
+// and reference kernels run in lock-step in tests/test_dim2_gpu.py.  NOT pinned against the reference: the collider branch of
+// grid_update in dim2 (the byte image of the dim2 GpuCollider / parry2d shapes was not recovered, so the harness cannot upload
+// colliders); there the pins are the shared code path with the 3D oracle, brute-force geometry checks and the x <-> y symmetry
+// tests of tests/test_dim2_cpu.py.
 #define SPK_DIM 2
 #include "../include/sparkl_abi.h"
 

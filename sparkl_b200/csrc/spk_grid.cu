@@ -265,7 +265,9 @@ __global__ void __launch_bounds__(256) grid_update_kernel(GridBuffers g, uint32_
         spk_unpack_key(g.blk_key[b], kx, ky, kz);
         const long long cx = ((long long)kx - SPK_PACK_ORIGIN) * 4 + (cell & 3), cy = ((long long)ky - SPK_PACK_ORIGIN) * 4 + ((cell >> 2) & 3),
                         cz = ((long long)kz - SPK_PACK_ORIGIN) * 4 + (cell >> 4);
-        const Vec3 pos{(float)cx * h, (float)cy * h, (float)cz * h}; // grid_update.rs:34-38
+        // grid_update.rs:34-38; __fmul_rn keeps the products rounded (no fma contraction with the collider code's subtractions),
+        // as in the reference: it decides ties such as `dist - h <= 0` for nodes exactly one cell above an axis-aligned surface
+        const Vec3 pos{__fmul_rn((float)cx, h), __fmul_rn((float)cy, h), __fmul_rn((float)cz, h)};
         bool have = false, best_inside = false;
         float best_dist = FLT_MAX;
         Vec3 best_dir{0.f, 0.f, 0.f};

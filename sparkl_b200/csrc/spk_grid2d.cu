@@ -176,7 +176,10 @@ __global__ void __launch_bounds__(256) grid_update_kernel(GridBuffers g, uint32_
         unsigned long long kx, ky;
         spk_unpack_key(g.blk_key[b], kx, ky);
         const long long cx = ((long long)kx - SPK_PACK_ORIGIN) * 4 + (cell & 3), cy = ((long long)ky - SPK_PACK_ORIGIN) * 4 + (cell >> 2);
-        const Vec2 pos{(float)cx * h, (float)cy * h}; // grid_update.rs:34-38
+        // grid_update.rs:34-38.  __fmul_rn: the product must be ROUNDED before the collider code subtracts from it, as in the
+        // reference (rustc never contracts a * b - c into an fma); a fused cy * h - y_surface decides the `dist - h <= 0` test of
+        // the friction branch differently for nodes exactly one cell above an axis-aligned surface
+        const Vec2 pos{__fmul_rn((float)cx, h), __fmul_rn((float)cy, h)};
         bool have = false, best_inside = false;
         float best_dist = FLT_MAX;
         Vec2 best_dir{0.f, 0.f};

@@ -14,6 +14,7 @@
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline long long __float2ll_rz(float x) { // cvt.rzi.s64.f32: saturating, NaN -> 0
     if (x != x) return 0;
     if (x >= 9.2233720368547758e18f) return INT64_MAX;
