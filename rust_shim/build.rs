@@ -6,11 +6,19 @@ use std::{env, path::PathBuf, process::Command};
 fn main() {
     let csrc = PathBuf::from(env::var("SPARKL_B200_CSRC").unwrap_or_else(|_| "../sparkl_b200/csrc".into()));
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
-    let sources = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu"];
+    // one source tree, two crates — like the reference's `dim2` / `dim3` features (crates/sparkl2d, crates/sparkl3d): the
+    // sparkl2d crate builds the same host sequencing / sort / ABI sources with -DSPK_DIM=2 and the dim2 stencil kernels
+    let dim2 = env::var("CARGO_FEATURE_DIM2").is_ok();
+    let sources: &[&str] = if dim2 {
+        &["spk_api.cu", "spk_sort.cu", "spk_g2p2g2d.cu", "spk_grid2d.cu", "spk_dist.cu"]
+    } else {
+        &["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu", "spk_dist.cu"]
+    };
     let mut objects = vec![];
     for s in sources {
         let obj = out.join(s.replace(".cu", ".o"));
         let status = Command::new("nvcc")
+            .arg(if dim2 { "-DSPK_DIM=2" } else { "-DSPK_DIM=3" })
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-c"])
             .arg(csrc.join(s))
             .arg("-o")
