@@ -360,6 +360,23 @@ int spk_colliders_upload(spk_ctx* ctx, const SpkGpuCollider* colliders, size_t n
 int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float gravity[SPK_DIM],
              SpkStepTimings* timings_or_null, float* simulated_time_out);
 
+/* ---- custom particle kernels: `CudaParticleKernelsLauncher` + `CudaMpmPipeline::step_generic`
+ * (src/cuda/cuda_particle_kernels.rs:7-27, cuda_mpm_pipeline.rs:273-281,299-302,381-392,479-498).  A host that compiles its own
+ * G2P2G kernel — `g2p2g_kernel<MODE, MyUpdater>` from sparkl_b200/csrc/spk_g2p2g_kernel.cuh, the counterpart of the reference's
+ * `g2p2g_generic::<MyUpdater>` — registers its launch functions here; spk_step / spk_stage_* then call them instead of the
+ * default ones.  A NULL member keeps the default for that launch.  The callbacks run on the caller's thread, must enqueue on the
+ * context's stream (spk_ctx_stream) and return 0 or a cudaError_t / SPK_E* code, which the calling entry point returns.
+ * `spk_default_launch_*` are the `DefaultCudaParticleKernelsLauncher`: a custom launcher may fall back to them. */
+typedef struct SpkParticleKernelsLauncher {
+    void* user;                                                                   /* passed back to every callback */
+    int (*timestep_started)(void* user);                                          /* once per spk_step, before the first substep */
+    int (*launch_estimate_particle_timestep_length)(void* user, spk_ctx* ctx, float min_dt, float max_dt);
+    int (*launch_g2p2g)(void* user, spk_ctx* ctx, float timestep_length);
+} SpkParticleKernelsLauncher;
+int spk_set_particle_kernels_launcher(spk_ctx* ctx, const SpkParticleKernelsLauncher* launcher_or_null); /* copied; NULL restores the default */
+int spk_default_launch_estimate_particle_timestep_length(spk_ctx* ctx, float min_dt, float max_dt);
+int spk_default_launch_g2p2g(spk_ctx* ctx, float timestep_length);
+
 /* ---- stage-level calls: the pieces step_generic sequences, exposed so that (a) the parity tests can compare
  * each stage with the oracle and (b) the multi-process pipeline can interleave the halo exchange. */
 /* reset of the frame's dt accumulator: timestep_length.copy_from(from_sec(params.dt)) (cuda_mpm_pipeline.rs:294-299) */

@@ -24,6 +24,7 @@ EXPORTS = [
     "spk_halo_begin", "spk_halo_active_keys", "spk_halo_tag", "spk_halo_count", "spk_halo_pack", "spk_halo_merge", "spk_grid_num_active_blocks",
     "spk_grid_read_headers", "spk_grid_read_nodes", "spk_grid_read_dispatch", "spk_device_ptr", "spk_g2p2g_time",
     "spk_dist_export", "spk_dist_attach", "spk_dist_detach", "spk_dist_info",
+    "spk_set_particle_kernels_launcher", "spk_default_launch_estimate_particle_timestep_length", "spk_default_launch_g2p2g",
 ]
 
 
@@ -68,6 +69,9 @@ def lib(dim: int = 3):
         l.spk_dist_attach.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
         l.spk_dist_detach.argtypes = [vp]
         l.spk_dist_info.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        l.spk_set_particle_kernels_launcher.argtypes = [vp, vp]
+        l.spk_default_launch_estimate_particle_timestep_length.argtypes = [vp, C.c_float, C.c_float]
+        l.spk_default_launch_g2p2g.argtypes = [vp, C.c_float]
         for name in EXPORTS:
             if name not in ("spk_error_string",):
                 getattr(l, name).restype = C.c_int

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu", "spk_dist.cu"]
 # the dim2 library: same host sequencing / sort / ABI sources compiled with -DSPK_DIM=2, its own stencil kernels
 SOURCES_2D = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g2d.cu", "spk_grid2d.cu", "spk_dist.cu"]
-HEADERS = ["spk_internal.cuh", "spk_device.cuh", "spk_math.cuh", "spk_math2d.cuh", "spk_g2p2g2d_body.cuh", "../../include/sparkl_abi.h"]
+HEADERS = ["spk_internal.cuh", "spk_device.cuh", "spk_math.cuh", "spk_math2d.cuh", "spk_g2p2g2d_body.cuh", "spk_updater.cuh", "spk_g2p2g_kernel.cuh", "../../include/sparkl_abi.h"]
 LIB = os.path.join(HERE, "libsparkl_b200.so")
 LIB_2D = os.path.join(HERE, "libsparkl_b200_2d.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -27,10 +27,23 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+EXAMPLE_SRC = os.path.join(os.path.dirname(HERE), "examples", "custom_updater", "custom_updater.cu")
+EXAMPLE_LIB = os.path.join(os.path.dirname(HERE), "examples", "custom_updater", "libcustom_updater.so")
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """builds both libraries; returns the path of the 3D one"""
+    """builds both libraries (and the custom-updater example that instantiates the library's kernel template); returns the path of
+    the 3D one"""
     _build_one(SOURCES, ".o", [], LIB, force, verbose)
     _build_one(SOURCES_2D, ".2d.o", ["-DSPK_DIM=2"], LIB_2D, force, verbose)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    if os.path.exists(EXAMPLE_SRC) and (force or _stale(EXAMPLE_LIB, [EXAMPLE_SRC] + hdrs)):
+        cmd = [NVCC] + [f for f in FLAGS if f not in ("-Xptxas", "-v")] + ["-shared", "-o", EXAMPLE_LIB, EXAMPLE_SRC]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed on the custom-updater example")
     return LIB
 
 

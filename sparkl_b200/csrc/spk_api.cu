@@ -318,6 +318,16 @@ int upload_range(spk_ctx* c, const SpkParticleStatus* status, const SpkParticleP
 
 } // namespace
 
+// CudaParticleKernelsLauncher dispatch: the registered callbacks, else the default launches
+static int launch_g2p2g_hooked(spk_ctx* c, float dt) {
+    if (c->launcher.launch_g2p2g) return c->launcher.launch_g2p2g(c->launcher.user, c, dt);
+    return (int)spk_launch_g2p2g(c, dt);
+}
+static int launch_estimate_dt_hooked(spk_ctx* c, float min_dt, float max_dt) {
+    if (c->launcher.launch_estimate_particle_timestep_length) return c->launcher.launch_estimate_particle_timestep_length(c->launcher.user, c, min_dt, max_dt);
+    return (int)spk_launch_estimate_dt(c, min_dt, max_dt);
+}
+
 int spk_dist_realloc_grids(spk_ctx* c, uint32_t cap_hash) {
     for (int g = 0; g < 2; ++g) CK(alloc_grid(c, c->grid[g], cap_hash));
     CK(ensure_slot_scratch(c, cap_hash));
@@ -642,7 +652,11 @@ int spk_models_upload(spk_ctx* c, const SpkGpuParticleModel* models, size_t n) {
             d.c[2] = m.constitutive.monaghan.m.viscosity; d.c[3] = m.constitutive.monaghan.m.max_neg_pressure;
             break;
         }
-        case SPK_CONSTITUTIVE_CUSTOM: break; // zero stress, no dt bound (gpu_constitutive_model.rs:83,108)
+        case SPK_CONSTITUTIVE_CUSTOM: { // zero stress, no dt bound in the default updater (gpu_constitutive_model.rs:83,108)
+            const uint32_t id = m.constitutive.custom.id; // kept (as bits) for custom updaters: GpuConstitutiveModel::Custom(id)
+            std::memcpy(&d.c[0], &id, 4);
+            break;
+        }
         default: return SPK_EINVAL;
         }
         switch (m.plastic_tag) {
@@ -754,6 +768,26 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
     return SPK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ custom particle kernels
+int spk_set_particle_kernels_launcher(spk_ctx* c, const SpkParticleKernelsLauncher* l) {
+    if (!c) return SPK_EINVAL;
+    if (l) c->launcher = *l;
+    else std::memset(&c->launcher, 0, sizeof(c->launcher));
+    c->dt_cache_valid = false; // the cached CFL candidate was produced by the previous updater
+    return SPK_OK;
+}
+int spk_default_launch_estimate_particle_timestep_length(spk_ctx* c, float min_dt, float max_dt) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    return (int)spk_launch_estimate_dt(c, min_dt, max_dt);
+}
+int spk_default_launch_g2p2g(spk_ctx* c, float dt) {
+    if (!c) return SPK_EINVAL;
+    if (!c->sorted_valid) return SPK_ESTATE;
+    CK(cudaSetDevice(c->device));
+    return (int)spk_launch_g2p2g(c, dt);
+}
+
 // ------------------------------------------------------------------------------------------------ stages
 int spk_frame_begin(spk_ctx* c, const SpkSolverParameters* params) {
     if (!c || !params) return SPK_EINVAL;
@@ -830,7 +864,7 @@ int spk_stage_estimate_dt(spk_ctx* c, float min_dt, float max_dt, float* dt_out)
             c->dt_acc_host = std::min(c->dt_acc_host, host_dt_from_sec(d));
         }
     } else {
-        CK(spk_launch_estimate_dt(c, min_dt, max_dt));
+        { int rc = launch_estimate_dt_hooked(c, min_dt, max_dt); if (rc) return rc; }
         if (spk_dist_active(c)) CK(spk_dist_launch_barrier(c, 2)); // dt_acc <- min over the ranks
         int rc = read_counters(c);
         if (rc) return rc;
@@ -856,8 +890,7 @@ int spk_stage_g2p2g(spk_ctx* c, float dt, uint32_t damage_model) {
     if (!c) return SPK_EINVAL;
     if (!c->sorted_valid) return SPK_ESTATE;
     CK(cudaSetDevice(c->device));
-    CK(spk_launch_g2p2g(c, dt));
-    return SPK_OK;
+    return launch_g2p2g_hooked(c, dt);
 }
 
 int spk_stage_grid_update(spk_ctx* c, float dt, const float gravity[SPK_DIM]) {
@@ -880,6 +913,7 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
     if ((rc = spk_frame_begin(c, params))) return rc;
     const bool dist = spk_dist_active(c);
     if (dist && c->n == 0) return SPK_ESTATE; // every rank takes part in the device-side barriers
+    if (c->launcher.timestep_started && (rc = c->launcher.timestep_started(c->launcher.user))) return rc; // :299-302
     if (params->dt == 0.0f || c->n == 0) { // nothing to simulate (:305-309)
         if (simulated_time_out) *simulated_time_out = params->dt;
         return SPK_OK;
@@ -905,7 +939,7 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
             CK(spk_dist_launch_detect(c));
         }
         if (timings) CK(cudaEventRecord(ev[3], c->stream));
-        CK(spk_launch_g2p2g(c, dt));
+        if ((rc = launch_g2p2g_hooked(c, dt))) return rc;
         if (timings) CK(cudaEventRecord(ev[4], c->stream));
         if (dist) { // NVLink red.add of the shared blocks into the peers, barrier (+ global dt minimum), fold what arrived
             if (!c->dist_fused_push) CK(spk_dist_launch_push(c)); // default: pushed by g2p2g's own flush

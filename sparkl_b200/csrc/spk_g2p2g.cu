@@ -10,622 +10,8 @@
 //            update in registers (one shared SVD), coalesced store into the NEXT particle buffer at the sorted index.
 //   stage 2  P2G into a shared-memory accumulation tile laid out [octant][channel][cell] (see p2g_* below).
 //   stage 3  the tile is flushed to the next grid with 8 TMA bulk reduce-adds (1.5 KB each, f32 add at L2).
-#include "spk_device.cuh"
-#include "spk_math.cuh"
+#include "spk_g2p2g_kernel.cuh"
 
-namespace {
+cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) { return spk_launch_g2p2g_with<DefaultParticleUpdater>(c, dt); }
 
-#ifndef SPK_G2P2G_MIN_CTAS
-#define SPK_G2P2G_MIN_CTAS 3
-#endif
-constexpr int G2P2G_THREADS = 256;
-constexpr int G2P2G_CHUNK = SPK_G2P2G_CHUNK;
-constexpr int NBINS = 216;         // 6x6x6 possible stencil-base cells of a block's particles after advection
-constexpr int PAY_FLOATS = 28;     // staged P2G payload per particle (7 float4)
-
-struct G2P2GParams {
-    ParticleBuffers src, dst;
-    float4* vel_out;
-    const float4* cold;
-    const uint32_t* perm;
-    const DispatchEntry* dispatch;
-    const DevModel* models;
-    const int32_t* nbr_self;
-    const int32_t* nbr_prev;
-    float* acc;             // next grid accumulators [block][6][64]
-    const float4* prev_vel; // previous grid velocities [block][64]
-    float h, inv_h, dt;
-    uint32_t ndispatch;
-    uint32_t* dt_raw_bits; // CFL candidate of the NEXT substep (fused K15)
-    // multi-GPU (world == 0: single GPU): shared blocks are ALSO reduced into every holder's halo accumulator over NVLink
-    uint32_t world;
-    const uint32_t* blk_halo;   // [block] bit0: active on another rank too (spk_dist.cu: dist_detect_kernel)
-    const int32_t* peer_ids;    // [block][world] the peer's id of the block, -1 if absent
-    float* const* peer_hacc;    // [world] peer-mapped `hacc` of each rank's next grid
-};
-
-// shared memory carve-up (dynamic)
-constexpr int SM_VEL = 0;                                   // float4[512]            [octant][cell]
-constexpr int SM_ACC = SM_VEL + 512 * 16;                   // float[8*6*64]          [octant][channel][cell]
-constexpr int SM_PAY = SM_ACC + 8 * 6 * 64 * 4;             // float[256*28]          staged P2G payloads, cell-sorted
-constexpr int SM_BINCNT = SM_PAY + G2P2G_CHUNK * PAY_FLOATS * 4;
-constexpr int SM_BINSTART = SM_BINCNT + 224 * 4;
-constexpr int SM_BINLIST = SM_BINSTART + 224 * 4;
-constexpr int SM_MISC = SM_BINLIST + 224 * 2;               // mbarrier (8) + nbr_self[8] + nbr_prev[8] + nnz
-constexpr int SM_HALO = SM_MISC + 8 + 32 + 32 + 16;          // uint32[8]: bit0 = octant block is shared with another rank (multi-GPU)
-constexpr int SM_TOTAL = SM_HALO + 32;
-
-// ---- TMA bulk helpers (sm_90+; SASS: UBLKCP / UBLKRED) ------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(phase)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_f32_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_commit_and_wait_read() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// tile index helpers: tile coordinate t in [0,8) per axis -> (cell part, octant part) of the [octant][...][cell] layout
-__device__ __forceinline__ int cell_part(int t, int axis) { return (t & 3) << (2 * axis); }
-__device__ __forceinline__ int oct_part(int t, int axis) { return (t >> 2) << axis; }
-
-// QuadraticKernel::eval_all, src_core/dynamics/solver/kernel.rs:15-21
-__device__ __forceinline__ void quad_weights(float x, float w[3]) {
-    w[0] = 0.5f * ((1.5f - x) * (1.5f - x));
-    w[1] = 0.75f - ((x - 1.f) * (x - 1.f));
-    w[2] = 0.5f * ((x - 0.5f) * (x - 0.5f));
-}
-
-// MODE 0: every particle adds its 27x6 contributions to the shared tile with float atomics (CAS loops on sm_100).
-// MODE 1: particles are counting-sorted by stencil-base cell inside the CTA, their P2G payloads staged in shared
-//         memory, and 9-lane groups (one lane per (sy, sz) stencil column) accumulate a whole cell in registers before
-//         touching the tile: shared float atomics drop from 162 per particle to 162 per occupied cell, with no
-//         same-address conflicts inside a group.
-template <int MODE>
-__global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kernel(const G2P2GParams P) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    float4* s_vel = reinterpret_cast<float4*>(smem + SM_VEL);
-    float* s_acc = reinterpret_cast<float*>(smem + SM_ACC);
-    float* s_pay = reinterpret_cast<float*>(smem + SM_PAY);
-    int* s_bin_cnt = reinterpret_cast<int*>(smem + SM_BINCNT);
-    int* s_bin_start = reinterpret_cast<int*>(smem + SM_BINSTART);
-    unsigned short* s_binlist = reinterpret_cast<unsigned short*>(smem + SM_BINLIST);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + SM_MISC);
-    int* s_nbr_self = reinterpret_cast<int*>(smem + SM_MISC + 8);
-    int* s_nbr_prev = reinterpret_cast<int*>(smem + SM_MISC + 40);
-    int* s_nnz = reinterpret_cast<int*>(smem + SM_MISC + 72);
-    unsigned* s_dtmin = reinterpret_cast<unsigned*>(smem + SM_MISC + 76);
-    uint32_t* s_halo = reinterpret_cast<uint32_t*>(smem + SM_HALO);
-
-    const int tid = threadIdx.x;
-    const DispatchEntry ent = P.dispatch[blockIdx.x];
-    if (tid < 8) {
-        const int nid = P.nbr_self[ent.block * 8 + tid];
-        s_nbr_self[tid] = nid;
-        s_nbr_prev[tid] = P.nbr_prev[ent.block * 8 + tid];
-        // multi-GPU: is the octant's block shared with a peer?  Fetched here by 8 threads in parallel, long before the flush needs
-        // it (a serial chain of 8 L2 loads by thread 0 at the very end kept every CTA's slot busy for ~2.5 us)
-        s_halo[tid] = (P.world > 1 && nid >= 0) ? P.blk_halo[nid] : 0u;
-    }
-    if (tid == 0) { mbar_init(s_bar, 1); *s_dtmin = SPK_DT_RAW_NONE; }
-    for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64; i += G2P2G_THREADS) s_acc[i] = 0.f;
-    if (MODE == 1 && tid < 224) s_bin_cnt[tid] = 0;
-    __syncthreads();
-    // ---- stage 0: velocity tile of the 2x2x2 blocks (transfer_global_blocks_to_shared_memory, g2p2g.rs:353-474)
-    if (tid == 0) {
-        uint32_t bytes = 0;
-        for (int o = 0; o < 8; ++o) bytes += s_nbr_prev[o] >= 0 ? 1024u : 0u;
-        fence_proxy_async();
-        mbar_expect_tx(s_bar, bytes);
-        for (int o = 0; o < 8; ++o)
-            if (s_nbr_prev[o] >= 0) tma_load_1d(&s_vel[o * 64], P.prev_vel + (size_t)s_nbr_prev[o] * 64, 1024u, s_bar);
-    }
-    for (int i = tid; i < SPK_TILE_CELLS; i += G2P2G_THREADS)
-        if (s_nbr_prev[i >> 6] < 0) s_vel[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    const float h = P.h, inv_h = P.inv_h, dt = P.dt;
-    const float inv_d = 4.f / (h * h);
-    const bool has_particle = (uint32_t)tid < ent.count;
-
-    // ---- stage 1: one particle per thread ------------------------------------------------------------------------
-    ParticleState p;
-    float vel[3] = {0.f, 0.f, 0.f};
-    Mat3 G = mat_zero();
-    Mat3 stress = mat_zero();
-    bool do_p2g = false;
-    int tcell[3] = {1, 1, 1};
-    float cell_before[3] = {0.f, 0.f, 0.f};
-    float ref[3], w[3][3];
-    if (has_particle) {
-        const uint32_t si = P.perm[ent.first + tid];
-        const float4 r0 = P.src.a0[si], r1 = P.src.a1[si], r2 = P.src.a2[si], r3 = P.src.a3[si], r4 = P.src.a4[si], r5 = P.src.a5[si];
-        p.x[0] = r0.x; p.x[1] = r0.y; p.x[2] = r0.z; p.flags = __float_as_uint(r0.w);
-        p.F.m[0] = r1.x; p.F.m[1] = r1.y; p.F.m[2] = r1.z; p.F.m[3] = r1.w;
-        p.F.m[4] = r2.x; p.F.m[5] = r2.y; p.F.m[6] = r2.z; p.F.m[7] = r2.w;
-        p.F.m[8] = r3.x; p.jp = r3.y; p.mass = r3.z; p.volume0 = r3.w;
-        p.phase = r4.x; p.psi_pos = r4.y; p.elastic_hardening = r4.z; p.plastic_hardening = r4.w;
-        p.log_vol_gain = r5.x; p.nacc_alpha = r5.y; p.orig_id = __float_as_uint(r5.z);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float q = roundf(spk_div_h(p.x[a], h, inv_h));
-            cell_before[a] = q;
-            ref[a] = (q - 1.f) * h - p.x[a];               // dir_to_associated_grid_node, particle.rs:37-47
-            quad_weights(spk_div_h(-ref[a], h, inv_h), w[a]);
-            const int assoc_cell = (q != q) ? -2 : (int)__float2ll_rz(q) - 2;
-            tcell[a] = (assoc_cell & 3) + 1;                // associated_cell_index_in_block_off_by_two, particle.rs:28-35
-        }
-    }
-    mbar_wait(s_bar, 0);
-    __syncthreads();
-
-    if (has_particle) {
-        const DevModel& model = P.models[p.flags >> SPK_F_MODEL_SHIFT];
-        // ---- G2P (particle_g2p2g, g2p2g.rs:192-245), separable accumulation: rows along x, then planes, then volume.
-        //   V = sum w v,  G[:,a] = inv_d * sum w dpt_a v   with w = wx wy wz and dpt = ref + s h
-        {
-            float V[3] = {0.f, 0.f, 0.f}, Gx[3] = {0.f, 0.f, 0.f}, Gy[3] = {0.f, 0.f, 0.f}, Gz[3] = {0.f, 0.f, 0.f};
-            const float wpx[3] = {w[0][0] * ref[0], w[0][1] * (ref[0] + h), w[0][2] * (ref[0] + 2.f * h)};
-#pragma unroll
-            for (int dz = 0; dz < 3; ++dz) {
-                const int iz = cell_part(tcell[2] + dz, 2) | (oct_part(tcell[2] + dz, 2) << 6);
-                float P0[3] = {0.f, 0.f, 0.f}, P1[3] = {0.f, 0.f, 0.f}, P2[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const int iy = iz | cell_part(tcell[1] + dy, 1) | (oct_part(tcell[1] + dy, 1) << 6);
-                    float R0[3] = {0.f, 0.f, 0.f}, R1[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const float4 c = s_vel[iy | cell_part(tcell[0] + dx, 0) | (oct_part(tcell[0] + dx, 0) << 6)];
-                        R0[0] += w[0][dx] * c.x; R0[1] += w[0][dx] * c.y; R0[2] += w[0][dx] * c.z;
-                        R1[0] += wpx[dx] * c.x; R1[1] += wpx[dx] * c.y; R1[2] += wpx[dx] * c.z;
-                    }
-                    const float wy = w[1][dy], wpy = wy * (ref[1] + (float)dy * h);
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) { P0[a] += wy * R0[a]; P1[a] += wy * R1[a]; P2[a] += wpy * R0[a]; }
-                }
-                const float wz = w[2][dz], wpz = wz * (ref[2] + (float)dz * h);
-#pragma unroll
-                for (int a = 0; a < 3; ++a) { V[a] += wz * P0[a]; Gx[a] += wz * P1[a]; Gy[a] += wz * P2[a]; Gz[a] += wpz * P0[a]; }
-            }
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                vel[a] = V[a];
-                M_(G, a, 0) = Gx[a] * inv_d; M_(G, a, 1) = Gy[a] * inv_d; M_(G, a, 2) = Gz[a] * inv_d;
-            }
-        }
-        const float div = M_(G, 0, 0) + M_(G, 1, 1) + M_(G, 2, 2); // velocity_gradient_det == trace of the affine matrix
-
-        // ---- particle update (particle_updater.rs:73-236)
-        const bool is_fluid = model_is_fluid(model);
-        if (p.flags & SPK_F_KINEMATIC) {
-            const float4 kv = P.cold[p.orig_id];
-            vel[0] = kv.x; vel[1] = kv.y; vel[2] = kv.z;
-        }
-        if (fabsf(vel[0]) * dt >= h || fabsf(vel[1]) * dt >= h || fabsf(vel[2]) * dt >= h) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) vel[a] = signum_f(vel[a]) * h / dt;
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) p.x[a] += vel[a] * dt;
-        if (!is_fluid) {
-            Mat3 Gdt;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Gdt.m[i] = G.m[i] * dt;
-            const Mat3 dF = mat_mul(Gdt, p.F);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) p.F.m[i] += dF.m[i];
-        } else {
-            p.F.m[0] += (div * dt) * p.F.m[0];
-        }
-        Svd3 svd;
-        if (model_needs_svd(model)) {
-            svd = svd3(p.F);
-            plastic_update(model, p, svd);
-        }
-        if (p.flags & SPK_F_STATIC) {
-            vel[0] = vel[1] = vel[2] = 0.f;
-            G = mat_zero();
-        }
-        const float j = mat_det(p.F);
-        const float density_def_grad = (p.mass / p.volume0) / j;
-        do_p2g = true;
-        if (density_def_grad == 0.f || (p.flags & SPK_F_FAILED) || (!is_fluid && fabsf(p.F.m[0]) > 1.0e4f)) {
-            p.flags |= SPK_F_FAILED;
-            p.F = mat_identity();
-            do_p2g = false;
-        }
-        if (do_p2g) {
-            // pos energy (gpu_constitutive_model.rs:27-48)
-            float energy = 0.f;
-            if (model.ctag == SPK_CONSTITUTIVE_COROTATED) { // elasticity_corotated_linear.rs:104-118
-                const float a0 = fmaxf(svd.s[0] - 1.f, 0.f), a1 = fmaxf(svd.s[1] - 1.f, 0.f), a2 = fmaxf(svd.s[2] - 1.f, 0.f);
-                const float pos_dev = model.c[2] * p.elastic_hardening * (a0 * a0 + a1 * a1 + a2 * a2);
-                const float sph = model.c[1] * p.elastic_hardening / 2.f * (j - 1.f) * (j - 1.f);
-                energy = j < 1.f ? pos_dev : pos_dev + sph;
-            } else if (model.ctag == SPK_CONSTITUTIVE_NEO_HOOKEAN) { // elasticity_neo_hookean.rs:117-141
-                const float pc = (1.f - 0.001f) * p.phase * p.phase + 0.001f;
-                const float hard = p.elastic_hardening;
-                const float kk = 2.f / 3.f * model.c[2] * hard + model.c[1] * hard;
-                float tr = 0.f;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) tr += p.F.m[i] * p.F.m[i];
-                const float dev = hard * model.c[2] / 2.f * (tr * powf(j, -2.f / 3.f) - 3.f);
-                const float vol = kk / 2.f * ((j * j - 1.f) / 2.f - logf(j));
-                energy = j < 1.f ? dev * pc : (dev + vol) * p.phase;
-            }
-            p.psi_pos = fmaxf(p.psi_pos, energy);
-            // stress (gpu_constitutive_model.rs:50-86); with a failure model the reference evaluates it twice (before/after
-            // the phase change, particle_updater.rs:185-235)
-            for (int pass = (model.ftag == SPK_FAILURE_MAXIMUM_STRESS ? 0 : 1); pass < 2; ++pass) {
-                if (model.ctag == SPK_CONSTITUTIVE_COROTATED) stress = corotated_stress(model, p.phase, p.elastic_hardening, p.F, svd, j);
-                else if (model.ctag == SPK_CONSTITUTIVE_NEO_HOOKEAN) stress = neo_hookean_stress(model, p.phase, p.elastic_hardening, p.F, j);
-                else if (model.ctag == SPK_CONSTITUTIVE_MONAGHAN) { // eos_monaghan_sph.rs:44-63, quirk 7
-                    const float density_fluid = (p.mass / p.volume0) / p.F.m[0];
-                    const float pr = -monaghan_pressure(model, p.mass, p.volume0, density_fluid) * p.jp;
-                    stress = mat_zero();
-                    stress.m[0] = pr; stress.m[4] = pr; stress.m[8] = pr;
-                    if (model.c[2] != 0.f) {
-                        Mat3 sr;
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) M_(sr, r, c) = (M_(G, r, c) + M_(G, c, r)) * 0.5f;
-                        const float sph = (sr.m[0] + sr.m[4] + sr.m[8]) / 3.f;
-                        sr.m[0] -= sph; sr.m[4] -= sph; sr.m[8] -= sph;
-                        const float kv = 2.f * model.c[2] * p.jp;
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) stress.m[i] += kv * sr.m[i];
-                    }
-                }
-                if (pass == 0) { // failure_maximum_stress.rs:20-28
-                    bool finite = true;
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) finite = finite && isfinite(stress.m[i]);
-                    if (finite) {
-                        float mn, mx;
-                        sym_eig_minmax(stress, mn, mx);
-                        if (mx > model.f[0] || (mx - mn) / 2.f > model.f[1]) p.phase = 0.f;
-                    }
-                }
-            }
-        }
-    }
-
-    // ---- fused K15 (timestep.rs:38-113): un-clamped dt candidate of this particle for the NEXT substep; the clamps and the
-    // fixed-point conversion are monotone, so they are applied once to the reduced value (spk_stage_estimate_dt)
-    {
-        unsigned cand_bits = SPK_DT_RAW_NONE;
-        if (has_particle && !(p.flags & SPK_F_FAILED)) {
-            const DevModel& model = P.models[p.flags >> SPK_F_MODEL_SHIFT];
-            const float cand = particle_dt_candidate(model, h, p.mass, p.volume0, p.F.m[0], p.elastic_hardening, vel[0], vel[1], vel[2]);
-            cand_bits = __float_as_uint(cand != cand ? 1.0e30f : fminf(fmaxf(cand, 0.f), 1.0e30f)); // NaN imposes no bound (Rust f32::min ignores NaN)
-        }
-        cand_bits = __reduce_min_sync(0xffffffffu, cand_bits);
-        if ((tid & 31) == 0 && cand_bits < SPK_DT_RAW_NONE) atomicMin(s_dtmin, cand_bits);
-    }
-
-    // ---- P2G preparation with the UPDATED position (g2p2g.rs:280-309)
-    float ref2[3], w2[3][3];
-    int t2[3] = {0, 0, 0};
-    Mat3 A = mat_zero(); // affine = mass * G - (volume0 * inv_d * dt) * stress
-    float mom[3] = {0.f, 0.f, 0.f}, psi_mass = 0.f, psi_mom = 0.f;
-    if (has_particle && do_p2g) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float q = roundf(spk_div_h(p.x[a], h, inv_h));
-            ref2[a] = (q - 1.f) * h - p.x[a];
-            quad_weights(spk_div_h(-ref2[a], h, inv_h), w2[a]);
-            const float mvf = q - cell_before[a];
-            const int mv = (mvf != mvf) ? 0 : (int)__float2ll_rz(mvf);
-            t2[a] = tcell[a] + mv; // in [0, 5] after the velocity clamp
-            do_p2g = do_p2g && t2[a] >= 0 && t2[a] <= 5;
-        }
-        const float ks = p.volume0 * inv_d * dt;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) A.m[i] = p.mass * G.m[i] - ks * stress.m[i];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) mom[a] = p.mass * vel[a];
-        psi_mass = (p.phase > 0.f && !(p.flags & SPK_F_FAILED)) ? p.mass : 0.f;
-        psi_mom = psi_mass * p.psi_pos;
-    }
-
-    uint32_t out_slot = tid; // slot inside the dispatch entry's range of the next buffer
-    if (MODE == 1) {
-        // ---- counting sort of the CTA's particles by stencil-base cell (bin 216 = particles without P2G)
-        const int bin = (has_particle && do_p2g) ? (t2[0] + 6 * t2[1] + 36 * t2[2]) : NBINS;
-        int rank = 0;
-        if (has_particle) rank = atomicAdd(&s_bin_cnt[bin], 1);
-        __syncthreads();
-        if (tid < 32) { // warp 0: exclusive scan of 217 counters (7 per lane) + list of the occupied cell bins
-            int c[7], sum = 0, nz = 0;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) { c[k] = s_bin_cnt[tid * 7 + k]; sum += c[k]; nz += (c[k] != 0 && tid * 7 + k < NBINS) ? 1 : 0; }
-            int inc = sum, inz = nz;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, inc, d), oz = __shfl_up_sync(0xffffffffu, inz, d);
-                if (tid >= d) { inc += o; inz += oz; }
-            }
-            int run = inc - sum, runz = inz - nz;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                s_bin_start[tid * 7 + k] = run;
-                run += c[k];
-                if (c[k] != 0 && tid * 7 + k < NBINS) s_binlist[runz++] = (unsigned short)(tid * 7 + k);
-            }
-            if (tid == 31) *s_nnz = inz;
-        }
-        __syncthreads();
-        out_slot = (uint32_t)(s_bin_start[bin] + rank);
-    }
-
-    // ---- store the particle into the next buffer (coalesced up to the in-CTA cell sort) -----------------------------
-    if (has_particle) {
-        const uint32_t di = ent.first + out_slot;
-        P.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
-        P.dst.a1[di] = make_float4(p.F.m[0], p.F.m[1], p.F.m[2], p.F.m[3]);
-        P.dst.a2[di] = make_float4(p.F.m[4], p.F.m[5], p.F.m[6], p.F.m[7]);
-        P.dst.a3[di] = make_float4(p.F.m[8], p.jp, p.mass, p.volume0);
-        P.dst.a4[di] = make_float4(p.phase, p.psi_pos, p.elastic_hardening, p.plastic_hardening);
-        P.dst.a5[di] = make_float4(p.log_vol_gain, p.nacc_alpha, __uint_as_float(p.orig_id), 0.f);
-        P.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
-    }
-
-    if (MODE == 0) {
-        // ---- P2G, one particle per thread, 27 x 6 shared float atomics (g2p2g.rs:311-349 without the spin lock)
-        if (has_particle && do_p2g) {
-#pragma unroll
-            for (int dz = 0; dz < 3; ++dz) {
-                const int bz = cell_part(t2[2] + dz, 2) + oct_part(t2[2] + dz, 2) * 384;
-                const float pz = ref2[2] + (float)dz * h;
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const int by = bz + cell_part(t2[1] + dy, 1) + oct_part(t2[1] + dy, 1) * 384;
-                    const float py = ref2[1] + (float)dy * h;
-                    const float wyz = w2[1][dy] * w2[2][dz];
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int base = by + cell_part(t2[0] + dx, 0) + oct_part(t2[0] + dx, 0) * 384;
-                        const float px = ref2[0] + (float)dx * h;
-                        const float wt = w2[0][dx] * wyz;
-                        float* a = &s_acc[base];
-                        atomicAdd(a + 0 * 64, wt * p.mass);
-                        atomicAdd(a + 1 * 64, wt * (M_(A, 0, 0) * px + M_(A, 0, 1) * py + M_(A, 0, 2) * pz + mom[0]));
-                        atomicAdd(a + 2 * 64, wt * (M_(A, 1, 0) * px + M_(A, 1, 1) * py + M_(A, 1, 2) * pz + mom[1]));
-                        atomicAdd(a + 3 * 64, wt * (M_(A, 2, 0) * px + M_(A, 2, 1) * py + M_(A, 2, 2) * pz + mom[2]));
-                        if (psi_mass != 0.f) {
-                            atomicAdd(a + 4 * 64, wt * psi_mom);
-                            atomicAdd(a + 5 * 64, wt * psi_mass);
-                        }
-                    }
-                }
-            }
-        }
-    } else {
-        // ---- stage the payload at the particle's cell-sorted slot:
-        //   q0 = {m, c.xyz}  c = A ref2 + mom          q1..q3 = {h A[:,k], (psi_mass, psi_mom, 0)}
-        //   q4 = {wx0, wx1, wx2, 0}   q5 = {wy0, wy1, wy2, wz0}   q6 = {wz1, wz2, 0, 0}
-        if (has_particle && do_p2g) {
-            float4* q = reinterpret_cast<float4*>(s_pay + (size_t)out_slot * PAY_FLOATS);
-            const float cx = M_(A, 0, 0) * ref2[0] + M_(A, 0, 1) * ref2[1] + M_(A, 0, 2) * ref2[2] + mom[0];
-            const float cy = M_(A, 1, 0) * ref2[0] + M_(A, 1, 1) * ref2[1] + M_(A, 1, 2) * ref2[2] + mom[1];
-            const float cz = M_(A, 2, 0) * ref2[0] + M_(A, 2, 1) * ref2[1] + M_(A, 2, 2) * ref2[2] + mom[2];
-            q[0] = make_float4(p.mass, cx, cy, cz);
-            q[1] = make_float4(h * M_(A, 0, 0), h * M_(A, 1, 0), h * M_(A, 2, 0), psi_mass);
-            q[2] = make_float4(h * M_(A, 0, 1), h * M_(A, 1, 1), h * M_(A, 2, 1), psi_mom);
-            q[3] = make_float4(h * M_(A, 0, 2), h * M_(A, 1, 2), h * M_(A, 2, 2), 0.f);
-            q[4] = make_float4(w2[0][0], w2[0][1], w2[0][2], 0.f);
-            q[5] = make_float4(w2[1][0], w2[1][1], w2[1][2], w2[2][0]);
-            q[6] = make_float4(w2[2][1], w2[2][2], 0.f, 0.f);
-        }
-        __syncthreads();
-        // ---- stage 2: 9-lane groups, lane = stencil column (sy, sz), 3 nodes (sx = 0..2) per lane in registers
-        const int lane = tid & 31, warp = tid >> 5;
-        const int grp = lane / 9, l9 = lane - grp * 9;
-        const int sy = l9 % 3, sz = l9 / 3;
-        const float fsy = (float)sy, fsz = (float)sz;
-        const int nnz = *s_nnz;
-        if (grp < 3) {
-            for (int e = warp * 3 + grp; e < nnz; e += (G2P2G_THREADS / 32) * 3) {
-                const int bin = s_binlist[e];
-                const int start = s_bin_start[bin], cnt = s_bin_cnt[bin];
-                float aM[3] = {0.f, 0.f, 0.f}, aX[3] = {0.f, 0.f, 0.f}, aY[3] = {0.f, 0.f, 0.f}, aZ[3] = {0.f, 0.f, 0.f}, aPm[3] = {0.f, 0.f, 0.f},
-                      aPp[3] = {0.f, 0.f, 0.f};
-                for (int i = 0; i < cnt; ++i) {
-                    const float* pay = s_pay + (size_t)(start + i) * PAY_FLOATS;
-                    const float4 q0 = *reinterpret_cast<const float4*>(pay), q1 = *reinterpret_cast<const float4*>(pay + 4),
-                                 q2 = *reinterpret_cast<const float4*>(pay + 8), q3 = *reinterpret_cast<const float4*>(pay + 12),
-                                 q4 = *reinterpret_cast<const float4*>(pay + 16);
-                    const float wyz = pay[20 + sy] * pay[23 + sz];
-                    // node momentum contribution at sx = 0: c + sy * hA[:,1] + sz * hA[:,2]
-                    float bx = q0.y + fsy * q2.x + fsz * q3.x, by = q0.z + fsy * q2.y + fsz * q3.y, bz = q0.w + fsy * q2.z + fsz * q3.z;
-                    const float wx[3] = {q4.x, q4.y, q4.z};
-#pragma unroll
-                    for (int sx = 0; sx < 3; ++sx) {
-                        const float wt = wx[sx] * wyz;
-                        aM[sx] += wt * q0.x;
-                        aX[sx] += wt * bx; aY[sx] += wt * by; aZ[sx] += wt * bz;
-                        aPm[sx] += wt * q1.w; aPp[sx] += wt * q2.w;
-                        bx += q1.x; by += q1.y; bz += q1.z;
-                    }
-                }
-                // flush the 3 x 6 sums of this (cell, column) into the tile
-                const int bxc = bin % 6, byc = (bin / 6) % 6, bzc = bin / 36;
-                const int byz = cell_part(byc + sy, 1) + oct_part(byc + sy, 1) * 384 + cell_part(bzc + sz, 2) + oct_part(bzc + sz, 2) * 384;
-#pragma unroll
-                for (int sx = 0; sx < 3; ++sx) {
-                    float* a = &s_acc[byz + cell_part(bxc + sx, 0) + oct_part(bxc + sx, 0) * 384];
-                    atomicAdd(a + 0 * 64, aM[sx]);
-                    atomicAdd(a + 1 * 64, aX[sx]);
-                    atomicAdd(a + 2 * 64, aY[sx]);
-                    atomicAdd(a + 3 * 64, aZ[sx]);
-                    if (aPp[sx] != 0.f) atomicAdd(a + 4 * 64, aPp[sx]);
-                    if (aPm[sx] != 0.f) atomicAdd(a + 5 * 64, aPm[sx]);
-                }
-            }
-        }
-    }
-
-    // ---- stage 3: flush the accumulation tile into the next grid (transfer_shared_blocks_to_grid, g2p2g.rs:476-553)
-    fence_proxy_async(); // make the generic-proxy smem writes visible to the async (TMA) proxy
-    __syncthreads();
-    if (tid == 0) {
-        for (int o = 0; o < 8; ++o) {
-            const int nid = s_nbr_self[o];
-            if (nid >= 0) tma_reduce_add_f32_1d(P.acc + (size_t)nid * (SPK_ACC_CHANNELS * 64), &s_acc[o * SPK_ACC_CHANNELS * 64], SPK_ACC_CHANNELS * 64 * 4);
-        }
-        // fused halo push (multi-GPU): the same tile chunks are bulk-reduced straight into the peers' halo accumulators,
-        // addressed by the peer's own block ids — the transfer rides on NVLink while other CTAs still compute
-        bool pushed = false;
-        if (P.world > 1) {
-            for (int o = 0; o < 8; ++o) {
-                const int nid = s_nbr_self[o];
-                if (nid < 0 || !(s_halo[o] & 1u)) continue;
-                for (uint32_t r = 0; r < P.world; ++r) {
-                    const int32_t pid = P.peer_ids[(size_t)nid * P.world + r];
-                    if (pid >= 0) {
-                        tma_reduce_add_f32_1d(P.peer_hacc[r] + (size_t)pid * (SPK_ACC_CHANNELS * 64), &s_acc[o * SPK_ACC_CHANNELS * 64], SPK_ACC_CHANNELS * 64 * 4);
-                        pushed = true;
-                    }
-                }
-            }
-        }
-        if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(P.dt_raw_bits, *s_dtmin);
-        if (pushed) { // remote reductions must be complete (not only read out of shared memory) before this CTA retires
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            __threadfence_system();
-        } else {
-            tma_commit_and_wait_read();
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------- dt (K15)
-constexpr int DT_THREADS = 256;
-__device__ __forceinline__ unsigned long long dt_from_sec(float dt) { // GpuTimestepLength::from_sec, gpu_timestep.rs:20-22
-    const float v = dt * 1000000000000.0f;
-    if (v != v) return 0ull;
-    return __float2ull_rz(v); // saturating
-}
-__global__ void __launch_bounds__(DT_THREADS) estimate_dt_kernel(const float4* __restrict__ a0, const float4* __restrict__ a1, const float4* __restrict__ a3,
-                                                                  const float4* __restrict__ a4, const float4* __restrict__ vel, uint32_t n,
-                                                                  const DevModel* __restrict__ models, float h, float min_dt, float max_dt,
-                                                                  DeviceCounters* counters) {
-    unsigned long long best = 0xffffffffffffffffull;
-    for (uint32_t i = blockIdx.x * DT_THREADS + threadIdx.x; i < n; i += gridDim.x * DT_THREADS) {
-        const uint32_t flags = __float_as_uint(a0[i].w);
-        if (flags & SPK_F_FAILED) continue; // timestep.rs:72-74
-        const DevModel& m = models[flags >> SPK_F_MODEL_SHIFT];
-        const float4 r3 = a3[i], r4 = a4[i], v = vel[i];
-        const float f00 = a1[i].x;
-        float dt = max_dt;
-        dt = fminf(dt, particle_dt_candidate(m, h, r3.z, r3.w, f00, r4.z, v.x, v.y, v.z));
-        if (dt < min_dt && max_dt > min_dt) dt = min_dt; // timestep.rs:107-109
-        const unsigned long long c = dt_from_sec(dt);
-        best = c < best ? c : best;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
-        best = o < best ? o : best;
-    }
-    __shared__ unsigned long long s_best[DT_THREADS / 32];
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int w = 1; w < DT_THREADS / 32; ++w) best = s_best[w] < best ? s_best[w] : best;
-        if (best != 0xffffffffffffffffull) atomicMin(&counters->dt_acc, best); // one atomic per CTA (the reference: one per particle)
-    }
-}
-
-} // namespace
-
-cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) {
-    GridBuffers& next = c->grid[1 - c->gcur];
-    GridBuffers& prev = c->grid[c->gcur];
-    const uint32_t nd = c->h_counters->ndispatch;
-    if (nd == 0) return cudaSuccess; // never launch with 0 CTAs (cuda_mpm_pipeline.rs:485-486)
-    G2P2GParams P;
-    P.src = c->pb[c->cur];
-    P.dst = c->pb[1 - c->cur];
-    P.vel_out = c->vel;
-    P.cold = c->cold;
-    P.perm = c->perm;
-    P.dispatch = c->dispatch;
-    P.models = c->models;
-    P.nbr_self = next.nbr_self;
-    P.nbr_prev = next.nbr_prev;
-    P.acc = next.acc;
-    P.prev_vel = prev.vel;
-    P.h = c->cell_width;
-    P.inv_h = 1.0f / c->cell_width;
-    P.dt = dt;
-    P.ndispatch = nd;
-    P.dt_raw_bits = &c->d_counters->dt_raw_bits;
-    P.world = (c->dist.world > 1 && c->dist_fused_push) ? c->dist.world : 0;
-    P.blk_halo = next.blk_halo;
-    P.peer_ids = c->dist_peer_ids;
-    P.peer_hacc = c->dist_push_ptrs;
-    { cudaError_t e = cudaMemsetAsync(&c->d_counters->dt_raw_bits, 0x7f, 4, c->stream); if (e != cudaSuccess) return e; }
-    if (!c->g2p2g_configured) { // a function attribute is per device: once per context, not once per process
-        cudaError_t e = cudaFuncSetAttribute(g2p2g_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        if (e != cudaSuccess) return e;
-        c->g2p2g_configured = true;
-    }
-    const bool timed = c->kev_on && c->kev_count < 256;
-    if (timed) cudaEventRecord(c->kev[2 * c->kev_count], c->stream);
-    if (c->g2p2g_mode == 0) g2p2g_kernel<0><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
-    else g2p2g_kernel<1><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
-    if (timed) { cudaEventRecord(c->kev[2 * c->kev_count + 1], c->stream); c->kev_count += 1; }
-    c->launches += 1;
-    c->g2p2g_launches += 1;
-    c->cur = 1 - c->cur; // the next buffer now holds the particles, physically in sorted order
-    c->sorted_valid = false;
-    c->dt_cache_valid = true;
-    c->counters_fresh = false;
-    return cudaGetLastError();
-}
-
-cudaError_t spk_launch_estimate_dt(spk_ctx* c, float min_dt, float max_dt) {
-    const uint32_t n = (uint32_t)c->n;
-    if (!n) return cudaSuccess;
-    const ParticleBuffers& pb = c->pb[c->cur];
-    int blocks = (int)((n + DT_THREADS - 1) / DT_THREADS);
-    const int maxb = c->sm_count * 8;
-    if (blocks > maxb) blocks = maxb;
-    *c->h_upload = c->dt_acc_host;
-    { cudaError_t e = cudaMemcpyAsync(&c->d_counters->dt_acc, c->h_upload, 8, cudaMemcpyHostToDevice, c->stream); if (e != cudaSuccess) return e; }
-    c->counters_fresh = false;
-    estimate_dt_kernel<<<blocks, DT_THREADS, 0, c->stream>>>(pb.a0, pb.a1, pb.a3, pb.a4, c->vel, n, c->models, c->cell_width, min_dt, max_dt, c->d_counters);
-    c->launches += 1;
-    return cudaGetLastError();
-}
+cudaError_t spk_launch_estimate_dt(spk_ctx* c, float min_dt, float max_dt) { return spk_launch_estimate_dt_with<DefaultParticleUpdater>(c, min_dt, max_dt); }

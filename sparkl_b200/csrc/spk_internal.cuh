@@ -184,6 +184,8 @@ struct spk_ctx {
     void* dist_mapped[SPK_MAX_RANKS];    // cudaIpcOpenMemHandle results (to close)
     float** dist_push_ptrs;              // [SPK_MAX_RANKS] device array: peer-mapped hacc of every rank's next grid (written by detect)
     int dist_fused_push;                 // 1: g2p2g's flush pushes shared blocks itself (default); 0: separate push kernel (A/B)
+    // custom particle kernels (spk_set_particle_kernels_launcher); all NULL = DefaultCudaParticleKernelsLauncher
+    SpkParticleKernelsLauncher launcher;
     // timing
     cudaEvent_t ev[12];
     cudaEvent_t ev_counters;
