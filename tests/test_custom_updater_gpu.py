@@ -41,6 +41,10 @@ def _launcher(example, models, damping=0.0):
 
 def _scene(custom: bool):
     sc = scenes.jitter(scenes.neo_hookean_block(12, 10, 8), 0.002, seed=4)
+    rng = np.random.Generator(np.random.PCG64(5))  # seeded pre-strain: the constitutive model acts from the first substep on
+    n = len(sc.particles)
+    F = np.tile(np.eye(3, dtype=np.float32), (n, 1, 1)) + rng.uniform(-0.05, 0.05, (n, 3, 3)).astype(np.float32) * np.float32(0.5)
+    sc.particles.volume["deformation_gradient"] = F.transpose(0, 2, 1).reshape(n, 9)
     real = sc.models[0]
     if custom:
         sc.models = [abi.ParticleModel(abi.CustomConstitutiveModel(0))]
@@ -64,7 +68,7 @@ def test_custom_updater_reproduces_the_builtin_model(example):
     a, b = g_cus.read_all(), g_ref.read_all()
     a.status["model_index"] = b.status["model_index"]
     util.assert_particles_close(a, b, sc_ref.cell_width, util.scene_tol(sc_ref, 2e-5 * nsub), "custom updater vs built-in model")
-    assert np.abs(b.volume["deformation_gradient"] - np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)).max() > 1e-4  # the block did deform
+    assert np.abs(b.velocity["vector"] - b.velocity["vector"].mean(axis=0)).max() > 1e-2  # the stress did act (not a rigid free fall)
     assert example.cu_launcher_calls(h, 0) == 2          # timestep_started: once per spk_step
     assert example.cu_launcher_calls(h, 2) == nsub       # launch_g2p2g: once per substep
     assert example.cu_launcher_calls(h, 1) == 1          # estimate: only the first substep (later ones use the candidate fused into g2p2g)
