@@ -108,6 +108,49 @@ impl B200MpmContext {
 }
 impl Drop for B200MpmContext { fn drop(&mut self) { unsafe { spk_ctx_destroy(self.raw); } } }
 
+// ---- custom particle kernels: `CudaParticleKernelsLauncher` (src/cuda/cuda_particle_kernels.rs:7-27) over the C ABI.
+// The trait object is boxed and reached through three `extern "C"` trampolines; the kernels it launches are the user's
+// instantiation of `g2p2g_kernel<MODE, MyUpdater>` (sparkl_b200/csrc/spk_g2p2g_kernel.cuh), compiled by the user's build.rs.
+#[repr(C)]
+pub struct SpkParticleKernelsLauncher {
+    pub user: *mut c_void,
+    pub timestep_started: Option<unsafe extern "C" fn(user: *mut c_void) -> c_int>,
+    pub launch_estimate_particle_timestep_length: Option<unsafe extern "C" fn(user: *mut c_void, ctx: *mut SpkCtx, min_dt: f32, max_dt: f32) -> c_int>,
+    pub launch_g2p2g: Option<unsafe extern "C" fn(user: *mut c_void, ctx: *mut SpkCtx, timestep_length: f32) -> c_int>,
+}
+extern "C" {
+    pub fn spk_set_particle_kernels_launcher(ctx: *mut SpkCtx, launcher: *const SpkParticleKernelsLauncher) -> c_int;
+    pub fn spk_default_launch_estimate_particle_timestep_length(ctx: *mut SpkCtx, min_dt: f32, max_dt: f32) -> c_int;
+    pub fn spk_default_launch_g2p2g(ctx: *mut SpkCtx, timestep_length: f32) -> c_int;
+}
+/// What a custom launcher implements on the Rust side (same three methods as the reference's trait, minus the arguments the
+/// library already owns: grid / block shapes, the halo flag, the solver parameters).
+pub trait B200ParticleKernelsLauncher {
+    fn timestep_started(&mut self) -> Result<(), SpkError> { Ok(()) }
+    fn launch_estimate_particle_timestep_length(&self, ctx: *mut SpkCtx, min_dt: f32, max_dt: f32) -> Result<(), SpkError> {
+        ck(unsafe { spk_default_launch_estimate_particle_timestep_length(ctx, min_dt, max_dt) })
+    }
+    fn launch_g2p2g(&self, ctx: *mut SpkCtx, timestep_length: f32) -> Result<(), SpkError> { ck(unsafe { spk_default_launch_g2p2g(ctx, timestep_length) }) }
+}
+unsafe extern "C" fn tramp_started(user: *mut c_void) -> c_int {
+    (*(user as *mut Box<dyn B200ParticleKernelsLauncher>)).timestep_started().map(|_| 0).unwrap_or_else(|e| e.0)
+}
+unsafe extern "C" fn tramp_estimate(user: *mut c_void, ctx: *mut SpkCtx, min_dt: f32, max_dt: f32) -> c_int {
+    (*(user as *mut Box<dyn B200ParticleKernelsLauncher>)).launch_estimate_particle_timestep_length(ctx, min_dt, max_dt).map(|_| 0).unwrap_or_else(|e| e.0)
+}
+unsafe extern "C" fn tramp_g2p2g(user: *mut c_void, ctx: *mut SpkCtx, dt: f32) -> c_int {
+    (*(user as *mut Box<dyn B200ParticleKernelsLauncher>)).launch_g2p2g(ctx, dt).map(|_| 0).unwrap_or_else(|e| e.0)
+}
+impl B200MpmContext {
+    /// `step_generic(…, custom_launchers)`: the launcher stays registered (and alive: it is leaked into the context) until replaced.
+    pub fn set_particle_kernels_launcher(&mut self, launcher: Box<dyn B200ParticleKernelsLauncher>) -> Result<(), SpkError> {
+        let user = Box::into_raw(Box::new(launcher)) as *mut c_void;
+        let vt = SpkParticleKernelsLauncher { user, timestep_started: Some(tramp_started),
+                                              launch_estimate_particle_timestep_length: Some(tramp_estimate), launch_g2p2g: Some(tramp_g2p2g) };
+        ck(unsafe { spk_set_particle_kernels_launcher(self.raw, &vt) })
+    }
+}
+
 /// Drop-in for `CudaMpmPipeline` (cuda_mpm_pipeline.rs:144-271).
 #[derive(Default)]
 pub struct B200MpmPipeline { pub step_id: u64 }

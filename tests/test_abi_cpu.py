@@ -80,3 +80,26 @@ def test_lame_parameters_f32():
     lam, mu = abi.lame_lambda_mu(1.0e7, 0.2)
     assert mu == np.float32(np.float32(1.0e7) / (np.float32(2.0) * (np.float32(1.0) + np.float32(0.2))))
     assert float(lam) == pytest.approx(1e7 * 0.2 / (1.2 * 0.6), rel=1e-6)
+
+
+def test_custom_kernel_launcher_abi_and_example_build():
+    """the launcher entry points are exported by both libraries, misuse is an SPK_E* code (no GPU needed), the
+    launcher struct is four pointers, and the example that instantiates the library's kernel template with a user updater builds"""
+    import ctypes as C
+    import subprocess
+    from sparkl_b200 import _lib, build
+    for dim in (2, 3):
+        l = _lib.lib(dim)
+        assert l.spk_set_particle_kernels_launcher(None, None) == abi.EINVAL
+        assert l.spk_default_launch_g2p2g(None, C.c_float(0.1)) == abi.EINVAL
+    src = '#include <stdio.h>\n#include "sparkl_abi.h"\nint main(void) { printf("%zu", sizeof(SpkParticleKernelsLauncher)); return 0; }\n'
+    exe = os.path.join(ROOT, "tests", "host", "_launcher_size")
+    subprocess.check_call(["gcc", "-x", "c", "-I" + os.path.join(ROOT, "include"), "-o", exe, "-"], input=src.encode())
+    assert subprocess.check_output([exe]).decode() == "32"
+    os.remove(exe)
+    build.build()
+    ex = C.CDLL(build.EXAMPLE_LIB)
+    for name in ("cu_launcher_create", "cu_launcher_vtable", "cu_launcher_calls", "cu_launcher_destroy"):
+        assert hasattr(ex, name)
+    from tests.host.emu2d import DEVMODEL
+    assert ex.cu_sizeof_devmodel() == DEVMODEL.itemsize
