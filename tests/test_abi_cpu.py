@@ -94,7 +94,7 @@ def test_custom_kernel_launcher_abi_and_example_build():
         assert l.spk_default_launch_g2p2g(None, C.c_float(0.1)) == abi.EINVAL
     src = '#include <stdio.h>\n#include "sparkl_abi.h"\nint main(void) { printf("%zu", sizeof(SpkParticleKernelsLauncher)); return 0; }\n'
     exe = os.path.join(ROOT, "tests", "host", "_launcher_size")
-    subprocess.check_call(["gcc", "-x", "c", "-I" + os.path.join(ROOT, "include"), "-o", exe, "-"], input=src.encode())
+    subprocess.run(["gcc", "-x", "c", "-I" + os.path.join(ROOT, "include"), "-o", exe, "-"], input=src.encode(), check=True)
     assert subprocess.check_output([exe]).decode() == "32"
     os.remove(exe)
     build.build()
