@@ -1368,3 +1368,15 @@ void orc_cuboid_project(const SpkGpuCollider* c, const float* pt, float* out_pt,
 }
 
 } // extern "C"
+
+// unit hook: DefaultParticleUpdater::update_particle_and_compute_kirchhoff_stress on ONE particle (tests/test_device_math3d_cpu.py
+// compares the product's host-compiled updater with it).  Returns 1 when the reference returns Some(..) (P2G happens).
+extern "C" int orc_update_particle(orc_ctx* c, float dt, SpkParticleStatus* st, SpkParticlePosition* pos, SpkParticleVelocity* vel, SpkParticleVolume* vol,
+                                   SpkParticlePhase* ph, SpkParticleData* data, const float* interp_vel, float* vel_grad9, float* stress9) {
+    M3 g, s = m3_zero();
+    std::memcpy(g.m, vel_grad9, 36);
+    const bool ok = update_particle(*c, dt, c->cell_width, 0, *st, *pos, *vel, *vol, *ph, *data, v3(interp_vel[0], interp_vel[1], interp_vel[2]), g, trace(g), s);
+    std::memcpy(vel_grad9, g.m, 36);
+    std::memcpy(stress9, s.m, 36);
+    return ok ? 1 : 0;
+}

@@ -367,6 +367,7 @@ __global__ void grid_export_kernel(GridBuffers g, uint32_t nblocks, SpkGpuGridNo
     out[t] = n;
 }
 
+#ifdef __CUDACC__ // everything below needs the device hash map / launch syntax; the per-node kernels above are also host-compiled by tests/host/
 // ---- halo path (one process per GPU) -----------------------------------------------------------------------------
 __global__ void halo_keys_kernel(GridBuffers g, uint32_t nab, unsigned long long* out, uint32_t capacity) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,8 +407,11 @@ __global__ void __launch_bounds__(64) halo_merge_kernel(GridBuffers g, const uns
     for (int ch = 0; ch < SPK_ACC_CHANNELS; ++ch) atomicAdd(&acc[ch * 64 + threadIdx.x], src[ch * 64 + threadIdx.x]);
 }
 
+#endif // __CUDACC__
+
 } // namespace
 
+#ifdef __CUDACC__
 cudaError_t spk_launch_reset_grid(spk_ctx* c) {
     GridBuffers& next = c->grid[1 - c->gcur];
     const uint32_t nab = next.nab_host;
@@ -469,3 +473,4 @@ cudaError_t spk_launch_halo_merge(spk_ctx* c, const unsigned long long* keys, co
     c->launches += 1;
     return cudaGetLastError();
 }
+#endif // __CUDACC__
