@@ -176,3 +176,108 @@ class NvlinkMpmPipeline:
 
     def close(self):
         self.ctx._call("dist_detach")
+
+
+# ---------------------------------------------------------------------------------------------------- particle migration
+# The reference never moves particles between devices (static ownership); results do not depend on ownership, but
+# the halo does: a slab decomposition only keeps its thin halo while every rank's particles stay inside its slab.  `migrate`
+# re-homes the particles that left: 128-byte records (the six reference structs + a global id) are exchanged point to point
+# (`torch.distributed` send / recv: NCCL over NVLink on the GPU box, gloo in the CPU tests) and the local set is re-uploaded.
+# It is a collective, host-orchestrated slow path meant to run every few frames (a particle moves at most one cell per substep,
+# SURVEY quirk 3, so ownership may lag by a block without harm); a device-side pack + NVLink push is the planned fast path.
+PARTICLE_RECORD = np.dtype([("status", abi.STATUS), ("position", abi.POSITION), ("velocity", abi.VELOCITY), ("volume", abi.VOLUME),
+                            ("phase", abi.PHASE), ("data", abi.DATA), ("gid", "<u4")])
+assert PARTICLE_RECORD.itemsize == 128
+
+
+class SlabPartition:
+    """ownership by block-x coordinate: rank r owns the particles whose block (gpu_grid.rs:271-279) has x in [bounds[r], bounds[r+1])"""
+
+    def __init__(self, bounds):
+        self.bounds = np.asarray(bounds, np.int64)  # world + 1 increasing block-x coordinates; the outer two are open ended
+        assert len(self.bounds) >= 2 and (np.diff(self.bounds) > 0).all()
+
+    @property
+    def world(self):
+        return len(self.bounds) - 1
+
+    @classmethod
+    def uniform(cls, x_min: float, x_max: float, world: int, cell_width: float):
+        """`world` slabs of equal width between the world coordinates x_min and x_max, snapped to block boundaries"""
+        lo, hi = cls.block_x(np.array([x_min, x_max], np.float32), cell_width)
+        edges = np.round(np.linspace(lo, hi + 1, world + 1)).astype(np.int64)
+        for r in range(1, world + 1):
+            edges[r] = max(edges[r], edges[r - 1] + 1)
+        return cls(edges)
+
+    @staticmethod
+    def block_x(x: np.ndarray, cell_width: float) -> np.ndarray:
+        q = np.asarray(x, np.float32) / np.float32(cell_width)
+        cell = np.trunc(q + np.copysign(np.float32(0.5), q)).astype(np.int64)  # Rust f32::round
+        return (cell - 2) // 4
+
+    def owner(self, x: np.ndarray, cell_width: float) -> np.ndarray:
+        bx = self.block_x(x, cell_width)
+        return np.clip(np.searchsorted(self.bounds[1:-1], bx, side="right"), 0, self.world - 1)
+
+
+def pack_records(pc: abi.ParticleComponents, gids: np.ndarray) -> np.ndarray:
+    rec = np.zeros(len(pc), PARTICLE_RECORD)
+    for name in ("status", "position", "velocity", "volume", "phase", "data"):
+        rec[name] = getattr(pc, name)
+    rec["gid"] = gids
+    return rec
+
+
+def unpack_records(rec: np.ndarray):
+    pc = abi.ParticleComponents(len(rec))
+    for name in ("status", "position", "velocity", "volume", "phase", "data"):
+        setattr(pc, name, np.ascontiguousarray(rec[name]))
+    return pc, np.ascontiguousarray(rec["gid"])
+
+
+def migrate(engine, gids: np.ndarray, partition: SlabPartition, dist=None, device=None):
+    """Collective.  Moves every particle of `engine` (a SingleGpuMpmContext, or the oracle in CPU tests) whose block left this
+    rank's slab to the rank that owns it, and re-uploads the local set.  `gids` are the global ids of the local particles (in
+    local particle-id order).  Returns (new_gids, number sent, number received).  Every rank must keep at least one particle when
+    the NVLink path is attached (its device-side barriers need every rank)."""
+    import torch
+    import torch.distributed as tdist
+    dist = dist or tdist
+    device = device if device is not None else torch.device("cpu")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    assert partition.world == world
+    pc = engine.read_all()
+    rec = pack_records(pc, np.asarray(gids, np.uint32))
+    owner = partition.owner(pc.position["point"][:, 0], engine.cell_width)
+    counts = torch.tensor([int((owner == r).sum()) if r != rank else 0 for r in range(world)], dtype=torch.int64, device=device)
+    table = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(table, counts)
+    table = torch.stack(table).cpu().numpy()  # table[src, dst]
+    ops, recv_bufs, send_bufs = [], {}, {}
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if table[rank, peer]:
+            buf = torch.from_numpy(np.ascontiguousarray(rec[owner == peer]).view(np.uint8).copy()).to(device)
+            send_bufs[peer] = buf
+            ops.append(dist.P2POp(dist.isend, buf, peer))
+        if table[peer, rank]:
+            recv_bufs[peer] = torch.empty(int(table[peer, rank]) * PARTICLE_RECORD.itemsize, dtype=torch.uint8, device=device)
+            ops.append(dist.P2POp(dist.irecv, recv_bufs[peer], peer))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    stay = rec[owner == rank]
+    incoming = [recv_bufs[p].cpu().numpy().view(PARTICLE_RECORD) for p in sorted(recv_bufs)]
+    merged = np.concatenate([stay] + incoming) if incoming else stay
+    n_sent, n_recv = int(table[rank].sum()), int(table[:, rank].sum())
+    if table.sum() > 0:
+        # EVERY rank re-uploads as soon as any particle moved anywhere: the peer-memory path requires the same call sequence on
+        # all ranks (a re-upload invalidates the fused dt candidate, and the stand-alone dt kernel that follows ends in a
+        # device-side barrier every rank must reach)
+        new_pc, new_gids = unpack_records(merged)
+        engine.upload(new_pc)
+    else:
+        new_gids = np.asarray(gids, np.uint32)
+    return new_gids, n_sent, n_recv

@@ -24,3 +24,19 @@ def test_two_ranks_peer_memory_path_matches_single_context():
     line = [l for l in out.splitlines() if "multi-gpu check" in l]
     assert line and line[-1].rstrip().endswith("OK"), out[-3000:]
     assert "halo blocks 0," not in line[-1], "the two slabs must share blocks"
+
+
+def test_particle_migration_on_the_peer_memory_path():
+    """north_star's "particle migration over NVLink", functional form: two ranks on the peer-memory halo path, a kinematic block
+    pushed across the slab boundary, `distributed.migrate` after every frame; same positions as the single-context run, nobody
+    lost (scripts/check_migration_gpu.py)"""
+    env = dict(os.environ, SPK_CHECK_ONE_GPU="1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29579", os.path.join(ROOT, "scripts", "check_migration_gpu.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    out = r.stdout + r.stderr
+    if "devices are busy or unavailable" in out or "exclusive" in out.lower():
+        pytest.skip("the GPU is in exclusive-process compute mode: two processes cannot share it")
+    assert r.returncode == 0, out[-3000:]
+    line = [l for l in out.splitlines() if "migration check" in l]
+    assert line and line[-1].rstrip().endswith("OK"), out[-3000:]
