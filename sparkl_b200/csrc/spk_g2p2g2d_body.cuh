@@ -52,33 +52,13 @@ __device__ __forceinline__ void g2p2g2d_load(const ParticleBuffers& src, uint32_
     }
 }
 
-// G2P from the staged velocity tile + DefaultParticleUpdater::update_particle_and_compute_kirchhoff_stress
-__device__ inline void g2p2g2d_update(const float4* s_vel, const DevModel* models, const float4* cold, float h, float dt, Particle2dWork& k) {
-    ParticleState2& p = k.p;
-    float* vel = k.vel;
-    Mat2& G = k.G;
-    const float inv_d = 4.f / (h * h); // Kernel::inv_d
-    const DevModel& model = models[p.flags >> SPK_F_MODEL_SHIFT];
-    // ---- G2P (particle_g2p2g, g2p2g.rs:192-245): V = sum w v, G[:, a] = inv_d * sum w dpt_a v
-    {
-        float V[2] = {0.f, 0.f}, Gx[2] = {0.f, 0.f}, Gy[2] = {0.f, 0.f};
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int iy = cell_part(k.tcell[1] + dy, 1) | (quad_part(k.tcell[1] + dy, 1) << SPK_CELL_SHIFT);
-            const float py = k.ref[1] + (float)dy * h;
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const float4 c = s_vel[iy | cell_part(k.tcell[0] + dx, 0) | (quad_part(k.tcell[0] + dx, 0) << SPK_CELL_SHIFT)];
-                const float wt = k.w[0][dx] * k.w[1][dy];
-                const float px = k.ref[0] + (float)dx * h;
-                V[0] += wt * c.x; V[1] += wt * c.y;
-                Gx[0] += (wt * px) * c.x; Gx[1] += (wt * px) * c.y;
-                Gy[0] += (wt * py) * c.x; Gy[1] += (wt * py) * c.y;
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 2; ++a) { vel[a] = V[a]; M2_(G, a, 0) = Gx[a] * inv_d; M2_(G, a, 1) = Gy[a] * inv_d; }
-    }
+// ---- the particle-updater extension point: see spk_updater.cuh for the contract.  An Updater is a type with
+// these two static device functions; the kernel template of spk_g2p2g2d.cu (`g2p2g2d_kernel<Updater>`) is instantiated with
+// DefaultParticleUpdater2 by the library and can be instantiated with a user's type through spk_launch_g2p2g2d_with<U>.
+struct DefaultParticleUpdater2 {
+    // DefaultParticleUpdater::update_particle_and_compute_kirchhoff_stress, src_kernels/cuda/particle_updater.rs:73-236 (dim2)
+    __device__ __forceinline__ static bool update(const DevModel& model, const float4* __restrict__ cold, float h, float dt, ParticleState2& p, float (&vel)[2],
+                                                  Mat2& G, Mat2& stress, const void* /*user*/) {
     const float div = M2_(G, 0, 0) + M2_(G, 1, 1); // velocity_gradient_det
 
     // ---- particle update (particle_updater.rs:73-236)
@@ -115,12 +95,12 @@ __device__ inline void g2p2g2d_update(const float4* s_vel, const DevModel* model
     }
     const float j = mat2_det(p.F);
     const float density_def_grad = (p.mass / p.volume0) / j;
-    k.do_p2g = true;
+    bool do_p2g = true;
     if (density_def_grad == 0.f || (p.flags & SPK_F_FAILED) || (!is_fluid && fabsf(p.F.m[0]) > 1.0e4f)) {
         p.flags |= SPK_F_FAILED;
         p.F = mat2_identity();
-        k.do_p2g = false;
-        return;
+        do_p2g = false;
+        return do_p2g;
     }
     float energy = 0.f; // pos energy (gpu_constitutive_model.rs:27-48)
     if (model.ctag == SPK_CONSTITUTIVE_COROTATED) { // elasticity_corotated_linear.rs:104-118
@@ -143,7 +123,6 @@ __device__ inline void g2p2g2d_update(const float4* s_vel, const DevModel* model
     // stress (gpu_constitutive_model.rs:50-86); with a failure model it is evaluated before and after the phase change
     // (particle_updater.rs:185-235)
     for (int pass = (model.ftag == SPK_FAILURE_MAXIMUM_STRESS ? 0 : 1); pass < 2; ++pass) {
-        Mat2& stress = k.stress;
         if (model.ctag == SPK_CONSTITUTIVE_COROTATED) stress = corotated_stress2(model, p.phase, p.elastic_hardening, p.F, svd, j);
         else if (model.ctag == SPK_CONSTITUTIVE_NEO_HOOKEAN) stress = neo_hookean_stress2(model, p.phase, p.elastic_hardening, p.F, j);
         else if (model.ctag == SPK_CONSTITUTIVE_MONAGHAN) { // eos_monaghan_sph.rs:44-63
@@ -173,14 +152,52 @@ __device__ inline void g2p2g2d_update(const float4* s_vel, const DevModel* model
             }
         }
     }
+    return do_p2g;
+    }
+    // estimate_particle_timestep_length (particle_updater.rs:47-70) + timestep.rs:74-112, before the clamps
+    __device__ __forceinline__ static float dt_candidate(const DevModel& model, float h, const ParticleState2& p, const float (&vel)[2], const void* /*user*/) {
+        return particle_dt_candidate2(model, h, p.mass, p.volume0, p.F.m[0], p.elastic_hardening, vel[0], vel[1]);
+    }
+};
+
+// G2P from the staged velocity tile + DefaultParticleUpdater::update_particle_and_compute_kirchhoff_stress
+template <class Updater>
+__device__ inline void g2p2g2d_update(const float4* s_vel, const DevModel* models, const float4* cold, float h, float dt, Particle2dWork& k, const void* user) {
+    ParticleState2& p = k.p;
+    float* vel = k.vel;
+    Mat2& G = k.G;
+    const float inv_d = 4.f / (h * h); // Kernel::inv_d
+    const DevModel& model = models[p.flags >> SPK_F_MODEL_SHIFT];
+    // ---- G2P (particle_g2p2g, g2p2g.rs:192-245): V = sum w v, G[:, a] = inv_d * sum w dpt_a v
+    {
+        float V[2] = {0.f, 0.f}, Gx[2] = {0.f, 0.f}, Gy[2] = {0.f, 0.f};
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = cell_part(k.tcell[1] + dy, 1) | (quad_part(k.tcell[1] + dy, 1) << SPK_CELL_SHIFT);
+            const float py = k.ref[1] + (float)dy * h;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4 c = s_vel[iy | cell_part(k.tcell[0] + dx, 0) | (quad_part(k.tcell[0] + dx, 0) << SPK_CELL_SHIFT)];
+                const float wt = k.w[0][dx] * k.w[1][dy];
+                const float px = k.ref[0] + (float)dx * h;
+                V[0] += wt * c.x; V[1] += wt * c.y;
+                Gx[0] += (wt * px) * c.x; Gx[1] += (wt * px) * c.y;
+                Gy[0] += (wt * py) * c.x; Gy[1] += (wt * py) * c.y;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) { vel[a] = V[a]; M2_(G, a, 0) = Gx[a] * inv_d; M2_(G, a, 1) = Gy[a] * inv_d; }
+    }
+    k.do_p2g = Updater::update(model, cold, h, dt, p, k.vel, G, k.stress, user);
 }
 
 // fused K15 (timestep.rs:38-113): un-clamped dt candidate (float bits) of this particle for the NEXT substep
-__device__ __forceinline__ unsigned g2p2g2d_dt_bits(const DevModel* models, float h, const Particle2dWork& k) {
+template <class Updater>
+__device__ __forceinline__ unsigned g2p2g2d_dt_bits(const DevModel* models, float h, const Particle2dWork& k, const void* user) {
     const ParticleState2& p = k.p;
     if (p.flags & SPK_F_FAILED) return SPK_DT_RAW_NONE;
     const DevModel& model = models[p.flags >> SPK_F_MODEL_SHIFT];
-    const float cand = particle_dt_candidate2(model, h, p.mass, p.volume0, p.F.m[0], p.elastic_hardening, k.vel[0], k.vel[1]);
+    const float cand = Updater::dt_candidate(model, h, p, k.vel, user);
     return __float_as_uint(cand != cand ? 1.0e30f : fminf(fmaxf(cand, 0.f), 1.0e30f)); // NaN imposes no bound (Rust f32::min ignores NaN)
 }
 

@@ -66,8 +66,8 @@ void hk_g2p2g(ParticleBuffers src, ParticleBuffers dst, float4* vel_out, const f
         for (uint32_t tid = 0; tid < ent.count; ++tid) {
             Particle2dWork k;
             g2p2g2d_load(src, perm[ent.first + tid], h, inv_h, k);
-            g2p2g2d_update(s_vel.data(), models, cold, h, dt, k);
-            const unsigned bits = g2p2g2d_dt_bits(models, h, k);
+            g2p2g2d_update<DefaultParticleUpdater2>(s_vel.data(), models, cold, h, dt, k, nullptr);
+            const unsigned bits = g2p2g2d_dt_bits<DefaultParticleUpdater2>(models, h, k, nullptr);
             if (bits < *dt_raw_bits) *dt_raw_bits = bits;
             g2p2g2d_store(dst, vel_out, ent.first + tid, k);
             g2p2g2d_scatter(s_acc.data(), h, inv_h, dt, k);
