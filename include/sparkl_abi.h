@@ -148,7 +148,7 @@ typedef struct SpkGpuParticleModel {
 
 /* ---------------------------------------------------------------- colliders
  * GpuCollider, 336 bytes: src_kernels/gpu_collider.rs:203-212 (offsets from the PTX).
- * Scope: Cuboid (tag 0), HeightField (tag 1) and Polyline (tag 3).  TriMesh is a SURVEY §8(f) "next" row -> SPK_EUNSUPPORTED.
+ * Scope: Cuboid (tag 0), HeightField (tag 1), TriMesh (tag 2) and Polyline (tag 3).
  * The reference's HeightField payload is parry's `CudaHeightFieldPtr` (device pointers of ITS CUDA context,
  * src_kernels/gpu_collider.rs:14-18, src/cuda/cuda_collider_set.rs:71-86); here the payload carries a HOST description of
  * the same rapier `HeightField` (heights matrix + scale) and the library owns the device copy. */
@@ -170,6 +170,15 @@ typedef struct SpkGpuCollider {
             uint32_t num_vertices;
             uint8_t flip_interior;
         } polyline;
+        struct {                      /* GpuColliderShape::TriMesh (src_kernels/gpu_collider.rs:19-23,58-68): a rapier `ColliderBuilder::trimesh(vertices,
+                                       * indices)` (no ORIENTED flag, hence no pseudo-normals: a surface, a point is "inside" only when it lies on
+                                       * it; flip_interior inverts that).  The reference's payload is parry's CudaTriMeshPtr (device QBVH); here a
+                                       * HOST description of the same mesh, projected by exhaustive search over the triangles. */
+            const float* vertices;    /* HOST pointer, num_vertices x (x, y, z) */
+            const uint32_t* indices;  /* HOST pointer, num_triangles x 3 vertex indices */
+            uint32_t num_vertices, num_triangles;
+            uint8_t flip_interior;
+        } trimesh;
         uint8_t _bytes[288];
     } shape;
     float rotation[4];    /* unit quaternion, nalgebra coordinate order (i, j, k, w) */

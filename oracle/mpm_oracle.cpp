@@ -267,6 +267,7 @@ struct orc_ctx {
     std::vector<SpkGpuParticleModel> models;
     std::vector<SpkGpuCollider> colliders;
     std::vector<std::vector<float>> collider_data; // owned copies of the heightfield matrices the colliders point to
+    std::vector<std::vector<uint32_t>> collider_indices; // owned copies of the trimesh index lists
     Grid grids[2];
     int curr = 0; // grids[curr] = read-only previous grid, grids[1-curr] = next
     std::vector<SpkDispatchBlock2ActiveBlock> dispatch;
@@ -840,7 +841,32 @@ static bool polyline_project_point(const SpkGpuCollider& c, V3 point, Projection
     out.point = quat_rotate(c.rotation, best.proj) + tr;
     return true;
 }
+// GpuColliderShape::TriMesh, src_kernels/gpu_collider.rs:58-68 with parry3d 0.13's TriMesh::project_point_with_max_dist(.., Real::MAX)
+// restated (the crate is not under /root/reference): the closest point over all triangles — the QBVH only prunes — and, for a mesh
+// without pseudo-normals (rapier's default trimesh flags), is_inside = the closest triangle's answer for solid = false, i.e. the
+// query lies on it.  PARITY: unpinned against the reference's kernels (CudaTriMeshPtr layout not recovered), checked against an
+// independent f64 brute force (tests/test_trimesh_cpu.py).
+static bool trimesh_project_point(const SpkGpuCollider& c, V3 pt, Projection& out) {
+    const auto& tm = c.shape.trimesh;
+    if (tm.num_triangles == 0) return false;
+    float qinv[4] = {-c.rotation[0], -c.rotation[1], -c.rotation[2], c.rotation[3]};
+    V3 tr = v3(c.translation[0], c.translation[1], c.translation[2]);
+    V3 lp = quat_rotate(qinv, pt - tr);
+    auto vertex = [&](uint32_t i) { return v3(tm.vertices[3 * i], tm.vertices[3 * i + 1], tm.vertices[3 * i + 2]); };
+    Real best_sq = FLT_MAX;
+    V3 best = v3(0, 0, 0);
+    for (uint32_t t = 0; t < tm.num_triangles; ++t) {
+        V3 q = triangle_closest_point(lp, vertex(tm.indices[3 * t]), vertex(tm.indices[3 * t + 1]), vertex(tm.indices[3 * t + 2]));
+        Real sq = norm_squared(lp - q);
+        if (sq < best_sq) { best_sq = sq; best = q; }
+    }
+    out.is_inside = best.x == lp.x && best.y == lp.y && best.z == lp.z;
+    if (tm.flip_interior) out.is_inside = !out.is_inside;
+    out.point = quat_rotate(c.rotation, best) + tr;
+    return true;
+}
 static bool collider_project(const SpkGpuCollider& c, V3 pt, Real max_dist, Projection& out) {
+    if (c.shape_tag == SPK_SHAPE_TRIMESH) return trimesh_project_point(c, pt, out);
     if (c.shape_tag == SPK_SHAPE_HEIGHTFIELD) return heightfield_project_point(c, pt, max_dist, out);
     if (c.shape_tag == SPK_SHAPE_POLYLINE) return polyline_project_point(c, pt, out);
     if (c.shape_tag != SPK_SHAPE_CUBOID) return false;
@@ -1003,9 +1029,10 @@ int orc_particles_read(orc_ctx* c, int which, void* dst, size_t n) {
 int orc_models_upload(orc_ctx* c, const SpkGpuParticleModel* models, size_t n) { c->models.assign(models, models + n); return SPK_OK; }
 int orc_colliders_upload(orc_ctx* c, const SpkGpuCollider* cols, size_t n) {
     for (size_t i = 0; i < n; ++i)
-        if (cols[i].shape_tag != SPK_SHAPE_CUBOID && cols[i].shape_tag != SPK_SHAPE_HEIGHTFIELD && cols[i].shape_tag != SPK_SHAPE_POLYLINE) return SPK_EUNSUPPORTED;
+        if (cols[i].shape_tag > SPK_SHAPE_POLYLINE) return SPK_EUNSUPPORTED;
     c->colliders.assign(cols, cols + n);
     c->collider_data.assign(n, {});
+    c->collider_indices.assign(n, {});
     for (size_t i = 0; i < n; ++i)
         if (cols[i].shape_tag == SPK_SHAPE_HEIGHTFIELD) { // keep an owned copy of the heights matrix
             const auto& hf = cols[i].shape.heightfield;
@@ -1017,6 +1044,14 @@ int orc_colliders_upload(orc_ctx* c, const SpkGpuCollider* cols, size_t n) {
             if (pl.num_vertices && !pl.vertices) return SPK_EINVAL;
             c->collider_data[i].assign(pl.vertices, pl.vertices + (size_t)pl.num_vertices * 3);
             c->colliders[i].shape.polyline.vertices = c->collider_data[i].data();
+        } else if (cols[i].shape_tag == SPK_SHAPE_TRIMESH) {
+            const auto& tm = cols[i].shape.trimesh;
+            if (!tm.vertices || !tm.indices || tm.num_vertices == 0 || tm.num_triangles == 0) return SPK_EINVAL;
+            for (size_t k = 0; k < (size_t)tm.num_triangles * 3; ++k) if (tm.indices[k] >= tm.num_vertices) return SPK_EINVAL;
+            c->collider_data[i].assign(tm.vertices, tm.vertices + (size_t)tm.num_vertices * 3);
+            c->collider_indices[i].assign(tm.indices, tm.indices + (size_t)tm.num_triangles * 3);
+            c->colliders[i].shape.trimesh.vertices = c->collider_data[i].data();
+            c->colliders[i].shape.trimesh.indices = c->collider_indices[i].data();
         }
     return SPK_OK;
 }

@@ -334,6 +334,33 @@ class PolylineCollider:
         return bytes(buf)
 
 
+class TriMeshCollider:
+    """A rapier `ColliderBuilder::trimesh(vertices, indices)` collider (default flags: a surface without pseudo-normals) -> 336-byte
+    GpuCollider image with the TriMesh payload of include/sparkl_abi.h (HOST pointers to the n x 3 vertices and the t x 3 indices).
+    Keep the object alive until the upload."""
+
+    def __init__(self, vertices, indices, translation=(0, 0, 0), rotation=(0, 0, 0, 1), friction=0.5, penalty_stiffness=0.0,
+                 grid_boundary_handling=BoundaryHandling.Friction, flip_interior=False):
+        self.vertices = np.ascontiguousarray(np.asarray(vertices, np.float32))
+        self.indices = np.ascontiguousarray(np.asarray(indices, np.uint32))
+        assert self.vertices.ndim == 2 and self.vertices.shape[1] == 3 and self.indices.ndim == 2 and self.indices.shape[1] == 3
+        self.translation, self.rotation = translation, rotation
+        self.friction, self.penalty_stiffness, self.grid_boundary_handling = friction, penalty_stiffness, grid_boundary_handling
+        self.flip_interior = flip_interior
+
+    def to_gpu_collider(self) -> bytes:
+        buf = bytearray(336)
+        np.frombuffer(buf, "<u4", 1, 0)[0] = 2
+        np.frombuffer(buf, "<u8", 2, 8)[:] = [self.vertices.ctypes.data, self.indices.ctypes.data]
+        np.frombuffer(buf, "<u4", 2, 24)[:] = [len(self.vertices), len(self.indices)]
+        np.frombuffer(buf, "u1", 1, 32)[0] = int(self.flip_interior)
+        np.frombuffer(buf, "<f4", 4, 296)[:] = self.rotation
+        np.frombuffer(buf, "<f4", 3, 312)[:] = self.translation
+        np.frombuffer(buf, "<f4", 2, 324)[:] = [self.friction, self.penalty_stiffness]
+        np.frombuffer(buf, "<u4", 1, 332)[0] = self.grid_boundary_handling
+        return bytes(buf)
+
+
 def pack_colliders(colliders) -> np.ndarray:
     out = np.zeros((len(colliders), 336), dtype=np.uint8)
     for i, c in enumerate(colliders):

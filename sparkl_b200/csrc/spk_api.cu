@@ -743,8 +743,18 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
             d.hf_flags = pl.flip_interior ? 2u : 0u;
             data_off[i] = data.size();
             data.insert(data.end(), pl.vertices, pl.vertices + (size_t)pl.num_vertices * 3);
+        } else if (cols[i].shape_tag == SPK_SHAPE_TRIMESH) {
+            const auto& tm = cols[i].shape.trimesh;
+            if (!tm.vertices || !tm.indices || tm.num_vertices == 0 || tm.num_triangles == 0) return SPK_EINVAL;
+            for (size_t k = 0; k < (size_t)tm.num_triangles * 3; ++k)
+                if (tm.indices[k] >= tm.num_vertices) return SPK_EINVAL;
+            d.nrows = tm.num_vertices; d.ncols = tm.num_triangles;
+            d.hf_flags = tm.flip_interior ? 2u : 0u;
+            data_off[i] = data.size();
+            data.insert(data.end(), tm.vertices, tm.vertices + (size_t)tm.num_vertices * 3); // [vertices | indices as raw bits]
+            for (size_t k = 0; k < (size_t)tm.num_triangles * 3; ++k) { float bits; std::memcpy(&bits, &tm.indices[k], 4); data.push_back(bits); }
         } else {
-            return SPK_EUNSUPPORTED; // trimesh: SURVEY §8(f) "next"
+            return SPK_EUNSUPPORTED;
         }
         std::memcpy(d.rot, cols[i].rotation, 16);
         std::memcpy(d.tr, cols[i].translation, 12);
@@ -759,7 +769,7 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
     CK(dev_alloc(c->collider_data, data.size()));
     if (!data.empty()) CK(cudaMemcpy(c->collider_data, data.data(), data.size() * sizeof(float), cudaMemcpyHostToDevice));
     for (size_t i = 0; i < n; ++i)
-        if (dc[i].shape == SPK_SHAPE_HEIGHTFIELD || dc[i].shape == SPK_SHAPE_POLYLINE) dc[i].heights = c->collider_data + data_off[i];
+        if (dc[i].shape == SPK_SHAPE_HEIGHTFIELD || dc[i].shape == SPK_SHAPE_POLYLINE || dc[i].shape == SPK_SHAPE_TRIMESH) dc[i].heights = c->collider_data + data_off[i];
     if (n) CK(cudaMemcpy(c->colliders, dc.data(), n * sizeof(DevCollider), cudaMemcpyHostToDevice));
     c->ncolliders = n;
     // colliders changed: invalidate the per-node projection cache of both grids (the reference uploads colliders once)

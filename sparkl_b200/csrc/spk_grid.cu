@@ -217,8 +217,37 @@ __device__ inline bool polyline_project(const DevCollider& c, Vec3 pt, Vec3& out
     out = Vec3{w.x + c.tr[0], w.y + c.tr[1], w.z + c.tr[2]};
     return true;
 }
+// GpuColliderShape::TriMesh, src_kernels/gpu_collider.rs:58-68: `trimesh.project_point_with_max_dist(position, point, solid, Real::MAX)`
+// (no distance limit), then flip_interior.  parry3d 0.13's TriMesh projection returns the closest point over all triangles (its QBVH
+// only prunes the search); without pseudo-normals (rapier's default trimesh flags) is_inside is the triangle's own answer for
+// solid = false: true only when the query lies on the triangle.  Exhaustive search here: the projection is computed once per node
+// and then carried in the cache (reset_grid_kernel), and collider meshes are small next to the grid.
+__device__ inline bool trimesh_project(const DevCollider& c, Vec3 pt, Vec3& out, bool& inside) {
+    const int nv = (int)c.nrows, nt = (int)c.ncols;
+    if (nt == 0) return false;
+    const float qinv[4] = {-c.rot[0], -c.rot[1], -c.rot[2], c.rot[3]};
+    const Vec3 lp = quat_rotate(qinv, Vec3{pt.x - c.tr[0], pt.y - c.tr[1], pt.z - c.tr[2]});
+    const float* v = c.heights;
+    const uint32_t* idx = reinterpret_cast<const uint32_t*>(c.heights + (size_t)nv * 3);
+    float best_sq = FLT_MAX;
+    Vec3 best{0.f, 0.f, 0.f};
+    for (int t = 0; t < nt; ++t) {
+        const uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
+        const Vec3 a{v[3 * i0], v[3 * i0 + 1], v[3 * i0 + 2]}, b{v[3 * i1], v[3 * i1 + 1], v[3 * i1 + 2]}, cc{v[3 * i2], v[3 * i2 + 1], v[3 * i2 + 2]};
+        const Vec3 q = closest_point_on_triangle(lp, a, b, cc);
+        const Vec3 d = v_sub(lp, q);
+        const float sq = v_dot(d, d);
+        if (sq < best_sq) { best_sq = sq; best = q; }
+    }
+    inside = best.x == lp.x && best.y == lp.y && best.z == lp.z;
+    if (c.hf_flags & 2u) inside = !inside;
+    const Vec3 w = quat_rotate(c.rot, best);
+    out = Vec3{w.x + c.tr[0], w.y + c.tr[1], w.z + c.tr[2]};
+    return true;
+}
 // GpuColliderShape::project_point_with_max_dist, gpu_collider.rs:42-103 (solid = false)
 __device__ __forceinline__ bool collider_project(const DevCollider& c, Vec3 pt, float max_dist, Vec3& out, bool& inside) {
+    if (c.shape == SPK_SHAPE_TRIMESH) return trimesh_project(c, pt, out, inside);
     if (c.shape == SPK_SHAPE_HEIGHTFIELD) return heightfield_project(c, pt, max_dist, out, inside);
     if (c.shape == SPK_SHAPE_POLYLINE) return polyline_project(c, pt, out, inside);
     cuboid_project(c, pt, out, inside);

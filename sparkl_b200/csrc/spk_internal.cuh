@@ -73,7 +73,8 @@ struct DevCollider {
     uint32_t handling;
     uint32_t shape;       // SPK_SHAPE_CUBOID / SPK_SHAPE_HEIGHTFIELD
     uint32_t nrows, ncols; // heightfield: height samples along z / x; polyline: nrows = number of vertices
-    const float* heights; // heightfield: device copy, column-major nrows x ncols; polyline: vertices (x, y, z)
+    const float* heights; // heightfield: device copy, column-major nrows x ncols; polyline: vertices (x, y, z); trimesh: nrows vertices (x, y, z)
+                          // followed by ncols x 3 vertex indices stored as raw u32 bits
     float scale[3];
     uint32_t hf_flags;    // bit0 bellow_heightfield_is_solid, bit1 flip_interior
 };

@@ -43,6 +43,10 @@ def _dev_colliders(colliders):
             d.heights = data.ctypes.data
             for a in range(3):
                 d.scale[a] = np.float32(c.scale[a])
+        elif isinstance(c, abi.TriMeshCollider):
+            data = np.concatenate([c.vertices.ravel(), c.indices.ravel().view(np.float32)]).astype(np.float32)  # [vertices | index bits]
+            keep.append(data)
+            d.shape, d.nrows, d.ncols, d.heights, d.hf_flags = 2, len(c.vertices), len(c.indices), data.ctypes.data, 2 if c.flip_interior else 0
         elif isinstance(c, abi.PolylineCollider):
             data = np.ascontiguousarray(c.vertices, np.float32)
             keep.append(data)
@@ -135,3 +139,23 @@ def test_grid_update_polyline_trough(hk3):
     trough = np.array([[-1.03, 0.31], [-1.03, 6.1], [-1.52, 6.1], [-1.52, -0.53], [3.51, -0.53], [3.51, 6.1], [3.07, 6.1], [3.07, 0.31]], np.float32)
     sc.colliders = [abi.PolylineCollider(trough)]
     _run(hk3, sc, 5)
+
+
+def ramp_mesh(nx=6, nz=5, x0=-1.0, x1=3.0, z0=-1.0, z1=2.0, y_lo=2.05, y_hi=2.9):
+    """a tilted, slightly bumpy surface triangulated on an nx x nz lattice (vertices off the grid nodes)"""
+    xs, zs = np.linspace(x0, x1, nx), np.linspace(z0, z1, nz)
+    verts = np.array([[x, y_lo + (y_hi - y_lo) * (x - x0) / (x1 - x0) + 0.07 * np.sin(3.1 * x + 1.7 * z), z] for x in xs for z in zs], np.float32)
+    tris = []
+    for i in range(nx - 1):
+        for j in range(nz - 1):
+            a, b, c, d = i * nz + j, (i + 1) * nz + j, (i + 1) * nz + j + 1, i * nz + j + 1
+            tris += [[a, b, c], [a, c, d]]
+    return verts, np.array(tris, np.uint32)
+
+
+def test_grid_update_trimesh_ramp(hk3):
+    sc = scenes.jitter(scenes.sand3(8, 4, 6, with_colliders=False, y0=2.4), 0.02, seed=15)
+    verts, tris = ramp_mesh()
+    sc.colliders = [abi.TriMeshCollider(verts, tris, friction=0.4), abi.CuboidCollider((9.0, 0.5, 9.0), (0.0, 1.0, 0.0))]
+    tags = _run(hk3, sc, 6)
+    assert tags[2] > 0

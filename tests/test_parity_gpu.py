@@ -115,14 +115,29 @@ def test_sand_in_a_polyline_trough(oracle):
     _run_frames(g, o, sc, 10, lambda s: RTOL_1 * (1 + 3 * s))
 
 
-def test_unsupported_collider_shapes_are_rejected():
+def test_sand_on_a_trimesh_ramp(oracle):
+    """TriMesh collider (gpu_collider.rs:58-68): a bumpy triangulated ramp over a cuboid floor"""
+    from tests.test_device_grid3d_cpu import ramp_mesh
+    sc = scenes.jitter(scenes.sand3(8, 4, 6, with_colliders=False, y0=2.4), 0.02, seed=15)
+    verts, tris = ramp_mesh()
+    sc.colliders = [abi.TriMeshCollider(verts, tris, friction=0.4), abi.CuboidCollider((9.0, 0.5, 9.0), (0.0, 1.0, 0.0))]
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 10, lambda s: RTOL_1 * (1 + 3 * s))
+
+
+def test_invalid_collider_shapes_are_rejected():
     from sparkl_b200.pipeline import SingleGpuMpmContext
     g = SingleGpuMpmContext(0.2)
     img = np.zeros((1, 336), np.uint8)
-    for tag in (2,):  # TriMesh: SURVEY §8f "next"
-        img[0, 0] = tag
-        rc = g._lib.spk_colliders_upload(g._h, img.ctypes.data, 1)
-        assert rc == abi.EUNSUPPORTED
+    img[0, 0] = 7  # no such GpuColliderShape variant
+    assert g._lib.spk_colliders_upload(g._h, img.ctypes.data, 1) == abi.EUNSUPPORTED
+    img[0, 0] = 2  # TriMesh without vertices / indices
+    assert g._lib.spk_colliders_upload(g._h, img.ctypes.data, 1) == abi.EINVAL
+    from tests.test_device_grid3d_cpu import ramp_mesh
+    verts, tris = ramp_mesh()
+    tris[3, 1] = len(verts)  # vertex index out of range
+    with pytest.raises(abi.SparklError):
+        g.colliders_upload([abi.TriMeshCollider(verts, tris)])
 
 
 def test_cube_through_sand_kinematic(oracle):
