@@ -189,13 +189,20 @@ typedef struct SpkGpuCollider {
 } SpkGpuCollider;
 #else
 /* dim2 GpuCollider (same Rust definition, src_kernels/gpu_collider.rs:203-212, with parry2d shapes and an Isometry2).
- * Cuboid (tag 0) and Polyline (tag 3); HeightField / TriMesh -> SPK_EUNSUPPORTED.  The byte image of the reference's dim2 enum
+ * Cuboid (tag 0), HeightField (tag 1) and Polyline (tag 3); TriMesh does not exist in 2D.  The byte image of the reference's dim2 enum
  * depends on parry2d's CUDA pointer types and was NOT recovered from sparkl2d-kernels.ptx: this layout is this library's own
  * (field order and meaning as in the Rust struct; the polyline payload is a HOST description like the 3D one). */
 typedef struct SpkGpuCollider {
     uint32_t shape_tag; uint32_t _pad0;
     union {
         struct { float half_extents[2]; } cuboid;
+        struct {                      /* parry2d HeightField::new(heights, scale) + GpuColliderShape::HeightField flags (examples2d/basic2.rs:32-41) */
+            const float* heights;     /* HOST pointer, num_heights samples (>= 2); sample i sits at x = (-0.5 + i / (n - 1)) * scale[0], y = heights[i] * scale[1] */
+            uint32_t num_heights;
+            float scale[2];
+            uint8_t bellow_heightfield_is_solid; /* always true in cuda_collider_set.rs:77 */
+            uint8_t flip_interior;
+        } heightfield;
         struct {
             const float* vertices;    /* HOST pointer, num_vertices x (x, y); segment i joins vertex i and (i + 1) % n */
             uint32_t num_vertices;

@@ -672,8 +672,47 @@ static bool polyline_project_point(const SpkGpuCollider& c, V2 point, Projection
     out.point = rot(c.rotation, best.proj) + tr;
     return true;
 }
+// GenericHeightField::project_local_point_with_max_dist over map_elements_in_local_aabb (parry2d 0.13 point_heightfield.rs,
+// heightfield2.rs; restated from the published algorithm, like its 3D sibling in mpm_oracle.cpp), then the inside test of
+// GpuColliderShape::project_point_with_max_dist (src_kernels/gpu_collider.rs:73-99).  Unpinned against the reference's kernels.
+static bool heightfield_project_point(const SpkGpuCollider& c, V2 pt, Real max_dist, Projection& out) {
+    const auto& hf = c.shape.heightfield;
+    V2 tr = v2(c.translation[0], c.translation[1]);
+    V2 lp = rot_inv(c.rotation, pt - tr);
+    const int cells = (int)hf.num_heights - 1;
+    const Real seg = 1.0f / (Real)cells;
+    const Real rminx = (lp.x - max_dist) / hf.scale[0], rmaxx = (lp.x + max_dist) / hf.scale[0];
+    if (rmaxx <= -0.5f || rminx >= 0.5f) return false;
+    auto clampf = [](Real v, Real lo, Real hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    const int min_x = (int)clampf(std::floor((rminx + 0.5f) / seg), 0.0f, (Real)(cells - 1));
+    const int max_x = (int)clampf(std::ceil((rmaxx + 0.5f) / seg), 0.0f, (Real)cells);
+    Real sq_smallest = FLT_MAX;
+    bool found = false;
+    V2 best = v2(0, 0);
+    for (int i = min_x; i < max_x; ++i) {
+        V2 a = v2((-0.5f + seg * (Real)i) * hf.scale[0], hf.heights[i] * hf.scale[1]);
+        V2 b = v2((-0.5f + seg * (Real)(i + 1)) * hf.scale[0], hf.heights[i + 1] * hf.scale[1]);
+        V2 ab = b - a, ap = lp - a;
+        Real ab_ap = dot(ab, ap), sqnab = dot(ab, ab);
+        V2 q = ab_ap <= 0 ? a : (ab_ap >= sqnab ? b : a + ab * (ab_ap / sqnab));
+        Real sq = norm_squared(lp - q);
+        if (sq < sq_smallest) {
+            sq_smallest = sq;
+            if (std::sqrt(sq) <= max_dist) { best = q; found = true; }
+        }
+    }
+    if (!found) return false;
+    if (hf.bellow_heightfield_is_solid) {
+        bool in_footprint = lp.x >= -0.5f * hf.scale[0] && lp.x <= 0.5f * hf.scale[0];
+        out.is_inside = in_footprint && (hf.flip_interior ? lp.y >= best.y : lp.y <= best.y);
+    } else {
+        out.is_inside = best.x == lp.x && best.y == lp.y;
+    }
+    out.point = rot(c.rotation, best) + tr;
+    return true;
+}
 static bool collider_project(const SpkGpuCollider& c, V2 pt, Real max_dist, Projection& out) {
-    (void)max_dist;
+    if (c.shape_tag == SPK_SHAPE_HEIGHTFIELD) return heightfield_project_point(c, pt, max_dist, out);
     if (c.shape_tag == SPK_SHAPE_POLYLINE) return polyline_project_point(c, pt, out);
     if (c.shape_tag != SPK_SHAPE_CUBOID) return false;
     out = cuboid_project_point(c, pt);
@@ -831,11 +870,16 @@ int orc_particles_read(orc_ctx* c, int which, void* dst, size_t n) {
 int orc_models_upload(orc_ctx* c, const SpkGpuParticleModel* models, size_t n) { c->models.assign(models, models + n); return SPK_OK; }
 int orc_colliders_upload(orc_ctx* c, const SpkGpuCollider* cols, size_t n) {
     for (size_t i = 0; i < n; ++i)
-        if (cols[i].shape_tag != SPK_SHAPE_CUBOID && cols[i].shape_tag != SPK_SHAPE_POLYLINE) return SPK_EUNSUPPORTED;
+        if (cols[i].shape_tag != SPK_SHAPE_CUBOID && cols[i].shape_tag != SPK_SHAPE_POLYLINE && cols[i].shape_tag != SPK_SHAPE_HEIGHTFIELD) return SPK_EUNSUPPORTED;
     c->colliders.assign(cols, cols + n);
     c->collider_data.assign(n, {});
     for (size_t i = 0; i < n; ++i)
-        if (cols[i].shape_tag == SPK_SHAPE_POLYLINE) {
+        if (cols[i].shape_tag == SPK_SHAPE_HEIGHTFIELD) {
+            const auto& hf = cols[i].shape.heightfield;
+            if (!hf.heights || hf.num_heights < 2) return SPK_EINVAL;
+            c->collider_data[i].assign(hf.heights, hf.heights + hf.num_heights);
+            c->colliders[i].shape.heightfield.heights = c->collider_data[i].data();
+        } else if (cols[i].shape_tag == SPK_SHAPE_POLYLINE) {
             const auto& pl = cols[i].shape.polyline;
             if (pl.num_vertices && !pl.vertices) return SPK_EINVAL;
             c->collider_data[i].assign(pl.vertices, pl.vertices + (size_t)pl.num_vertices * 2);

@@ -104,6 +104,28 @@ class PolylineCollider(CuboidCollider):
         return bytes(buf)
 
 
+class HeightFieldCollider(CuboidCollider):
+    """A rapier2d `ColliderBuilder::heightfield(heights, scale)` (examples2d/basic2.rs:32-41) -> 72-byte dim2 SpkGpuCollider with a
+    HOST pointer to the height samples; the field spans [-scale.x / 2, scale.x / 2].  Keep the object alive until the upload."""
+
+    def __init__(self, heights, scale, translation=(0, 0), rotation=0.0, friction=0.5, penalty_stiffness=0.0,
+                 grid_boundary_handling=BoundaryHandling.Friction, flip_interior=False):
+        h = np.ascontiguousarray(np.asarray(heights, np.float32))
+        assert h.ndim == 1 and len(h) >= 2
+        super().__init__((0, 0), translation, rotation, friction, penalty_stiffness, grid_boundary_handling)
+        self.heights, self.scale, self.flip_interior = h, tuple(scale), flip_interior
+
+    def to_gpu_collider(self) -> bytes:
+        buf = bytearray(72)
+        np.frombuffer(buf, "<u4", 1, 0)[0] = 1
+        np.frombuffer(buf, "<u8", 1, 8)[0] = self.heights.ctypes.data
+        np.frombuffer(buf, "<u4", 1, 16)[0] = len(self.heights)
+        np.frombuffer(buf, "<f4", 2, 20)[:] = self.scale
+        np.frombuffer(buf, "u1", 2, 28)[:] = [1, int(self.flip_interior)]  # bellow_heightfield_is_solid: cuda_collider_set.rs:77
+        self._tail(buf)
+        return bytes(buf)
+
+
 def pack_colliders(colliders) -> np.ndarray:
     out = np.zeros((len(colliders), 72), dtype=np.uint8)
     for i, c in enumerate(colliders):

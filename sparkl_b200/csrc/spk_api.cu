@@ -720,8 +720,16 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
             d.hf_flags = pl.flip_interior ? 2u : 0u;
             data_off[i] = data.size();
             data.insert(data.end(), pl.vertices, pl.vertices + (size_t)pl.num_vertices * 2);
+        } else if (cols[i].shape_tag == SPK_SHAPE_HEIGHTFIELD) {
+            const auto& hf = cols[i].shape.heightfield;
+            if (!hf.heights || hf.num_heights < 2) return SPK_EINVAL; // HeightField::new asserts > 1 samples
+            d.nrows = hf.num_heights;
+            std::memcpy(d.scale, hf.scale, 8);
+            d.hf_flags = (hf.bellow_heightfield_is_solid ? 1u : 0u) | (hf.flip_interior ? 2u : 0u);
+            data_off[i] = data.size();
+            data.insert(data.end(), hf.heights, hf.heights + hf.num_heights);
         } else {
-            return SPK_EUNSUPPORTED; // heightfield / trimesh are not built in dim2
+            return SPK_EUNSUPPORTED; // a TriMesh is a 3D shape
         }
         std::memcpy(d.rot, cols[i].rotation, 8);
         std::memcpy(d.tr, cols[i].translation, 8);

@@ -133,19 +133,61 @@ __device__ inline bool polyline_project(const DevCollider& c, Vec2 pt, Vec2& out
     out = Vec2{w.x + c.tr[0], w.y + c.tr[1]};
     return true;
 }
-__device__ __forceinline__ bool collider_project(const DevCollider& c, Vec2 pt, Vec2& out, bool& inside) {
+// heightfield projection: parry2d 0.13 `GenericHeightField::project_local_point_with_max_dist` over `map_elements_in_local_aabb`
+// (heightfield2.rs: the segments whose x range meets [p.x - max_dist, p.x + max_dist]), restated; then the inside test of
+// GpuColliderShape::project_point_with_max_dist (src_kernels/gpu_collider.rs:73-99)
+__device__ inline bool heightfield_project(const DevCollider& c, Vec2 pt, float max_dist, Vec2& out, bool& inside) {
+    const Vec2 lp = rot_inv(c.rot, Vec2{pt.x - c.tr[0], pt.y - c.tr[1]});
+    const int cells = (int)c.nrows - 1;
+    const float seg = 1.f / (float)cells;
+    const float rminx = (lp.x - max_dist) / c.scale[0], rmaxx = (lp.x + max_dist) / c.scale[0];
+    if (rmaxx <= -0.5f || rminx >= 0.5f) return false; // outside of the heightfield bounds
+    const int min_x = (int)fminf(fmaxf(floorf((rminx + 0.5f) / seg), 0.f), (float)(cells - 1));
+    const int max_x = (int)fminf(fmaxf(ceilf((rmaxx + 0.5f) / seg), 0.f), (float)cells);
+    float sq_smallest = FLT_MAX;
+    bool found = false;
+    Vec2 best{0.f, 0.f};
+    for (int i = min_x; i < max_x; ++i) {
+        const Vec2 a{(-0.5f + seg * (float)i) * c.scale[0], c.heights[i] * c.scale[1]};
+        const Vec2 b{(-0.5f + seg * (float)(i + 1)) * c.scale[0], c.heights[i + 1] * c.scale[1]};
+        const Vec2 ab{b.x - a.x, b.y - a.y}, ap{lp.x - a.x, lp.y - a.y};
+        const float ab_ap = ab.x * ap.x + ab.y * ap.y, sqnab = ab.x * ab.x + ab.y * ab.y;
+        Vec2 q; // Segment::project_local_point
+        if (ab_ap <= 0.f) q = a;
+        else if (ab_ap >= sqnab) q = b;
+        else { const float u = ab_ap / sqnab; q = Vec2{a.x + ab.x * u, a.y + ab.y * u}; }
+        const float dx = lp.x - q.x, dy = lp.y - q.y;
+        const float sq = dx * dx + dy * dy;
+        if (sq < sq_smallest) {
+            sq_smallest = sq;
+            if (sqrtf(sq) <= max_dist) { best = q; found = true; }
+        }
+    }
+    if (!found) return false;
+    if (c.hf_flags & 1u) { // bellow_heightfield_is_solid: within the x footprint and on the solid side of the surface
+        const bool in_footprint = lp.x >= -0.5f * c.scale[0] && lp.x <= 0.5f * c.scale[0];
+        inside = in_footprint && ((c.hf_flags & 2u) ? lp.y >= best.y : lp.y <= best.y);
+    } else {
+        inside = best.x == lp.x && best.y == lp.y;
+    }
+    const Vec2 w = rot(c.rot, best);
+    out = Vec2{w.x + c.tr[0], w.y + c.tr[1]};
+    return true;
+}
+__device__ __forceinline__ bool collider_project(const DevCollider& c, Vec2 pt, float max_dist, Vec2& out, bool& inside) {
+    if (c.shape == SPK_SHAPE_HEIGHTFIELD) return heightfield_project(c, pt, max_dist, out, inside);
     if (c.shape == SPK_SHAPE_POLYLINE) return polyline_project(c, pt, out, inside);
     cuboid_project(c, pt, out, inside);
     return true;
 }
 // sdf, grid_update.rs:54-71
-__device__ inline bool sdf(const DevCollider* cols, uint32_t ncol, Vec2 q, float& out) {
+__device__ inline bool sdf(const DevCollider* cols, uint32_t ncol, Vec2 q, float max_dist, float& out) {
     bool any = false;
     float best = 0.f;
     for (uint32_t i = 0; i < ncol; ++i) {
         if (cols[i].handling == SPK_BOUNDARY_NONE) continue;
         Vec2 p; bool inside;
-        if (!collider_project(cols[i], q, p, inside)) continue;
+        if (!collider_project(cols[i], q, max_dist, p, inside)) continue;
         const float dx = p.x - q.x, dy = p.y - q.y;
         const float d = sqrtf(dx * dx + dy * dy) * (inside ? -1.f : 1.f);
         if (!any || d < best) { best = d; any = true; }
@@ -187,7 +229,7 @@ __global__ void __launch_bounds__(256) grid_update_kernel(GridBuffers g, uint32_
         for (uint32_t i = 0; i < ncol; ++i) {
             if (cols[i].handling == SPK_BOUNDARY_NONE) continue;
             Vec2 p; bool inside;
-            if (!collider_project(cols[i], pos, p, inside)) continue;
+            if (!collider_project(cols[i], pos, h * 2.f, p, inside)) continue; // max_dist = cell_width * 2, grid_update.rs:118
             const Vec2 dir{pos.x - p.x, pos.y - p.y};
             const float dist = sqrtf(dir.x * dir.x + dir.y * dir.y);
             if (dist < (have ? best_dist : FLT_MAX)) { have = true; best_dist = dist; best_dir = dir; best_inside = inside; best_id = i; }
@@ -206,7 +248,7 @@ __global__ void __launch_bounds__(256) grid_update_kernel(GridBuffers g, uint32_
             Vec2 qp = pos, qn = pos;
             if (a == 0) { qp.x += off; qn.x += -off; } else { qp.y += off; qn.y += -off; }
             float sp, sn;
-            const bool hp = sdf(cols, ncol, qp, sp), hn = sdf(cols, ncol, qn, sn);
+            const bool hp = sdf(cols, ncol, qp, h * 2.f, sp), hn = sdf(cols, ncol, qn, h * 2.f, sn);
             grad[a] = (hp && hn) ? (sp - sn) / h / 0.1f / 2.f : 0.f;
         }
         const float gn = sqrtf(grad[0] * grad[0] + grad[1] * grad[1]);

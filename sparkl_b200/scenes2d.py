@@ -107,6 +107,31 @@ def sand2(ni=40, nj=80, with_colliders=True) -> Scene:
     return Scene("sand2", h, pc, models, cols, gravity=GRAVITY, params=SolverParameters(max_num_substeps=50))
 
 
+def basic2_ground(friction=0.5, handling=BoundaryHandling.Friction):
+    """the ground of examples2d/basic2.rs:32-41: a 41-sample heightfield, heights[i] = -sin(i pi / 40), scale (2, 1), translated by
+    (0.5, 1.5): a trough whose bottom (y = 0.5) is at x = 0.5"""
+    n = 40
+    i = np.arange(n + 1, dtype=np.float32)
+    heights = -np.sin(i * np.float32(np.pi) / np.float32(n)).astype(np.float32)
+    return abi2d.HeightFieldCollider(heights, (2.0, 1.0), translation=(0.5, 1.5), friction=friction, grid_boundary_handling=handling)
+
+
+def basic2(ni=12, nj=24, drop=0.02) -> Scene:
+    """examples2d/basic2.rs:43-72 reduced: a snow column and a sand column (corotated E = 1e5, nu = 0.2; Snow / Drucker-Prager
+    plasticity, h = 1/128, r = h / 4, density 1000) starting `drop` above the reference's heightfield ground"""
+    h = 1.0 / 128.0
+    models = [ParticleModel.with_plasticity(CorotatedLinearElasticity(1.0e5, 0.2), SnowPlasticity()),
+              ParticleModel.with_plasticity(CorotatedLinearElasticity(1.0e5, 0.2), DruckerPragerPlasticity(1.0e5, 0.2))]
+    r = h / 4.0
+    x0 = h * 40.0
+    ground = basic2_ground()
+    y_ground = 1.5 - np.sin((x0 + 0.5) / 2.0 * np.pi)  # height of the trough around x0 (heights are -sin(pi (x + 0.5) / 2) before scaling)
+    snow = rect_particles((x0, y_ground + 0.05 + drop), ni, nj, 0, r, 1000.0)
+    sand = rect_particles((x0 + ni * 2.0 * r + 6 * h, y_ground + 0.05 + drop), ni, nj, 1, r, 1000.0)
+    pc = ParticleComponents.concatenate([snow, sand])
+    return Scene("basic2", h, pc, models, [ground], gravity=GRAVITY, params=SolverParameters(max_num_substeps=50))
+
+
 def model_block2(kind: str, ni=16, nj=16, seed: int = 21) -> Scene:
     """dim2 counterpart of scenes.model_block: a small pre-strained block over a cuboid floor for every constitutive / plastic /
     failure model: corotated | neo_hookean | fluid | sand | nacc | rankine | snow | failure | failure_split"""
@@ -154,4 +179,4 @@ def jitter(scene: Scene, amplitude: float, seed: int = 42) -> Scene:
     return scene
 
 
-SCENES = {"elasticity2": elasticity2, "fluids2": fluids2, "sand2": sand2, "model_block2": model_block2}
+SCENES = {"elasticity2": elasticity2, "fluids2": fluids2, "sand2": sand2, "basic2": basic2, "model_block2": model_block2}

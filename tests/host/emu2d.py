@@ -199,9 +199,14 @@ class Emu2D:
         self._keep = []
         for i, c in enumerate(colliders):
             d = self.cols[i]
-            d.shape = 3 if isinstance(c, abi2d.PolylineCollider) else 0
+            d.shape = 3 if isinstance(c, abi2d.PolylineCollider) else (1 if isinstance(c, abi2d.HeightFieldCollider) else 0)
             if d.shape == 0:
                 d.half_extents[0], d.half_extents[1] = np.float32(c.half_extents[0]), np.float32(c.half_extents[1])
+            elif d.shape == 1:
+                v = np.ascontiguousarray(c.heights, np.float32)
+                self._keep.append(v)
+                d.heights, d.nrows, d.hf_flags = v.ctypes.data, len(v), 1 | (2 if c.flip_interior else 0)
+                d.scale[0], d.scale[1] = np.float32(c.scale[0]), np.float32(c.scale[1])
             else:
                 v = np.ascontiguousarray(c.vertices, np.float32)
                 self._keep.append(v)

@@ -226,6 +226,39 @@ def test_polyline_projection_dim2_inside_outside():
     assert n_checked > 300
 
 
+def test_heightfield_projection_dim2_against_brute_force():
+    """parry2d HeightField (examples2d/basic2.rs ground): closest point on the polyline of samples within max_dist, inside = under
+    the surface and within the x footprint (gpu_collider.rs:73-99)"""
+    rng = np.random.default_rng(16)
+    g = scenes2d.basic2_ground()
+    flipped = abi2d.HeightFieldCollider(g.heights, g.scale, translation=g.translation, flip_interior=True)
+    n = len(g.heights)
+    xs = (-0.5 + np.arange(n) / (n - 1)) * g.scale[0] + g.translation[0]
+    ys = g.heights.astype(np.float64) * g.scale[1] + g.translation[1]
+    pts = np.stack([xs, ys], axis=1)
+    hits = 0
+    for _ in range(400):
+        px = rng.uniform(-0.8, 1.8)
+        p = np.array([px, np.interp(px, xs, ys) + rng.uniform(-0.2, 0.2)])  # around the surface (and beyond both ends of the field)
+        max_dist = 0.08
+        r = ob.collider_project2d(g, p, max_dist)
+        d = min(_seg_dist(p, pts[i], pts[i + 1]) for i in range(n - 1))
+        if d > max_dist * (1 + 1e-4) or p[0] < xs[0] - max_dist or p[0] > xs[-1] + max_dist:
+            assert r is None or abs(d - max_dist) <= 1e-4, (p, d)
+            continue
+        if d > max_dist * (1 - 1e-4):
+            continue
+        assert r is not None, (p, d)
+        proj, inside = r
+        hits += 1
+        assert abs(np.linalg.norm(proj - p) - d) <= 2e-6
+        surface_y = np.interp(p[0], xs, ys)
+        if abs(p[1] - surface_y) > 1e-3 and xs[0] + 1e-3 < p[0] < xs[-1] - 1e-3 and abs(p[1] - proj[1]) > 1e-4:
+            assert inside == bool(p[1] <= proj[1])  # the reference compares with the PROJECTION's y, not the surface height at p.x
+            assert ob.collider_project2d(flipped, p, max_dist)[1] == bool(p[1] >= proj[1])
+    assert hits > 40
+
+
 def _seg_dist(p, a, b):
     ab, ap = b - a, p - a
     u = np.clip(np.dot(ab, ap) / np.dot(ab, ab), 0, 1)
@@ -503,6 +536,10 @@ def test_device_kernels_on_host_clamping_models(gpu_test_bodies, kind):
 def test_device_kernels_on_host_fluid_and_polyline(gpu_test_bodies):
     gpu_test_bodies.test_fluids2_dam_break_lockstep()
     gpu_test_bodies.test_polyline_trough_dim2()
+
+
+def test_device_kernels_on_host_basic2_heightfield_ground(gpu_test_bodies):
+    gpu_test_bodies.test_basic2_on_the_heightfield_ground()
 
 
 def test_device_kernels_on_host_roundtrip_and_kinematic():

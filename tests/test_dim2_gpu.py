@@ -135,6 +135,16 @@ def test_polyline_trough_dim2():
     _run(sc, 8)
 
 
+def test_basic2_on_the_heightfield_ground():
+    """examples2d/basic2.rs: snow and sand columns dropped on the reference's heightfield ground (parry2d HeightField restated:
+    product vs oracle; the columns reach the ground within the compared substeps)"""
+    sc = scenes2d.basic2(drop=0.004)
+    sc.particles.position["point"][:, 1] -= np.float32(0.045)  # start ~1 cell above the surface
+    g, o = _run(sc, 14)
+    tags = np.bincount(o.grid_nodes(0)["projection_status_tag"].ravel().astype(int), minlength=4)
+    assert tags[1] + tags[2] > 0 and tags[3] > 0  # nodes near the surface got a projection, far ones TooFar (max_dist = 2 h)
+
+
 def test_full_step_matches_oracle_dim2():
     """whole frames through spk_step (adaptive substeps, dt fused into g2p2g) against orc_step: same substep count, same
     simulated time, particle state within the multi-substep tolerance"""
@@ -177,8 +187,10 @@ def test_unsupported_dim2_features_fail_loudly():
     from sparkl_b200.pipeline import SingleGpuMpmContext
     g = SingleGpuMpmContext(0.1, dim=2)
     buf = np.zeros((1, 72), np.uint8)
-    buf.view("<u4")[0, 0] = 1  # heightfield
+    buf.view("<u4")[0, 0] = 2  # a TriMesh is a 3D shape
     assert g._lib.spk_colliders_upload(g._h, buf.ctypes.data_as(C.c_void_p), 1) == abi.EUNSUPPORTED
+    buf.view("<u4")[0, 0] = 1  # heightfield without samples
+    assert g._lib.spk_colliders_upload(g._h, buf.ctypes.data_as(C.c_void_p), 1) == abi.EINVAL
     desc = np.zeros(128, np.uint8)
     assert g._lib.spk_dist_export(g._h, desc.ctypes.data_as(C.c_void_p)) == abi.EUNSUPPORTED
 
