@@ -94,7 +94,7 @@ def fluids2(ni=300, nj=300, with_colliders=True) -> Scene:
 
 def sand2(ni=40, nj=80, with_colliders=True) -> Scene:
     """the snow + sand columns of examples2d/basic2.rs:43-72 (corotated E = 1e5, nu = 0.2 with Snow / Drucker-Prager plasticity,
-    h = 1/128, r = h / 4, density 1000) on a cuboid ground (the reference's heightfield ground is not built in dim2)"""
+    h = 1/128, r = h / 4, density 1000) on a flat cuboid ground (`basic2` uses the reference's heightfield ground)"""
     h = 1.0 / 128.0
     models = [ParticleModel.with_plasticity(CorotatedLinearElasticity(1.0e5, 0.2), SnowPlasticity()),
               ParticleModel.with_plasticity(CorotatedLinearElasticity(1.0e5, 0.2), DruckerPragerPlasticity(1.0e5, 0.2))]
