@@ -11,7 +11,9 @@
 //   PrefixSumWorkspace::{reserve,launch,read_max}    src/utils/prefix_sum.rs:38-151
 //   CudaMpmPipeline::step_generic                    src/cuda/cuda_mpm_pipeline.rs:273-659
 //   DefaultCudaParticleKernelsLauncher               src/cuda/cuda_particle_kernels.rs:29-99
-// It exports the same stage-level C API as the product (prefix `ref_`), so sparkl_b200.engine.Engine drives it.
+// It exports the same stage-level C API as the product (prefix `ref_`), so sparkl_b200.engine.Engine drives it.  Colliders: Cuboid
+// images pass through unchanged; HeightField / Polyline host descriptions are converted to the reference's own device images
+// (parry's CudaHeightFieldPtr / CudaArrayPointer1 layouts recovered from the PTX, see ref_colliders_upload).
 // libcuda is dlopen'ed so the file builds on a GPU-less host.
 #include <cuda.h>
 #include <dlfcn.h>
@@ -112,6 +114,7 @@ struct ref_ctx {
     DevBuf status, pos, vel, volume, phase, data, sorted_ids;
     std::vector<SpkGpuParticleModel> models;
     DevBuf d_models, d_colliders;
+    std::vector<DevBuf> collider_bufs; // device arrays the HeightField / Polyline images point to
     size_t ncolliders = 0;
     GridData grid[2];
     int curr = 0;
@@ -295,6 +298,7 @@ int ref_destroy(ref_ctx* c) {
                       &c->num_active_blocks, &c->scan_values, &c->halo_scan_values, &c->timestep_length})
         b->release();
     for (auto& g : c->grid) { g.buffer.release(); g.active_blocks.release(); g.hashmap.release(); }
+    for (auto& b : c->collider_bufs) b.release();
     for (auto& s : c->stages) s.buf.release();
     if (c->mod) D.p_cuModuleUnload(c->mod);
     delete c;
@@ -349,9 +353,59 @@ int ref_colliders_upload(ref_ctx* c, const SpkGpuCollider* cols, size_t n) {
 #if SPK_DIM == 2
     if (n) return SPK_EUNSUPPORTED; // the byte image of the dim2 GpuCollider was not recovered: collider-free scenes only
 #endif
-    for (size_t i = 0; i < n; ++i) if (cols[i].shape_tag != SPK_SHAPE_CUBOID) return SPK_EUNSUPPORTED; // parry device layouts are not vendored
+#if SPK_DIM == 3
+    // The reference's own byte images of the non-cuboid shapes, recovered from the ld.global offsets of `grid_update` in
+    // resources/sparkl3d-kernels.ptx (tag: u16 @0; all shapes share position @296, friction @324, handling @332):
+    //   HeightField (tag 1) = parry3d GenericHeightField<CudaStoragePtr>: heights {ptr @8, nrows @16, ncols @24} (f32, column-major),
+    //     status {ptr @32, nrows - 1 @40, ncols - 1 @48} (u8 HeightFieldCellStatus, 0 = both triangles, default diagonal),
+    //     scale @56, aabb mins @68 / maxs @80, num_triangles @96, bellow_heightfield_is_solid @104, flip_interior @105
+    //   Polyline (tag 3): vertices {ptr @8, len @16} (Point3<f32>), flip_interior @24
+    // TriMesh (tag 2) holds a device QBVH and is not reproduced.
+    for (auto& b : c->collider_bufs) b.release();
+    c->collider_bufs.clear();
+    c->collider_bufs.reserve(2 * n + 1);
+    std::vector<unsigned char> img(std::max<size_t>(n, 1) * 336, 0);
+    for (size_t i = 0; i < n; ++i) {
+        unsigned char* b = img.data() + i * 336;
+        std::memcpy(b, &cols[i], 336);
+        auto put64 = [&](size_t off, uint64_t v) { std::memcpy(b + off, &v, 8); };
+        if (cols[i].shape_tag == SPK_SHAPE_CUBOID) continue;
+        std::memset(b + 8, 0, 288);
+        if (cols[i].shape_tag == SPK_SHAPE_HEIGHTFIELD) {
+            const auto& hf = cols[i].shape.heightfield;
+            if (!hf.heights || hf.nrows < 2 || hf.ncols < 2) return SPK_EINVAL;
+            const size_t nh = (size_t)hf.nrows * hf.ncols, ns = (size_t)(hf.nrows - 1) * (hf.ncols - 1);
+            c->collider_bufs.emplace_back(); DevBuf& dh = c->collider_bufs.back();
+            if (int r = dh.ensure(nh * 4, false)) return r;
+            CU(D.p_cuMemcpyHtoD_v2(dh.p, hf.heights, nh * 4));
+            c->collider_bufs.emplace_back(); DevBuf& ds = c->collider_bufs.back();
+            if (int r = ds.ensure(ns, true)) return r;
+            put64(8, dh.p); put64(16, hf.nrows); put64(24, hf.ncols);
+            put64(32, ds.p); put64(40, hf.nrows - 1); put64(48, hf.ncols - 1);
+            std::memcpy(b + 56, hf.scale, 12);
+            float lo = hf.heights[0], hi = hf.heights[0];
+            for (size_t k = 1; k < nh; ++k) { lo = std::min(lo, hf.heights[k]); hi = std::max(hi, hf.heights[k]); }
+            const float mins[3] = {-0.5f * hf.scale[0], lo * hf.scale[1], -0.5f * hf.scale[2]}, maxs[3] = {0.5f * hf.scale[0], hi * hf.scale[1], 0.5f * hf.scale[2]};
+            std::memcpy(b + 68, mins, 12); std::memcpy(b + 80, maxs, 12);
+            put64(96, (uint64_t)ns * 2);
+            b[104] = hf.bellow_heightfield_is_solid; b[105] = hf.flip_interior;
+        } else if (cols[i].shape_tag == SPK_SHAPE_POLYLINE) {
+            const auto& pl = cols[i].shape.polyline;
+            if (!pl.vertices || pl.num_vertices == 0) return SPK_EINVAL;
+            c->collider_bufs.emplace_back(); DevBuf& dv = c->collider_bufs.back();
+            if (int r = dv.ensure((size_t)pl.num_vertices * 12, false)) return r;
+            CU(D.p_cuMemcpyHtoD_v2(dv.p, pl.vertices, (size_t)pl.num_vertices * 12));
+            put64(8, dv.p); put64(16, pl.num_vertices);
+            b[24] = pl.flip_interior;
+        } else {
+            return SPK_EUNSUPPORTED;
+        }
+    }
+    if (int r = c->d_colliders.ensure(std::max<size_t>(n, 1) * 336, true)) return r;
+    if (n) CU(D.p_cuMemcpyHtoD_v2(c->d_colliders.p, img.data(), n * 336));
+#else
     if (int r = c->d_colliders.ensure(std::max<size_t>(n, 1) * sizeof(SpkGpuCollider), true)) return r;
-    if (n) CU(D.p_cuMemcpyHtoD_v2(c->d_colliders.p, cols, n * sizeof(SpkGpuCollider)));
+#endif
     c->ncolliders = n;
     return SPK_OK;
 }

@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(256) grid_update_kernel(GridBuffers g, uint32_
         spk_unpack_key(g.blk_key[b], kx, ky);
         const long long cx = ((long long)kx - SPK_PACK_ORIGIN) * 4 + (cell & 3), cy = ((long long)ky - SPK_PACK_ORIGIN) * 4 + (cell >> 2);
         // grid_update.rs:34-38.  __fmul_rn: the product must be ROUNDED before the collider code subtracts from it, as in the
-        // reference (rustc never contracts a * b - c into an fma); a fused cy * h - y_surface decides the `dist - h <= 0` test of
-        // the friction branch differently for nodes exactly one cell above an axis-aligned surface
+        // reference's PTX (the node position is a plain mul.f32 reused by every subtraction); a fused cy * h - y_surface decides
+        // the `dist - h <= 0` test of the friction branch differently for nodes exactly one cell above an axis-aligned surface
         const Vec2 pos{__fmul_rn((float)cx, h), __fmul_rn((float)cy, h)};
         bool have = false, best_inside = false;
         float best_dist = FLT_MAX;
