@@ -68,7 +68,8 @@ __device__ __forceinline__ unsigned long long spk_block_key_of_point(float x, fl
 }
 #endif
 
-#ifdef __CUDACC__ // hash map + warp helpers: device only (the arithmetic helpers above are also host-compiled by tests/host/)
+#if defined(__CUDACC__) || defined(SPK_EMU) // hash map + warp helpers: device only (the arithmetic helpers above are also host-compiled by tests/host/;
+// SPK_EMU = the whole library compiled for the host under the CUDA emulation shim of tests/host/emu/)
 // 64-bit finaliser hash (same family as hashmap.rs:7-14; only set semantics of the map are observable)
 __device__ __forceinline__ uint32_t spk_hash(unsigned long long key, uint32_t mask) {
     key ^= key >> 33;
@@ -115,8 +116,12 @@ __device__ __forceinline__ int32_t spk_hash_get(const GridBuffers& g, unsigned l
 }
 
 __device__ __forceinline__ uint32_t spk_lanemask_lt() {
+#ifdef SPK_EMU
+    return (1u << (threadIdx.x & 31u)) - 1u;
+#else
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+#endif
 }
 #endif // __CUDACC__

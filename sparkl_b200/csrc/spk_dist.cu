@@ -18,8 +18,8 @@
 //              mailbox; two per substep.  The dt minimum rides on the second one.
 // The host never blocks for the exchange: the only read-back per substep is the 64-byte counter record of the sort.
 #include "spk_internal.cuh"
-#if SPK_DIM == 2
-// dim2 build: the NVLink peer-memory path is not built (the 2D scenes of the reference are single-GPU sized); the entry points
+#if SPK_DIM == 2 || defined(SPK_EMU)
+// dim2 build (and the host emulation of tests/host/emu/): the NVLink peer-memory path is not built (the 2D scenes of the reference are single-GPU sized); the entry points
 // exist so both libraries export the same symbols, and fail loudly.
 bool spk_dist_active(const spk_ctx*) { return false; }
 bool spk_dist_grid_storage(spk_ctx*, int, uint32_t, unsigned long long**, uint32_t**) { return false; }

@@ -31,6 +31,18 @@ struct G2P2GParams {
     const void* user;       // opaque device pointer handed to the updater (NULL for the default)
 };
 
+#ifdef SPK_EMU // host emulation (tests/host/emu/): the bulk copies / reductions become plain loops, the mbarrier disappears (the
+// kernel has a __syncthreads between the loads and their consumers)
+__device__ __forceinline__ void mbar_init(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t*) { memcpy(smem_dst, gmem_src, bytes); }
+__device__ __forceinline__ void tma_reduce_add_f32_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    for (uint32_t i = 0; i < bytes / 4; ++i) static_cast<float*>(gmem_dst)[i] += static_cast<const float*>(smem_src)[i];
+}
+__device__ __forceinline__ void tma_commit_and_wait_read() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -62,6 +74,7 @@ __device__ __forceinline__ void tma_commit_and_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif // SPK_EMU
 
 template <class Updater>
 __global__ void __launch_bounds__(G2P2G_THREADS) g2p2g2d_kernel(const G2P2GParams P) {

@@ -51,6 +51,18 @@ constexpr int SM_HALO = SM_MISC + 8 + 32 + 32 + 16;          // uint32[8]: bit0 
 constexpr int SM_TOTAL = SM_HALO + 32;
 
 // ---- TMA bulk helpers (sm_90+; SASS: UBLKCP / UBLKRED) ------------------------------------------------------------
+#ifdef SPK_EMU // host emulation (tests/host/emu/): the bulk copies / reductions become plain loops, the mbarrier disappears (the
+// kernel has a __syncthreads between the loads and their consumers)
+__device__ __forceinline__ void mbar_init(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t*) { memcpy(smem_dst, gmem_src, bytes); }
+__device__ __forceinline__ void tma_reduce_add_f32_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    for (uint32_t i = 0; i < bytes / 4; ++i) static_cast<float*>(gmem_dst)[i] += static_cast<const float*>(smem_src)[i];
+}
+__device__ __forceinline__ void tma_commit_and_wait_read() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -85,6 +97,7 @@ __device__ __forceinline__ void tma_commit_and_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif // SPK_EMU
 
 // tile index helpers: tile coordinate t in [0,8) per axis -> (cell part, octant part) of the [octant][...][cell] layout
 __device__ __forceinline__ int cell_part(int t, int axis) { return (t & 3) << (2 * axis); }
@@ -104,7 +117,11 @@ __device__ __forceinline__ void quad_weights(float x, float w[3]) {
 //         same-address conflicts inside a group.
 template <int MODE, class Updater>
 __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kernel(const G2P2GParams P) {
+#ifdef SPK_EMU
+    unsigned char* smem = emu::dynamic_smem();
+#else
     extern __shared__ __align__(128) unsigned char smem[];
+#endif
     float4* s_vel = reinterpret_cast<float4*>(smem + SM_VEL);
     float* s_acc = reinterpret_cast<float*>(smem + SM_ACC);
     float* s_pay = reinterpret_cast<float*>(smem + SM_PAY);
@@ -418,8 +435,10 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
         }
         if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(P.dt_raw_bits, *s_dtmin);
         if (pushed) { // remote reductions must be complete (not only read out of shared memory) before this CTA retires
+#ifndef SPK_EMU
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
             __threadfence_system();
         } else {
             tma_commit_and_wait_read();

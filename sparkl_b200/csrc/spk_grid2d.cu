@@ -318,7 +318,7 @@ __global__ void grid_export_kernel(GridBuffers g, uint32_t nblocks, SpkGpuGridNo
     out[t] = n;
 }
 
-#ifdef __CUDACC__ // everything below needs the device hash map / launch syntax; the per-node kernels above are also host-compiled by tests/host/
+#if defined(__CUDACC__) || defined(SPK_EMU) // everything below needs the device hash map / launch syntax; the per-node kernels above are also host-compiled by tests/host/
 // ---- halo path (portable multi-process protocol, same contract as the 3D build with 96 floats per block) ---------------
 __global__ void halo_keys_kernel(GridBuffers g, uint32_t nab, unsigned long long* out, uint32_t capacity) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(CELLS) halo_merge_kernel(GridBuffers g, const 
 
 } // namespace
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(SPK_EMU)
 cudaError_t spk_launch_reset_grid(spk_ctx* c) {
     GridBuffers& next = c->grid[1 - c->gcur];
     const uint32_t nab = next.nab_host;

@@ -1,0 +1,150 @@
+// cuda_emu.cpp — the fiber scheduler and the host stand-ins for the CUDA runtime calls the product makes (see cuda_emu.h).
+// TEST INFRASTRUCTURE ONLY.
+#include "cuda_emu.h"
+
+#include <ucontext.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+namespace emu {
+Idx tid{0, 0, 0}, bid{0, 0, 0}, bdim{1, 1, 1}, gdim{1, 1, 1};
+
+namespace {
+enum State { READY, WAIT_BLOCK, WAIT_WARP, DONE };
+struct Fiber {
+    ucontext_t ctx;
+    char* stack = nullptr;
+    State state = DONE;
+    unsigned wait_mask = 0;
+};
+constexpr size_t STACK_BYTES = 512 * 1024;
+std::vector<Fiber> fibers;
+ucontext_t sched_ctx;
+int cur = -1;
+const std::function<void()>* body_fn = nullptr;
+unsigned long long scratch[32][32];
+alignas(128) unsigned char dyn_smem[232448];
+
+void trampoline() {
+    (*body_fn)();
+    fibers[cur].state = DONE;
+    swapcontext(&fibers[cur].ctx, &sched_ctx);
+}
+void park(State s, unsigned mask) {
+    Fiber& f = fibers[cur];
+    f.state = s;
+    f.wait_mask = mask;
+    swapcontext(&f.ctx, &sched_ctx);
+}
+void run_cta(unsigned nthreads) {
+    if (fibers.size() < nthreads) fibers.resize(nthreads);
+    for (unsigned t = 0; t < nthreads; ++t) {
+        Fiber& f = fibers[t];
+        if (!f.stack) f.stack = (char*)std::malloc(STACK_BYTES);
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = STACK_BYTES;
+        f.ctx.uc_link = &sched_ctx;
+        makecontext(&f.ctx, trampoline, 0);
+        f.state = READY;
+    }
+    for (;;) {
+        bool ran = false;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            if (fibers[t].state != READY) continue;
+            cur = (int)t;
+            tid = Idx{t, 0, 0};
+            swapcontext(&sched_ctx, &fibers[t].ctx);
+            ran = true;
+        }
+        // release warp-level waits: every live lane named by the mask has arrived with the same mask
+        bool released = false;
+        for (unsigned w = 0; w * 32 < nthreads; ++w) {
+            for (unsigned l = 0; l < 32 && w * 32 + l < nthreads; ++l) {
+                Fiber& f = fibers[w * 32 + l];
+                if (f.state != WAIT_WARP) continue;
+                const unsigned mask = f.wait_mask;
+                bool all = true;
+                for (unsigned k = 0; k < 32 && all; ++k) {
+                    if (!(mask >> k & 1u) || w * 32 + k >= nthreads) continue;
+                    const Fiber& o = fibers[w * 32 + k];
+                    all = o.state == DONE || (o.state == WAIT_WARP && o.wait_mask == mask);
+                }
+                if (!all) continue;
+                for (unsigned k = 0; k < 32; ++k)
+                    if ((mask >> k & 1u) && w * 32 + k < nthreads && fibers[w * 32 + k].state == WAIT_WARP) fibers[w * 32 + k].state = READY;
+                released = true;
+            }
+        }
+        if (released) continue;
+        // release the CTA barrier: every live thread waits on it
+        bool any_live = false, all_block = true;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            if (fibers[t].state == DONE) continue;
+            any_live = true;
+            if (fibers[t].state != WAIT_BLOCK) all_block = false;
+        }
+        if (!any_live) return;
+        if (all_block) {
+            for (unsigned t = 0; t < nthreads; ++t) if (fibers[t].state == WAIT_BLOCK) fibers[t].state = READY;
+            continue;
+        }
+        if (!ran) {
+            std::fprintf(stderr, "cuda_emu: deadlock in block %u (threads wait on different barriers)\n", bid.x);
+            std::abort();
+        }
+    }
+}
+} // namespace
+
+void launch(unsigned grid, unsigned block, const std::function<void()>& body) {
+    if (grid == 0 || block == 0) return;
+    body_fn = &body;
+    gdim = Idx{grid, 1, 1};
+    bdim = Idx{block, 1, 1};
+    for (unsigned b = 0; b < grid; ++b) {
+        bid = Idx{b, 0, 0};
+        run_cta(block);
+    }
+    cur = -1;
+    body_fn = nullptr;
+}
+void block_sync() { park(WAIT_BLOCK, 0); }
+void warp_sync(unsigned mask) { park(WAIT_WARP, mask); }
+unsigned long long* warp_scratch() { return scratch[(tid.x >> 5) & 31u]; }
+unsigned char* dynamic_smem() { return dyn_smem; }
+} // namespace emu
+
+// ---- CUDA runtime stand-ins: one "device", memory is host memory, streams and events are inert ---------------------------------
+extern "C" {
+cudaError_t cudaSetDevice(int dev) { return dev == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* p, int) { std::memset(p, 0, sizeof(*p)); p->major = 10; p->minor = 0; p->multiProcessorCount = 148; return cudaSuccess; }
+cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
+cudaError_t cudaMemset(void* p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)std::malloc(8); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+struct EmuEvent { std::chrono::steady_clock::time_point t; };
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t) new EmuEvent(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete (EmuEvent*)e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { ((EmuEvent*)e)->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(((EmuEvent*)b)->t - ((EmuEvent*)a)->t).count();
+    return cudaSuccess;
+}
+}

@@ -1,0 +1,97 @@
+"""The product's CUDA sources on a GPU-less machine.
+
+tests/host/emu/ compiles sparkl_b200/csrc/*.cu — every kernel AND the host sequencing of spk_api.cu — for the host with g++ on top
+of a small CUDA execution model (each CUDA thread is a fiber; __syncthreads / warp collectives are scheduling points; TMA bulk
+copies become loops; see tests/host/emu/cuda_emu.h).  The resulting libsparkl_b200_emu*.so export the same C ABI, so the bodies of
+the GPU test modules run against them unchanged: same scenes, same comparisons with the oracle and with the committed outputs of
+the reference's own kernels, same tolerances.  What the emulation cannot show: anything about performance, the asynchronous
+overlap of streams, real TMA / mbarrier behaviour and the NVLink path — those stay with `pytest -m gpu`.
+
+The emulated libraries are test infrastructure: they live in tests/host/, nothing under sparkl_b200/ knows them, and the product
+still fails loudly without a GPU (tests/test_abi_cpu.py::test_no_cpu_fallback runs with the real library)."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "host", "emu"))
+
+
+@pytest.fixture()
+def emulated(monkeypatch):
+    """route sparkl_b200._lib.lib(dim) to the emulated libraries for the duration of one test"""
+    import build_emu
+    from sparkl_b200 import _lib
+    monkeypatch.setattr(_lib, "LIB_PATH", build_emu.build(3))
+    monkeypatch.setattr(_lib, "LIB2D_PATH", build_emu.build(2))
+    monkeypatch.setattr(_lib, "_LIBS", {})
+    monkeypatch.setattr(_lib, "_LIB", None)
+    yield _lib
+    # monkeypatch restores the real paths and an empty cache: the next lib() call loads the real library again
+
+
+def test_the_emulation_is_not_a_product_path():
+    from sparkl_b200 import _lib
+    for attr in ("LIB_PATH", "LIB2D_PATH"):
+        assert "emu" not in os.path.basename(getattr(_lib, attr))
+    for root, _, files in os.walk(os.path.join(ROOT, "sparkl_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "libsparkl_b200_emu" not in open(os.path.join(root, f)).read(), f
+
+
+# ---------------------------------------------------------------------------------------------- dim3: product vs oracle, stage by stage
+@pytest.mark.parametrize("name", ["test_sand_first_substeps", "test_fluid_dam_break", "test_neo_hookean_block", "test_sand_on_heightfield_ground",
+                                  "test_sand_in_a_polyline_trough", "test_sand_on_a_trimesh_ramp", "test_cube_through_sand_kinematic",
+                                  "test_full_step_matches_oracle", "test_empty_and_single_particle", "test_ragged_blocks_and_chunk_boundaries",
+                                  "test_append_remove_read_roundtrip"])
+def test_dim3_parity_bodies_on_the_emulation(emulated, oracle, name):
+    import tests.test_parity_gpu as T
+    getattr(T, name)(oracle)
+
+
+@pytest.mark.parametrize("kind", ["nacc", "rankine", "snow", "failure", "failure_split"])
+def test_dim3_other_models_on_the_emulation(emulated, oracle, kind):
+    import tests.test_parity_gpu as T
+    T.test_other_plasticity_and_failure_models(oracle, kind)
+
+
+@pytest.mark.parametrize("name", ["test_async_readback_matches_blocking_reads", "test_invalid_collider_shapes_are_rejected"])  # the async-upload test pins host memory through torch, which needs a driver
+def test_dim3_api_bodies_on_the_emulation(emulated, name):
+    import tests.test_parity_gpu as T
+    getattr(T, name)()
+
+
+@pytest.mark.parametrize("name", ["test_negative_far_and_nan_coordinates", "test_failed_and_static_particles", "test_model_table_with_unused_entries"])
+# (test_hash_map_grows_when_blocks_outnumber_the_estimate also passes on the emulation but takes a minute there: GPU suite only)
+def test_dim3_edge_cases_on_the_emulation(emulated, oracle, name):
+    import tests.test_edge_gpu as T
+    getattr(T, name)(oracle)
+
+
+# ---------------------------------------------------------------------------------------------- product vs the reference's own kernels (fixtures)
+def _golden_cases():
+    from tests import util
+    return util.golden_cases()
+
+
+@pytest.mark.parametrize("case", _golden_cases())
+def test_product_matches_reference_fixture_on_the_emulation(emulated, case):
+    import tests.test_golden_gpu as T
+    T.test_product_matches_reference_fixture(case)
+
+
+# ---------------------------------------------------------------------------------------------- dim2
+@pytest.mark.parametrize("name", ["test_upload_read_roundtrip_dim2", "test_elasticity2_lockstep", "test_elasticity2_on_the_ground", "test_fluids2_dam_break_lockstep",
+                                  "test_polyline_trough_dim2", "test_basic2_on_the_heightfield_ground", "test_full_step_matches_oracle_dim2",
+                                  "test_momentum_conservation_and_free_fall_dim2", "test_unsupported_dim2_features_fail_loudly"])
+def test_dim2_bodies_on_the_emulation(emulated, name):
+    import tests.test_dim2_gpu as T
+    getattr(T, name)()
+
+
+@pytest.mark.parametrize("kind", ["corotated", "neo_hookean", "fluid", "sand", "nacc", "failure", "failure_split"])
+def test_dim2_models_on_the_emulation(emulated, kind):
+    import tests.test_dim2_gpu as T
+    T.test_model_block2_lockstep(kind)
