@@ -95,3 +95,27 @@ def test_dim2_bodies_on_the_emulation(emulated, name):
 def test_dim2_models_on_the_emulation(emulated, kind):
     import tests.test_dim2_gpu as T
     T.test_model_block2_lockstep(kind)
+
+
+def test_streaming_upload_and_async_readback_on_the_emulation(emulated):
+    """the e2e loop of bench.py (stage the next state, commit, step, asynchronous read-back) through the same entry points, with plain
+    numpy arrays standing in for pinned memory: same state as the blocking calls"""
+    import numpy as np
+    from sparkl_b200 import abi, scenes
+    from sparkl_b200.pipeline import context_from_scene
+    sc = scenes.jitter(scenes.sand3(8, 4, 6), 0.02, seed=5)
+    a, b = context_from_scene(sc), context_from_scene(sc)
+    pc = sc.particles
+    for frame in range(2):
+        a.upload(pc)
+        b.upload_async(pc, stage_only=True)
+        b.commit_staged()
+        (sa, ta), (sb, tb) = a.step(sc.params, sc.gravity), b.step(sc.params, sc.gravity, timings=False)
+        assert ta.num_substeps > 0 and abs(sa - sb) < 1e-7
+        out = {w: np.empty(len(pc), abi.ATTR_DTYPES[w]) for w in (abi.ATTR_POSITION, abi.ATTR_VELOCITY, abi.ATTR_PHASE)}
+        for w, buf in out.items():
+            b.read_async(w, buf)
+        b.read_wait()
+        for w, buf in out.items():
+            assert np.array_equal(buf, a.read(w)), w  # the emulation is deterministic: bit-identical
+        pc = a.read_all()
