@@ -119,3 +119,12 @@ def test_streaming_upload_and_async_readback_on_the_emulation(emulated):
         for w, buf in out.items():
             assert np.array_equal(buf, a.read(w)), w  # the emulation is deterministic: bit-identical
         pc = a.read_all()
+
+
+def test_g2p2g_mode0_on_the_emulation(emulated, oracle, monkeypatch):
+    """the A/B variant of the fused kernel (SPK_G2P2G_MODE=0: per-particle shared atomics instead of the cell-binned register
+    accumulation) gives the same physics"""
+    import tests.test_parity_gpu as T
+    monkeypatch.setenv("SPK_G2P2G_MODE", "0")
+    T.test_sand_first_substeps(oracle)
+    T.test_cube_through_sand_kinematic(oracle)
