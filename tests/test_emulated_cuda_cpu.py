@@ -128,3 +128,38 @@ def test_g2p2g_mode0_on_the_emulation(emulated, oracle, monkeypatch):
     monkeypatch.setenv("SPK_G2P2G_MODE", "0")
     T.test_sand_first_substeps(oracle)
     T.test_cube_through_sand_kinematic(oracle)
+
+
+def test_cpp_host_example_builds_and_matches_the_python_host(emulated, tmp_path):
+    """include/sparkl_b200.hpp (the C++ mirror of the reference's host API) + examples/cpp_host/sand_column.cpp: linked against the
+    emulated library it must reproduce, bit for bit, what the Python mirror computes through the same library; linked against the
+    real library on a GPU-less machine it must fail loudly (no CPU fallback)"""
+    import subprocess
+    import numpy as np
+    import build_emu
+    from sparkl_b200 import abi, scenes
+    from sparkl_b200.pipeline import context_from_scene
+    src = os.path.join(ROOT, "examples", "cpp_host", "sand_column.cpp")
+    inc = os.path.join(ROOT, "include")
+    emu_lib = build_emu.build(3)
+    exe = str(tmp_path / "sand_column_emu")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + inc, src, "-o", exe, emu_lib, "-Wl,-rpath," + os.path.dirname(emu_lib)])
+    out_bin = str(tmp_path / "pos.bin")
+    out = subprocess.check_output([exe, "8", "4", "6", "2", out_bin]).decode()
+    assert "particles 384" in out and "ERROR" not in out, out
+    pos_cpp = np.fromfile(out_bin, np.float32).reshape(-1, 3)
+    # the same scene through the Python mirror (scenes.sand3 builds exactly this lattice) and the same library
+    sc = scenes.sand3(8, 4, 6, with_colliders=False)
+    ext = 0.1
+    sc.colliders = [abi.CuboidCollider((8 * ext / 2 + 6.0, 1.0, 6 * ext / 2 + 6.0), (8 * ext / 2, 1.0, 6 * ext / 2))]
+    g = context_from_scene(sc)
+    for _ in range(2):
+        g.step(sc.params, sc.gravity)
+    assert np.array_equal(g.read(abi.ATTR_POSITION)["point"], pos_cpp)
+    # against the real library: builds, and without a GPU exits with the "no usable CUDA device" code
+    import torch
+    real = os.path.join(ROOT, "sparkl_b200", "libsparkl_b200.so")
+    if os.path.exists(real) and not torch.cuda.is_available():
+        exe2 = str(tmp_path / "sand_column")
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + inc, src, "-o", exe2, real, "-Wl,-rpath," + os.path.dirname(real)])
+        assert subprocess.run([exe2, "4", "2", "2", "1"], capture_output=True).returncode == 10
