@@ -410,6 +410,13 @@ int spk_dt_acc_set(spk_ctx* ctx, uint64_t value);
 int spk_stage_g2p2g(spk_ctx* ctx, float dt, uint32_t damage_model);
 /* grid_update + swap_buffers (cuda_mpm_pipeline.rs:536-558): K19 */
 int spk_stage_grid_update(spk_ctx* ctx, float dt, const float gravity[SPK_DIM]);
+/* Fluids-volume recomputation: recompute_fluids_volume_p2g / _g2p (src_kernels/cuda/fluids_volume.rs:9-105; the reference comments the
+ * two kernels out of its build, src_kernels/cuda/mod.rs:2,18, and runs the same pass on the CPU after the sort when
+ * SolverParameters::force_fluids_volume_recomputation is set, src/dynamics/solver/mls_solver.rs:46-48, fluids_volume.rs:9-116).
+ * F[0][0] of every Monaghan particle <- (mass / (sum_nodes w * node_mass / h^DIM)) / volume0.  Valid between spk_stage_reset_grid and
+ * spk_stage_g2p2g (SPK_ESTATE before the first sort); the next grid is left zeroed.  spk_step never calls it: the reference's CUDA
+ * pipeline ignores the flag. */
+int spk_stage_recompute_fluids_volume(spk_ctx* ctx);
 
 /* ---- halo exchange for multi-process runs (replaces K3,K4,K17,K18 and the D2D copies,
  * cuda_sparse_grid.rs:256-322, cuda_mpm_pipeline.rs:407-533).  Keys travel as u64 virtual ids; payload is the

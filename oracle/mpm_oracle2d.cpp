@@ -1057,6 +1057,52 @@ int orc_stage_g2p2g(orc_ctx* c, float dt, uint32_t damage_model) {
     return SPK_OK;
 }
 
+// Fluids-volume recomputation: MlsSolver::recompute_fluids_volumes, src/dynamics/solver/fluids_volume.rs:9-116 (the live CPU pass;
+// the GPU kernels src_kernels/cuda/fluids_volume.rs:9-105 are the same arithmetic, commented out of the reference's build).  Runs after
+// the sort on the zeroed next grid: P2G of the particle masses, G2P of the node masses into F[0][0] of the fluid particles, node masses
+// back to zero.  Node sums in double then rounded once (the order of the reference's additions is unspecified on either path).
+int orc_stage_recompute_fluids_volume(orc_ctx* c) {
+    Grid& next = c->next_grid();
+    const Real h = c->cell_width;
+    const size_t n = c->pos.size();
+    std::vector<double> acc(next.nodes.size(), 0.0);
+    std::vector<long long> node((size_t)n * 9, -1);
+    std::vector<Real> wgt((size_t)n * 9, 0.0f);
+    for (size_t i = 0; i < n; ++i) {
+        auto ref = dir_to_associated_grid_node(c->pos[i].point, h);
+        Real w[2][3];
+        uint64_t base[2];
+        int cib[2];
+        main_block_of_point(c->pos[i].point, h, base);
+        for (int a = 0; a < 2; ++a) {
+            eval_all(-ref[a] / h, w[a]);
+            int assoc_cell = sat_i32(std::round(c->pos[i].point[a] / h)) - 2; // particle.rs:28-35
+            int assoc_block = sat_i32(std::floor((Real)assoc_cell / 4.0f)) * 4;
+            cib[a] = assoc_cell - assoc_block;
+        }
+        for (int k = 0; k < 9; ++k) {
+            const int* s = NBH[k];
+            int t[2];
+            for (int a = 0; a < 2; ++a) t[a] = cib[a] + 1 + s[a];
+            int b = next.find(pack_key(base[0] + (uint64_t)(t[0] >> 2), base[1] + (uint64_t)(t[1] >> 2)));
+            if (b < 0) continue; // cannot happen after touch_particle_blocks
+            node[i * 9 + k] = (long long)b * 16 + (t[0] & 3) * 1 + (t[1] & 3) * 4;
+            wgt[i * 9 + k] = w[0][s[0]] * w[1][s[1]];
+            acc[(size_t)node[i * 9 + k]] += (double)(wgt[i * 9 + k] * c->volume[i].mass); // fluids_volume.rs:40-47
+        }
+    }
+    for (size_t i = 0; i < n; ++i) {
+        if (!model_is_fluid(c->models[c->status[i].model_index])) continue; // :70-77
+        Real new_mass = 0.0f;
+        for (int k = 0; k < 9; ++k)
+            if (node[i * 9 + k] >= 0) new_mass += wgt[i * 9 + k] * ftz((Real)acc[(size_t)node[i * 9 + k]]);
+        Real new_density = new_mass / (h * h); // cell_width.powi(DIM)
+        Real new_volume = c->volume[i].mass / new_density;
+        c->volume[i].deformation_gradient[0] = new_volume / c->volume[i].volume0;
+    }
+    return SPK_OK; // the next grid's masses were never written: "Reset the modified cells" (:98-113) is implicit
+}
+
 // grid_update + swap_buffers, src_kernels/cuda/grid_update.rs:10-52, cuda_mpm_pipeline.rs:536-558
 int orc_stage_grid_update(orc_ctx* c, float dt, const float gravity[2]) {
     Grid& next = c->next_grid();

@@ -911,6 +911,18 @@ int spk_stage_g2p2g(spk_ctx* c, float dt, uint32_t damage_model) {
     return launch_g2p2g_hooked(c, dt);
 }
 
+// recompute_fluids_volume_{p2g,g2p} (src_kernels/cuda/fluids_volume.rs, not compiled into the reference's module) with the sequencing of
+// MlsSolver::recompute_fluids_volumes (src/dynamics/solver/fluids_volume.rs:9-116): after the sort, before the transfer
+int spk_stage_recompute_fluids_volume(spk_ctx* c) {
+    if (!c) return SPK_EINVAL;
+    if (!c->sorted_valid) return SPK_ESTATE; // needs the particle -> block map of spk_stage_sort (and the zeroed next grid)
+    if (spk_dist_active(c)) return SPK_EUNSUPPORTED; // the node masses of shared blocks would need their own halo exchange
+    CK(cudaSetDevice(c->device));
+    CK(spk_launch_fluids_volume(c));
+    c->dt_cache_valid = false; // F[0][0] of the fluid particles changed: the cached CFL candidate is stale
+    return SPK_OK;
+}
+
 int spk_stage_grid_update(spk_ctx* c, float dt, const float gravity[SPK_DIM]) {
     if (!c || !gravity) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));

@@ -204,6 +204,7 @@ cudaError_t spk_launch_reset_grid(spk_ctx* c);
 cudaError_t spk_launch_estimate_dt(spk_ctx* c, float min_dt, float max_dt);
 cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt);
 cudaError_t spk_launch_grid_update(spk_ctx* c, float dt, const float gravity[SPK_DIM]);
+cudaError_t spk_launch_fluids_volume(spk_ctx* c);             // spk_fluids.cu
 cudaError_t spk_launch_pack_upload(spk_ctx* c, const void* d_status, const void* d_pos, const void* d_vel, const void* d_volume,
                                    const void* d_phase, const void* d_data, size_t first, size_t n);
 cudaError_t spk_launch_unpack(spk_ctx* c, int which, void* d_out, size_t n);

@@ -39,7 +39,8 @@ def declare(lib, prefix: str):
         "grid_read_nodes": [_vp, C.c_int, _vp, C.c_uint32],
         "grid_read_dispatch": [_vp, _vp, C.c_uint32],
     }
-    for name, args in sig.items():
+    optional = {"stage_recompute_fluids_volume": [_vp]}  # not part of the reference's compiled module: absent from the `ref_` harness
+    for name, args in list(sig.items()) + [(k, v) for k, v in optional.items() if hasattr(lib, prefix + k)]:
         fn = getattr(lib, prefix + name)
         fn.argtypes = args
         fn.restype = C.c_int
@@ -135,6 +136,11 @@ class Engine:
     def stage_grid_update(self, dt: float, gravity):
         g = (C.c_float * 3)(*gravity)
         self._call("stage_grid_update", dt, C.byref(g))
+
+    def stage_recompute_fluids_volume(self):
+        """fluids-volume recomputation (src/dynamics/solver/fluids_volume.rs:9-116, src_kernels/cuda/fluids_volume.rs): between
+        stage_reset_grid and stage_g2p2g"""
+        self._call("stage_recompute_fluids_volume")
 
     def substep(self, params: abi.SolverParameters, gravity, remaining: float) -> float:
         """One iteration of the `while remaining_time > 0` loop of cuda_mpm_pipeline.rs:322-638."""
