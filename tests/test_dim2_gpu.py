@@ -221,26 +221,3 @@ def test_three_way_lockstep_with_reference_dim2_kernels_clamping_models(ref2d, c
     from tests.test_reference_gpu import _lockstep
     sc, nsub, _ = build_case(case)
     _lockstep(sc, ref2d, nsub, 2e-5, robust=True)
-
-
-def test_fluids_volume_recomputation_dim2():
-    """fluids-volume recomputation (src_kernels/cuda/fluids_volume.rs with the `dim2` feature) against the dim2 oracle,
-    and the rest-lattice property (interior F[0][0] = 1)"""
-    sc = scenes2d.jitter(scenes2d.fluids2(40, 30, with_colliders=False), 0.004, seed=6)
-    g, o = _engines(sc)
-    with pytest.raises(abi.SparklError) as e:
-        g.stage_recompute_fluids_volume()
-    assert e.value.code == abi.ESTATE
-    g.stage_sort(); o.stage_sort()
-    g.stage_reset_grid(); o.stage_reset_grid()
-    before = g.read(abi.ATTR_VOLUME).copy()
-    g.stage_recompute_fluids_volume(); o.stage_recompute_fluids_volume()
-    Fg, Fo = g.read(abi.ATTR_VOLUME)["deformation_gradient"], o.read(abi.ATTR_VOLUME)["deformation_gradient"]
-    assert np.allclose(Fg[:, 0], Fo[:, 0], rtol=2e-5, atol=0), np.abs(Fg[:, 0] / Fo[:, 0] - 1).max()
-    assert np.array_equal(Fg[:, 1:], before["deformation_gradient"][:, 1:])
-    assert not g.grid_nodes(1)["mass"].any()
-    rest = scenes2d.fluids2(32, 32, with_colliders=False)
-    g2, _ = _engines(rest)
-    g2.stage_sort(); g2.stage_reset_grid(); g2.stage_recompute_fluids_volume()
-    F00 = g2.read(abi.ATTR_VOLUME)["deformation_gradient"][:, 0].reshape(32, 32)
-    assert np.abs(F00[8:-8, 8:-8] - 1.0).max() < 1e-4 and F00[0, 0] > 2.0

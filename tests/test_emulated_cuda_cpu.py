@@ -45,7 +45,7 @@ def test_the_emulation_is_not_a_product_path():
 @pytest.mark.parametrize("name", ["test_sand_first_substeps", "test_fluid_dam_break", "test_neo_hookean_block", "test_sand_on_heightfield_ground",
                                   "test_sand_in_a_polyline_trough", "test_sand_on_a_trimesh_ramp", "test_cube_through_sand_kinematic",
                                   "test_full_step_matches_oracle", "test_empty_and_single_particle", "test_ragged_blocks_and_chunk_boundaries",
-                                  "test_append_remove_read_roundtrip", "test_fluids_volume_recomputation"])
+                                  "test_append_remove_read_roundtrip"])
 def test_dim3_parity_bodies_on_the_emulation(emulated, oracle, name):
     import tests.test_parity_gpu as T
     getattr(T, name)(oracle)
@@ -57,8 +57,7 @@ def test_dim3_other_models_on_the_emulation(emulated, oracle, kind):
     T.test_other_plasticity_and_failure_models(oracle, kind)
 
 
-@pytest.mark.parametrize("name", ["test_async_readback_matches_blocking_reads", "test_invalid_collider_shapes_are_rejected",
-                                  "test_fluids_volume_of_a_rest_lattice_is_its_rest_volume"])  # the async-upload test pins host memory through torch, which needs a driver
+@pytest.mark.parametrize("name", ["test_async_readback_matches_blocking_reads", "test_invalid_collider_shapes_are_rejected"])  # the async-upload test pins host memory through torch, which needs a driver
 def test_dim3_api_bodies_on_the_emulation(emulated, name):
     import tests.test_parity_gpu as T
     getattr(T, name)()
@@ -69,6 +68,13 @@ def test_dim3_api_bodies_on_the_emulation(emulated, name):
 def test_dim3_edge_cases_on_the_emulation(emulated, oracle, name):
     import tests.test_edge_gpu as T
     getattr(T, name)(oracle)
+
+
+def test_fluids_volume_recomputation_on_the_emulation(emulated, oracle):
+    import tests.test_volume_recomputation_gpu as T
+    T.test_fluids_volume_recomputation(oracle)
+    T.test_fluids_volume_of_a_rest_lattice_is_its_rest_volume()
+    T.test_fluids_volume_recomputation_dim2()
 
 
 # ---------------------------------------------------------------------------------------------- product vs the reference's own kernels (fixtures)
@@ -86,8 +92,7 @@ def test_product_matches_reference_fixture_on_the_emulation(emulated, case):
 # ---------------------------------------------------------------------------------------------- dim2
 @pytest.mark.parametrize("name", ["test_upload_read_roundtrip_dim2", "test_elasticity2_lockstep", "test_elasticity2_on_the_ground", "test_fluids2_dam_break_lockstep",
                                   "test_polyline_trough_dim2", "test_basic2_on_the_heightfield_ground", "test_full_step_matches_oracle_dim2",
-                                  "test_momentum_conservation_and_free_fall_dim2", "test_unsupported_dim2_features_fail_loudly",
-                                  "test_fluids_volume_recomputation_dim2"])
+                                  "test_momentum_conservation_and_free_fall_dim2", "test_unsupported_dim2_features_fail_loudly"])
 def test_dim2_bodies_on_the_emulation(emulated, name):
     import tests.test_dim2_gpu as T
     getattr(T, name)()
