@@ -443,6 +443,39 @@ int spk_dist_attach(spk_ctx* ctx, uint32_t rank, uint32_t world, const SpkDistDe
 int spk_dist_detach(spk_ctx* ctx);
 int spk_dist_info(spk_ctx* ctx, uint32_t* num_halo_blocks, uint32_t* barrier_epoch);
 
+/* ---- particle migration between slabs, device side.  The reference keeps particle ownership static
+ * (SingleGpuMpmContext, src/cuda/cuda_mpm_pipeline.rs:177-194: one CudaParticleSet per device for the whole run); with spatial slabs
+ * a particle that leaves its slab is handed to the rank that owns its block column.  The wire format is one row per particle: the
+ * reference's six per-particle structs (src_core/dynamics/particle.rs:14-219) + a 32-bit global id — 128 bytes in dim3. */
+typedef struct SpkParticleRecord {
+    SpkParticleStatus status;
+    SpkParticlePosition position;
+    SpkParticleVelocity velocity;
+    SpkParticleVolume volume;
+    SpkParticlePhase phase;
+    SpkParticleData data;
+    uint32_t gid;
+} SpkParticleRecord;
+#if defined(__cplusplus) && SPK_DIM == 3
+static_assert(sizeof(SpkParticleRecord) == 128, "SpkParticleRecord");
+#endif
+/* optional global ids, indexed by particle id (HOST arrays; n must equal the particle count).  Default: gid == particle id.  Any
+ * host-side edit of the set (upload, append, remove_range) resets them to the identity. */
+int spk_particles_set_gids(spk_ctx* ctx, const uint32_t* gids, size_t n);
+int spk_particles_read_gids(spk_ctx* ctx, uint32_t* dst, size_t n);
+/* Owner of a particle = slab r with bounds[r] <= block_x < bounds[r + 1], block_x as in GpuGrid::block_associated_to_point
+ * (gpu_grid.rs:271-279); `bounds` is a HOST array of world + 1 increasing block coordinates whose outer two are open ended.  Every
+ * particle owned by another rank is written to dev_records (DEVICE memory, `capacity` rows): grouped by destination rank, ascending
+ * particle id inside a group; counts_out[world] (HOST) receives the rows per destination.  The remaining particles keep their relative
+ * order and are renumbered densely.  dev_records == NULL only counts.  Nothing changes when nobody leaves (the sort state stays
+ * valid) or when `capacity` is too small (SPK_EOVERFLOW; counts_out is still filled). */
+int spk_particles_migrate_out(spk_ctx* ctx, const int64_t* bounds, uint32_t world, uint32_t rank, SpkParticleRecord* dev_records, size_t capacity,
+                              uint32_t* counts_out);
+/* appends n rows from DEVICE memory; their particle ids continue after the current ones, in row order (grows on the device).  n == 0
+ * only marks the set as edited: in a collective migration every rank calls this, so that all ranks take the same path (stand-alone dt
+ * kernel + its device-side barrier) in the next step of the peer-memory pipeline. */
+int spk_particles_migrate_in(spk_ctx* ctx, const SpkParticleRecord* dev_records, size_t n);
+
 /* ---- read-back of the sparse grid in the reference's layouts (parity tests; ≙ the commented-out
  * check_active_blocks, cuda_sparse_grid.rs:491-652).  which_grid: 0 = curr, 1 = next. */
 int spk_grid_num_active_blocks(spk_ctx* ctx, int which_grid, uint32_t* out);

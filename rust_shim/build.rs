@@ -10,9 +10,9 @@ fn main() {
     // sparkl2d crate builds the same host sequencing / sort / ABI sources with -DSPK_DIM=2 and the dim2 stencil kernels
     let dim2 = env::var("CARGO_FEATURE_DIM2").is_ok();
     let sources: &[&str] = if dim2 {
-        &["spk_api.cu", "spk_sort.cu", "spk_g2p2g2d.cu", "spk_grid2d.cu", "spk_dist.cu", "spk_fluids.cu"]
+        &["spk_api.cu", "spk_sort.cu", "spk_g2p2g2d.cu", "spk_grid2d.cu", "spk_dist.cu", "spk_fluids.cu", "spk_migrate.cu"]
     } else {
-        &["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu", "spk_dist.cu", "spk_fluids.cu"]
+        &["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu", "spk_dist.cu", "spk_fluids.cu", "spk_migrate.cu"]
     };
     let mut objects = vec![];
     for s in sources {

@@ -7,9 +7,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu", "spk_dist.cu", "spk_fluids.cu"]
+SOURCES = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g.cu", "spk_grid.cu", "spk_dist.cu", "spk_fluids.cu", "spk_migrate.cu"]
 # the dim2 library: same host sequencing / sort / ABI sources compiled with -DSPK_DIM=2, its own stencil kernels
-SOURCES_2D = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g2d.cu", "spk_grid2d.cu", "spk_dist.cu", "spk_fluids.cu"]
+SOURCES_2D = ["spk_api.cu", "spk_sort.cu", "spk_g2p2g2d.cu", "spk_grid2d.cu", "spk_dist.cu", "spk_fluids.cu", "spk_migrate.cu"]
 HEADERS = ["spk_internal.cuh", "spk_device.cuh", "spk_math.cuh", "spk_math2d.cuh", "spk_g2p2g2d_body.cuh", "spk_updater.cuh", "spk_g2p2g_kernel.cuh", "spk_g2p2g2d_kernel.cuh", "../../include/sparkl_abi.h"]
 LIB = os.path.join(HERE, "libsparkl_b200.so")
 LIB_2D = os.path.join(HERE, "libsparkl_b200_2d.so")

@@ -113,7 +113,7 @@ void free_particles(spk_ctx* c) {
     for (int b = 0; b < 2; ++b) {
         dev_free(c->pb[b].a0); dev_free(c->pb[b].a1); dev_free(c->pb[b].a2); dev_free(c->pb[b].a3); dev_free(c->pb[b].a4); dev_free(c->pb[b].a5);
     }
-    dev_free(c->vel); dev_free(c->cold); dev_free(c->slot_of); dev_free(c->rank_of); dev_free(c->perm);
+    dev_free(c->vel); dev_free(c->cold); dev_free(c->slot_of); dev_free(c->rank_of); dev_free(c->perm); dev_free(c->gid);
     c->cap = 0;
 }
 cudaError_t alloc_particles(spk_ctx* c, size_t cap) {
@@ -318,6 +318,38 @@ int upload_range(spk_ctx* c, const SpkParticleStatus* status, const SpkParticleP
 
 } // namespace
 
+// ---- internal entry points for spk_migrate.cu (device-resident counterparts of upload / read) ------------------------------
+cudaError_t spk_launch_pack_upload(spk_ctx* c, const void* d_status, const void* d_pos, const void* d_vel, const void* d_volume, const void* d_phase,
+                                   const void* d_data, size_t first, size_t n) {
+    if (n == 0) return cudaSuccess;
+    pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->pb[c->cur], c->vel, c->cold, (const SpkParticleStatus*)d_status, (const SpkParticlePosition*)d_pos,
+                                                                     (const SpkParticleVelocity*)d_vel, (const SpkParticleVolume*)d_volume, (const SpkParticlePhase*)d_phase,
+                                                                     (const SpkParticleData*)d_data, first, n, &c->d_counters->pad[0]);
+    c->launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t spk_launch_unpack(spk_ctx* c, int which, void* d_out, size_t n) {
+    if (n == 0) return cudaSuccess;
+    unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->pb[c->cur], c->vel, c->cold, nullptr, which, d_out, n);
+    c->launches += 1;
+    return cudaGetLastError();
+}
+// the bookkeeping of spk_particles_upload without the copy: capacity (reallocating DISCARDS the particle streams), counts, grid sizing
+int spk_particles_resize(spk_ctx* c, size_t n, bool fresh) {
+    if (n >= 0xffffffffull) return SPK_EOVERFLOW;
+    if (n > c->cap) { CK(cudaStreamSynchronize(c->stream)); CK(alloc_particles(c, n + n / 8 + 1024)); fresh = true; }
+    c->n = n;
+    if (fresh) c->cur = 0;
+    c->sorted_valid = false;
+    c->dt_cache_valid = false;
+    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (SPK_CELLS_PER_BLOCK * SPK_PARTICLES_PER_CELL * 50)) * 4u, 2048u);
+    GridBuffers& next = c->grid[1 - c->gcur];
+    if (c->dist_arena && want > c->dist_cap_hash) return SPK_EOVERFLOW; // the arena shared with the peers cannot grow
+    if (next.cap_hash < want) { CK(alloc_grid(c, next, want)); CK(ensure_slot_scratch(c, want)); }
+    CK(ensure_dispatch(c));
+    return SPK_OK;
+}
+
 // CudaParticleKernelsLauncher dispatch: the registered callbacks, else the default launches
 static int launch_g2p2g_hooked(spk_ctx* c, float dt) {
     if (c->launcher.launch_g2p2g) return c->launcher.launch_g2p2g(c->launcher.user, c, dt);
@@ -439,6 +471,7 @@ int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkP
     if (n >= 0xffffffffull) return SPK_EOVERFLOW;
     CK(cudaSetDevice(c->device));
     if (n > c->cap) CK(alloc_particles(c, n + n / 8 + 1024));
+    dev_free(c->gid); // a new particle set: global ids are the identity again (spk_particles_set_gids)
     c->n = n;
     c->cur = 0;
     c->sorted_valid = false;
@@ -495,6 +528,7 @@ int spk_particles_commit_staged(spk_ctx* c) {
     CK(cudaSetDevice(c->device));
     const size_t n = c->up_staged_n;
     if (n > c->cap) { CK(cudaStreamSynchronize(c->stream)); CK(alloc_particles(c, n + n / 8 + 1024)); }
+    if (c->gid) { CK(cudaStreamSynchronize(c->stream)); dev_free(c->gid); }
     c->n = n;
     c->cur = 0;
     c->sorted_valid = false;
@@ -603,6 +637,7 @@ int spk_particles_append(spk_ctx* c, const SpkParticleStatus* status, const SpkP
         for (size_t i = 0; i < n; ++i) d[old_n + i] = data ? data[i] : SpkParticleData{-0.01f, 1.0f, 1.0f, 0.0f};
         return spk_particles_upload(c, s.data(), p.data(), v.data(), vo.data(), ph.data(), d.data(), new_n);
     }
+    if (c->gid) { CK(cudaStreamSynchronize(c->stream)); dev_free(c->gid); } // host-side edits reset the global ids to the identity
     c->n = new_n;
     c->sorted_valid = false;
     c->dt_cache_valid = false;

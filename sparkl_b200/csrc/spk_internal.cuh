@@ -148,6 +148,7 @@ struct spk_ctx {
     uint32_t* slot_of; // hash slot of the particle's block (current order)
     uint32_t* rank_of; // rank inside its block
     uint32_t* perm;    // sorted index -> index in current order
+    uint32_t* gid;     // optional global particle ids (multi-GPU migration), indexed by particle id; NULL = identity
     bool sorted_valid; // perm/slot tables describe pb[cur]
     bool dt_cache_valid; // d_counters->dt_raw_bits describes pb[cur] (set by g2p2g, cleared by any particle/model edit)
     unsigned long long dt_acc_host; // GpuTimestepLength accumulator (host-authoritative)
@@ -208,6 +209,7 @@ cudaError_t spk_launch_fluids_volume(spk_ctx* c);             // spk_fluids.cu
 cudaError_t spk_launch_pack_upload(spk_ctx* c, const void* d_status, const void* d_pos, const void* d_vel, const void* d_volume,
                                    const void* d_phase, const void* d_data, size_t first, size_t n);
 cudaError_t spk_launch_unpack(spk_ctx* c, int which, void* d_out, size_t n);
+int spk_particles_resize(spk_ctx* c, size_t n, bool fresh);   // spk_api.cu: capacity / counts / grid sizing of an upload, without the copy
 cudaError_t spk_launch_grid_export(spk_ctx* c, int which_grid, SpkGpuGridNode* d_out, uint32_t nblocks);
 cudaError_t spk_launch_halo_keys(spk_ctx* c, unsigned long long* out, uint32_t capacity);
 cudaError_t spk_launch_halo_tag(spk_ctx* c, const unsigned long long* remote, uint32_t n);

@@ -281,3 +281,56 @@ def migrate(engine, gids: np.ndarray, partition: SlabPartition, dist=None, devic
     else:
         new_gids = np.asarray(gids, np.uint32)
     return new_gids, n_sent, n_recv
+
+
+def migrate_device(ctx, partition: SlabPartition, dist=None, device=None, wire=None):
+    """Collective.  The device-side counterpart of `migrate` for a SingleGpuMpmContext (dim3): the leaving particles are packed
+    into 128-byte rows by the GPU (`spk_particles_migrate_out`: stable partition by destination slab), the rows travel between the
+    ranks' device buffers (`torch.distributed` send / recv: NCCL over NVLink), and the arrivals are appended on the device
+    (`spk_particles_migrate_in`).  Only the per-destination counts cross PCIe; global ids live in the context (`ctx.set_gids`,
+    `ctx.read_gids`).  When nothing moves anywhere no particle state is touched and the sort state stays valid.  `wire` (default:
+    `device`) is where the rows sit during the exchange: the CPU when the process group is gloo (tests on one GPU), which cannot
+    send CUDA tensors.  Returns (number sent, number received)."""
+    import torch
+    import torch.distributed as tdist
+    dist = dist or tdist
+    device = device if device is not None else torch.device("cuda", ctx.device)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    assert partition.world == world
+    row = PARTICLE_RECORD.itemsize
+    counts = ctx.migrate_out(partition.bounds, rank)  # count only
+    mine = torch.tensor(counts.astype(np.int64), dtype=torch.int64, device=device)
+    table = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(table, mine)
+    table = torch.stack(table).cpu().numpy()  # table[src, dst]
+    n_sent, n_recv = int(table[rank].sum()), int(table[:, rank].sum())
+    if table.sum() == 0:
+        return 0, 0
+    send = torch.empty(max(n_sent, 1) * row, dtype=torch.uint8, device=device)
+    if n_sent:
+        again = ctx.migrate_out(partition.bounds, rank, send.data_ptr(), n_sent)
+        assert np.array_equal(again, counts)
+    offs = np.concatenate([[0], np.cumsum(table[rank])]) * row  # rows are grouped by destination rank
+    recv = torch.empty(max(n_recv, 1) * row, dtype=torch.uint8, device=device)
+    roffs = np.concatenate([[0], np.cumsum(table[:, rank])]) * row
+    wire = wire if wire is not None else device
+    staged = wire != device
+    wsend = send.to(wire) if staged else send
+    wrecv = torch.empty_like(recv, device=wire) if staged else recv
+    ops = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if table[rank, peer]:
+            ops.append(dist.P2POp(dist.isend, wsend[int(offs[peer]):int(offs[peer + 1])], peer))
+        if table[peer, rank]:
+            ops.append(dist.P2POp(dist.irecv, wrecv[int(roffs[peer]):int(roffs[peer + 1])], peer))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if staged:
+        recv.copy_(wrecv)
+    if device.type == "cuda":
+        torch.cuda.current_stream(device).synchronize()  # the rows have landed before the context's stream reads them
+    ctx.migrate_in(recv.data_ptr() if n_recv else 0, n_recv)  # n_recv == 0: marks the set as edited (same path on every rank)
+    return n_sent, n_recv

@@ -100,6 +100,29 @@ class SingleGpuMpmContext(Engine):
     def read_wait(self):
         self._call("particles_read_wait")
 
+    # ---- device-side particle migration (sparkl_b200/distributed.py::migrate_device drives it) ----------
+    def set_gids(self, gids):
+        """global ids of the local particles, by particle id (default: the identity); reset by upload / append / remove_range"""
+        g = np.ascontiguousarray(gids, np.uint32)
+        self._call("particles_set_gids", _ptr(g), len(g))
+
+    def read_gids(self) -> np.ndarray:
+        out = np.empty(len(self), np.uint32)
+        self._call("particles_read_gids", _ptr(out), len(out))
+        return out
+
+    def migrate_out(self, bounds, rank: int, dev_records: int = 0, capacity: int = 0) -> np.ndarray:
+        """spk_particles_migrate_out: `bounds` = world + 1 increasing block-x coordinates; `dev_records` = DEVICE address of a
+        buffer of `capacity` 128-byte rows, or 0 to count only.  Returns the number of rows per destination rank."""
+        b = np.ascontiguousarray(bounds, np.int64)
+        counts = np.zeros(len(b) - 1, np.uint32)
+        self._call("particles_migrate_out", _ptr(b), len(b) - 1, rank, C.c_void_p(dev_records or None), capacity, _ptr(counts))
+        return counts
+
+    def migrate_in(self, dev_records: int, n: int):
+        """spk_particles_migrate_in: append `n` rows from DEVICE memory"""
+        self._call("particles_migrate_in", C.c_void_p(dev_records or None), n)
+
     def g2p2g_time(self, enable: bool = True):
         """(summed g2p2g kernel time in ms, launches) since the previous call, measured with CUDA events recorded on the
         context's stream without synchronising; `enable` arms / disarms the recording for the launches that follow"""

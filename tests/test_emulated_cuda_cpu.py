@@ -77,6 +77,84 @@ def test_fluids_volume_recomputation_on_the_emulation(emulated, oracle):
     T.test_fluids_volume_recomputation_dim2()
 
 
+def test_device_side_migration_on_the_emulation(emulated):
+    import tests.test_zmigration_gpu as T
+    for k in (0, 3):
+        T.test_migrate_out_is_a_stable_partition_and_in_appends(k)
+    T.test_simulation_goes_on_from_a_migrated_set()
+    T.test_migrate_in_grows_on_the_device()
+    T.test_migration_argument_errors()
+
+
+def _emulated_migration_worker(rank, world, port, nframes, out_dir):
+    """one rank of a 2-process run of the PRODUCT (emulated library) over gloo: host-staged halo exchange through the stage calls
+    (DistributedMpmPipeline) + device-side migration (migrate_device) after every frame"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import build_emu
+    from sparkl_b200 import _lib
+    _lib.LIB_PATH, _lib.LIB2D_PATH, _lib._LIBS, _lib._LIB = build_emu.build(3), build_emu.build(2), {}, None
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sparkl_b200 import abi
+        from sparkl_b200.distributed import DistributedMpmPipeline, SlabPartition, migrate_device
+        from sparkl_b200.pipeline import SingleGpuMpmContext
+        from tests.test_distributed_cpu import _migration_scene
+        sc = _migration_scene()
+        part = SlabPartition([-(1 << 40), -1, 1 << 40])
+        owner = part.owner(sc.particles.position["point"][:, 0], sc.cell_width)
+        gids = np.nonzero(owner == rank)[0].astype(np.uint32)
+        e = SingleGpuMpmContext(sc.cell_width)
+        e.models_upload(sc.models); e.colliders_upload(sc.colliders)
+        e.upload(sc.particles.take(gids))
+        e.set_gids(gids)
+        cpu = torch.device("cpu")
+        pipe = DistributedMpmPipeline(e, dist, cpu)
+        moved = 0
+        for _ in range(nframes):
+            pipe.step(sc.params, sc.gravity)
+            sent, recv = migrate_device(e, part, dist, cpu)
+            moved += sent
+            assert (part.owner(e.read(abi.ATTR_POSITION)["point"][:, 0], sc.cell_width) == rank).all()
+        pc = e.read_all()
+        np.savez(os.path.join(out_dir, f"mig{rank}.npz"), ids=e.read_gids(), pos=pc.position, vel=pc.velocity, vol=pc.volume, moved=moved)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_ranks_with_device_side_migration_on_the_emulation(tmp_path, oracle):
+    """world_size-2 gloo run of the product's own code (emulated): the particles that cross the slab boundary are re-homed by
+    spk_particles_migrate_out / _in, and the union of the two ranks equals the single-rank oracle run"""
+    import numpy as np
+    import torch.multiprocessing as mp
+    import build_emu
+    from sparkl_b200 import abi
+    from tests import util
+    from tests.test_distributed_cpu import _free_port, _migration_scene
+    build_emu.build(3); build_emu.build(2)  # before the workers race to build them
+    nframes = 4
+    mp.spawn(_emulated_migration_worker, args=(2, _free_port(), nframes, str(tmp_path)), nprocs=2, join=True)
+    sc = _migration_scene()
+    e = oracle.OracleEngine(sc.cell_width)
+    e.models_upload(sc.models); e.colliders_upload(sc.colliders); e.upload(sc.particles)
+    for _ in range(nframes):
+        e.step(sc.params, sc.gravity)
+    ref = e.read_all()
+    r = [np.load(tmp_path / f"mig{k}.npz") for k in range(2)]
+    assert int(r[0]["moved"]) + int(r[1]["moved"]) > 0
+    ids = np.concatenate([r[0]["ids"], r[1]["ids"]])
+    assert np.array_equal(np.sort(ids), np.arange(len(ref)))
+    pos = np.zeros(len(ref), abi.POSITION); vel = np.zeros(len(ref), abi.VELOCITY); vol = np.zeros(len(ref), abi.VOLUME)
+    for k in range(2):
+        pos[r[k]["ids"]], vel[r[k]["ids"]], vol[r[k]["ids"]] = r[k]["pos"], r[k]["vel"], r[k]["vol"]
+    assert util.rel_err(pos["point"], ref.position["point"]) < 2e-5
+    assert util.rel_err(vel["vector"], ref.velocity["vector"], floor=1e-2) < 2e-3
+    assert util.rel_err(vol["deformation_gradient"], ref.volume["deformation_gradient"], floor=1.0) < 2e-4
+
+
 # ---------------------------------------------------------------------------------------------- product vs the reference's own kernels (fixtures)
 def _golden_cases():
     from tests import util

@@ -1,0 +1,182 @@
+"""Device-side particle migration: spk_particles_migrate_out / _in against a numpy restatement of the stable
+partition, and the simulation going on from the migrated set.  The same bodies run on the CUDA emulation in the CPU suite
+(tests/test_emulated_cuda_cpu.py), where "device memory" is host memory."""
+import numpy as np
+import pytest
+
+from sparkl_b200 import abi, scenes
+from sparkl_b200.distributed import PARTICLE_RECORD, SlabPartition, pack_records
+
+pytestmark = pytest.mark.gpu
+
+
+class _DevBuf:
+    """`nbytes` of device memory (CUDA when there is a GPU; host memory under the emulation, whose device pointers are host pointers)"""
+
+    def __init__(self, nbytes):
+        import torch
+        self.t = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device="cuda" if torch.cuda.is_available() else "cpu")
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+    def rows(self, n):
+        return self.t.cpu().numpy()[: n * PARTICLE_RECORD.itemsize].view(PARTICLE_RECORD).copy()
+
+    def fill(self, rec):
+        import torch
+        raw = torch.from_numpy(np.ascontiguousarray(rec).view(np.uint8).copy())
+        self.t[: len(raw)] = raw.to(self.t.device)
+        if self.t.is_cuda:
+            torch.cuda.synchronize()  # torch's stream is not the context's
+
+
+def _scene():
+    return scenes.jitter(scenes.sand3(12, 6, 8), 0.02, seed=11)
+
+
+def _expected_partition(pc, gids, part, rank, h):
+    owner = part.owner(pc.position["point"][:, 0], h)
+    rec = pack_records(pc, gids)
+    leaving = np.concatenate([rec[owner == r] for r in range(part.world) if r != rank])
+    counts = np.array([0 if r == rank else int((owner == r).sum()) for r in range(part.world)], np.uint32)
+    return rec[owner == rank], leaving, counts
+
+
+def _assert_rows_equal(a, b, what):
+    assert len(a) == len(b), what
+    for name in PARTICLE_RECORD.names:
+        assert np.array_equal(a[name], b[name]), f"{what}: {name}"
+
+
+@pytest.mark.parametrize("after_substeps", [0, 3])
+def test_migrate_out_is_a_stable_partition_and_in_appends(after_substeps):
+    from sparkl_b200.pipeline import context_from_scene
+    sc = _scene()
+    g = context_from_scene(sc)
+    n = len(sc.particles)
+    gids = (np.arange(n, dtype=np.uint32) * 7 + 3).astype(np.uint32)
+    g.set_gids(gids)
+    if after_substeps:  # the physical order is then the block-sorted one, not the id order
+        p = abi.SolverParameters(max_substep_dt=1.0e-3, max_num_substeps=after_substeps)
+        p.dt = after_substeps * 1.0e-3
+        g.step(p, sc.gravity)
+        assert np.array_equal(g.read_gids(), gids)
+    pc = g.read_all()
+    x = pc.position["point"][:, 0]
+    bx = SlabPartition.block_x(x, sc.cell_width)
+    lo, hi = int(np.quantile(bx, 0.3)), int(np.quantile(bx, 0.7))
+    part = SlabPartition([-(1 << 40), lo, max(hi, lo + 1), 1 << 40])
+    stay, leaving, counts = _expected_partition(pc, gids, part, 1, sc.cell_width)
+    assert counts[0] > 0 and counts[2] > 0 and len(stay) > 0
+    # count only: nothing changes
+    assert np.array_equal(g.migrate_out(part.bounds, 1), counts)
+    assert len(g) == n
+    # too small a buffer: SPK_EOVERFLOW, nothing changes
+    small = _DevBuf(PARTICLE_RECORD.itemsize)
+    with pytest.raises(abi.SparklError) as e:
+        g.migrate_out(part.bounds, 1, small.ptr, 1)
+    assert e.value.code == abi.EOVERFLOW and len(g) == n
+    _assert_rows_equal(pack_records(g.read_all(), g.read_gids()), pack_records(pc, gids), "state after the refused call")
+    # the real thing
+    buf = _DevBuf(len(leaving) * PARTICLE_RECORD.itemsize)
+    assert np.array_equal(g.migrate_out(part.bounds, 1, buf.ptr, len(leaving)), counts)
+    _assert_rows_equal(buf.rows(len(leaving)), leaving, "records (grouped by destination, ascending id)")
+    _assert_rows_equal(pack_records(g.read_all(), g.read_gids()), stay, "residents (relative order kept, dense ids)")
+    # nobody leaves now: a no-op
+    assert not g.migrate_out(part.bounds, 1, buf.ptr, len(leaving)).any() and len(g) == len(stay)
+    # and back in: appended after the residents, in row order
+    g.migrate_in(buf.ptr, len(leaving))
+    _assert_rows_equal(pack_records(g.read_all(), g.read_gids()), np.concatenate([stay, leaving]), "after migrate_in")
+
+
+def test_simulation_goes_on_from_a_migrated_set():
+    """the set assembled on the device by migrate_out + migrate_in behaves like the same arrays uploaded from the host"""
+    from sparkl_b200.pipeline import context_from_scene
+    sc = _scene()
+    g = context_from_scene(sc)
+    p = abi.SolverParameters(max_substep_dt=1.0e-3)
+    g.step(p, sc.gravity)
+    bx = SlabPartition.block_x(g.read(abi.ATTR_POSITION)["point"][:, 0], sc.cell_width)
+    part = SlabPartition([-(1 << 40), int(np.median(bx)), 1 << 40])
+    n_leave = int(g.migrate_out(part.bounds, 0)[1])
+    assert 0 < n_leave < len(g)
+    buf = _DevBuf(n_leave * PARTICLE_RECORD.itemsize)
+    g.migrate_out(part.bounds, 0, buf.ptr, n_leave)
+    g.migrate_in(buf.ptr, n_leave)
+    pc = g.read_all()
+    f = context_from_scene(sc)
+    f.upload(pc)
+    # `g` still holds the grid of the step before the migration, `f` starts from an empty one: give both the same history
+    # by stepping each once from here and comparing after a second step would mix the two effects, so compare the particle
+    # update of ONE step driven by the same (empty-history) grid instead: a fresh context for both
+    g2 = context_from_scene(sc)
+    rows = pack_records(pc, g.read_gids())
+    up = _DevBuf(len(rows) * PARTICLE_RECORD.itemsize)
+    up.fill(rows)
+    g2.remove_range(0, len(g2))
+    g2.migrate_in(up.ptr, len(rows))  # the whole set arrives through the device path (and grows the buffers on the device)
+    assert len(g2) == len(f) and np.array_equal(g2.read_gids(), g.read_gids())
+    for _ in range(2):
+        f.step(p, sc.gravity)
+        g2.step(p, sc.gravity)
+    a, b = f.read_all(), g2.read_all()
+    from tests import util
+    assert util.rel_err(a.position["point"], b.position["point"]) < 2e-6
+    assert util.rel_err(a.velocity["vector"], b.velocity["vector"], floor=1e-2) < 2e-4
+    assert util.rel_err(a.volume["deformation_gradient"], b.volume["deformation_gradient"], floor=1.0) < 2e-5
+
+
+def test_migrate_in_grows_on_the_device():
+    from sparkl_b200.pipeline import SingleGpuMpmContext
+    sc = _scene()
+    small = sc.particles.take(np.arange(64))
+    g = SingleGpuMpmContext(sc.cell_width)
+    g.models_upload(sc.models); g.colliders_upload(sc.colliders)
+    g.upload(small)
+    g.set_gids(np.arange(64, dtype=np.uint32) + 1000)
+    rest = sc.particles.take(np.arange(64, len(sc.particles)))  # far more than the capacity reserved for 64 particles
+    rows = pack_records(rest, np.arange(len(rest), dtype=np.uint32) + 5000)
+    buf = _DevBuf(len(rows) * PARTICLE_RECORD.itemsize)
+    buf.fill(rows)
+    g.migrate_in(buf.ptr, len(rows))
+    want = np.concatenate([pack_records(small, np.arange(64, dtype=np.uint32) + 1000), rows])
+    _assert_rows_equal(pack_records(g.read_all(), g.read_gids()), want, "after the device-side growth")
+    g.step(abi.SolverParameters(max_substep_dt=1.0e-3), sc.gravity)  # and it runs
+    assert np.isfinite(g.read(abi.ATTR_POSITION)["point"]).all()
+
+
+def test_migration_argument_errors():
+    from sparkl_b200.pipeline import context_from_scene
+    g = context_from_scene(_scene())
+    for bad in ([0, 0, 5], [3, 2, 5]):  # bounds must increase
+        with pytest.raises(abi.SparklError) as e:
+            g.migrate_out(bad, 0)
+        assert e.value.code == abi.EINVAL
+    with pytest.raises(abi.SparklError) as e:
+        g.migrate_out([0, 5, 10], 2)  # rank outside the world
+    assert e.value.code == abi.EINVAL
+    with pytest.raises(abi.SparklError) as e:
+        g.set_gids(np.arange(3, dtype=np.uint32))  # one id per particle
+    assert e.value.code == abi.EINVAL
+
+
+def test_device_side_migration_on_the_peer_memory_path():
+    """two ranks on the NVLink peer-memory halo path (sharing cuda:0, gloo for the row exchange), a kinematic block pushed across
+    the slab boundary, `distributed.migrate_device` after every frame: same positions as the single-context run, nobody lost
+    (scripts/check_migration_gpu.py with SPK_MIGRATE=device)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPK_CHECK_ONE_GPU="1", SPK_MIGRATE="device", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29581", os.path.join(root, "scripts", "check_migration_gpu.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=root)
+    out = r.stdout + r.stderr
+    if "devices are busy or unavailable" in out or "exclusive" in out.lower():
+        pytest.skip("the GPU is in exclusive-process compute mode: two processes cannot share it")
+    assert r.returncode == 0, out[-3000:]
+    line = [l for l in out.splitlines() if "migration check" in l]
+    assert line and "device-side" in line[-1] and line[-1].rstrip().endswith("OK"), out[-3000:]
