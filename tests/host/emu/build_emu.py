@@ -40,20 +40,22 @@ def transform(text: str) -> str:
     return text.replace('#include "../../include/sparkl_abi.h"', f'#include "{os.path.join(ROOT, "include", "sparkl_abi.h")}"')
 
 
-def lib_path(dim: int) -> str:
-    return os.path.join(OUT_DIR, "libsparkl_b200_emu.so" if dim == 3 else "libsparkl_b200_emu_2d.so")
+def lib_path(dim: int, tag: str = "") -> str:
+    return os.path.join(OUT_DIR, f"libsparkl_b200_emu{tag}.so" if dim == 3 else f"libsparkl_b200_emu{tag}_2d.so")
 
 
-def build(dim: int = 3, force: bool = False) -> str:
+def build(dim: int = 3, force: bool = False, tag: str = "", extra_flags=()) -> str:
+    """`tag` / `extra_flags`: instrumented variants (e.g. tag="_asan", extra_flags=["-fsanitize=address", "-g"])"""
+    extra_flags = list(extra_flags)
     sys.path.insert(0, ROOT)
     from sparkl_b200 import build as pb
     sources = pb.SOURCES if dim == 3 else pb.SOURCES_2D
-    out = lib_path(dim)
+    out = lib_path(dim, tag)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "build_emu.py")]
     deps.append(os.path.join(ROOT, "include", "sparkl_abi.h"))
     if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(d) for d in deps):
         return out
-    src_dir = os.path.join(HERE, f"_src{dim}")
+    src_dir = os.path.join(HERE, f"_src{dim}{tag}")
     os.makedirs(src_dir, exist_ok=True)
     for f in os.listdir(CSRC):
         if f.endswith((".cu", ".cuh")):
@@ -63,6 +65,7 @@ def build(dim: int = 3, force: bool = False) -> str:
                 fh.write(text)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-DSPK_EMU", f"-DSPK_DIM={dim}", "-I" + cuda_inc, "-I" + HERE, "-include", "cuda_emu.h"]
+    flags += extra_flags
     objs = []
     for s in list(sources) + ["cuda_emu"]:
         src = os.path.join(HERE, "cuda_emu.cpp") if s == "cuda_emu" else os.path.join(src_dir, s.replace(".cu", ".cpp"))
@@ -72,7 +75,7 @@ def build(dim: int = 3, force: bool = False) -> str:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError(f"emulation build failed on {s}")
         objs.append(obj)
-    subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", out] + objs)
+    subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", out] + [f for f in extra_flags if f.startswith("-fsanitize")] + objs)
     return out
 
 

@@ -124,7 +124,14 @@ cudaError_t cudaSetDevice(int dev) { return dev == 0 ? cudaSuccess : cudaErrorIn
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* p, int) { std::memset(p, 0, sizeof(*p)); p->major = 10; p->minor = 0; p->multiProcessorCount = 148; return cudaSuccess; }
-cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// device memory comes back zeroed by default; SPK_EMU_POISON=<byte> fills it with that byte instead (cudaMalloc returns garbage on a
+// GPU: tests/test_emulated_cuda_cpu.py runs the parity bodies with poisoned allocations to catch reads of uninitialised memory)
+cudaError_t cudaMalloc(void** p, size_t n) {
+    static const char* poison = std::getenv("SPK_EMU_POISON");
+    *p = std::calloc(n ? n : 1, 1);
+    if (*p && poison) std::memset(*p, (int)std::strtol(poison, nullptr, 0), n ? n : 1);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }

@@ -23,8 +23,11 @@ def emulated(monkeypatch):
     """route sparkl_b200._lib.lib(dim) to the emulated libraries for the duration of one test"""
     import build_emu
     from sparkl_b200 import _lib
-    monkeypatch.setattr(_lib, "LIB_PATH", build_emu.build(3))
-    monkeypatch.setattr(_lib, "LIB2D_PATH", build_emu.build(2))
+    kw = {}
+    if os.environ.get("SPK_EMU_ASAN") == "1":  # AddressSanitizer build: run pytest with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+        kw = dict(tag="_asan", extra_flags=["-fsanitize=address", "-fno-omit-frame-pointer", "-g"])
+    monkeypatch.setattr(_lib, "LIB_PATH", build_emu.build(3, **kw))
+    monkeypatch.setattr(_lib, "LIB2D_PATH", build_emu.build(2, **kw))
     monkeypatch.setattr(_lib, "_LIBS", {})
     monkeypatch.setattr(_lib, "_LIB", None)
     yield _lib
@@ -248,3 +251,19 @@ def test_cpp_host_example_builds_and_matches_the_python_host(emulated, tmp_path)
         exe2 = str(tmp_path / "sand_column")
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + inc, src, "-o", exe2, real, "-Wl,-rpath," + os.path.dirname(real)])
         assert subprocess.run([exe2, "4", "2", "2", "1"], capture_output=True).returncode == 10
+
+
+@pytest.mark.timeout(600)
+def test_no_kernel_depends_on_zeroed_allocations():
+    """cudaMalloc returns garbage on a GPU but calloc'ed memory here: re-run a cross-section of the bodies above in a subprocess whose
+    emulated cudaMalloc fills every allocation with 0xff bytes (NaN floats, all-ones integers).  scripts/emu_sanitize.sh runs the whole
+    module this way (two poison bytes) and under AddressSanitizer."""
+    import subprocess
+    if os.environ.get("SPK_EMU_POISON"):
+        pytest.skip("already running poisoned")
+    picks = ("test_sand_first_substeps or test_fluid_dam_break or test_sand_on_heightfield_ground or test_elasticity2_lockstep or "
+             "fluids_volume or device_side_migration_on or test_ragged_blocks or sand3_jitter")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", picks, "-p", "no:cacheprovider"],
+                       env=dict(os.environ, SPK_EMU_POISON="0xff"), capture_output=True, text=True, cwd=ROOT, timeout=580)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert " passed" in r.stdout and "no tests ran" not in r.stdout
