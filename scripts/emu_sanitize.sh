@@ -12,3 +12,5 @@ for b in 0xff 0x7b; do
     echo "== poisoned allocations ($b)"
     SPK_EMU_POISON=$b python -m pytest tests/test_emulated_cuda_cpu.py -x -q
 done
+echo "== reversed thread / CTA schedule (a read that misses a barrier or a __syncwarp passes in one order and fails in the other)"
+SPK_EMU_SCHEDULE=reverse python -m pytest tests/test_emulated_cuda_cpu.py -x -q

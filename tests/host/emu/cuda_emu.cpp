@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 namespace emu {
@@ -51,9 +52,13 @@ void run_cta(unsigned nthreads) {
         makecontext(&f.ctx, trampoline, 0);
         f.state = READY;
     }
+    // SPK_EMU_SCHEDULE=reverse runs the ready threads of a CTA (and the CTAs of a grid) in descending order: a read that is missing a
+    // barrier after another thread's write passes in one order and fails in the other
+    static const bool reverse = std::getenv("SPK_EMU_SCHEDULE") && std::string(std::getenv("SPK_EMU_SCHEDULE")) == "reverse";
     for (;;) {
         bool ran = false;
-        for (unsigned t = 0; t < nthreads; ++t) {
+        for (unsigned k = 0; k < nthreads; ++k) {
+            const unsigned t = reverse ? nthreads - 1 - k : k;
             if (fibers[t].state != READY) continue;
             cur = (int)t;
             tid = Idx{t, 0, 0};
@@ -105,8 +110,9 @@ void launch(unsigned grid, unsigned block, const std::function<void()>& body) {
     body_fn = &body;
     gdim = Idx{grid, 1, 1};
     bdim = Idx{block, 1, 1};
-    for (unsigned b = 0; b < grid; ++b) {
-        bid = Idx{b, 0, 0};
+    static const bool reverse = std::getenv("SPK_EMU_SCHEDULE") && std::string(std::getenv("SPK_EMU_SCHEDULE")) == "reverse";
+    for (unsigned k = 0; k < grid; ++k) {
+        bid = Idx{reverse ? grid - 1 - k : k, 0, 0};
         run_cta(block);
     }
     cur = -1;
