@@ -44,6 +44,8 @@ class DistributedMpmPipeline:
         self.cuda = self.device.type == "cuda"
         self.stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=self.device) if self.cuda else None
         self.key_cap = int(key_capacity)  # agreed capacity of the active-key exchange (blocks per rank)
+        # accumulated floats per block on the wire: 6 channels x 4^DIM cells (HaloBlockData minus the unsummed fields)
+        self.payload_floats = 6 * (16 if getattr(ctx, "dim", 3) == 2 else 64)
         z = lambda *shape, dt: torch.zeros(shape, dtype=dt, device=self.device)
         self._keys = z(self.key_cap, dt=torch.int64)
         self._allkeys = z(self.world, self.key_cap, dt=torch.int64)
@@ -71,9 +73,9 @@ class DistributedMpmPipeline:
         torch = self.torch
         self._halo_cap = cap
         self._hk = torch.zeros(cap, dtype=torch.int64, device=self.device)
-        self._hp = torch.zeros((cap, BLOCK_PAYLOAD_FLOATS), dtype=torch.float32, device=self.device)
+        self._hp = torch.zeros((cap, self.payload_floats), dtype=torch.float32, device=self.device)
         self._allhk = torch.zeros((self.world, cap), dtype=torch.int64, device=self.device)
-        self._allhp = torch.zeros((self.world, cap, BLOCK_PAYLOAD_FLOATS), dtype=torch.float32, device=self.device)
+        self._allhp = torch.zeros((self.world, cap, self.payload_floats), dtype=torch.float32, device=self.device)
 
     def _others(self, t2d):
         """the two contiguous row ranges of a [world, ...] buffer that belong to the OTHER ranks"""
@@ -126,7 +128,7 @@ class DistributedMpmPipeline:
                 for pk, pp in zip(self._others(allhk), self._others(allhp)):
                     ctx._call("halo_merge", vp(pk.data_ptr()), vp(pp.data_ptr()), int(pk.numel()))
             self.halo_blocks_last = int(nh.value)
-            self.halo_bytes_last = int(nh.value) * (8 + 4 * BLOCK_PAYLOAD_FLOATS)
+            self.halo_bytes_last = int(nh.value) * (8 + 4 * self.payload_floats)
             ctx.stage_grid_update(dt, gravity)
         return dt
 

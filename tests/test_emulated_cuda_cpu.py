@@ -253,6 +253,71 @@ def test_cpp_host_example_builds_and_matches_the_python_host(emulated, tmp_path)
         assert subprocess.run([exe2, "4", "2", "2", "1"], capture_output=True).returncode == 10
 
 
+def _dim2_scene():
+    from sparkl_b200 import scenes2d
+    return scenes2d.jitter(scenes2d.elasticity2(2, scale=0.3), 0.002, seed=9)
+
+
+def _emulated_dim2_worker(rank, world, port, nframes, out_dir):
+    """one rank of a 2-process run of the dim2 PRODUCT (emulated libsparkl_b200_2d) over gloo through the portable halo protocol"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import build_emu
+    from sparkl_b200 import _lib
+    _lib.LIB_PATH, _lib.LIB2D_PATH, _lib._LIBS, _lib._LIB = build_emu.build(3), build_emu.build(2), {}, None
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sparkl_b200.distributed import DistributedMpmPipeline
+        from sparkl_b200.pipeline import SingleGpuMpmContext
+        sc = _dim2_scene()
+        ids = np.arange(len(sc.particles))[rank::world].copy()  # interleaved ownership: every block is shared (any ownership is valid, SURVEY §8e)
+        e = SingleGpuMpmContext(sc.cell_width, dim=2)
+        e.models_upload(sc.models); e.colliders_upload(sc.colliders)
+        e.upload(sc.particles.take(ids))
+        pipe = DistributedMpmPipeline(e, dist, torch.device("cpu"))
+        assert pipe.payload_floats == 96
+        halo = 0
+        for _ in range(nframes):
+            pipe.step(sc.params, sc.gravity)
+            halo = max(halo, pipe.halo_blocks_last)
+        pc = e.read_all()
+        np.savez(os.path.join(out_dir, f"d2_{rank}.npz"), ids=ids, pos=pc.position, vel=pc.velocity, vol=pc.volume, halo=halo)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_ranks_dim2_on_the_emulation(tmp_path):
+    """the dim2 build on the portable multi-process path (spk_halo_* of spk_grid2d.cu, 96 floats per shared block): two gloo ranks
+    with interleaved particle ownership against the single-rank dim2 oracle run"""
+    import numpy as np
+    import torch.multiprocessing as mp
+    import build_emu
+    from oracle import binding as ob
+    from sparkl_b200 import abi2d
+    from tests import util
+    from tests.test_distributed_cpu import _free_port
+    build_emu.build(3); build_emu.build(2)
+    nframes = 2
+    mp.spawn(_emulated_dim2_worker, args=(2, _free_port(), nframes, str(tmp_path)), nprocs=2, join=True)
+    sc = _dim2_scene()
+    e = ob.OracleEngine2D(sc.cell_width)
+    e.models_upload(sc.models); e.colliders_upload(sc.colliders); e.upload(sc.particles)
+    for _ in range(nframes):
+        e.step(sc.params, sc.gravity)
+    ref = e.read_all()
+    r = [np.load(tmp_path / f"d2_{k}.npz") for k in range(2)]
+    assert int(r[0]["halo"]) > 0 and int(r[1]["halo"]) > 0
+    pos = np.zeros(len(ref), abi2d.POSITION); vel = np.zeros(len(ref), abi2d.VELOCITY); vol = np.zeros(len(ref), abi2d.VOLUME)
+    for k in range(2):
+        pos[r[k]["ids"]], vel[r[k]["ids"]], vol[r[k]["ids"]] = r[k]["pos"], r[k]["vel"], r[k]["vol"]
+    assert util.rel_err(pos["point"], ref.position["point"]) < 2e-5
+    assert util.rel_err(vel["vector"], ref.velocity["vector"], floor=1e-2) < 2e-3
+    assert util.rel_err(vol["deformation_gradient"], ref.volume["deformation_gradient"], floor=1.0) < 2e-4
+
+
 @pytest.mark.timeout(600)
 def test_no_kernel_depends_on_zeroed_allocations():
     """cudaMalloc returns garbage on a GPU but calloc'ed memory here: re-run a cross-section of the bodies above in a subprocess whose
