@@ -189,9 +189,9 @@ typedef struct SpkGpuCollider {
 } SpkGpuCollider;
 #else
 /* dim2 GpuCollider (same Rust definition, src_kernels/gpu_collider.rs:203-212, with parry2d shapes and an Isometry2).
- * Cuboid (tag 0), HeightField (tag 1) and Polyline (tag 3); TriMesh does not exist in 2D.  The byte image of the reference's dim2 enum
- * depends on parry2d's CUDA pointer types and was NOT recovered from sparkl2d-kernels.ptx: this layout is this library's own
- * (field order and meaning as in the Rust struct; the polyline payload is a HOST description like the 3D one). */
+ * Cuboid (tag 0), HeightField (tag 1) and Polyline (tag 3).  The reference's own dim2 image is 280 bytes and holds parry2d's CUDA
+ * pointer types (recovered from sparkl2d-kernels.ptx: oracle/ref_harness.cpp, ref_colliders_upload); this 72-byte layout is this
+ * library's own: field order and meaning as in the Rust struct, heightfield / polyline payloads as HOST descriptions like the 3D ones. */
 typedef struct SpkGpuCollider {
     uint32_t shape_tag; uint32_t _pad0;
     union {

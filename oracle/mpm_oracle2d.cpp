@@ -16,10 +16,10 @@
 // path; its dim2 kernels (resources/sparkl2d-kernels.ptx, assembled for sm_100a and driven by the -DSPK_DIM=2 build of
 // oracle/ref_harness.cpp) were run on a B200 on ten seeded scenes (every constitutive / plastic / failure model) and their outputs
 // are committed as tests/golden/*2.npz: this file reproduces them to ~1e-6 relative (tests/test_golden_cpu.py), and product, oracle
-// and reference kernels run in lock-step in tests/test_dim2_gpu.py.  NOT pinned against the reference: the collider branch of
-// grid_update in dim2 (the byte image of the dim2 GpuCollider / parry2d shapes was not recovered, so the harness cannot upload
-// colliders); there the pins are the shared code path with the 3D oracle, brute-force geometry checks and the x <-> y symmetry
-// tests of tests/test_dim2_cpu.py.
+// and reference kernels run in lock-step in tests/test_dim2_gpu.py.  NOT YET pinned against the reference: the collider branch of
+// grid_update in dim2 (the 280-byte dim2 GpuCollider image has been recovered from the PTX and the harness builds it, but the
+// three-way collider tests have not run on a GPU yet: SPK_RUN_UNVERIFIED=1); until then the pins are the shared code path with the
+// 3D oracle, brute-force geometry checks and the x <-> y symmetry tests of tests/test_dim2_cpu.py.
 #define SPK_DIM 2
 #include "../include/sparkl_abi.h"
 

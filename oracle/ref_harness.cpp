@@ -31,8 +31,7 @@
 // The same file builds the dim2 harness (-DSPK_DIM=2 -> oracle/_ref/libref_harness2d.so driving resources/sparkl2d-kernels.ptx):
 // the kernels take the same parameter blocks in both dimensions (checked against the .entry declarations of both PTX files);
 // what changes is the block shape (4x4 threads, 16 nodes of 56 bytes per block), G2P2G_THREADS (64, src_kernels/cuda/mod.rs:12-13),
-// the particle struct sizes and the 8-byte gravity vector.  The dim2 GpuCollider byte image was not recovered, so the dim2
-// harness only runs collider-free scenes.
+// the particle struct sizes, the 8-byte gravity vector and the 280-byte GpuCollider image (see ref_colliders_upload).
 #if SPK_DIM == 2
 #define REF_CELLS 16u
 #define REF_BLOCK_Z 1u
@@ -351,7 +350,64 @@ int ref_colliders_upload(ref_ctx* c, const SpkGpuCollider* cols, size_t n) {
     if (!c) return SPK_EINVAL;
     CU(D.p_cuCtxSetCurrent(c->ctx));
 #if SPK_DIM == 2
-    if (n) return SPK_EUNSUPPORTED; // the byte image of the dim2 GpuCollider was not recovered: collider-free scenes only
+    // The reference's dim2 GpuCollider image (280 bytes), recovered from the ld.global offsets of `grid_update` in
+    // resources/sparkl2d-kernels.ptx (collider loop: `add.s64 ..., 280` :9562-9563; BoundaryHandling::None test `[c+272] == 3` :9564-9565;
+    // tag dispatch u16 @0: 1 -> HeightField, 2 -> TriMesh, 3 -> Polyline, else Cuboid :9568-9576):
+    //   position: UnitComplex re @248, im @252, translation @256 / @260 (:9580-9590); friction @264, penalty @268, handling @272
+    //   Cuboid (tag 0): half_extents @8 / @12 (:10289-10290)
+    //   HeightField (tag 1) = parry2d GenericHeightField<CudaStoragePtr>: heights {ptr @8, len @16}, status {ptr @24, len @32} (u8,
+    //     0 = segment removed: `setp.eq.s16 ..., 0 -> skip` :9999-10002, so present segments are 1), scale @40, aabb mins @48 / maxs @56,
+    //     bellow_heightfield_is_solid @64, flip_interior @65 (:9918-9919, :9961-9990, :10217-10229)
+    //   Polyline (tag 3): vertices {ptr @8, len @16} (Point2<f32>), flip_interior @24 (:9578, :9593-9597)
+    for (auto& b : c->collider_bufs) b.release();
+    c->collider_bufs.clear();
+    c->collider_bufs.reserve(2 * n + 1);
+    std::vector<unsigned char> img(std::max<size_t>(n, 1) * 280, 0);
+    for (size_t i = 0; i < n; ++i) {
+        unsigned char* b = img.data() + i * 280;
+        auto put64 = [&](size_t off, uint64_t v) { std::memcpy(b + off, &v, 8); };
+        const uint16_t tag = (uint16_t)cols[i].shape_tag;
+        std::memcpy(b, &tag, 2);
+        std::memcpy(b + 248, cols[i].rotation, 8);
+        std::memcpy(b + 256, cols[i].translation, 8);
+        std::memcpy(b + 264, &cols[i].friction, 4);
+        std::memcpy(b + 268, &cols[i].penalty_stiffness, 4);
+        std::memcpy(b + 272, &cols[i].grid_boundary_handling, 4);
+        if (cols[i].shape_tag == SPK_SHAPE_CUBOID) {
+            std::memcpy(b + 8, cols[i].shape.cuboid.half_extents, 8);
+        } else if (cols[i].shape_tag == SPK_SHAPE_HEIGHTFIELD) {
+            const auto& hf = cols[i].shape.heightfield;
+            if (!hf.heights || hf.num_heights < 2) return SPK_EINVAL;
+            const size_t nh = hf.num_heights, ns = nh - 1;
+            c->collider_bufs.emplace_back(); DevBuf& dh = c->collider_bufs.back();
+            if (int r = dh.ensure(nh * 4, false)) return r;
+            CU(D.p_cuMemcpyHtoD_v2(dh.p, hf.heights, nh * 4));
+            c->collider_bufs.emplace_back(); DevBuf& ds = c->collider_bufs.back();
+            if (int r = ds.ensure(ns, false)) return r;
+            std::vector<unsigned char> present(ns, 1);
+            CU(D.p_cuMemcpyHtoD_v2(ds.p, present.data(), ns));
+            put64(8, dh.p); put64(16, nh);
+            put64(24, ds.p); put64(32, ns);
+            std::memcpy(b + 40, hf.scale, 8);
+            float lo = hf.heights[0], hi = hf.heights[0];
+            for (size_t k = 1; k < nh; ++k) { lo = std::min(lo, hf.heights[k]); hi = std::max(hi, hf.heights[k]); }
+            const float mins[2] = {-0.5f * hf.scale[0], lo * hf.scale[1]}, maxs[2] = {0.5f * hf.scale[0], hi * hf.scale[1]};
+            std::memcpy(b + 48, mins, 8); std::memcpy(b + 56, maxs, 8);
+            b[64] = hf.bellow_heightfield_is_solid; b[65] = hf.flip_interior;
+        } else if (cols[i].shape_tag == SPK_SHAPE_POLYLINE) {
+            const auto& pl = cols[i].shape.polyline;
+            if (!pl.vertices || pl.num_vertices == 0) return SPK_EINVAL;
+            c->collider_bufs.emplace_back(); DevBuf& dv = c->collider_bufs.back();
+            if (int r = dv.ensure((size_t)pl.num_vertices * 8, false)) return r;
+            CU(D.p_cuMemcpyHtoD_v2(dv.p, pl.vertices, (size_t)pl.num_vertices * 8));
+            put64(8, dv.p); put64(16, pl.num_vertices);
+            b[24] = pl.flip_interior;
+        } else {
+            return SPK_EUNSUPPORTED;
+        }
+    }
+    if (int r = c->d_colliders.ensure(std::max<size_t>(n, 1) * 280, true)) return r;
+    if (n) CU(D.p_cuMemcpyHtoD_v2(c->d_colliders.p, img.data(), n * 280));
 #endif
 #if SPK_DIM == 3
     // The reference's own byte images of the non-cuboid shapes, recovered from the ld.global offsets of `grid_update` in
@@ -403,8 +459,6 @@ int ref_colliders_upload(ref_ctx* c, const SpkGpuCollider* cols, size_t n) {
     }
     if (int r = c->d_colliders.ensure(std::max<size_t>(n, 1) * 336, true)) return r;
     if (n) CU(D.p_cuMemcpyHtoD_v2(c->d_colliders.p, img.data(), n * 336));
-#else
-    if (int r = c->d_colliders.ensure(std::max<size_t>(n, 1) * sizeof(SpkGpuCollider), true)) return r;
 #endif
     c->ncolliders = n;
     return SPK_OK;

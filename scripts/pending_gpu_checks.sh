@@ -6,8 +6,9 @@
 cd "$(dirname "$0")/.."
 declare -A status
 run() { local name=$1; shift; echo "=== $name: $*"; if "$@"; then status[$name]=PASS; else status[$name]=FAIL; fi; }
-# 1. reference-harness device images of HeightField / Polyline colliders (layouts recovered from the PTX): three-way lock-step
-SPK_RUN_UNVERIFIED=1 run ref_colliders python -m pytest tests/test_reference_gpu.py -q -x -k unverified
+# 1. reference-harness device images of HeightField / Polyline colliders, dim3 and dim2 (layouts recovered from the PTX):
+#    three-way lock-step
+SPK_RUN_UNVERIFIED=1 run ref_colliders python -m pytest tests/test_reference_gpu.py tests/test_dim2_gpu.py -q -k unverified
 # 2. fluids-volume recomputation stage (spk_fluids.cu), dim3 + dim2
 run fluids_volume python -m pytest tests/test_volume_recomputation_gpu.py -q -x
 # 3. device-side particle migration (spk_migrate.cu), incl. two ranks on the peer-memory path sharing cuda:0

@@ -94,13 +94,17 @@ def test_elasticity2_lockstep():
     _run(sc, 12)
 
 
-def test_elasticity2_on_the_ground():
-    """the same blocks resting on / pressed into the ground so that the collider branch of grid_update is exercised"""
+def _elasticity2_on_the_ground_scene():
     sc = scenes2d.elasticity2(nblocks=2, scale=0.3)
     pts = sc.particles.position["point"]
     pts[:, 1] -= pts[:, 1].min() - np.float32(sc.cell_width * 40.0 + 0.01)  # lowest particle 0.01 above the ground surface
     sc.particles.velocity["vector"][:, 1] = -1.0
-    _run(sc, 10)
+    return sc
+
+
+def test_elasticity2_on_the_ground():
+    """the same blocks resting on / pressed into the ground so that the collider branch of grid_update is exercised"""
+    _run(_elasticity2_on_the_ground_scene(), 10)
 
 
 @pytest.mark.parametrize("kind", ["corotated", "neo_hookean", "fluid", "sand", "nacc", "failure", "failure_split"])
@@ -122,8 +126,7 @@ def test_fluids2_dam_break_lockstep():
     _run(sc, 8)
 
 
-def test_polyline_trough_dim2():
-    """sand dropped into a polyline trough: the in-tree polyline_project_point (gpu_collider.rs:105-201, dim2 normal)"""
+def _polyline_trough_scene():
     sc = scenes2d.model_block2("sand", 12, 10)
     ext = 12 * 0.1
     # counter-clockwise = solid; no vertex / edge passes through a grid node (multiples of h = 0.2): a node exactly on an edge has
@@ -132,15 +135,24 @@ def test_polyline_trough_dim2():
                                      (ext + 2.09, 0.47), (-2.11, 0.47), (-2.11, 3.51)][::-1])
     sc.colliders = [trough]
     sc.particles.velocity["vector"][:, 1] = -2.0
-    _run(sc, 8)
+    return sc
+
+
+def test_polyline_trough_dim2():
+    """sand dropped into a polyline trough: the in-tree polyline_project_point (gpu_collider.rs:105-201, dim2 normal)"""
+    _run(_polyline_trough_scene(), 8)
+
+
+def _basic2_scene():
+    sc = scenes2d.basic2(drop=0.004)
+    sc.particles.position["point"][:, 1] -= np.float32(0.045)  # start ~1 cell above the surface
+    return sc
 
 
 def test_basic2_on_the_heightfield_ground():
     """examples2d/basic2.rs: snow and sand columns dropped on the reference's heightfield ground (parry2d HeightField restated:
     product vs oracle; the columns reach the ground within the compared substeps)"""
-    sc = scenes2d.basic2(drop=0.004)
-    sc.particles.position["point"][:, 1] -= np.float32(0.045)  # start ~1 cell above the surface
-    g, o = _run(sc, 14)
+    g, o = _run(_basic2_scene(), 14)
     tags = np.bincount(o.grid_nodes(0)["projection_status_tag"].ravel().astype(int), minlength=4)
     assert tags[1] + tags[2] > 0 and tags[3] > 0  # nodes near the surface got a projection, far ones TooFar (max_dist = 2 h)
 
@@ -221,3 +233,23 @@ def test_three_way_lockstep_with_reference_dim2_kernels_clamping_models(ref2d, c
     from tests.test_reference_gpu import _lockstep
     sc, nsub, _ = build_case(case)
     _lockstep(sc, ref2d, nsub, 2e-5, robust=True)
+
+
+
+# The dim2 GpuCollider byte image of the reference (280 bytes; parry2d's device heightfield / polyline layouts) was recovered from the
+# ld.global offsets of `grid_update` in resources/sparkl2d-kernels.ptx (oracle/ref_harness.cpp: ref_colliders_upload), so the collider
+# scenes can go through the reference's own dim2 kernels too.  Written after this round's GPU budget was spent: enabled with
+# SPK_RUN_UNVERIFIED=1 until they have passed on a GPU (scripts/pending_gpu_checks.sh).
+import os  # noqa: E402
+
+_unverified = pytest.mark.skipif(os.environ.get("SPK_RUN_UNVERIFIED") != "1",
+                                 reason="not yet run on a GPU (written after the round's GPU budget was spent); set SPK_RUN_UNVERIFIED=1")
+
+
+@_unverified
+@pytest.mark.parametrize("which", ["cuboid_ground", "polyline_trough", "heightfield_ground"])
+def test_three_way_lockstep_with_colliders_dim2_unverified(ref2d, which):
+    from tests.test_reference_gpu import _lockstep
+    sc, nsub = {"cuboid_ground": (_elasticity2_on_the_ground_scene, 10), "polyline_trough": (_polyline_trough_scene, 8),
+                "heightfield_ground": (_basic2_scene, 14)}[which]
+    _lockstep(sc(), ref2d, nsub, 2e-5)
