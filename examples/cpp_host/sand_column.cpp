@@ -1,9 +1,11 @@
 // sand_column.cpp — a C++ host driving libsparkl_b200 through include/sparkl_b200.hpp, written like examples3d/sand3.rs: a
 // Drucker-Prager sand lattice on a corotated block, cuboid floor, `CudaMpmPipeline::step` per frame, positions read back.
 // Build:  g++ -std=c++17 -Iinclude examples/cpp_host/sand_column.cpp -Lsparkl_b200 -lsparkl_b200 -o sand_column
-// Usage:  sand_column [ni nj nk frames [positions.bin]]   (prints one summary line; optionally dumps the final positions)
+// Usage:  sand_column [ni nj nk frames [positions.bin [heightfield]]]   (prints one summary line; optionally dumps the final positions;
+//         `heightfield` replaces the cuboid floor by a heightfield ground)
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "sparkl_b200.hpp"
 
@@ -27,7 +29,18 @@ int main(int argc, char** argv) {
                     }
         ctx.particles().from_particles(pc);
         const float he[3] = {(float)ni * ext / 2 + 6.0f, 1.0f, (float)nk * ext / 2 + 6.0f}, tr[3] = {(float)ni * ext / 2, 1.0f, (float)nk * ext / 2};
-        ctx.colliders().from_collider_set({CudaColliderSet::cuboid(he, tr)});
+        if (argc > 6 && std::string(argv[6]) == "heightfield") {
+            // a 41 x 41 heightfield like the reference scene's ground (examples3d/sand3.rs:23-38), with a bumpy surface made of exactly
+            // representable samples (no transcendental: hosts in other languages reproduce it bit for bit); column-major, rows <-> z
+            const int n = 41;
+            std::vector<float> heights((size_t)n * n);
+            for (int col = 0; col < n; ++col)
+                for (int row = 0; row < n; ++row) heights[(size_t)col * n + row] = (float)((col * 3 + row * 5) % 7) * 0.001f;
+            const float scale[3] = {40.0f, 10.0f, 40.0f}, at[3] = {(float)ni * ext / 2, y0 - 0.3f, (float)nk * ext / 2};
+            ctx.colliders().from_collider_set({CudaColliderSet::heightfield(heights.data(), n, n, scale, at)});
+        } else {
+            ctx.colliders().from_collider_set({CudaColliderSet::cuboid(he, tr)});
+        }
         CudaMpmPipeline pipeline;
         SpkSolverParameters params = default_solver_parameters();
         const float gravity[3] = {0.0f, -9.81f, 0.0f};

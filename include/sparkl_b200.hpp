@@ -176,6 +176,56 @@ class CudaColliderSet { // cuda_collider_set.rs:13-131
         c.friction = friction; c.grid_boundary_handling = handling;
         return c;
     }
+    // the other shapes of GpuColliderShape (src_kernels/gpu_collider.rs:10-96).  The payload is a HOST description: the arrays must stay
+    // alive until from_collider_set() returns (the library keeps its own device copy).
+#if SPK_DIM == 3
+    // rapier `ColliderBuilder::heightfield(heights, scale)` (examples3d/sand3.rs:23-38): column-major nrows x ncols samples
+    static SpkGpuCollider heightfield(const float* heights, uint32_t nrows, uint32_t ncols, const float* scale, const float* translation, float friction = 0.5f,
+                                      uint32_t handling = SPK_BOUNDARY_FRICTION, bool flip_interior = false) {
+        const float zero[3] = {0.f, 0.f, 0.f};
+        SpkGpuCollider c = cuboid(zero, translation, friction, handling);
+        c.shape_tag = SPK_SHAPE_HEIGHTFIELD;
+        c.shape.heightfield.heights = heights; c.shape.heightfield.nrows = nrows; c.shape.heightfield.ncols = ncols;
+        for (int a = 0; a < 3; ++a) c.shape.heightfield.scale[a] = scale[a];
+        c.shape.heightfield.bellow_heightfield_is_solid = 1; // cuda_collider_set.rs:77
+        c.shape.heightfield.flip_interior = flip_interior;
+        return c;
+    }
+    // rapier `ColliderBuilder::trimesh(vertices, indices)` (no ORIENTED flag)
+    static SpkGpuCollider trimesh(const float* vertices, uint32_t num_vertices, const uint32_t* indices, uint32_t num_triangles, const float* translation,
+                                  float friction = 0.5f, uint32_t handling = SPK_BOUNDARY_FRICTION, bool flip_interior = false) {
+        const float zero[3] = {0.f, 0.f, 0.f};
+        SpkGpuCollider c = cuboid(zero, translation, friction, handling);
+        c.shape_tag = SPK_SHAPE_TRIMESH;
+        c.shape.trimesh.vertices = vertices; c.shape.trimesh.indices = indices;
+        c.shape.trimesh.num_vertices = num_vertices; c.shape.trimesh.num_triangles = num_triangles;
+        c.shape.trimesh.flip_interior = flip_interior;
+        return c;
+    }
+#else
+    // rapier2d `ColliderBuilder::heightfield(heights, scale)` (examples2d/basic2.rs:32-41)
+    static SpkGpuCollider heightfield(const float* heights, uint32_t num_heights, const float* scale, const float* translation, float friction = 0.5f,
+                                      uint32_t handling = SPK_BOUNDARY_FRICTION, bool flip_interior = false) {
+        const float zero[2] = {0.f, 0.f};
+        SpkGpuCollider c = cuboid(zero, translation, friction, handling);
+        c.shape_tag = SPK_SHAPE_HEIGHTFIELD;
+        c.shape.heightfield.heights = heights; c.shape.heightfield.num_heights = num_heights;
+        for (int a = 0; a < 2; ++a) c.shape.heightfield.scale[a] = scale[a];
+        c.shape.heightfield.bellow_heightfield_is_solid = 1;
+        c.shape.heightfield.flip_interior = flip_interior;
+        return c;
+    }
+#endif
+    // GpuColliderShape::Polyline: a closed polygon of num_vertices x SPK_DIM coordinates (gpu_collider.rs:24-27,105-201)
+    static SpkGpuCollider polyline(const float* vertices, uint32_t num_vertices, const float* translation, float friction = 0.5f,
+                                   uint32_t handling = SPK_BOUNDARY_FRICTION, bool flip_interior = false) {
+        const float zero[3] = {0.f, 0.f, 0.f};
+        SpkGpuCollider c = cuboid(zero, translation, friction, handling);
+        c.shape_tag = SPK_SHAPE_POLYLINE;
+        c.shape.polyline.vertices = vertices; c.shape.polyline.num_vertices = num_vertices;
+        c.shape.polyline.flip_interior = flip_interior;
+        return c;
+    }
 
   private:
     spk_ctx* c_;
@@ -224,6 +274,22 @@ class SingleGpuMpmContext { // cuda_mpm_pipeline.rs:177-194
         vt.launch_estimate_particle_timestep_length = [](void* u, spk_ctx* c, float a, float b) { return static_cast<CudaParticleKernelsLauncher*>(u)->launch_estimate_particle_timestep_length(c, a, b); };
         vt.launch_g2p2g = [](void* u, spk_ctx* c, float dt) { return static_cast<CudaParticleKernelsLauncher*>(u)->launch_g2p2g(c, dt); };
         check(spk_set_particle_kernels_launcher(c_, &vt), "set_particle_kernels_launcher");
+    }
+    // MlsSolver::recompute_fluids_volumes (src/dynamics/solver/fluids_volume.rs:9-116) as an explicit stage: between the sort / grid
+    // reset and the transfer of a hand-sequenced substep (spk_stage_* calls on raw())
+    void recompute_fluids_volume() { check(spk_stage_recompute_fluids_volume(c_), "SingleGpuMpmContext::recompute_fluids_volume"); }
+    // device-side particle migration between slabs (the reference keeps ownership static): see include/sparkl_abi.h
+    std::vector<uint32_t> migrate_out(const std::vector<int64_t>& bounds, uint32_t rank, SpkParticleRecord* dev_records, size_t capacity) {
+        std::vector<uint32_t> counts(bounds.size() > 1 ? bounds.size() - 1 : 0);
+        check(spk_particles_migrate_out(c_, bounds.data(), (uint32_t)counts.size(), rank, dev_records, capacity, counts.data()), "SingleGpuMpmContext::migrate_out");
+        return counts;
+    }
+    void migrate_in(const SpkParticleRecord* dev_records, size_t n) { check(spk_particles_migrate_in(c_, dev_records, n), "SingleGpuMpmContext::migrate_in"); }
+    void set_gids(const std::vector<uint32_t>& gids) { check(spk_particles_set_gids(c_, gids.data(), gids.size()), "SingleGpuMpmContext::set_gids"); }
+    std::vector<uint32_t> read_gids() {
+        std::vector<uint32_t> out(particles().len());
+        check(spk_particles_read_gids(c_, out.data(), out.size()), "SingleGpuMpmContext::read_gids");
+        return out;
     }
     spk_ctx* raw() { return c_; }
 

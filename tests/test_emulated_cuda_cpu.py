@@ -244,6 +244,19 @@ def test_cpp_host_example_builds_and_matches_the_python_host(emulated, tmp_path)
     for _ in range(2):
         g.step(sc.params, sc.gravity)
     assert np.array_equal(g.read(abi.ATTR_POSITION)["point"], pos_cpp)
+    # the heightfield builder of the C++ mirror against the Python one
+    out = subprocess.check_output([exe, "8", "4", "6", "2", out_bin, "heightfield"]).decode()
+    assert "particles 384" in out, out
+    pos_cpp = np.fromfile(out_bin, np.float32).reshape(-1, 3)
+    col, row = np.meshgrid(np.arange(41), np.arange(41), indexing="xy")  # heights[row, col]
+    heights = (((col * 3 + row * 5) % 7).astype(np.float32) * np.float32(0.001)).astype(np.float32)
+    y0 = np.float32(0.2) * np.float32(3.0) + np.float32(2.0)
+    sc.colliders = [abi.HeightFieldCollider(heights, (40.0, 10.0, 40.0), (8 * ext / 2, float(y0 - np.float32(0.3)), 6 * ext / 2))]
+    g = context_from_scene(sc)
+    for _ in range(2):
+        g.step(sc.params, sc.gravity)
+    assert np.array_equal(g.read(abi.ATTR_POSITION)["point"], pos_cpp)
+    assert (g.grid_nodes(0)["projection_status_tag"] == 1).any()  # some nodes are inside the ground: the collider acts
     # against the real library: builds, and without a GPU exits with the "no usable CUDA device" code
     import torch
     real = os.path.join(ROOT, "sparkl_b200", "libsparkl_b200.so")
