@@ -266,6 +266,18 @@ def test_cpp_host_example_builds_and_matches_the_python_host(emulated, tmp_path)
         assert subprocess.run([exe2, "4", "2", "2", "1"], capture_output=True).returncode == 10
 
 
+@pytest.mark.parametrize("name", ["F1M_fluids3", "S4M_sand3", "C16M_cube_through_sand3", "N8M_neo_hookean_slab"])
+def test_size_independent_properties_on_the_emulation(emulated, monkeypatch, name):
+    """the property checks of tests/test_fullsize_gpu.py (bit-exact block membership recomputed on the host, active set, exclusive-scan
+    headers, sort idempotence, P2G mass / momentum conservation, update invariants) on the same scenes at sizes the emulation handles"""
+    import tests.test_fullsize_gpu as T
+    from sparkl_b200 import scenes
+    small = {"F1M_fluids3": lambda: scenes.fluids3(24, 12, 12), "S4M_sand3": lambda: scenes.sand3(16, 8, 8),
+             "C16M_cube_through_sand3": lambda: scenes.cube_through_sand3(20, 10, 10, 5), "N8M_neo_hookean_slab": lambda: scenes.neo_hookean_block(14, 14, 14)}
+    monkeypatch.setattr(T, "CONFIGS", small)
+    T.test_full_size_properties(name)
+
+
 def _dim2_scene():
     from sparkl_b200 import scenes2d
     return scenes2d.jitter(scenes2d.elasticity2(2, scale=0.3), 0.002, seed=9)
