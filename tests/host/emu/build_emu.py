@@ -79,6 +79,26 @@ def build(dim: int = 3, force: bool = False, tag: str = "", extra_flags=()) -> s
     return out
 
 
+def build_example() -> str:
+    """examples/custom_updater/custom_updater.cu (a user's own instantiation of the library's kernel templates) for the emulation:
+    compiled against the transformed headers of the dim3 build and linked to the emulated library (whose CUDA stand-ins it shares)"""
+    lib3 = build(3)
+    src = os.path.join(ROOT, "examples", "custom_updater", "custom_updater.cu")
+    out = os.path.join(OUT_DIR, "libcustom_updater_emu.so")
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(lib3)):
+        return out
+    src_dir = os.path.join(HERE, "_src3")
+    with open(src) as fh:
+        text = transform(fh.read()).replace('#include "../../sparkl_b200/csrc/spk_g2p2g_kernel.cuh"', '#include "spk_g2p2g_kernel.cuh"')
+    cpp = os.path.join(src_dir, "custom_updater.cpp")
+    with open(cpp, "w") as fh:
+        fh.write(text)
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-DSPK_EMU", "-DSPK_DIM=3", "-I" + cuda_inc, "-I" + HERE, "-I" + src_dir, "-include", "cuda_emu.h"]
+    subprocess.check_call(["g++"] + flags + ["-shared", "-o", out, cpp, lib3, "-Wl,-rpath," + OUT_DIR])
+    return out
+
+
 if __name__ == "__main__":
     for d in (3, 2):
         print(build(d, force="--force" in sys.argv))

@@ -17,6 +17,10 @@ EXAMPLE = os.path.join(ROOT, "examples", "custom_updater", "libcustom_updater.so
 
 @pytest.fixture(scope="module")
 def example():
+    return _load_example()
+
+
+def _load_example():
     if not os.path.exists(EXAMPLE):
         from sparkl_b200 import build
         build.build()

@@ -278,6 +278,19 @@ def test_size_independent_properties_on_the_emulation(emulated, monkeypatch, nam
     T.test_full_size_properties(name)
 
 
+def test_custom_particle_kernels_on_the_emulation(emulated, monkeypatch):
+    """SURVEY §8 f-4 without a GPU: examples/custom_updater (a user's updater type instantiating the library's G2P2G / dt kernel
+    templates in its own shared object, plugged in through spk_set_particle_kernels_launcher) built for the emulation; the bodies of
+    tests/test_custom_updater_gpu.py run on it"""
+    import build_emu
+    import tests.test_custom_updater_gpu as T
+    monkeypatch.setattr(T, "EXAMPLE", build_emu.build_example())
+    example = T._load_example()
+    T.test_custom_updater_reproduces_the_builtin_model(example)
+    T.test_default_launcher_treats_custom_as_zero_stress_and_null_restores_it(example)
+    T.test_custom_updater_damping_and_stage_calls(example)
+
+
 def _dim2_scene():
     from sparkl_b200 import scenes2d
     return scenes2d.jitter(scenes2d.elasticity2(2, scale=0.3), 0.002, seed=9)
