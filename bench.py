@@ -59,6 +59,35 @@ except Exception as e:
 """
 
 
+def summarize_clock_samples(lines, t0, t1, t_load0, t_load1, reasons_bits):
+    """(pure: unit-tested on the CPU) `lines` = the sampler's output.  Samples taken inside the timed region [t0, t1] are used when there
+    are any; a timed region shorter than one NVML poll (a poll of a busy GPU can take tens of ms) falls back to the samples of the
+    loaded phases around it [t_load0, t_load1] — settle, warm-up, the timed steps and the repeat of the same K substeps that collects
+    the per-kernel timings, all the same kernels at the same load — and says so in `window`."""
+    mx, timed, loaded = None, [], []
+    for line in lines:
+        f = line.split()
+        if len(f) == 2 and f[0] == "max":
+            mx = float(f[1])
+        elif len(f) == 3:
+            try:
+                t, mhz, mask = float(f[0]), float(f[1]), int(f[2])
+            except ValueError:
+                continue
+            if t0 <= t <= t1:
+                timed.append((mhz, mask))
+            if t_load0 <= t <= t_load1:
+                loaded.append((mhz, mask))
+    use, window = (timed, "timed region") if timed else (loaded, "loaded phases around the timed region (it was shorter than one NVML poll)")
+    mask = 0
+    for _, m in use:
+        mask |= m
+    reasons = sorted(n for n, bit in reasons_bits.items() if mask & bit)
+    sm = [mhz for mhz, _ in use]
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "window": window if sm else None,
+            "source": "nvml (separate process)"}
+
+
 class ClockSampler:
     """samples SM clocks / throttle reasons during the timed region from a SEPARATE process (NVML, 200 Hz): an in-process
     poller competes with the launching thread for the GIL and the driver lock and was measured to slow the multi-GPU step"""
@@ -67,13 +96,21 @@ class ClockSampler:
 
     def __init__(self, index):
         self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        self.t0 = self.t1 = None
+        self.t0 = self.t1 = self.t_load0 = None
+
+    def load_begins(self):
+        self.t_load0 = time.time()
 
     def start(self):
         self.t0 = time.time()
 
-    def finish(self):
+    def stop(self):
         self.t1 = time.time()
+
+    def finish(self):
+        t_load1 = time.time()
+        if self.t1 is None:
+            self.t1 = t_load1
         time.sleep(0.02)
         self.proc.terminate()
         try:
@@ -81,17 +118,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, mask = [], None, 0
-        for line in out.splitlines():
-            f = line.split()
-            if len(f) == 2 and f[0] == "max":
-                mx = float(f[1])
-            elif len(f) == 3:
-                t = float(f[0])
-                if self.t0 <= t <= self.t1:
-                    sm.append(float(f[1])); mask |= int(f[2])
-        reasons = sorted(n for n, bit in self.REASONS.items() if mask & bit)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "source": "nvml (separate process)"}
+        return summarize_clock_samples(out.splitlines(), self.t0, self.t1, self.t_load0 if self.t_load0 is not None else self.t0, t_load1, self.REASONS)
 
 
 def build_scene(rank, world, dims):
@@ -210,6 +237,8 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None  # started early: its process is up by the time the timed region begins
     # bring the scene into a loaded state first (material compressing under gravity, F != I): the rest lattice makes the
     # per-particle SVD converge in one sweep and would flatter the kernel.  Untimed, not part of the warm-up contract.
+    if sampler:
+        sampler.load_begins()
     for _ in range(args.settle):
         one_substep()
     for _ in range(max(args.warmup, 3)):
@@ -228,7 +257,8 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     g2p2g_live_ms, g2p2g_live_n = ctx.g2p2g_time(enable=False)
-    clocks = sampler.finish() if sampler else None
+    if sampler:
+        sampler.stop()
     # per-kernel CUDA-event timings (inside spk_step, on its stream) over the SAME K substeps repeated: they need one event
     # synchronisation per substep, so they are taken in a second pass and do not perturb the throughput figure above
     if world == 1:
@@ -237,6 +267,9 @@ def run_ours(args):
             g2p2g_ms += t.g2p2g_ms
             launches += t.kernel_launches
             stage_ms += [t.grid_resize_and_sort_ms, t.reset_grid_ms, t.estimate_timestep_ms, t.g2p2g_ms, t.grid_update_ms]
+    if world > 1:
+        torch.cuda.synchronize()
+    clocks = sampler.finish() if sampler else None
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
