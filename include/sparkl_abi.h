@@ -189,7 +189,7 @@ typedef struct SpkGpuCollider {
 } SpkGpuCollider;
 #else
 /* dim2 GpuCollider (same Rust definition, src_kernels/gpu_collider.rs:203-212, with parry2d shapes and an Isometry2).
- * Cuboid (tag 0), HeightField (tag 1) and Polyline (tag 3).  The reference's own dim2 image is 280 bytes and holds parry2d's CUDA
+ * Cuboid (tag 0), HeightField (tag 1) and Polyline (tag 3); parry2d's TriMesh (tag 2) is rejected with SPK_EUNSUPPORTED.  The reference's own dim2 image is 280 bytes and holds parry2d's CUDA
  * pointer types (recovered from sparkl2d-kernels.ptx: oracle/ref_harness.cpp, ref_colliders_upload); this 72-byte layout is this
  * library's own: field order and meaning as in the Rust struct, heightfield / polyline payloads as HOST descriptions like the 3D ones. */
 typedef struct SpkGpuCollider {

@@ -764,7 +764,7 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
             data_off[i] = data.size();
             data.insert(data.end(), hf.heights, hf.heights + hf.num_heights);
         } else {
-            return SPK_EUNSUPPORTED; // a TriMesh is a 3D shape
+            return SPK_EUNSUPPORTED; // parry2d's TriMesh (a 2D triangle soup) is not built in dim2, DESIGN §9
         }
         std::memcpy(d.rot, cols[i].rotation, 8);
         std::memcpy(d.tr, cols[i].translation, 8);

@@ -199,7 +199,7 @@ def test_unsupported_dim2_features_fail_loudly():
     from sparkl_b200.pipeline import SingleGpuMpmContext
     g = SingleGpuMpmContext(0.1, dim=2)
     buf = np.zeros((1, 72), np.uint8)
-    buf.view("<u4")[0, 0] = 2  # a TriMesh is a 3D shape
+    buf.view("<u4")[0, 0] = 2  # parry2d's TriMesh is not built in dim2
     assert g._lib.spk_colliders_upload(g._h, buf.ctypes.data_as(C.c_void_p), 1) == abi.EUNSUPPORTED
     buf.view("<u4")[0, 0] = 1  # heightfield without samples
     assert g._lib.spk_colliders_upload(g._h, buf.ctypes.data_as(C.c_void_p), 1) == abi.EINVAL
