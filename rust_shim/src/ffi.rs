@@ -36,6 +36,22 @@ extern "C" {
     pub fn spk_dist_export(ctx: *mut SpkCtx, out: *mut SpkDistDescriptor) -> c_int;
     pub fn spk_dist_attach(ctx: *mut SpkCtx, rank: u32, world: u32, all_ranks: *const SpkDistDescriptor) -> c_int;
     pub fn spk_dist_detach(ctx: *mut SpkCtx) -> c_int;
+    // device-side particle migration between slabs (sparkl_b200/csrc/spk_migrate.cu): rows in DEVICE memory, transport left to the host
+    pub fn spk_particles_set_gids(ctx: *mut SpkCtx, gids: *const u32, n: usize) -> c_int;
+    pub fn spk_particles_read_gids(ctx: *mut SpkCtx, dst: *mut u32, n: usize) -> c_int;
+    pub fn spk_particles_migrate_out(ctx: *mut SpkCtx, bounds: *const i64, world: u32, rank: u32, dev_records: *mut SpkParticleRecord, capacity: usize,
+                                     counts_out: *mut u32) -> c_int;
+    pub fn spk_particles_migrate_in(ctx: *mut SpkCtx, dev_records: *const SpkParticleRecord, n: usize) -> c_int;
+    // MlsSolver::recompute_fluids_volumes as an explicit stage (sparkl_b200/csrc/spk_fluids.cu)
+    pub fn spk_stage_recompute_fluids_volume(ctx: *mut SpkCtx) -> c_int;
+}
+
+/// Wire format of one migrating particle (128 bytes in dim3): the six per-particle structs + a global id.
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct SpkParticleRecord {
+    pub status: ParticleStatus, pub position: ParticlePosition, pub velocity: ParticleVelocity, pub volume: ParticleVolume,
+    pub phase: ParticlePhase, pub data: ParticleData, pub gid: u32,
 }
 
 /// Opaque 128-byte blob (CUDA IPC handle of the rank's shared arena + its capacity); all-gather it with the host's transport.
