@@ -350,6 +350,10 @@ int spk_particles_commit_staged(spk_ctx* ctx);
 int spk_particles_remove_range(spk_ctx* ctx, size_t begin, size_t end);
 /* CudaParticleSet::len (cuda_particle_set.rs:73). */
 int spk_particles_len(const spk_ctx* ctx, size_t* out);
+/* CudaParticleSet::truncate / capacity (cuda_particle_set.rs:77-87): drop the particles with id >= new_len (no-op when the set is
+ * shorter); number of particles the device buffers hold without reallocating */
+int spk_particles_truncate(spk_ctx* ctx, size_t new_len);
+int spk_particles_capacity(const spk_ctx* ctx, size_t* out);
 /* CudaParticleSet::read_* (cuda_particle_set.rs:93-119): copies attribute `which` of the first n particles,
  * indexed by the caller's particle id (upload order), in the reference's struct layout, into host memory. */
 int spk_particles_read(spk_ctx* ctx, int which, void* dst, size_t n);

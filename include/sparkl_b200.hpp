@@ -125,6 +125,8 @@ class CudaParticleSet { // cuda_particle_set.rs:12-177
     }
     void remove_range(size_t begin, size_t end) { check(spk_particles_remove_range(c_, begin, end), "CudaParticleSet::remove_range"); }
     size_t len() const { size_t n = 0; check(spk_particles_len(c_, &n), "CudaParticleSet::len"); return n; }
+    size_t capacity() const { size_t n = 0; check(spk_particles_capacity(c_, &n), "CudaParticleSet::capacity"); return n; }
+    void truncate(size_t new_len) { check(spk_particles_truncate(c_, new_len), "CudaParticleSet::truncate"); }
     bool is_empty() const { return len() == 0; }
     std::vector<SpkParticlePosition> read_positions() const { return read<SpkParticlePosition>(SPK_ATTR_POSITION); }
     std::vector<SpkParticleVelocity> read_velocities() const { return read<SpkParticleVelocity>(SPK_ATTR_VELOCITY); }

@@ -27,6 +27,8 @@ extern "C" {
                                 volume: *const ParticleVolume, phase: *const ParticlePhase, data: *const ParticleData, n: usize) -> c_int;
     pub fn spk_particles_remove_range(ctx: *mut SpkCtx, begin: usize, end: usize) -> c_int;
     pub fn spk_particles_len(ctx: *const SpkCtx, out: *mut usize) -> c_int;
+    pub fn spk_particles_truncate(ctx: *mut SpkCtx, new_len: usize) -> c_int;
+    pub fn spk_particles_capacity(ctx: *const SpkCtx, out: *mut usize) -> c_int;
     pub fn spk_particles_read(ctx: *mut SpkCtx, which: c_int, dst: *mut c_void, n: usize) -> c_int;
     pub fn spk_models_upload(ctx: *mut SpkCtx, models: *const GpuParticleModel, n: usize) -> c_int;
     pub fn spk_colliders_upload(ctx: *mut SpkCtx, colliders: *const GpuCollider, n: usize) -> c_int;

@@ -24,7 +24,7 @@ EXPORTS = [
     "spk_halo_begin", "spk_halo_active_keys", "spk_halo_tag", "spk_halo_count", "spk_halo_pack", "spk_halo_merge", "spk_grid_num_active_blocks",
     "spk_grid_read_headers", "spk_grid_read_nodes", "spk_grid_read_dispatch", "spk_device_ptr", "spk_g2p2g_time",
     "spk_dist_export", "spk_dist_attach", "spk_dist_detach", "spk_dist_info",
-    "spk_particles_set_gids", "spk_particles_read_gids", "spk_particles_migrate_out", "spk_particles_migrate_in",
+    "spk_particles_truncate", "spk_particles_capacity", "spk_particles_set_gids", "spk_particles_read_gids", "spk_particles_migrate_out", "spk_particles_migrate_in",
     "spk_set_particle_kernels_launcher", "spk_default_launch_estimate_particle_timestep_length", "spk_default_launch_g2p2g",
 ]
 
@@ -73,6 +73,8 @@ def lib(dim: int = 3):
         l.spk_set_particle_kernels_launcher.argtypes = [vp, vp]
         l.spk_default_launch_estimate_particle_timestep_length.argtypes = [vp, C.c_float, C.c_float]
         l.spk_default_launch_g2p2g.argtypes = [vp, C.c_float]
+        l.spk_particles_truncate.argtypes = [vp, C.c_size_t]
+        l.spk_particles_capacity.argtypes = [vp, C.POINTER(C.c_size_t)]
         l.spk_particles_set_gids.argtypes = [vp, vp, C.c_size_t]
         l.spk_particles_read_gids.argtypes = [vp, vp, C.c_size_t]
         l.spk_particles_migrate_out.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_size_t, vp]

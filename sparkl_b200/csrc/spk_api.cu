@@ -663,6 +663,18 @@ int spk_particles_remove_range(spk_ctx* c, size_t begin, size_t end) {
     return spk_particles_upload(c, s.data(), p.data(), v.data(), vo.data(), ph.data(), d.data(), s.size());
 }
 
+// CudaParticleSet::truncate / capacity, cuda_particle_set.rs:77-87
+int spk_particles_truncate(spk_ctx* c, size_t new_len) {
+    if (!c) return SPK_EINVAL;
+    if (new_len >= c->n) return SPK_OK; // CudaVec::truncate: a no-op when the set is not longer than new_len
+    return spk_particles_remove_range(c, new_len, c->n);
+}
+int spk_particles_capacity(const spk_ctx* c, size_t* out) {
+    if (!c || !out) return SPK_EINVAL;
+    *out = c->cap;
+    return SPK_OK;
+}
+
 int spk_models_upload(spk_ctx* c, const SpkGpuParticleModel* models, size_t n) {
     if (!c || (n && !models)) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));

@@ -72,6 +72,16 @@ class SingleGpuMpmContext(Engine):
     def remove_range(self, begin: int, end: int):
         self._call("particles_remove_range", begin, end)
 
+    def truncate(self, new_len: int):
+        """CudaParticleSet::truncate, cuda_particle_set.rs:81-87"""
+        self._call("particles_truncate", new_len)
+
+    def capacity(self) -> int:
+        """CudaParticleSet::capacity, cuda_particle_set.rs:77-79"""
+        out = C.c_size_t()
+        self._call("particles_capacity", C.byref(out))
+        return out.value
+
     def step(self, params: abi.SolverParameters, gravity, timings: bool = True):
         return CudaMpmPipeline().step(params, gravity, [self], timings)
 
@@ -174,6 +184,12 @@ class CudaParticleSet:
 
     def remove_range(self, begin, end):
         self._ctx.remove_range(begin, end)
+
+    def truncate(self, new_len):
+        self._ctx.truncate(new_len)
+
+    def capacity(self):
+        return self._ctx.capacity()
 
 
 def _default_data(n):

@@ -86,6 +86,7 @@ def test_device_side_migration_on_the_emulation(emulated):
         T.test_migrate_out_is_a_stable_partition_and_in_appends(k)
     T.test_simulation_goes_on_from_a_migrated_set()
     T.test_migrate_in_grows_on_the_device()
+    T.test_truncate_and_capacity()
     T.test_migration_argument_errors()
 
 

@@ -147,6 +147,28 @@ def test_migrate_in_grows_on_the_device():
     assert np.isfinite(g.read(abi.ATTR_POSITION)["point"]).all()
 
 
+def test_truncate_and_capacity():
+    """CudaParticleSet::truncate / capacity (cuda_particle_set.rs:77-87)"""
+    from sparkl_b200.pipeline import context_from_scene
+    sc = _scene()
+    g = context_from_scene(sc)
+    n = len(g)
+    assert g.particles.capacity() >= n
+    g.step(abi.SolverParameters(max_substep_dt=1.0e-3), sc.gravity)
+    before = g.read_all()
+    g.particles.truncate(n + 5)  # not longer than that: a no-op
+    assert len(g) == n
+    g.particles.truncate(n - 37)
+    assert len(g) == n - 37 and g.particles.capacity() >= n - 37
+    after = g.read_all()
+    for name in ("position", "velocity", "volume", "status", "phase", "data"):
+        assert np.array_equal(getattr(after, name), getattr(before, name)[: n - 37]), name
+    g.step(abi.SolverParameters(max_substep_dt=1.0e-3), sc.gravity)
+    assert np.isfinite(g.read(abi.ATTR_POSITION)["point"]).all()
+    g.particles.truncate(0)
+    assert len(g) == 0 and g.particles.is_empty()
+
+
 def test_migration_argument_errors():
     from sparkl_b200.pipeline import context_from_scene
     g = context_from_scene(_scene())
