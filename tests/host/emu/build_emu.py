@@ -81,11 +81,11 @@ def build(dim: int = 3, force: bool = False, tag: str = "", extra_flags=()) -> s
 
 def build_example() -> str:
     """examples/custom_updater/custom_updater.cu (a user's own instantiation of the library's kernel templates) for the emulation:
-    compiled against the transformed headers of the dim3 build and linked to the emulated library (whose CUDA stand-ins it shares)"""
+    compiled against the transformed headers of the dim3 build, with its own copy of the CUDA stand-ins"""
     lib3 = build(3)
     src = os.path.join(ROOT, "examples", "custom_updater", "custom_updater.cu")
     out = os.path.join(OUT_DIR, "libcustom_updater_emu.so")
-    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(lib3)):
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(lib3), os.path.getmtime(os.path.abspath(__file__))):
         return out
     src_dir = os.path.join(HERE, "_src3")
     with open(src) as fh:
@@ -95,7 +95,9 @@ def build_example() -> str:
         fh.write(text)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-DSPK_EMU", "-DSPK_DIM=3", "-I" + cuda_inc, "-I" + HERE, "-I" + src_dir, "-include", "cuda_emu.h"]
-    subprocess.check_call(["g++"] + flags + ["-shared", "-o", out, cpp, lib3, "-Wl,-rpath," + OUT_DIR])
+    # like the CUDA build of the example (its own .so with its own CUDA runtime), the emulated one carries its own copy of the CUDA
+    # stand-ins, bound with -Bsymbolic: a real libcudart that some other module (torch) loaded into the process must not capture them
+    subprocess.check_call(["g++"] + flags + ["-shared", "-Wl,-Bsymbolic", "-o", out, cpp, os.path.join(HERE, "cuda_emu.cpp")])
     return out
 
 
