@@ -189,7 +189,7 @@ typedef struct SpkGpuCollider {
 } SpkGpuCollider;
 #else
 /* dim2 GpuCollider (same Rust definition, src_kernels/gpu_collider.rs:203-212, with parry2d shapes and an Isometry2).
- * Cuboid (tag 0), HeightField (tag 1) and Polyline (tag 3); parry2d's TriMesh (tag 2) is rejected with SPK_EUNSUPPORTED.  The reference's own dim2 image is 280 bytes and holds parry2d's CUDA
+ * Cuboid (tag 0), HeightField (tag 1), TriMesh (tag 2) and Polyline (tag 3).  The reference's own dim2 image is 280 bytes and holds parry2d's CUDA
  * pointer types (recovered from sparkl2d-kernels.ptx: oracle/ref_harness.cpp, ref_colliders_upload); this 72-byte layout is this
  * library's own: field order and meaning as in the Rust struct, heightfield / polyline payloads as HOST descriptions like the 3D ones. */
 typedef struct SpkGpuCollider {
@@ -208,6 +208,14 @@ typedef struct SpkGpuCollider {
             uint32_t num_vertices;
             uint8_t flip_interior;
         } polyline;
+        struct {                      /* GpuColliderShape::TriMesh with parry2d's TriMesh: a soup of SOLID 2D triangles.  The closest triangle
+                                       * decides; with `solid = false` (grid_update.rs:59-64) a point inside a triangle is projected onto that
+                                       * triangle's nearest edge and flagged inside (parry2d point_triangle.rs).  HOST description, exhaustive search. */
+            const float* vertices;    /* HOST pointer, num_vertices x (x, y) */
+            const uint32_t* indices;  /* HOST pointer, num_triangles x 3 vertex indices */
+            uint32_t num_vertices, num_triangles;
+            uint8_t flip_interior;
+        } trimesh;
         uint8_t _bytes[32];
     } shape;
     float rotation[2];    /* unit complex (re, im) = (cos, sin), nalgebra UnitComplex */

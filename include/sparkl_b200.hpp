@@ -180,6 +180,17 @@ class CudaColliderSet { // cuda_collider_set.rs:13-131
     }
     // the other shapes of GpuColliderShape (src_kernels/gpu_collider.rs:10-96).  The payload is a HOST description: the arrays must stay
     // alive until from_collider_set() returns (the library keeps its own device copy).
+    // rapier `ColliderBuilder::trimesh(vertices, indices)` (no ORIENTED flag): num_vertices x SPK_DIM coordinates, num_triangles x 3 indices
+    static SpkGpuCollider trimesh(const float* vertices, uint32_t num_vertices, const uint32_t* indices, uint32_t num_triangles, const float* translation,
+                                  float friction = 0.5f, uint32_t handling = SPK_BOUNDARY_FRICTION, bool flip_interior = false) {
+        const float zero[3] = {0.f, 0.f, 0.f};
+        SpkGpuCollider c = cuboid(zero, translation, friction, handling);
+        c.shape_tag = SPK_SHAPE_TRIMESH;
+        c.shape.trimesh.vertices = vertices; c.shape.trimesh.indices = indices;
+        c.shape.trimesh.num_vertices = num_vertices; c.shape.trimesh.num_triangles = num_triangles;
+        c.shape.trimesh.flip_interior = flip_interior;
+        return c;
+    }
 #if SPK_DIM == 3
     // rapier `ColliderBuilder::heightfield(heights, scale)` (examples3d/sand3.rs:23-38): column-major nrows x ncols samples
     static SpkGpuCollider heightfield(const float* heights, uint32_t nrows, uint32_t ncols, const float* scale, const float* translation, float friction = 0.5f,
@@ -191,17 +202,6 @@ class CudaColliderSet { // cuda_collider_set.rs:13-131
         for (int a = 0; a < 3; ++a) c.shape.heightfield.scale[a] = scale[a];
         c.shape.heightfield.bellow_heightfield_is_solid = 1; // cuda_collider_set.rs:77
         c.shape.heightfield.flip_interior = flip_interior;
-        return c;
-    }
-    // rapier `ColliderBuilder::trimesh(vertices, indices)` (no ORIENTED flag)
-    static SpkGpuCollider trimesh(const float* vertices, uint32_t num_vertices, const uint32_t* indices, uint32_t num_triangles, const float* translation,
-                                  float friction = 0.5f, uint32_t handling = SPK_BOUNDARY_FRICTION, bool flip_interior = false) {
-        const float zero[3] = {0.f, 0.f, 0.f};
-        SpkGpuCollider c = cuboid(zero, translation, friction, handling);
-        c.shape_tag = SPK_SHAPE_TRIMESH;
-        c.shape.trimesh.vertices = vertices; c.shape.trimesh.indices = indices;
-        c.shape.trimesh.num_vertices = num_vertices; c.shape.trimesh.num_triangles = num_triangles;
-        c.shape.trimesh.flip_interior = flip_interior;
         return c;
     }
 #else

@@ -193,7 +193,8 @@ struct orc_ctx {
     std::vector<uint32_t> sorted_ids;
     std::vector<SpkGpuParticleModel> models;
     std::vector<SpkGpuCollider> colliders;
-    std::vector<std::vector<float>> collider_data; // owned copies of the polyline vertices
+    std::vector<std::vector<float>> collider_data; // owned copies of the polyline / trimesh vertices and the height samples
+    std::vector<std::vector<uint32_t>> collider_idx; // owned copies of the trimesh indices
     Grid grids[2];
     int curr = 0;
     std::vector<SpkDispatchBlock2ActiveBlock> dispatch;
@@ -711,7 +712,62 @@ static bool heightfield_project_point(const SpkGpuCollider& c, V2 pt, Real max_d
     out.point = rot(c.rotation, best) + tr;
     return true;
 }
+// parry2d 0.13 Triangle::project_local_point_and_get_location (query/point/point_triangle.rs with the `dim2` feature), solid = false.
+// parry2d is an un-vendored dependency (crates-ptx/Cargo.lock pins 0.13.0): restated from its published algorithm — vertex regions,
+// edge regions through perp products, and for a point inside the triangle the nearest of the three edge lines, flagged inside.
+// PARITY: unpinned against the reference's kernels (its TriMesh payload holds a device QBVH that is not reproduced); checked against an
+// independent f64 brute force (tests/test_dim2_cpu.py).
+static void triangle_project2(V2 a, V2 b, V2 c, V2 p, V2& q, bool& inside) {
+    V2 ab = b - a, ac = c - a, ap = p - a;
+    Real ab_ap = dot(ab, ap), ac_ap = dot(ac, ap);
+    inside = false;
+    if (ab_ap <= 0.0f && ac_ap <= 0.0f) { q = a; inside = p.x == a.x && p.y == a.y; return; }
+    V2 bp = p - b;
+    Real ab_bp = dot(ab, bp), ac_bp = dot(ac, bp);
+    if (ab_bp >= 0.0f && ac_bp <= ab_bp) { q = b; inside = p.x == b.x && p.y == b.y; return; }
+    V2 cp = p - c;
+    Real ab_cp = dot(ab, cp), ac_cp = dot(ac, cp);
+    if (ac_cp >= 0.0f && ab_cp <= ac_cp) { q = c; inside = p.x == c.x && p.y == c.y; return; }
+    V2 bc = c - b;
+    Real n = ab.x * ac.y - ab.y * ac.x;
+    Real sq_ab = dot(ab, ab), sq_ac = dot(ac, ac), sq_bc = dot(bc, bc);
+    Real vc = n * (ab.x * ap.y - ab.y * ap.x);
+    if (vc < 0.0f && ab_ap >= 0.0f && ab_bp <= 0.0f) { Real v = ab_ap / sq_ab; q = a + ab * v; inside = q.x == p.x && q.y == p.y; return; }
+    Real vb = -n * (ac.x * cp.y - ac.y * cp.x);
+    if (vb < 0.0f && ac_ap >= 0.0f && ac_cp <= 0.0f) { Real w = ac_ap / sq_ac; q = a + ac * w; inside = q.x == p.x && q.y == p.y; return; }
+    Real va = n * (bc.x * bp.y - bc.y * bp.x);
+    if (va < 0.0f && ac_bp - ab_bp >= 0.0f && ab_cp - ac_cp >= 0.0f) { Real w = dot(bc, bp) / sq_bc; q = b + bc * w; inside = q.x == p.x && q.y == p.y; return; }
+    Real v = ab_ap / (ab_ap - ab_bp), w = ac_ap / (ac_ap - ac_cp), u = (ac_bp - ab_bp) / (ac_bp - ab_bp + ab_cp - ac_cp);
+    Real sq_ap = dot(ap, ap), sq_bp = dot(bp, bp);
+    Real d_ab = sq_ap - sq_ab * v * v, d_ac = sq_ap - sq_ac * w * w, d_bc = sq_bp - sq_bc * u * u;
+    inside = true;
+    if (d_ab < d_ac) q = d_ab < d_bc ? a + ab * v : b + bc * u;
+    else q = d_ac < d_bc ? a + ac * w : b + bc * u;
+}
+// GpuColliderShape::TriMesh, src_kernels/gpu_collider.rs:58-68: project_point_with_max_dist(.., Real::MAX) = the closest triangle of the
+// whole mesh (ties: lowest index), then flip_interior
+static bool trimesh_project_point(const SpkGpuCollider& c, V2 pt, Projection& out) {
+    const auto& tm = c.shape.trimesh;
+    V2 tr = v2(c.translation[0], c.translation[1]);
+    V2 lp = rot_inv(c.rotation, pt - tr);
+    Real best_sq = FLT_MAX;
+    bool found = false, best_in = false;
+    V2 best = v2(0, 0);
+    for (uint32_t t = 0; t < tm.num_triangles; ++t) {
+        const uint32_t* id = tm.indices + 3 * (size_t)t;
+        V2 q; bool in;
+        triangle_project2(v2(tm.vertices[2 * id[0]], tm.vertices[2 * id[0] + 1]), v2(tm.vertices[2 * id[1]], tm.vertices[2 * id[1] + 1]),
+                          v2(tm.vertices[2 * id[2]], tm.vertices[2 * id[2] + 1]), lp, q, in);
+        Real sq = norm_squared(lp - q);
+        if (sq < best_sq) { best_sq = sq; best = q; best_in = in; found = true; }
+    }
+    if (!found) return false;
+    out.is_inside = tm.flip_interior ? !best_in : best_in;
+    out.point = rot(c.rotation, best) + tr;
+    return true;
+}
 static bool collider_project(const SpkGpuCollider& c, V2 pt, Real max_dist, Projection& out) {
+    if (c.shape_tag == SPK_SHAPE_TRIMESH) return trimesh_project_point(c, pt, out);
     if (c.shape_tag == SPK_SHAPE_HEIGHTFIELD) return heightfield_project_point(c, pt, max_dist, out);
     if (c.shape_tag == SPK_SHAPE_POLYLINE) return polyline_project_point(c, pt, out);
     if (c.shape_tag != SPK_SHAPE_CUBOID) return false;
@@ -870,9 +926,10 @@ int orc_particles_read(orc_ctx* c, int which, void* dst, size_t n) {
 int orc_models_upload(orc_ctx* c, const SpkGpuParticleModel* models, size_t n) { c->models.assign(models, models + n); return SPK_OK; }
 int orc_colliders_upload(orc_ctx* c, const SpkGpuCollider* cols, size_t n) {
     for (size_t i = 0; i < n; ++i)
-        if (cols[i].shape_tag != SPK_SHAPE_CUBOID && cols[i].shape_tag != SPK_SHAPE_POLYLINE && cols[i].shape_tag != SPK_SHAPE_HEIGHTFIELD) return SPK_EUNSUPPORTED;
+        if (cols[i].shape_tag > SPK_SHAPE_POLYLINE) return SPK_EUNSUPPORTED;
     c->colliders.assign(cols, cols + n);
     c->collider_data.assign(n, {});
+    c->collider_idx.assign(n, {});
     for (size_t i = 0; i < n; ++i)
         if (cols[i].shape_tag == SPK_SHAPE_HEIGHTFIELD) {
             const auto& hf = cols[i].shape.heightfield;
@@ -884,6 +941,15 @@ int orc_colliders_upload(orc_ctx* c, const SpkGpuCollider* cols, size_t n) {
             if (pl.num_vertices && !pl.vertices) return SPK_EINVAL;
             c->collider_data[i].assign(pl.vertices, pl.vertices + (size_t)pl.num_vertices * 2);
             c->colliders[i].shape.polyline.vertices = c->collider_data[i].data();
+        } else if (cols[i].shape_tag == SPK_SHAPE_TRIMESH) {
+            const auto& tm = cols[i].shape.trimesh;
+            if (!tm.vertices || !tm.indices || tm.num_vertices == 0 || tm.num_triangles == 0) return SPK_EINVAL;
+            for (size_t k = 0; k < (size_t)tm.num_triangles * 3; ++k)
+                if (tm.indices[k] >= tm.num_vertices) return SPK_EINVAL;
+            c->collider_data[i].assign(tm.vertices, tm.vertices + (size_t)tm.num_vertices * 2);
+            c->collider_idx[i].assign(tm.indices, tm.indices + (size_t)tm.num_triangles * 3);
+            c->colliders[i].shape.trimesh.vertices = c->collider_data[i].data();
+            c->colliders[i].shape.trimesh.indices = c->collider_idx[i].data();
         }
     return SPK_OK;
 }

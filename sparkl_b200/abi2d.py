@@ -126,6 +126,28 @@ class HeightFieldCollider(CuboidCollider):
         return bytes(buf)
 
 
+class TriMeshCollider(CuboidCollider):
+    """A rapier2d `ColliderBuilder::trimesh(vertices, indices)`: parry2d's TriMesh, a soup of solid 2D triangles -> 72-byte dim2
+    SpkGpuCollider with HOST pointers to the n x 2 vertices and the m x 3 indices.  Keep the object alive until the upload."""
+
+    def __init__(self, vertices, indices, translation=(0, 0), rotation=0.0, friction=0.5, penalty_stiffness=0.0,
+                 grid_boundary_handling=BoundaryHandling.Friction, flip_interior=False):
+        v = np.ascontiguousarray(np.asarray(vertices, np.float32))
+        t = np.ascontiguousarray(np.asarray(indices, np.uint32))
+        assert v.ndim == 2 and v.shape[1] == 2 and t.ndim == 2 and t.shape[1] == 3
+        super().__init__((0, 0), translation, rotation, friction, penalty_stiffness, grid_boundary_handling)
+        self.vertices, self.indices, self.flip_interior = v, t, flip_interior
+
+    def to_gpu_collider(self) -> bytes:
+        buf = bytearray(72)
+        np.frombuffer(buf, "<u4", 1, 0)[0] = 2
+        np.frombuffer(buf, "<u8", 2, 8)[:] = [self.vertices.ctypes.data, self.indices.ctypes.data]
+        np.frombuffer(buf, "<u4", 2, 24)[:] = [len(self.vertices), len(self.indices)]
+        np.frombuffer(buf, "u1", 1, 32)[0] = int(self.flip_interior)
+        self._tail(buf)
+        return bytes(buf)
+
+
 def pack_colliders(colliders) -> np.ndarray:
     out = np.zeros((len(colliders), 72), dtype=np.uint8)
     for i, c in enumerate(colliders):

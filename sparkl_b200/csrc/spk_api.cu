@@ -775,8 +775,18 @@ int spk_colliders_upload(spk_ctx* c, const SpkGpuCollider* cols, size_t n) {
             d.hf_flags = (hf.bellow_heightfield_is_solid ? 1u : 0u) | (hf.flip_interior ? 2u : 0u);
             data_off[i] = data.size();
             data.insert(data.end(), hf.heights, hf.heights + hf.num_heights);
+        } else if (cols[i].shape_tag == SPK_SHAPE_TRIMESH) {
+            const auto& tm = cols[i].shape.trimesh;
+            if (!tm.vertices || !tm.indices || tm.num_vertices == 0 || tm.num_triangles == 0) return SPK_EINVAL;
+            for (size_t k = 0; k < (size_t)tm.num_triangles * 3; ++k)
+                if (tm.indices[k] >= tm.num_vertices) return SPK_EINVAL;
+            d.nrows = tm.num_vertices; d.ncols = tm.num_triangles;
+            d.hf_flags = tm.flip_interior ? 2u : 0u;
+            data_off[i] = data.size();
+            data.insert(data.end(), tm.vertices, tm.vertices + (size_t)tm.num_vertices * 2); // [vertices | indices as raw bits]
+            for (size_t k = 0; k < (size_t)tm.num_triangles * 3; ++k) { float bits; std::memcpy(&bits, &tm.indices[k], 4); data.push_back(bits); }
         } else {
-            return SPK_EUNSUPPORTED; // parry2d's TriMesh (a 2D triangle soup) is not built in dim2, DESIGN §9
+            return SPK_EUNSUPPORTED;
         }
         std::memcpy(d.rot, cols[i].rotation, 8);
         std::memcpy(d.tr, cols[i].translation, 8);

@@ -174,7 +174,70 @@ __device__ inline bool heightfield_project(const DevCollider& c, Vec2 pt, float 
     out = Vec2{w.x + c.tr[0], w.y + c.tr[1]};
     return true;
 }
+// parry2d 0.13 Triangle::project_local_point_and_get_location (query/point/point_triangle.rs, `dim2` paths) with solid = false:
+// vertex / edge Voronoi regions as in 3D (perp products instead of cross products); a point inside the triangle is projected onto
+// the nearest of the three edge LINES (squared distances by Pythagoras) and flagged inside.  Restated from the published algorithm.
+__device__ inline void triangle_project2(Vec2 a, Vec2 b, Vec2 c, Vec2 p, Vec2& q, bool& inside) {
+    const Vec2 ab{b.x - a.x, b.y - a.y}, ac{c.x - a.x, c.y - a.y}, ap{p.x - a.x, p.y - a.y};
+    const float ab_ap = ab.x * ap.x + ab.y * ap.y, ac_ap = ac.x * ap.x + ac.y * ap.y;
+    inside = false;
+    if (ab_ap <= 0.f && ac_ap <= 0.f) { q = a; inside = p.x == a.x && p.y == a.y; return; }
+    const Vec2 bp{p.x - b.x, p.y - b.y};
+    const float ab_bp = ab.x * bp.x + ab.y * bp.y, ac_bp = ac.x * bp.x + ac.y * bp.y;
+    if (ab_bp >= 0.f && ac_bp <= ab_bp) { q = b; inside = p.x == b.x && p.y == b.y; return; }
+    const Vec2 cp{p.x - c.x, p.y - c.y};
+    const float ab_cp = ab.x * cp.x + ab.y * cp.y, ac_cp = ac.x * cp.x + ac.y * cp.y;
+    if (ac_cp >= 0.f && ab_cp <= ac_cp) { q = c; inside = p.x == c.x && p.y == c.y; return; }
+    const Vec2 bc{c.x - b.x, c.y - b.y};
+    const float n = ab.x * ac.y - ab.y * ac.x;
+    const float sq_ab = ab.x * ab.x + ab.y * ab.y, sq_ac = ac.x * ac.x + ac.y * ac.y, sq_bc = bc.x * bc.x + bc.y * bc.y;
+    const float vc = n * (ab.x * ap.y - ab.y * ap.x);
+    if (vc < 0.f && ab_ap >= 0.f && ab_bp <= 0.f) { const float v = ab_ap / sq_ab; q = Vec2{a.x + ab.x * v, a.y + ab.y * v}; inside = q.x == p.x && q.y == p.y; return; }
+    const float vb = -n * (ac.x * cp.y - ac.y * cp.x);
+    if (vb < 0.f && ac_ap >= 0.f && ac_cp <= 0.f) { const float w = ac_ap / sq_ac; q = Vec2{a.x + ac.x * w, a.y + ac.y * w}; inside = q.x == p.x && q.y == p.y; return; }
+    const float va = n * (bc.x * bp.y - bc.y * bp.x);
+    if (va < 0.f && ac_bp - ab_bp >= 0.f && ab_cp - ac_cp >= 0.f) {
+        const float w = (bc.x * bp.x + bc.y * bp.y) / sq_bc;
+        q = Vec2{b.x + bc.x * w, b.y + bc.y * w}; inside = q.x == p.x && q.y == p.y; return;
+    }
+    // inside the (solid) triangle, solid = false: the closest edge
+    const float v = ab_ap / (ab_ap - ab_bp), w = ac_ap / (ac_ap - ac_cp), u = (ac_bp - ab_bp) / (ac_bp - ab_bp + ab_cp - ac_cp);
+    const float sq_ap = ap.x * ap.x + ap.y * ap.y, sq_bp = bp.x * bp.x + bp.y * bp.y;
+    const float d_ab = sq_ap - sq_ab * v * v, d_ac = sq_ap - sq_ac * w * w, d_bc = sq_bp - sq_bc * u * u;
+    inside = true;
+    if (d_ab < d_ac) {
+        if (d_ab < d_bc) q = Vec2{a.x + ab.x * v, a.y + ab.y * v};
+        else q = Vec2{b.x + bc.x * u, b.y + bc.y * u};
+    } else {
+        if (d_ac < d_bc) q = Vec2{a.x + ac.x * w, a.y + ac.y * w};
+        else q = Vec2{b.x + bc.x * u, b.y + bc.y * u};
+    }
+}
+// TriMesh::project_point_with_max_dist(.., Real::MAX) (gpu_collider.rs:58-68): the closest triangle over the whole mesh (parry's QBVH
+// only prunes; ties go to the lowest triangle index here), flip_interior applied afterwards
+__device__ inline bool trimesh_project(const DevCollider& c, Vec2 pt, Vec2& out, bool& inside) {
+    const Vec2 lp = rot_inv(c.rot, Vec2{pt.x - c.tr[0], pt.y - c.tr[1]});
+    const float* verts = c.heights;
+    const float* idx = c.heights + (size_t)c.nrows * 2;
+    float best_sq = FLT_MAX;
+    Vec2 best{0.f, 0.f};
+    bool best_in = false, found = false;
+    for (uint32_t t = 0; t < c.ncols; ++t) {
+        const uint32_t i0 = __float_as_uint(idx[3 * t]), i1 = __float_as_uint(idx[3 * t + 1]), i2 = __float_as_uint(idx[3 * t + 2]);
+        Vec2 q; bool in;
+        triangle_project2(Vec2{verts[2 * i0], verts[2 * i0 + 1]}, Vec2{verts[2 * i1], verts[2 * i1 + 1]}, Vec2{verts[2 * i2], verts[2 * i2 + 1]}, lp, q, in);
+        const float dx = lp.x - q.x, dy = lp.y - q.y;
+        const float sq = dx * dx + dy * dy;
+        if (sq < best_sq) { best_sq = sq; best = q; best_in = in; found = true; }
+    }
+    if (!found) return false;
+    inside = (c.hf_flags & 2u) ? !best_in : best_in;
+    const Vec2 w = rot(c.rot, best);
+    out = Vec2{w.x + c.tr[0], w.y + c.tr[1]};
+    return true;
+}
 __device__ __forceinline__ bool collider_project(const DevCollider& c, Vec2 pt, float max_dist, Vec2& out, bool& inside) {
+    if (c.shape == SPK_SHAPE_TRIMESH) return trimesh_project(c, pt, out, inside);
     if (c.shape == SPK_SHAPE_HEIGHTFIELD) return heightfield_project(c, pt, max_dist, out, inside);
     if (c.shape == SPK_SHAPE_POLYLINE) return polyline_project(c, pt, out, inside);
     cuboid_project(c, pt, out, inside);

@@ -226,6 +226,64 @@ def test_polyline_projection_dim2_inside_outside():
     assert n_checked > 300
 
 
+def _tri_mesh_2d():
+    """an L-shaped region made of four triangles (internal edges included) + a detached triangle"""
+    v = np.array([[0.03, 0.02], [2.04, 0.05], [2.01, 1.03], [0.02, 1.01], [1.02, 1.02], [1.03, 2.05], [0.01, 2.02], [3.1, 3.2], [4.2, 3.1], [3.6, 4.3]], np.float32)
+    t = np.array([[0, 1, 2], [0, 2, 3], [3, 4, 5], [3, 5, 6], [7, 8, 9]], np.uint32)
+    return v, t
+
+
+def test_trimesh_projection_dim2_against_brute_force():
+    """dim2 TriMesh (parry2d: a soup of solid triangles; the closest triangle decides, a point inside a triangle goes to that triangle's
+    nearest edge and is flagged inside) against an independent f64 computation"""
+    v, t = _tri_mesh_2d()
+    col = abi2d.TriMeshCollider(v, t, translation=(0.4, -0.3), rotation=0.35)
+    flipped = abi2d.TriMeshCollider(v, t, translation=(0.4, -0.3), rotation=0.35, flip_interior=True)
+    rng = np.random.Generator(np.random.PCG64(17))
+    c, s_ = np.cos(np.float32(0.35)), np.sin(np.float32(0.35))
+    V = v.astype(np.float64)
+
+    def seg_dist(p, a, b):
+        ab, ap = b - a, p - a
+        u = np.clip(ab @ ap / (ab @ ab), 0.0, 1.0)
+        return np.linalg.norm(p - (a + u * ab)), a + u * ab
+
+    def line_dist(p, a, b):
+        ab, ap = b - a, p - a
+        u = ab @ ap / (ab @ ab)
+        return np.linalg.norm(p - (a + u * ab)), a + u * ab
+
+    checked_flags = 0
+    for _ in range(600):
+        lp = rng.uniform([-0.8, -0.8], [4.8, 4.8])
+        per_tri = []
+        for tri in t:
+            a, b, cc = V[tri[0]], V[tri[1]], V[tri[2]]
+            m = np.array([b - a, cc - a]).T
+            l1, l2 = np.linalg.solve(m, lp - a)
+            inside = l1 > 0 and l2 > 0 and l1 + l2 < 1
+            edges = [(a, b), (b, cc), (cc, a)]
+            if inside:
+                d, q = min((line_dist(lp, *e) for e in edges), key=lambda x: x[0])
+            else:
+                d, q = min((seg_dist(lp, *e) for e in edges), key=lambda x: x[0])
+            per_tri.append((d, q, inside))
+        order = sorted(range(len(t)), key=lambda k: per_tri[k][0])
+        d0, q0, in0 = per_tri[order[0]]
+        wp = np.array([c * lp[0] - s_ * lp[1] + 0.4, s_ * lp[0] + c * lp[1] - 0.3])
+        got = ob.collider_project2d(col, wp.astype(np.float32), 1.0)
+        assert got is not None
+        gq, gin = got
+        wq = np.array([c * q0[0] - s_ * q0[1] + 0.4, s_ * q0[0] + c * q0[1] - 0.3])
+        assert abs(np.linalg.norm(gq - wp) - d0) < 2e-5, (lp, gq, wq)       # the distance is that of the closest triangle
+        if per_tri[order[1]][0] - d0 > 1e-4:                               # an unambiguous winner (not a shared edge): point and flag too
+            assert np.abs(gq - wq).max() < 5e-5, (lp, gq, wq)
+            assert gin == bool(in0)
+            assert ob.collider_project2d(flipped, wp.astype(np.float32), 1.0)[1] == (not in0)
+            checked_flags += 1
+    assert checked_flags > 300
+
+
 def test_heightfield_projection_dim2_against_brute_force():
     """parry2d HeightField (examples2d/basic2.rs ground): closest point on the polyline of samples within max_dist, inside = under
     the surface and within the x footprint (gpu_collider.rs:73-99)"""

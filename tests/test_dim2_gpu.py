@@ -199,10 +199,11 @@ def test_unsupported_dim2_features_fail_loudly():
     from sparkl_b200.pipeline import SingleGpuMpmContext
     g = SingleGpuMpmContext(0.1, dim=2)
     buf = np.zeros((1, 72), np.uint8)
-    buf.view("<u4")[0, 0] = 2  # parry2d's TriMesh is not built in dim2
+    buf.view("<u4")[0, 0] = 7  # not a GpuColliderShape
     assert g._lib.spk_colliders_upload(g._h, buf.ctypes.data_as(C.c_void_p), 1) == abi.EUNSUPPORTED
-    buf.view("<u4")[0, 0] = 1  # heightfield without samples
-    assert g._lib.spk_colliders_upload(g._h, buf.ctypes.data_as(C.c_void_p), 1) == abi.EINVAL
+    for tag in (1, 2):  # heightfield without samples, trimesh without vertices
+        buf.view("<u4")[0, 0] = tag
+        assert g._lib.spk_colliders_upload(g._h, buf.ctypes.data_as(C.c_void_p), 1) == abi.EINVAL
     desc = np.zeros(128, np.uint8)
     assert g._lib.spk_dist_export(g._h, desc.ctypes.data_as(C.c_void_p)) == abi.EUNSUPPORTED
 

@@ -292,6 +292,12 @@ def test_custom_particle_kernels_on_the_emulation(emulated, monkeypatch):
     T.test_custom_updater_damping_and_stage_calls(example)
 
 
+def test_dim2_trimesh_on_the_emulation(emulated):
+    import tests.test_ztrimesh2d_gpu as T
+    T.test_sand_on_a_trimesh_ramp_dim2()
+    T.test_trimesh_argument_errors_dim2()
+
+
 def _dim2_scene():
     from sparkl_b200 import scenes2d
     return scenes2d.jitter(scenes2d.elasticity2(2, scale=0.3), 0.002, seed=9)
