@@ -15,6 +15,8 @@ run fluids_volume python -m pytest tests/test_volume_recomputation_gpu.py -q -x
 run migration python -m pytest tests/test_zmigration_gpu.py -q -x
 # 3b. dim2 TriMesh colliders (spk_grid2d.cu)
 run trimesh2d python -m pytest tests/test_ztrimesh2d_gpu.py -q -x
+# 3c. the remaining example scenes (rotated heightfields of sand_penetration3, l_panel2)
+run scenes python -m pytest tests/test_zscenes_gpu.py -q -x
 # 4. the C++ host example against the real library
 run cpp_host bash -c 'g++ -std=c++17 -O2 -Iinclude examples/cpp_host/sand_column.cpp -Lsparkl_b200 -lsparkl_b200 -Wl,-rpath,$PWD/sparkl_b200 -o /tmp/sand_column && /tmp/sand_column 40 20 20 3'
 # 5. the whole GPU suite, smoke and a bench line (unchanged kernels: SASS-identical to the last measured state)

@@ -82,6 +82,37 @@ def sand3(ni=100, nj=50, nk=50, x_offset=0.0, with_colliders=True, ground="cuboi
     return Scene("sand3", h, pc, models, cols)
 
 
+def _axis_angle_x(angle):
+    """rapier `.rotation(vector![angle, 0, 0])`: UnitQuaternion::new(axis-angle) in nalgebra coordinate order (i, j, k, w)"""
+    half = np.float32(angle) * np.float32(0.5)
+    return (float(np.sin(half)), 0.0, 0.0, float(np.cos(half)))
+
+
+def sand_penetration3(ni=100, nj=50, nk=50, origin=None) -> Scene:
+    """examples3d/sand_penetration3.rs:11-152: a Drucker-Prager sand lattice (E = 1e7, nu = 0.2, h = 0.2, r = h / 4, rho0 = 2700)
+    inside four 41 x 41 heightfields, heights[(i, j)] = sin(10 i pi / 40), scale (40, 1, 40): a floor at y = 10, a ceiling at y = 12
+    turned by pi about x, and two walls at z = +-5 turned by -+pi / 2 about x — the reference's scene with ROTATED heightfields.
+    `origin` moves the lattice (reference: (0, 15.2, 0)); the reference inserts only the sand batch (:136-137)."""
+    E, NU = 1.0e7, 0.2
+    h = 0.2
+    r = np.float32(h) / np.float32(4.0)
+    models = [ParticleModel.with_plasticity(CorotatedLinearElasticity(E, NU), DruckerPragerPlasticity(E, NU)),
+              ParticleModel(CorotatedLinearElasticity(E, NU))]
+    n = 40
+    i = np.arange(n + 1, dtype=np.float32)
+    col = np.sin(i * np.float32(np.pi) / np.float32(n) * np.float32(10.0)).astype(np.float32)
+    heights = np.repeat(col[:, None], n + 1, axis=1)
+    pi = float(np.float32(np.pi))
+    cols = [HeightFieldCollider(heights, (40.0, 1.0, 40.0), translation=(0.0, 10.0, 0.0)),
+            HeightFieldCollider(heights, (40.0, 1.0, 40.0), translation=(0.0, 12.0, 0.0), rotation=_axis_angle_x(pi)),
+            HeightFieldCollider(heights, (40.0, 1.0, 40.0), translation=(0.0, 0.0, 5.0), rotation=_axis_angle_x(-pi / 2.0)),
+            HeightFieldCollider(heights, (40.0, 1.0, 40.0), translation=(0.0, 0.0, -5.0), rotation=_axis_angle_x(pi / 2.0))]
+    if origin is None:
+        origin = (0.0, float(np.float32(2.0) * (np.float32(h) * np.float32(3.0) + np.float32(2.0) + r * np.float32(2.0) * np.float32(50.0))), 0.0)
+    pc = cube_particles(origin, ni, nj, nk, 0, r, 2700.0)
+    return Scene("sand_penetration3", h, pc, models, cols)
+
+
 def fluids3(ni=38, nj=20, nk=20, with_colliders=True) -> Scene:
     """examples3d/fluids3.rs:17-38: Monaghan weakly-compressible fluid, radius 0.1, h = 0.8 (64 particles per cell
     at rest), rho0 = 1000.  The reference has no collider; the dam-break variant adds a cuboid floor and walls."""
@@ -174,5 +205,5 @@ def jitter(scene: Scene, amplitude: float, seed: int = 42) -> Scene:
     return scene
 
 
-SCENES = {"sand3": sand3, "fluids3": fluids3, "cube_through_sand3": cube_through_sand3, "neo_hookean_block": neo_hookean_block,
+SCENES = {"sand3": sand3, "fluids3": fluids3, "cube_through_sand3": cube_through_sand3, "sand_penetration3": sand_penetration3, "neo_hookean_block": neo_hookean_block,
           "model_block": model_block}

@@ -132,6 +132,26 @@ def basic2(ni=12, nj=24, drop=0.02) -> Scene:
     return Scene("basic2", h, pc, models, [ground], gravity=GRAVITY, params=SolverParameters(max_num_substeps=50))
 
 
+def l_panel2(scale=1.0) -> Scene:
+    """examples2d/l_panel2.rs:18-113: two L-shaped concrete panels (corotated E = 25.85e9, nu = 0.18; the second one with a
+    MaximumStressFailure(2.7e6, MAX)), h = 0.005, r = h / 4, density 2500, a cuboid ground, no gravity, dt = 1 / 6000.  The scene's
+    pulled-node boundary condition is an `MpmHooks::post_grid_update_hook` on the CPU solver's SpGrid (:124-138) and its Eigenerosion
+    damage model is CPU-only: neither exists on the GPU path, the GPU run of this scene is the free panels.
+    `scale` < 1 shrinks the panels for the parity tests."""
+    E, NU = 25.85e9, 0.18
+    h = 0.005
+    gs = h * 40.0
+    models = [ParticleModel(CorotatedLinearElasticity(E, NU)),
+              ParticleModel(CorotatedLinearElasticity(E, NU), None, MaximumStressFailure(2.7e6, 3.4028235e38))]
+    panel = np.array([[0.0, 0.0], [0.25, 0.0], [0.25, 0.25], [0.5, 0.25], [0.5, 0.5], [0.0, 0.5]], np.float32) * np.float32(scale)
+    parts = [sample_polygon(panel, (gs, gs), 0, h / 4.0, 2500.0), sample_polygon(panel, (gs * 8.0, gs), 1, h / 4.0, 2500.0)]
+    pc = ParticleComponents.concatenate(parts)
+    cols = [CuboidCollider((1000.0, h * 10.0), (0.0, gs - h * 10.0))]
+    params = SolverParameters(boundary_handling=BoundaryHandling.Stick)
+    params.dt = 1.0 / 6000.0
+    return Scene("l_panel2", h, pc, models, cols, gravity=(0.0, 0.0), params=params)
+
+
 def model_block2(kind: str, ni=16, nj=16, seed: int = 21) -> Scene:
     """dim2 counterpart of scenes.model_block: a small pre-strained block over a cuboid floor for every constitutive / plastic /
     failure model: corotated | neo_hookean | fluid | sand | nacc | rankine | snow | failure | failure_split"""
@@ -179,4 +199,4 @@ def jitter(scene: Scene, amplitude: float, seed: int = 42) -> Scene:
     return scene
 
 
-SCENES = {"elasticity2": elasticity2, "fluids2": fluids2, "sand2": sand2, "basic2": basic2, "model_block2": model_block2}
+SCENES = {"elasticity2": elasticity2, "fluids2": fluids2, "sand2": sand2, "basic2": basic2, "l_panel2": l_panel2, "model_block2": model_block2}

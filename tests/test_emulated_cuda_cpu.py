@@ -298,6 +298,12 @@ def test_dim2_trimesh_on_the_emulation(emulated):
     T.test_trimesh_argument_errors_dim2()
 
 
+def test_remaining_example_scenes_on_the_emulation(emulated, oracle):
+    import tests.test_zscenes_gpu as T
+    T.test_sand_penetration3_against_the_rotated_heightfield_wall(oracle)
+    T.test_l_panel2_lockstep()
+
+
 def _dim2_scene():
     from sparkl_b200 import scenes2d
     return scenes2d.jitter(scenes2d.elasticity2(2, scale=0.3), 0.002, seed=9)
