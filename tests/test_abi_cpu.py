@@ -103,3 +103,16 @@ def test_custom_kernel_launcher_abi_and_example_build():
         assert hasattr(ex, name)
     from tests.host.emu2d import DEVMODEL
     assert ex.cu_sizeof_devmodel() == DEVMODEL.itemsize
+
+
+def test_abi_header_is_plain_c_in_both_dimensions(tmp_path):
+    """include/sparkl_abi.h is the drop-in boundary: it must compile as C11 (no C++-isms) for the dim3 and the dim2 build, and the wire
+    record of the migration entry points is 128 bytes in dim3"""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "sparkl_abi.h"\n#include <stdio.h>\nint main(void) { printf("%d %d %d\\n", (int)sizeof(SpkParticleRecord), (int)sizeof(SpkGpuCollider), '
+                   '(int)sizeof(SpkGpuGridNode)); return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for dim, want in ((3, "128 336 72"), (2, "104 72 56")):
+        exe = str(tmp_path / f"abi{dim}")
+        subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", f"-DSPK_DIM={dim}", "-I" + inc, str(src), "-o", exe])
+        assert subprocess.check_output([exe]).decode().strip() == want
