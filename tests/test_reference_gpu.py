@@ -169,3 +169,9 @@ def test_sand_in_a_polyline_trough_against_reference_kernels(ref):
     trough = np.array([[-1.03, 0.31], [-1.03, 6.1], [-1.52, 6.1], [-1.52, -0.53], [3.51, -0.53], [3.51, 6.1], [3.07, 6.1], [3.07, 0.31]], np.float32)
     sc.colliders = [abi.PolylineCollider(trough)]
     _lockstep(sc, ref, 8, 2e-5)
+
+
+@_unverified
+def test_sand_penetration3_rotated_heightfields_against_reference_kernels(ref):
+    """examples3d/sand_penetration3.rs: four heightfields, three of them rotated — through the reference's own kernels"""
+    _lockstep(scenes.jitter(scenes.sand_penetration3(8, 6, 6, origin=(0.0, 13.7, 3.52)), 0.02, seed=12), ref, 8, 2e-5)
