@@ -380,8 +380,12 @@ int spk_models_upload(spk_ctx* ctx, const SpkGpuParticleModel* models, size_t n)
 int spk_colliders_upload(spk_ctx* ctx, const SpkGpuCollider* colliders, size_t n);
 
 /* CudaMpmPipeline::step (cuda_mpm_pipeline.rs:262-659): advances all contexts by params->dt with adaptive
- * substeps; writes the simulated time (params.dt - remaining) to *simulated_time_out.  nctx must be 1 per
- * process (one process per GPU; multi-GPU runs attach the contexts with spk_dist_* and then call spk_step on every rank).
+ * substeps; writes the simulated time (params.dt - remaining) to *simulated_time_out.  The fast multi-GPU path is one process
+ * per GPU with nctx == 1 (attach the contexts with spk_dist_* and call spk_step on every rank).  nctx > 1 is the reference's own
+ * calling convention — one host thread driving several contexts, which may sit on different devices or on one: every substep the
+ * active block keys are gathered, shared blocks tagged, dt reduced over the contexts and the shared blocks exchanged with
+ * device-to-device copies and merged (cuda_mpm_pipeline.rs:329-351, 393-398, 458-532); a compatibility path, synchronous, with
+ * only num_substeps / last_dt / block counts filled in the timings.
  * With timings_or_null == NULL the call returns once the frame is ENQUEUED (every substep still reads its 64-byte counter
  * record back, so only the tail of the last substep is outstanding): consecutive frames then run back to back on the GPU.
  * All other entry points are ordered on the context's stream; spk_ctx_synchronize() waits for completion. */

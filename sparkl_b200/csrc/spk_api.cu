@@ -987,10 +987,160 @@ int spk_stage_grid_update(spk_ctx* c, float dt, const float gravity[SPK_DIM]) {
     return SPK_OK;
 }
 
+// CudaMpmPipeline::step with SEVERAL contexts driven serially by one host thread — the reference's own multi-GPU mode
+// (cuda_mpm_pipeline.rs:262-659: per substep every context sorts, the active block headers are gathered and shared blocks tagged
+// :329-351 / cuda_sparse_grid.rs:256-322, dt is the minimum over the devices :393-398, the halo blocks are copied between the devices
+// :458-472 and merged :512-532).  A compatibility path for hosts that keep that calling convention: it sequences the portable halo
+// protocol (spk_halo_*) with device-to-device copies; the fast multi-GPU path is one process per GPU over NVLink peer memory
+// (spk_dist_attach + plain spk_step).  Contexts may live on the same device.
+namespace {
+struct MultiScratch { // per context, on the context's device; grown on demand, freed when the call returns
+    unsigned long long *keys = nullptr, *rkeys = nullptr, *hk = nullptr, *rhk = nullptr;
+    float *hp = nullptr, *rhp = nullptr;
+    uint32_t kcap = 0, hcap = 0;
+};
+struct MultiScratchSet {
+    std::vector<MultiScratch> s;
+    std::vector<spk_ctx*> ctx;
+    ~MultiScratchSet() {
+        for (size_t i = 0; i < s.size(); ++i) {
+            cudaSetDevice(ctx[i]->device);
+            cudaStreamSynchronize(ctx[i]->stream);
+            cudaFree(s[i].keys); cudaFree(s[i].rkeys); cudaFree(s[i].hk); cudaFree(s[i].rhk); cudaFree(s[i].hp); cudaFree(s[i].rhp);
+        }
+    }
+};
+int sync_all(spk_ctx** ctxs, size_t nctx) {
+    for (size_t i = 0; i < nctx; ++i) { CK(cudaSetDevice(ctxs[i]->device)); CK(cudaStreamSynchronize(ctxs[i]->stream)); }
+    return SPK_OK;
+}
+int step_multi(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float* gravity, SpkStepTimings* timings, float* simulated_time_out) {
+    constexpr size_t PAYLOAD = (size_t)SPK_ACC_CHANNELS * SPK_CELLS_PER_BLOCK;
+    for (size_t i = 0; i < nctx; ++i) {
+        if (!ctxs[i]) return SPK_EINVAL;
+        if (spk_dist_active(ctxs[i])) return SPK_ESTATE; // attached to the peer-memory path: one context per process there
+        if (ctxs[i]->cell_width != ctxs[0]->cell_width) return SPK_EINVAL;
+        for (size_t j = 0; j < i; ++j) if (ctxs[j] == ctxs[i]) return SPK_EINVAL;
+    }
+    if (timings) std::memset(timings, 0, sizeof(*timings));
+    int rc;
+    for (size_t i = 0; i < nctx; ++i) {
+        spk_ctx* c = ctxs[i];
+        if ((rc = spk_frame_begin(c, params))) return rc;
+        if (c->launcher.timestep_started && (rc = c->launcher.timestep_started(c->launcher.user))) return rc;
+    }
+    size_t total = 0;
+    for (size_t i = 0; i < nctx; ++i) total += ctxs[i]->n;
+    if (params->dt == 0.0f || total == 0) {
+        if (simulated_time_out) *simulated_time_out = params->dt;
+        return SPK_OK;
+    }
+    MultiScratchSet scratch;
+    scratch.s.resize(nctx);
+    scratch.ctx.assign(ctxs, ctxs + nctx);
+    const float min_dt = params->dt / (float)params->max_num_substeps;
+    float remaining = params->dt, dt = 0.f;
+    uint32_t niter = 0;
+    std::vector<SpkSortInfo> info(nctx);
+    while (remaining > 0.0f) {
+        ++niter;
+        uint32_t max_nab = 0;
+        for (size_t i = 0; i < nctx; ++i) {
+            if ((rc = spk_stage_sort(ctxs[i], &info[i]))) return rc;
+            max_nab = std::max(max_nab, info[i].num_active_blocks);
+        }
+        // ---- gather the active block keys and tag the shared blocks (cuda_sparse_grid.rs:256-322)
+        const uint32_t kcap = (max_nab + 255u) / 256u * 256u;
+        for (size_t i = 0; i < nctx; ++i) {
+            spk_ctx* c = ctxs[i];
+            MultiScratch& m = scratch.s[i];
+            CK(cudaSetDevice(c->device));
+            if (m.kcap < kcap) {
+                CK(cudaStreamSynchronize(c->stream));
+                cudaFree(m.keys); cudaFree(m.rkeys); m.keys = m.rkeys = nullptr; m.kcap = 0;
+                CK(cudaMalloc((void**)&m.keys, (size_t)kcap * 8)); CK(cudaMalloc((void**)&m.rkeys, (size_t)kcap * 8));
+                m.kcap = kcap;
+            }
+            if ((rc = spk_halo_begin(c))) return rc;
+            if ((rc = spk_halo_active_keys(c, (uint64_t*)m.keys, kcap))) return rc;
+        }
+        if ((rc = sync_all(ctxs, nctx))) return rc;
+        for (size_t i = 0; i < nctx; ++i) {
+            spk_ctx* c = ctxs[i];
+            CK(cudaSetDevice(c->device));
+            for (size_t o = 0; o < nctx; ++o) {
+                if (o == i) continue;
+                CK(cudaMemcpyPeerAsync(scratch.s[i].rkeys, c->device, scratch.s[o].keys, ctxs[o]->device, (size_t)kcap * 8, c->stream));
+                if ((rc = spk_halo_tag(c, (const uint64_t*)scratch.s[i].rkeys, kcap))) return rc;
+            }
+            CK(spk_launch_reset_grid(c));
+        }
+        // ---- dt: the minimum over the contexts (cuda_mpm_pipeline.rs:381-398)
+        unsigned long long acc = ~0ull;
+        for (size_t i = 0; i < nctx; ++i) {
+            if ((rc = spk_stage_estimate_dt(ctxs[i], min_dt, std::fmin(remaining, params->max_substep_dt), nullptr))) return rc;
+            acc = std::min(acc, ctxs[i]->dt_acc_host);
+        }
+        for (size_t i = 0; i < nctx; ++i) ctxs[i]->dt_acc_host = acc;
+        dt = host_dt_into_sec(acc);
+        uint32_t max_halo = 0;
+        for (size_t i = 0; i < nctx; ++i) {
+            uint32_t nh = 0;
+            if ((rc = spk_halo_count(ctxs[i], &nh))) return rc;
+            max_halo = std::max(max_halo, nh);
+        }
+        // ---- transfers, then exchange and merge the shared blocks (:407-533)
+        for (size_t i = 0; i < nctx; ++i)
+            if (info[i].num_dispatch_blocks > 0 && (rc = launch_g2p2g_hooked(ctxs[i], dt))) return rc;
+        if (max_halo > 0) {
+            const uint32_t hcap = (max_halo + 255u) / 256u * 256u;
+            for (size_t i = 0; i < nctx; ++i) {
+                spk_ctx* c = ctxs[i];
+                MultiScratch& m = scratch.s[i];
+                CK(cudaSetDevice(c->device));
+                if (m.hcap < hcap) {
+                    CK(cudaStreamSynchronize(c->stream));
+                    cudaFree(m.hk); cudaFree(m.rhk); cudaFree(m.hp); cudaFree(m.rhp); m.hk = m.rhk = nullptr; m.hp = m.rhp = nullptr; m.hcap = 0;
+                    CK(cudaMalloc((void**)&m.hk, (size_t)hcap * 8)); CK(cudaMalloc((void**)&m.rhk, (size_t)hcap * 8));
+                    CK(cudaMalloc((void**)&m.hp, (size_t)hcap * PAYLOAD * 4)); CK(cudaMalloc((void**)&m.rhp, (size_t)hcap * PAYLOAD * 4));
+                    m.hcap = hcap;
+                }
+                if ((rc = spk_halo_pack(c, (uint64_t*)m.hk, m.hp, hcap))) return rc;
+            }
+            if ((rc = sync_all(ctxs, nctx))) return rc;
+            for (size_t i = 0; i < nctx; ++i) {
+                spk_ctx* c = ctxs[i];
+                CK(cudaSetDevice(c->device));
+                for (size_t o = 0; o < nctx; ++o) {
+                    if (o == i) continue;
+                    CK(cudaMemcpyPeerAsync(scratch.s[i].rhk, c->device, scratch.s[o].hk, ctxs[o]->device, (size_t)hcap * 8, c->stream));
+                    CK(cudaMemcpyPeerAsync(scratch.s[i].rhp, c->device, scratch.s[o].hp, ctxs[o]->device, (size_t)hcap * PAYLOAD * 4, c->stream));
+                    if ((rc = spk_halo_merge(c, (const uint64_t*)scratch.s[i].rhk, scratch.s[i].rhp, hcap))) return rc;
+                }
+            }
+        }
+        for (size_t i = 0; i < nctx; ++i) {
+            CK(cudaSetDevice(ctxs[i]->device));
+            CK(spk_launch_grid_update(ctxs[i], dt, gravity));
+        }
+        remaining -= dt;
+        if (remaining <= 10.0f / DT_FACTOR || params->stop_after_one_substep) break;
+    }
+    if ((rc = sync_all(ctxs, nctx))) return rc;
+    if (timings) {
+        timings->num_substeps = niter;
+        timings->last_dt = dt;
+        for (size_t i = 0; i < nctx; ++i) { timings->num_active_blocks += info[i].num_active_blocks; timings->num_dispatch_blocks += info[i].num_dispatch_blocks; }
+    }
+    if (simulated_time_out) *simulated_time_out = params->dt - remaining;
+    return SPK_OK;
+}
+} // namespace
+
 // CudaMpmPipeline::step_generic, cuda_mpm_pipeline.rs:273-659
 int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, const float gravity[SPK_DIM], SpkStepTimings* timings, float* simulated_time_out) {
     if (!ctxs || nctx == 0 || !params || !gravity) return SPK_EINVAL;
-    if (nctx != 1) return SPK_EUNSUPPORTED; // one process per GPU; multi-GPU runs drive the stage + halo calls (sparkl_b200/distributed.py)
+    if (nctx != 1) return step_multi(ctxs, nctx, params, gravity, timings, simulated_time_out);
     spk_ctx* c = ctxs[0];
     if (!c) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));

@@ -243,14 +243,16 @@ class CudaMpmPipeline:
         self.step_id = 0
 
     def step(self, params: abi.SolverParameters, gravity, contexts, timings: bool = True):
-        if len(contexts) != 1:
-            raise abi.SparklError(abi.EUNSUPPORTED, "one process per GPU: use sparkl_b200.distributed for multi-GPU runs")
+        """several contexts = the reference's in-process multi-GPU mode (one host thread drives all devices, shared grid blocks are
+        exchanged between the contexts every substep): a compatibility path; the fast one is one process per GPU, sparkl_b200.distributed"""
+        if len(contexts) == 0:
+            raise abi.SparklError(abi.EINVAL, "no context")
         ctx = contexts[0]
         g = (C.c_float * 3)(*gravity)
         t = abi.StepTimings()
         sim = C.c_float()
-        arr = (C.c_void_p * 1)(ctx._h)
-        rc = ctx._lib.spk_step(arr, 1, C.byref(params), C.byref(g), C.byref(t) if timings else None, C.byref(sim))
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        rc = ctx._lib.spk_step(arr, len(contexts), C.byref(params), C.byref(g), C.byref(t) if timings else None, C.byref(sim))
         if rc:
             raise abi.SparklError(rc, "spk_step: " + error_string(rc, getattr(ctx, "dim", 3)))
         self.step_id += t.num_substeps

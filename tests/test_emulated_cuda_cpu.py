@@ -304,6 +304,11 @@ def test_remaining_example_scenes_on_the_emulation(emulated, oracle):
     T.test_l_panel2_lockstep()
 
 
+def test_several_contexts_in_one_step_call_on_the_emulation(emulated, oracle):
+    import tests.test_zscenes_gpu as T
+    T.test_several_contexts_in_one_call(oracle)
+
+
 def _dim2_scene():
     from sparkl_b200 import scenes2d
     return scenes2d.jitter(scenes2d.elasticity2(2, scale=0.3), 0.002, seed=9)

@@ -27,3 +27,39 @@ def test_sand_penetration3_against_the_rotated_heightfield_wall(oracle):
 def test_l_panel2_lockstep():
     sc = scenes2d.jitter(scenes2d.l_panel2(0.25), 0.0002, seed=3)
     D2._run(sc, 5)
+
+
+def test_several_contexts_in_one_call(oracle):
+    """`CudaMpmPipeline::step(.., contexts: &mut [SingleGpuMpmContext])` with more than one context (the reference's in-process multi-GPU
+    mode, cuda_mpm_pipeline.rs:262-659): the particles of a scene are dealt out to three contexts (interleaved: every block is shared),
+    one spk_step call advances them all; the union equals the single-context oracle run.  (Contexts on one device here.)"""
+    from sparkl_b200.pipeline import CudaMpmPipeline, SingleGpuMpmContext
+    from tests import util
+    sc = scenes.jitter(scenes.sand3(10, 5, 6), 0.02, seed=5)
+    n = len(sc.particles)
+    parts = [np.arange(n)[k::3].copy() for k in range(3)]
+    ctxs = []
+    for ids in parts:
+        c = SingleGpuMpmContext(sc.cell_width)
+        c.models_upload(sc.models); c.colliders_upload(sc.colliders)
+        c.upload(sc.particles.take(ids))
+        ctxs.append(c)
+    o = oracle.OracleEngine(sc.cell_width)
+    o.models_upload(sc.models); o.colliders_upload(sc.colliders); o.upload(sc.particles)
+    pipe = CudaMpmPipeline()
+    for _ in range(2):
+        sim, t = pipe.step(sc.params, sc.gravity, ctxs)
+        so, to = o.step(sc.params, sc.gravity)
+        assert t.num_substeps == to.num_substeps and abs(sim - so) < 1e-7
+    ref = o.read_all()
+    pos = np.zeros(n, abi.POSITION); vel = np.zeros(n, abi.VELOCITY); vol = np.zeros(n, abi.VOLUME)
+    for ids, c in zip(parts, ctxs):
+        pc = c.read_all()
+        pos[ids], vel[ids], vol[ids] = pc.position, pc.velocity, pc.volume
+    assert util.rel_err(pos["point"], ref.position["point"]) < 2e-5
+    assert util.rel_err(vel["vector"], ref.velocity["vector"], floor=1e-2) < 2e-3
+    assert util.rel_err(vol["deformation_gradient"], ref.volume["deformation_gradient"], floor=1.0) < 2e-4
+    # a context cannot be listed twice
+    with pytest.raises(abi.SparklError) as e:
+        pipe.step(sc.params, sc.gravity, [ctxs[0], ctxs[0]])
+    assert e.value.code == abi.EINVAL
