@@ -307,6 +307,7 @@ def test_remaining_example_scenes_on_the_emulation(emulated, oracle):
 def test_several_contexts_in_one_step_call_on_the_emulation(emulated, oracle):
     import tests.test_zscenes_gpu as T
     T.test_several_contexts_in_one_call(oracle)
+    T.test_several_contexts_in_one_call_dim2()
 
 
 def _dim2_scene():

@@ -63,3 +63,34 @@ def test_several_contexts_in_one_call(oracle):
     with pytest.raises(abi.SparklError) as e:
         pipe.step(sc.params, sc.gravity, [ctxs[0], ctxs[0]])
     assert e.value.code == abi.EINVAL
+
+
+def test_several_contexts_in_one_call_dim2():
+    """the same in the dim2 build (96 floats per shared block): two contexts vs the single-context dim2 oracle"""
+    from oracle import binding as ob
+    from sparkl_b200 import abi2d
+    from sparkl_b200.pipeline import CudaMpmPipeline, SingleGpuMpmContext
+    from tests import util
+    sc = scenes2d.jitter(scenes2d.elasticity2(2, scale=0.3), 0.002, seed=9)
+    n = len(sc.particles)
+    parts = [np.arange(n)[k::2].copy() for k in range(2)]
+    ctxs = []
+    for ids in parts:
+        c = SingleGpuMpmContext(sc.cell_width, dim=2)
+        c.models_upload(sc.models); c.colliders_upload(sc.colliders)
+        c.upload(sc.particles.take(ids))
+        ctxs.append(c)
+    o = ob.OracleEngine2D(sc.cell_width)
+    o.models_upload(sc.models); o.colliders_upload(sc.colliders); o.upload(sc.particles)
+    pipe = CudaMpmPipeline()
+    for _ in range(2):
+        sim, t = pipe.step(sc.params, sc.gravity, ctxs)
+        so, to = o.step(sc.params, sc.gravity)
+        assert t.num_substeps == to.num_substeps
+    ref = o.read_all()
+    pos = np.zeros(n, abi2d.POSITION); vel = np.zeros(n, abi2d.VELOCITY)
+    for ids, c in zip(parts, ctxs):
+        pc = c.read_all()
+        pos[ids], vel[ids] = pc.position, pc.velocity
+    assert util.rel_err(pos["point"], ref.position["point"]) < 2e-5
+    assert util.rel_err(vel["vector"], ref.velocity["vector"], floor=1e-2) < 2e-3
