@@ -88,7 +88,9 @@ cudaError_t alloc_grid(spk_ctx* c, GridBuffers& g, uint32_t cap_hash) {
 cudaError_t ensure_slot_scratch(spk_ctx* c, uint32_t cap_hash) {
     if (c->slot_cnt_cap >= cap_hash) return cudaSuccess;
     dev_free(c->slot_cnt);
+    dev_free(c->cell_cnt);
     cudaError_t e = dev_alloc(c->slot_cnt, cap_hash);
+    if (e == cudaSuccess) e = dev_alloc(c->cell_cnt, (size_t)cap_hash * SPK_CELLS_PER_BLOCK);
     c->slot_cnt_cap = e == cudaSuccess ? cap_hash : 0;
     return e;
 }
@@ -401,8 +403,15 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     c->cell_width = cell_width;
     c->sm_count = prop.multiProcessorCount;
     c->chunk = SPK_G2P2G_CHUNK;
+#if SPK_DIM == 3
+    // 2 (default): cell-coherent kernel, 512 particles per dispatch entry; 1: round-1 cell-binned kernel; 0: per-particle shared atomics
+    // (the last two with 256-particle entries; kept for A/B profiling, SPK_G2P2G_MODE)
+    c->g2p2g_mode = 2;
+    if (const char* m = getenv("SPK_G2P2G_MODE")) { const int v = atoi(m); c->g2p2g_mode = v < 0 ? 0 : (v > 2 ? 2 : v); }
+    if (c->g2p2g_mode == 2) c->chunk = 512;
+#else
     c->g2p2g_mode = 1;
-    if (const char* m = getenv("SPK_G2P2G_MODE")) c->g2p2g_mode = atoi(m) ? 1 : 0; // A/B switch for profiling
+#endif
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
@@ -438,7 +447,7 @@ int spk_ctx_destroy(spk_ctx* c) {
     if (c->dist_arena) { c->grid[0].external_hash = c->grid[1].external_hash = 1; }
     free_particles(c);
     free_grid(c->grid[0]); free_grid(c->grid[1]);
-    dev_free(c->slot_cnt); dev_free(c->dispatch); dev_free(c->models); dev_free(c->colliders); dev_free(c->collider_data); dev_free(c->d_counters);
+    dev_free(c->slot_cnt); dev_free(c->cell_cnt); dev_free(c->dispatch); dev_free(c->models); dev_free(c->colliders); dev_free(c->collider_data); dev_free(c->d_counters);
     if (c->staging) cudaFree(c->staging);
     cudaStreamSynchronize(c->halo_stream);
     for (int k = 0; k < 8; ++k) {

@@ -446,6 +446,338 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
     }
 }
 
+
+// ================================================================================================================================
+// MODE 2 (default): the cell-coherent kernel.  The sort orders particles by (block, cell) (spk_sort.cu), a dispatch entry holds up to
+// 512 particles of one block, and a CTA of 256 threads walks it in two passes of one particle per thread:
+//   * a warp's 32 consecutive particles sit in a handful of cells, so the 27 velocity loads of G2P are shared-memory broadcasts;
+//   * every particle leaves its P2G payload (20 floats) in shared memory at its own slot and is stored to the next buffer at once
+//     (nothing of it stays in registers across the in-CTA cell sort, which only moves 16-bit slot numbers);
+//   * the per-CTA fixed work (tile staging, zeroing, scan, flush: 8 TMA loads + 8 TMA reduce-adds) is paid once per 512 particles and
+//     the P2G bins hold twice the particles of a 256-particle chunk (the per-bin flush is the expensive part of P2G).
+constexpr int C_CHUNK = 512;                  // particles per dispatch entry
+constexpr int C_ITERS = C_CHUNK / G2P2G_THREADS;
+constexpr int C_PAY = 20;                     // floats per staged payload
+constexpr int CS_VEL = 0;                                    // float4[512]
+constexpr int CS_ACC = CS_VEL + 512 * 16;                    // float[8][6][64]
+constexpr int CS_PAY = CS_ACC + 8 * 6 * 64 * 4;              // float[512][20]
+constexpr int CS_BINCNT = CS_PAY + C_CHUNK * C_PAY * 4;      // int[224]
+constexpr int CS_BINSTART = CS_BINCNT + 224 * 4;             // int[224]
+constexpr int CS_BINLIST = CS_BINSTART + 224 * 4;            // u16[224] occupied bins
+constexpr int CS_SORTED = CS_BINLIST + 224 * 2;              // u16[512] slot numbers in bin order
+constexpr int CS_BINOF = CS_SORTED + C_CHUNK * 2;            // u16[512] bin of slot s
+constexpr int CS_RANK = CS_BINOF + C_CHUNK * 2;              // u16[512] rank of slot s inside its bin
+constexpr int CS_MISC = CS_RANK + C_CHUNK * 2;               // mbarrier (8) + nbr_self[8] + nbr_prev[8] + nnz + dtmin
+constexpr int CS_HALO = CS_MISC + 8 + 32 + 32 + 16;
+constexpr int CS_TOTAL = CS_HALO + 32;
+
+template <class Updater>
+__global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_cell_kernel(const G2P2GParams P) {
+#ifdef SPK_EMU
+    unsigned char* smem = emu::dynamic_smem();
+#else
+    extern __shared__ __align__(128) unsigned char smem[];
+#endif
+    float4* s_vel = reinterpret_cast<float4*>(smem + CS_VEL);
+    float* s_acc = reinterpret_cast<float*>(smem + CS_ACC);
+    float* s_pay = reinterpret_cast<float*>(smem + CS_PAY);
+    int* s_bin_cnt = reinterpret_cast<int*>(smem + CS_BINCNT);
+    int* s_bin_start = reinterpret_cast<int*>(smem + CS_BINSTART);
+    unsigned short* s_binlist = reinterpret_cast<unsigned short*>(smem + CS_BINLIST);
+    unsigned short* s_sorted = reinterpret_cast<unsigned short*>(smem + CS_SORTED);
+    unsigned short* s_binof = reinterpret_cast<unsigned short*>(smem + CS_BINOF);
+    unsigned short* s_rank = reinterpret_cast<unsigned short*>(smem + CS_RANK);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + CS_MISC);
+    int* s_nbr_self = reinterpret_cast<int*>(smem + CS_MISC + 8);
+    int* s_nbr_prev = reinterpret_cast<int*>(smem + CS_MISC + 40);
+    int* s_nnz = reinterpret_cast<int*>(smem + CS_MISC + 72);
+    unsigned* s_dtmin = reinterpret_cast<unsigned*>(smem + CS_MISC + 76);
+    uint32_t* s_halo = reinterpret_cast<uint32_t*>(smem + CS_HALO);
+
+    const int tid = threadIdx.x;
+    const DispatchEntry ent = P.dispatch[blockIdx.x];
+    if (tid < 8) {
+        const int nid = P.nbr_self[ent.block * 8 + tid];
+        s_nbr_self[tid] = nid;
+        s_nbr_prev[tid] = P.nbr_prev[ent.block * 8 + tid];
+        s_halo[tid] = (P.world > 1 && nid >= 0) ? P.blk_halo[nid] : 0u;
+    }
+    if (tid == 0) { mbar_init(s_bar, 1); *s_dtmin = SPK_DT_RAW_NONE; }
+    for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64; i += G2P2G_THREADS) s_acc[i] = 0.f;
+    if (tid < 224) s_bin_cnt[tid] = 0;
+    __syncthreads();
+    // ---- stage 0: velocity tile of the 2x2x2 blocks (transfer_global_blocks_to_shared_memory, g2p2g.rs:353-474)
+    if (tid == 0) {
+        uint32_t bytes = 0;
+        for (int o = 0; o < 8; ++o) bytes += s_nbr_prev[o] >= 0 ? 1024u : 0u;
+        fence_proxy_async();
+        mbar_expect_tx(s_bar, bytes);
+        for (int o = 0; o < 8; ++o)
+            if (s_nbr_prev[o] >= 0) tma_load_1d(&s_vel[o * 64], P.prev_vel + (size_t)s_nbr_prev[o] * 64, 1024u, s_bar);
+    }
+    for (int i = tid; i < SPK_TILE_CELLS; i += G2P2G_THREADS)
+        if (s_nbr_prev[i >> 6] < 0) s_vel[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const float h = P.h, inv_h = P.inv_h, dt = P.dt;
+    const float inv_d = 4.f / (h * h);
+
+    // ---- stage 1: two passes, one particle per thread and pass ---------------------------------------------------------------
+#pragma unroll 1
+    for (int it = 0; it < C_ITERS; ++it) {
+        const int s = it * G2P2G_THREADS + tid; // slot of the particle inside the dispatch entry
+        const bool has_particle = (uint32_t)s < ent.count;
+        ParticleState p;
+        float vel[3] = {0.f, 0.f, 0.f};
+        Mat3 G = mat_zero();
+        Mat3 stress = mat_zero();
+        bool do_p2g = false;
+        int tcell[3] = {1, 1, 1};
+        float cell_before[3] = {0.f, 0.f, 0.f};
+        float ref[3], w[3][3];
+        if (has_particle) {
+            const uint32_t si = P.perm[ent.first + s];
+            const float4 r0 = P.src.a0[si], r1 = P.src.a1[si], r2 = P.src.a2[si], r3 = P.src.a3[si], r4 = P.src.a4[si], r5 = P.src.a5[si];
+            p.x[0] = r0.x; p.x[1] = r0.y; p.x[2] = r0.z; p.flags = __float_as_uint(r0.w);
+            p.F.m[0] = r1.x; p.F.m[1] = r1.y; p.F.m[2] = r1.z; p.F.m[3] = r1.w;
+            p.F.m[4] = r2.x; p.F.m[5] = r2.y; p.F.m[6] = r2.z; p.F.m[7] = r2.w;
+            p.F.m[8] = r3.x; p.jp = r3.y; p.mass = r3.z; p.volume0 = r3.w;
+            p.phase = r4.x; p.psi_pos = r4.y; p.elastic_hardening = r4.z; p.plastic_hardening = r4.w;
+            p.log_vol_gain = r5.x; p.nacc_alpha = r5.y; p.orig_id = __float_as_uint(r5.z);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float q = roundf(spk_div_h(p.x[a], h, inv_h));
+                cell_before[a] = q;
+                ref[a] = (q - 1.f) * h - p.x[a];               // dir_to_associated_grid_node, particle.rs:37-47
+                quad_weights(spk_div_h(-ref[a], h, inv_h), w[a]);
+                const int assoc_cell = (q != q) ? -2 : (int)__float2ll_rz(q) - 2;
+                tcell[a] = (assoc_cell & 3) + 1;                // associated_cell_index_in_block_off_by_two, particle.rs:28-35
+            }
+        }
+        if (it == 0) { // the tile is complete (TMA) and the absent octants are zero-filled
+            mbar_wait(s_bar, 0);
+            __syncthreads();
+        }
+
+        if (has_particle) {
+            const DevModel& model = P.models[p.flags >> SPK_F_MODEL_SHIFT];
+            // ---- G2P (particle_g2p2g, g2p2g.rs:192-245), separable accumulation: rows along x, then planes, then volume.
+            {
+                float V[3] = {0.f, 0.f, 0.f}, Gx[3] = {0.f, 0.f, 0.f}, Gy[3] = {0.f, 0.f, 0.f}, Gz[3] = {0.f, 0.f, 0.f};
+                const float wpx[3] = {w[0][0] * ref[0], w[0][1] * (ref[0] + h), w[0][2] * (ref[0] + 2.f * h)};
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                    const int iz = cell_part(tcell[2] + dz, 2) | (oct_part(tcell[2] + dz, 2) << 6);
+                    float P0[3] = {0.f, 0.f, 0.f}, P1[3] = {0.f, 0.f, 0.f}, P2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const int iy = iz | cell_part(tcell[1] + dy, 1) | (oct_part(tcell[1] + dy, 1) << 6);
+                        float R0[3] = {0.f, 0.f, 0.f}, R1[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float4 c = s_vel[iy | cell_part(tcell[0] + dx, 0) | (oct_part(tcell[0] + dx, 0) << 6)];
+                            R0[0] += w[0][dx] * c.x; R0[1] += w[0][dx] * c.y; R0[2] += w[0][dx] * c.z;
+                            R1[0] += wpx[dx] * c.x; R1[1] += wpx[dx] * c.y; R1[2] += wpx[dx] * c.z;
+                        }
+                        const float wy = w[1][dy], wpy = wy * (ref[1] + (float)dy * h);
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) { P0[a] += wy * R0[a]; P1[a] += wy * R1[a]; P2[a] += wpy * R0[a]; }
+                    }
+                    const float wz = w[2][dz], wpz = wz * (ref[2] + (float)dz * h);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { V[a] += wz * P0[a]; Gx[a] += wz * P1[a]; Gy[a] += wz * P2[a]; Gz[a] += wpz * P0[a]; }
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    vel[a] = V[a];
+                    M_(G, a, 0) = Gx[a] * inv_d; M_(G, a, 1) = Gy[a] * inv_d; M_(G, a, 2) = Gz[a] * inv_d;
+                }
+            }
+            do_p2g = Updater::update(model, P.cold, h, dt, p, vel, G, stress, P.user);
+        }
+
+        // ---- fused K15 (timestep.rs:38-113): un-clamped dt candidate of this particle for the NEXT substep
+        {
+            unsigned cand_bits = SPK_DT_RAW_NONE;
+            if (has_particle && !(p.flags & SPK_F_FAILED)) {
+                const DevModel& model = P.models[p.flags >> SPK_F_MODEL_SHIFT];
+                const float cand = Updater::dt_candidate(model, h, p, vel, P.user);
+                cand_bits = __float_as_uint(cand != cand ? 1.0e30f : fminf(fmaxf(cand, 0.f), 1.0e30f)); // NaN imposes no bound (Rust f32::min ignores NaN)
+            }
+            cand_bits = __reduce_min_sync(0xffffffffu, cand_bits);
+            if ((tid & 31) == 0 && cand_bits < SPK_DT_RAW_NONE) atomicMin(s_dtmin, cand_bits);
+        }
+
+        // ---- the particle is final: store it (slot order == sorted order of this substep; the next sort re-orders by cell)
+        if (has_particle) {
+            const uint32_t di = ent.first + (uint32_t)s;
+            P.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
+            P.dst.a1[di] = make_float4(p.F.m[0], p.F.m[1], p.F.m[2], p.F.m[3]);
+            P.dst.a2[di] = make_float4(p.F.m[4], p.F.m[5], p.F.m[6], p.F.m[7]);
+            P.dst.a3[di] = make_float4(p.F.m[8], p.jp, p.mass, p.volume0);
+            P.dst.a4[di] = make_float4(p.phase, p.psi_pos, p.elastic_hardening, p.plastic_hardening);
+            P.dst.a5[di] = make_float4(p.log_vol_gain, p.nacc_alpha, __uint_as_float(p.orig_id), 0.f);
+            P.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
+        }
+
+        // ---- P2G preparation with the UPDATED position (g2p2g.rs:280-309): stencil-base cell (bin) and the payload
+        //   q0 = {m, c.xyz}  c = A ref2 + m v        q1 = {h A[:,0], psi_mass}   q2 = {h A[:,1], psi_mom}   q3 = {h A[:,2], fy}
+        //   q4 = {wx0, wx1, wx2, fz}                 A = m G - (volume0 inv_d dt) stress,  fy / fz: B-spline arguments along y / z
+        int bin = NBINS;
+        if (has_particle && do_p2g) {
+            float ref2[3], f2[3];
+            int t2[3];
+            bool inside = true;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float q = roundf(spk_div_h(p.x[a], h, inv_h));
+                ref2[a] = (q - 1.f) * h - p.x[a];
+                f2[a] = spk_div_h(-ref2[a], h, inv_h);
+                const float mvf = q - cell_before[a];
+                const int mv = (mvf != mvf) ? 0 : (int)__float2ll_rz(mvf);
+                t2[a] = tcell[a] + mv; // in [0, 5] after the velocity clamp
+                inside = inside && t2[a] >= 0 && t2[a] <= 5;
+            }
+            if (inside) {
+                bin = t2[0] + 6 * t2[1] + 36 * t2[2];
+                const float ks = p.volume0 * inv_d * dt;
+                Mat3 A;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) A.m[i] = p.mass * G.m[i] - ks * stress.m[i];
+                const float psi_mass = (p.phase > 0.f && !(p.flags & SPK_F_FAILED)) ? p.mass : 0.f;
+                float wx[3];
+                quad_weights(f2[0], wx);
+                float4* q = reinterpret_cast<float4*>(s_pay + (size_t)s * C_PAY);
+                q[0] = make_float4(p.mass, M_(A, 0, 0) * ref2[0] + M_(A, 0, 1) * ref2[1] + M_(A, 0, 2) * ref2[2] + p.mass * vel[0],
+                                   M_(A, 1, 0) * ref2[0] + M_(A, 1, 1) * ref2[1] + M_(A, 1, 2) * ref2[2] + p.mass * vel[1],
+                                   M_(A, 2, 0) * ref2[0] + M_(A, 2, 1) * ref2[1] + M_(A, 2, 2) * ref2[2] + p.mass * vel[2]);
+                q[1] = make_float4(h * M_(A, 0, 0), h * M_(A, 1, 0), h * M_(A, 2, 0), psi_mass);
+                q[2] = make_float4(h * M_(A, 0, 1), h * M_(A, 1, 1), h * M_(A, 2, 1), psi_mass * p.psi_pos);
+                q[3] = make_float4(h * M_(A, 0, 2), h * M_(A, 1, 2), h * M_(A, 2, 2), f2[1]);
+                q[4] = make_float4(wx[0], wx[1], wx[2], f2[2]);
+            }
+        }
+        if (has_particle) {
+            s_binof[s] = (unsigned short)bin;
+            s_rank[s] = (unsigned short)atomicAdd(&s_bin_cnt[bin], 1);
+        }
+    }
+    __syncthreads();
+
+    // ---- counting sort of the slots by stencil-base cell (bin 216 = particles without P2G): exclusive scan by warp 0
+    if (tid < 32) {
+        int c[7], sum = 0, nz = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { c[k] = s_bin_cnt[tid * 7 + k]; sum += c[k]; nz += (c[k] != 0 && tid * 7 + k < NBINS) ? 1 : 0; }
+        int inc = sum, inz = nz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, inc, d), oz = __shfl_up_sync(0xffffffffu, inz, d);
+            if (tid >= d) { inc += o; inz += oz; }
+        }
+        int run = inc - sum, runz = inz - nz;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            s_bin_start[tid * 7 + k] = run;
+            run += c[k];
+            if (c[k] != 0 && tid * 7 + k < NBINS) s_binlist[runz++] = (unsigned short)(tid * 7 + k);
+        }
+        if (tid == 31) *s_nnz = inz;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < C_ITERS; ++it) {
+        const int s = it * G2P2G_THREADS + tid;
+        if ((uint32_t)s < ent.count) s_sorted[s_bin_start[s_binof[s]] + s_rank[s]] = (unsigned short)s;
+    }
+    __syncthreads();
+
+    // ---- stage 2: 9-lane groups, one occupied bin at a time; lane = stencil column (sy, sz), 3 nodes (sx = 0..2) x 6 channels in
+    // registers over the bin's particles (payload reads are broadcasts), then one flush of the 18 sums into the tile
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int grp = lane / 9, l9 = lane - grp * 9;
+        const int sy = l9 % 3, sz = l9 / 3;
+        const float fsy = (float)sy, fsz = (float)sz;
+        // QuadraticKernel::eval_all (kernel.rs:15-21) for ONE node: w_s(x) = A_s (x - B_s)^2 + C_s
+        const float Ay = sy == 1 ? -1.f : 0.5f, By = sy == 0 ? 1.5f : (sy == 1 ? 1.f : 0.5f), Cy = sy == 1 ? 0.75f : 0.f;
+        const float Az = sz == 1 ? -1.f : 0.5f, Bz = sz == 0 ? 1.5f : (sz == 1 ? 1.f : 0.5f), Cz = sz == 1 ? 0.75f : 0.f;
+        const int nnz = *s_nnz;
+        if (grp < 3) {
+            for (int e = warp * 3 + grp; e < nnz; e += (G2P2G_THREADS / 32) * 3) {
+                const int bin = s_binlist[e];
+                const int start = s_bin_start[bin], cnt = s_bin_cnt[bin];
+                float aM[3] = {0.f, 0.f, 0.f}, aX[3] = {0.f, 0.f, 0.f}, aY[3] = {0.f, 0.f, 0.f}, aZ[3] = {0.f, 0.f, 0.f}, aPm[3] = {0.f, 0.f, 0.f},
+                      aPp[3] = {0.f, 0.f, 0.f};
+                for (int i = 0; i < cnt; ++i) {
+                    const float* pay = s_pay + (size_t)s_sorted[start + i] * C_PAY;
+                    const float4 q0 = *reinterpret_cast<const float4*>(pay), q1 = *reinterpret_cast<const float4*>(pay + 4),
+                                 q2 = *reinterpret_cast<const float4*>(pay + 8), q3 = *reinterpret_cast<const float4*>(pay + 12),
+                                 q4 = *reinterpret_cast<const float4*>(pay + 16);
+                    const float dy = q3.w - By, dz = q4.w - Bz;
+                    const float wyz = fmaf(Ay * dy, dy, Cy) * fmaf(Az * dz, dz, Cz);
+                    // node momentum contribution at sx = 0: c + sy * hA[:,1] + sz * hA[:,2]
+                    float bx = q0.y + fsy * q2.x + fsz * q3.x, by = q0.z + fsy * q2.y + fsz * q3.y, bz = q0.w + fsy * q2.z + fsz * q3.z;
+                    const float wx[3] = {q4.x, q4.y, q4.z};
+#pragma unroll
+                    for (int sx = 0; sx < 3; ++sx) {
+                        const float wt = wx[sx] * wyz;
+                        aM[sx] += wt * q0.x;
+                        aX[sx] += wt * bx; aY[sx] += wt * by; aZ[sx] += wt * bz;
+                        aPm[sx] += wt * q1.w; aPp[sx] += wt * q2.w;
+                        bx += q1.x; by += q1.y; bz += q1.z;
+                    }
+                }
+                const int bxc = bin % 6, byc = (bin / 6) % 6, bzc = bin / 36;
+                const int byz = cell_part(byc + sy, 1) + oct_part(byc + sy, 1) * 384 + cell_part(bzc + sz, 2) + oct_part(bzc + sz, 2) * 384;
+#pragma unroll
+                for (int sx = 0; sx < 3; ++sx) {
+                    float* a = &s_acc[byz + cell_part(bxc + sx, 0) + oct_part(bxc + sx, 0) * 384];
+                    atomicAdd(a + 0 * 64, aM[sx]);
+                    atomicAdd(a + 1 * 64, aX[sx]);
+                    atomicAdd(a + 2 * 64, aY[sx]);
+                    atomicAdd(a + 3 * 64, aZ[sx]);
+                    if (aPp[sx] != 0.f) atomicAdd(a + 4 * 64, aPp[sx]);
+                    if (aPm[sx] != 0.f) atomicAdd(a + 5 * 64, aPm[sx]);
+                }
+            }
+        }
+    }
+
+    // ---- stage 3: flush the accumulation tile into the next grid (transfer_shared_blocks_to_grid, g2p2g.rs:476-553)
+    fence_proxy_async(); // make the generic-proxy smem writes visible to the async (TMA) proxy
+    __syncthreads();
+    if (tid == 0) {
+        for (int o = 0; o < 8; ++o) {
+            const int nid = s_nbr_self[o];
+            if (nid >= 0) tma_reduce_add_f32_1d(P.acc + (size_t)nid * (SPK_ACC_CHANNELS * 64), &s_acc[o * SPK_ACC_CHANNELS * 64], SPK_ACC_CHANNELS * 64 * 4);
+        }
+        bool pushed = false;
+        if (P.world > 1) { // fused halo push (multi-GPU), see g2p2g_kernel
+            for (int o = 0; o < 8; ++o) {
+                const int nid = s_nbr_self[o];
+                if (nid < 0 || !(s_halo[o] & 1u)) continue;
+                for (uint32_t r = 0; r < P.world; ++r) {
+                    const int32_t pid = P.peer_ids[(size_t)nid * P.world + r];
+                    if (pid >= 0) {
+                        tma_reduce_add_f32_1d(P.peer_hacc[r] + (size_t)pid * (SPK_ACC_CHANNELS * 64), &s_acc[o * SPK_ACC_CHANNELS * 64], SPK_ACC_CHANNELS * 64 * 4);
+                        pushed = true;
+                    }
+                }
+            }
+        }
+        if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(P.dt_raw_bits, *s_dtmin);
+        if (pushed) {
+#ifndef SPK_EMU
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+            __threadfence_system();
+        } else {
+            tma_commit_and_wait_read();
+        }
+    }
+}
+
 } // namespace spk_g2p2g_detail
 
 // DefaultCudaParticleKernelsLauncher::launch_g2p2g (src/cuda/cuda_particle_kernels.rs:64-99) for any updater; `user` reaches the
@@ -484,6 +816,7 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
         cudaError_t e = cudaFuncSetAttribute(g2p2g_kernel<0, Updater>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_kernel<1, Updater>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_cell_kernel<Updater>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_TOTAL);
         if (e != cudaSuccess) return e;
         if (c->device >= 0 && c->device < 64) configured[c->device] = true;
         c->g2p2g_configured = true;
@@ -491,7 +824,8 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     const bool timed = c->kev_on && c->kev_count < 256;
     if (timed) cudaEventRecord(c->kev[2 * c->kev_count], c->stream);
     if (c->g2p2g_mode == 0) g2p2g_kernel<0, Updater><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
-    else g2p2g_kernel<1, Updater><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
+    else if (c->g2p2g_mode == 1) g2p2g_kernel<1, Updater><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
+    else g2p2g_cell_kernel<Updater><<<nd, G2P2G_THREADS, CS_TOTAL, c->stream>>>(P);
     if (timed) { cudaEventRecord(c->kev[2 * c->kev_count + 1], c->stream); c->kev_count += 1; }
     c->launches += 1;
     c->g2p2g_launches += 1;

@@ -146,7 +146,7 @@ struct spk_ctx {
     float4* vel;     // vx, vy, vz, unused — aligned with pb[cur]
     float4* cold;    // kinematic_vel.xyz, radius0 — indexed by ORIGINAL particle id
     uint32_t* slot_of; // hash slot of the particle's block (current order)
-    uint32_t* rank_of; // rank inside its block
+    uint32_t* rank_of; // cell inside its block << (32 - SPK_CELL_SHIFT) | rank inside that cell
     uint32_t* perm;    // sorted index -> index in current order
     uint32_t* gid;     // optional global particle ids (multi-GPU migration), indexed by particle id; NULL = identity
     bool sorted_valid; // perm/slot tables describe pb[cur]
@@ -160,6 +160,7 @@ struct spk_ctx {
     GridBuffers grid[2];
     int gcur;             // grid[gcur] = curr (read only), grid[1-gcur] = next
     uint32_t* slot_cnt;   // [cap_hash of next] particles per hash slot
+    uint32_t* cell_cnt;   // [cap_hash of next][cells per block] particles per (hash slot, cell); after cell_scan_kernel: exclusive offsets inside the block
     uint32_t slot_cnt_cap;
     DispatchEntry* dispatch; uint32_t dispatch_cap;
     uint32_t chunk;       // particles per g2p2g dispatch entry

@@ -18,9 +18,28 @@ constexpr int BIN_THREADS = 256;
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8; // slots per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int SPK_RANK_BITS = 32 - SPK_CELL_SHIFT; // rank_of = cell << SPK_RANK_BITS | rank inside the cell
+constexpr uint32_t SPK_RANK_MASK = (1u << SPK_RANK_BITS) - 1u;
 
+// cell of the block (4^DIM cells, x fastest) that owns a coordinate: (associated cell - 2) mod 4 per axis — the same arithmetic as
+// spk_block_coord, so (block key, cell) is the particle's full cell address (particle.rs:28-35)
+__device__ __forceinline__ uint32_t spk_cell_in_block(float x, float y, float z, float h) {
+    const uint32_t cx = (uint32_t)(spk_assoc_cell(x, h) - 2) & 3u, cy = (uint32_t)(spk_assoc_cell(y, h) - 2) & 3u;
+#if SPK_DIM == 3
+    const uint32_t cz = (uint32_t)(spk_assoc_cell(z, h) - 2) & 3u;
+    return cx | (cy << 2) | (cz << 4);
+#else
+    (void)z;
+    return cx | (cy << 2);
+#endif
+}
+
+// K1: one pass over the positions.  Per particle: block key + cell inside the block; per (warp, block) one hash insert; per
+// (warp, block, cell) one atomicAdd on the cell counter of the block's hash slot, which also hands out the particle's rank inside
+// its cell.  Sorting by (block, cell) instead of by block alone costs nothing extra here and makes every g2p2g warp read a handful
+// of cells (shared-memory broadcasts in G2P, few P2G bins per CTA).
 __global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4* __restrict__ a0, uint32_t n, float h, unsigned long long* keys,
-                                                                     uint32_t cap_hash, uint32_t* slot_cnt, uint32_t* __restrict__ slot_of,
+                                                                     uint32_t cap_hash, uint32_t* cell_cnt, uint32_t* __restrict__ slot_of,
                                                                      uint32_t* __restrict__ rank_of, DeviceCounters* counters) {
     const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
     const bool valid = i < n;
@@ -28,29 +47,61 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4
     if (!valid) return;
     const float4 p = a0[i];
     const unsigned long long key = spk_block_key_of_point(p.x, p.y, p.z, h);
+    const uint32_t cell = spk_cell_in_block(p.x, p.y, p.z, h);
     const unsigned group = __match_any_sync(active, key);
-    const int leader = __ffs(group) - 1;
+    const unsigned cgroup = group & __match_any_sync(active, (unsigned long long)cell);
+    const int leader = __ffs(group) - 1, cleader = __ffs(cgroup) - 1;
     const int lane = threadIdx.x & 31;
     uint32_t slot = SPK_NO_BLOCK, base = 0;
     if (lane == leader) {
         slot = spk_hash_insert(keys, cap_hash, key);
-        if (slot != SPK_NO_BLOCK) base = atomicAdd(&slot_cnt[slot], (uint32_t)__popc(group));
-        else counters->overflow = 1;
+        if (slot == SPK_NO_BLOCK) counters->overflow = 1;
     }
     slot = __shfl_sync(group, slot, leader);
-    base = __shfl_sync(group, base, leader);
+    if (lane == cleader && slot != SPK_NO_BLOCK) base = atomicAdd(&cell_cnt[(size_t)slot * SPK_CELLS_PER_BLOCK + cell], (uint32_t)__popc(cgroup));
+    base = __shfl_sync(cgroup, base, cleader);
+    const uint32_t rank = base + __popc(cgroup & spk_lanemask_lt());
+    if (rank >> SPK_RANK_BITS) counters->overflow = 1; // > 2^26 particles in one cell
     slot_of[i] = slot;
-    rank_of[i] = base + __popc(group & spk_lanemask_lt());
+    rank_of[i] = (cell << SPK_RANK_BITS) | (rank & SPK_RANK_MASK);
 }
 
-// touch_particle_blocks (sort.rs:58-72) done per occupied block: activate key + {0,1}^3 (gpu_grid.rs:307-321)
-__global__ void activate_neighbours_kernel(unsigned long long* keys, uint32_t cap_hash, const uint32_t* __restrict__ slot_cnt, DeviceCounters* counters) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+// per hash slot (one warp each): exclusive scan of the slot's cell counters (in place: they become the cell offsets inside the
+// block), particle count of the block, and touch_particle_blocks (sort.rs:58-72) done per occupied block: activate key + {0,1}^3
+// (gpu_grid.rs:307-321).  Slots created here own no particles: their counters are all zero whether or not their warp sees the key.
+__global__ void __launch_bounds__(256) cell_scan_kernel(unsigned long long* keys, uint32_t cap_hash, uint32_t* cell_cnt, uint32_t* __restrict__ slot_cnt,
+                                                          DeviceCounters* counters) {
+    const uint32_t s = (blockIdx.x * 256u + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (s >= cap_hash) return;
-    if (slot_cnt[s] == 0) return; // only blocks that own particles (slots created here keep a zero count)
     const unsigned long long key = keys[s];
-    for (int o = 1; o < SPK_NBR; ++o)
-        if (spk_hash_insert(keys, cap_hash, spk_key_offset(key, o)) == SPK_NO_BLOCK) counters->overflow = 1;
+    if (key == SPK_EMPTY_KEY) return;
+    uint32_t* cc = cell_cnt + (size_t)s * SPK_CELLS_PER_BLOCK;
+#if SPK_DIM == 3
+    const uint32_t c0 = cc[2 * lane], c1 = cc[2 * lane + 1]; // lane owns cells 2 lane, 2 lane + 1
+    const uint32_t mine = c0 + c1;
+#else
+    const uint32_t c0 = lane < SPK_CELLS_PER_BLOCK ? cc[lane] : 0u, c1 = 0u;
+    const uint32_t mine = c0;
+#endif
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) return; // a block activated as a neighbour only
+#if SPK_DIM == 3
+    cc[2 * lane] = inc - mine;
+    cc[2 * lane + 1] = inc - mine + c0;
+#else
+    if (lane < SPK_CELLS_PER_BLOCK) cc[lane] = inc - mine;
+    (void)c1;
+#endif
+    if (lane == 0) slot_cnt[s] = total;
+    if (lane >= 1 && lane < SPK_NBR)
+        if (spk_hash_insert(keys, cap_hash, spk_key_offset(key, lane)) == SPK_NO_BLOCK) counters->overflow = 1;
 }
 
 struct Triple { uint32_t occ, cnt, mult; };
@@ -161,17 +212,19 @@ __global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, const De
     next.nbr_prev[b * SPK_NBR + o] = spk_hash_get(prev, key);
 }
 
-// finalize_particles_sort (sort.rs:201-221): sorted slot -> index in the current physical order
+// finalize_particles_sort (sort.rs:201-221): sorted slot -> index in the current physical order; inside a block particles are ordered
+// by cell
 __global__ void __launch_bounds__(BIN_THREADS) scatter_perm_kernel(const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ rank_of, uint32_t n,
                                                                     const uint32_t* __restrict__ vals, const uint32_t* __restrict__ blk_first,
-                                                                    uint32_t cap_blocks, uint32_t* __restrict__ perm) {
+                                                                    const uint32_t* __restrict__ cell_off, uint32_t cap_blocks, uint32_t* __restrict__ perm) {
     const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
     if (i >= n) return;
     const uint32_t slot = slot_of[i];
     if (slot == SPK_NO_BLOCK) return;
     const uint32_t id = vals[slot];
     if (id >= cap_blocks) return;
-    perm[blk_first[id] + rank_of[i]] = i;
+    const uint32_t cr = rank_of[i];
+    perm[blk_first[id] + cell_off[(size_t)slot * SPK_CELLS_PER_BLOCK + (cr >> SPK_RANK_BITS)] + (cr & SPK_RANK_MASK)] = i;
 }
 
 } // namespace
@@ -182,13 +235,14 @@ cudaError_t spk_launch_sort_bin(spk_ctx* c) {
     cudaError_t e;
     if ((e = cudaMemsetAsync(g.keys, 0xff, (size_t)g.cap_hash * 8, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(c->slot_cnt, 0, (size_t)g.cap_hash * 4, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(c->cell_cnt, 0, (size_t)g.cap_hash * SPK_CELLS_PER_BLOCK * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(c->d_counters, 0, 16, s)) != cudaSuccess) return e; // nab, ndispatch, overflow, nparticles_binned
     c->counters_fresh = false;
     const uint32_t n = (uint32_t)c->n;
     if (n) {
-        bin_particles_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->pb[c->cur].a0, n, c->cell_width, g.keys, g.cap_hash, c->slot_cnt,
+        bin_particles_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->pb[c->cur].a0, n, c->cell_width, g.keys, g.cap_hash, c->cell_cnt,
                                                                                         c->slot_of, c->rank_of, c->d_counters);
-        activate_neighbours_kernel<<<(g.cap_hash + 255) / 256, 256, 0, s>>>(g.keys, g.cap_hash, c->slot_cnt, c->d_counters);
+        cell_scan_kernel<<<(g.cap_hash + 7) / 8, 256, 0, s>>>(g.keys, g.cap_hash, c->cell_cnt, c->slot_cnt, c->d_counters);
         c->launches += 2;
     }
     const uint32_t ntiles = (g.cap_hash + SCAN_TILE - 1) / SCAN_TILE;
@@ -209,7 +263,7 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c) {
         c->launches += 1;
     }
     if (n) {
-        scatter_perm_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->slot_of, c->rank_of, n, g.vals, g.blk_first, g.cap_blocks, c->perm);
+        scatter_perm_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->slot_of, c->rank_of, n, g.vals, g.blk_first, c->cell_cnt, g.cap_blocks, c->perm);
         c->launches += 1;
     }
     return cudaGetLastError();
