@@ -3,6 +3,8 @@
 // `g2p2g_generic::<MyUpdater>` includes this header in their own .cu, defines `MyUpdater` and registers
 // `spk_launch_g2p2g_with<MyUpdater>` through spk_set_particle_kernels_launcher (examples/custom_updater/).
 #pragma once
+#include <type_traits>
+
 #include "spk_device.cuh"
 #include "spk_math.cuh"
 #include "spk_updater.cuh"
@@ -98,6 +100,16 @@ __device__ __forceinline__ void tma_commit_and_wait_read() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif // SPK_EMU
+
+// an updater with `static constexpr bool kPhased = true` provides advect / constitutive (spk_updater.cuh) next to update
+template <class U, class = void> struct updater_is_phased { static constexpr bool value = false; };
+template <class U> struct updater_is_phased<U, std::enable_if_t<U::kPhased>> { static constexpr bool value = true; };
+// keeps the compiler from forwarding values across a park / un-park pair (the point is to free the registers in between)
+__device__ __forceinline__ void spk_compiler_fence() {
+#ifndef SPK_EMU
+    asm volatile("" ::: "memory");
+#endif
+}
 
 // tile index helpers: tile coordinate t in [0,8) per axis -> (cell part, octant part) of the [octant][...][cell] layout
 __device__ __forceinline__ int cell_part(int t, int axis) { return (t & 3) << (2 * axis); }
@@ -449,30 +461,45 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
 
 // ================================================================================================================================
 // MODE 2 (default): the cell-coherent kernel.  The sort orders particles by (block, cell) (spk_sort.cu), a dispatch entry holds up to
-// 512 particles of one block, and a CTA of 256 threads walks it in two passes of one particle per thread:
+// 512 particles of one block, and a CTA of 512 threads processes it with one particle per thread:
 //   * a warp's 32 consecutive particles sit in a handful of cells, so the 27 velocity loads of G2P are shared-memory broadcasts;
-//   * every particle leaves its P2G payload (20 floats) in shared memory at its own slot and is stored to the next buffer at once
-//     (nothing of it stays in registers across the in-CTA cell sort, which only moves 16-bit slot numbers);
+//   * every particle owns a 36-float slot in shared memory.  The tail of its record (F, volume, phase, plasticity state: 80 bytes)
+//     is brought there by cp.async while G2P runs and is read field by field when a phase needs it; the interpolated velocity and
+//     velocity gradient are parked there across the SVD / return mapping / stress evaluation; at the end the slot holds the P2G
+//     payload (20 floats).  Registers only ever hold what the current phase computes on (64 per thread, 2 CTAs = 32 warps per SM);
+//   * the particle is stored to the next buffer as soon as its fields are final (nothing of it stays in registers across the
+//     in-CTA cell sort, which only moves 16-bit slot numbers);
 //   * the per-CTA fixed work (tile staging, zeroing, scan, flush: 8 TMA loads + 8 TMA reduce-adds) is paid once per 512 particles and
 //     the P2G bins hold twice the particles of a 256-particle chunk (the per-bin flush is the expensive part of P2G).
-constexpr int C_CHUNK = 512;                  // particles per dispatch entry
-constexpr int C_ITERS = C_CHUNK / G2P2G_THREADS;
-constexpr int C_PAY = 20;                     // floats per staged payload
+#ifndef SPK_CELL_MIN_CTAS
+#define SPK_CELL_MIN_CTAS 2
+#endif
+constexpr int C_THREADS = 512;                // == particles per dispatch entry
+constexpr int C_SLOT = 36;                    // floats per particle slot: [0,20) record tail / payload, [20,32) parked G + velocity, [32,35) ref2
+constexpr int C_PARK = 20;
 constexpr int CS_VEL = 0;                                    // float4[512]
 constexpr int CS_ACC = CS_VEL + 512 * 16;                    // float[8][6][64]
-constexpr int CS_PAY = CS_ACC + 8 * 6 * 64 * 4;              // float[512][20]
-constexpr int CS_BINCNT = CS_PAY + C_CHUNK * C_PAY * 4;      // int[224]
+constexpr int CS_SLOT = CS_ACC + 8 * 6 * 64 * 4;             // float[512][36]
+constexpr int CS_BINCNT = CS_SLOT + C_THREADS * C_SLOT * 4;  // int[224]
 constexpr int CS_BINSTART = CS_BINCNT + 224 * 4;             // int[224]
 constexpr int CS_BINLIST = CS_BINSTART + 224 * 4;            // u16[224] occupied bins
 constexpr int CS_SORTED = CS_BINLIST + 224 * 2;              // u16[512] slot numbers in bin order
-constexpr int CS_BINOF = CS_SORTED + C_CHUNK * 2;            // u16[512] bin of slot s
-constexpr int CS_RANK = CS_BINOF + C_CHUNK * 2;              // u16[512] rank of slot s inside its bin
-constexpr int CS_MISC = CS_RANK + C_CHUNK * 2;               // mbarrier (8) + nbr_self[8] + nbr_prev[8] + nnz + dtmin
+constexpr int CS_MISC = CS_SORTED + C_THREADS * 2;           // mbarrier (8) + nbr_self[8] + nbr_prev[8] + nnz + dtmin
 constexpr int CS_HALO = CS_MISC + 8 + 32 + 32 + 16;
 constexpr int CS_TOTAL = CS_HALO + 32;
 
+#ifdef SPK_EMU
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
 template <class Updater>
-__global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_cell_kernel(const G2P2GParams P) {
+__global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kernel(const G2P2GParams P) {
 #ifdef SPK_EMU
     unsigned char* smem = emu::dynamic_smem();
 #else
@@ -480,13 +507,11 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_cell_
 #endif
     float4* s_vel = reinterpret_cast<float4*>(smem + CS_VEL);
     float* s_acc = reinterpret_cast<float*>(smem + CS_ACC);
-    float* s_pay = reinterpret_cast<float*>(smem + CS_PAY);
+    float* s_slot = reinterpret_cast<float*>(smem + CS_SLOT);
     int* s_bin_cnt = reinterpret_cast<int*>(smem + CS_BINCNT);
     int* s_bin_start = reinterpret_cast<int*>(smem + CS_BINSTART);
     unsigned short* s_binlist = reinterpret_cast<unsigned short*>(smem + CS_BINLIST);
     unsigned short* s_sorted = reinterpret_cast<unsigned short*>(smem + CS_SORTED);
-    unsigned short* s_binof = reinterpret_cast<unsigned short*>(smem + CS_BINOF);
-    unsigned short* s_rank = reinterpret_cast<unsigned short*>(smem + CS_RANK);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + CS_MISC);
     int* s_nbr_self = reinterpret_cast<int*>(smem + CS_MISC + 8);
     int* s_nbr_prev = reinterpret_cast<int*>(smem + CS_MISC + 40);
@@ -496,6 +521,21 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_cell_
 
     const int tid = threadIdx.x;
     const DispatchEntry ent = P.dispatch[blockIdx.x];
+    const bool has_particle = (uint32_t)tid < ent.count;
+    float* const slot = s_slot + (size_t)tid * C_SLOT;
+    // ---- the particle: position now (registers), the rest of the record on its way into the slot (cp.async, no registers)
+    float x[3] = {0.f, 0.f, 0.f};
+    uint32_t flags = 0;
+    if (has_particle) {
+        const uint32_t si = P.perm[ent.first + tid];
+        cp_async16(slot + 0, &P.src.a1[si]);
+        cp_async16(slot + 4, &P.src.a2[si]);
+        cp_async16(slot + 8, &P.src.a3[si]);
+        cp_async16(slot + 12, &P.src.a4[si]);
+        cp_async16(slot + 16, &P.src.a5[si]);
+        const float4 r0 = P.src.a0[si];
+        x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; flags = __float_as_uint(r0.w);
+    }
     if (tid < 8) {
         const int nid = P.nbr_self[ent.block * 8 + tid];
         s_nbr_self[tid] = nid;
@@ -503,7 +543,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_cell_
         s_halo[tid] = (P.world > 1 && nid >= 0) ? P.blk_halo[nid] : 0u;
     }
     if (tid == 0) { mbar_init(s_bar, 1); *s_dtmin = SPK_DT_RAW_NONE; }
-    for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64; i += G2P2G_THREADS) s_acc[i] = 0.f;
+    for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64; i += C_THREADS) s_acc[i] = 0.f;
     if (tid < 224) s_bin_cnt[tid] = 0;
     __syncthreads();
     // ---- stage 0: velocity tile of the 2x2x2 blocks (transfer_global_blocks_to_shared_memory, g2p2g.rs:353-474)
@@ -515,152 +555,188 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_cell_
         for (int o = 0; o < 8; ++o)
             if (s_nbr_prev[o] >= 0) tma_load_1d(&s_vel[o * 64], P.prev_vel + (size_t)s_nbr_prev[o] * 64, 1024u, s_bar);
     }
-    for (int i = tid; i < SPK_TILE_CELLS; i += G2P2G_THREADS)
-        if (s_nbr_prev[i >> 6] < 0) s_vel[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s_nbr_prev[tid >> 6] < 0) s_vel[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const float h = P.h, inv_h = P.inv_h, dt = P.dt;
     const float inv_d = 4.f / (h * h);
 
-    // ---- stage 1: two passes, one particle per thread and pass ---------------------------------------------------------------
-#pragma unroll 1
-    for (int it = 0; it < C_ITERS; ++it) {
-        const int s = it * G2P2G_THREADS + tid; // slot of the particle inside the dispatch entry
-        const bool has_particle = (uint32_t)s < ent.count;
-        ParticleState p;
-        float vel[3] = {0.f, 0.f, 0.f};
-        Mat3 G = mat_zero();
-        Mat3 stress = mat_zero();
-        bool do_p2g = false;
-        int tcell[3] = {1, 1, 1};
-        float cell_before[3] = {0.f, 0.f, 0.f};
-        float ref[3], w[3][3];
-        if (has_particle) {
-            const uint32_t si = P.perm[ent.first + s];
-            const float4 r0 = P.src.a0[si], r1 = P.src.a1[si], r2 = P.src.a2[si], r3 = P.src.a3[si], r4 = P.src.a4[si], r5 = P.src.a5[si];
-            p.x[0] = r0.x; p.x[1] = r0.y; p.x[2] = r0.z; p.flags = __float_as_uint(r0.w);
-            p.F.m[0] = r1.x; p.F.m[1] = r1.y; p.F.m[2] = r1.z; p.F.m[3] = r1.w;
-            p.F.m[4] = r2.x; p.F.m[5] = r2.y; p.F.m[6] = r2.z; p.F.m[7] = r2.w;
-            p.F.m[8] = r3.x; p.jp = r3.y; p.mass = r3.z; p.volume0 = r3.w;
-            p.phase = r4.x; p.psi_pos = r4.y; p.elastic_hardening = r4.z; p.plastic_hardening = r4.w;
-            p.log_vol_gain = r5.x; p.nacc_alpha = r5.y; p.orig_id = __float_as_uint(r5.z);
+    int tcell[3] = {1, 1, 1};
+    float cell_before[3] = {0.f, 0.f, 0.f};
+    float ref[3] = {0.f, 0.f, 0.f}, w[3][3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float q = roundf(spk_div_h(p.x[a], h, inv_h));
-                cell_before[a] = q;
-                ref[a] = (q - 1.f) * h - p.x[a];               // dir_to_associated_grid_node, particle.rs:37-47
-                quad_weights(spk_div_h(-ref[a], h, inv_h), w[a]);
-                const int assoc_cell = (q != q) ? -2 : (int)__float2ll_rz(q) - 2;
-                tcell[a] = (assoc_cell & 3) + 1;                // associated_cell_index_in_block_off_by_two, particle.rs:28-35
-            }
-        }
-        if (it == 0) { // the tile is complete (TMA) and the absent octants are zero-filled
-            mbar_wait(s_bar, 0);
-            __syncthreads();
-        }
+    for (int a = 0; a < 3; ++a) {
+        const float q = roundf(spk_div_h(x[a], h, inv_h));
+        cell_before[a] = q;
+        ref[a] = (q - 1.f) * h - x[a];                  // dir_to_associated_grid_node, particle.rs:37-47
+        quad_weights(spk_div_h(-ref[a], h, inv_h), w[a]);
+        const int assoc_cell = (q != q) ? -2 : (int)__float2ll_rz(q) - 2;
+        tcell[a] = (assoc_cell & 3) + 1;                 // associated_cell_index_in_block_off_by_two, particle.rs:28-35
+    }
+    mbar_wait(s_bar, 0); // the tile is complete (TMA) ...
+    __syncthreads();     // ... and the absent octants are zero-filled
 
-        if (has_particle) {
-            const DevModel& model = P.models[p.flags >> SPK_F_MODEL_SHIFT];
-            // ---- G2P (particle_g2p2g, g2p2g.rs:192-245), separable accumulation: rows along x, then planes, then volume.
-            {
-                float V[3] = {0.f, 0.f, 0.f}, Gx[3] = {0.f, 0.f, 0.f}, Gy[3] = {0.f, 0.f, 0.f}, Gz[3] = {0.f, 0.f, 0.f};
-                const float wpx[3] = {w[0][0] * ref[0], w[0][1] * (ref[0] + h), w[0][2] * (ref[0] + 2.f * h)};
-#pragma unroll
-                for (int dz = 0; dz < 3; ++dz) {
-                    const int iz = cell_part(tcell[2] + dz, 2) | (oct_part(tcell[2] + dz, 2) << 6);
-                    float P0[3] = {0.f, 0.f, 0.f}, P1[3] = {0.f, 0.f, 0.f}, P2[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const int iy = iz | cell_part(tcell[1] + dy, 1) | (oct_part(tcell[1] + dy, 1) << 6);
-                        float R0[3] = {0.f, 0.f, 0.f}, R1[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const float4 c = s_vel[iy | cell_part(tcell[0] + dx, 0) | (oct_part(tcell[0] + dx, 0) << 6)];
-                            R0[0] += w[0][dx] * c.x; R0[1] += w[0][dx] * c.y; R0[2] += w[0][dx] * c.z;
-                            R1[0] += wpx[dx] * c.x; R1[1] += wpx[dx] * c.y; R1[2] += wpx[dx] * c.z;
-                        }
-                        const float wy = w[1][dy], wpy = wy * (ref[1] + (float)dy * h);
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) { P0[a] += wy * R0[a]; P1[a] += wy * R1[a]; P2[a] += wpy * R0[a]; }
-                    }
-                    const float wz = w[2][dz], wpz = wz * (ref[2] + (float)dz * h);
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) { V[a] += wz * P0[a]; Gx[a] += wz * P1[a]; Gy[a] += wz * P2[a]; Gz[a] += wpz * P0[a]; }
-                }
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    vel[a] = V[a];
-                    M_(G, a, 0) = Gx[a] * inv_d; M_(G, a, 1) = Gy[a] * inv_d; M_(G, a, 2) = Gz[a] * inv_d;
-                }
-            }
-            do_p2g = Updater::update(model, P.cold, h, dt, p, vel, G, stress, P.user);
-        }
-
-        // ---- fused K15 (timestep.rs:38-113): un-clamped dt candidate of this particle for the NEXT substep
+    int bin = NBINS;
+    unsigned cand_bits = SPK_DT_RAW_NONE;
+    if (has_particle) {
+        const DevModel& model = P.models[flags >> SPK_F_MODEL_SHIFT];
+        float vel[3];
+        Mat3 G;
+        // ---- G2P (particle_g2p2g, g2p2g.rs:192-245): rows along x are accumulated separably, then folded into the 12 sums
+        //   V = sum w v,  G[:,a] = inv_d * sum w dpt_a v   with w = wx wy wz and dpt = ref + s h
         {
-            unsigned cand_bits = SPK_DT_RAW_NONE;
-            if (has_particle && !(p.flags & SPK_F_FAILED)) {
-                const DevModel& model = P.models[p.flags >> SPK_F_MODEL_SHIFT];
-                const float cand = Updater::dt_candidate(model, h, p, vel, P.user);
-                cand_bits = __float_as_uint(cand != cand ? 1.0e30f : fminf(fmaxf(cand, 0.f), 1.0e30f)); // NaN imposes no bound (Rust f32::min ignores NaN)
+            float V[3] = {0.f, 0.f, 0.f}, Gx[3] = {0.f, 0.f, 0.f}, Gy[3] = {0.f, 0.f, 0.f}, Gz[3] = {0.f, 0.f, 0.f};
+            const float wpx[3] = {w[0][0] * ref[0], w[0][1] * (ref[0] + h), w[0][2] * (ref[0] + 2.f * h)};
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz) {
+                const int iz = cell_part(tcell[2] + dz, 2) | (oct_part(tcell[2] + dz, 2) << 6);
+                const float pz = ref[2] + (float)dz * h;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int iy = iz | cell_part(tcell[1] + dy, 1) | (oct_part(tcell[1] + dy, 1) << 6);
+                    float R0[3] = {0.f, 0.f, 0.f}, R1[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const float4 c = s_vel[iy | cell_part(tcell[0] + dx, 0) | (oct_part(tcell[0] + dx, 0) << 6)];
+                        R0[0] += w[0][dx] * c.x; R0[1] += w[0][dx] * c.y; R0[2] += w[0][dx] * c.z;
+                        R1[0] += wpx[dx] * c.x; R1[1] += wpx[dx] * c.y; R1[2] += wpx[dx] * c.z;
+                    }
+                    const float wyz = w[1][dy] * w[2][dz];
+                    const float wpy = wyz * (ref[1] + (float)dy * h), wpz = wyz * pz;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { V[a] += wyz * R0[a]; Gx[a] += wyz * R1[a]; Gy[a] += wpy * R0[a]; Gz[a] += wpz * R0[a]; }
+                }
             }
-            cand_bits = __reduce_min_sync(0xffffffffu, cand_bits);
-            if ((tid & 31) == 0 && cand_bits < SPK_DT_RAW_NONE) atomicMin(s_dtmin, cand_bits);
-        }
-
-        // ---- the particle is final: store it (slot order == sorted order of this substep; the next sort re-orders by cell)
-        if (has_particle) {
-            const uint32_t di = ent.first + (uint32_t)s;
-            P.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
-            P.dst.a1[di] = make_float4(p.F.m[0], p.F.m[1], p.F.m[2], p.F.m[3]);
-            P.dst.a2[di] = make_float4(p.F.m[4], p.F.m[5], p.F.m[6], p.F.m[7]);
-            P.dst.a3[di] = make_float4(p.F.m[8], p.jp, p.mass, p.volume0);
-            P.dst.a4[di] = make_float4(p.phase, p.psi_pos, p.elastic_hardening, p.plastic_hardening);
-            P.dst.a5[di] = make_float4(p.log_vol_gain, p.nacc_alpha, __uint_as_float(p.orig_id), 0.f);
-            P.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
-        }
-
-        // ---- P2G preparation with the UPDATED position (g2p2g.rs:280-309): stencil-base cell (bin) and the payload
-        //   q0 = {m, c.xyz}  c = A ref2 + m v        q1 = {h A[:,0], psi_mass}   q2 = {h A[:,1], psi_mom}   q3 = {h A[:,2], fy}
-        //   q4 = {wx0, wx1, wx2, fz}                 A = m G - (volume0 inv_d dt) stress,  fy / fz: B-spline arguments along y / z
-        int bin = NBINS;
-        if (has_particle && do_p2g) {
-            float ref2[3], f2[3];
-            int t2[3];
-            bool inside = true;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
+                vel[a] = V[a];
+                M_(G, a, 0) = Gx[a] * inv_d; M_(G, a, 1) = Gy[a] * inv_d; M_(G, a, 2) = Gz[a] * inv_d;
+            }
+        }
+        cp_async_wait_all(); // this thread's record tail is in its slot
+        const uint32_t di = ent.first + (uint32_t)tid; // slot order == sorted order of this substep; the next sort re-orders by cell
+        ParticleState p;
+        p.x[0] = x[0]; p.x[1] = x[1]; p.x[2] = x[2]; p.flags = flags;
+        Mat3 stress = mat_zero();
+        bool do_p2g;
+        float ref2[3], f2[3];
+        if constexpr (updater_is_phased<Updater>::value) {
+            // phase 1: advection and F update; position, velocity and velocity gradient are final afterwards: stored / parked
+            {
+                const float4 r1 = *reinterpret_cast<const float4*>(slot), r2 = *reinterpret_cast<const float4*>(slot + 4);
+                p.F.m[0] = r1.x; p.F.m[1] = r1.y; p.F.m[2] = r1.z; p.F.m[3] = r1.w;
+                p.F.m[4] = r2.x; p.F.m[5] = r2.y; p.F.m[6] = r2.z; p.F.m[7] = r2.w;
+                p.F.m[8] = slot[8];
+                p.orig_id = __float_as_uint(slot[18]);
+            }
+            Updater::advect(model, P.cold, h, dt, p, vel, G, P.user);
+            bool inside = true;
+            int t2[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { // P2G geometry with the UPDATED position (g2p2g.rs:280-309)
                 const float q = roundf(spk_div_h(p.x[a], h, inv_h));
                 ref2[a] = (q - 1.f) * h - p.x[a];
-                f2[a] = spk_div_h(-ref2[a], h, inv_h);
                 const float mvf = q - cell_before[a];
                 const int mv = (mvf != mvf) ? 0 : (int)__float2ll_rz(mvf);
                 t2[a] = tcell[a] + mv; // in [0, 5] after the velocity clamp
                 inside = inside && t2[a] >= 0 && t2[a] <= 5;
             }
-            if (inside) {
-                bin = t2[0] + 6 * t2[1] + 36 * t2[2];
-                const float ks = p.volume0 * inv_d * dt;
-                Mat3 A;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) A.m[i] = p.mass * G.m[i] - ks * stress.m[i];
-                const float psi_mass = (p.phase > 0.f && !(p.flags & SPK_F_FAILED)) ? p.mass : 0.f;
-                float wx[3];
-                quad_weights(f2[0], wx);
-                float4* q = reinterpret_cast<float4*>(s_pay + (size_t)s * C_PAY);
-                q[0] = make_float4(p.mass, M_(A, 0, 0) * ref2[0] + M_(A, 0, 1) * ref2[1] + M_(A, 0, 2) * ref2[2] + p.mass * vel[0],
-                                   M_(A, 1, 0) * ref2[0] + M_(A, 1, 1) * ref2[1] + M_(A, 1, 2) * ref2[2] + p.mass * vel[1],
-                                   M_(A, 2, 0) * ref2[0] + M_(A, 2, 1) * ref2[1] + M_(A, 2, 2) * ref2[2] + p.mass * vel[2]);
-                q[1] = make_float4(h * M_(A, 0, 0), h * M_(A, 1, 0), h * M_(A, 2, 0), psi_mass);
-                q[2] = make_float4(h * M_(A, 0, 1), h * M_(A, 1, 1), h * M_(A, 2, 1), psi_mass * p.psi_pos);
-                q[3] = make_float4(h * M_(A, 0, 2), h * M_(A, 1, 2), h * M_(A, 2, 2), f2[1]);
-                q[4] = make_float4(wx[0], wx[1], wx[2], f2[2]);
+            if (inside) bin = t2[0] + 6 * t2[1] + 36 * t2[2];
+            P.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
+            P.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
+            float4* park = reinterpret_cast<float4*>(slot + C_PARK);
+            park[0] = make_float4(G.m[0], G.m[1], G.m[2], G.m[3]);
+            park[1] = make_float4(G.m[4], G.m[5], G.m[6], G.m[7]);
+            park[2] = make_float4(G.m[8], vel[0], vel[1], vel[2]);
+            park[3] = make_float4(ref2[0], ref2[1], ref2[2], 0.f);
+            spk_compiler_fence();
+            // phase 2: the decomposition, alone in the register file
+            Svd3 svd;
+            if (model_needs_svd(model)) svd = Updater::decompose(model, p.F, P.user);
+            spk_compiler_fence();
+            // phase 3: plasticity, failure, energies, stress on the scalars of the record (read from the slot only now)
+            {
+                const float4 r3 = *reinterpret_cast<const float4*>(slot + 8), r4 = *reinterpret_cast<const float4*>(slot + 12),
+                             r5 = *reinterpret_cast<const float4*>(slot + 16);
+                p.jp = r3.y; p.mass = r3.z; p.volume0 = r3.w;
+                p.phase = r4.x; p.psi_pos = r4.y; p.elastic_hardening = r4.z; p.plastic_hardening = r4.w;
+                p.log_vol_gain = r5.x; p.nacc_alpha = r5.y; p.orig_id = __float_as_uint(r5.z);
             }
+            const uint32_t flags0 = p.flags;
+            do_p2g = Updater::constitutive(model, p, svd, slot + C_PARK, stress, P.user);
+            if (p.flags != flags0) P.dst.a0[di].w = __uint_as_float(p.flags); // the particle failed in phase 3 (rare)
+            spk_compiler_fence();
+            {
+                const float4 g0 = park[0], g1 = park[1], g2 = park[2], g3 = park[3];
+                G.m[0] = g0.x; G.m[1] = g0.y; G.m[2] = g0.z; G.m[3] = g0.w; G.m[4] = g1.x; G.m[5] = g1.y; G.m[6] = g1.z; G.m[7] = g1.w; G.m[8] = g2.x;
+                vel[0] = g2.y; vel[1] = g2.z; vel[2] = g2.w;
+                ref2[0] = g3.x; ref2[1] = g3.y; ref2[2] = g3.z;
+            }
+        } else {
+            {
+                const float4 r1 = *reinterpret_cast<const float4*>(slot), r2 = *reinterpret_cast<const float4*>(slot + 4),
+                             r3 = *reinterpret_cast<const float4*>(slot + 8), r4 = *reinterpret_cast<const float4*>(slot + 12),
+                             r5 = *reinterpret_cast<const float4*>(slot + 16);
+                p.F.m[0] = r1.x; p.F.m[1] = r1.y; p.F.m[2] = r1.z; p.F.m[3] = r1.w;
+                p.F.m[4] = r2.x; p.F.m[5] = r2.y; p.F.m[6] = r2.z; p.F.m[7] = r2.w;
+                p.F.m[8] = r3.x; p.jp = r3.y; p.mass = r3.z; p.volume0 = r3.w;
+                p.phase = r4.x; p.psi_pos = r4.y; p.elastic_hardening = r4.z; p.plastic_hardening = r4.w;
+                p.log_vol_gain = r5.x; p.nacc_alpha = r5.y; p.orig_id = __float_as_uint(r5.z);
+            }
+            do_p2g = Updater::update(model, P.cold, h, dt, p, vel, G, stress, P.user);
+            bool inside = true;
+            int t2[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float q = roundf(spk_div_h(p.x[a], h, inv_h));
+                ref2[a] = (q - 1.f) * h - p.x[a];
+                const float mvf = q - cell_before[a];
+                const int mv = (mvf != mvf) ? 0 : (int)__float2ll_rz(mvf);
+                t2[a] = tcell[a] + mv;
+                inside = inside && t2[a] >= 0 && t2[a] <= 5;
+            }
+            if (inside) bin = t2[0] + 6 * t2[1] + 36 * t2[2];
+            P.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
+            P.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
         }
-        if (has_particle) {
-            s_binof[s] = (unsigned short)bin;
-            s_rank[s] = (unsigned short)atomicAdd(&s_bin_cnt[bin], 1);
+        if (!do_p2g) bin = NBINS;
+        // ---- fused K15 (timestep.rs:38-113): un-clamped dt candidate of this particle for the NEXT substep; the clamps and the
+        // fixed-point conversion are monotone, so they are applied once to the reduced value (spk_stage_estimate_dt)
+        if (!(p.flags & SPK_F_FAILED)) {
+            const float cand = Updater::dt_candidate(model, h, p, vel, P.user);
+            cand_bits = __float_as_uint(cand != cand ? 1.0e30f : fminf(fmaxf(cand, 0.f), 1.0e30f)); // NaN imposes no bound (Rust f32::min ignores NaN)
+        }
+        P.dst.a1[di] = make_float4(p.F.m[0], p.F.m[1], p.F.m[2], p.F.m[3]);
+        P.dst.a2[di] = make_float4(p.F.m[4], p.F.m[5], p.F.m[6], p.F.m[7]);
+        P.dst.a3[di] = make_float4(p.F.m[8], p.jp, p.mass, p.volume0);
+        P.dst.a4[di] = make_float4(p.phase, p.psi_pos, p.elastic_hardening, p.plastic_hardening);
+        P.dst.a5[di] = make_float4(p.log_vol_gain, p.nacc_alpha, __uint_as_float(p.orig_id), 0.f);
+        // ---- P2G payload (overwrites the record tail in the slot)
+        //   q0 = {m, c.xyz}  c = A ref2 + m v        q1 = {h A[:,0], psi_mass}   q2 = {h A[:,1], psi_mom}   q3 = {h A[:,2], fy}
+        //   q4 = {wx0, wx1, wx2, fz}                 A = m G - (volume0 inv_d dt) stress,  fy / fz: B-spline arguments along y / z
+        if (bin != NBINS) {
+            const float ks = p.volume0 * inv_d * dt;
+            Mat3 A;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) A.m[i] = p.mass * G.m[i] - ks * stress.m[i];
+            const float psi_mass = (p.phase > 0.f && !(p.flags & SPK_F_FAILED)) ? p.mass : 0.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) f2[a] = spk_div_h(-ref2[a], h, inv_h);
+            float wx[3];
+            quad_weights(f2[0], wx);
+            float4* q = reinterpret_cast<float4*>(slot);
+            q[0] = make_float4(p.mass, M_(A, 0, 0) * ref2[0] + M_(A, 0, 1) * ref2[1] + M_(A, 0, 2) * ref2[2] + p.mass * vel[0],
+                               M_(A, 1, 0) * ref2[0] + M_(A, 1, 1) * ref2[1] + M_(A, 1, 2) * ref2[2] + p.mass * vel[1],
+                               M_(A, 2, 0) * ref2[0] + M_(A, 2, 1) * ref2[1] + M_(A, 2, 2) * ref2[2] + p.mass * vel[2]);
+            q[1] = make_float4(h * M_(A, 0, 0), h * M_(A, 1, 0), h * M_(A, 2, 0), psi_mass);
+            q[2] = make_float4(h * M_(A, 0, 1), h * M_(A, 1, 1), h * M_(A, 2, 1), psi_mass * p.psi_pos);
+            q[3] = make_float4(h * M_(A, 0, 2), h * M_(A, 1, 2), h * M_(A, 2, 2), f2[1]);
+            q[4] = make_float4(wx[0], wx[1], wx[2], f2[2]);
         }
     }
+    cand_bits = __reduce_min_sync(0xffffffffu, cand_bits);
+    if ((tid & 31) == 0 && cand_bits < SPK_DT_RAW_NONE) atomicMin(s_dtmin, cand_bits);
+    int rank = 0;
+    if (has_particle) rank = atomicAdd(&s_bin_cnt[bin], 1);
     __syncthreads();
 
     // ---- counting sort of the slots by stencil-base cell (bin 216 = particles without P2G): exclusive scan by warp 0
@@ -684,11 +760,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_cell_
         if (tid == 31) *s_nnz = inz;
     }
     __syncthreads();
-#pragma unroll
-    for (int it = 0; it < C_ITERS; ++it) {
-        const int s = it * G2P2G_THREADS + tid;
-        if ((uint32_t)s < ent.count) s_sorted[s_bin_start[s_binof[s]] + s_rank[s]] = (unsigned short)s;
-    }
+    if (has_particle) s_sorted[s_bin_start[bin] + rank] = (unsigned short)tid;
     __syncthreads();
 
     // ---- stage 2: 9-lane groups, one occupied bin at a time; lane = stencil column (sy, sz), 3 nodes (sx = 0..2) x 6 channels in
@@ -703,13 +775,13 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_cell_
         const float Az = sz == 1 ? -1.f : 0.5f, Bz = sz == 0 ? 1.5f : (sz == 1 ? 1.f : 0.5f), Cz = sz == 1 ? 0.75f : 0.f;
         const int nnz = *s_nnz;
         if (grp < 3) {
-            for (int e = warp * 3 + grp; e < nnz; e += (G2P2G_THREADS / 32) * 3) {
-                const int bin = s_binlist[e];
-                const int start = s_bin_start[bin], cnt = s_bin_cnt[bin];
+            for (int e = warp * 3 + grp; e < nnz; e += (C_THREADS / 32) * 3) {
+                const int b = s_binlist[e];
+                const int start = s_bin_start[b], cnt = s_bin_cnt[b];
                 float aM[3] = {0.f, 0.f, 0.f}, aX[3] = {0.f, 0.f, 0.f}, aY[3] = {0.f, 0.f, 0.f}, aZ[3] = {0.f, 0.f, 0.f}, aPm[3] = {0.f, 0.f, 0.f},
                       aPp[3] = {0.f, 0.f, 0.f};
                 for (int i = 0; i < cnt; ++i) {
-                    const float* pay = s_pay + (size_t)s_sorted[start + i] * C_PAY;
+                    const float* pay = s_slot + (size_t)s_sorted[start + i] * C_SLOT;
                     const float4 q0 = *reinterpret_cast<const float4*>(pay), q1 = *reinterpret_cast<const float4*>(pay + 4),
                                  q2 = *reinterpret_cast<const float4*>(pay + 8), q3 = *reinterpret_cast<const float4*>(pay + 12),
                                  q4 = *reinterpret_cast<const float4*>(pay + 16);
@@ -727,7 +799,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_cell_
                         bx += q1.x; by += q1.y; bz += q1.z;
                     }
                 }
-                const int bxc = bin % 6, byc = (bin / 6) % 6, bzc = bin / 36;
+                const int bxc = b % 6, byc = (b / 6) % 6, bzc = b / 36;
                 const int byz = cell_part(byc + sy, 1) + oct_part(byc + sy, 1) * 384 + cell_part(bzc + sz, 2) + oct_part(bzc + sz, 2) * 384;
 #pragma unroll
                 for (int sx = 0; sx < 3; ++sx) {
@@ -825,7 +897,7 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     if (timed) cudaEventRecord(c->kev[2 * c->kev_count], c->stream);
     if (c->g2p2g_mode == 0) g2p2g_kernel<0, Updater><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
     else if (c->g2p2g_mode == 1) g2p2g_kernel<1, Updater><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
-    else g2p2g_cell_kernel<Updater><<<nd, G2P2G_THREADS, CS_TOTAL, c->stream>>>(P);
+    else g2p2g_cell_kernel<Updater><<<nd, C_THREADS, CS_TOTAL, c->stream>>>(P);
     if (timed) { cudaEventRecord(c->kev[2 * c->kev_count + 1], c->stream); c->kev_count += 1; }
     c->launches += 1;
     c->g2p2g_launches += 1;

@@ -14,16 +14,19 @@
 #include "spk_math.cuh"
 
 struct DefaultParticleUpdater {
-    // DefaultParticleUpdater::update_particle_and_compute_kirchhoff_stress, src_kernels/cuda/particle_updater.rs:73-236.
-    // In: the particle `p`, the interpolated velocity `vel` and velocity gradient `G` (InterpolatedParticleData).  Out: the advected /
-    // updated particle, its new velocity, `G` (zeroed for static particles), the Kirchhoff `stress`.  Returns false when the reference
-    // returns None (no P2G for this particle).
-    __device__ __forceinline__ static bool update(const DevModel& model, const float4* __restrict__ cold, float h, float dt, ParticleState& p, float (&vel)[3], Mat3& G,
-                                                  Mat3& stress, const void* /*user*/) {
-        const float div = M_(G, 0, 0) + M_(G, 1, 1) + M_(G, 2, 2); // velocity_gradient_det == trace of the affine matrix
+    // The update comes in two phases so that the fused kernel can keep the interpolated velocity and velocity gradient in shared
+    // memory (not in registers) across the SVD / return mapping / stress evaluation (spk_g2p2g_kernel.cuh, g2p2g_cell_kernel):
+    //   advect        velocity handling, position, deformation-gradient update        particle_updater.rs:87-138 (+ :151-155)
+    //                 (reads x, flags, F, orig_id of the particle; the other fields need not be loaded yet)
+    //   decompose     the shared SVD of F
+    //   constitutive  plasticity, failure, energies, Kirchhoff stress                 particle_updater.rs:140-236
+    // `update` runs them in order and is the interface a custom updater implements; an updater that also wants the phased schedule declares
+    // `static constexpr bool kPhased = true` and provides the three functions below.
+    static constexpr bool kPhased = true;
 
-        // ---- particle update (particle_updater.rs:73-236)
-        const bool is_fluid = model_is_fluid(model);
+    __device__ __forceinline__ static void advect(const DevModel& model, const float4* __restrict__ cold, float h, float dt, ParticleState& p, float (&vel)[3], Mat3& G,
+                                                  const void* /*user*/) {
+        const float div = M_(G, 0, 0) + M_(G, 1, 1) + M_(G, 2, 2); // velocity_gradient_det == trace of the affine matrix
         if (p.flags & SPK_F_KINEMATIC) {
             const float4 kv = cold[p.orig_id];
             vel[0] = kv.x; vel[1] = kv.y; vel[2] = kv.z;
@@ -34,7 +37,7 @@ struct DefaultParticleUpdater {
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a) p.x[a] += vel[a] * dt;
-        if (!is_fluid) {
+        if (!model_is_fluid(model)) {
             Mat3 Gdt;
 #pragma unroll
             for (int i = 0; i < 9; ++i) Gdt.m[i] = G.m[i] * dt;
@@ -44,15 +47,21 @@ struct DefaultParticleUpdater {
         } else {
             p.F.m[0] += (div * dt) * p.F.m[0];
         }
-        Svd3 svd;
-        if (model_needs_svd(model)) {
-            svd = svd3(p.F);
-            plastic_update(model, p, svd);
-        }
+        // particle_updater.rs:151-155 (after the plastic update there; the return mapping reads neither, so the order is free)
         if (p.flags & SPK_F_STATIC) {
             vel[0] = vel[1] = vel[2] = 0.f;
             G = mat_zero();
         }
+    }
+
+    // the one decomposition F = U diag(s) V^T that plasticity, energy and stress share (called when model_needs_svd(model))
+    __device__ __forceinline__ static Svd3 decompose(const DevModel& /*model*/, const Mat3& F, const void* /*user*/) { return svd3(F); }
+
+    // `svd`: decompose(F) when model_needs_svd(model), unspecified otherwise.  `Gp`: the (final) velocity gradient, 9 floats
+    // column-major, wherever the caller keeps it — only the Monaghan viscosity reads it
+    __device__ __forceinline__ static bool constitutive(const DevModel& model, ParticleState& p, Svd3& svd, const float* Gp, Mat3& stress, const void* /*user*/) {
+        const bool is_fluid = model_is_fluid(model);
+        if (model_needs_svd(model)) plastic_update(model, p, svd);
         const float j = mat_det(p.F);
         const float density_def_grad = (p.mass / p.volume0) / j;
         bool do_p2g = true;
@@ -96,7 +105,7 @@ struct DefaultParticleUpdater {
 #pragma unroll
                         for (int r = 0; r < 3; ++r)
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) M_(sr, r, c) = (M_(G, r, c) + M_(G, c, r)) * 0.5f;
+                            for (int c = 0; c < 3; ++c) M_(sr, r, c) = (Gp[c * 3 + r] + Gp[r * 3 + c]) * 0.5f;
                         const float sph = (sr.m[0] + sr.m[4] + sr.m[8]) / 3.f;
                         sr.m[0] -= sph; sr.m[4] -= sph; sr.m[8] -= sph;
                         const float kv = 2.f * model.c[2] * p.jp;
@@ -117,6 +126,18 @@ struct DefaultParticleUpdater {
             }
         }
         return do_p2g;
+    }
+
+    // DefaultParticleUpdater::update_particle_and_compute_kirchhoff_stress, src_kernels/cuda/particle_updater.rs:73-236.
+    // In: the particle `p`, the interpolated velocity `vel` and velocity gradient `G` (InterpolatedParticleData).  Out: the advected /
+    // updated particle, its new velocity, `G` (zeroed for static particles), the Kirchhoff `stress`.  Returns false when the reference
+    // returns None (no P2G for this particle).
+    __device__ __forceinline__ static bool update(const DevModel& model, const float4* __restrict__ cold, float h, float dt, ParticleState& p, float (&vel)[3], Mat3& G,
+                                                  Mat3& stress, const void* user) {
+        advect(model, cold, h, dt, p, vel, G, user);
+        Svd3 svd;
+        if (model_needs_svd(model)) svd = decompose(model, p.F, user);
+        return constitutive(model, p, svd, G.m, stress, user);
     }
 
     // estimate_particle_timestep_length (particle_updater.rs:47-70) + timestep.rs:74-112: the particle's dt candidate BEFORE the
