@@ -409,6 +409,7 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     c->g2p2g_mode = 2;
     if (const char* m = getenv("SPK_G2P2G_MODE")) { const int v = atoi(m); c->g2p2g_mode = v < 0 ? 0 : (v > 2 ? 2 : v); }
     if (c->g2p2g_mode == 2) c->chunk = 512;
+    c->g2p2g_specialize = getenv("SPK_G2P2G_GENERIC") ? 0 : 1;
 #else
     c->g2p2g_mode = 1;
 #endif
@@ -751,6 +752,8 @@ int spk_models_upload(spk_ctx* c, const SpkGpuParticleModel* models, size_t n) {
     CK(dev_alloc(c->models, n));
     if (n) CK(cudaMemcpy(c->models, dm.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice));
     c->nmodels = n;
+    c->model_mask = 0;
+    for (size_t i = 0; i < n; ++i) c->model_mask |= (1u << dm[i].ctag) | (1u << (4 + dm[i].ptag)) | (dm[i].ftag == SPK_FAILURE_MAXIMUM_STRESS ? (1u << 10) : 0u); // SPK_MM_*
     c->dt_cache_valid = false; // the cached CFL candidate was computed with the previous models
     return SPK_OK;
 }

@@ -60,7 +60,7 @@ __device__ __forceinline__ float* fv_node_mass(const GridBuffers& g, const int32
     }
     const int32_t nid = nbr[oct];
     if (nid < 0) return nullptr;
-    return g.acc + ((size_t)nid * SPK_ACC_CHANNELS + 0) * SPK_CELLS_PER_BLOCK + cell;
+    return g.acc + ((size_t)nid * SPK_ACC_CHANNELS + 0) * SPK_CELLS_PER_BLOCK + SPK_ACC_SWZ((uint32_t)cell);
 }
 
 __device__ __forceinline__ const int32_t* fv_block_of(const GridBuffers& next, const uint32_t* __restrict__ slot_of, uint32_t i) {

@@ -12,6 +12,22 @@
 //   stage 3  the tile is flushed to the next grid with 8 TMA bulk reduce-adds (1.5 KB each, f32 add at L2).
 #include "spk_g2p2g_kernel.cuh"
 
-cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) { return spk_launch_g2p2g_with<DefaultParticleUpdater>(c, dt); }
+// Model-set specialisations of the default kernel (see SPK_MM_* in spk_math.cuh): same source, dead models compiled out.
+namespace {
+constexpr uint32_t MM_NO_PLASTICITY = SPK_MM_P(SPK_PLASTIC_NONE) | SPK_MM_P(SPK_PLASTIC_CUSTOM); // both are no-ops (gpu_plastic_model.rs:59)
+constexpr uint32_t MM_SAND = SPK_MM_C(SPK_CONSTITUTIVE_COROTATED) | SPK_MM_P(SPK_PLASTIC_DRUCKER_PRAGER) | MM_NO_PLASTICITY;   // sand3, cube_through_sand3
+constexpr uint32_t MM_FLUID = SPK_MM_C(SPK_CONSTITUTIVE_MONAGHAN) | MM_NO_PLASTICITY;                                              // fluids3
+constexpr uint32_t MM_ELASTIC = SPK_MM_C(SPK_CONSTITUTIVE_COROTATED) | SPK_MM_C(SPK_CONSTITUTIVE_NEO_HOOKEAN) | MM_NO_PLASTICITY; // elasticity3, the N256M block
+} // namespace
+
+cudaError_t spk_launch_g2p2g(spk_ctx* c, float dt) {
+    const uint32_t mm = c->model_mask;
+    if (c->g2p2g_mode == 2 && c->g2p2g_specialize && mm) {
+        if (!(mm & ~MM_SAND)) return spk_launch_g2p2g_with<DefaultParticleUpdaterT<MM_SAND>>(c, dt);
+        if (!(mm & ~MM_FLUID)) return spk_launch_g2p2g_with<DefaultParticleUpdaterT<MM_FLUID>>(c, dt);
+        if (!(mm & ~MM_ELASTIC)) return spk_launch_g2p2g_with<DefaultParticleUpdaterT<MM_ELASTIC>>(c, dt);
+    }
+    return spk_launch_g2p2g_with<DefaultParticleUpdater>(c, dt);
+}
 
 cudaError_t spk_launch_estimate_dt(spk_ctx* c, float min_dt, float max_dt) { return spk_launch_estimate_dt_with<DefaultParticleUpdater>(c, min_dt, max_dt); }

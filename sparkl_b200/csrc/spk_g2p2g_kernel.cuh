@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
                     const float wyz = w2[1][dy] * w2[2][dz];
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
-                        const int base = by + cell_part(t2[0] + dx, 0) + oct_part(t2[0] + dx, 0) * 384;
+                        const int base = by + (cell_part(t2[0] + dx, 0) ^ ((t2[2] + dz) & 2)) + oct_part(t2[0] + dx, 0) * 384; // SPK_ACC_SWZ
                         const float px = ref2[0] + (float)dx * h;
                         const float wt = w2[0][dx] * wyz;
                         float* a = &s_acc[base];
@@ -407,9 +407,10 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
                 // flush the 3 x 6 sums of this (cell, column) into the tile
                 const int bxc = bin % 6, byc = (bin / 6) % 6, bzc = bin / 36;
                 const int byz = cell_part(byc + sy, 1) + oct_part(byc + sy, 1) * 384 + cell_part(bzc + sz, 2) + oct_part(bzc + sz, 2) * 384;
+                const int zsw = (bzc + sz) & 2; // SPK_ACC_SWZ
 #pragma unroll
                 for (int sx = 0; sx < 3; ++sx) {
-                    float* a = &s_acc[byz + cell_part(bxc + sx, 0) + oct_part(bxc + sx, 0) * 384];
+                    float* a = &s_acc[byz + (cell_part(bxc + sx, 0) ^ zsw) + oct_part(bxc + sx, 0) * 384];
                     atomicAdd(a + 0 * 64, aM[sx]);
                     atomicAdd(a + 1 * 64, aX[sx]);
                     atomicAdd(a + 2 * 64, aY[sx]);
@@ -475,18 +476,29 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
 #define SPK_CELL_MIN_CTAS 2
 #endif
 constexpr int C_THREADS = 512;                // == particles per dispatch entry
-constexpr int C_SLOT = 36;                    // floats per particle slot: [0,20) record tail / payload, [20,32) parked G + velocity, [32,35) ref2
-constexpr int C_PARK = 20;
+// per-particle shared-memory slot, stored as 9 arrays of float4 indexed by the particle's thread ([k][tid]: every per-thread access is
+// a conflict-free 16-byte access): arrays 0-4 hold the record tail (a1..a5), later the P2G payload; arrays 5-8 the parked G, velocity, ref2
+constexpr int C_TAIL = 5, C_PARKED = 4;
 constexpr int CS_VEL = 0;                                    // float4[512]
 constexpr int CS_ACC = CS_VEL + 512 * 16;                    // float[8][6][64]
-constexpr int CS_SLOT = CS_ACC + 8 * 6 * 64 * 4;             // float[512][36]
-constexpr int CS_BINCNT = CS_SLOT + C_THREADS * C_SLOT * 4;  // int[224]
+constexpr int CS_SLOT = CS_ACC + 8 * 6 * 64 * 4;             // float4[9][512]
+constexpr int CS_BINCNT = CS_SLOT + (C_TAIL + C_PARKED) * C_THREADS * 16;  // int[224]
 constexpr int CS_BINSTART = CS_BINCNT + 224 * 4;             // int[224]
 constexpr int CS_BINLIST = CS_BINSTART + 224 * 4;            // u16[224] occupied bins
 constexpr int CS_SORTED = CS_BINLIST + 224 * 2;              // u16[512] slot numbers in bin order
-constexpr int CS_MISC = CS_SORTED + C_THREADS * 2;           // mbarrier (8) + nbr_self[8] + nbr_prev[8] + nnz + dtmin
+constexpr int CS_MISC = CS_SORTED + C_THREADS * 2;           // mbarrier (8) + nbr_self[8] + nbr_prev[8] + nnz + dtmin + next work item
 constexpr int CS_HALO = CS_MISC + 8 + 32 + 32 + 16;
-constexpr int CS_TOTAL = CS_HALO + 32;
+constexpr int CS_WTOT = CS_HALO + 32;                        // int2[8]: per-warp totals of the bin scan
+constexpr int CS_TOTAL = CS_WTOT + 64;
+
+// the velocity gradient of a particle where the cell kernel parks it: G.m[i] = float i of the float4 sequence base[0], base[stride], ...
+struct ParkedGradient {
+    const float4* base;
+    __device__ __forceinline__ float operator[](int i) const { // i is a compile-time constant after unrolling
+        const float4 v = base[(i >> 2) * 512];
+        return (i & 3) == 0 ? v.x : ((i & 3) == 1 ? v.y : ((i & 3) == 2 ? v.z : v.w));
+    }
+};
 
 #ifdef SPK_EMU
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
@@ -507,7 +519,8 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
 #endif
     float4* s_vel = reinterpret_cast<float4*>(smem + CS_VEL);
     float* s_acc = reinterpret_cast<float*>(smem + CS_ACC);
-    float* s_slot = reinterpret_cast<float*>(smem + CS_SLOT);
+    float4* s_tail = reinterpret_cast<float4*>(smem + CS_SLOT);                  // [5][512]
+    float4* s_park = s_tail + C_TAIL * C_THREADS;                                // [4][512]
     int* s_bin_cnt = reinterpret_cast<int*>(smem + CS_BINCNT);
     int* s_bin_start = reinterpret_cast<int*>(smem + CS_BINSTART);
     unsigned short* s_binlist = reinterpret_cast<unsigned short*>(smem + CS_BINLIST);
@@ -517,22 +530,25 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     int* s_nbr_prev = reinterpret_cast<int*>(smem + CS_MISC + 40);
     int* s_nnz = reinterpret_cast<int*>(smem + CS_MISC + 72);
     unsigned* s_dtmin = reinterpret_cast<unsigned*>(smem + CS_MISC + 76);
+    int* s_next = reinterpret_cast<int*>(smem + CS_MISC + 80);
     uint32_t* s_halo = reinterpret_cast<uint32_t*>(smem + CS_HALO);
+    int2* s_wtot = reinterpret_cast<int2*>(smem + CS_WTOT);
 
     const int tid = threadIdx.x;
     const DispatchEntry ent = P.dispatch[blockIdx.x];
     const bool has_particle = (uint32_t)tid < ent.count;
-    float* const slot = s_slot + (size_t)tid * C_SLOT;
+    float4* const tail = s_tail + tid; // tail[k * C_THREADS]: a(k+1) of this particle, later payload vector k
+    float4* const park = s_park + tid;
     // ---- the particle: position now (registers), the rest of the record on its way into the slot (cp.async, no registers)
     float x[3] = {0.f, 0.f, 0.f};
     uint32_t flags = 0;
     if (has_particle) {
         const uint32_t si = P.perm[ent.first + tid];
-        cp_async16(slot + 0, &P.src.a1[si]);
-        cp_async16(slot + 4, &P.src.a2[si]);
-        cp_async16(slot + 8, &P.src.a3[si]);
-        cp_async16(slot + 12, &P.src.a4[si]);
-        cp_async16(slot + 16, &P.src.a5[si]);
+        cp_async16(tail + 0 * C_THREADS, &P.src.a1[si]);
+        cp_async16(tail + 1 * C_THREADS, &P.src.a2[si]);
+        cp_async16(tail + 2 * C_THREADS, &P.src.a3[si]);
+        cp_async16(tail + 3 * C_THREADS, &P.src.a4[si]);
+        cp_async16(tail + 4 * C_THREADS, &P.src.a5[si]);
         const float4 r0 = P.src.a0[si];
         x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; flags = __float_as_uint(r0.w);
     }
@@ -542,7 +558,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         s_nbr_prev[tid] = P.nbr_prev[ent.block * 8 + tid];
         s_halo[tid] = (P.world > 1 && nid >= 0) ? P.blk_halo[nid] : 0u;
     }
-    if (tid == 0) { mbar_init(s_bar, 1); *s_dtmin = SPK_DT_RAW_NONE; }
+    if (tid == 0) { mbar_init(s_bar, 1); *s_dtmin = SPK_DT_RAW_NONE; *s_next = 0; }
     for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64; i += C_THREADS) s_acc[i] = 0.f;
     if (tid < 224) s_bin_cnt[tid] = 0;
     __syncthreads();
@@ -622,11 +638,11 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         if constexpr (updater_is_phased<Updater>::value) {
             // phase 1: advection and F update; position, velocity and velocity gradient are final afterwards: stored / parked
             {
-                const float4 r1 = *reinterpret_cast<const float4*>(slot), r2 = *reinterpret_cast<const float4*>(slot + 4);
+                const float4 r1 = tail[0], r2 = tail[C_THREADS];
                 p.F.m[0] = r1.x; p.F.m[1] = r1.y; p.F.m[2] = r1.z; p.F.m[3] = r1.w;
                 p.F.m[4] = r2.x; p.F.m[5] = r2.y; p.F.m[6] = r2.z; p.F.m[7] = r2.w;
-                p.F.m[8] = slot[8];
-                p.orig_id = __float_as_uint(slot[18]);
+                p.F.m[8] = tail[2 * C_THREADS].x;
+                p.orig_id = __float_as_uint(tail[4 * C_THREADS].z);
             }
             Updater::advect(model, P.cold, h, dt, p, vel, G, P.user);
             bool inside = true;
@@ -643,39 +659,35 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             if (inside) bin = t2[0] + 6 * t2[1] + 36 * t2[2];
             P.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
             P.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
-            float4* park = reinterpret_cast<float4*>(slot + C_PARK);
             park[0] = make_float4(G.m[0], G.m[1], G.m[2], G.m[3]);
-            park[1] = make_float4(G.m[4], G.m[5], G.m[6], G.m[7]);
-            park[2] = make_float4(G.m[8], vel[0], vel[1], vel[2]);
-            park[3] = make_float4(ref2[0], ref2[1], ref2[2], 0.f);
+            park[C_THREADS] = make_float4(G.m[4], G.m[5], G.m[6], G.m[7]);
+            park[2 * C_THREADS] = make_float4(G.m[8], vel[0], vel[1], vel[2]);
+            park[3 * C_THREADS] = make_float4(ref2[0], ref2[1], ref2[2], 0.f);
             spk_compiler_fence();
             // phase 2: the decomposition, alone in the register file
             Svd3 svd;
-            if (model_needs_svd(model)) svd = Updater::decompose(model, p.F, P.user);
+            if (Updater::needs_decomposition(model)) svd = Updater::decompose(model, p.F, P.user);
             spk_compiler_fence();
             // phase 3: plasticity, failure, energies, stress on the scalars of the record (read from the slot only now)
             {
-                const float4 r3 = *reinterpret_cast<const float4*>(slot + 8), r4 = *reinterpret_cast<const float4*>(slot + 12),
-                             r5 = *reinterpret_cast<const float4*>(slot + 16);
+                const float4 r3 = tail[2 * C_THREADS], r4 = tail[3 * C_THREADS], r5 = tail[4 * C_THREADS];
                 p.jp = r3.y; p.mass = r3.z; p.volume0 = r3.w;
                 p.phase = r4.x; p.psi_pos = r4.y; p.elastic_hardening = r4.z; p.plastic_hardening = r4.w;
                 p.log_vol_gain = r5.x; p.nacc_alpha = r5.y; p.orig_id = __float_as_uint(r5.z);
             }
             const uint32_t flags0 = p.flags;
-            do_p2g = Updater::constitutive(model, p, svd, slot + C_PARK, stress, P.user);
+            do_p2g = Updater::constitutive(model, p, svd, ParkedGradient{park}, stress, P.user);
             if (p.flags != flags0) P.dst.a0[di].w = __uint_as_float(p.flags); // the particle failed in phase 3 (rare)
             spk_compiler_fence();
             {
-                const float4 g0 = park[0], g1 = park[1], g2 = park[2], g3 = park[3];
+                const float4 g0 = park[0], g1 = park[C_THREADS], g2 = park[2 * C_THREADS], g3 = park[3 * C_THREADS];
                 G.m[0] = g0.x; G.m[1] = g0.y; G.m[2] = g0.z; G.m[3] = g0.w; G.m[4] = g1.x; G.m[5] = g1.y; G.m[6] = g1.z; G.m[7] = g1.w; G.m[8] = g2.x;
                 vel[0] = g2.y; vel[1] = g2.z; vel[2] = g2.w;
                 ref2[0] = g3.x; ref2[1] = g3.y; ref2[2] = g3.z;
             }
         } else {
             {
-                const float4 r1 = *reinterpret_cast<const float4*>(slot), r2 = *reinterpret_cast<const float4*>(slot + 4),
-                             r3 = *reinterpret_cast<const float4*>(slot + 8), r4 = *reinterpret_cast<const float4*>(slot + 12),
-                             r5 = *reinterpret_cast<const float4*>(slot + 16);
+                const float4 r1 = tail[0], r2 = tail[C_THREADS], r3 = tail[2 * C_THREADS], r4 = tail[3 * C_THREADS], r5 = tail[4 * C_THREADS];
                 p.F.m[0] = r1.x; p.F.m[1] = r1.y; p.F.m[2] = r1.z; p.F.m[3] = r1.w;
                 p.F.m[4] = r2.x; p.F.m[5] = r2.y; p.F.m[6] = r2.z; p.F.m[7] = r2.w;
                 p.F.m[8] = r3.x; p.jp = r3.y; p.mass = r3.z; p.volume0 = r3.w;
@@ -723,14 +735,13 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             for (int a = 0; a < 3; ++a) f2[a] = spk_div_h(-ref2[a], h, inv_h);
             float wx[3];
             quad_weights(f2[0], wx);
-            float4* q = reinterpret_cast<float4*>(slot);
-            q[0] = make_float4(p.mass, M_(A, 0, 0) * ref2[0] + M_(A, 0, 1) * ref2[1] + M_(A, 0, 2) * ref2[2] + p.mass * vel[0],
+            tail[0] = make_float4(p.mass, M_(A, 0, 0) * ref2[0] + M_(A, 0, 1) * ref2[1] + M_(A, 0, 2) * ref2[2] + p.mass * vel[0],
                                M_(A, 1, 0) * ref2[0] + M_(A, 1, 1) * ref2[1] + M_(A, 1, 2) * ref2[2] + p.mass * vel[1],
                                M_(A, 2, 0) * ref2[0] + M_(A, 2, 1) * ref2[1] + M_(A, 2, 2) * ref2[2] + p.mass * vel[2]);
-            q[1] = make_float4(h * M_(A, 0, 0), h * M_(A, 1, 0), h * M_(A, 2, 0), psi_mass);
-            q[2] = make_float4(h * M_(A, 0, 1), h * M_(A, 1, 1), h * M_(A, 2, 1), psi_mass * p.psi_pos);
-            q[3] = make_float4(h * M_(A, 0, 2), h * M_(A, 1, 2), h * M_(A, 2, 2), f2[1]);
-            q[4] = make_float4(wx[0], wx[1], wx[2], f2[2]);
+            tail[C_THREADS] = make_float4(h * M_(A, 0, 0), h * M_(A, 1, 0), h * M_(A, 2, 0), psi_mass);
+            tail[2 * C_THREADS] = make_float4(h * M_(A, 0, 1), h * M_(A, 1, 1), h * M_(A, 2, 1), psi_mass * p.psi_pos);
+            tail[3 * C_THREADS] = make_float4(h * M_(A, 0, 2), h * M_(A, 1, 2), h * M_(A, 2, 2), f2[1]);
+            tail[4 * C_THREADS] = make_float4(wx[0], wx[1], wx[2], f2[2]);
         }
     }
     cand_bits = __reduce_min_sync(0xffffffffu, cand_bits);
@@ -739,25 +750,37 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     if (has_particle) rank = atomicAdd(&s_bin_cnt[bin], 1);
     __syncthreads();
 
-    // ---- counting sort of the slots by stencil-base cell (bin 216 = particles without P2G): exclusive scan by warp 0
-    if (tid < 32) {
-        int c[7], sum = 0, nz = 0;
+    // ---- counting sort of the slots by stencil-base cell (bin 216 = particles without P2G): exclusive scan of the 217 counters by
+    // 7 warps (one bin per thread: warp scan, then the per-warp totals), and the list of the occupied bins in bin order
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        int c = 0, inc = 0, nzb = 0;
+        bool occ = false;
+        if (tid < 224) {
+            c = s_bin_cnt[tid];
+            occ = c != 0 && tid < NBINS;
+            const unsigned ball = __ballot_sync(0xffffffffu, occ);
+            nzb = __popc(ball & spk_lanemask_lt());
+            inc = c;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) { c[k] = s_bin_cnt[tid * 7 + k]; sum += c[k]; nz += (c[k] != 0 && tid * 7 + k < NBINS) ? 1 : 0; }
-        int inc = sum, inz = nz;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, inc, d), oz = __shfl_up_sync(0xffffffffu, inz, d);
-            if (tid >= d) { inc += o; inz += oz; }
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (lane == 31) s_wtot[warp] = make_int2(inc, __popc(ball));
         }
-        int run = inc - sum, runz = inz - nz;
+        __syncthreads();
+        if (tid < 224) {
+            int base = 0, nzbase = 0;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            s_bin_start[tid * 7 + k] = run;
-            run += c[k];
-            if (c[k] != 0 && tid * 7 + k < NBINS) s_binlist[runz++] = (unsigned short)(tid * 7 + k);
+            for (int wv = 0; wv < 7; ++wv) {
+                const int2 t = s_wtot[wv];
+                if (wv < warp) { base += t.x; nzbase += t.y; }
+            }
+            if (tid == 223) *s_nnz = nzbase + s_wtot[6].y;
+            s_bin_start[tid] = base + inc - c;
+            if (occ) s_binlist[nzbase + nzb] = (unsigned short)tid;
         }
-        if (tid == 31) *s_nnz = inz;
     }
     __syncthreads();
     if (has_particle) s_sorted[s_bin_start[bin] + rank] = (unsigned short)tid;
@@ -766,7 +789,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     // ---- stage 2: 9-lane groups, one occupied bin at a time; lane = stencil column (sy, sz), 3 nodes (sx = 0..2) x 6 channels in
     // registers over the bin's particles (payload reads are broadcasts), then one flush of the 18 sums into the tile
     {
-        const int lane = tid & 31, warp = tid >> 5;
+        const int lane = tid & 31;
         const int grp = lane / 9, l9 = lane - grp * 9;
         const int sy = l9 % 3, sz = l9 / 3;
         const float fsy = (float)sy, fsz = (float)sz;
@@ -775,16 +798,19 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         const float Az = sz == 1 ? -1.f : 0.5f, Bz = sz == 0 ? 1.5f : (sz == 1 ? 1.f : 0.5f), Cz = sz == 1 ? 0.75f : 0.f;
         const int nnz = *s_nnz;
         if (grp < 3) {
-            for (int e = warp * 3 + grp; e < nnz; e += (C_THREADS / 32) * 3) {
+            for (;;) { // a warp takes the next three occupied bins (in bin order: mostly x-neighbours) until the list is exhausted
+                int e = 0;
+                if (lane == 0) e = atomicAdd(s_next, 3);
+                e = __shfl_sync(0x07ffffffu, e, 0) + grp;
+                if (e - grp >= nnz) break;
+                if (e >= nnz) continue;
                 const int b = s_binlist[e];
                 const int start = s_bin_start[b], cnt = s_bin_cnt[b];
                 float aM[3] = {0.f, 0.f, 0.f}, aX[3] = {0.f, 0.f, 0.f}, aY[3] = {0.f, 0.f, 0.f}, aZ[3] = {0.f, 0.f, 0.f}, aPm[3] = {0.f, 0.f, 0.f},
                       aPp[3] = {0.f, 0.f, 0.f};
                 for (int i = 0; i < cnt; ++i) {
-                    const float* pay = s_slot + (size_t)s_sorted[start + i] * C_SLOT;
-                    const float4 q0 = *reinterpret_cast<const float4*>(pay), q1 = *reinterpret_cast<const float4*>(pay + 4),
-                                 q2 = *reinterpret_cast<const float4*>(pay + 8), q3 = *reinterpret_cast<const float4*>(pay + 12),
-                                 q4 = *reinterpret_cast<const float4*>(pay + 16);
+                    const float4* pay = s_tail + s_sorted[start + i];
+                    const float4 q0 = pay[0], q1 = pay[C_THREADS], q2 = pay[2 * C_THREADS], q3 = pay[3 * C_THREADS], q4 = pay[4 * C_THREADS];
                     const float dy = q3.w - By, dz = q4.w - Bz;
                     const float wyz = fmaf(Ay * dy, dy, Cy) * fmaf(Az * dz, dz, Cz);
                     // node momentum contribution at sx = 0: c + sy * hA[:,1] + sz * hA[:,2]
@@ -801,9 +827,10 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                 }
                 const int bxc = b % 6, byc = (b / 6) % 6, bzc = b / 36;
                 const int byz = cell_part(byc + sy, 1) + oct_part(byc + sy, 1) * 384 + cell_part(bzc + sz, 2) + oct_part(bzc + sz, 2) * 384;
+                const int zsw = (bzc + sz) & 2; // SPK_ACC_SWZ: bit 1 of the node's z inside its block flips bit 1 of its x
 #pragma unroll
                 for (int sx = 0; sx < 3; ++sx) {
-                    float* a = &s_acc[byz + cell_part(bxc + sx, 0) + oct_part(bxc + sx, 0) * 384];
+                    float* a = &s_acc[byz + (cell_part(bxc + sx, 0) ^ zsw) + oct_part(bxc + sx, 0) * 384];
                     atomicAdd(a + 0 * 64, aM[sx]);
                     atomicAdd(a + 1 * 64, aX[sx]);
                     atomicAdd(a + 2 * 64, aY[sx]);

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) reset_grid_kernel(GridBuffers next, GridB
     if (pb >= 0) {
         const size_t pnode = (size_t)pb * 64 + cell;
         float4 n = prev.cacheN[pnode];
-        n.w = spk_ftz(prev.acc[(size_t)pb * (SPK_ACC_CHANNELS * 64) + cell]); // prev_mass = prev.mass (reset_grid.rs:54)
+        n.w = spk_ftz(prev.acc[(size_t)pb * (SPK_ACC_CHANNELS * 64) + SPK_ACC_SWZ(cell)]); // prev_mass = prev.mass (reset_grid.rs:54)
         next.cacheN[node] = n;
         next.cacheD[node] = prev.cacheD[pnode];
         next.proj[node] = prev.proj[pnode];
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) grid_update_kernel(GridBuffers g, uint32_
     const uint32_t b = blockIdx.x * 4 + (threadIdx.x >> 6);
     const uint32_t cell = threadIdx.x & 63;
     if (b >= nab) return;
-    const float* acc = g.acc + (size_t)b * (SPK_ACC_CHANNELS * 64);
+    const float* acc = g.acc + (size_t)b * (SPK_ACC_CHANNELS * 64) + SPK_ACC_SWZ(cell) - cell; // acc[ch * 64 + cell] below: the swizzled slot
     const size_t node = (size_t)b * 64 + cell;
     // the reference's `red.global.add.f32` flushes subnormals (PTX ISA); keep 1/mass finite the same way
     const float mass = spk_ftz(acc[cell]);
@@ -373,7 +373,7 @@ __global__ void grid_export_kernel(GridBuffers g, uint32_t nblocks, SpkGpuGridNo
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nblocks * 64) return;
     const uint32_t b = t >> 6, cell = t & 63;
-    const float* acc = g.acc + (size_t)b * (SPK_ACC_CHANNELS * 64);
+    const float* acc = g.acc + (size_t)b * (SPK_ACC_CHANNELS * 64) + SPK_ACC_SWZ(cell) - cell;
     SpkGpuGridNode n;
     n.mass = spk_ftz(acc[cell]);
     n.psi_mass = spk_ftz(acc[5 * 64 + cell]);

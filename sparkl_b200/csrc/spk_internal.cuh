@@ -33,6 +33,15 @@
 #define SPK_REF_G2P2G_THREADS 64u /* dim2: src_kernels/cuda/mod.rs:12-13 */
 #endif
 #define SPK_ACC_CHANNELS 6
+// Position of a cell inside the 64-float channel chunk of `acc` (NOT of `vel` / the collider cache).  dim3: bit 1 of the cell's z flips
+// bit 1 of its x, so that the 3 x 3 (y, z) columns of a P2G stencil fall into 9 different shared-memory banks when a g2p2g CTA adds a
+// bin's sums into its tile (without it the columns sz = 0 and sz = 2 share a bank).  The tile chunk is copied to / from global memory
+// as a whole (TMA), so every kernel that addresses one node of `acc` uses the same mapping.
+#if SPK_DIM == 3
+#define SPK_ACC_SWZ(cell) ((cell) ^ (((cell) >> 4) & 2u))
+#else
+#define SPK_ACC_SWZ(cell) (cell)
+#endif
 #define SPK_EMPTY_KEY 0xffffffffffffffffull
 #define SPK_NO_BLOCK 0xffffffffu
 #ifndef SPK_G2P2G_CHUNK
@@ -154,6 +163,8 @@ struct spk_ctx {
     unsigned long long dt_acc_host; // GpuTimestepLength accumulator (host-authoritative)
     // models / colliders
     DevModel* models; size_t nmodels; uint32_t model_flags_any; // bit0: any model needs an SVD
+    uint32_t model_mask;  // union of model_mask_of(...) over the uploaded model table (SPK_MM_*, spk_math.cuh): picks the kernel instantiation
+    int g2p2g_specialize; // 1 (default): use the model-set specialisations of the fused kernel; 0: always the generic one (SPK_G2P2G_GENERIC=1)
     DevCollider* colliders; size_t ncolliders;
     float* collider_data; // device copies of the heightfield matrices, one allocation
     // grid

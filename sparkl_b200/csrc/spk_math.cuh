@@ -216,9 +216,23 @@ struct ParticleState { // everything g2p2g keeps in registers for one particle
     uint32_t orig_id;
 };
 
-__device__ __forceinline__ bool model_is_fluid(const DevModel& m) { return m.ctag == SPK_CONSTITUTIVE_MONAGHAN; }
+// Model mask: which constitutive / plastic / failure models a kernel instantiation is COMPILED for.  The library instantiates the
+// fused kernel for a few common model sets (sand, fluid, elastic solids) next to the generic one and picks the narrowest
+// instantiation that covers the uploaded model table (spk_g2p2g.cu): the dead models cost neither registers nor instruction cache.
+#define SPK_MM_C(tag) (1u << (tag))
+#define SPK_MM_P(tag) (1u << (4 + (tag)))
+#define SPK_MM_F_MAX_STRESS (1u << 10)
+#define SPK_MM_ALL 0xffffffffu
+__host__ __device__ __forceinline__ uint32_t model_mask_of(uint32_t ctag, uint32_t ptag, uint32_t ftag) {
+    return SPK_MM_C(ctag) | SPK_MM_P(ptag) | (ftag == SPK_FAILURE_MAXIMUM_STRESS ? SPK_MM_F_MAX_STRESS : 0u);
+}
+
+template <uint32_t MM = SPK_MM_ALL>
+__device__ __forceinline__ bool model_is_fluid(const DevModel& m) { return (MM & SPK_MM_C(SPK_CONSTITUTIVE_MONAGHAN)) && m.ctag == SPK_CONSTITUTIVE_MONAGHAN; }
+template <uint32_t MM = SPK_MM_ALL>
 __device__ __forceinline__ bool model_needs_svd(const DevModel& m) {
-    return m.ctag == SPK_CONSTITUTIVE_COROTATED || (m.ptag <= SPK_PLASTIC_SNOW);
+    constexpr uint32_t plastic = SPK_MM_P(SPK_PLASTIC_DRUCKER_PRAGER) | SPK_MM_P(SPK_PLASTIC_NACC) | SPK_MM_P(SPK_PLASTIC_RANKINE) | SPK_MM_P(SPK_PLASTIC_SNOW);
+    return ((MM & SPK_MM_C(SPK_CONSTITUTIVE_COROTATED)) && m.ctag == SPK_CONSTITUTIVE_COROTATED) || ((MM & plastic) && m.ptag <= SPK_PLASTIC_SNOW);
 }
 
 // eos_monaghan_sph.rs:28-38
@@ -229,11 +243,13 @@ __device__ __forceinline__ float monaghan_pressure(const DevModel& m, float mass
 
 // GpuPlasticModel::update_particle (gpu_plastic_model.rs:21-61) on a shared SVD.  Returns true when F changed
 // (svd.s then holds the projected singular values and F has been recomposed).
+template <uint32_t MM>
 __device__ __forceinline__ bool plastic_update_other(const DevModel& m, ParticleState& p, Svd3& svd);
+template <uint32_t MM = SPK_MM_ALL>
 __device__ __forceinline__ bool plastic_update(const DevModel& m, ParticleState& p, Svd3& svd) {
     float* s = svd.s;
-    switch (m.ptag) {
-    case SPK_PLASTIC_DRUCKER_PRAGER: { // plasticity_drucker_prager.rs:36-104
+    if ((MM & SPK_MM_P(SPK_PLASTIC_DRUCKER_PRAGER)) && m.ptag == SPK_PLASTIC_DRUCKER_PRAGER) { // plasticity_drucker_prager.rs:36-104
+        {
         if ((m.flags & 2u) && p.phase != 0.f) return false;
         const float h0 = m.p[0], h1 = m.p[1], h2 = m.p[2], h3 = m.p[3], lambda = m.p[4], mu = m.p[5], volume_correction = m.p[6];
         const float q = p.plastic_hardening;
@@ -267,15 +283,17 @@ __device__ __forceinline__ bool plastic_update(const DevModel& m, ParticleState&
         p.plastic_hardening += dq;
         p.F = svd_recompose(svd.u, s, svd.v);
         return true;
+        }
     }
-    case SPK_PLASTIC_NACC: case SPK_PLASTIC_RANKINE: case SPK_PLASTIC_SNOW: return plastic_update_other(m, p, svd);
-    default: return false; // Custom / None: no-op (gpu_plastic_model.rs:59)
-    }
+    constexpr uint32_t others = SPK_MM_P(SPK_PLASTIC_NACC) | SPK_MM_P(SPK_PLASTIC_RANKINE) | SPK_MM_P(SPK_PLASTIC_SNOW);
+    if ((MM & others) && m.ptag >= SPK_PLASTIC_NACC && m.ptag <= SPK_PLASTIC_SNOW) return plastic_update_other<MM>(m, p, svd);
+    return false; // Custom / None: no-op (gpu_plastic_model.rs:59)
 }
+template <uint32_t MM>
 __device__ __forceinline__ bool plastic_update_other(const DevModel& m, ParticleState& p, Svd3& svd) {
     float* s = svd.s;
-    switch (m.ptag) {
-    case SPK_PLASTIC_NACC: { // plasticity_nacc.rs:61-165
+    if ((MM & SPK_MM_P(SPK_PLASTIC_NACC)) && m.ptag == SPK_PLASTIC_NACC) { // plasticity_nacc.rs:61-165
+        {
         const float mu = m.p[0], kappa = m.p[1], xi = m.p[2], beta = m.p[3], mm = m.p[4];
         const bool hardening_enabled = (m.flags & 4u) != 0;
         const float d = 3.f;
@@ -324,8 +342,10 @@ __device__ __forceinline__ bool plastic_update_other(const DevModel& m, Particle
         p.nacc_alpha = alpha;
         p.F = svd_recompose(svd.u, s, svd.v);
         return true;
+        }
     }
-    case SPK_PLASTIC_RANKINE: { // plasticity_rankine.rs:35-78
+    if ((MM & SPK_MM_P(SPK_PLASTIC_RANKINE)) && m.ptag == SPK_PLASTIC_RANKINE) { // plasticity_rankine.rs:35-78
+        {
         const float mu = m.p[0], lambda = m.p[1], tensile = m.p[2], softening = m.p[3];
         float e[3] = {logf(s[0]), logf(s[1]), logf(s[2])};
         const float pr0 = e[0], pr1 = e[1], pr2 = e[2];
@@ -351,8 +371,10 @@ __device__ __forceinline__ bool plastic_update_other(const DevModel& m, Particle
         s[0] = expf(e[0]); s[1] = expf(e[1]); s[2] = expf(e[2]);
         p.F = svd_recompose(svd.u, s, svd.v);
         return true;
+        }
     }
-    case SPK_PLASTIC_SNOW: { // plasticity_snow.rs:26-48
+    if ((MM & SPK_MM_P(SPK_PLASTIC_SNOW)) && m.ptag == SPK_PLASTIC_SNOW) { // plasticity_snow.rs:26-48
+        {
         const float lo = 1.f - m.p[0], hi = 1.f + m.p[1];
         const float n0 = fminf(fmaxf(s[0], lo), hi), n1 = fminf(fmaxf(s[1], lo), hi), n2 = fminf(fmaxf(s[2], lo), hi);
         p.jp *= (s[0] * s[1] * s[2]) / (n0 * n1 * n2);
@@ -360,9 +382,9 @@ __device__ __forceinline__ bool plastic_update_other(const DevModel& m, Particle
         s[0] = n0; s[1] = n1; s[2] = n2;
         p.F = svd_recompose(svd.u, s, svd.v);
         return true;
+        }
     }
-    default: return false; // Custom / None: no-op (gpu_plastic_model.rs:59)
-    }
+    return false; // Custom / None: no-op (gpu_plastic_model.rs:59)
 }
 
 // CorotatedLinearElasticity::kirchhoff_stress, elasticity_corotated_linear.rs:31-77, from the shared SVD of F.
@@ -430,14 +452,15 @@ __device__ __forceinline__ Mat3 neo_hookean_stress(const DevModel& m, float phas
 // timestep bounds: estimate_particle_timestep_length (particle_updater.rs:47-70) + timestep.rs:74-112.
 // Returns the per-particle candidate BEFORE the max_dt/min_dt clamps (those are monotone and applied once to the
 // reduced value, SURVEY §2.2 "fused-op opportunities").  +inf when the particle imposes no bound.
-__device__ inline float particle_dt_candidate(const DevModel& m, float h, float mass, float volume0, float f00, float elastic_hardening, float vx, float vy, float vz) {
+template <uint32_t MM = SPK_MM_ALL>
+__device__ __forceinline__ float particle_dt_candidate(const DevModel& m, float h, float mass, float volume0, float f00, float elastic_hardening, float vx, float vy, float vz) {
     const float vn2 = vx * vx + vy * vy + vz * vz;
     const float vn = sqrtf(vn2);
     float cand = FLT_MAX;
     bool velocity_bound = false;
-    switch (m.ctag) {
-    case SPK_CONSTITUTIVE_COROTATED:
-    case SPK_CONSTITUTIVE_NEO_HOOKEAN: {
+    constexpr uint32_t solids = SPK_MM_C(SPK_CONSTITUTIVE_COROTATED) | SPK_MM_C(SPK_CONSTITUTIVE_NEO_HOOKEAN);
+    if ((MM & solids) && (m.ctag == SPK_CONSTITUTIVE_COROTATED || m.ctag == SPK_CONSTITUTIVE_NEO_HOOKEAN)) {
+        {
         // elasticity_sound_speed_timestep_bound.rs:22-34; NeoHookean is called with (cell_width, hardening) swapped
         // (gpu_constitutive_model.rs:129-137)
         const bool nh = m.ctag == SPK_CONSTITUTIVE_NEO_HOOKEAN;
@@ -449,9 +472,9 @@ __device__ inline float particle_dt_candidate(const DevModel& m, float h, float 
         const float c_dir = sqrtf((bulk + 4.f / 3.f * shear) * 1.f / density0);
         cand = m.c[0] * cw / fmaxf(vn, c_dir);
         velocity_bound = true;
-        break;
-    }
-    case SPK_CONSTITUTIVE_MONAGHAN: { // eos_monaghan_sph.rs:72-99
+        }
+    } else if (model_is_fluid<MM>(m)) { // eos_monaghan_sph.rs:72-99
+        {
         const float j = f00;
         const float density0 = mass / volume0;
         const float pressure = -monaghan_pressure(m, mass, volume0, density0 / j);
@@ -459,10 +482,8 @@ __device__ inline float particle_dt_candidate(const DevModel& m, float h, float 
         const float c_square = fmaxf(vn2, 1.f) / 0.1f;
         cand = fminf(single, h / sqrtf(c_square));
         velocity_bound = true;
-        break;
-    }
-    default: break; // Custom: ActiveTimestepBounds::NONE
-    }
+        }
+    } // Custom: ActiveTimestepBounds::NONE
     if (velocity_bound) cand = fminf(cand, h / vn);
     return cand;
 }

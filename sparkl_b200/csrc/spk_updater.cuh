@@ -13,7 +13,8 @@
 #pragma once
 #include "spk_math.cuh"
 
-struct DefaultParticleUpdater {
+template <uint32_t MM>
+struct DefaultParticleUpdaterT {
     // The update comes in two phases so that the fused kernel can keep the interpolated velocity and velocity gradient in shared
     // memory (not in registers) across the SVD / return mapping / stress evaluation (spk_g2p2g_kernel.cuh, g2p2g_cell_kernel):
     //   advect        velocity handling, position, deformation-gradient update        particle_updater.rs:87-138 (+ :151-155)
@@ -37,7 +38,7 @@ struct DefaultParticleUpdater {
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a) p.x[a] += vel[a] * dt;
-        if (!model_is_fluid(model)) {
+        if (!model_is_fluid<MM>(model)) {
             Mat3 Gdt;
 #pragma unroll
             for (int i = 0; i < 9; ++i) Gdt.m[i] = G.m[i] * dt;
@@ -54,14 +55,16 @@ struct DefaultParticleUpdater {
         }
     }
 
+    __device__ __forceinline__ static bool needs_decomposition(const DevModel& model) { return model_needs_svd<MM>(model); }
     // the one decomposition F = U diag(s) V^T that plasticity, energy and stress share (called when model_needs_svd(model))
     __device__ __forceinline__ static Svd3 decompose(const DevModel& /*model*/, const Mat3& F, const void* /*user*/) { return svd3(F); }
 
-    // `svd`: decompose(F) when model_needs_svd(model), unspecified otherwise.  `Gp`: the (final) velocity gradient, 9 floats
-    // column-major, wherever the caller keeps it — only the Monaghan viscosity reads it
-    __device__ __forceinline__ static bool constitutive(const DevModel& model, ParticleState& p, Svd3& svd, const float* Gp, Mat3& stress, const void* /*user*/) {
-        const bool is_fluid = model_is_fluid(model);
-        if (model_needs_svd(model)) plastic_update(model, p, svd);
+    // `svd`: decompose(F) when model_needs_svd(model), unspecified otherwise.  `Gp`: the (final) velocity gradient, Gp[i] =
+    // G.m[i] column-major, wherever the caller keeps it — only the Monaghan viscosity reads it
+    template <class GradientView>
+    __device__ __forceinline__ static bool constitutive(const DevModel& model, ParticleState& p, Svd3& svd, const GradientView& Gp, Mat3& stress, const void* /*user*/) {
+        const bool is_fluid = model_is_fluid<MM>(model);
+        if (model_needs_svd<MM>(model)) plastic_update<MM>(model, p, svd);
         const float j = mat_det(p.F);
         const float density_def_grad = (p.mass / p.volume0) / j;
         bool do_p2g = true;
@@ -73,12 +76,12 @@ struct DefaultParticleUpdater {
         if (do_p2g) {
             // pos energy (gpu_constitutive_model.rs:27-48)
             float energy = 0.f;
-            if (model.ctag == SPK_CONSTITUTIVE_COROTATED) { // elasticity_corotated_linear.rs:104-118
+            if ((MM & SPK_MM_C(SPK_CONSTITUTIVE_COROTATED)) && model.ctag == SPK_CONSTITUTIVE_COROTATED) { // elasticity_corotated_linear.rs:104-118
                 const float a0 = fmaxf(svd.s[0] - 1.f, 0.f), a1 = fmaxf(svd.s[1] - 1.f, 0.f), a2 = fmaxf(svd.s[2] - 1.f, 0.f);
                 const float pos_dev = model.c[2] * p.elastic_hardening * (a0 * a0 + a1 * a1 + a2 * a2);
                 const float sph = model.c[1] * p.elastic_hardening / 2.f * (j - 1.f) * (j - 1.f);
                 energy = j < 1.f ? pos_dev : pos_dev + sph;
-            } else if (model.ctag == SPK_CONSTITUTIVE_NEO_HOOKEAN) { // elasticity_neo_hookean.rs:117-141
+            } else if ((MM & SPK_MM_C(SPK_CONSTITUTIVE_NEO_HOOKEAN)) && model.ctag == SPK_CONSTITUTIVE_NEO_HOOKEAN) { // elasticity_neo_hookean.rs:117-141
                 const float pc = (1.f - 0.001f) * p.phase * p.phase + 0.001f;
                 const float hard = p.elastic_hardening;
                 const float kk = 2.f / 3.f * model.c[2] * hard + model.c[1] * hard;
@@ -92,10 +95,10 @@ struct DefaultParticleUpdater {
             p.psi_pos = fmaxf(p.psi_pos, energy);
             // stress (gpu_constitutive_model.rs:50-86); with a failure model the reference evaluates it twice (before/after
             // the phase change, particle_updater.rs:185-235)
-            for (int pass = (model.ftag == SPK_FAILURE_MAXIMUM_STRESS ? 0 : 1); pass < 2; ++pass) {
-                if (model.ctag == SPK_CONSTITUTIVE_COROTATED) stress = corotated_stress(model, p.phase, p.elastic_hardening, p.F, svd, j);
-                else if (model.ctag == SPK_CONSTITUTIVE_NEO_HOOKEAN) stress = neo_hookean_stress(model, p.phase, p.elastic_hardening, p.F, j);
-                else if (model.ctag == SPK_CONSTITUTIVE_MONAGHAN) { // eos_monaghan_sph.rs:44-63, quirk 7
+            for (int pass = (((MM & SPK_MM_F_MAX_STRESS) && model.ftag == SPK_FAILURE_MAXIMUM_STRESS) ? 0 : 1); pass < 2; ++pass) {
+                if ((MM & SPK_MM_C(SPK_CONSTITUTIVE_COROTATED)) && model.ctag == SPK_CONSTITUTIVE_COROTATED) stress = corotated_stress(model, p.phase, p.elastic_hardening, p.F, svd, j);
+                else if ((MM & SPK_MM_C(SPK_CONSTITUTIVE_NEO_HOOKEAN)) && model.ctag == SPK_CONSTITUTIVE_NEO_HOOKEAN) stress = neo_hookean_stress(model, p.phase, p.elastic_hardening, p.F, j);
+                else if (is_fluid) { // eos_monaghan_sph.rs:44-63, quirk 7
                     const float density_fluid = (p.mass / p.volume0) / p.F.m[0];
                     const float pr = -monaghan_pressure(model, p.mass, p.volume0, density_fluid) * p.jp;
                     stress = mat_zero();
@@ -113,7 +116,7 @@ struct DefaultParticleUpdater {
                         for (int i = 0; i < 9; ++i) stress.m[i] += kv * sr.m[i];
                     }
                 }
-                if (pass == 0) { // failure_maximum_stress.rs:20-28
+                if ((MM & SPK_MM_F_MAX_STRESS) && pass == 0) { // failure_maximum_stress.rs:20-28
                     bool finite = true;
 #pragma unroll
                     for (int i = 0; i < 9; ++i) finite = finite && isfinite(stress.m[i]);
@@ -136,13 +139,14 @@ struct DefaultParticleUpdater {
                                                   Mat3& stress, const void* user) {
         advect(model, cold, h, dt, p, vel, G, user);
         Svd3 svd;
-        if (model_needs_svd(model)) svd = decompose(model, p.F, user);
+        if (model_needs_svd<MM>(model)) svd = decompose(model, p.F, user);
         return constitutive(model, p, svd, G.m, stress, user);
     }
 
     // estimate_particle_timestep_length (particle_updater.rs:47-70) + timestep.rs:74-112: the particle's dt candidate BEFORE the
     // max_dt / min_dt clamps; FLT_MAX-like when it imposes no bound
     __device__ __forceinline__ static float dt_candidate(const DevModel& model, float h, const ParticleState& p, const float (&vel)[3], const void* /*user*/) {
-        return particle_dt_candidate(model, h, p.mass, p.volume0, p.F.m[0], p.elastic_hardening, vel[0], vel[1], vel[2]);
+        return particle_dt_candidate<MM>(model, h, p.mass, p.volume0, p.F.m[0], p.elastic_hardening, vel[0], vel[1], vel[2]);
     }
 };
+using DefaultParticleUpdater = DefaultParticleUpdaterT<SPK_MM_ALL>; // every model of src_core/dynamics/models compiled in

@@ -71,6 +71,8 @@ def _to_device_layout(hdr, nodes):
     for a in range(3):
         g["acc"][:nb, 1 + a] = nodes["momentum_velocity"][..., a]
     g["acc"][:nb, 4], g["acc"][:nb, 5] = nodes["psi_momentum_velocity"], nodes["psi_mass"]
+    cell = np.arange(64)
+    g["acc"][:, :, cell ^ ((cell >> 4) & 2)] = g["acc"][:, :, cell].copy()  # SPK_ACC_SWZ (spk_internal.cuh): position of a cell inside a channel chunk
     tag, payload = nodes["projection_status_tag"].astype(np.uint32), nodes["projection_status_payload"].astype(np.uint32)
     g["proj"][:nb * 64] = (tag | np.where((tag == 1) | (tag == 2), payload << 2, 0)).ravel()
     g["cacheN"][:nb * 64, :3] = nodes["collision_normal"].reshape(-1, 3)
