@@ -45,7 +45,7 @@ uint32_t next_pow2(uint64_t v) {
 
 void free_grid(GridBuffers& g) {
     if (g.external_hash) { g.keys = nullptr; g.vals = nullptr; g.external_hash = 0; } // owned by the multi-GPU arena
-    dev_free(g.keys); dev_free(g.vals); dev_free(g.blk_key); dev_free(g.blk_first); dev_free(g.blk_count); dev_free(g.blk_halo);
+    dev_free(g.keys); dev_free(g.vals); dev_free(g.blk_key); dev_free(g.blk_first); dev_free(g.blk_count); dev_free(g.blk_halo); dev_free(g.blk_dfirst);
     dev_free(g.nbr_self); dev_free(g.nbr_prev); dev_free(g.vel); dev_free(g.acc); dev_free(g.proj); dev_free(g.cacheN); dev_free(g.cacheD);
 }
 // (re)allocate one grid buffer for `cap_hash` hash slots; contents are NOT preserved (only ever done on the next grid,
@@ -68,6 +68,7 @@ cudaError_t alloc_grid(spk_ctx* c, GridBuffers& g, uint32_t cap_hash) {
     if ((e = dev_alloc(g.blk_first, nb)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.blk_count, nb)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.blk_halo, nb)) != cudaSuccess) return e;
+    if ((e = dev_alloc(g.blk_dfirst, nb)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.nbr_self, nb * SPK_NBR)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.nbr_prev, nb * SPK_NBR)) != cudaSuccess) return e;
     if ((e = dev_alloc(g.vel, nn)) != cudaSuccess) return e;
@@ -99,7 +100,9 @@ cudaError_t ensure_dispatch(spk_ctx* c) {
     const uint64_t need = c->n / c->chunk + g.cap_blocks + 2;
     if (c->dispatch_cap >= need) return cudaSuccess;
     dev_free(c->dispatch);
+    dev_free(c->dispatch_nbr);
     cudaError_t e = dev_alloc(c->dispatch, need);
+    if (e == cudaSuccess) e = dev_alloc(c->dispatch_nbr, need * 2 * SPK_NBR);
     c->dispatch_cap = e == cudaSuccess ? (uint32_t)need : 0;
     return e;
 }
@@ -448,7 +451,7 @@ int spk_ctx_destroy(spk_ctx* c) {
     if (c->dist_arena) { c->grid[0].external_hash = c->grid[1].external_hash = 1; }
     free_particles(c);
     free_grid(c->grid[0]); free_grid(c->grid[1]);
-    dev_free(c->slot_cnt); dev_free(c->cell_cnt); dev_free(c->dispatch); dev_free(c->models); dev_free(c->colliders); dev_free(c->collider_data); dev_free(c->d_counters);
+    dev_free(c->slot_cnt); dev_free(c->cell_cnt); dev_free(c->dispatch); dev_free(c->dispatch_nbr); dev_free(c->models); dev_free(c->colliders); dev_free(c->collider_data); dev_free(c->d_counters);
     if (c->staging) cudaFree(c->staging);
     cudaStreamSynchronize(c->halo_stream);
     for (int k = 0; k < 8; ++k) {

@@ -25,6 +25,7 @@ struct G2P2GParams {
     const float4* cold;
     const uint32_t* perm;
     const DispatchEntry* dispatch;
+    const int32_t* dispatch_nbr; // [ndispatch][16]: nbr_self | nbr_prev of the entry's block
     const DevModel* models;
     const int32_t* nbr_self;
     const int32_t* nbr_prev;
@@ -472,6 +473,12 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
 //     in-CTA cell sort, which only moves 16-bit slot numbers);
 //   * the per-CTA fixed work (tile staging, zeroing, scan, flush: 8 TMA loads + 8 TMA reduce-adds) is paid once per 512 particles and
 //     the P2G bins hold twice the particles of a 256-particle chunk (the per-bin flush is the expensive part of P2G).
+#ifndef SPK_P2G_TRIPLE
+#define SPK_P2G_TRIPLE 0 /* 1: P2G work items are triples of x-neighbouring bins with a sliding window (5 node flushes per triple) */
+#endif
+#ifndef SPK_P2G_PREFETCH
+#define SPK_P2G_PREFETCH 0
+#endif
 #ifndef SPK_CELL_MIN_CTAS
 #define SPK_CELL_MIN_CTAS 2
 #endif
@@ -536,6 +543,29 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
 
     const int tid = threadIdx.x;
     const DispatchEntry ent = P.dispatch[blockIdx.x];
+    // ---- stage 0: velocity tile of the 2x2x2 blocks (transfer_global_blocks_to_shared_memory, g2p2g.rs:353-474).  Warp 0 reads the
+    // block ids of the tile (one coalesced 64-byte load that depends on blockIdx only) and launches the 8 TMA bulk copies by itself,
+    // before the CTA-wide barrier: the tile travels while the other warps zero the accumulators and fetch their particles
+    if (tid < 32) {
+        int nid = -1;
+        if (tid < 16) {
+            nid = P.dispatch_nbr[(size_t)blockIdx.x * 16 + tid];
+            s_nbr_self[tid] = nid; // s_nbr_prev follows s_nbr_self
+        }
+        if (tid < 8) s_halo[tid] = (P.world > 1 && nid >= 0) ? P.blk_halo[nid] : 0u;
+        __syncwarp();
+        if (tid == 0) {
+            mbar_init(s_bar, 1);
+            *s_dtmin = SPK_DT_RAW_NONE;
+            *s_next = 0;
+            uint32_t bytes = 0;
+            for (int o = 0; o < 8; ++o) bytes += s_nbr_prev[o] >= 0 ? 1024u : 0u;
+            fence_proxy_async();
+            mbar_expect_tx(s_bar, bytes);
+            for (int o = 0; o < 8; ++o)
+                if (s_nbr_prev[o] >= 0) tma_load_1d(&s_vel[o * 64], P.prev_vel + (size_t)s_nbr_prev[o] * 64, 1024u, s_bar);
+        }
+    }
     const bool has_particle = (uint32_t)tid < ent.count;
     float4* const tail = s_tail + tid; // tail[k * C_THREADS]: a(k+1) of this particle, later payload vector k
     float4* const park = s_park + tid;
@@ -552,26 +582,10 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         const float4 r0 = P.src.a0[si];
         x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; flags = __float_as_uint(r0.w);
     }
-    if (tid < 8) {
-        const int nid = P.nbr_self[ent.block * 8 + tid];
-        s_nbr_self[tid] = nid;
-        s_nbr_prev[tid] = P.nbr_prev[ent.block * 8 + tid];
-        s_halo[tid] = (P.world > 1 && nid >= 0) ? P.blk_halo[nid] : 0u;
-    }
-    if (tid == 0) { mbar_init(s_bar, 1); *s_dtmin = SPK_DT_RAW_NONE; *s_next = 0; }
     for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64; i += C_THREADS) s_acc[i] = 0.f;
     if (tid < 224) s_bin_cnt[tid] = 0;
     __syncthreads();
-    // ---- stage 0: velocity tile of the 2x2x2 blocks (transfer_global_blocks_to_shared_memory, g2p2g.rs:353-474)
-    if (tid == 0) {
-        uint32_t bytes = 0;
-        for (int o = 0; o < 8; ++o) bytes += s_nbr_prev[o] >= 0 ? 1024u : 0u;
-        fence_proxy_async();
-        mbar_expect_tx(s_bar, bytes);
-        for (int o = 0; o < 8; ++o)
-            if (s_nbr_prev[o] >= 0) tma_load_1d(&s_vel[o * 64], P.prev_vel + (size_t)s_nbr_prev[o] * 64, 1024u, s_bar);
-    }
-    if (s_nbr_prev[tid >> 6] < 0) s_vel[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s_nbr_prev[tid >> 6] < 0) s_vel[tid] = make_float4(0.f, 0.f, 0.f, 0.f); // blocks absent from the previous grid read as zero
 
     const float h = P.h, inv_h = P.inv_h, dt = P.dt;
     const float inv_d = 4.f / (h * h);
@@ -750,6 +764,56 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     if (has_particle) rank = atomicAdd(&s_bin_cnt[bin], 1);
     __syncthreads();
 
+#if SPK_P2G_TRIPLE
+    // ---- counting sort of the slots by stencil-base cell (bin 216 = particles without P2G): exclusive scan of the 217 counters by
+    // 7 warps (one bin per thread: warp scan, then the per-warp totals), and the list of the occupied bin TRIPLES (three x-neighbours
+    // 3t, 3t+1, 3t+2 of one (y, z) row: the work items of P2G) in bin order
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        int c = 0, inc = 0;
+        if (tid < 224) {
+            c = s_bin_cnt[tid];
+            inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (lane == 31) s_wtot[warp].x = inc;
+        }
+        if (tid >= 224 && tid < 256) { // warp 7: 72 triples, three per lane
+            int n = 0;
+            unsigned occ = 0;
+            if (lane < 24) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int t = lane * 3 + k;
+                    if (s_bin_cnt[3 * t] + s_bin_cnt[3 * t + 1] + s_bin_cnt[3 * t + 2] != 0) { occ |= 1u << k; ++n; }
+                }
+            }
+            int pre = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += o;
+            }
+            if (lane == 31) *s_nnz = pre;
+            pre -= n;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (occ >> k & 1u) s_binlist[pre++] = (unsigned short)(lane * 3 + k);
+        }
+        __syncthreads();
+        if (tid < 224) {
+            int base = 0;
+#pragma unroll
+            for (int wv = 0; wv < 6; ++wv)
+                if (wv < warp) base += s_wtot[wv].x;
+            s_bin_start[tid] = base + inc - c;
+        }
+    }
+    __syncthreads();
+#else
     // ---- counting sort of the slots by stencil-base cell (bin 216 = particles without P2G): exclusive scan of the 217 counters by
     // 7 warps (one bin per thread: warp scan, then the per-warp totals), and the list of the occupied bins in bin order
     {
@@ -783,9 +847,95 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         }
     }
     __syncthreads();
+#endif
     if (has_particle) s_sorted[s_bin_start[bin] + rank] = (unsigned short)tid;
     __syncthreads();
 
+#if SPK_P2G_TRIPLE
+    // ---- stage 2: 9-lane groups, one occupied bin triple at a time; lane = stencil column (sy, sz).  The group walks the three bins
+    // along x with a sliding window of 3 nodes x 6 channels in registers (payload reads are broadcasts): after bin j the node
+    // x0 + j is complete for this triple and is added to the tile, the window moves on by one node.  5 node flushes per triple
+    // instead of 9 (the shared float atomics of the flush are the most expensive instructions of the kernel).
+    {
+        const int lane = tid & 31;
+        const int grp = lane / 9, l9 = lane - grp * 9;
+        const int sy = l9 % 3, sz = l9 / 3;
+        const float fsy = (float)sy, fsz = (float)sz;
+        // QuadraticKernel::eval_all (kernel.rs:15-21) for ONE node: w_s(x) = A_s (x - B_s)^2 + C_s
+        const float Ay = sy == 1 ? -1.f : 0.5f, By = sy == 0 ? 1.5f : (sy == 1 ? 1.f : 0.5f), Cy = sy == 1 ? 0.75f : 0.f;
+        const float Az = sz == 1 ? -1.f : 0.5f, Bz = sz == 0 ? 1.5f : (sz == 1 ? 1.f : 0.5f), Cz = sz == 1 ? 0.75f : 0.f;
+        const int nnz = *s_nnz;
+        if (grp < 3) {
+            for (;;) { // a warp takes the next three occupied triples until the list is exhausted
+                // (the three triples of a pass are taken a third of the list apart: neighbouring rows would add into the same nodes in
+                // the same instruction, and same-address shared atomics serialise)
+                const int third = (nnz + 2) / 3;
+                int e = 0;
+                if (lane == 0) e = atomicAdd(s_next, 1);
+                e = __shfl_sync(0x07ffffffu, e, 0);
+                if (e >= third) break;
+                e += grp * third;
+                if (e >= nnz) continue;
+                const int t = s_binlist[e];
+                const int x0 = 3 * (t & 1), byc = (t >> 1) % 6, bzc = t / 12;
+                const int byz = cell_part(byc + sy, 1) + oct_part(byc + sy, 1) * 384 + cell_part(bzc + sz, 2) + oct_part(bzc + sz, 2) * 384;
+                const int zsw = (bzc + sz) & 2; // SPK_ACC_SWZ: bit 1 of the node's z inside its block flips bit 1 of its x
+                float acc[3][6];
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int ch = 0; ch < 6; ++ch) acc[k][ch] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { // j < 3: accumulate bin 3t + j, then flush node x0 + j; j = 3, 4: the two nodes left in the window
+                    if (j < 3) {
+                        const int start = s_bin_start[3 * t + j], cnt = s_bin_cnt[3 * t + j];
+#if SPK_P2G_PREFETCH
+                        int idx = cnt > 0 ? s_sorted[start] : 0;
+#endif
+                        for (int i = 0; i < cnt; ++i) {
+#if SPK_P2G_PREFETCH
+                            const float4* pay = s_tail + idx;
+#else
+                            const float4* pay = s_tail + s_sorted[start + i];
+#endif
+                            const float4 q0 = pay[0], q1 = pay[C_THREADS], q2 = pay[2 * C_THREADS], q3 = pay[3 * C_THREADS], q4 = pay[4 * C_THREADS];
+#if SPK_P2G_PREFETCH
+                            if (i + 1 < cnt) idx = s_sorted[start + i + 1];
+#endif
+                            const float dy = q3.w - By, dz = q4.w - Bz;
+                            const float wyz = fmaf(Ay * dy, dy, Cy) * fmaf(Az * dz, dz, Cz);
+                            // node momentum contribution at sx = 0: c + sy * hA[:,1] + sz * hA[:,2]
+                            float bx = q0.y + fsy * q2.x + fsz * q3.x, by = q0.z + fsy * q2.y + fsz * q3.y, bz = q0.w + fsy * q2.z + fsz * q3.z;
+                            const float wx[3] = {q4.x, q4.y, q4.z};
+#pragma unroll
+                            for (int sx = 0; sx < 3; ++sx) {
+                                float* a = acc[(j + sx) % 3];
+                                const float wt = wx[sx] * wyz;
+                                a[0] += wt * q0.x;
+                                a[1] += wt * bx; a[2] += wt * by; a[3] += wt * bz;
+                                a[4] += wt * q2.w; a[5] += wt * q1.w;
+                                bx += q1.x; by += q1.y; bz += q1.z;
+                            }
+                        }
+                    }
+                    float* a = acc[j % 3];
+                    if (a[0] != 0.f) { // a node that received nothing keeps an exact zero mass (all weights are positive)
+                        float* n = &s_acc[byz + (cell_part(x0 + j, 0) ^ zsw) + oct_part(x0 + j, 0) * 384];
+                        atomicAdd(n + 0 * 64, a[0]);
+                        atomicAdd(n + 1 * 64, a[1]);
+                        atomicAdd(n + 2 * 64, a[2]);
+                        atomicAdd(n + 3 * 64, a[3]);
+                        if (a[4] != 0.f) atomicAdd(n + 4 * 64, a[4]);
+                        if (a[5] != 0.f) atomicAdd(n + 5 * 64, a[5]);
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 6; ++ch) a[ch] = 0.f;
+                }
+            }
+        }
+    }
+
+#else
     // ---- stage 2: 9-lane groups, one occupied bin at a time; lane = stencil column (sy, sz), 3 nodes (sx = 0..2) x 6 channels in
     // registers over the bin's particles (payload reads are broadcasts), then one flush of the 18 sums into the tile
     {
@@ -808,9 +958,19 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                 const int start = s_bin_start[b], cnt = s_bin_cnt[b];
                 float aM[3] = {0.f, 0.f, 0.f}, aX[3] = {0.f, 0.f, 0.f}, aY[3] = {0.f, 0.f, 0.f}, aZ[3] = {0.f, 0.f, 0.f}, aPm[3] = {0.f, 0.f, 0.f},
                       aPp[3] = {0.f, 0.f, 0.f};
+#if SPK_P2G_PREFETCH
+                int idx = s_sorted[start];
+#endif
                 for (int i = 0; i < cnt; ++i) {
+#if SPK_P2G_PREFETCH
+                    const float4* pay = s_tail + idx;
+#else
                     const float4* pay = s_tail + s_sorted[start + i];
+#endif
                     const float4 q0 = pay[0], q1 = pay[C_THREADS], q2 = pay[2 * C_THREADS], q3 = pay[3 * C_THREADS], q4 = pay[4 * C_THREADS];
+#if SPK_P2G_PREFETCH
+                    if (i + 1 < cnt) idx = s_sorted[start + i + 1];
+#endif
                     const float dy = q3.w - By, dz = q4.w - Bz;
                     const float wyz = fmaf(Ay * dy, dy, Cy) * fmaf(Az * dz, dz, Cz);
                     // node momentum contribution at sx = 0: c + sy * hA[:,1] + sz * hA[:,2]
@@ -842,6 +1002,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         }
     }
 
+#endif
     // ---- stage 3: flush the accumulation tile into the next grid (transfer_shared_blocks_to_grid, g2p2g.rs:476-553)
     fence_proxy_async(); // make the generic-proxy smem writes visible to the async (TMA) proxy
     __syncthreads();
@@ -895,6 +1056,7 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     P.cold = c->cold;
     P.perm = c->perm;
     P.dispatch = c->dispatch;
+    P.dispatch_nbr = c->dispatch_nbr;
     P.models = c->models;
     P.nbr_self = next.nbr_self;
     P.nbr_prev = next.nbr_prev;

@@ -99,6 +99,7 @@ struct GridBuffers { // one of the two sparse-grid buffers (curr / next)
     uint32_t* blk_first;
     uint32_t* blk_count;
     uint32_t* blk_halo;
+    uint32_t* blk_dfirst; // first g2p2g dispatch entry of the block (it owns ceil(count / chunk) consecutive entries)
     int32_t* nbr_self; // [cap_blocks][8] ids of key + {0,1}^3 in THIS grid (octant bit0 = x, bit1 = y, bit2 = z)
     int32_t* nbr_prev; // [cap_blocks][8] ids of the same keys in the OTHER (previous) grid, -1 when absent
     // per node
@@ -174,6 +175,7 @@ struct spk_ctx {
     uint32_t* cell_cnt;   // [cap_hash of next][cells per block] particles per (hash slot, cell); after cell_scan_kernel: exclusive offsets inside the block
     uint32_t slot_cnt_cap;
     DispatchEntry* dispatch; uint32_t dispatch_cap;
+    int32_t* dispatch_nbr; // [dispatch_cap][2 * SPK_NBR]: nbr_self | nbr_prev of the entry's block, so that a g2p2g CTA finds its tile with ONE load
     uint32_t chunk;       // particles per g2p2g dispatch entry
     int g2p2g_mode;       // 0: per-particle shared atomics, 1: cell-binned register accumulation (default)
     bool g2p2g_configured; // the >48 KB dynamic shared memory opt-in was set on this context's device

@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned
                 g.blk_first[id] = run.cnt;
                 g.blk_count[id] = item[k].cnt;
                 g.blk_halo[id] = 0; // HaloState::EMPTY, gpu_grid.rs:353-368
+                g.blk_dfirst[id] = run.mult;
             } else {
                 counters->overflow = 1;
             }
@@ -203,13 +204,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned
 // neighbour-block tables: for block b, ids of key + {0,1}^3 in the next grid (always present) and in the previous grid
 // (launched for the grid's block CAPACITY before the host has read the block count back, so that the read-back overlaps this
 // kernel and scatter_perm_kernel; the true count comes from the device-side record)
-__global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, const DeviceCounters* __restrict__ counters) {
+__global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, const DeviceCounters* __restrict__ counters, int32_t* __restrict__ dispatch_nbr,
+                                    uint32_t dispatch_cap, uint32_t chunk) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t b = t >> SPK_NBR_SHIFT, o = t & (SPK_NBR - 1);
     if (b >= counters->nab || b >= next.cap_blocks) return;
     const unsigned long long key = spk_key_offset(next.blk_key[b], (int)o);
-    next.nbr_self[b * SPK_NBR + o] = spk_hash_get(next, key);
-    next.nbr_prev[b * SPK_NBR + o] = spk_hash_get(prev, key);
+    const int32_t ns = spk_hash_get(next, key), np = spk_hash_get(prev, key);
+    next.nbr_self[b * SPK_NBR + o] = ns;
+    next.nbr_prev[b * SPK_NBR + o] = np;
+    // the same ids once more per g2p2g dispatch entry of the block: a CTA then reads its entry and its tile's block ids in one round trip
+    const uint32_t d0 = next.blk_dfirst[b], nd = (next.blk_count[b] + chunk - 1) / chunk;
+    for (uint32_t d = d0; d < d0 + nd && d < dispatch_cap; ++d) {
+        dispatch_nbr[(size_t)d * (2 * SPK_NBR) + o] = ns;
+        dispatch_nbr[(size_t)d * (2 * SPK_NBR) + SPK_NBR + o] = np;
+    }
 }
 
 // finalize_particles_sort (sort.rs:201-221): sorted slot -> index in the current physical order; inside a block particles are ordered
@@ -259,7 +268,7 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c) {
     cudaStream_t s = c->stream;
     const uint32_t n = (uint32_t)c->n;
     {
-        build_tables_kernel<<<(g.cap_blocks * SPK_NBR + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters);
+        build_tables_kernel<<<(g.cap_blocks * SPK_NBR + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters, c->dispatch_nbr, c->dispatch_cap, c->chunk);
         c->launches += 1;
     }
     if (n) {
