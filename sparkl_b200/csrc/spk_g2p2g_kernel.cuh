@@ -476,6 +476,9 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
 #ifndef SPK_P2G_TRIPLE
 #define SPK_P2G_TRIPLE 0 /* 1: P2G work items are triples of x-neighbouring bins with a sliding window (5 node flushes per triple) */
 #endif
+#ifndef SPK_PSI_SHARE
+#define SPK_PSI_SHARE 1 /* 1: a CTA whose particles all have psi_mass == mass accumulates the mass channel once and flushes it twice */
+#endif
 #ifndef SPK_P2G_PREFETCH
 #define SPK_P2G_PREFETCH 0
 #endif
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     int* s_nnz = reinterpret_cast<int*>(smem + CS_MISC + 72);
     unsigned* s_dtmin = reinterpret_cast<unsigned*>(smem + CS_MISC + 76);
     int* s_next = reinterpret_cast<int*>(smem + CS_MISC + 80);
+    int* s_psi_generic = reinterpret_cast<int*>(smem + CS_MISC + 84); // 1: some particle of this CTA has psi_mass != mass (phase <= 0)
     uint32_t* s_halo = reinterpret_cast<uint32_t*>(smem + CS_HALO);
     int2* s_wtot = reinterpret_cast<int2*>(smem + CS_WTOT);
 
@@ -558,6 +562,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             mbar_init(s_bar, 1);
             *s_dtmin = SPK_DT_RAW_NONE;
             *s_next = 0;
+            *s_psi_generic = 0;
             uint32_t bytes = 0;
             for (int o = 0; o < 8; ++o) bytes += s_nbr_prev[o] >= 0 ? 1024u : 0u;
             fence_proxy_async();
@@ -582,7 +587,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         const float4 r0 = P.src.a0[si];
         x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; flags = __float_as_uint(r0.w);
     }
-    for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64; i += C_THREADS) s_acc[i] = 0.f;
+    for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64 / 4; i += C_THREADS) reinterpret_cast<float4*>(s_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < 224) s_bin_cnt[tid] = 0;
     __syncthreads();
     if (s_nbr_prev[tid >> 6] < 0) s_vel[tid] = make_float4(0.f, 0.f, 0.f, 0.f); // blocks absent from the previous grid read as zero
@@ -745,6 +750,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
 #pragma unroll
             for (int i = 0; i < 9; ++i) A.m[i] = p.mass * G.m[i] - ks * stress.m[i];
             const float psi_mass = (p.phase > 0.f && !(p.flags & SPK_F_FAILED)) ? p.mass : 0.f;
+            if (!SPK_PSI_SHARE || psi_mass != p.mass) *s_psi_generic = 1; // (benign race: every writer stores 1)
 #pragma unroll
             for (int a = 0; a < 3; ++a) f2[a] = spk_div_h(-ref2[a], h, inv_h);
             float wx[3];
@@ -865,6 +871,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         const float Ay = sy == 1 ? -1.f : 0.5f, By = sy == 0 ? 1.5f : (sy == 1 ? 1.f : 0.5f), Cy = sy == 1 ? 0.75f : 0.f;
         const float Az = sz == 1 ? -1.f : 0.5f, Bz = sz == 0 ? 1.5f : (sz == 1 ? 1.f : 0.5f), Cz = sz == 1 ? 0.75f : 0.f;
         const int nnz = *s_nnz;
+        const bool psi_generic = *s_psi_generic != 0; // see the bin-level variant
         if (grp < 3) {
             for (;;) { // a warp takes the next three occupied triples until the list is exhausted
                 // (the three triples of a pass are taken a third of the list apart: neighbouring rows would add into the same nodes in
@@ -913,7 +920,8 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                                 const float wt = wx[sx] * wyz;
                                 a[0] += wt * q0.x;
                                 a[1] += wt * bx; a[2] += wt * by; a[3] += wt * bz;
-                                a[4] += wt * q2.w; a[5] += wt * q1.w;
+                                a[4] += wt * q2.w;
+                                if (psi_generic) a[5] += wt * q1.w;
                                 bx += q1.x; by += q1.y; bz += q1.z;
                             }
                         }
@@ -926,7 +934,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                         atomicAdd(n + 2 * 64, a[2]);
                         atomicAdd(n + 3 * 64, a[3]);
                         if (a[4] != 0.f) atomicAdd(n + 4 * 64, a[4]);
-                        if (a[5] != 0.f) atomicAdd(n + 5 * 64, a[5]);
+                        if (psi_generic && a[5] != 0.f) atomicAdd(n + 5 * 64, a[5]);
                     }
 #pragma unroll
                     for (int ch = 0; ch < 6; ++ch) a[ch] = 0.f;
@@ -947,6 +955,9 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         const float Ay = sy == 1 ? -1.f : 0.5f, By = sy == 0 ? 1.5f : (sy == 1 ? 1.f : 0.5f), Cy = sy == 1 ? 0.75f : 0.f;
         const float Az = sz == 1 ? -1.f : 0.5f, Bz = sz == 0 ? 1.5f : (sz == 1 ? 1.f : 0.5f), Cz = sz == 1 ? 0.75f : 0.f;
         const int nnz = *s_nnz;
+        // psi_mass == mass for every particle of the CTA (no failed / phase <= 0 particle: the usual case): the psi_mass sums are then
+        // the mass sums, term by term — they are not accumulated a second time, the flush sends the mass channel to both places
+        const bool psi_generic = *s_psi_generic != 0;
         if (grp < 3) {
             for (;;) { // a warp takes the next three occupied bins (in bin order: mostly x-neighbours) until the list is exhausted
                 int e = 0;
@@ -981,7 +992,8 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                         const float wt = wx[sx] * wyz;
                         aM[sx] += wt * q0.x;
                         aX[sx] += wt * bx; aY[sx] += wt * by; aZ[sx] += wt * bz;
-                        aPm[sx] += wt * q1.w; aPp[sx] += wt * q2.w;
+                        aPp[sx] += wt * q2.w;
+                        if (psi_generic) aPm[sx] += wt * q1.w;
                         bx += q1.x; by += q1.y; bz += q1.z;
                     }
                 }
@@ -996,7 +1008,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                     atomicAdd(a + 2 * 64, aY[sx]);
                     atomicAdd(a + 3 * 64, aZ[sx]);
                     if (aPp[sx] != 0.f) atomicAdd(a + 4 * 64, aPp[sx]);
-                    if (aPm[sx] != 0.f) atomicAdd(a + 5 * 64, aPm[sx]);
+                    if (psi_generic && aPm[sx] != 0.f) atomicAdd(a + 5 * 64, aPm[sx]);
                 }
             }
         }
@@ -1007,9 +1019,21 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     fence_proxy_async(); // make the generic-proxy smem writes visible to the async (TMA) proxy
     __syncthreads();
     if (tid == 0) {
+        // one block chunk of the tile -> one block chunk of an accumulator array (this rank's grid or a peer's halo accumulator);
+        // when the psi_mass channel was not accumulated separately it is the mass channel, sent a second time
+        const bool psi_generic = *s_psi_generic != 0;
+        auto reduce_chunk = [&](float* dst, int o) {
+            const float* src = &s_acc[o * SPK_ACC_CHANNELS * 64];
+            if (psi_generic) {
+                tma_reduce_add_f32_1d(dst, src, SPK_ACC_CHANNELS * 64 * 4);
+            } else {
+                tma_reduce_add_f32_1d(dst, src, 5 * 64 * 4);
+                tma_reduce_add_f32_1d(dst + 5 * 64, src, 64 * 4);
+            }
+        };
         for (int o = 0; o < 8; ++o) {
             const int nid = s_nbr_self[o];
-            if (nid >= 0) tma_reduce_add_f32_1d(P.acc + (size_t)nid * (SPK_ACC_CHANNELS * 64), &s_acc[o * SPK_ACC_CHANNELS * 64], SPK_ACC_CHANNELS * 64 * 4);
+            if (nid >= 0) reduce_chunk(P.acc + (size_t)nid * (SPK_ACC_CHANNELS * 64), o);
         }
         bool pushed = false;
         if (P.world > 1) { // fused halo push (multi-GPU), see g2p2g_kernel
@@ -1019,7 +1043,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                 for (uint32_t r = 0; r < P.world; ++r) {
                     const int32_t pid = P.peer_ids[(size_t)nid * P.world + r];
                     if (pid >= 0) {
-                        tma_reduce_add_f32_1d(P.peer_hacc[r] + (size_t)pid * (SPK_ACC_CHANNELS * 64), &s_acc[o * SPK_ACC_CHANNELS * 64], SPK_ACC_CHANNELS * 64 * 4);
+                        reduce_chunk(P.peer_hacc[r] + (size_t)pid * (SPK_ACC_CHANNELS * 64), o);
                         pushed = true;
                     }
                 }

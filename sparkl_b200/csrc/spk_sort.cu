@@ -69,39 +69,40 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4
 // per hash slot (one warp each): exclusive scan of the slot's cell counters (in place: they become the cell offsets inside the
 // block), particle count of the block, and touch_particle_blocks (sort.rs:58-72) done per occupied block: activate key + {0,1}^3
 // (gpu_grid.rs:307-321).  Slots created here own no particles: their counters are all zero whether or not their warp sees the key.
+constexpr int CELL_SCAN_SLOTS = 16; // hash slots per warp (most are empty: the table is at most half full)
 __global__ void __launch_bounds__(256) cell_scan_kernel(unsigned long long* keys, uint32_t cap_hash, uint32_t* cell_cnt, uint32_t* __restrict__ slot_cnt,
                                                           DeviceCounters* counters) {
-    const uint32_t s = (blockIdx.x * 256u + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (s >= cap_hash) return;
-    const unsigned long long key = keys[s];
-    if (key == SPK_EMPTY_KEY) return;
-    uint32_t* cc = cell_cnt + (size_t)s * SPK_CELLS_PER_BLOCK;
+    const uint32_t s0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * CELL_SCAN_SLOTS;
+    for (uint32_t s = s0; s < s0 + CELL_SCAN_SLOTS && s < cap_hash; ++s) {
+        const unsigned long long key = keys[s];
+        if (key == SPK_EMPTY_KEY) continue;
+        uint32_t* cc = cell_cnt + (size_t)s * SPK_CELLS_PER_BLOCK;
 #if SPK_DIM == 3
-    const uint32_t c0 = cc[2 * lane], c1 = cc[2 * lane + 1]; // lane owns cells 2 lane, 2 lane + 1
-    const uint32_t mine = c0 + c1;
+        const uint32_t c0 = cc[2 * lane], c1 = cc[2 * lane + 1]; // lane owns cells 2 lane, 2 lane + 1
+        const uint32_t mine = c0 + c1;
 #else
-    const uint32_t c0 = lane < SPK_CELLS_PER_BLOCK ? cc[lane] : 0u, c1 = 0u;
-    const uint32_t mine = c0;
+        const uint32_t c0 = lane < SPK_CELLS_PER_BLOCK ? cc[lane] : 0u;
+        const uint32_t mine = c0;
 #endif
-    uint32_t inc = mine;
+        uint32_t inc = mine;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    if (total == 0) return; // a block activated as a neighbour only
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        if (total == 0) continue; // a block activated as a neighbour only
 #if SPK_DIM == 3
-    cc[2 * lane] = inc - mine;
-    cc[2 * lane + 1] = inc - mine + c0;
+        cc[2 * lane] = inc - mine;
+        cc[2 * lane + 1] = inc - mine + c0;
 #else
-    if (lane < SPK_CELLS_PER_BLOCK) cc[lane] = inc - mine;
-    (void)c1;
+        if (lane < SPK_CELLS_PER_BLOCK) cc[lane] = inc - mine;
 #endif
-    if (lane == 0) slot_cnt[s] = total;
-    if (lane >= 1 && lane < SPK_NBR)
-        if (spk_hash_insert(keys, cap_hash, spk_key_offset(key, lane)) == SPK_NO_BLOCK) counters->overflow = 1;
+        if (lane == 0) slot_cnt[s] = total;
+        if (lane >= 1 && lane < SPK_NBR)
+            if (spk_hash_insert(keys, cap_hash, spk_key_offset(key, lane)) == SPK_NO_BLOCK) counters->overflow = 1;
+    }
 }
 
 struct Triple { uint32_t occ, cnt, mult; };
@@ -251,7 +252,7 @@ cudaError_t spk_launch_sort_bin(spk_ctx* c) {
     if (n) {
         bin_particles_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->pb[c->cur].a0, n, c->cell_width, g.keys, g.cap_hash, c->cell_cnt,
                                                                                         c->slot_of, c->rank_of, c->d_counters);
-        cell_scan_kernel<<<(g.cap_hash + 7) / 8, 256, 0, s>>>(g.keys, g.cap_hash, c->cell_cnt, c->slot_cnt, c->d_counters);
+        cell_scan_kernel<<<(g.cap_hash + 8 * CELL_SCAN_SLOTS - 1) / (8 * CELL_SCAN_SLOTS), 256, 0, s>>>(g.keys, g.cap_hash, c->cell_cnt, c->slot_cnt, c->d_counters);
         c->launches += 2;
     }
     const uint32_t ntiles = (g.cap_hash + SCAN_TILE - 1) / SCAN_TILE;

@@ -27,7 +27,7 @@ F_FAILED, F_STATIC, F_KINEMATIC, F_MODEL_SHIFT = 1, 2, 4, 8
 
 class GridBuffers(C.Structure):  # sparkl_b200/csrc/spk_internal.cuh
     _fields_ = [("keys", vp), ("vals", vp), ("cap_hash", C.c_uint32), ("cap_blocks", C.c_uint32), ("blk_key", vp), ("blk_first", vp), ("blk_count", vp),
-                ("blk_halo", vp), ("nbr_self", vp), ("nbr_prev", vp), ("vel", vp), ("acc", vp), ("proj", vp), ("cacheN", vp), ("cacheD", vp),
+                ("blk_halo", vp), ("blk_dfirst", vp), ("nbr_self", vp), ("nbr_prev", vp), ("vel", vp), ("acc", vp), ("proj", vp), ("cacheN", vp), ("cacheD", vp),
                 ("external_hash", C.c_uint32), ("nab_host", C.c_uint32), ("has_velocity", C.c_uint32)]
 
 
