@@ -12,6 +12,9 @@
 //    g2p2g / reset never probe the hash map.
 #include "spk_device.cuh"
 
+#ifndef SPK_CELL_SCAN_SLOTS
+#define SPK_CELL_SCAN_SLOTS 16
+#endif
 namespace {
 
 constexpr int BIN_THREADS = 256;
@@ -69,13 +72,15 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4
 // per hash slot (one warp each): exclusive scan of the slot's cell counters (in place: they become the cell offsets inside the
 // block), particle count of the block, and touch_particle_blocks (sort.rs:58-72) done per occupied block: activate key + {0,1}^3
 // (gpu_grid.rs:307-321).  Slots created here own no particles: their counters are all zero whether or not their warp sees the key.
-constexpr int CELL_SCAN_SLOTS = 16; // hash slots per warp (most are empty: the table is at most half full)
+constexpr int CELL_SCAN_SLOTS = SPK_CELL_SCAN_SLOTS; // hash slots per warp (most are empty: the table is at most half full)
 __global__ void __launch_bounds__(256) cell_scan_kernel(unsigned long long* keys, uint32_t cap_hash, uint32_t* cell_cnt, uint32_t* __restrict__ slot_cnt,
                                                           DeviceCounters* counters) {
     const int lane = threadIdx.x & 31;
     const uint32_t s0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * CELL_SCAN_SLOTS;
     for (uint32_t s = s0; s < s0 + CELL_SCAN_SLOTS && s < cap_hash; ++s) {
-        const unsigned long long key = keys[s];
+        // lane 0's view of the slot decides for the warp: the lanes that activated neighbours in the previous iteration arrive here
+        // later than the others, and a key inserted in between (by any warp) must not split the warp at the `continue`s below
+        const unsigned long long key = __shfl_sync(0xffffffffu, keys[s], 0);
         if (key == SPK_EMPTY_KEY) continue;
         uint32_t* cc = cell_cnt + (size_t)s * SPK_CELLS_PER_BLOCK;
 #if SPK_DIM == 3
