@@ -149,21 +149,15 @@ def test_reference_run_to_run_spread_and_product_within_it(ref):
 # ---------------------------------------------------------------------------------------------- non-cuboid colliders vs the reference
 # The harness converts the host descriptions of HeightField / Polyline colliders into the reference's own device images (parry's
 # CudaHeightFieldPtr and CudaArrayPointer1 layouts, recovered from the ld.global offsets of `grid_update` in the shipped PTX), so the
-# two shapes can be run through the reference's kernels too.  These tests were written after this round's GPU budget was spent and
-# have not been run on a GPU yet; they are enabled with SPK_RUN_UNVERIFIED=1 and become regular tests once they have passed there.
-import os  # noqa: E402
-
-_unverified = pytest.mark.skipif(os.environ.get("SPK_RUN_UNVERIFIED") != "1",
-                                 reason="not yet run on a GPU (written after the round's GPU budget was spent); set SPK_RUN_UNVERIFIED=1")
+# two shapes run through the reference's kernels too (first run on a B200 in round 2: heightfield ground and polyline trough agree with
+# the reference's kernels within the lock-step tolerances; see DESIGN §6 for the one deviation kept as an expected failure below).
 
 
-@_unverified
 def test_sand_on_heightfield_ground_against_reference_kernels(ref):
     """the ground of examples3d/sand3.rs through the reference's own kernels: pins the HeightField restatement"""
     _lockstep(scenes.jitter(scenes.sand3(8, 4, 6, ground="heightfield", y0=0.9), 0.02, seed=13), ref, 8, 2e-5)
 
 
-@_unverified
 def test_sand_in_a_polyline_trough_against_reference_kernels(ref):
     sc = scenes.jitter(scenes.sand3(8, 4, 6, with_colliders=False, y0=0.5), 0.02, seed=6)
     trough = np.array([[-1.03, 0.31], [-1.03, 6.1], [-1.52, 6.1], [-1.52, -0.53], [3.51, -0.53], [3.51, 6.1], [3.07, 6.1], [3.07, 0.31]], np.float32)
@@ -171,7 +165,9 @@ def test_sand_in_a_polyline_trough_against_reference_kernels(ref):
     _lockstep(sc, ref, 8, 2e-5)
 
 
-@_unverified
+@pytest.mark.xfail(strict=False, reason="ROTATED heightfields: on the massless nodes 1.9-2.0 h away from a rotated field (12 of 1152 nodes of this scene) the "
+                                       "reference's kernels keep one component of the finite-difference SDF gradient where product and oracle get none "
+                                       "(collision_normal (0,-1,0) vs 0); tags, projections, velocities and particles agree (scripts/diag_colliders.py hf3)")
 def test_sand_penetration3_rotated_heightfields_against_reference_kernels(ref):
     """examples3d/sand_penetration3.rs: four heightfields, three of them rotated — through the reference's own kernels"""
     _lockstep(scenes.jitter(scenes.sand_penetration3(8, 6, 6, origin=(0.0, 13.7, 3.52)), 0.02, seed=12), ref, 8, 2e-5)
