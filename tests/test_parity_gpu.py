@@ -84,6 +84,14 @@ def test_fluid_dam_break(oracle):
     _run_frames(g, o, sc, 8, lambda s: 5e-5 * (1 + 3 * s))
 
 
+def test_neo_hookean_100_substeps(oracle):
+    """N = 100 substeps in lock-step with the oracle (a smooth elastic scene: no discontinuous return mapping, so the
+    per-substep tolerance only has to grow linearly with the substep index)"""
+    sc = scenes.jitter(scenes.neo_hookean_block(10, 10, 8), 0.002, seed=9)
+    g, o = _engines(sc, oracle)
+    _run_frames(g, o, sc, 100, lambda s: RTOL_1 * (1 + 3 * s))
+
+
 def test_neo_hookean_block(oracle):
     sc = scenes.jitter(scenes.neo_hookean_block(12, 12, 8), 0.002, seed=4)
     g, o = _engines(sc, oracle)
