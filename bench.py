@@ -32,6 +32,16 @@ UNIT = "particle-substeps/s"
 A_G2P2G_SAND = 264.0
 FULL = (200, 100, 100)       # per-GPU lattice (x2 stacked) = 4,000,000 particles
 CPU_SAMPLE = (100, 50, 50)   # bounded CPU sample = the reference's own sand3 size (examples3d/sand3.rs:51-71): 500,000 particles
+# BASELINE.json configs[1..4].  weak: every rank owns an x-slab of `dims`; strong: ONE scene of `dims`, cut into x-slabs of blocks
+# (SlabPartition) with device-side particle migration between the ranks every MIGRATE_EVERY substeps
+CONFIGS = {
+    "S4M": {"scene": "sand3", "dims": (200, 100, 100), "scaling": "weak", "what": "examples3d/sand3.rs scaled: 2 stacked lattices, Drucker-Prager sand over corotated block"},
+    "F1M": {"scene": "fluids3", "dims": (160, 80, 80), "scaling": "weak", "what": "examples3d/fluids3.rs scaled: Monaghan weakly-compressible dam break (1 GPU)"},
+    "C16M": {"scene": "cube_through_sand3", "dims": (400, 200, 200, 100), "scaling": "strong", "what": "examples3d/cube_through_sand3.rs scaled: kinematic block through Drucker-Prager sand"},
+    "N32M": {"scene": "neo_hookean_block", "dims": (400, 400, 200), "scaling": "weak", "what": "synthetic uniform-density Neo-Hookean block, 32 M particles per GPU (256 M on 8)"},
+}
+MIGRATE_EVERY = 10
+CPU_SAMPLES = {"S4M": (100, 50, 50), "F1M": (80, 40, 40), "C16M": (100, 50, 50, 25), "N32M": (100, 100, 50)}  # bounded CPU samples of the same scenes
 
 
 def _peaks():
@@ -121,22 +131,54 @@ class ClockSampler:
         return summarize_clock_samples(out.splitlines(), self.t0, self.t1, self.t_load0 if self.t_load0 is not None else self.t0, t_load1, self.REASONS)
 
 
-def build_scene(rank, world, dims):
+def build_scene(rank, world, dims, config="S4M"):
+    """this rank's particles of the configuration, and (strong scaling) the slab partition they were cut with"""
     from sparkl_b200 import scenes
-    ni, nj, nk = dims
-    ext = float(np.float32(0.2) / np.float32(4.0)) * 2.0
-    # slabs side by side along x; one floor + outer walls for the whole domain, identical on every rank
-    sc = scenes.sand3(ni, nj, nk, x_offset=rank * ni * ext, with_colliders=False)
-    sc.colliders = scenes.box_colliders((-4.0, 2.0, -4.0), (world * ni * ext + 4.0, 2.0 + 2 * nj * ext + 8.0, nk * ext + 4.0))
-    return sc
+    cfg = CONFIGS[config]
+    if cfg["scene"] == "sand3":
+        ni, nj, nk = dims
+        ext = float(np.float32(0.2) / np.float32(4.0)) * 2.0
+        # slabs side by side along x; one floor + outer walls for the whole domain, identical on every rank
+        sc = scenes.sand3(ni, nj, nk, x_offset=rank * ni * ext, with_colliders=False)
+        sc.colliders = scenes.box_colliders((-4.0, 2.0, -4.0), (world * ni * ext + 4.0, 2.0 + 2 * nj * ext + 8.0, nk * ext + 4.0))
+        return sc, None
+    if cfg["scene"] == "neo_hookean_block":
+        ni, nj, nk = dims
+        sc = scenes.neo_hookean_block(ni, nj, nk, x_offset=rank * ni * 0.1)
+        return sc, None
+    if cfg["scene"] == "fluids3":
+        if world != 1:
+            raise SystemExit("config F1M is a single-GPU configuration (BASELINE.json configs[1])")
+        return scenes.fluids3(*dims), None
+    # strong scaling: the same scene on every rank count, particles dealt to the ranks by the block column that holds them
+    from sparkl_b200.distributed import SlabPartition
+    sc = scenes.cube_through_sand3(*dims)
+    if world == 1:
+        return sc, None
+    x = sc.particles.position["point"][:, 0]
+    part = SlabPartition.uniform(float(x.min()), float(x.max()), world, sc.cell_width)
+    mine = np.nonzero(part.owner(x, sc.cell_width) == rank)[0]
+    sub = scenes.Scene(sc.name, sc.cell_width, sc.particles.take(mine), sc.models, sc.colliders, sc.gravity, sc.params)
+    sub.global_ids = mine.astype(np.uint32)
+    sub.total_particles = sc.num_particles
+    return sub, part
 
 
-def cpu_baseline(steps, warmup, dims=CPU_SAMPLE):
+def host_threads():
+    """the host cores this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arm must not inherit that)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_baseline(steps, warmup, config="S4M"):
     """the oracle port timed on the host cores (all threads) on a bounded sample of the workload"""
     from oracle import binding as ob
     from sparkl_b200 import abi
-    threads = ob.set_threads(0)
-    sc = build_scene(0, 1, dims)
+    threads = ob.set_threads(host_threads())
+    dims = CPU_SAMPLES[config]
+    sc, _ = build_scene(0, 1, dims, config)
     e = ob.OracleEngine(sc.cell_width)
     e.models_upload(sc.models); e.colliders_upload(sc.colliders); e.upload(sc.particles)
     p = abi.SolverParameters(stop_after_one_substep=1)
@@ -149,7 +191,7 @@ def cpu_baseline(steps, warmup, dims=CPU_SAMPLE):
         n += t.num_substeps
     dt = time.perf_counter() - t0
     return {"value": sc.num_particles * n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"sand3 lattice {dims[0]}x{dims[1]}x{dims[2]} x2 = {sc.num_particles} particles, {n} substeps, oracle/mpm_oracle.cpp (OpenMP)"}, dt / max(n, 1)
+            "sample": f"{config} scene at lattice {'x'.join(str(d) for d in dims)} = {sc.num_particles} particles, {n} substeps, oracle/mpm_oracle.cpp (OpenMP, {threads} threads)"}, dt / max(n, 1)
 
 
 def reference_gpu(sc, settle, steps):
@@ -181,10 +223,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, ms = cpu_baseline(args.steps, args.warmup)
+    base, ms = cpu_baseline(args.steps, args.warmup, args.config)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "sand3 (examples3d/sand3.rs) Drucker-Prager sand on corotated block, CPU arm on a bounded sample", "sample": base["sample"]},
+            "config": {"workload": f"{args.config}: {CONFIGS[args.config]['what']}, CPU arm on a bounded sample", "name": args.config, "sample": base["sample"]},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -195,6 +237,67 @@ def pinned_like(arr):
     out = t.numpy().view(arr.dtype).reshape(arr.shape)
     out[...] = arr
     return out, t
+
+
+def multi_gpu_check(rank, world, local, dist, args):
+    """driver-side evidence that the N-GPU path computes what one GPU computes: a small jittered sand scene cut into `world` x-slabs
+    runs two frames through the same halo path as the benchmark; rank 0 runs the whole scene alone; positions are compared"""
+    import torch
+    from sparkl_b200 import abi, scenes
+    from sparkl_b200.pipeline import context_from_scene
+    from sparkl_b200.distributed import DistributedMpmPipeline, NvlinkMpmPipeline
+    sc = scenes.jitter(scenes.sand3(8 * world, 8, 8), 0.02, seed=9)
+    x = sc.particles.position["point"][:, 0]
+    edges = np.linspace(x.min(), x.max() + 1e-3, world + 1)
+    mine = np.nonzero((x >= edges[rank]) & (x < edges[rank + 1]))[0]
+    part = scenes.Scene(sc.name, sc.cell_width, sc.particles.take(mine), sc.models, sc.colliders, sc.gravity, sc.params)
+    ctx = context_from_scene(part, device=local)
+    nsub = 0
+    if args.halo == "nvlink":
+        pipe = NvlinkMpmPipeline(ctx, dist)
+        for _ in range(2):
+            nsub += pipe.step(sc.params, sc.gravity)[1].num_substeps
+        halo = pipe.halo_blocks()
+        pipe.close()
+    else:
+        pipe = DistributedMpmPipeline(ctx, dist, torch.device("cuda", local))
+        for _ in range(2):
+            nsub += pipe.step(sc.params, sc.gravity)[1]
+        halo = None
+    pos = torch.zeros((len(sc.particles), 3), dtype=torch.float32, device="cuda")
+    pos[torch.from_numpy(mine).cuda()] = torch.from_numpy(ctx.read(abi.ATTR_POSITION)["point"].copy()).cuda()
+    dist.all_reduce(pos)
+    del ctx
+    if rank != 0:
+        return None
+    ref = context_from_scene(sc, device=local)
+    nref = sum(ref.step(sc.params, sc.gravity)[1].num_substeps for _ in range(2))
+    err = float(np.abs(pos.cpu().numpy() - ref.read(abi.ATTR_POSITION)["point"]).max() / sc.cell_width)
+    return {"scene": f"sand3 {8 * world}x8x8 x2 jittered, {len(sc.particles)} particles in {world} x-slabs, 2 frames", "substeps": nsub, "substeps_single_gpu": nref,
+            "max_dx_over_h_vs_single_gpu": err, "halo_blocks_rank0": halo, "ok": bool(err < 1e-4 and nsub == nref)}
+
+
+def h2d_ceiling(pins, dist, world, local):
+    """what the box gives when every rank copies its pinned frame input host -> device at the same time (the e2e frame cannot be faster)"""
+    import torch
+    dev = [torch.empty(p[1].numel(), dtype=torch.uint8, device="cuda") for p in pins]
+    nbytes = sum(p[1].numel() for p in pins)
+    best = 0.0
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for d, p in zip(dev, pins):
+            d.copy_(p[1], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        best = max(best, nbytes / dt / 1e9)
+    return {"per_rank_GBps": best, "aggregate_GBps": best * world, "what": "concurrent cudaMemcpyAsync of every rank's pinned frame input, best of 3 (slowest rank)"}
 
 
 def run_ours(args):
@@ -208,10 +311,25 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dims = tuple(args.dims) if args.dims else FULL
-    sc = build_scene(rank, world, dims)
-    npart = sc.num_particles
+    # each rank keeps to its own share of the host cores (and, with them, of the memory controllers next to its GPU's PCIe root):
+    # eight ranks staging 0.5 GB per frame from pinned memory otherwise contend for the same cores and NUMA node
+    nloc = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if nloc > 1 and len(cores) >= nloc:
+            per = len(cores) // nloc
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+    except (AttributeError, OSError):
+        pass
+    cfg = CONFIGS[args.config]
+    dims = tuple(args.dims) if args.dims else cfg["dims"]
+    check = multi_gpu_check(rank, world, local, dist, args) if world > 1 else None
+    sc, partition = build_scene(rank, world, dims, args.config)
+    npart = sc.num_particles                                           # this rank's particles
+    total = getattr(sc, "total_particles", None) or npart * world       # the job's particles
     ctx = context_from_scene(sc, device=local)
+    if partition is not None:
+        ctx.set_gids(sc.global_ids)
     stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=torch.device("cuda", local))
     params = abi.SolverParameters(stop_after_one_substep=1)
     pipe = None
@@ -222,8 +340,18 @@ def run_ours(args):
         else:                      # the portable torch.distributed (NCCL) protocol, kept for A/B
             from sparkl_b200.distributed import DistributedMpmPipeline
             pipe = DistributedMpmPipeline(ctx, dist, torch.device("cuda", local))
+    migrated = [0, 0]  # particles sent by this rank, migration calls
+    substeps_done = [0]
 
     def one_substep(timings=False):
+        if partition is not None and substeps_done[0] and substeps_done[0] % MIGRATE_EVERY == 0:
+            # strong-scaled scene with a moving body: particles whose block column left this rank's slab move to their new owner
+            # (spk_particles_migrate_out / _in + NCCL point-to-point over NVLink); a collective, every rank calls it at the same substep
+            from sparkl_b200.distributed import migrate_device
+            sent, _ = migrate_device(ctx, partition, dist)
+            migrated[0] += sent
+            migrated[1] += 1
+        substeps_done[0] += 1
         if pipe is None:  # without timings spk_step returns once the substep is enqueued: no host-side gap between steps
             return ctx.step(params, sc.gravity, timings=timings)[1]
         pipe.step(params, sc.gravity)
@@ -274,16 +402,17 @@ def run_ours(args):
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    value = npart * world * args.steps / (ms * 1e-3)
+    value = total * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers: upload (pinned H2D) -> one frame -> read back pos/vel/phase
     # into pinned host buffers; every rank does it for its own slab, the frame time is the max over ranks
     e2e = None
     if args.e2e_frames > 0:
-        host = sc.particles
+        host = ctx.read_all()  # the LOADED state reached by the timed substeps (not the rest lattice): every frame re-uploads it
         pins = [pinned_like(a) for a in (host.status, host.position, host.velocity, host.volume, host.phase, host.data)]
         pc = abi.ParticleComponents(0)
         pc.status, pc.position, pc.velocity, pc.volume, pc.phase, pc.data = [p[0] for p in pins]
+        npart = len(host)  # (strong scaling with migration: this rank's count may have changed since the upload)
         outs = {w: pinned_like(np.empty(npart, abi.ATTR_DTYPES[w])) for w in (abi.ATTR_POSITION, abi.ATTR_VELOCITY, abi.ATTR_PHASE)}
         frame = abi.SolverParameters()
         h2d = sum(p[0].nbytes for p in pins)
@@ -330,11 +459,12 @@ def run_ours(args):
             tt = torch.tensor([wall, wall_blocking], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             wall, wall_blocking = float(tt[0].item()), float(tt[1].item())
-        e2e = {"value": npart * world * per_frame * nfr / wall, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+        ceiling = h2d_ceiling(pins, dist, world, local)
+        e2e = {"value": total * per_frame * nfr / wall, "h2d_ceiling": ceiling, "h2d_frac_of_ceiling": (h2d * (total / npart) / (wall / nfr) / 1e9) / ceiling["aggregate_GBps"] if ceiling else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d * total / npart), "d2h_bytes_per_step": int(d2h * total / npart),
                "step": f"per rank and frame: spk_particles_stage_async + _commit_staged (pinned host, all 6 attributes) + spk_step(dt=1/60: {per_frame} substeps) + "
                        "spk_particles_read_async(pos, vel, phase) into pinned host buffers; transfers of neighbouring frames overlap the compute",
                "frames": nfr, "ms_per_frame": wall * 1e3 / nfr,
-               "blocking_calls": {"value": npart * world * subs / wall_blocking, "ms_per_frame": wall_blocking * 1e3 / args.e2e_frames,
+               "blocking_calls": {"value": total * subs / wall_blocking, "ms_per_frame": wall_blocking * 1e3 / args.e2e_frames,
                                   "what": "spk_particles_upload + spk_step + spk_particles_read x3, nothing overlapped"}}
 
     # ---- the reference testbed's frame loop (testbed_plugin.rs:490-588): step one frame, read pos / vel / phase back; no
@@ -378,26 +508,40 @@ def run_ours(args):
                 "stage_ms_per_substep": dict(zip(["sort", "reset_grid", "estimate_dt", "g2p2g", "grid_update"], (stage_ms / args.steps).round(4).tolist()))}
     base = None
     if world == 1 and not args.no_cpu_baseline:
-        base, _ = cpu_baseline(12, 1)  # ~10-20 s of host time
+        base, _ = cpu_baseline(12, 1, args.config)  # ~10-20 s of host time
     ref_gpu = None
     if world == 1 and not args.no_ref_gpu:
         ref_gpu = reference_gpu(sc, args.settle, min(args.steps, 10))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"sand3 (examples3d/sand3.rs scaled): 2 stacked lattices {dims[0]}x{dims[1]}x{dims[2]} per GPU = {npart} particles/GPU, h=0.2, "
-                                   "Drucker-Prager sand over corotated block, cuboid floor+walls", "particles_per_gpu": npart,
-                       "parallelism": f"x-slabs x{world}, halo accumulate over {'NVLink peer memory (device-initiated)' if args.halo == 'nvlink' else 'NCCL all-gather'}" if world > 1 else "single GPU", "l2": "inputs larger than L2 (particle state ~0.8 GB per GPU)"},
+            "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {cfg['what']}; lattice {'x'.join(str(d) for d in dims)}" + (" per GPU" if cfg["scaling"] == "weak" else " in total") +
+                                   f" = {total} particles on {world} GPU(s)", "name": args.config, "particles_total": int(total), "particles_rank0": int(sc.num_particles),
+                       "parallelism": (f"x-slabs x{world}, halo accumulate over {'NVLink peer memory (device-initiated)' if args.halo == 'nvlink' else 'NCCL all-gather'}"
+                                       + (f", device-side particle migration every {MIGRATE_EVERY} substeps ({migrated[1]} calls, {migrated[0]} particles sent by rank 0)" if partition is not None else ""))
+                       if world > 1 else "single GPU", "l2": "inputs larger than L2 (particle state >= 0.25 GB per GPU)"},
             "clocks": clocks, "gpu_launches": int(launches) if launches else None, "e2e": e2e, "roofline": roof, "cpu_baseline": base,
-            "reference_gpu": ref_gpu, "frame_loop": frame_loop}
+            "reference_gpu": ref_gpu, "frame_loop": frame_loop, "multi_gpu_check": check}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _lib_sha16():
+    import hashlib
+    from sparkl_b200 import _lib
+    try:
+        return hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:16]
+    except Exception:
+        return None
+
+
 def _ncu_traffic():
-    """dram bytes per g2p2g launch from the committed ncu summary of the same command (profiles/), if present"""
+    """dram bytes per g2p2g launch from the committed `ncu --set full` summary (profiles/g2p2g_ncu_summary.json) — only when that
+    capture was taken with THIS build of the library (the summary records the library's sha256)"""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "g2p2g_ncu_summary.json")))
+        if d.get("lib_sha16") and d["lib_sha16"] != _lib_sha16():
+            return None
         return float(d["dram_bytes_per_launch"])
     except Exception:
         return None
@@ -409,7 +553,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dims", type=int, nargs=3, default=None, help="per-GPU lattice (default 200 100 100)")
+    ap.add_argument("--config", default="S4M", choices=sorted(CONFIGS), help="BASELINE.json configuration: S4M (default, the headline), F1M, C16M (strong scaling, migration on), N32M (256 M on 8 GPUs)")
+    ap.add_argument("--dims", type=int, nargs="+", default=None, help="lattice of the configuration (default: its BASELINE size)")
     ap.add_argument("--e2e-frames", type=int, default=3)
     ap.add_argument("--settle", type=int, default=120, help="untimed substeps run before the warm-up to load the material")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own GPU kernels (oracle/_ref)")

@@ -19,6 +19,14 @@ KEY = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"]
 
 
+def _lib_sha16():
+    import hashlib, os
+    try:
+        return hashlib.sha256(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sparkl_b200", "libsparkl_b200.so"), "rb").read()).hexdigest()[:16]
+    except Exception:
+        return None
+
+
 def launches(src, dst):
     rows = list(csv.reader(open(src)))
     for i, r in enumerate(rows):
@@ -94,7 +102,9 @@ def kernel(src, dst, json_out=None):
             v = float(v)
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
         json.dump({"kernel": m.get("Kernel Name", ("?",))[0], "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
-                   "duration_us": float(m["gpu__time_duration.sum"][0]), "source": dst + ".md"}, open(json_out, "w"), indent=1)
+                   "duration_us": float(m["gpu__time_duration.sum"][0]), "source": dst + ".md", "lib_sha16": _lib_sha16(),
+                   "note": "lib_sha16 = sha256 of sparkl_b200/libsparkl_b200.so at capture time; bench.py reports `traffic` only for the same build"},
+                  open(json_out, "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -33,3 +33,13 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_reference_arm_ignores_the_single_thread_default_of_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must still use the host cores it may run on (round-1 finding)"""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       cwd=ROOT, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))

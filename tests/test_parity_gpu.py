@@ -259,8 +259,7 @@ def test_async_upload_matches_blocking_upload():
         a.step(sc.params, sc.gravity)
         b.step(sc.params, sc.gravity, timings=False)
     pa, pb = a.read_all(), b.read_all()
-    for name in ("position", "velocity", "volume", "status", "phase", "data"):
-        assert np.array_equal(getattr(pa, name), getattr(pb, name)) or name in ("position", "velocity", "volume", "phase", "data")
+    assert np.array_equal(pa.status, pb.status)  # discrete state: exact; the floating-point fields differ by the order of the P2G atomics
     util.assert_particles_close(pb, pa, sc.cell_width, util.scene_tol(sc, 1e-4), "async vs blocking upload")
     # an out-of-range model index is reported by the next step
     pc.status["model_index"][0] = 1 << 25
