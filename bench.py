@@ -340,7 +340,7 @@ def run_ours(args):
         else:                      # the portable torch.distributed (NCCL) protocol, kept for A/B
             from sparkl_b200.distributed import DistributedMpmPipeline
             pipe = DistributedMpmPipeline(ctx, dist, torch.device("cuda", local))
-    migrated = [0, 0]  # particles sent by this rank, migration calls
+    migrated = [0, 0, 0.0]  # particles sent by this rank, migration calls, host seconds spent in them (they synchronise)
     substeps_done = [0]
 
     def one_substep(timings=False):
@@ -348,9 +348,11 @@ def run_ours(args):
             # strong-scaled scene with a moving body: particles whose block column left this rank's slab move to their new owner
             # (spk_particles_migrate_out / _in + NCCL point-to-point over NVLink); a collective, every rank calls it at the same substep
             from sparkl_b200.distributed import migrate_device
-            sent, _ = migrate_device(ctx, partition, dist)
+            t_m = time.perf_counter()
+            sent, _ = migrate_device(ctx, partition, dist, hysteresis=1)
             migrated[0] += sent
             migrated[1] += 1
+            migrated[2] += time.perf_counter() - t_m
         substeps_done[0] += 1
         if pipe is None:  # without timings spk_step returns once the substep is enqueued: no host-side gap between steps
             return ctx.step(params, sc.gravity, timings=timings)[1]
@@ -517,7 +519,7 @@ def run_ours(args):
             "config": {"workload": f"{args.config}: {cfg['what']}; lattice {'x'.join(str(d) for d in dims)}" + (" per GPU" if cfg["scaling"] == "weak" else " in total") +
                                    f" = {total} particles on {world} GPU(s)", "name": args.config, "particles_total": int(total), "particles_rank0": int(sc.num_particles),
                        "parallelism": (f"x-slabs x{world}, halo accumulate over {'NVLink peer memory (device-initiated)' if args.halo == 'nvlink' else 'NCCL all-gather'}"
-                                       + (f", device-side particle migration every {MIGRATE_EVERY} substeps ({migrated[1]} calls, {migrated[0]} particles sent by rank 0)" if partition is not None else ""))
+                                       + (f", device-side particle migration every {MIGRATE_EVERY} substeps ({migrated[1]} calls, {migrated[0]} particles sent by rank 0, {1e3 * migrated[2] / max(migrated[1], 1):.2f} ms per call, one block column of hysteresis)" if partition is not None else ""))
                        if world > 1 else "single GPU", "l2": "inputs larger than L2 (particle state >= 0.25 GB per GPU)"},
             "clocks": clocks, "gpu_launches": int(launches) if launches else None, "e2e": e2e, "roofline": roof, "cpu_baseline": base,
             "reference_gpu": ref_gpu, "frame_loop": frame_loop, "multi_gpu_check": check}

@@ -41,6 +41,8 @@ extern "C" {
 #define SPK_EUNSUPPORTED (-2) /* feature outside the hot-path scope (e.g. heightfield colliders) */
 #define SPK_ESTATE (-3)       /* call sequence error (e.g. stage call before sort) */
 #define SPK_EOVERFLOW (-4)    /* u32 particle/block limits exceeded (cuda_sparse_grid.rs:197,332) */
+#define SPK_EPEER (-5)        /* multi-GPU: a peer rank did not reach a device-side barrier in time (SPK_DIST_TIMEOUT_MS, default 3000); the halo sums
+                                 and the time step of that substep are incomplete — the run must be abandoned.  Sticky until spk_dist_detach */
 
 /* ---------------------------------------------------------------- particle PODs
  * src_core/dynamics/particle.rs:14-219 (one device array per struct in the reference, cuda_particle_set.rs:12-19) */
@@ -398,7 +400,10 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
  * `g2p2g_generic::<MyUpdater>` — registers its launch functions here; spk_step / spk_stage_* then call them instead of the
  * default ones.  A NULL member keeps the default for that launch.  The callbacks run on the caller's thread, must enqueue on the
  * context's stream (spk_ctx_stream) and return 0 or a cudaError_t / SPK_E* code, which the calling entry point returns.
- * `spk_default_launch_*` are the `DefaultCudaParticleKernelsLauncher`: a custom launcher may fall back to them. */
+ * `spk_default_launch_*` are the `DefaultCudaParticleKernelsLauncher`: a custom launcher may fall back to them.
+ * Fused CFL estimate: the library's G2P2G kernels (the default one and every `g2p2g_kernel<.., Updater>` instantiation) also reduce the
+ * NEXT substep's time-step candidate, so with the DEFAULT estimate launcher the stand-alone estimate kernel only runs after a
+ * particle / model edit.  A REGISTERED launch_estimate_particle_timestep_length is called every substep, like step_generic does. */
 typedef struct SpkParticleKernelsLauncher {
     void* user;                                                                   /* passed back to every callback */
     int (*timestep_started)(void* user);                                          /* once per spk_step, before the first substep */

@@ -43,7 +43,7 @@ ATTR_DTYPES = {ATTR_POSITION: POSITION, ATTR_VELOCITY: VELOCITY, ATTR_STATUS: ST
 PROJ_NOT_COMPUTED, PROJ_INSIDE, PROJ_OUTSIDE, PROJ_TOO_FAR = range(4)
 
 # error codes
-OK, EINVAL, EUNSUPPORTED, ESTATE, EOVERFLOW = 0, -1, -2, -3, -4
+OK, EINVAL, EUNSUPPORTED, ESTATE, EOVERFLOW, EPEER = 0, -1, -2, -3, -4, -5
 
 
 class SparklError(RuntimeError):

@@ -266,7 +266,7 @@ int publish_counters(spk_ctx* c) {
 int wait_counters(spk_ctx* c) {
     CK(cudaEventSynchronize(c->ev_counters));
     c->counters_fresh = true;
-    return SPK_OK;
+    return c->h_counters->pad[1] ? SPK_EPEER : SPK_OK; // a device-side barrier of the multi-GPU path gave up on a peer (sticky)
 }
 int read_counters(spk_ctx* c) {
     static_assert(sizeof(DeviceCounters) % 4 == 0 && sizeof(DeviceCounters) <= 128, "one warp copies the record");
@@ -274,7 +274,7 @@ int read_counters(spk_ctx* c) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     c->counters_fresh = true;
-    return SPK_OK;
+    return c->h_counters->pad[1] ? SPK_EPEER : SPK_OK;
 }
 
 const float DT_FACTOR = 1000000000000.0f; // GpuTimestepLength::FACTOR, gpu_timestep.rs:18
@@ -342,14 +342,15 @@ cudaError_t spk_launch_unpack(spk_ctx* c, int which, void* d_out, size_t n) {
 // the bookkeeping of spk_particles_upload without the copy: capacity (reallocating DISCARDS the particle streams), counts, grid sizing
 int spk_particles_resize(spk_ctx* c, size_t n, bool fresh) {
     if (n >= 0xffffffffull) return SPK_EOVERFLOW;
+    // every capacity is checked BEFORE the context changes: on SPK_EOVERFLOW the particle set is exactly what it was
+    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (SPK_CELLS_PER_BLOCK * SPK_PARTICLES_PER_CELL * 50)) * 4u, 2048u);
+    if (c->dist_arena && want > c->dist_cap_hash) return SPK_EOVERFLOW; // the arena shared with the peers cannot grow
     if (n > c->cap) { CK(cudaStreamSynchronize(c->stream)); CK(alloc_particles(c, n + n / 8 + 1024)); fresh = true; }
     c->n = n;
     if (fresh) c->cur = 0;
     c->sorted_valid = false;
     c->dt_cache_valid = false;
-    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (SPK_CELLS_PER_BLOCK * SPK_PARTICLES_PER_CELL * 50)) * 4u, 2048u);
     GridBuffers& next = c->grid[1 - c->gcur];
-    if (c->dist_arena && want > c->dist_cap_hash) return SPK_EOVERFLOW; // the arena shared with the peers cannot grow
     if (next.cap_hash < want) { CK(alloc_grid(c, next, want)); CK(ensure_slot_scratch(c, want)); }
     CK(ensure_dispatch(c));
     return SPK_OK;
@@ -388,6 +389,7 @@ const char* spk_error_string(int code) {
     case SPK_EUNSUPPORTED: return "unsupported (outside the hot-path scope)";
     case SPK_ESTATE: return "invalid call sequence";
     case SPK_EOVERFLOW: return "u32 particle/block limit exceeded";
+    case SPK_EPEER: return "a peer rank did not reach a device-side barrier in time (multi-GPU)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }
@@ -476,7 +478,12 @@ int spk_ctx_destroy(spk_ctx* c) {
 
 int spk_ctx_cell_width(const spk_ctx* c, float* out) { if (!c || !out) return SPK_EINVAL; *out = c->cell_width; return SPK_OK; }
 int spk_ctx_stream(spk_ctx* c, void** out) { if (!c || !out) return SPK_EINVAL; *out = (void*)c->stream; return SPK_OK; }
-int spk_ctx_synchronize(spk_ctx* c) { if (!c) return SPK_EINVAL; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return SPK_OK; }
+int spk_ctx_synchronize(spk_ctx* c) {
+    if (!c) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return c->h_counters->pad[1] ? SPK_EPEER : SPK_OK;
+}
 
 int spk_particles_upload(spk_ctx* c, const SpkParticleStatus* status, const SpkParticlePosition* pos, const SpkParticleVelocity* vel,
                          const SpkParticleVolume* volume, const SpkParticlePhase* phase, const SpkParticleData* data, size_t n) {
@@ -540,15 +547,15 @@ int spk_particles_commit_staged(spk_ctx* c) {
     if (!c->up_staged) return SPK_ESTATE;
     CK(cudaSetDevice(c->device));
     const size_t n = c->up_staged_n;
+    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (SPK_CELLS_PER_BLOCK * SPK_PARTICLES_PER_CELL * 50)) * 4u, 2048u);
+    if (c->dist_arena && want > c->dist_cap_hash) return SPK_EOVERFLOW; // checked before anything changes: the staged upload stays staged
     if (n > c->cap) { CK(cudaStreamSynchronize(c->stream)); CK(alloc_particles(c, n + n / 8 + 1024)); }
     if (c->gid) { CK(cudaStreamSynchronize(c->stream)); dev_free(c->gid); }
     c->n = n;
     c->cur = 0;
     c->sorted_valid = false;
     c->dt_cache_valid = false;
-    const uint32_t want = std::max<uint32_t>(next_pow2((uint64_t)n * 100 / (SPK_CELLS_PER_BLOCK * SPK_PARTICLES_PER_CELL * 50)) * 4u, 2048u);
     GridBuffers& next = c->grid[1 - c->gcur];
-    if (c->dist_arena && want > c->dist_cap_hash) return SPK_EOVERFLOW;
     if (next.cap_hash < want) { CK(alloc_grid(c, next, want)); CK(ensure_slot_scratch(c, want)); }
     CK(ensure_dispatch(c));
     c->up_staged = false;
@@ -891,6 +898,7 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
     if (c->n && !c->models) return SPK_ESTATE;
     for (int attempt = 0; attempt < 16; ++attempt) {
         GridBuffers& g = c->grid[1 - c->gcur];
+        CK(ensure_staging(c, ((size_t)g.cap_hash / 2048 + 1) * 12)); // the scan partials of spk_launch_sort_bin: 12 bytes per 2048 hash slots
         CK(spk_launch_sort_bin(c));
         // The counter record (block / dispatch counts, overflow flag, dt candidate) is published to mapped host memory, then
         // the two kernels that finish the sort are enqueued for the grid's CAPACITY (they read the true block count on the
@@ -940,7 +948,9 @@ int spk_stage_reset_grid(spk_ctx* c) {
 int spk_stage_estimate_dt(spk_ctx* c, float min_dt, float max_dt, float* dt_out) {
     if (!c) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));
-    if (c->dt_cache_valid) {
+    // A registered estimate launcher is called EVERY substep, like the reference's step_generic does (cuda_mpm_pipeline.rs:381-392); the
+    // candidate fused into g2p2g replaces only the DEFAULT estimate kernel (its result is bit-identical, see below)
+    if (c->dt_cache_valid && !c->launcher.launch_estimate_particle_timestep_length) {
         // K15 was fused into the previous g2p2g (the particle state has not changed since): the reduced un-clamped
         // candidate arrived with the counters record; apply timestep.rs:87-112 to it.  min / clamp / fixed-point
         // conversion are monotone, so min_p f(c_p) == f(min_p c_p), bit for bit.
@@ -1165,6 +1175,7 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
     if ((rc = spk_frame_begin(c, params))) return rc;
     const bool dist = spk_dist_active(c);
     if (dist && c->n == 0) return SPK_ESTATE; // every rank takes part in the device-side barriers
+    if (dist && c->h_counters->pad[1]) return SPK_EPEER; // a peer was given up on during an earlier call: the ranks have diverged
     if (c->launcher.timestep_started && (rc = c->launcher.timestep_started(c->launcher.user))) return rc; // :299-302
     if (params->dt == 0.0f || c->n == 0) { // nothing to simulate (:305-309)
         if (simulated_time_out) *simulated_time_out = params->dt;
@@ -1224,6 +1235,9 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
         timings->kernel_launches = c->launches - launches0;
     }
     if (simulated_time_out) *simulated_time_out = params->dt - remaining;
+    // (the barriers of the frame's last substep run after its counter record was published: a time-out there is written straight into
+    // the mapped host record by the barrier kernel and is seen by the next call that looks — the next spk_step, spk_ctx_synchronize)
+    if (dist && c->h_counters->pad[1]) return SPK_EPEER;
     return SPK_OK;
 }
 

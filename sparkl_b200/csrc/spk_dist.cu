@@ -88,7 +88,7 @@ __device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) {
 //   mode 0: plain barrier, publishes `gnext` (which grid buffer is this rank's next grid)
 //   mode 1: additionally min-reduces counters->dt_raw_bits over the ranks (fused CFL reduction of g2p2g)
 //   mode 2: additionally min-reduces counters->dt_acc over the ranks (stand-alone estimate_dt kernel)
-__global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext, int mode, DeviceCounters* counters) {
+__global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext, int mode, DeviceCounters* counters, long long timeout_cycles, DeviceCounters* host_record) {
     const uint32_t p = threadIdx.x;
     const uint32_t slot = epoch & 1u;
     unsigned long long mine = 0;
@@ -105,7 +105,14 @@ __global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext,
             st_sys_u32(&remote->flag[d.rank], epoch);
             const long long t0 = clock64();
             while ((int)(ld_sys_u32(&d.mailbox->flag[p]) - epoch) < 0) {
-                if (clock64() - t0 > 6000000000ll) { counters->overflow = 0x100u + p; break; } // ~3 s: a peer died; never hang the GPU
+                // a peer that died must not hang the GPU: give up, and leave a STICKY mark (pad[1] is outside the words the sort clears
+                // every substep) that the host turns into SPK_EPEER at its next look at the counters and at the end of spk_step
+                if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) {
+                    counters->pad[1] = 0x100u + p;
+                    host_record->pad[1] = 0x100u + p; // mapped pinned memory: the host sees it without another read-back
+                    __threadfence_system();
+                    break;
+                }
                 __nanosleep(64);
             }
             __threadfence_system();
@@ -200,7 +207,7 @@ bool spk_dist_grid_storage(spk_ctx* c, int g, uint32_t cap_hash, unsigned long l
 cudaError_t spk_dist_launch_barrier(spk_ctx* c, int mode) {
     DistState& d = c->dist;
     d.epoch += 1;
-    dist_barrier_kernel<<<1, SPK_MAX_RANKS, 0, c->stream>>>(d, d.epoch, (uint32_t)(1 - c->gcur), mode, c->d_counters);
+    dist_barrier_kernel<<<1, SPK_MAX_RANKS, 0, c->stream>>>(d, d.epoch, (uint32_t)(1 - c->gcur), mode, c->d_counters, c->dist_timeout_cycles, c->h_counters_dev);
     c->launches += 1;
     c->counters_fresh = false;
     return cudaGetLastError();
@@ -256,6 +263,14 @@ int spk_dist_export(spk_ctx* c, SpkDistDescriptor* out) {
     CK(cudaMemset(c->dist_push_ptrs, 0, SPK_MAX_RANKS * sizeof(float*)));
     c->dist_fused_push = 1;
     if (const char* m = getenv("SPK_DIST_PUSH")) c->dist_fused_push = std::strcmp(m, "kernel") != 0; // A/B: separate push kernel
+    {   // barrier timeout: SPK_DIST_TIMEOUT_MS (default 3000, 0 = unbounded), converted with the device's SM clock
+        long long ms = 3000;
+        if (const char* t = getenv("SPK_DIST_TIMEOUT_MS")) ms = atoll(t);
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+        c->dist_timeout_cycles = ms <= 0 ? 0 : ms * (long long)(khz > 0 ? khz : 2000000);
+    }
+    CK(cudaMemsetAsync(&c->d_counters->pad[1], 0, 4, c->stream));
     DescriptorWire w;
     std::memset(&w, 0, sizeof(w));
     CK(cudaIpcGetMemHandle(&w.handle, arena));
@@ -303,6 +318,8 @@ int spk_dist_detach(spk_ctx* c) {
     for (uint32_t p = 0; p < SPK_MAX_RANKS; ++p)
         if (c->dist_mapped[p]) { cudaIpcCloseMemHandle(c->dist_mapped[p]); c->dist_mapped[p] = nullptr; }
     std::memset(&c->dist, 0, sizeof(c->dist));
+    cudaMemset(&c->d_counters->pad[1], 0, 4); // the sticky peer-timeout mark dies with the attachment
+    c->h_counters->pad[1] = 0;
     return SPK_OK;
 }
 

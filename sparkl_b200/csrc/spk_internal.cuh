@@ -123,7 +123,8 @@ struct DeviceCounters { // one 64-byte record read back once per substep (pinned
     uint32_t halo_cursor;
     uint32_t dt_raw_bits;    // min over non-failed particles of the un-clamped dt candidate (float bits), written by g2p2g's
                              // epilogue for the NEXT substep; >= SPK_DT_RAW_NONE when no particle contributed
-    uint32_t pad[5];
+    uint32_t pad[5];         // pad[0]: invalid model index seen by the asynchronous upload; pad[1]: STICKY 0x100 + peer once a device-side barrier of
+                             // the multi-GPU path timed out on that peer (never cleared by the per-substep memsets; spk_dist.cu)
 };
 #define SPK_DT_RAW_NONE 0x7f7f7f7fu /* memset pattern; valid candidates are capped at 1e30f */
 
@@ -199,6 +200,7 @@ struct spk_ctx {
     int32_t* dist_peer_ids;              // [cap_blocks][world]: the peer's id of each of this rank's active blocks, -1 if absent
     void* dist_mapped[SPK_MAX_RANKS];    // cudaIpcOpenMemHandle results (to close)
     float** dist_push_ptrs;              // [SPK_MAX_RANKS] device array: peer-mapped hacc of every rank's next grid (written by detect)
+    long long dist_timeout_cycles;       // device-side barrier: give up on a peer after this many SM cycles (0 = wait for ever)
     int dist_fused_push;                 // 1: g2p2g's flush pushes shared blocks itself (default); 0: separate push kernel (A/B)
     // custom particle kernels (spk_set_particle_kernels_launcher); all NULL = DefaultCudaParticleKernelsLauncher
     SpkParticleKernelsLauncher launcher;

@@ -261,7 +261,8 @@ cudaError_t spk_launch_sort_bin(spk_ctx* c) {
         c->launches += 2;
     }
     const uint32_t ntiles = (g.cap_hash + SCAN_TILE - 1) / SCAN_TILE;
-    Triple* partials = (Triple*)c->staging; // staging is at least 64 KB
+    if ((size_t)ntiles * sizeof(Triple) > c->staging_bytes) return cudaErrorInvalidValue; // sized by spk_stage_sort (ensure_staging) before the launch
+    Triple* partials = (Triple*)c->staging;
     slot_totals_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials);
     assign_ids_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials, g.vals, g, c->dispatch, c->dispatch_cap, c->d_counters);
     c->launches += 2;

@@ -285,14 +285,17 @@ def migrate(engine, gids: np.ndarray, partition: SlabPartition, dist=None, devic
     return new_gids, n_sent, n_recv
 
 
-def migrate_device(ctx, partition: SlabPartition, dist=None, device=None, wire=None):
+def migrate_device(ctx, partition: SlabPartition, dist=None, device=None, wire=None, hysteresis: int = 0):
     """Collective.  The device-side counterpart of `migrate` for a SingleGpuMpmContext (dim3): the leaving particles are packed
     into 128-byte rows by the GPU (`spk_particles_migrate_out`: stable partition by destination slab), the rows travel between the
     ranks' device buffers (`torch.distributed` send / recv: NCCL over NVLink), and the arrivals are appended on the device
     (`spk_particles_migrate_in`).  Only the per-destination counts cross PCIe; global ids live in the context (`ctx.set_gids`,
     `ctx.read_gids`).  When nothing moves anywhere no particle state is touched and the sort state stays valid.  `wire` (default:
     `device`) is where the rows sit during the exchange: the CPU when the process group is gloo (tests on one GPU), which cannot
-    send CUDA tensors.  Returns (number sent, number received)."""
+    send CUDA tensors.  `hysteresis` (blocks): a rank keeps the particles that are less than that many block columns outside its slab —
+    ownership may lag behind the position without any effect on the result (only the halo grows by as many columns), and particles
+    that oscillate across a slab boundary (a lattice on cell-boundary ties does, every substep) are not sent back and forth.
+    Returns (number sent, number received)."""
     import torch
     import torch.distributed as tdist
     dist = dist or tdist
@@ -300,7 +303,13 @@ def migrate_device(ctx, partition: SlabPartition, dist=None, device=None, wire=N
     world, rank = dist.get_world_size(), dist.get_rank()
     assert partition.world == world
     row = PARTICLE_RECORD.itemsize
-    counts = ctx.migrate_out(partition.bounds, rank)  # count only
+    bounds = np.array(partition.bounds, np.int64)
+    if hysteresis:  # this rank's view: its own slab widened; the bounds between the OTHER ranks stay where they are
+        if rank > 0:
+            bounds[rank] = max(bounds[rank] - hysteresis, bounds[rank - 1] + 1)
+        if rank < world - 1:
+            bounds[rank + 1] = min(bounds[rank + 1] + hysteresis, bounds[rank + 2] - 1)
+    counts = ctx.migrate_out(bounds, rank)  # count only
     mine = torch.tensor(counts.astype(np.int64), dtype=torch.int64, device=device)
     table = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(table, mine)
@@ -310,7 +319,7 @@ def migrate_device(ctx, partition: SlabPartition, dist=None, device=None, wire=N
         return 0, 0
     send = torch.empty(max(n_sent, 1) * row, dtype=torch.uint8, device=device)
     if n_sent:
-        again = ctx.migrate_out(partition.bounds, rank, send.data_ptr(), n_sent)
+        again = ctx.migrate_out(bounds, rank, send.data_ptr(), n_sent)
         assert np.array_equal(again, counts)
     offs = np.concatenate([[0], np.cumsum(table[rank])]) * row  # rows are grouped by destination rank
     recv = torch.empty(max(n_recv, 1) * row, dtype=torch.uint8, device=device)

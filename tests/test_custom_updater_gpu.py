@@ -75,7 +75,7 @@ def test_custom_updater_reproduces_the_builtin_model(example):
     assert np.abs(b.velocity["vector"] - b.velocity["vector"].mean(axis=0)).max() > 1e-2  # the stress did act (not a rigid free fall)
     assert example.cu_launcher_calls(h, 0) == 2          # timestep_started: once per spk_step
     assert example.cu_launcher_calls(h, 2) == nsub       # launch_g2p2g: once per substep
-    assert example.cu_launcher_calls(h, 1) == 1          # estimate: only the first substep (later ones use the candidate fused into g2p2g)
+    assert example.cu_launcher_calls(h, 1) == nsub       # estimate: a REGISTERED estimate launcher is called every substep (step_generic, cuda_mpm_pipeline.rs:381-392)
     g_cus.close()
     example.cu_launcher_destroy(h)
 

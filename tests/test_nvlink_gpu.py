@@ -40,3 +40,18 @@ def test_particle_migration_on_the_peer_memory_path():
     assert r.returncode == 0, out[-3000:]
     line = [l for l in out.splitlines() if "migration check" in l]
     assert line and line[-1].rstrip().endswith("OK"), out[-3000:]
+
+
+def test_a_late_peer_is_reported_not_ignored():
+    """a peer that misses a device-side barrier (here: 2 s late against a 300 ms time-out) must surface as SPK_EPEER on
+    the rank that waited, at the latest by the end of the frame / the next call (scripts/check_peer_timeout.py)"""
+    env = dict(os.environ, SPK_CHECK_ONE_GPU="1", OMP_NUM_THREADS="1", SPK_DIST_TIMEOUT_MS="300", SPK_CHECK_DELAY_S="2.0")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29581", os.path.join(ROOT, "scripts", "check_peer_timeout.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    out = r.stdout + r.stderr
+    if "devices are busy or unavailable" in out or "exclusive" in out.lower():
+        pytest.skip("the GPU is in exclusive-process compute mode: two processes cannot share it")
+    assert r.returncode == 0, out[-3000:]
+    line = [l for l in out.splitlines() if "peer timeout check: rank 0" in l]
+    assert line and line[-1].rstrip().endswith("OK"), out[-3000:]
