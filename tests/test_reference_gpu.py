@@ -45,6 +45,8 @@ def _lockstep(scene, ob, nsub, base, growth=3.0, robust=False, dt_rtol=1e-5):
     worst = {}
     for s in range(nsub):
         tol = util.scene_tol(scene, base * (1 + growth * s))
+        if any(getattr(m.plastic_model, "tag", None) == 0 for m in scene.models):
+            tol.few = 2e-3  # Drucker-Prager: see util.Tol.few
         max_dt = float(min(remaining, np.float32(p.max_substep_dt)))
         canon = {}
         for k, e in E.items():

@@ -30,13 +30,21 @@ def nodes_by_key(engine, which):
     return hdr["virtual_id"][order], nodes[order]
 
 
-def rel_err(a, b, floor=0.0, atol=0.0):
-    """max |a-b| minus an absolute allowance, relative to the scale of b"""
+def rel_err(a, b, floor=0.0, atol=0.0, few=0.0):
+    """max |a-b| minus an absolute allowance, relative to the scale of b.  `few` > 0: the max over all but that fraction (at least one)
+    of the entries — for quantities that depend discontinuously on the state (see Tol.few)"""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     if not a.size:
         return 0.0
     scale = max(float(np.max(np.abs(b))), floor, 1e-30)
-    return max(float(np.max(np.abs(a - b))) - atol, 0.0) / scale
+    d = np.abs(a - b)
+    if few > 0.0:
+        d = np.sort(d.ravel())
+        k = max(1, int(np.ceil(few * d.size)))
+        worst = float(d[-k - 1]) if d.size > k else 0.0
+    else:
+        worst = float(np.max(d))
+    return max(worst - atol, 0.0) / scale
 
 
 def rel_err_but_few(a, b, floor=0.0, atol=0.0, few=1e-3):
@@ -53,6 +61,10 @@ def rel_err_but_few(a, b, floor=0.0, atol=0.0, few=1e-3):
 
 
 class Tol:
+    few = 0.0  # set by a caller that compares against the REFERENCE's kernels on a scene with Drucker-Prager plasticity: the return mapping
+               # is discontinuous at zero volumetric strain (plasticity_drucker_prager.rs:47-49), so round-off flips single particles between
+               # branches — between two runs of the reference itself too (test_reference_run_to_run_spread_and_product_within_it).  A
+               # fraction `few` of the entries of the stress-dependent fields is then exempt from the max-norm check.
     """Tolerance classes of the parity tests (all relative to the field's scale over the scene):
       base       well-conditioned state: positions (in units of h), F, Jp, masses, hardening variables
       20 x base  velocity-like: particle velocities, node momenta / velocities (they carry the stress error below)
@@ -89,14 +101,14 @@ def assert_particles_close(pa: abi.ParticleComponents, pb: abi.ParticleComponent
     b = tol.base
     checks = {  # name: (error, allowed)
         "pos": (float(np.max(np.abs(pa.position["point"].astype(np.float64) - pb.position["point"]))) / max(h, 1e-30) if len(pa) else 0.0, b),
-        "vel": (rel_err(pa.velocity["vector"], pb.velocity["vector"], floor=1e-2), 20 * b),
-        "F": (rel_err(pa.volume["deformation_gradient"], pb.volume["deformation_gradient"], floor=1.0), b),
-        "Jp": (rel_err(pa.volume["plastic_deformation_gradient_det"], pb.volume["plastic_deformation_gradient_det"], floor=1.0), b),
+        "vel": (rel_err(pa.velocity["vector"], pb.velocity["vector"], floor=1e-2, few=tol.few), 20 * b),
+        "F": (rel_err(pa.volume["deformation_gradient"], pb.volume["deformation_gradient"], floor=1.0, few=tol.few), b),
+        "Jp": (rel_err(pa.volume["plastic_deformation_gradient_det"], pb.volume["plastic_deformation_gradient_det"], floor=1.0, few=tol.few), b),
         "psi_pos": (rel_err_but_few(pa.phase["psi_pos"], pb.phase["psi_pos"], floor=1e-3, atol=tol.energy_atol), 50 * b),
         "phase": (rel_err(pa.phase["phase"], pb.phase["phase"], floor=1.0), b),
-        "plastic_hardening": (rel_err(pa.data["plastic_hardening"], pb.data["plastic_hardening"], floor=1.0), b),
+        "plastic_hardening": (rel_err(pa.data["plastic_hardening"], pb.data["plastic_hardening"], floor=1.0, few=tol.few), b),
         "elastic_hardening": (rel_err(pa.data["elastic_hardening"], pb.data["elastic_hardening"], floor=1.0), b),
-        "log_vol_gain": (rel_err(pa.data["log_vol_gain"], pb.data["log_vol_gain"], floor=5e-2), 50 * b),
+        "log_vol_gain": (rel_err(pa.data["log_vol_gain"], pb.data["log_vol_gain"], floor=5e-2, few=tol.few), 50 * b),
         "nacc_alpha": (rel_err(pa.data["nacc_alpha"], pb.data["nacc_alpha"], floor=1e-2), 50 * b),
     }
     bad = {k: v for k, v in checks.items() if not (v[0] <= v[1])}
@@ -191,7 +203,7 @@ def assert_nodes_close(na, nb, tol, what="", scene=None, vids=None, oracle=None,
     pv_b = nb["psi_momentum_velocity"].astype(np.float64) * wgt
     checks = {
         "mass": (rel_err(na["mass"], nb["mass"]), b),
-        "momentum_velocity": (rel_err(mv_a, mv_b, floor=1e-2), 50 * b),
+        "momentum_velocity": (rel_err(mv_a, mv_b, floor=1e-2, few=tol.few), 50 * b),
         "psi_momentum_velocity": (rel_err(pv_a, pv_b, floor=1e-3, atol=tol.energy_atol * max(mscale, 1.0)), 50 * b),
         "psi_mass": (rel_err(na["psi_mass"], nb["psi_mass"]), b),
         "prev_mass": (rel_err(na["prev_mass"], nb["prev_mass"]), b),
