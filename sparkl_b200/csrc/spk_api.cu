@@ -356,6 +356,13 @@ int spk_particles_resize(spk_ctx* c, size_t n, bool fresh) {
     return SPK_OK;
 }
 
+// orders the main stream behind a grid update that spk_step left running on its own stream (no-op otherwise); called by every entry
+// point that reads or writes the sparse grid outside spk_step's own loop
+int spk_join_grid_update(spk_ctx* c) {
+    if (c->gu_pending) { CK(cudaStreamWaitEvent(c->stream, c->ev_gu_done, 0)); c->gu_pending = false; }
+    return SPK_OK;
+}
+
 // CudaParticleKernelsLauncher dispatch: the registered callbacks, else the default launches
 static int launch_g2p2g_hooked(spk_ctx* c, float dt) {
     if (c->launcher.launch_g2p2g) return c->launcher.launch_g2p2g(c->launcher.user, c, dt);
@@ -421,6 +428,10 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->gu_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_transfer_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_gu_done, cudaEventDisableTiming));
+    c->overlap_grid_update = getenv("SPK_NO_GU_OVERLAP") ? 0 : 1;
     CK(cudaEventCreateWithFlags(&c->up_ready, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->up_consumed, cudaEventDisableTiming));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
@@ -463,6 +474,7 @@ int spk_ctx_destroy(spk_ctx* c) {
     if (c->dist_arena) cudaFree(c->dist_arena);
     if (c->dist_peer_ids) cudaFree(c->dist_peer_ids);
     if (c->dist_push_ptrs) cudaFree(c->dist_push_ptrs);
+    if (c->dist_bbox) cudaFree(c->dist_bbox);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_upload) cudaFreeHost(c->h_upload);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -471,7 +483,8 @@ int spk_ctx_destroy(spk_ctx* c) {
     cudaStreamSynchronize(c->h2d_stream);
     if (c->up_staging) cudaFree(c->up_staging);
     cudaEventDestroy(c->up_ready); cudaEventDestroy(c->up_consumed);
-    cudaStreamDestroy(c->stream); cudaStreamDestroy(c->halo_stream); cudaStreamDestroy(c->h2d_stream);
+    cudaStreamDestroy(c->stream); cudaStreamDestroy(c->halo_stream); cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->gu_stream);
+    cudaEventDestroy(c->ev_transfer_done); cudaEventDestroy(c->ev_gu_done);
     delete c;
     return SPK_OK;
 }
@@ -481,6 +494,7 @@ int spk_ctx_stream(spk_ctx* c, void** out) { if (!c || !out) return SPK_EINVAL; 
 int spk_ctx_synchronize(spk_ctx* c) {
     if (!c) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     CK(cudaStreamSynchronize(c->stream));
     return c->h_counters->pad[1] ? SPK_EPEER : SPK_OK;
 }
@@ -941,6 +955,7 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
 int spk_stage_reset_grid(spk_ctx* c) {
     if (!c) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     CK(spk_launch_reset_grid(c));
     return SPK_OK;
 }
@@ -990,6 +1005,7 @@ int spk_stage_g2p2g(spk_ctx* c, float dt, uint32_t damage_model) {
     if (!c) return SPK_EINVAL;
     if (!c->sorted_valid) return SPK_ESTATE;
     CK(cudaSetDevice(c->device));
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     return launch_g2p2g_hooked(c, dt);
 }
 
@@ -1000,6 +1016,7 @@ int spk_stage_recompute_fluids_volume(spk_ctx* c) {
     if (!c->sorted_valid) return SPK_ESTATE; // needs the particle -> block map of spk_stage_sort (and the zeroed next grid)
     if (spk_dist_active(c)) return SPK_EUNSUPPORTED; // the node masses of shared blocks would need their own halo exchange
     CK(cudaSetDevice(c->device));
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     CK(spk_launch_fluids_volume(c));
     c->dt_cache_valid = false; // F[0][0] of the fluid particles changed: the cached CFL candidate is stale
     return SPK_OK;
@@ -1008,6 +1025,7 @@ int spk_stage_recompute_fluids_volume(spk_ctx* c) {
 int spk_stage_grid_update(spk_ctx* c, float dt, const float gravity[SPK_DIM]) {
     if (!c || !gravity) return SPK_EINVAL;
     CK(cudaSetDevice(c->device));
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     CK(spk_launch_grid_update(c, dt, gravity));
     return SPK_OK;
 }
@@ -1193,6 +1211,7 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
         SpkSortInfo info;
         if ((rc = spk_stage_sort(c, &info))) return rc;
         if (timings) CK(cudaEventRecord(ev[1], c->stream));
+        if ((rc = spk_join_grid_update(c))) return rc; // reset / g2p2g read what the last grid update wrote
         CK(spk_launch_reset_grid(c));
         if (timings) CK(cudaEventRecord(ev[2], c->stream));
         float dt;
@@ -1209,7 +1228,21 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
             CK(spk_dist_launch_barrier(c, 1));
             CK(spk_dist_launch_merge(c));
         }
-        CK(spk_launch_grid_update(c, dt, gravity));
+        if (!timings && !dist && c->overlap_grid_update) {
+            // the grid update only touches the grid g2p2g just filled; the next substep's sort only reads the particles g2p2g just wrote
+            // and builds the OTHER grid buffer: the two run side by side, and meet again before the next reset_grid
+            CK(cudaEventRecord(c->ev_transfer_done, c->stream));
+            CK(cudaStreamWaitEvent(c->gu_stream, c->ev_transfer_done, 0));
+            cudaStream_t main_stream = c->stream;
+            c->stream = c->gu_stream;
+            const cudaError_t ge = spk_launch_grid_update(c, dt, gravity);
+            c->stream = main_stream;
+            CK(ge);
+            CK(cudaEventRecord(c->ev_gu_done, c->gu_stream));
+            c->gu_pending = true;
+        } else {
+            CK(spk_launch_grid_update(c, dt, gravity));
+        }
         if (timings) {
             CK(cudaEventRecord(ev[5], c->stream));
             CK(cudaEventSynchronize(ev[5]));
@@ -1234,6 +1267,8 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
         timings->g2p2g_launches = c->g2p2g_launches - g2p2g0;
         timings->kernel_launches = c->launches - launches0;
     }
+    // (a grid update left on its own stream is joined by the next call that touches the grid: the next spk_step does so only before
+    // its reset_grid, i.e. after its particle sort ran next to it)
     if (simulated_time_out) *simulated_time_out = params->dt - remaining;
     // (the barriers of the frame's last substep run after its counter record was published: a time-out there is written straight into
     // the mapped host record by the barrier kernel and is seen by the next call that looks — the next spk_step, spk_ctx_synchronize)
@@ -1249,6 +1284,7 @@ int spk_grid_num_active_blocks(spk_ctx* c, int which_grid, uint32_t* out) {
 }
 int spk_grid_read_headers(spk_ctx* c, int which_grid, SpkActiveBlockHeader* dst, uint32_t n) {
     if (!c || (n && !dst)) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     GridBuffers& g = which_grid ? c->grid[1 - c->gcur] : c->grid[c->gcur];
     if (n > g.nab_host) return SPK_EINVAL;
     if (!n) return SPK_OK;
@@ -1265,6 +1301,7 @@ int spk_grid_read_headers(spk_ctx* c, int which_grid, SpkActiveBlockHeader* dst,
 }
 int spk_grid_read_nodes(spk_ctx* c, int which_grid, SpkGpuGridNode* dst, uint32_t n_blocks) {
     if (!c || (n_blocks && !dst)) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     GridBuffers& g = which_grid ? c->grid[1 - c->gcur] : c->grid[c->gcur];
     if (n_blocks > g.nab_host) return SPK_EINVAL;
     if (!n_blocks) return SPK_OK;
@@ -1280,6 +1317,7 @@ int spk_grid_read_nodes(spk_ctx* c, int which_grid, SpkGpuGridNode* dst, uint32_
 // (write_blocks_multiplicity_to_scan_value + init_gpu_dispatch_blocks_mapping, sort.rs:226-280), derived from the headers
 int spk_grid_read_dispatch(spk_ctx* c, SpkDispatchBlock2ActiveBlock* dst, uint32_t n) {
     if (!c || (n && !dst)) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     GridBuffers& g = c->sorted_valid ? c->grid[1 - c->gcur] : c->grid[c->gcur];
     std::vector<SpkActiveBlockHeader> h(g.nab_host);
     int rc = spk_grid_read_headers(c, c->sorted_valid ? 1 : 0, h.data(), g.nab_host);
@@ -1324,12 +1362,14 @@ int spk_device_ptr(spk_ctx* c, int which, void** out) {
 // ------------------------------------------------------------------------------------------------ halo (multi-process)
 int spk_halo_begin(spk_ctx* c) {
     if (!c) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(&c->d_counters->num_halo, 0, 4, c->stream));
     return SPK_OK;
 }
 int spk_halo_active_keys(spk_ctx* c, uint64_t* dev_keys_out, uint32_t capacity) {
     if (!c || (capacity && !dev_keys_out)) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     if (c->grid[1 - c->gcur].nab_host > capacity) return SPK_EOVERFLOW;
     CK(cudaSetDevice(c->device));
     CK(spk_launch_halo_keys(c, (unsigned long long*)dev_keys_out, capacity));
@@ -1337,12 +1377,14 @@ int spk_halo_active_keys(spk_ctx* c, uint64_t* dev_keys_out, uint32_t capacity) 
 }
 int spk_halo_tag(spk_ctx* c, const uint64_t* dev_remote_keys, uint32_t n_remote) {
     if (!c) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     CK(cudaSetDevice(c->device));
     CK(spk_launch_halo_tag(c, (const unsigned long long*)dev_remote_keys, n_remote));
     return SPK_OK;
 }
 int spk_halo_count(spk_ctx* c, uint32_t* num_halo_out) {
     if (!c || !num_halo_out) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     CK(cudaSetDevice(c->device));
     int rc = read_counters(c);
     if (rc) return rc;
@@ -1351,12 +1393,14 @@ int spk_halo_count(spk_ctx* c, uint32_t* num_halo_out) {
 }
 int spk_halo_pack(spk_ctx* c, uint64_t* dev_keys_out, float* dev_payload_out, uint32_t capacity) {
     if (!c) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     CK(cudaSetDevice(c->device));
     CK(spk_launch_halo_pack(c, (unsigned long long*)dev_keys_out, dev_payload_out, capacity));
     return SPK_OK;
 }
 int spk_halo_merge(spk_ctx* c, const uint64_t* dev_keys, const float* dev_payload, uint32_t n_blocks) {
     if (!c) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     CK(cudaSetDevice(c->device));
     CK(spk_launch_halo_merge(c, (const unsigned long long*)dev_keys, dev_payload, n_blocks));
     return SPK_OK;

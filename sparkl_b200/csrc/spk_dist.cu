@@ -27,6 +27,7 @@ cudaError_t spk_dist_launch_barrier(spk_ctx*, int) { return cudaErrorNotSupporte
 cudaError_t spk_dist_launch_detect(spk_ctx*) { return cudaErrorNotSupported; }
 cudaError_t spk_dist_launch_push(spk_ctx*) { return cudaErrorNotSupported; }
 cudaError_t spk_dist_launch_merge(spk_ctx*) { return cudaErrorNotSupported; }
+float* spk_dist_hacc_of_next(spk_ctx*) { return nullptr; }
 extern "C" {
 int spk_dist_export(spk_ctx*, SpkDistDescriptor*) { return SPK_EUNSUPPORTED; }
 int spk_dist_attach(spk_ctx*, uint32_t, uint32_t, const SpkDistDescriptor*) { return SPK_EUNSUPPORTED; }
@@ -88,7 +89,8 @@ __device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) {
 //   mode 0: plain barrier, publishes `gnext` (which grid buffer is this rank's next grid)
 //   mode 1: additionally min-reduces counters->dt_raw_bits over the ranks (fused CFL reduction of g2p2g)
 //   mode 2: additionally min-reduces counters->dt_acc over the ranks (stand-alone estimate_dt kernel)
-__global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext, int mode, DeviceCounters* counters, long long timeout_cycles, DeviceCounters* host_record) {
+__global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext, int mode, DeviceCounters* counters, long long timeout_cycles, DeviceCounters* host_record,
+                                    const uint32_t* __restrict__ bbox) {
     const uint32_t p = threadIdx.x;
     const uint32_t slot = epoch & 1u;
     unsigned long long mine = 0;
@@ -101,6 +103,8 @@ __global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext,
             DistMailbox* remote = d.peer_mailbox[p];
             remote->val[slot][d.rank] = mine;
             remote->gnext[slot][d.rank] = gnext;
+            if (mode == 0) // the barrier before the detection carries the bounding box of this rank's active blocks
+                for (int k = 0; k < 6; ++k) remote->bbox[slot][d.rank][k] = bbox[k];
             __threadfence_system(); // payload (and everything this rank wrote before, incl. NVLink atomics) before the flag
             st_sys_u32(&remote->flag[d.rank], epoch);
             const long long t0 = clock64();
@@ -143,6 +147,14 @@ __global__ void __launch_bounds__(256) dist_detect_kernel(DistState d, GridBuffe
         const unsigned long long* keys = d.peer_grid[p][g].keys;
         const uint32_t cap = d.peer_cap_hash[p], mask = cap - 1;
         const unsigned long long key = next.blk_key[b];
+        // geometric pre-filter: only a block inside the peer's bounding box can be active there too — for slabs that is the
+        // layer of blocks at the common face; every other block skips the probe of the peer's hash table over NVLink
+        unsigned long long kx, ky, kz;
+        spk_unpack_key(key, kx, ky, kz);
+        const uint32_t* bb = const_cast<const uint32_t*>(d.mailbox->bbox[epoch & 1u][p]);
+        const bool maybe = (uint32_t)kx >= __ldcv(&bb[0]) && (uint32_t)kx <= __ldcv(&bb[3]) && (uint32_t)ky >= __ldcv(&bb[1]) && (uint32_t)ky <= __ldcv(&bb[4]) &&
+                           (uint32_t)kz >= __ldcv(&bb[2]) && (uint32_t)kz <= __ldcv(&bb[5]);
+        if (maybe) {
         // GridHashMap::get (hashmap.rs:72-87) on the PEER's table: volatile loads, never served from a stale L1 line
         uint32_t slot = spk_hash(key, mask);
         for (uint32_t probe = 0; probe < cap; ++probe) {
@@ -153,6 +165,7 @@ __global__ void __launch_bounds__(256) dist_detect_kernel(DistState d, GridBuffe
         }
         if ((uint32_t)id >= cap / 2) id = -1;
         if (id >= 0 && atomicExch(&next.blk_halo[b], 1u) == 0u) atomicAdd(&counters->num_halo, 1u);
+        }
     }
     peer_ids[(size_t)b * d.world + p] = id;
 }
@@ -207,7 +220,7 @@ bool spk_dist_grid_storage(spk_ctx* c, int g, uint32_t cap_hash, unsigned long l
 cudaError_t spk_dist_launch_barrier(spk_ctx* c, int mode) {
     DistState& d = c->dist;
     d.epoch += 1;
-    dist_barrier_kernel<<<1, SPK_MAX_RANKS, 0, c->stream>>>(d, d.epoch, (uint32_t)(1 - c->gcur), mode, c->d_counters, c->dist_timeout_cycles, c->h_counters_dev);
+    dist_barrier_kernel<<<1, SPK_MAX_RANKS, 0, c->stream>>>(d, d.epoch, (uint32_t)(1 - c->gcur), mode, c->d_counters, c->dist_timeout_cycles, c->h_counters_dev, c->dist_bbox);
     c->launches += 1;
     c->counters_fresh = false;
     return cudaGetLastError();
@@ -230,9 +243,10 @@ cudaError_t spk_dist_launch_push(spk_ctx* c) {
     c->launches += 1;
     return cudaGetLastError();
 }
+float* spk_dist_hacc_of_next(spk_ctx* c) { return c->dist_arena && c->dist.world > 1 ? arena_grid(c->dist_arena, c->dist_cap_hash, 1 - c->gcur).hacc : nullptr; }
 cudaError_t spk_dist_launch_merge(spk_ctx* c) {
     GridBuffers& next = c->grid[1 - c->gcur];
-    if (!next.nab_host) return cudaSuccess;
+    if (!next.nab_host || c->dist_merge_in_update) return cudaSuccess; // folded into grid_update_kernel
     dist_merge_kernel<<<next.nab_host, 128, 0, c->stream>>>(next, next.nab_host, arena_grid(c->dist_arena, c->dist_cap_hash, 1 - c->gcur).hacc);
     c->launches += 1;
     return cudaGetLastError();
@@ -242,6 +256,7 @@ extern "C" {
 
 int spk_dist_export(spk_ctx* c, SpkDistDescriptor* out) {
     if (!c || !out) return SPK_EINVAL;
+    { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
     if (c->dist_arena) return SPK_ESTATE;
     CK(cudaSetDevice(c->device));
     // the shared arena has a fixed capacity: size it generously from what the particle count suggested (growth of the hash
@@ -261,6 +276,10 @@ int spk_dist_export(spk_ctx* c, SpkDistDescriptor* out) {
     CK(cudaMalloc((void**)&c->dist_peer_ids, (size_t)(cap / 2) * SPK_MAX_RANKS * sizeof(int32_t)));
     CK(cudaMalloc((void**)&c->dist_push_ptrs, SPK_MAX_RANKS * sizeof(float*)));
     CK(cudaMemset(c->dist_push_ptrs, 0, SPK_MAX_RANKS * sizeof(float*)));
+    CK(cudaMalloc((void**)&c->dist_bbox, 6 * sizeof(uint32_t)));
+    c->dist_push_wait = getenv("SPK_DIST_PUSH_WAIT") ? 1 : 0;
+    c->dist_merge_in_update = 1;
+    if (const char* m = getenv("SPK_DIST_MERGE")) c->dist_merge_in_update = std::strcmp(m, "kernel") != 0;
     c->dist_fused_push = 1;
     if (const char* m = getenv("SPK_DIST_PUSH")) c->dist_fused_push = std::strcmp(m, "kernel") != 0; // A/B: separate push kernel
     {   // barrier timeout: SPK_DIST_TIMEOUT_MS (default 3000, 0 = unbounded), converted with the device's SM clock

@@ -39,6 +39,7 @@ struct G2P2GParams {
     const uint32_t* blk_halo;   // [block] bit0: active on another rank too (spk_dist.cu: dist_detect_kernel)
     const int32_t* peer_ids;    // [block][world] the peer's id of the block, -1 if absent
     float* const* peer_hacc;    // [world] peer-mapped `hacc` of each rank's next grid
+    uint32_t push_wait;         // 1: a CTA that pushed waits for the remote completion of its reductions (A/B); 0: the kernel boundary orders them
     const void* user;           // opaque device pointer handed to the updater (custom updaters; NULL for the default)
 };
 
@@ -448,7 +449,10 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
             }
         }
         if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(P.dt_raw_bits, *s_dtmin);
-        if (pushed) { // remote reductions must be complete (not only read out of shared memory) before this CTA retires
+        // Remote reductions must have landed before the peer is told so.  The telling is done by the barrier kernel that FOLLOWS this
+        // kernel on the stream (system fence, then the flag): a kernel is complete only when its bulk operations are, so the CTA
+        // only has to wait until its shared memory has been read (push_wait = 1 restores the per-CTA wait for completion, A/B)
+        if (pushed && P.push_wait) {
 #ifndef SPK_EMU
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1050,7 +1054,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             }
         }
         if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(P.dt_raw_bits, *s_dtmin);
-        if (pushed) {
+        if (pushed && P.push_wait) {
 #ifndef SPK_EMU
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1095,6 +1099,7 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     P.blk_halo = next.blk_halo;
     P.peer_ids = c->dist_peer_ids;
     P.peer_hacc = c->dist_push_ptrs;
+    P.push_wait = (uint32_t)c->dist_push_wait;
     P.user = user;
     { cudaError_t e = cudaMemsetAsync(&c->d_counters->dt_raw_bits, 0x7f, 4, c->stream); if (e != cudaSuccess) return e; }
     static bool configured[64] = {}; // per instantiation and device: the > 48 KB dynamic shared memory opt-in is a per-device function attribute

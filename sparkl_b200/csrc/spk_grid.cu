@@ -270,10 +270,20 @@ __device__ inline bool sdf(const DevCollider* cols, uint32_t ncol, Vec3 q, float
 }
 
 __global__ void __launch_bounds__(256) grid_update_kernel(GridBuffers g, uint32_t nab, const DevCollider* __restrict__ cols, uint32_t ncol, float h, float dt,
-                                                           float gx, float gy, float gz) {
+                                                           float gx, float gy, float gz, float* hacc) {
     const uint32_t b = blockIdx.x * 4 + (threadIdx.x >> 6);
     const uint32_t cell = threadIdx.x & 63;
     if (b >= nab) return;
+    if (hacc && (g.blk_halo[b] & 1u)) { // multi-GPU, merge_halo_blocks (sort.rs:142-164): fold what the peers pushed, clear it for the next use
+        float* a = g.acc + (size_t)b * (SPK_ACC_CHANNELS * 64);
+        float* hh = hacc + (size_t)b * (SPK_ACC_CHANNELS * 64);
+#pragma unroll
+        for (int ch = 0; ch < SPK_ACC_CHANNELS; ++ch) {
+            const uint32_t i = ch * 64 + SPK_ACC_SWZ(cell); // exactly the entries this thread reads below, through `acc`
+            a[i] += __ldcg(&hh[i]);
+            hh[i] = 0.f;
+        }
+    }
     const float* acc = g.acc + (size_t)b * (SPK_ACC_CHANNELS * 64) + SPK_ACC_SWZ(cell) - cell; // acc[ch * 64 + cell] below: the swizzled slot
     const size_t node = (size_t)b * 64 + cell;
     // the reference's `red.global.add.f32` flushes subnormals (PTX ISA); keep 1/mass finite the same way
@@ -455,7 +465,8 @@ cudaError_t spk_launch_grid_update(spk_ctx* c, float dt, const float gravity[SPK
     GridBuffers& next = c->grid[1 - c->gcur];
     const uint32_t nab = next.nab_host;
     if (nab) {
-        grid_update_kernel<<<(nab + 3) / 4, 256, 0, c->stream>>>(next, nab, c->colliders, (uint32_t)c->ncolliders, c->cell_width, dt, gravity[0], gravity[1], gravity[2]);
+        grid_update_kernel<<<(nab + 3) / 4, 256, 0, c->stream>>>(next, nab, c->colliders, (uint32_t)c->ncolliders, c->cell_width, dt, gravity[0], gravity[1], gravity[2],
+                                                                 c->dist_merge_in_update ? spk_dist_hacc_of_next(c) : nullptr);
         c->launches += 1;
     }
     next.has_velocity = 1;

@@ -136,6 +136,8 @@ struct DistMailbox { // first 4 KB of every rank's shared arena; written by the 
     volatile uint32_t flag[SPK_MAX_RANKS];        // flag[p]: last barrier epoch signalled by rank p
     uint32_t gnext[2][SPK_MAX_RANKS];             // [epoch & 1][p]: which grid buffer is rank p's next grid
     unsigned long long val[2][SPK_MAX_RANKS];     // [epoch & 1][p]: rank p's dt candidate
+    uint32_t bbox[2][SPK_MAX_RANKS][6];           // [epoch & 1][p]: bounding box of rank p's active blocks (min x, y, z, max x, y, z of the raw
+                                                  // key coordinates): a block outside it cannot be shared with rank p and is not probed
 };
 struct DistGridView { unsigned long long* keys; uint32_t* vals; float* hacc; }; // one grid buffer's shared arrays
 struct DistState {   // passed by value to the kernels
@@ -150,6 +152,9 @@ struct spk_ctx {
     int device;
     float cell_width;
     cudaStream_t stream, halo_stream;
+    // spk_step runs the grid update of substep n on its own stream, next to the particle sort of substep n + 1 (both only depend on
+    // g2p2g of substep n); `gu_pending`: the main stream has not yet been ordered behind the last grid update
+    cudaStream_t gu_stream; cudaEvent_t ev_transfer_done, ev_gu_done; bool gu_pending; int overlap_grid_update;
     // particles
     size_t n, cap;
     int cur; // index of the current particle buffer
@@ -197,6 +202,10 @@ struct spk_ctx {
     // multi-GPU (all zero / null in single-GPU runs)
     DistState dist;
     char* dist_arena; size_t dist_arena_bytes; uint32_t dist_cap_hash;
+    uint32_t* dist_bbox;                 // [6] device: bounding box of this rank's active blocks of the current sort (build_tables_kernel)
+    int dist_merge_in_update;            // 1 (default): grid_update folds the peers' halo sums itself; 0: separate merge kernel (A/B: SPK_DIST_MERGE=kernel)
+    int dist_push_wait;                  // 1: a CTA that pushed halo sums waits for their remote completion (A/B: SPK_DIST_PUSH_WAIT=1); 0 (default): the
+                                         // kernel boundary + the barrier's system fence order them before the flag
     int32_t* dist_peer_ids;              // [cap_blocks][world]: the peer's id of each of this rank's active blocks, -1 if absent
     void* dist_mapped[SPK_MAX_RANKS];    // cudaIpcOpenMemHandle results (to close)
     float** dist_push_ptrs;              // [SPK_MAX_RANKS] device array: peer-mapped hacc of every rank's next grid (written by detect)
@@ -235,7 +244,9 @@ cudaError_t spk_launch_halo_merge(spk_ctx* c, const unsigned long long* keys, co
 bool spk_dist_active(const spk_ctx* c);
 bool spk_dist_grid_storage(spk_ctx* c, int g, uint32_t cap_hash, unsigned long long** keys, uint32_t** vals);
 int spk_dist_realloc_grids(spk_ctx* c, uint32_t cap_hash); // defined in spk_api.cu
+int spk_join_grid_update(spk_ctx* c);                        // spk_api.cu: main stream waits for a grid update left on its own stream
 cudaError_t spk_dist_launch_barrier(spk_ctx* c, int mode); // 0 barrier, 1 + min of dt_raw_bits, 2 + min of dt_acc
 cudaError_t spk_dist_launch_detect(spk_ctx* c);
 cudaError_t spk_dist_launch_push(spk_ctx* c);
 cudaError_t spk_dist_launch_merge(spk_ctx* c);
+float* spk_dist_hacc_of_next(spk_ctx* c); // this rank's halo accumulator of the next grid (NULL without an attachment)

@@ -211,10 +211,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned
 // (launched for the grid's block CAPACITY before the host has read the block count back, so that the read-back overlaps this
 // kernel and scatter_perm_kernel; the true count comes from the device-side record)
 __global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, const DeviceCounters* __restrict__ counters, int32_t* __restrict__ dispatch_nbr,
-                                    uint32_t dispatch_cap, uint32_t chunk) {
+                                    uint32_t dispatch_cap, uint32_t chunk, uint32_t* bbox) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t b = t >> SPK_NBR_SHIFT, o = t & (SPK_NBR - 1);
-    if (b >= counters->nab || b >= next.cap_blocks) return;
+    const bool live = b < counters->nab && b < next.cap_blocks;
+#if SPK_DIM == 3
+    if (bbox) { // multi-GPU: bounding box of the active blocks (raw key coordinates), one atomic per warp and bound
+        unsigned long long kx = 0, ky = 0, kz = 0;
+        if (live) spk_unpack_key(next.blk_key[b], kx, ky, kz);
+        const uint32_t lo[3] = {live ? (uint32_t)kx : 0xffffffffu, live ? (uint32_t)ky : 0xffffffffu, live ? (uint32_t)kz : 0xffffffffu};
+        const uint32_t hi[3] = {live ? (uint32_t)kx : 0u, live ? (uint32_t)ky : 0u, live ? (uint32_t)kz : 0u};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const uint32_t mn = __reduce_min_sync(0xffffffffu, lo[a]), mx = __reduce_max_sync(0xffffffffu, hi[a]);
+            if ((threadIdx.x & 31) == 0 && mn <= mx) { atomicMin(&bbox[a], mn); atomicMax(&bbox[3 + a], mx); }
+        }
+    }
+#endif
+    if (!live) return;
     const unsigned long long key = spk_key_offset(next.blk_key[b], (int)o);
     const int32_t ns = spk_hash_get(next, key), np = spk_hash_get(prev, key);
     next.nbr_self[b * SPK_NBR + o] = ns;
@@ -275,7 +289,12 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c) {
     cudaStream_t s = c->stream;
     const uint32_t n = (uint32_t)c->n;
     {
-        build_tables_kernel<<<(g.cap_blocks * SPK_NBR + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters, c->dispatch_nbr, c->dispatch_cap, c->chunk);
+        if (c->dist_bbox) { // {min x, y, z} = 0xffffffff, {max x, y, z} = 0
+            cudaError_t e = cudaMemsetAsync(c->dist_bbox, 0xff, 12, s);
+            if (e == cudaSuccess) e = cudaMemsetAsync(c->dist_bbox + 3, 0, 12, s);
+            if (e != cudaSuccess) return e;
+        }
+        build_tables_kernel<<<(g.cap_blocks * SPK_NBR + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters, c->dispatch_nbr, c->dispatch_cap, c->chunk, c->dist_bbox);
         c->launches += 1;
     }
     if (n) {

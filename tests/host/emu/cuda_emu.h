@@ -97,11 +97,22 @@ static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
     return r;
 }
 
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    unsigned long long* s = emu::warp_scratch();
+    s[emu::lane()] = v;
+    emu::warp_sync(mask);
+    unsigned r = 0u;
+    for (int l = 0; l < 32; ++l) if ((mask >> l & 1u) && (unsigned)s[l] > r) r = (unsigned)s[l];
+    emu::warp_sync(mask);
+    return r;
+}
+
 // ---- atomics (one fiber runs at a time) -----------------------------------------------------------------------------------------
 template <typename T> static inline T atomicAdd(T* p, T v) { const T old = *p; *p = old + v; return old; }
 static inline unsigned atomicAdd(unsigned* p, int v) { const unsigned old = *p; *p = old + (unsigned)v; return old; }
 static inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }
 template <typename T> static inline T atomicMin(T* p, T v) { const T old = *p; if (v < old) *p = v; return old; }
+template <typename T> static inline T atomicMax(T* p, T v) { const T old = *p; if (v > old) *p = v; return old; }
 template <typename T> static inline T atomicExch(T* p, T v) { const T old = *p; *p = v; return old; }
 template <typename T> static inline T atomicCAS(T* p, T cmp, T v) { const T old = *p; if (old == cmp) *p = v; return old; }
 

@@ -47,7 +47,7 @@ void launch(K kernel, unsigned grid, unsigned block, Args... args) {
 extern "C" {
 void hk3_reset_grid(GridBuffers next, GridBuffers prev, uint32_t nab) { if (nab) launch(reset_grid_kernel, (nab + 3) / 4, 256, next, prev, nab); }
 void hk3_grid_update(GridBuffers g, uint32_t nab, const DevCollider* cols, uint32_t ncol, float h, float dt, float gx, float gy, float gz) {
-    if (nab) launch(grid_update_kernel, (nab + 3) / 4, 256, g, nab, cols, ncol, h, dt, gx, gy, gz);
+    if (nab) launch(grid_update_kernel, (nab + 3) / 4, 256, g, nab, cols, ncol, h, dt, gx, gy, gz, (float*)nullptr);
 }
 void hk3_grid_export(GridBuffers g, uint32_t nblocks, SpkGpuGridNode* out) { if (nblocks) launch(grid_export_kernel, (nblocks * 64 + 255) / 256, 256, g, nblocks, out); }
 int hk3_sizeof_gridbuffers(void) { return (int)sizeof(GridBuffers); }
