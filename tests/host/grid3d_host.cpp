@@ -14,6 +14,7 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline float __fdividef(float a, float b) { return a / b; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline long long __float2ll_rz(float x) {
     if (x != x) return 0;
     if (x >= 9.2233720368547758e18f) return INT64_MAX;
