@@ -176,10 +176,10 @@ def cpu_baseline(steps, warmup, config="S4M"):
     """the oracle port timed on the host cores (all threads) on a bounded sample of the workload"""
     from oracle import binding as ob
     from sparkl_b200 import abi
-    threads = ob.set_threads(host_threads())
+    threads = ob.set_threads(host_threads(), fast=True)
     dims = CPU_SAMPLES[config]
     sc, _ = build_scene(0, 1, dims, config)
-    e = ob.OracleEngine(sc.cell_width)
+    e = ob.OracleEngine(sc.cell_width, fast=True)  # liboracle_fast.so: the oracle's source built for speed (f32 SVD and node sums, -O3)
     e.models_upload(sc.models); e.colliders_upload(sc.colliders); e.upload(sc.particles)
     p = abi.SolverParameters(stop_after_one_substep=1)
     for _ in range(warmup):
@@ -191,7 +191,7 @@ def cpu_baseline(steps, warmup, config="S4M"):
         n += t.num_substeps
     dt = time.perf_counter() - t0
     return {"value": sc.num_particles * n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{config} scene at lattice {'x'.join(str(d) for d in dims)} = {sc.num_particles} particles, {n} substeps, oracle/mpm_oracle.cpp (OpenMP, {threads} threads)"}, dt / max(n, 1)
+            "sample": f"{config} scene at lattice {'x'.join(str(d) for d in dims)} = {sc.num_particles} particles, {n} substeps, oracle/mpm_oracle.cpp built for speed (ORC_FAST: f32 Jacobi SVD and node sums, 8-colour block-parallel fused G2P2G, -O3, OpenMP on {threads} threads)"}, dt / max(n, 1)
 
 
 def reference_gpu(sc, settle, steps):

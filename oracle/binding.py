@@ -15,18 +15,35 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
-def build(force: bool = False) -> str:
-    so = os.path.join(_HERE, "liboracle.so")
+def build(force: bool = False, name: str = "liboracle.so") -> str:
+    so = os.path.join(_HERE, name)
     src = os.path.join(_HERE, "mpm_oracle.cpp")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, name], stdout=subprocess.DEVNULL)
     return so
+
+
+_LIB_FAST = None
+
+
+def lib_fast():
+    """liboracle_fast.so: the same source built for speed (ORC_FAST: f32 Jacobi SVD, f32 node sums, -O3) — the CPU ARM of bench.py
+    only; every parity check uses lib()"""
+    global _LIB_FAST
+    if _LIB_FAST is None:
+        _LIB_FAST = _declare_all(C.CDLL(build(name="liboracle_fast.so")))
+    return _LIB_FAST
 
 
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
+        _LIB = _declare_all(C.CDLL(build()))
+    return _LIB
+
+
+def _declare_all(_LIB):
+    if True:
         declare(_LIB, "orc_")
         _LIB.orc_create.argtypes = [C.c_float]
         _LIB.orc_create.restype = C.c_void_p
@@ -55,8 +72,8 @@ def lib():
 
 
 class OracleEngine(Engine):
-    def __init__(self, cell_width: float):
-        l = lib()
+    def __init__(self, cell_width: float, fast: bool = False):
+        l = lib_fast() if fast else lib()
         super().__init__(l, "orc_", C.c_void_p(l.orc_create(cell_width)))
         self.cell_width = cell_width
         self.device = -1
@@ -77,8 +94,8 @@ class OracleEngine(Engine):
         return sim.value, t
 
 
-def set_threads(n: int) -> int:
-    return lib().orc_set_threads(n)
+def set_threads(n: int, fast: bool = False) -> int:
+    return (lib_fast() if fast else lib()).orc_set_threads(n)
 
 
 def svd3(F: np.ndarray):

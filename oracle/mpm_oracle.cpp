@@ -129,59 +129,71 @@ static inline Real inv_exact(Real e) { return e == 0.0f ? 0.0f : 1.0f / e; }
 // Stand-in for nalgebra 0.32.1 `svd_unordered(true,true)` (call sites: elasticity_corotated_linear.rs:38,88,107,
 // plasticity_drucker_prager.rs:80, plasticity_nacc.rs:71, plasticity_rankine.rs:43, plasticity_snow.rs:36).
 // One-sided Jacobi (Hestenes) in double; singular values are non-negative and unordered, U/V orthogonal.
+// ORC_FAST (liboracle_fast.so, the CPU ARM of bench.py only — never the checker): the same algorithm compiled for speed: f32 Jacobi with
+// an f32 stopping rule instead of the f64 iteration to round-off, f32 node sums, -O3 -march=x86-64-v3.  What a competently written CPU
+// path of the reference does (its own SVDs are nalgebra's f32 ones); the parity tests always use the accurate build.
+#ifdef ORC_FAST
+typedef float SvdReal;
+#define ORC_SVD_TOL 1e-7f
+typedef float AccReal;
+#else
+typedef double SvdReal;
+#define ORC_SVD_TOL 1e-17
+typedef double AccReal;
+#endif
 struct Svd3 { M3 u; V3 s; M3 vt; };
 static Svd3 svd_unordered(const M3& a) {
-    double U[3][3], V[3][3];
+    SvdReal U[3][3], V[3][3];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { U[r][c] = a(r, c); V[r][c] = (r == c) ? 1.0 : 0.0; }
     for (int sweep = 0; sweep < 60; ++sweep) {
         bool rotated = false;
         for (int p = 0; p < 2; ++p)
             for (int q = p + 1; q < 3; ++q) {
-                double alpha = 0, beta = 0, gamma = 0;
+                SvdReal alpha = 0, beta = 0, gamma = 0;
                 for (int r = 0; r < 3; ++r) { alpha += U[r][p] * U[r][p]; beta += U[r][q] * U[r][q]; gamma += U[r][p] * U[r][q]; }
-                if (gamma == 0.0 || std::fabs(gamma) <= 1e-17 * std::sqrt(alpha * beta)) continue;
+                if (gamma == 0 || std::fabs(gamma) <= (SvdReal)ORC_SVD_TOL * std::sqrt(alpha * beta)) continue;
                 rotated = true;
-                double zeta = (beta - alpha) / (2.0 * gamma);
-                double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
-                double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+                SvdReal zeta = (beta - alpha) / (2 * gamma);
+                SvdReal t = (zeta >= 0 ? (SvdReal)1 : (SvdReal)-1) / (std::fabs(zeta) + std::sqrt(1 + zeta * zeta));
+                SvdReal c = 1 / std::sqrt(1 + t * t), s = c * t;
                 for (int r = 0; r < 3; ++r) {
-                    double up = U[r][p], uq = U[r][q];
+                    SvdReal up = U[r][p], uq = U[r][q];
                     U[r][p] = c * up - s * uq; U[r][q] = s * up + c * uq;
-                    double vp = V[r][p], vq = V[r][q];
+                    SvdReal vp = V[r][p], vq = V[r][q];
                     V[r][p] = c * vp - s * vq; V[r][q] = s * vp + c * vq;
                 }
             }
         if (!rotated) break;
     }
-    double sig[3];
+    SvdReal sig[3];
     bool ok[3];
-    double smax = 0;
+    SvdReal smax = 0;
     for (int c = 0; c < 3; ++c) { sig[c] = std::sqrt(U[0][c] * U[0][c] + U[1][c] * U[1][c] + U[2][c] * U[2][c]); smax = std::max(smax, sig[c]); }
     for (int c = 0; c < 3; ++c) {
-        ok[c] = sig[c] > 1e-300 && sig[c] > 1e-14 * smax;
+        ok[c] = sig[c] > (SvdReal)(sizeof(SvdReal) == 8 ? 1e-300 : 1e-37) && sig[c] > (SvdReal)(sizeof(SvdReal) == 8 ? 1e-14 : 1e-7) * smax;
         if (ok[c]) for (int r = 0; r < 3; ++r) U[r][c] /= sig[c];
     }
     // complete U to an orthonormal basis where a singular value vanished
     for (int c = 0; c < 3; ++c) {
         if (ok[c]) continue;
         int a1 = (c + 1) % 3, a2 = (c + 2) % 3;
-        double w[3] = {0, 0, 0};
+        SvdReal w[3] = {0, 0, 0};
         if (ok[a1] && ok[a2]) {
             w[0] = U[1][a1] * U[2][a2] - U[2][a1] * U[1][a2];
             w[1] = U[2][a1] * U[0][a2] - U[0][a1] * U[2][a2];
             w[2] = U[0][a1] * U[1][a2] - U[1][a1] * U[0][a2];
         } else {
             // pick any unit vector orthogonal to the valid columns (Gram-Schmidt over the canonical basis)
-            double best = -1;
+            SvdReal best = -1;
             for (int e = 0; e < 3; ++e) {
-                double cand[3] = {0, 0, 0};
-                cand[e] = 1.0;
+                SvdReal cand[3] = {0, 0, 0};
+                cand[e] = 1;
                 for (int k = 0; k < 3; ++k) {
                     if (k == c || !ok[k]) continue;
-                    double d = cand[0] * U[0][k] + cand[1] * U[1][k] + cand[2] * U[2][k];
+                    SvdReal d = cand[0] * U[0][k] + cand[1] * U[1][k] + cand[2] * U[2][k];
                     for (int r = 0; r < 3; ++r) cand[r] -= d * U[r][k];
                 }
-                double n = std::sqrt(cand[0] * cand[0] + cand[1] * cand[1] + cand[2] * cand[2]);
+                SvdReal n = std::sqrt(cand[0] * cand[0] + cand[1] * cand[1] + cand[2] * cand[2]);
                 if (n > best) { best = n; for (int r = 0; r < 3; ++r) w[r] = cand[r] / n; }
             }
         }
@@ -588,7 +600,7 @@ static inline V3 dir_to_associated_grid_node(const float p[3], Real h) {
 
 struct TileCell { // GridGatherData, g2p2g.rs:22-40 (fields the default updater consumes)
     V3 velocity; Real psi_velocity;
-    double mass, momentum[3], psi_momentum, psi_mass; // accumulators
+    AccReal mass, momentum[3], psi_momentum, psi_mass; // accumulators
 };
 
 // DefaultParticleUpdater::update_particle_and_compute_kirchhoff_stress, src_kernels/cuda/particle_updater.rs:73-236
@@ -684,10 +696,10 @@ static void particle_g2p2g(const orc_ctx& ctx, Real dt, uint32_t pid, SpkParticl
         if (ci < 0 || ci >= 512) continue; // cannot happen after the velocity clamp (|dx| < h); guards NaN inputs
         TileCell& cell = tile[ci];
         V3 am = weight * (affine * dpt + momentum);
-        cell.mass += (double)(weight * vol.mass);
-        cell.momentum[0] += (double)am.x; cell.momentum[1] += (double)am.y; cell.momentum[2] += (double)am.z;
-        cell.psi_momentum += (double)(weight * psi_pos_mom);
-        cell.psi_mass += (double)(weight * psi_mass);
+        cell.mass += (AccReal)(weight * vol.mass);
+        cell.momentum[0] += (AccReal)am.x; cell.momentum[1] += (AccReal)am.y; cell.momentum[2] += (AccReal)am.z;
+        cell.psi_momentum += (AccReal)(weight * psi_pos_mom);
+        cell.psi_mass += (AccReal)(weight * psi_mass);
     }
 }
 
@@ -1177,7 +1189,7 @@ int orc_stage_g2p2g(orc_ctx* c, float dt, uint32_t damage_model) {
     Grid& next = c->next_grid();
     const Grid& curr = c->curr_grid();
     const size_t nab = next.headers.size();
-    std::vector<double> acc(nab * 64 * 6, 0.0);
+    std::vector<AccReal> acc(nab * 64 * 6, (AccReal)0);
     // 8 colours by block-coordinate parity: two blocks of one colour never write the same node (a block writes b + {0,1}^3)
     std::vector<std::vector<uint32_t>> colours(8);
     for (size_t b = 0; b < nab; ++b) {
@@ -1226,13 +1238,13 @@ int orc_stage_g2p2g(orc_ctx* c, float dt, uint32_t damage_model) {
                 for (int o = 0; o < 8; ++o) {
                     int ox = o & 1, oy = (o >> 1) & 1, oz = (o >> 2) & 1;
                     if (oct_next[o] < 0) continue; // the reference unwrap()s: cannot be missing after touch_particle_blocks
-                    double* a = &acc[(size_t)oct_next[o] * 64 * 6];
+                    AccReal* a = &acc[(size_t)oct_next[o] * 64 * 6];
                     for (int id = 0; id < 64; ++id) {
                         int sx = id & 3, sy = (id >> 2) & 3, sz = id >> 4;
                         const TileCell& t = tile[(ox * 4 + sx) + (oy * 4 + sy) * 8 + (oz * 4 + sz) * 64];
-                        a[id * 6 + 0] += (double)ftz((Real)t.mass); a[id * 6 + 1] += (double)ftz((Real)t.momentum[0]);
-                        a[id * 6 + 2] += (double)ftz((Real)t.momentum[1]); a[id * 6 + 3] += (double)ftz((Real)t.momentum[2]);
-                        a[id * 6 + 4] += (double)ftz((Real)t.psi_momentum); a[id * 6 + 5] += (double)ftz((Real)t.psi_mass);
+                        a[id * 6 + 0] += (AccReal)ftz((Real)t.mass); a[id * 6 + 1] += (AccReal)ftz((Real)t.momentum[0]);
+                        a[id * 6 + 2] += (AccReal)ftz((Real)t.momentum[1]); a[id * 6 + 3] += (AccReal)ftz((Real)t.momentum[2]);
+                        a[id * 6 + 4] += (AccReal)ftz((Real)t.psi_momentum); a[id * 6 + 5] += (AccReal)ftz((Real)t.psi_mass);
                     }
                 }
             }
