@@ -12,7 +12,7 @@ label = sys.argv[1] if len(sys.argv) > 1 else "run"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 settle = int(sys.argv[3]) if len(sys.argv) > 3 else 120
 dims = tuple(int(x) for x in sys.argv[4:7]) if len(sys.argv) > 6 else bench.FULL
-sc = bench.build_scene(0, 1, dims)
+sc, _ = bench.build_scene(0, 1, dims)
 ctx = context_from_scene(sc, device=0)
 params = abi.SolverParameters(stop_after_one_substep=1)
 out = {"label": label, "mode": os.environ.get("SPK_G2P2G_MODE", "default"), "lib": os.path.basename(os.environ.get("SPK_LIB_PATH", "default"))}

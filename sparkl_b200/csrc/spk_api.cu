@@ -422,6 +422,11 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     if (const char* m = getenv("SPK_G2P2G_MODE")) { const int v = atoi(m); c->g2p2g_mode = v < 0 ? 0 : (v > 2 ? 2 : v); }
     if (c->g2p2g_mode == 2) c->chunk = 512;
     c->g2p2g_specialize = getenv("SPK_G2P2G_GENERIC") ? 0 : 1;
+    // persistent CTAs that prefetch their next entry (kept for A/B: SPK_G2P2G_STREAM=1).  Measured slower on the B200 (0.88 vs 0.68 ms on the 4 M
+    // sand scene): the two CTAs of an SM fall into step, so their LSU-bound P2G phases and their FMA-bound update phases no longer
+    // overlap, and the entry loop costs ~5 live registers the 64-register body does not have (profiles/r2_g2p2g_experiments.md)
+    c->g2p2g_stream = 0;
+    if (const char* m = getenv("SPK_G2P2G_STREAM")) c->g2p2g_stream = atoi(m) ? 1 : 0;
 #else
     c->g2p2g_mode = 1;
 #endif

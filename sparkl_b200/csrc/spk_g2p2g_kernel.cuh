@@ -477,14 +477,8 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
 //     in-CTA cell sort, which only moves 16-bit slot numbers);
 //   * the per-CTA fixed work (tile staging, zeroing, scan, flush: 8 TMA loads + 8 TMA reduce-adds) is paid once per 512 particles and
 //     the P2G bins hold twice the particles of a 256-particle chunk (the per-bin flush is the expensive part of P2G).
-#ifndef SPK_P2G_TRIPLE
-#define SPK_P2G_TRIPLE 0 /* 1: P2G work items are triples of x-neighbouring bins with a sliding window (5 node flushes per triple) */
-#endif
 #ifndef SPK_PSI_SHARE
 #define SPK_PSI_SHARE 1 /* 1: a CTA whose particles all have psi_mass == mass accumulates the mass channel once and flushes it twice */
-#endif
-#ifndef SPK_P2G_PREFETCH
-#define SPK_P2G_PREFETCH 0
 #endif
 #ifndef SPK_CELL_MIN_CTAS
 #define SPK_CELL_MIN_CTAS 2
@@ -504,6 +498,13 @@ constexpr int CS_MISC = CS_SORTED + C_THREADS * 2;           // mbarrier (8) + n
 constexpr int CS_HALO = CS_MISC + 8 + 32 + 32 + 16;
 constexpr int CS_WTOT = CS_HALO + 32;                        // int2[8]: per-warp totals of the bin scan
 constexpr int CS_TOTAL = CS_WTOT + 64;
+// the streaming variant (one CTA walks many dispatch entries): a second accumulation tile (the flush of entry k is still being read
+// by the TMA engine while entry k + 1 accumulates) and the prefetched dispatch record of the next entry
+constexpr int CS_ENTN = (CS_TOTAL + 127) / 128 * 128;                            // DispatchEntry (16) + int[16] block ids of the next entry's tile
+constexpr int CS_ACC2 = CS_ENTN + 128;                       // float[8][6][64]
+constexpr int CS_PARAMS = CS_ACC2 + 8 * 6 * 64 * 4;          // G2P2GParams (the kernel parameters, see the top of the kernel)
+constexpr int CS_TOTAL_STREAM = CS_PARAMS + 384;
+static_assert(CS_ENTN % 16 == 0 && CS_ACC2 % 128 == 0 && CS_PARAMS % 16 == 0 && sizeof(G2P2GParams) <= 384, "cp.async / TMA alignment of the streaming variant's extra shared memory");
 
 // the velocity gradient of a particle where the cell kernel parks it: G.m[i] = float i of the float4 sequence base[0], base[stride], ...
 struct ParkedGradient {
@@ -517,22 +518,38 @@ struct ParkedGradient {
 #ifdef SPK_EMU
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
 __device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait_group() {}
+__device__ __forceinline__ void tma_commit_group() {}
+template <int N> __device__ __forceinline__ void tma_wait_group_read() {}
 #else
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 #endif
 
-template <class Updater>
-__global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kernel(const G2P2GParams P) {
+// STREAM: the CTA is persistent — it walks the dispatch entries blockIdx.x, blockIdx.x + gridDim.x, ... and, while entry k is in its
+// scan / P2G / flush phases, already brings in entry k + 1: its dispatch record and tile block ids (cp.async at the top of k), its
+// velocity tile (TMA, as soon as every thread has finished G2P of k), the sort permutation and the positions (cp.async into the
+// parking arrays, idle during P2G) and, once the payloads of k are consumed, the record tails.  The ~3 serial memory round trips that
+// open a CTA's life (dispatch -> tile ids -> tile, dispatch -> permutation -> particle) are then paid once per CTA, not once per entry.
+template <class Updater, bool STREAM>
+__global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kernel(const __grid_constant__ G2P2GParams P) {
 #ifdef SPK_EMU
     unsigned char* smem = emu::dynamic_smem();
 #else
     extern __shared__ __align__(128) unsigned char smem[];
 #endif
     float4* s_vel = reinterpret_cast<float4*>(smem + CS_VEL);
-    float* s_acc = reinterpret_cast<float*>(smem + CS_ACC);
+    float* s_acc = reinterpret_cast<float*>(smem + CS_ACC); // (STREAM: re-pointed at the top of every entry)
+    DispatchEntry* s_entn = reinterpret_cast<DispatchEntry*>(smem + CS_ENTN);
+    volatile uint32_t* s_state = reinterpret_cast<volatile uint32_t*>(smem + CS_ENTN + 96); // STREAM: {entry, turn, first particle, count} of the current entry
+    int* s_nbrn = reinterpret_cast<int*>(smem + CS_ENTN + 16);
     float4* s_tail = reinterpret_cast<float4*>(smem + CS_SLOT);                  // [5][512]
     float4* s_park = s_tail + C_TAIL * C_THREADS;                                // [4][512]
     int* s_bin_cnt = reinterpret_cast<int*>(smem + CS_BINCNT);
@@ -550,17 +567,33 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     int2* s_wtot = reinterpret_cast<int2*>(smem + CS_WTOT);
 
     const int tid = threadIdx.x;
-    const DispatchEntry ent = P.dispatch[blockIdx.x];
+    // STREAM: the kernel parameters are read from a shared-memory copy.  Inside the entry loop the compiler would otherwise keep every
+    // pointer of the parameter block in registers across the whole body (loop-invariant loads), i.e. spill them: shared-memory loads
+    // cannot be moved across the barriers of the loop and are re-issued where they are used
+    if (STREAM) {
+        if (tid < (int)(sizeof(G2P2GParams) / 4)) reinterpret_cast<uint32_t*>(smem + CS_PARAMS)[tid] = reinterpret_cast<const uint32_t*>(&P)[tid];
+        __syncthreads();
+    }
+    const G2P2GParams& Q = STREAM ? *reinterpret_cast<const G2P2GParams*>(smem + CS_PARAMS) : P;
+    // the dispatch entry this CTA works on.  STREAM keeps it (and the turn counter) in shared memory, re-read where needed: loop-carried
+    // registers would be live across the whole particle update, which has none to spare
+    const DispatchEntry ent0 = Q.dispatch[blockIdx.x];
+    if (STREAM && tid == 0) { s_state[0] = blockIdx.x; s_state[1] = 0; s_state[2] = ent0.first; s_state[3] = ent0.count; }
+#define CUR_E (STREAM ? s_state[0] : blockIdx.x)
+#define CUR_ITER (STREAM ? s_state[1] : 0u)
+#define CUR_FIRST (STREAM ? s_state[2] : ent0.first)
+#define CUR_COUNT (STREAM ? s_state[3] : ent0.count)
+#define NEXT_VALID (STREAM && CUR_E + gridDim.x < Q.ndispatch)
     // ---- stage 0: velocity tile of the 2x2x2 blocks (transfer_global_blocks_to_shared_memory, g2p2g.rs:353-474).  Warp 0 reads the
     // block ids of the tile (one coalesced 64-byte load that depends on blockIdx only) and launches the 8 TMA bulk copies by itself,
     // before the CTA-wide barrier: the tile travels while the other warps zero the accumulators and fetch their particles
     if (tid < 32) {
         int nid = -1;
         if (tid < 16) {
-            nid = P.dispatch_nbr[(size_t)blockIdx.x * 16 + tid];
+            nid = Q.dispatch_nbr[(size_t)blockIdx.x * 16 + tid];
             s_nbr_self[tid] = nid; // s_nbr_prev follows s_nbr_self
         }
-        if (tid < 8) s_halo[tid] = (P.world > 1 && nid >= 0) ? P.blk_halo[nid] : 0u;
+        if (tid < 8) s_halo[tid] = (Q.world > 1 && nid >= 0) ? Q.blk_halo[nid] : 0u;
         __syncwarp();
         if (tid == 0) {
             mbar_init(s_bar, 1);
@@ -572,32 +605,64 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             fence_proxy_async();
             mbar_expect_tx(s_bar, bytes);
             for (int o = 0; o < 8; ++o)
-                if (s_nbr_prev[o] >= 0) tma_load_1d(&s_vel[o * 64], P.prev_vel + (size_t)s_nbr_prev[o] * 64, 1024u, s_bar);
+                if (s_nbr_prev[o] >= 0) tma_load_1d(&s_vel[o * 64], Q.prev_vel + (size_t)s_nbr_prev[o] * 64, 1024u, s_bar);
         }
     }
-    const bool has_particle = (uint32_t)tid < ent.count;
+    bool has_particle = (uint32_t)tid < ent0.count;
     float4* const tail = s_tail + tid; // tail[k * C_THREADS]: a(k+1) of this particle, later payload vector k
     float4* const park = s_park + tid;
     // ---- the particle: position now (registers), the rest of the record on its way into the slot (cp.async, no registers)
     float x[3] = {0.f, 0.f, 0.f};
     uint32_t flags = 0;
     if (has_particle) {
-        const uint32_t si = P.perm[ent.first + tid];
-        cp_async16(tail + 0 * C_THREADS, &P.src.a1[si]);
-        cp_async16(tail + 1 * C_THREADS, &P.src.a2[si]);
-        cp_async16(tail + 2 * C_THREADS, &P.src.a3[si]);
-        cp_async16(tail + 3 * C_THREADS, &P.src.a4[si]);
-        cp_async16(tail + 4 * C_THREADS, &P.src.a5[si]);
-        const float4 r0 = P.src.a0[si];
+        const uint32_t si = Q.perm[ent0.first + tid];
+        cp_async16(tail + 0 * C_THREADS, &Q.src.a1[si]);
+        cp_async16(tail + 1 * C_THREADS, &Q.src.a2[si]);
+        cp_async16(tail + 2 * C_THREADS, &Q.src.a3[si]);
+        cp_async16(tail + 3 * C_THREADS, &Q.src.a4[si]);
+        cp_async16(tail + 4 * C_THREADS, &Q.src.a5[si]);
+        const float4 r0 = Q.src.a0[si];
         x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; flags = __float_as_uint(r0.w);
     }
-    for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64 / 4; i += C_THREADS) reinterpret_cast<float4*>(s_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (STREAM) cp_async_commit(); // group "tails of the first entry"
+    for (int i = tid; i < (STREAM ? 2 : 1) * 8 * SPK_ACC_CHANNELS * 64 / 4; i += C_THREADS) {
+        float4* a = reinterpret_cast<float4*>(i < 768 ? smem + CS_ACC : smem + CS_ACC2 - 768 * 16);
+        a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (tid < 224) s_bin_cnt[tid] = 0;
-    __syncthreads();
-    if (s_nbr_prev[tid >> 6] < 0) s_vel[tid] = make_float4(0.f, 0.f, 0.f, 0.f); // blocks absent from the previous grid read as zero
 
-    const float h = P.h, inv_h = P.inv_h, dt = P.dt;
+    const float h = Q.h, inv_h = Q.inv_h, dt = Q.dt;
     const float inv_d = 4.f / (h * h);
+
+#pragma unroll 1
+    for (;;) { // ================================================================ one dispatch entry per turn (!STREAM: exactly one turn)
+    __syncthreads();
+    const uint32_t iter = CUR_ITER;
+    if (STREAM) {
+        s_acc = reinterpret_cast<float*>(smem + ((iter & 1u) ? CS_ACC2 : CS_ACC));
+        has_particle = (uint32_t)tid < CUR_COUNT;
+    }
+    if (s_nbr_prev[tid >> 6] < 0) s_vel[tid] = make_float4(0.f, 0.f, 0.f, 0.f); // blocks absent from the previous grid read as zero
+    if (STREAM) {
+        // the dispatch record of the next entry (5 x 16 bytes), on its way while this entry is updated
+        if (tid < 5 && NEXT_VALID) {
+            const uint32_t e_next = CUR_E + gridDim.x;
+            if (tid == 0) cp_async16(s_entn, &Q.dispatch[e_next]);
+            else cp_async16(s_nbrn + 4 * (tid - 1), &Q.dispatch_nbr[(size_t)e_next * 16 + 4 * (tid - 1)]);
+        }
+        cp_async_commit(); // group "next record" (empty for most threads: every thread commits the same sequence of groups)
+        // this turn's accumulation tile was flushed two turns ago; thread 0 made sure at the end of the last turn that the TMA engine
+        // has read it (the first two turns use the tiles zeroed in the prologue)
+        if (iter >= 2)
+            for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64 / 4; i += C_THREADS) reinterpret_cast<float4*>(s_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (STREAM && iter > 0) {
+        // position and flags of this entry's particle were prefetched into the first parking array during the previous P2G
+        cp_async_wait_group<2>(); // all but the two youngest groups ("tails of this entry", "next record"): the positions have landed
+        const float4 r0 = park[0];
+        x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; flags = __float_as_uint(r0.w);
+        if (!has_particle) { x[0] = x[1] = x[2] = 0.f; flags = 0; }
+    }
 
     int tcell[3] = {1, 1, 1};
     float cell_before[3] = {0.f, 0.f, 0.f};
@@ -611,13 +676,13 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         const int assoc_cell = (q != q) ? -2 : (int)__float2ll_rz(q) - 2;
         tcell[a] = (assoc_cell & 3) + 1;                 // associated_cell_index_in_block_off_by_two, particle.rs:28-35
     }
-    mbar_wait(s_bar, 0); // the tile is complete (TMA) ...
-    __syncthreads();     // ... and the absent octants are zero-filled
+    mbar_wait(s_bar, iter & 1u); // the tile is complete (TMA) ...
+    __syncthreads();             // ... and the absent octants are zero-filled
 
     int bin = NBINS;
     unsigned cand_bits = SPK_DT_RAW_NONE;
     if (has_particle) {
-        const DevModel& model = P.models[flags >> SPK_F_MODEL_SHIFT];
+        const DevModel& model = Q.models[flags >> SPK_F_MODEL_SHIFT];
         float vel[3];
         Mat3 G;
         // ---- G2P (particle_g2p2g, g2p2g.rs:192-245): rows along x are accumulated separably, then folded into the 12 sums
@@ -652,7 +717,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             }
         }
         cp_async_wait_all(); // this thread's record tail is in its slot
-        const uint32_t di = ent.first + (uint32_t)tid; // slot order == sorted order of this substep; the next sort re-orders by cell
+        const uint32_t di = CUR_FIRST + (uint32_t)tid; // slot order == sorted order of this substep; the next sort re-orders by cell
         ParticleState p;
         p.x[0] = x[0]; p.x[1] = x[1]; p.x[2] = x[2]; p.flags = flags;
         Mat3 stress = mat_zero();
@@ -667,7 +732,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                 p.F.m[8] = tail[2 * C_THREADS].x;
                 p.orig_id = __float_as_uint(tail[4 * C_THREADS].z);
             }
-            Updater::advect(model, P.cold, h, dt, p, vel, G, P.user);
+            Updater::advect(model, Q.cold, h, dt, p, vel, G, Q.user);
             bool inside = true;
             int t2[3];
 #pragma unroll
@@ -680,8 +745,8 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                 inside = inside && t2[a] >= 0 && t2[a] <= 5;
             }
             if (inside) bin = t2[0] + 6 * t2[1] + 36 * t2[2];
-            P.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
-            P.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
+            Q.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
+            Q.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
             park[0] = make_float4(G.m[0], G.m[1], G.m[2], G.m[3]);
             park[C_THREADS] = make_float4(G.m[4], G.m[5], G.m[6], G.m[7]);
             park[2 * C_THREADS] = make_float4(G.m[8], vel[0], vel[1], vel[2]);
@@ -689,7 +754,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             spk_compiler_fence();
             // phase 2: the decomposition, alone in the register file
             Svd3 svd;
-            if (Updater::needs_decomposition(model)) svd = Updater::decompose(model, p.F, P.user);
+            if (Updater::needs_decomposition(model)) svd = Updater::decompose(model, p.F, Q.user);
             spk_compiler_fence();
             // phase 3: plasticity, failure, energies, stress on the scalars of the record (read from the slot only now)
             {
@@ -699,8 +764,8 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                 p.log_vol_gain = r5.x; p.nacc_alpha = r5.y; p.orig_id = __float_as_uint(r5.z);
             }
             const uint32_t flags0 = p.flags;
-            do_p2g = Updater::constitutive(model, p, svd, ParkedGradient{park}, stress, P.user);
-            if (p.flags != flags0) P.dst.a0[di].w = __uint_as_float(p.flags); // the particle failed in phase 3 (rare)
+            do_p2g = Updater::constitutive(model, p, svd, ParkedGradient{park}, stress, Q.user);
+            if (p.flags != flags0) Q.dst.a0[di].w = __uint_as_float(p.flags); // the particle failed in phase 3 (rare)
             spk_compiler_fence();
             {
                 const float4 g0 = park[0], g1 = park[C_THREADS], g2 = park[2 * C_THREADS], g3 = park[3 * C_THREADS];
@@ -717,7 +782,7 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                 p.phase = r4.x; p.psi_pos = r4.y; p.elastic_hardening = r4.z; p.plastic_hardening = r4.w;
                 p.log_vol_gain = r5.x; p.nacc_alpha = r5.y; p.orig_id = __float_as_uint(r5.z);
             }
-            do_p2g = Updater::update(model, P.cold, h, dt, p, vel, G, stress, P.user);
+            do_p2g = Updater::update(model, Q.cold, h, dt, p, vel, G, stress, Q.user);
             bool inside = true;
             int t2[3];
 #pragma unroll
@@ -730,21 +795,21 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                 inside = inside && t2[a] >= 0 && t2[a] <= 5;
             }
             if (inside) bin = t2[0] + 6 * t2[1] + 36 * t2[2];
-            P.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
-            P.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
+            Q.dst.a0[di] = make_float4(p.x[0], p.x[1], p.x[2], __uint_as_float(p.flags));
+            Q.vel_out[di] = make_float4(vel[0], vel[1], vel[2], 0.f);
         }
         if (!do_p2g) bin = NBINS;
         // ---- fused K15 (timestep.rs:38-113): un-clamped dt candidate of this particle for the NEXT substep; the clamps and the
         // fixed-point conversion are monotone, so they are applied once to the reduced value (spk_stage_estimate_dt)
         if (!(p.flags & SPK_F_FAILED)) {
-            const float cand = Updater::dt_candidate(model, h, p, vel, P.user);
+            const float cand = Updater::dt_candidate(model, h, p, vel, Q.user);
             cand_bits = __float_as_uint(cand != cand ? 1.0e30f : fminf(fmaxf(cand, 0.f), 1.0e30f)); // NaN imposes no bound (Rust f32::min ignores NaN)
         }
-        P.dst.a1[di] = make_float4(p.F.m[0], p.F.m[1], p.F.m[2], p.F.m[3]);
-        P.dst.a2[di] = make_float4(p.F.m[4], p.F.m[5], p.F.m[6], p.F.m[7]);
-        P.dst.a3[di] = make_float4(p.F.m[8], p.jp, p.mass, p.volume0);
-        P.dst.a4[di] = make_float4(p.phase, p.psi_pos, p.elastic_hardening, p.plastic_hardening);
-        P.dst.a5[di] = make_float4(p.log_vol_gain, p.nacc_alpha, __uint_as_float(p.orig_id), 0.f);
+        Q.dst.a1[di] = make_float4(p.F.m[0], p.F.m[1], p.F.m[2], p.F.m[3]);
+        Q.dst.a2[di] = make_float4(p.F.m[4], p.F.m[5], p.F.m[6], p.F.m[7]);
+        Q.dst.a3[di] = make_float4(p.F.m[8], p.jp, p.mass, p.volume0);
+        Q.dst.a4[di] = make_float4(p.phase, p.psi_pos, p.elastic_hardening, p.plastic_hardening);
+        Q.dst.a5[di] = make_float4(p.log_vol_gain, p.nacc_alpha, __uint_as_float(p.orig_id), 0.f);
         // ---- P2G payload (overwrites the record tail in the slot)
         //   q0 = {m, c.xyz}  c = A ref2 + m v        q1 = {h A[:,0], psi_mass}   q2 = {h A[:,1], psi_mom}   q3 = {h A[:,2], fy}
         //   q4 = {wx0, wx1, wx2, fz}                 A = m G - (volume0 inv_d dt) stress,  fy / fz: B-spline arguments along y / z
@@ -772,58 +837,24 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     if ((tid & 31) == 0 && cand_bits < SPK_DT_RAW_NONE) atomicMin(s_dtmin, cand_bits);
     int rank = 0;
     if (has_particle) rank = atomicAdd(&s_bin_cnt[bin], 1);
+    if (STREAM && tid < 5) cp_async_wait_all(); // the next entry's dispatch record is in shared memory (its 5 loaders make sure)
     __syncthreads();
-
-#if SPK_P2G_TRIPLE
-    // ---- counting sort of the slots by stencil-base cell (bin 216 = particles without P2G): exclusive scan of the 217 counters by
-    // 7 warps (one bin per thread: warp scan, then the per-warp totals), and the list of the occupied bin TRIPLES (three x-neighbours
-    // 3t, 3t+1, 3t+2 of one (y, z) row: the work items of P2G) in bin order
-    {
-        const int lane = tid & 31, warp = tid >> 5;
-        int c = 0, inc = 0;
-        if (tid < 224) {
-            c = s_bin_cnt[tid];
-            inc = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            if (lane == 31) s_wtot[warp].x = inc;
+    // ---- STREAM: every thread is done with the velocity tile -> the next entry's tile may overwrite it; its particles are looked up
+    uint32_t si_next = 0;
+    bool has_next = false;
+    if (NEXT_VALID) {
+        if (tid == 0) {
+            uint32_t bytes = 0;
+            for (int o = 0; o < 8; ++o) bytes += s_nbrn[8 + o] >= 0 ? 1024u : 0u;
+            fence_proxy_async();
+            mbar_expect_tx(s_bar, bytes);
+            for (int o = 0; o < 8; ++o)
+                if (s_nbrn[8 + o] >= 0) tma_load_1d(&s_vel[o * 64], Q.prev_vel + (size_t)s_nbrn[8 + o] * 64, 1024u, s_bar);
         }
-        if (tid >= 224 && tid < 256) { // warp 7: 72 triples, three per lane
-            int n = 0;
-            unsigned occ = 0;
-            if (lane < 24) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int t = lane * 3 + k;
-                    if (s_bin_cnt[3 * t] + s_bin_cnt[3 * t + 1] + s_bin_cnt[3 * t + 2] != 0) { occ |= 1u << k; ++n; }
-                }
-            }
-            int pre = n;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, pre, d);
-                if (lane >= d) pre += o;
-            }
-            if (lane == 31) *s_nnz = pre;
-            pre -= n;
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (occ >> k & 1u) s_binlist[pre++] = (unsigned short)(lane * 3 + k);
-        }
-        __syncthreads();
-        if (tid < 224) {
-            int base = 0;
-#pragma unroll
-            for (int wv = 0; wv < 6; ++wv)
-                if (wv < warp) base += s_wtot[wv].x;
-            s_bin_start[tid] = base + inc - c;
-        }
+        has_next = (uint32_t)tid < s_entn->count;
+        if (has_next) si_next = Q.perm[s_entn->first + tid];
     }
-    __syncthreads();
-#else
+
     // ---- counting sort of the slots by stencil-base cell (bin 216 = particles without P2G): exclusive scan of the 217 counters by
     // 7 warps (one bin per thread: warp scan, then the per-warp totals), and the list of the occupied bins in bin order
     {
@@ -857,97 +888,17 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         }
     }
     __syncthreads();
-#endif
     if (has_particle) s_sorted[s_bin_start[bin] + rank] = (unsigned short)tid;
+    if (STREAM) { // the parking arrays are idle from here to the next entry's update: they receive its positions and keep its permutation
+        if (has_next) {
+            cp_async16(park, &Q.src.a0[si_next]);
+            reinterpret_cast<uint32_t*>(park + C_THREADS)[0] = si_next;
+        }
+        reinterpret_cast<uint32_t*>(park + C_THREADS)[1] = has_next ? 1u : 0u;
+        cp_async_commit(); // group "positions of the next entry"
+    }
     __syncthreads();
 
-#if SPK_P2G_TRIPLE
-    // ---- stage 2: 9-lane groups, one occupied bin triple at a time; lane = stencil column (sy, sz).  The group walks the three bins
-    // along x with a sliding window of 3 nodes x 6 channels in registers (payload reads are broadcasts): after bin j the node
-    // x0 + j is complete for this triple and is added to the tile, the window moves on by one node.  5 node flushes per triple
-    // instead of 9 (the shared float atomics of the flush are the most expensive instructions of the kernel).
-    {
-        const int lane = tid & 31;
-        const int grp = lane / 9, l9 = lane - grp * 9;
-        const int sy = l9 % 3, sz = l9 / 3;
-        const float fsy = (float)sy, fsz = (float)sz;
-        // QuadraticKernel::eval_all (kernel.rs:15-21) for ONE node: w_s(x) = A_s (x - B_s)^2 + C_s
-        const float Ay = sy == 1 ? -1.f : 0.5f, By = sy == 0 ? 1.5f : (sy == 1 ? 1.f : 0.5f), Cy = sy == 1 ? 0.75f : 0.f;
-        const float Az = sz == 1 ? -1.f : 0.5f, Bz = sz == 0 ? 1.5f : (sz == 1 ? 1.f : 0.5f), Cz = sz == 1 ? 0.75f : 0.f;
-        const int nnz = *s_nnz;
-        const bool psi_generic = *s_psi_generic != 0; // see the bin-level variant
-        if (grp < 3) {
-            for (;;) { // a warp takes the next three occupied triples until the list is exhausted
-                // (the three triples of a pass are taken a third of the list apart: neighbouring rows would add into the same nodes in
-                // the same instruction, and same-address shared atomics serialise)
-                const int third = (nnz + 2) / 3;
-                int e = 0;
-                if (lane == 0) e = atomicAdd(s_next, 1);
-                e = __shfl_sync(0x07ffffffu, e, 0);
-                if (e >= third) break;
-                e += grp * third;
-                if (e >= nnz) continue;
-                const int t = s_binlist[e];
-                const int x0 = 3 * (t & 1), byc = (t >> 1) % 6, bzc = t / 12;
-                const int byz = cell_part(byc + sy, 1) + oct_part(byc + sy, 1) * 384 + cell_part(bzc + sz, 2) + oct_part(bzc + sz, 2) * 384;
-                const int zsw = (bzc + sz) & 2; // SPK_ACC_SWZ: bit 1 of the node's z inside its block flips bit 1 of its x
-                float acc[3][6];
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-#pragma unroll
-                    for (int ch = 0; ch < 6; ++ch) acc[k][ch] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 5; ++j) { // j < 3: accumulate bin 3t + j, then flush node x0 + j; j = 3, 4: the two nodes left in the window
-                    if (j < 3) {
-                        const int start = s_bin_start[3 * t + j], cnt = s_bin_cnt[3 * t + j];
-#if SPK_P2G_PREFETCH
-                        int idx = cnt > 0 ? s_sorted[start] : 0;
-#endif
-                        for (int i = 0; i < cnt; ++i) {
-#if SPK_P2G_PREFETCH
-                            const float4* pay = s_tail + idx;
-#else
-                            const float4* pay = s_tail + s_sorted[start + i];
-#endif
-                            const float4 q0 = pay[0], q1 = pay[C_THREADS], q2 = pay[2 * C_THREADS], q3 = pay[3 * C_THREADS], q4 = pay[4 * C_THREADS];
-#if SPK_P2G_PREFETCH
-                            if (i + 1 < cnt) idx = s_sorted[start + i + 1];
-#endif
-                            const float dy = q3.w - By, dz = q4.w - Bz;
-                            const float wyz = fmaf(Ay * dy, dy, Cy) * fmaf(Az * dz, dz, Cz);
-                            // node momentum contribution at sx = 0: c + sy * hA[:,1] + sz * hA[:,2]
-                            float bx = q0.y + fsy * q2.x + fsz * q3.x, by = q0.z + fsy * q2.y + fsz * q3.y, bz = q0.w + fsy * q2.z + fsz * q3.z;
-                            const float wx[3] = {q4.x, q4.y, q4.z};
-#pragma unroll
-                            for (int sx = 0; sx < 3; ++sx) {
-                                float* a = acc[(j + sx) % 3];
-                                const float wt = wx[sx] * wyz;
-                                a[0] += wt * q0.x;
-                                a[1] += wt * bx; a[2] += wt * by; a[3] += wt * bz;
-                                a[4] += wt * q2.w;
-                                if (psi_generic) a[5] += wt * q1.w;
-                                bx += q1.x; by += q1.y; bz += q1.z;
-                            }
-                        }
-                    }
-                    float* a = acc[j % 3];
-                    if (a[0] != 0.f) { // a node that received nothing keeps an exact zero mass (all weights are positive)
-                        float* n = &s_acc[byz + (cell_part(x0 + j, 0) ^ zsw) + oct_part(x0 + j, 0) * 384];
-                        atomicAdd(n + 0 * 64, a[0]);
-                        atomicAdd(n + 1 * 64, a[1]);
-                        atomicAdd(n + 2 * 64, a[2]);
-                        atomicAdd(n + 3 * 64, a[3]);
-                        if (a[4] != 0.f) atomicAdd(n + 4 * 64, a[4]);
-                        if (psi_generic && a[5] != 0.f) atomicAdd(n + 5 * 64, a[5]);
-                    }
-#pragma unroll
-                    for (int ch = 0; ch < 6; ++ch) a[ch] = 0.f;
-                }
-            }
-        }
-    }
-
-#else
     // ---- stage 2: 9-lane groups, one occupied bin at a time; lane = stencil column (sy, sz), 3 nodes (sx = 0..2) x 6 channels in
     // registers over the bin's particles (payload reads are broadcasts), then one flush of the 18 sums into the tile
     {
@@ -973,19 +924,9 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
                 const int start = s_bin_start[b], cnt = s_bin_cnt[b];
                 float aM[3] = {0.f, 0.f, 0.f}, aX[3] = {0.f, 0.f, 0.f}, aY[3] = {0.f, 0.f, 0.f}, aZ[3] = {0.f, 0.f, 0.f}, aPm[3] = {0.f, 0.f, 0.f},
                       aPp[3] = {0.f, 0.f, 0.f};
-#if SPK_P2G_PREFETCH
-                int idx = s_sorted[start];
-#endif
                 for (int i = 0; i < cnt; ++i) {
-#if SPK_P2G_PREFETCH
-                    const float4* pay = s_tail + idx;
-#else
                     const float4* pay = s_tail + s_sorted[start + i];
-#endif
                     const float4 q0 = pay[0], q1 = pay[C_THREADS], q2 = pay[2 * C_THREADS], q3 = pay[3 * C_THREADS], q4 = pay[4 * C_THREADS];
-#if SPK_P2G_PREFETCH
-                    if (i + 1 < cnt) idx = s_sorted[start + i + 1];
-#endif
                     const float dy = q3.w - By, dz = q4.w - Bz;
                     const float wyz = fmaf(Ay * dy, dy, Cy) * fmaf(Az * dz, dz, Cz);
                     // node momentum contribution at sx = 0: c + sy * hA[:,1] + sz * hA[:,2]
@@ -1018,7 +959,6 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         }
     }
 
-#endif
     // ---- stage 3: flush the accumulation tile into the next grid (transfer_shared_blocks_to_grid, g2p2g.rs:476-553)
     fence_proxy_async(); // make the generic-proxy smem writes visible to the async (TMA) proxy
     __syncthreads();
@@ -1037,34 +977,81 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         };
         for (int o = 0; o < 8; ++o) {
             const int nid = s_nbr_self[o];
-            if (nid >= 0) reduce_chunk(P.acc + (size_t)nid * (SPK_ACC_CHANNELS * 64), o);
+            if (nid >= 0) reduce_chunk(Q.acc + (size_t)nid * (SPK_ACC_CHANNELS * 64), o);
         }
         bool pushed = false;
-        if (P.world > 1) { // fused halo push (multi-GPU), see g2p2g_kernel
+        if (Q.world > 1) { // fused halo push (multi-GPU), see g2p2g_kernel
             for (int o = 0; o < 8; ++o) {
                 const int nid = s_nbr_self[o];
                 if (nid < 0 || !(s_halo[o] & 1u)) continue;
-                for (uint32_t r = 0; r < P.world; ++r) {
-                    const int32_t pid = P.peer_ids[(size_t)nid * P.world + r];
+                for (uint32_t r = 0; r < Q.world; ++r) {
+                    const int32_t pid = Q.peer_ids[(size_t)nid * Q.world + r];
                     if (pid >= 0) {
-                        reduce_chunk(P.peer_hacc[r] + (size_t)pid * (SPK_ACC_CHANNELS * 64), o);
+                        reduce_chunk(Q.peer_hacc[r] + (size_t)pid * (SPK_ACC_CHANNELS * 64), o);
                         pushed = true;
                     }
                 }
             }
         }
-        if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(P.dt_raw_bits, *s_dtmin);
-        if (pushed && P.push_wait) {
+        if (!STREAM) {
+            if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(Q.dt_raw_bits, *s_dtmin);
+            if (pushed && Q.push_wait) {
 #ifndef SPK_EMU
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #endif
-            __threadfence_system();
+                __threadfence_system();
+            } else {
+                tma_commit_and_wait_read();
+            }
         } else {
-            tma_commit_and_wait_read();
+            // one bulk group per entry; the group of the PREVIOUS entry (the other accumulation tile) must have been read before that
+            // tile is zeroed again at the top of the next turn (and everything must have been read before the CTA retires)
+            tma_commit_group();
+            if (NEXT_VALID) {
+                tma_wait_group_read<1>();
+            } else {
+                if (*s_dtmin < SPK_DT_RAW_NONE) atomicMin(Q.dt_raw_bits, *s_dtmin);
+                if (pushed && Q.push_wait) {
+#ifndef SPK_EMU
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+                    __threadfence_system();
+                } else {
+                    tma_wait_group_read<0>();
+                }
+            }
         }
     }
+    if (!NEXT_VALID) break;
+    // ---- STREAM: the payloads of this entry are consumed; the next entry takes over
+    if (reinterpret_cast<const uint32_t*>(park + C_THREADS)[1]) {
+        const uint32_t si = reinterpret_cast<const uint32_t*>(park + C_THREADS)[0];
+        cp_async16(tail + 0 * C_THREADS, &Q.src.a1[si]);
+        cp_async16(tail + 1 * C_THREADS, &Q.src.a2[si]);
+        cp_async16(tail + 2 * C_THREADS, &Q.src.a3[si]);
+        cp_async16(tail + 3 * C_THREADS, &Q.src.a4[si]);
+        cp_async16(tail + 4 * C_THREADS, &Q.src.a5[si]);
+    }
+    cp_async_commit(); // group "tails of the next entry"
+    if (tid < 224) s_bin_cnt[tid] = 0;
+    if (tid < 32) {
+        __syncwarp(); // thread 0 has issued the flush with this entry's block ids
+        int nid = -1;
+        if (tid < 16) { nid = s_nbrn[tid]; s_nbr_self[tid] = nid; }
+        if (tid < 8) s_halo[tid] = (Q.world > 1 && nid >= 0) ? Q.blk_halo[nid] : 0u;
+        if (tid == 0) { *s_next = 0; *s_psi_generic = 0; }
+    }
+    __syncthreads(); // every thread has read the current entry's state (NEXT_VALID above) before thread 0 moves it on
+    if (tid == 0) { s_state[0] = s_state[0] + gridDim.x; s_state[1] = s_state[1] + 1u; s_state[2] = s_entn->first; s_state[3] = s_entn->count; }
+    } // ======================================================================================================== next dispatch entry
 }
+
+#undef CUR_E
+#undef CUR_ITER
+#undef CUR_FIRST
+#undef CUR_COUNT
+#undef NEXT_VALID
 
 } // namespace spk_g2p2g_detail
 
@@ -1106,7 +1093,8 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
         cudaError_t e = cudaFuncSetAttribute(g2p2g_kernel<0, Updater>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_kernel<1, Updater>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_cell_kernel<Updater>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_cell_kernel<Updater, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_cell_kernel<Updater, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_TOTAL_STREAM);
         if (e != cudaSuccess) return e;
         if (c->device >= 0 && c->device < 64) configured[c->device] = true;
         c->g2p2g_configured = true;
@@ -1115,7 +1103,11 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     if (timed) cudaEventRecord(c->kev[2 * c->kev_count], c->stream);
     if (c->g2p2g_mode == 0) g2p2g_kernel<0, Updater><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
     else if (c->g2p2g_mode == 1) g2p2g_kernel<1, Updater><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
-    else g2p2g_cell_kernel<Updater><<<nd, C_THREADS, CS_TOTAL, c->stream>>>(P);
+    else if (!c->g2p2g_stream) g2p2g_cell_kernel<Updater, false><<<nd, C_THREADS, CS_TOTAL, c->stream>>>(P);
+    else { // persistent CTAs: two per SM (64 registers x 512 threads), each walking every (2 x SMs)-th dispatch entry
+        const uint32_t resident = 2u * (uint32_t)c->sm_count;
+        g2p2g_cell_kernel<Updater, true><<<nd < resident ? nd : resident, C_THREADS, CS_TOTAL_STREAM, c->stream>>>(P);
+    }
     if (timed) { cudaEventRecord(c->kev[2 * c->kev_count + 1], c->stream); c->kev_count += 1; }
     c->launches += 1;
     c->g2p2g_launches += 1;
