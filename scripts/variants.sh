@@ -1,17 +1,24 @@
 #!/bin/bash
-# dev aid: build A/B variants of libsparkl_b200.so that differ in the G2P2G translation unit only (extra nvcc defines) into
-# build/variants/<name>.so; the other objects are the ones of the in-tree build.
-#   scripts/variants.sh build name "-DSPK_G2P2G_MIN_CTAS=2" ...   |   scripts/variants.sh run [steps]   (on the GPU box: one line per variant)
+# dev aid: build A/B variants of libsparkl_b200.so with extra nvcc defines into build/variants/<name>.so
+#   scripts/variants.sh build name "-DSPK_G2P2G_MIN_CTAS=2" ...     only the G2P2G translation unit is recompiled (the other objects are the in-tree ones)
+#   scripts/variants.sh buildall name "-DSPK_CELL_THREADS=256" ...  every translation unit is recompiled (defines that the host code sees too)
+#   scripts/variants.sh run [steps]                                  (on the GPU box: one line per variant)
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p build/variants
-if [ "$1" = build ]; then
-  name=$2; shift 2
-  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v "$@" -c sparkl_b200/csrc/spk_g2p2g.cu -o build/variants/${name}_g2p2g.o 2>&1 | grep -A2 "g2p2g_cell_kernel" | grep -E "stack|Used" || true
+NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
+if [ "$1" = build ] || [ "$1" = buildall ]; then
+  mode=$1; name=$2; shift 2
   objs=""
-  for f in spk_api spk_sort spk_grid spk_dist spk_fluids spk_migrate; do objs="$objs sparkl_b200/csrc/$f.o"; done
-  /usr/local/cuda/bin/nvcc -shared -Xlinker -Bsymbolic -o build/variants/$name.so build/variants/${name}_g2p2g.o $objs -gencode arch=compute_100a,code=sm_100a
-  rm -f build/variants/${name}_g2p2g.o
+  for f in spk_g2p2g spk_api spk_sort spk_grid spk_dist spk_fluids spk_migrate; do
+    if [ $mode = buildall ] || [ $f = spk_g2p2g ]; then
+      if [ $f = spk_g2p2g ]; then $NV -Xptxas -v "$@" -c sparkl_b200/csrc/$f.cu -o build/variants/${name}_$f.o 2>&1 | grep -A2 "g2p2g_cell_kernelI23DefaultParticleUpdaterTILj785EELb0" | grep -E "stack|Used" || true
+      else $NV "$@" -c sparkl_b200/csrc/$f.cu -o build/variants/${name}_$f.o; fi
+      objs="$objs build/variants/${name}_$f.o"
+    else objs="$objs sparkl_b200/csrc/$f.o"; fi
+  done
+  /usr/local/cuda/bin/nvcc -shared -Xlinker -Bsymbolic -o build/variants/$name.so $objs -gencode arch=compute_100a,code=sm_100a
+  rm -f build/variants/${name}_*.o
   echo built build/variants/$name.so
 else
   for so in build/variants/*.so; do

@@ -420,7 +420,7 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     // (the last two with 256-particle entries; kept for A/B profiling, SPK_G2P2G_MODE)
     c->g2p2g_mode = 2;
     if (const char* m = getenv("SPK_G2P2G_MODE")) { const int v = atoi(m); c->g2p2g_mode = v < 0 ? 0 : (v > 2 ? 2 : v); }
-    if (c->g2p2g_mode == 2) c->chunk = 512;
+    if (c->g2p2g_mode == 2) c->chunk = SPK_CELL_THREADS;
     c->g2p2g_specialize = getenv("SPK_G2P2G_GENERIC") ? 0 : 1;
     // persistent CTAs that prefetch their next entry (kept for A/B: SPK_G2P2G_STREAM=1).  Measured slower on the B200 (0.88 vs 0.68 ms on the 4 M
     // sand scene): the two CTAs of an SM fall into step, so their LSU-bound P2G phases and their FMA-bound update phases no longer

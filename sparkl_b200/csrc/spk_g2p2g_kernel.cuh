@@ -481,15 +481,18 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
 #define SPK_PSI_SHARE 1 /* 1: a CTA whose particles all have psi_mass == mass accumulates the mass channel once and flushes it twice */
 #endif
 #ifndef SPK_CELL_MIN_CTAS
-#define SPK_CELL_MIN_CTAS 2
+#define SPK_CELL_MIN_CTAS (1024 / SPK_CELL_THREADS)
 #endif
-constexpr int C_THREADS = 512;                // == particles per dispatch entry
+#ifndef SPK_CELL_ALIAS
+#define SPK_CELL_ALIAS (SPK_CELL_THREADS < 512) /* 1: the accumulation tile reuses the shared memory of the velocity tile (zeroed after G2P) */
+#endif
+constexpr int C_THREADS = SPK_CELL_THREADS;   // == particles per dispatch entry
 // per-particle shared-memory slot, stored as 9 arrays of float4 indexed by the particle's thread ([k][tid]: every per-thread access is
 // a conflict-free 16-byte access): arrays 0-4 hold the record tail (a1..a5), later the P2G payload; arrays 5-8 the parked G, velocity, ref2
 constexpr int C_TAIL = 5, C_PARKED = 4;
 constexpr int CS_VEL = 0;                                    // float4[512]
-constexpr int CS_ACC = CS_VEL + 512 * 16;                    // float[8][6][64]
-constexpr int CS_SLOT = CS_ACC + 8 * 6 * 64 * 4;             // float4[9][512]
+constexpr int CS_ACC = SPK_CELL_ALIAS ? CS_VEL : CS_VEL + 512 * 16;   // float[8][6][64]
+constexpr int CS_SLOT = CS_ACC + 8 * 6 * 64 * 4;             // float4[9][C_THREADS]
 constexpr int CS_BINCNT = CS_SLOT + (C_TAIL + C_PARKED) * C_THREADS * 16;  // int[224]
 constexpr int CS_BINSTART = CS_BINCNT + 224 * 4;             // int[224]
 constexpr int CS_BINLIST = CS_BINSTART + 224 * 4;            // u16[224] occupied bins
@@ -510,7 +513,7 @@ static_assert(CS_ENTN % 16 == 0 && CS_ACC2 % 128 == 0 && CS_PARAMS % 16 == 0 && 
 struct ParkedGradient {
     const float4* base;
     __device__ __forceinline__ float operator[](int i) const { // i is a compile-time constant after unrolling
-        const float4 v = base[(i >> 2) * 512];
+        const float4 v = base[(i >> 2) * SPK_CELL_THREADS];
         return (i & 3) == 0 ? v.x : ((i & 3) == 1 ? v.y : ((i & 3) == 2 ? v.z : v.w));
     }
 };
@@ -625,10 +628,12 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; flags = __float_as_uint(r0.w);
     }
     if (STREAM) cp_async_commit(); // group "tails of the first entry"
-    for (int i = tid; i < (STREAM ? 2 : 1) * 8 * SPK_ACC_CHANNELS * 64 / 4; i += C_THREADS) {
-        float4* a = reinterpret_cast<float4*>(i < 768 ? smem + CS_ACC : smem + CS_ACC2 - 768 * 16);
-        a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    static_assert(!(STREAM && SPK_CELL_ALIAS), "the streaming variant keeps its accumulation tiles apart from the velocity tile");
+    if (!SPK_CELL_ALIAS)
+        for (int i = tid; i < (STREAM ? 2 : 1) * 8 * SPK_ACC_CHANNELS * 64 / 4; i += C_THREADS) {
+            float4* a = reinterpret_cast<float4*>(i < 768 ? smem + CS_ACC : smem + CS_ACC2 - 768 * 16);
+            a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     if (tid < 224) s_bin_cnt[tid] = 0;
 
     const float h = Q.h, inv_h = Q.inv_h, dt = Q.dt;
@@ -642,7 +647,8 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         s_acc = reinterpret_cast<float*>(smem + ((iter & 1u) ? CS_ACC2 : CS_ACC));
         has_particle = (uint32_t)tid < CUR_COUNT;
     }
-    if (s_nbr_prev[tid >> 6] < 0) s_vel[tid] = make_float4(0.f, 0.f, 0.f, 0.f); // blocks absent from the previous grid read as zero
+    for (int i = tid; i < SPK_TILE_CELLS; i += C_THREADS)
+        if (s_nbr_prev[i >> 6] < 0) s_vel[i] = make_float4(0.f, 0.f, 0.f, 0.f); // blocks absent from the previous grid read as zero
     if (STREAM) {
         // the dispatch record of the next entry (5 x 16 bytes), on its way while this entry is updated
         if (tid < 5 && NEXT_VALID) {
@@ -839,6 +845,8 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     if (has_particle) rank = atomicAdd(&s_bin_cnt[bin], 1);
     if (STREAM && tid < 5) cp_async_wait_all(); // the next entry's dispatch record is in shared memory (its 5 loaders make sure)
     __syncthreads();
+    if (SPK_CELL_ALIAS) // every thread is done with the velocity tile: its shared memory becomes the (zeroed) accumulation tile
+        for (int i = tid; i < 8 * SPK_ACC_CHANNELS * 64 / 4; i += C_THREADS) reinterpret_cast<float4*>(s_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     // ---- STREAM: every thread is done with the velocity tile -> the next entry's tile may overwrite it; its particles are looked up
     uint32_t si_next = 0;
     bool has_next = false;
@@ -1094,7 +1102,9 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
         cudaError_t e = cudaFuncSetAttribute(g2p2g_kernel<0, Updater>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_kernel<1, Updater>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_cell_kernel<Updater, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_TOTAL);
+#if !SPK_CELL_ALIAS
         if (e == cudaSuccess) e = cudaFuncSetAttribute(g2p2g_cell_kernel<Updater, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_TOTAL_STREAM);
+#endif
         if (e != cudaSuccess) return e;
         if (c->device >= 0 && c->device < 64) configured[c->device] = true;
         c->g2p2g_configured = true;
@@ -1103,11 +1113,13 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     if (timed) cudaEventRecord(c->kev[2 * c->kev_count], c->stream);
     if (c->g2p2g_mode == 0) g2p2g_kernel<0, Updater><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
     else if (c->g2p2g_mode == 1) g2p2g_kernel<1, Updater><<<nd, G2P2G_THREADS, SM_TOTAL, c->stream>>>(P);
-    else if (!c->g2p2g_stream) g2p2g_cell_kernel<Updater, false><<<nd, C_THREADS, CS_TOTAL, c->stream>>>(P);
+    else if (!c->g2p2g_stream || SPK_CELL_ALIAS) g2p2g_cell_kernel<Updater, false><<<nd, C_THREADS, CS_TOTAL, c->stream>>>(P);
+#if !SPK_CELL_ALIAS
     else { // persistent CTAs: two per SM (64 registers x 512 threads), each walking every (2 x SMs)-th dispatch entry
         const uint32_t resident = 2u * (uint32_t)c->sm_count;
         g2p2g_cell_kernel<Updater, true><<<nd < resident ? nd : resident, C_THREADS, CS_TOTAL_STREAM, c->stream>>>(P);
     }
+#endif
     if (timed) { cudaEventRecord(c->kev[2 * c->kev_count + 1], c->stream); c->kev_count += 1; }
     c->launches += 1;
     c->g2p2g_launches += 1;

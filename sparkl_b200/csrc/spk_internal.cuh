@@ -32,6 +32,9 @@
 #define SPK_CELL_SHIFT 4
 #define SPK_REF_G2P2G_THREADS 64u /* dim2: src_kernels/cuda/mod.rs:12-13 */
 #endif
+#ifndef SPK_CELL_THREADS
+#define SPK_CELL_THREADS 256 /* threads per CTA == particles per dispatch entry of the cell-coherent g2p2g kernel (mode 2) */
+#endif
 #define SPK_ACC_CHANNELS 6
 // Position of a cell inside the 64-float channel chunk of `acc` (NOT of `vel` / the collider cache).  dim3: bit 1 of the cell's z flips
 // bit 1 of its x, so that the 3 x 3 (y, z) columns of a P2G stencil fall into 9 different shared-memory banks when a g2p2g CTA adds a
