@@ -425,6 +425,8 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     // persistent CTAs that prefetch their next entry (kept for A/B: SPK_G2P2G_STREAM=1).  Measured slower on the B200 (0.88 vs 0.68 ms on the 4 M
     // sand scene): the two CTAs of an SM fall into step, so their LSU-bound P2G phases and their FMA-bound update phases no longer
     // overlap, and the entry loop costs ~5 live registers the 64-register body does not have (profiles/r2_g2p2g_experiments.md)
+    c->g2p2g_prefetch = 0; // measured: 0.630 vs 0.624 ms with it on (the waiting threads were not idle issue slots after all)
+    if (const char* m = getenv("SPK_G2P2G_PREFETCH")) c->g2p2g_prefetch = atoi(m) ? 1 : 0;
     c->g2p2g_stream = 0;
     if (const char* m = getenv("SPK_G2P2G_STREAM")) c->g2p2g_stream = atoi(m) ? 1 : 0;
 #else

@@ -39,6 +39,7 @@ struct G2P2GParams {
     const uint32_t* blk_halo;   // [block] bit0: active on another rank too (spk_dist.cu: dist_detect_kernel)
     const int32_t* peer_ids;    // [block][world] the peer's id of the block, -1 if absent
     float* const* peer_hacc;    // [world] peer-mapped `hacc` of each rank's next grid
+    uint32_t prefetch_dist;     // cell kernel: CTA i warms the L2 with the particles of dispatch entry i + prefetch_dist (0 = off)
     uint32_t push_wait;         // 1: a CTA that pushed waits for the remote completion of its reductions (A/B); 0: the kernel boundary orders them
     const void* user;           // opaque device pointer handed to the updater (custom updaters; NULL for the default)
 };
@@ -480,6 +481,9 @@ __global__ void __launch_bounds__(G2P2G_THREADS, SPK_G2P2G_MIN_CTAS) g2p2g_kerne
 #ifndef SPK_PSI_SHARE
 #define SPK_PSI_SHARE 1 /* 1: a CTA whose particles all have psi_mass == mass accumulates the mass channel once and flushes it twice */
 #endif
+#ifndef SPK_P2G_LANES8
+#define SPK_P2G_LANES8 0 /* 1: four 8-lane P2G groups per warp (quarter-warp aligned payload broadcasts); 0: three 9-lane groups */
+#endif
 #ifndef SPK_CELL_MIN_CTAS
 #define SPK_CELL_MIN_CTAS (1024 / SPK_CELL_THREADS)
 #endif
@@ -508,6 +512,14 @@ constexpr int CS_ACC2 = CS_ENTN + 128;                       // float[8][6][64]
 constexpr int CS_PARAMS = CS_ACC2 + 8 * 6 * 64 * 4;          // G2P2GParams (the kernel parameters, see the top of the kernel)
 constexpr int CS_TOTAL_STREAM = CS_PARAMS + 384;
 static_assert(CS_ENTN % 16 == 0 && CS_ACC2 % 128 == 0 && CS_PARAMS % 16 == 0 && sizeof(G2P2GParams) <= 384, "cp.async / TMA alignment of the streaming variant's extra shared memory");
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef SPK_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
 // the velocity gradient of a particle where the cell kernel parks it: G.m[i] = float i of the float4 sequence base[0], base[stride], ...
 struct ParkedGradient {
@@ -681,6 +693,20 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
         quad_weights(spk_div_h(-ref[a], h, inv_h), w[a]);
         const int assoc_cell = (q != q) ? -2 : (int)__float2ll_rz(q) - 2;
         tcell[a] = (assoc_cell & 3) + 1;                 // associated_cell_index_in_block_off_by_two, particle.rs:28-35
+    }
+    if (!STREAM && Q.prefetch_dist) {
+        // While this CTA waits for its tile anyway: warm the L2 with the particle records of the dispatch entry that will start about one
+        // CTA lifetime from now (the CTAs resident right now cover entries up to blockIdx + prefetch_dist).  Its dependent chain
+        // dispatch -> permutation -> record then ends in L2 hits instead of DRAM round trips.
+        const uint32_t e2 = blockIdx.x + Q.prefetch_dist;
+        if (e2 < Q.ndispatch) {
+            const DispatchEntry ent2 = Q.dispatch[e2];
+            if ((uint32_t)tid < ent2.count) {
+                const uint32_t s2 = Q.perm[ent2.first + tid];
+                prefetch_l2(&Q.src.a0[s2]); prefetch_l2(&Q.src.a1[s2]); prefetch_l2(&Q.src.a2[s2]);
+                prefetch_l2(&Q.src.a3[s2]); prefetch_l2(&Q.src.a4[s2]); prefetch_l2(&Q.src.a5[s2]);
+            }
+        }
     }
     mbar_wait(s_bar, iter & 1u); // the tile is complete (TMA) ...
     __syncthreads();             // ... and the absent octants are zero-filled
@@ -907,6 +933,90 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
     }
     __syncthreads();
 
+#if SPK_P2G_LANES8
+    // ---- stage 2: 8-lane groups (a quarter warp each: the 128-bit payload reads of a group are ONE shared-memory wavefront), one occupied
+    // bin at a time, four bins per warp.  Lane l = stencil column (sy, sz) = (l % 3, l / 3) for l = 0..7 with its 3 nodes (sx = 0..2) x 6
+    // channels in registers over the bin's particles; the ninth column (2, 2) is shared out: lanes 0..2 each carry ONE more node of it
+    // (sx = l).  One flush of the 27 x 6 sums into the tile per bin.
+    {
+        const int lane = tid & 31;
+        const int grp = lane >> 3, l8 = lane & 7;
+        const int sy = l8 % 3, sz = l8 / 3;
+        const float fsy = (float)sy, fsz = (float)sz, fl8 = (float)l8;
+        // QuadraticKernel::eval_all (kernel.rs:15-21) for ONE node: w_s(x) = A_s (x - B_s)^2 + C_s
+        const float Ay = sy == 1 ? -1.f : 0.5f, By = sy == 0 ? 1.5f : (sy == 1 ? 1.f : 0.5f), Cy = sy == 1 ? 0.75f : 0.f;
+        const float Az = sz == 1 ? -1.f : 0.5f, Bz = sz == 0 ? 1.5f : (sz == 1 ? 1.f : 0.5f), Cz = sz == 1 ? 0.75f : 0.f;
+        const int nnz = *s_nnz;
+        // psi_mass == mass for every particle of the CTA (no failed / phase <= 0 particle: the usual case): the psi_mass sums are then
+        // the mass sums, term by term — they are not accumulated a second time, the flush sends the mass channel to both places
+        const bool psi_generic = *s_psi_generic != 0;
+        for (;;) { // a warp takes the next four occupied bins until the list is exhausted
+            int e = 0;
+            if (lane == 0) e = atomicAdd(s_next, 4);
+            e = __shfl_sync(0xffffffffu, e, 0) + grp;
+            if (e - grp >= nnz) break;
+            if (e >= nnz) continue;
+            const int b = s_binlist[e];
+            const int start = s_bin_start[b], cnt = s_bin_cnt[b];
+            float aM[3] = {0.f, 0.f, 0.f}, aX[3] = {0.f, 0.f, 0.f}, aY[3] = {0.f, 0.f, 0.f}, aZ[3] = {0.f, 0.f, 0.f}, aPm[3] = {0.f, 0.f, 0.f},
+                  aPp[3] = {0.f, 0.f, 0.f};
+            float eM = 0.f, eX = 0.f, eY = 0.f, eZ = 0.f, ePm = 0.f, ePp = 0.f; // the extra node (sx = l8, 2, 2) of lanes 0..2
+            for (int i = 0; i < cnt; ++i) {
+                const float4* pay = s_tail + s_sorted[start + i];
+                const float4 q0 = pay[0], q1 = pay[C_THREADS], q2 = pay[2 * C_THREADS], q3 = pay[3 * C_THREADS], q4 = pay[4 * C_THREADS];
+                const float dy = q3.w - By, dz = q4.w - Bz;
+                const float wyz = fmaf(Ay * dy, dy, Cy) * fmaf(Az * dz, dz, Cz);
+                // node momentum contribution at sx = 0: c + sy * hA[:,1] + sz * hA[:,2]
+                float bx = q0.y + fsy * q2.x + fsz * q3.x, by = q0.z + fsy * q2.y + fsz * q3.y, bz = q0.w + fsy * q2.z + fsz * q3.z;
+                const float wx[3] = {q4.x, q4.y, q4.z};
+#pragma unroll
+                for (int sx = 0; sx < 3; ++sx) {
+                    const float wt = wx[sx] * wyz;
+                    aM[sx] += wt * q0.x;
+                    aX[sx] += wt * bx; aY[sx] += wt * by; aZ[sx] += wt * bz;
+                    aPp[sx] += wt * q2.w;
+                    if (psi_generic) aPm[sx] += wt * q1.w;
+                    bx += q1.x; by += q1.y; bz += q1.z;
+                }
+                // the shared-out column (sy, sz) = (2, 2): weight 0.5 (fy - 0.5)^2 * 0.5 (fz - 0.5)^2, node sx = l8 (weight 0 for lanes 3..7)
+                const float ey = q3.w - 0.5f, ez = q4.w - 0.5f;
+                const float wte = (l8 == 0 ? q4.x : (l8 == 1 ? q4.y : (l8 == 2 ? q4.z : 0.f))) * ((0.5f * (ey * ey)) * (0.5f * (ez * ez)));
+                eM += wte * q0.x;
+                eX += wte * (q0.y + 2.f * (q2.x + q3.x) + fl8 * q1.x);
+                eY += wte * (q0.z + 2.f * (q2.y + q3.y) + fl8 * q1.y);
+                eZ += wte * (q0.w + 2.f * (q2.z + q3.z) + fl8 * q1.z);
+                ePp += wte * q2.w;
+                if (psi_generic) ePm += wte * q1.w;
+            }
+            const int bxc = b % 6, byc = (b / 6) % 6, bzc = b / 36;
+            {
+                const int byz = cell_part(byc + sy, 1) + oct_part(byc + sy, 1) * 384 + cell_part(bzc + sz, 2) + oct_part(bzc + sz, 2) * 384;
+                const int zsw = (bzc + sz) & 2; // SPK_ACC_SWZ: bit 1 of the node's z inside its block flips bit 1 of its x
+#pragma unroll
+                for (int sx = 0; sx < 3; ++sx) {
+                    float* a = &s_acc[byz + (cell_part(bxc + sx, 0) ^ zsw) + oct_part(bxc + sx, 0) * 384];
+                    atomicAdd(a + 0 * 64, aM[sx]);
+                    atomicAdd(a + 1 * 64, aX[sx]);
+                    atomicAdd(a + 2 * 64, aY[sx]);
+                    atomicAdd(a + 3 * 64, aZ[sx]);
+                    if (aPp[sx] != 0.f) atomicAdd(a + 4 * 64, aPp[sx]);
+                    if (psi_generic && aPm[sx] != 0.f) atomicAdd(a + 5 * 64, aPm[sx]);
+                }
+            }
+            if (l8 < 3) {
+                const int byz = cell_part(byc + 2, 1) + oct_part(byc + 2, 1) * 384 + cell_part(bzc + 2, 2) + oct_part(bzc + 2, 2) * 384;
+                const int zsw = (bzc + 2) & 2;
+                float* a = &s_acc[byz + (cell_part(bxc + l8, 0) ^ zsw) + oct_part(bxc + l8, 0) * 384];
+                atomicAdd(a + 0 * 64, eM);
+                atomicAdd(a + 1 * 64, eX);
+                atomicAdd(a + 2 * 64, eY);
+                atomicAdd(a + 3 * 64, eZ);
+                if (ePp != 0.f) atomicAdd(a + 4 * 64, ePp);
+                if (psi_generic && ePm != 0.f) atomicAdd(a + 5 * 64, ePm);
+            }
+        }
+    }
+#else
     // ---- stage 2: 9-lane groups, one occupied bin at a time; lane = stencil column (sy, sz), 3 nodes (sx = 0..2) x 6 channels in
     // registers over the bin's particles (payload reads are broadcasts), then one flush of the 18 sums into the tile
     {
@@ -966,6 +1076,8 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             }
         }
     }
+
+#endif
 
     // ---- stage 3: flush the accumulation tile into the next grid (transfer_shared_blocks_to_grid, g2p2g.rs:476-553)
     fence_proxy_async(); // make the generic-proxy smem writes visible to the async (TMA) proxy
@@ -1095,6 +1207,7 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     P.peer_ids = c->dist_peer_ids;
     P.peer_hacc = c->dist_push_ptrs;
     P.push_wait = (uint32_t)c->dist_push_wait;
+    P.prefetch_dist = c->g2p2g_prefetch ? (uint32_t)(c->sm_count * (1024 / SPK_CELL_THREADS)) : 0u;
     P.user = user;
     { cudaError_t e = cudaMemsetAsync(&c->d_counters->dt_raw_bits, 0x7f, 4, c->stream); if (e != cudaSuccess) return e; }
     static bool configured[64] = {}; // per instantiation and device: the > 48 KB dynamic shared memory opt-in is a per-device function attribute

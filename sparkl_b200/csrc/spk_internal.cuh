@@ -175,6 +175,7 @@ struct spk_ctx {
     DevModel* models; size_t nmodels; uint32_t model_flags_any; // bit0: any model needs an SVD
     uint32_t model_mask;  // union of model_mask_of(...) over the uploaded model table (SPK_MM_*, spk_math.cuh): picks the kernel instantiation
     int g2p2g_stream;     // mode 2: 1 (default) persistent CTAs that prefetch their next dispatch entry, 0: one CTA per entry (SPK_G2P2G_STREAM=0)
+    int g2p2g_prefetch;   // mode 2: 1: every CTA warms the L2 with the particles of a later dispatch entry (SPK_G2P2G_PREFETCH=1; off by default: no gain measured)
     int g2p2g_specialize; // 1 (default): use the model-set specialisations of the fused kernel; 0: always the generic one (SPK_G2P2G_GENERIC=1)
     DevCollider* colliders; size_t ncolliders;
     float* collider_data; // device copies of the heightfield matrices, one allocation
