@@ -270,6 +270,7 @@ int wait_counters(spk_ctx* c) {
 }
 int read_counters(spk_ctx* c) {
     static_assert(sizeof(DeviceCounters) % 4 == 0 && sizeof(DeviceCounters) <= 128, "one warp copies the record");
+    if (spk_dist_active(c) && c->gu_pending) { CK(cudaStreamWaitEvent(c->stream, c->ev_gu_done, 0)); c->gu_pending = false; } // the dt minimum may still be on its way there
     publish_counters_kernel<<<1, sizeof(DeviceCounters) / 4, 0, c->stream>>>(c->d_counters, c->h_counters_dev);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
@@ -925,6 +926,9 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
         // the two kernels that finish the sort are enqueued for the grid's CAPACITY (they read the true block count on the
         // device), and only then does the host wait for the record: its wake-up and the launches of the following stages
         // overlap ~30 us of GPU work instead of leaving the GPU idle in the middle of every substep.
+        // (multi-GPU: the record carries the dt minimum over the ranks, which the wait half of the last barrier — left on the grid-update
+        // stream by spk_step — writes: the main stream meets that stream here, after the binning kernels ran next to it)
+        if (spk_dist_active(c)) { int jrc = spk_join_grid_update(c); if (jrc) return jrc; }
         int rc = publish_counters(c);
         if (rc) return rc;
         CK(spk_launch_sort_finish(c));
@@ -948,6 +952,10 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
         }
         g.nab_host = hc.nab;
         c->sorted_valid = true;
+        // the fused dt candidate of the last g2p2g travelled in this record; the device word has since been reset for the next g2p2g
+        // (build_tables_kernel), so the host keeps the value until that g2p2g runs
+        c->dt_raw_host = hc.dt_raw_bits;
+        c->dt_raw_host_valid = true;
         if (info) {
             info->num_active_blocks = hc.nab;
             info->num_dispatch_blocks = hc.ndispatch;
@@ -976,8 +984,8 @@ int spk_stage_estimate_dt(spk_ctx* c, float min_dt, float max_dt, float* dt_out)
         // K15 was fused into the previous g2p2g (the particle state has not changed since): the reduced un-clamped
         // candidate arrived with the counters record; apply timestep.rs:87-112 to it.  min / clamp / fixed-point
         // conversion are monotone, so min_p f(c_p) == f(min_p c_p), bit for bit.
-        if (!c->counters_fresh) { int rc = read_counters(c); if (rc) return rc; }
-        const uint32_t bits = c->h_counters->dt_raw_bits;
+        if (!c->dt_raw_host_valid && !c->counters_fresh) { int rc = read_counters(c); if (rc) return rc; }
+        const uint32_t bits = c->dt_raw_host_valid ? c->dt_raw_host : c->h_counters->dt_raw_bits;
         if (bits < SPK_DT_RAW_NONE) { // at least one non-failed particle
             float raw;
             std::memcpy(&raw, &bits, 4);
@@ -1224,25 +1232,36 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
         float dt;
         if ((rc = spk_stage_estimate_dt(c, min_dt, std::fmin(remaining, params->max_substep_dt), &dt))) return rc;
         if (dist) { // every rank has built its hash table and zeroed its grid: find the blocks shared with the peers
-            CK(spk_dist_launch_barrier(c, 0));
+            CK(spk_dist_launch_barrier(c, 0, c->dist_s1_arrived ? 2 : 3)); // (the sort already told the peers: only the wait half is left)
+            c->dist_s1_arrived = 0;
             CK(spk_dist_launch_detect(c));
         }
         if (timings) CK(cudaEventRecord(ev[3], c->stream));
         if ((rc = launch_g2p2g_hooked(c, dt))) return rc;
         if (timings) CK(cudaEventRecord(ev[4], c->stream));
-        if (dist) { // NVLink red.add of the shared blocks into the peers, barrier (+ global dt minimum), fold what arrived
-            if (!c->dist_fused_push) CK(spk_dist_launch_push(c)); // default: pushed by g2p2g's own flush
-            CK(spk_dist_launch_barrier(c, 1));
+        const bool side = !timings && c->overlap_grid_update && (!dist || c->dist_split_barriers);
+        if (dist && !side) { // NVLink red.add of the shared blocks into the peers, barrier (+ global dt minimum), fold what arrived
+            if (!c->dist_fused_push) CK(spk_dist_launch_push(c)); // (SPK_DIST_PUSH=fused: pushed by g2p2g's own flush)
+            CK(spk_dist_launch_barrier(c, 1, 3));
             CK(spk_dist_launch_merge(c));
         }
-        if (!timings && !dist && c->overlap_grid_update) {
+        if (side) {
             // the grid update only touches the grid g2p2g just filled; the next substep's sort only reads the particles g2p2g just wrote
-            // and builds the OTHER grid buffer: the two run side by side, and meet again before the next reset_grid
+            // and builds the OTHER grid buffer: the two run side by side, and meet again before the next reset_grid (multi-GPU: before
+            // the next sort publishes its counter record, which carries the dt minimum the barrier computes).  Multi-GPU: the halo push and
+            // the whole post-g2p2g barrier sit on the side stream too: the NVLink reductions and the peers' flags travel while the next
+            // sort bins particles on the main stream
             CK(cudaEventRecord(c->ev_transfer_done, c->stream));
             CK(cudaStreamWaitEvent(c->gu_stream, c->ev_transfer_done, 0));
             cudaStream_t main_stream = c->stream;
             c->stream = c->gu_stream;
-            const cudaError_t ge = spk_launch_grid_update(c, dt, gravity);
+            cudaError_t ge = cudaSuccess;
+            if (dist) {
+                if (!c->dist_fused_push) ge = spk_dist_launch_push(c);
+                if (ge == cudaSuccess) ge = spk_dist_launch_barrier(c, 1, 3);
+                if (ge == cudaSuccess) ge = spk_dist_launch_merge(c);
+            }
+            if (ge == cudaSuccess) ge = spk_launch_grid_update(c, dt, gravity);
             c->stream = main_stream;
             CK(ge);
             CK(cudaEventRecord(c->ev_gu_done, c->gu_stream));

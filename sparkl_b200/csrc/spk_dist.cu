@@ -23,7 +23,7 @@
 // exist so both libraries export the same symbols, and fail loudly.
 bool spk_dist_active(const spk_ctx*) { return false; }
 bool spk_dist_grid_storage(spk_ctx*, int, uint32_t, unsigned long long**, uint32_t**) { return false; }
-cudaError_t spk_dist_launch_barrier(spk_ctx*, int) { return cudaErrorNotSupported; }
+cudaError_t spk_dist_launch_barrier(spk_ctx*, int, int) { return cudaErrorNotSupported; }
 cudaError_t spk_dist_launch_detect(spk_ctx*) { return cudaErrorNotSupported; }
 cudaError_t spk_dist_launch_push(spk_ctx*) { return cudaErrorNotSupported; }
 cudaError_t spk_dist_launch_merge(spk_ctx*) { return cudaErrorNotSupported; }
@@ -89,8 +89,10 @@ __device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) {
 //   mode 0: plain barrier, publishes `gnext` (which grid buffer is this rank's next grid)
 //   mode 1: additionally min-reduces counters->dt_raw_bits over the ranks (fused CFL reduction of g2p2g)
 //   mode 2: additionally min-reduces counters->dt_acc over the ranks (stand-alone estimate_dt kernel)
-__global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext, int mode, DeviceCounters* counters, long long timeout_cycles, DeviceCounters* host_record,
-                                    const uint32_t* __restrict__ bbox) {
+//   phase bit 0: ARRIVE (payload + flag into every peer's mailbox), bit 1: WAIT (spin on this rank's mailbox, reduce).  spk_step issues
+//   the two halves apart, with independent work in between, so the flags usually have landed when the wait half runs
+__global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext, int mode, int phase, DeviceCounters* counters, long long timeout_cycles,
+                                    DeviceCounters* host_record, const uint32_t* __restrict__ bbox) {
     const uint32_t p = threadIdx.x;
     const uint32_t slot = epoch & 1u;
     unsigned long long mine = 0;
@@ -99,7 +101,7 @@ __global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext,
     __shared__ unsigned long long s_val[SPK_MAX_RANKS];
     if (p < d.world) {
         s_val[p] = mine;
-        if (p != d.rank) {
+        if (p != d.rank && (phase & 1)) {
             DistMailbox* remote = d.peer_mailbox[p];
             remote->val[slot][d.rank] = mine;
             remote->gnext[slot][d.rank] = gnext;
@@ -107,6 +109,8 @@ __global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext,
                 for (int k = 0; k < 6; ++k) remote->bbox[slot][d.rank][k] = bbox[k];
             __threadfence_system(); // payload (and everything this rank wrote before, incl. NVLink atomics) before the flag
             st_sys_u32(&remote->flag[d.rank], epoch);
+        }
+        if (p != d.rank && (phase & 2)) {
             const long long t0 = clock64();
             while ((int)(ld_sys_u32(&d.mailbox->flag[p]) - epoch) < 0) {
                 // a peer that died must not hang the GPU: give up, and leave a STICKY mark (pad[1] is outside the words the sort clears
@@ -124,7 +128,7 @@ __global__ void dist_barrier_kernel(DistState d, uint32_t epoch, uint32_t gnext,
         }
     }
     __syncthreads();
-    if (p == 0 && mode != 0) {
+    if (p == 0 && mode != 0 && (phase & 2)) {
         unsigned long long m = s_val[0];
         for (uint32_t r = 1; r < d.world; ++r) m = s_val[r] < m ? s_val[r] : m;
         if (mode == 1) counters->dt_raw_bits = (uint32_t)m;
@@ -217,10 +221,17 @@ bool spk_dist_grid_storage(spk_ctx* c, int g, uint32_t cap_hash, unsigned long l
     return true;
 }
 
-cudaError_t spk_dist_launch_barrier(spk_ctx* c, int mode) {
+// phase 3: the whole barrier; 1: arrive only (takes a new epoch, remembered per mode); 2: the wait half of the last arrive of this mode.
+// Runs on the context's current stream (spk_step points it at the grid-update stream for the wait half of the second barrier).
+cudaError_t spk_dist_launch_barrier(spk_ctx* c, int mode, int phase) {
     DistState& d = c->dist;
-    d.epoch += 1;
-    dist_barrier_kernel<<<1, SPK_MAX_RANKS, 0, c->stream>>>(d, d.epoch, (uint32_t)(1 - c->gcur), mode, c->d_counters, c->dist_timeout_cycles, c->h_counters_dev, c->dist_bbox);
+    if (phase & 1) {
+        d.epoch += 1;
+        c->dist_epoch_of[mode] = d.epoch;
+        c->dist_gnext_of[mode] = (uint32_t)(1 - c->gcur);
+    }
+    dist_barrier_kernel<<<1, SPK_MAX_RANKS, 0, c->stream>>>(d, c->dist_epoch_of[mode], c->dist_gnext_of[mode], mode, phase, c->d_counters, c->dist_timeout_cycles,
+                                                            c->h_counters_dev, c->dist_bbox);
     c->launches += 1;
     c->counters_fresh = false;
     return cudaGetLastError();
@@ -229,9 +240,8 @@ cudaError_t spk_dist_launch_detect(spk_ctx* c) {
     DistState& d = c->dist;
     GridBuffers& next = c->grid[1 - c->gcur];
     const uint32_t nab = next.nab_host;
-    cudaError_t e = cudaMemsetAsync(&c->d_counters->num_halo, 0, 4, c->stream);
-    if (e != cudaSuccess || !nab) return e;
-    dist_detect_kernel<<<(nab * d.world + 255) / 256, 256, 0, c->stream>>>(d, next, nab, d.epoch, c->dist_peer_ids, c->dist_push_ptrs, c->d_counters);
+    if (!nab) return cudaSuccess; // (num_halo was zeroed by this substep's sort: build_tables_kernel)
+    dist_detect_kernel<<<(nab * d.world + 255) / 256, 256, 0, c->stream>>>(d, next, nab, c->dist_epoch_of[0], c->dist_peer_ids, c->dist_push_ptrs, c->d_counters);
     c->launches += 1;
     return cudaGetLastError();
 }
@@ -239,7 +249,7 @@ cudaError_t spk_dist_launch_push(spk_ctx* c) {
     DistState& d = c->dist;
     GridBuffers& next = c->grid[1 - c->gcur];
     if (!next.nab_host) return cudaSuccess;
-    dist_push_kernel<<<next.nab_host, 128, 0, c->stream>>>(d, next, next.nab_host, d.epoch, c->dist_peer_ids);
+    dist_push_kernel<<<next.nab_host, 128, 0, c->stream>>>(d, next, next.nab_host, c->dist_epoch_of[0], c->dist_peer_ids);
     c->launches += 1;
     return cudaGetLastError();
 }
@@ -280,8 +290,12 @@ int spk_dist_export(spk_ctx* c, SpkDistDescriptor* out) {
     c->dist_push_wait = getenv("SPK_DIST_PUSH_WAIT") ? 1 : 0;
     c->dist_merge_in_update = 1;
     if (const char* m = getenv("SPK_DIST_MERGE")) c->dist_merge_in_update = std::strcmp(m, "kernel") != 0;
-    c->dist_fused_push = 1;
-    if (const char* m = getenv("SPK_DIST_PUSH")) c->dist_fused_push = std::strcmp(m, "kernel") != 0; // A/B: separate push kernel
+    c->dist_split_barriers = getenv("SPK_DIST_SPLIT") ? atoi(getenv("SPK_DIST_SPLIT")) : 1;
+    c->dist_s1_arrived = 0;
+    // halo push: a kernel of its own after g2p2g (default; measured 12 us per substep faster at 4 M particles per GPU: the pushes of the few
+    // shared blocks stretch the whole fused kernel) or fused into g2p2g's flush (A/B: SPK_DIST_PUSH=fused)
+    c->dist_fused_push = 0;
+    if (const char* m = getenv("SPK_DIST_PUSH")) c->dist_fused_push = std::strcmp(m, "fused") == 0;
     {   // barrier timeout: SPK_DIST_TIMEOUT_MS (default 3000, 0 = unbounded), converted with the device's SM clock
         long long ms = 3000;
         if (const char* t = getenv("SPK_DIST_TIMEOUT_MS")) ms = atoll(t);

@@ -221,6 +221,7 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     c->cur = 1 - c->cur; // the next buffer now holds the particles, physically in sorted order
     c->sorted_valid = false;
     c->dt_cache_valid = true;
+    c->dt_raw_host_valid = false;
     c->counters_fresh = false;
     return cudaGetLastError();
 }

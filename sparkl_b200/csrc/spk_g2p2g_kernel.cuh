@@ -608,7 +608,6 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             nid = Q.dispatch_nbr[(size_t)blockIdx.x * 16 + tid];
             s_nbr_self[tid] = nid; // s_nbr_prev follows s_nbr_self
         }
-        if (tid < 8) s_halo[tid] = (Q.world > 1 && nid >= 0) ? Q.blk_halo[nid] : 0u;
         __syncwarp();
         if (tid == 0) {
             mbar_init(s_bar, 1);
@@ -622,6 +621,9 @@ __global__ void __launch_bounds__(C_THREADS, SPK_CELL_MIN_CTAS) g2p2g_cell_kerne
             for (int o = 0; o < 8; ++o)
                 if (s_nbr_prev[o] >= 0) tma_load_1d(&s_vel[o * 64], Q.prev_vel + (size_t)s_nbr_prev[o] * 64, 1024u, s_bar);
         }
+        // (multi-GPU: the halo bits of the tile's blocks are only read by the flush; fetched AFTER the tile copies are on their way, so
+        // that this dependent load does not sit on the critical path of every CTA)
+        if (tid < 8) s_halo[tid] = (Q.world > 1 && nid >= 0) ? Q.blk_halo[nid] : 0u;
     }
     bool has_particle = (uint32_t)tid < ent0.count;
     float4* const tail = s_tail + tid; // tail[k * C_THREADS]: a(k+1) of this particle, later payload vector k
@@ -1209,7 +1211,7 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     P.push_wait = (uint32_t)c->dist_push_wait;
     P.prefetch_dist = c->g2p2g_prefetch ? (uint32_t)(c->sm_count * (1024 / SPK_CELL_THREADS)) : 0u;
     P.user = user;
-    { cudaError_t e = cudaMemsetAsync(&c->d_counters->dt_raw_bits, 0x7f, 4, c->stream); if (e != cudaSuccess) return e; }
+    // (the dt candidate word was reset to SPK_DT_RAW_NONE by this substep's sort: build_tables_kernel, after the counter record was published)
     static bool configured[64] = {}; // per instantiation and device: the > 48 KB dynamic shared memory opt-in is a per-device function attribute
     if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
         cudaError_t e = cudaFuncSetAttribute(g2p2g_kernel<0, Updater>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
@@ -1239,6 +1241,7 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     c->cur = 1 - c->cur; // the next buffer now holds the particles, physically in sorted order
     c->sorted_valid = false;
     c->dt_cache_valid = true;
+    c->dt_raw_host_valid = false;
     c->counters_fresh = false;
     return cudaGetLastError();
 }

@@ -169,6 +169,7 @@ struct spk_ctx {
     uint32_t* perm;    // sorted index -> index in current order
     uint32_t* gid;     // optional global particle ids (multi-GPU migration), indexed by particle id; NULL = identity
     bool sorted_valid; // perm/slot tables describe pb[cur]
+    uint32_t dt_raw_host; bool dt_raw_host_valid; // the candidate as the last sort's counter record carried it (the device word is reset by that sort)
     bool dt_cache_valid; // d_counters->dt_raw_bits describes pb[cur] (set by g2p2g, cleared by any particle/model edit)
     unsigned long long dt_acc_host; // GpuTimestepLength accumulator (host-authoritative)
     // models / colliders
@@ -215,7 +216,10 @@ struct spk_ctx {
     void* dist_mapped[SPK_MAX_RANKS];    // cudaIpcOpenMemHandle results (to close)
     float** dist_push_ptrs;              // [SPK_MAX_RANKS] device array: peer-mapped hacc of every rank's next grid (written by detect)
     long long dist_timeout_cycles;       // device-side barrier: give up on a peer after this many SM cycles (0 = wait for ever)
-    int dist_fused_push;                 // 1: g2p2g's flush pushes shared blocks itself (default); 0: separate push kernel (A/B)
+    uint32_t dist_epoch_of[3], dist_gnext_of[3]; // epoch / next-grid index of the last ARRIVE of each barrier mode (the wait half may be issued later)
+    int dist_split_barriers;             // 1 (default): arrive / wait halves of the two barriers are issued apart (A/B: SPK_DIST_SPLIT=0)
+    int dist_s1_arrived;                 // 1: the arrive half of the pre-detection barrier was issued by the sort (spk_launch_sort_finish)
+    int dist_fused_push;                 // 0 (default): a push kernel after g2p2g; 1: g2p2g's flush pushes shared blocks itself (A/B: SPK_DIST_PUSH=fused)
     // custom particle kernels (spk_set_particle_kernels_launcher); all NULL = DefaultCudaParticleKernelsLauncher
     SpkParticleKernelsLauncher launcher;
     // timing
@@ -250,7 +254,7 @@ bool spk_dist_active(const spk_ctx* c);
 bool spk_dist_grid_storage(spk_ctx* c, int g, uint32_t cap_hash, unsigned long long** keys, uint32_t** vals);
 int spk_dist_realloc_grids(spk_ctx* c, uint32_t cap_hash); // defined in spk_api.cu
 int spk_join_grid_update(spk_ctx* c);                        // spk_api.cu: main stream waits for a grid update left on its own stream
-cudaError_t spk_dist_launch_barrier(spk_ctx* c, int mode); // 0 barrier, 1 + min of dt_raw_bits, 2 + min of dt_acc
+cudaError_t spk_dist_launch_barrier(spk_ctx* c, int mode, int phase = 3); // mode 0 barrier, 1 + min of dt_raw_bits, 2 + min of dt_acc; phase 1 arrive, 2 wait, 3 both
 cudaError_t spk_dist_launch_detect(spk_ctx* c);
 cudaError_t spk_dist_launch_push(spk_ctx* c);
 cudaError_t spk_dist_launch_merge(spk_ctx* c);

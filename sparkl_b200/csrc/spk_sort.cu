@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) slot_totals_kernel(const unsigne
 // pass 2: ids = rank of the slot, first_particle / dispatch base = exclusive prefix sums (replaces K6-K9, K11, K12)
 __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ slot_cnt,
                                                                    uint32_t cap_hash, uint32_t chunk, const Triple* __restrict__ partials, uint32_t* vals,
-                                                                   GridBuffers g, DispatchEntry* dispatch, uint32_t dispatch_cap, DeviceCounters* counters) {
+                                                                   GridBuffers g, DispatchEntry* dispatch, uint32_t dispatch_cap, DeviceCounters* counters, uint32_t* bbox) {
     __shared__ Triple s_base;
     // redundant reduction of the partials of all previous CTAs (at most a few hundred values)
     Triple pre{0, 0, 0};
@@ -204,15 +204,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned
         counters->nab = run.occ;
         counters->ndispatch = run.mult;
         counters->nparticles_binned = run.cnt;
+        if (bbox) { // multi-GPU: empty bounding box for build_tables_kernel's min / max (no memsets)
+            bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
+            bbox[3] = bbox[4] = bbox[5] = 0u;
+        }
     }
 }
 
 // neighbour-block tables: for block b, ids of key + {0,1}^3 in the next grid (always present) and in the previous grid
 // (launched for the grid's block CAPACITY before the host has read the block count back, so that the read-back overlaps this
 // kernel and scatter_perm_kernel; the true count comes from the device-side record)
-__global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, const DeviceCounters* __restrict__ counters, int32_t* __restrict__ dispatch_nbr,
+__global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, DeviceCounters* counters, int32_t* __restrict__ dispatch_nbr,
                                     uint32_t dispatch_cap, uint32_t chunk, uint32_t* bbox) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) { // the counter record of this sort has been published: reset the words the rest of the substep accumulates into (no memsets)
+        counters->dt_raw_bits = SPK_DT_RAW_NONE; // g2p2g's fused CFL candidate (atomicMin)
+        counters->num_halo = 0;                  // multi-GPU halo detection (atomicAdd)
+    }
     const uint32_t b = t >> SPK_NBR_SHIFT, o = t & (SPK_NBR - 1);
     const bool live = b < counters->nab && b < next.cap_blocks;
 #if SPK_DIM == 3
@@ -278,7 +286,7 @@ cudaError_t spk_launch_sort_bin(spk_ctx* c) {
     if ((size_t)ntiles * sizeof(Triple) > c->staging_bytes) return cudaErrorInvalidValue; // sized by spk_stage_sort (ensure_staging) before the launch
     Triple* partials = (Triple*)c->staging;
     slot_totals_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials);
-    assign_ids_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials, g.vals, g, c->dispatch, c->dispatch_cap, c->d_counters);
+    assign_ids_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials, g.vals, g, c->dispatch, c->dispatch_cap, c->d_counters, c->dist_bbox);
     c->launches += 2;
     return cudaGetLastError();
 }
@@ -289,13 +297,15 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c) {
     cudaStream_t s = c->stream;
     const uint32_t n = (uint32_t)c->n;
     {
-        if (c->dist_bbox) { // {min x, y, z} = 0xffffffff, {max x, y, z} = 0
-            cudaError_t e = cudaMemsetAsync(c->dist_bbox, 0xff, 12, s);
-            if (e == cudaSuccess) e = cudaMemsetAsync(c->dist_bbox + 3, 0, 12, s);
-            if (e != cudaSuccess) return e;
-        }
         build_tables_kernel<<<(g.cap_blocks * SPK_NBR + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters, c->dispatch_nbr, c->dispatch_cap, c->chunk, c->dist_bbox);
         c->launches += 1;
+        // multi-GPU: this rank's hash table and bounding box are final -> tell the peers now (the arrive half of the barrier that precedes the
+        // halo detection); its wait half runs ~60 us of independent work later (permutation, grid reset), when the peers' flags have landed
+        if (spk_dist_active(c) && c->dist_split_barriers) {
+            cudaError_t e = spk_dist_launch_barrier(c, 0, 1);
+            if (e != cudaSuccess) return e;
+            c->dist_s1_arrived = 1;
+        }
     }
     if (n) {
         scatter_perm_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->slot_of, c->rank_of, n, g.vals, g.blk_first, c->cell_cnt, g.cap_blocks, c->perm);
