@@ -920,7 +920,7 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
     if (c->n && !c->models) return SPK_ESTATE;
     for (int attempt = 0; attempt < 16; ++attempt) {
         GridBuffers& g = c->grid[1 - c->gcur];
-        CK(ensure_staging(c, ((size_t)g.cap_hash / 2048 + 1) * 12)); // the scan partials of spk_launch_sort_bin: 12 bytes per 2048 hash slots
+        CK(ensure_staging(c, ((size_t)g.cap_hash / 256 + 1) * 12)); // the scan partials of spk_launch_sort_bin: 12 bytes per scan tile (>= 256 hash slots)
         CK(spk_launch_sort_bin(c));
         // The counter record (block / dispatch counts, overflow flag, dt candidate) is published to mapped host memory, then
         // the two kernels that finish the sort are enqueued for the grid's CAPACITY (they read the true block count on the
@@ -1231,15 +1231,27 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
         if (timings) CK(cudaEventRecord(ev[2], c->stream));
         float dt;
         if ((rc = spk_stage_estimate_dt(c, min_dt, std::fmin(remaining, params->max_substep_dt), &dt))) return rc;
-        if (dist) { // every rank has built its hash table and zeroed its grid: find the blocks shared with the peers
-            CK(spk_dist_launch_barrier(c, 0, c->dist_s1_arrived ? 2 : 3)); // (the sort already told the peers: only the wait half is left)
+        const bool side = !timings && c->overlap_grid_update && (!dist || c->dist_split_barriers);
+        if (dist) { // every rank has built its hash table: find the blocks shared with the peers
+            // With the push kernel (the default) only the side-stream work after g2p2g reads what the detection writes (halo bits, the peers'
+            // block ids): the wait for the peers and the probes of their hash tables over NVLink then run on the side stream, next to this
+            // substep's grid reset and g2p2g, and are off the critical path altogether
+            const bool detect_aside = side && !c->dist_fused_push;
+            cudaStream_t main_stream = c->stream;
+            if (detect_aside) {
+                CK(cudaEventRecord(c->ev_transfer_done, c->stream));
+                CK(cudaStreamWaitEvent(c->gu_stream, c->ev_transfer_done, 0));
+                c->stream = c->gu_stream;
+            }
+            cudaError_t de = spk_dist_launch_barrier(c, 0, c->dist_s1_arrived ? 2 : 3); // (the sort already told the peers: only the wait half is left)
             c->dist_s1_arrived = 0;
-            CK(spk_dist_launch_detect(c));
+            if (de == cudaSuccess) de = spk_dist_launch_detect(c);
+            c->stream = main_stream;
+            CK(de);
         }
         if (timings) CK(cudaEventRecord(ev[3], c->stream));
         if ((rc = launch_g2p2g_hooked(c, dt))) return rc;
         if (timings) CK(cudaEventRecord(ev[4], c->stream));
-        const bool side = !timings && c->overlap_grid_update && (!dist || c->dist_split_barriers);
         if (dist && !side) { // NVLink red.add of the shared blocks into the peers, barrier (+ global dt minimum), fold what arrived
             if (!c->dist_fused_push) CK(spk_dist_launch_push(c)); // (SPK_DIST_PUSH=fused: pushed by g2p2g's own flush)
             CK(spk_dist_launch_barrier(c, 1, 3));

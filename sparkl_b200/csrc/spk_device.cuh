@@ -54,6 +54,12 @@ __device__ __forceinline__ float spk_div_h(float x, float h, float inv_h) {
     const float ax = fabsf(x);
     return (ax < 1.0e30f && ax > 1.0e-30f) ? q : __fdiv_rn(x, h);
 }
+// the same cell through spk_div_h (bit-identical quotient, ~10 instructions fewer per axis)
+__device__ __forceinline__ long long spk_assoc_cell_m(float p, float h, float inv_h) {
+    float q = roundf(spk_div_h(p, h, inv_h));
+    if (q != q) return 0;
+    return __float2ll_rz(q);
+}
 // block_associated_to_point, gpu_grid.rs:271-279: ((cell - 2 + 2^22) as usize) / 4 per axis
 __device__ __forceinline__ unsigned long long spk_block_coord(long long cell) {
     return (unsigned long long)(cell - 2 + SPK_PACK_ORIGIN * 4) / 4ull;

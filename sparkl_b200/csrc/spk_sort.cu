@@ -13,35 +13,28 @@
 #include "spk_device.cuh"
 
 #ifndef SPK_CELL_SCAN_SLOTS
-#define SPK_CELL_SCAN_SLOTS 16
+#define SPK_CELL_SCAN_SLOTS 2
+#endif
+#ifndef SPK_PERM_ITEMS
+#define SPK_PERM_ITEMS 4
 #endif
 namespace {
 
 constexpr int BIN_THREADS = 256;
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8; // slots per thread
+#ifndef SPK_SCAN_ITEMS
+#define SPK_SCAN_ITEMS 2
+#endif
+constexpr int SCAN_ITEMS = SPK_SCAN_ITEMS; // slots per thread (few: the table has only tens of thousands of slots, the scan wants CTAs, not long threads)
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr int SPK_RANK_BITS = 32 - SPK_CELL_SHIFT; // rank_of = cell << SPK_RANK_BITS | rank inside the cell
 constexpr uint32_t SPK_RANK_MASK = (1u << SPK_RANK_BITS) - 1u;
-
-// cell of the block (4^DIM cells, x fastest) that owns a coordinate: (associated cell - 2) mod 4 per axis — the same arithmetic as
-// spk_block_coord, so (block key, cell) is the particle's full cell address (particle.rs:28-35)
-__device__ __forceinline__ uint32_t spk_cell_in_block(float x, float y, float z, float h) {
-    const uint32_t cx = (uint32_t)(spk_assoc_cell(x, h) - 2) & 3u, cy = (uint32_t)(spk_assoc_cell(y, h) - 2) & 3u;
-#if SPK_DIM == 3
-    const uint32_t cz = (uint32_t)(spk_assoc_cell(z, h) - 2) & 3u;
-    return cx | (cy << 2) | (cz << 4);
-#else
-    (void)z;
-    return cx | (cy << 2);
-#endif
-}
 
 // K1: one pass over the positions.  Per particle: block key + cell inside the block; per (warp, block) one hash insert; per
 // (warp, block, cell) one atomicAdd on the cell counter of the block's hash slot, which also hands out the particle's rank inside
 // its cell.  Sorting by (block, cell) instead of by block alone costs nothing extra here and makes every g2p2g warp read a handful
 // of cells (shared-memory broadcasts in G2P, few P2G bins per CTA).
-__global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4* __restrict__ a0, uint32_t n, float h, unsigned long long* keys,
+__global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4* __restrict__ a0, uint32_t n, float h, float inv_h, unsigned long long* keys,
                                                                      uint32_t cap_hash, uint32_t* cell_cnt, uint32_t* __restrict__ slot_of,
                                                                      uint32_t* __restrict__ rank_of, DeviceCounters* counters) {
     const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
@@ -49,8 +42,17 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4
     const unsigned active = __ballot_sync(0xffffffffu, valid);
     if (!valid) return;
     const float4 p = a0[i];
-    const unsigned long long key = spk_block_key_of_point(p.x, p.y, p.z, h);
-    const uint32_t cell = spk_cell_in_block(p.x, p.y, p.z, h);
+    // associated cells once (correctly rounded p / h through the host's RN(1 / h): bit-identical to div.rn, spk_div_h), then block key and
+    // cell inside the block from the same integers
+    const long long acx = spk_assoc_cell_m(p.x, h, inv_h), acy = spk_assoc_cell_m(p.y, h, inv_h);
+#if SPK_DIM == 3
+    const long long acz = spk_assoc_cell_m(p.z, h, inv_h);
+    const unsigned long long key = spk_pack_key(spk_block_coord(acx), spk_block_coord(acy), spk_block_coord(acz));
+    const uint32_t cell = ((uint32_t)(acx - 2) & 3u) | (((uint32_t)(acy - 2) & 3u) << 2) | (((uint32_t)(acz - 2) & 3u) << 4);
+#else
+    const unsigned long long key = spk_pack_key(spk_block_coord(acx), spk_block_coord(acy));
+    const uint32_t cell = ((uint32_t)(acx - 2) & 3u) | (((uint32_t)(acy - 2) & 3u) << 2);
+#endif
     const unsigned group = __match_any_sync(active, key);
     const unsigned cgroup = group & __match_any_sync(active, (unsigned long long)cell);
     const int leader = __ffs(group) - 1, cleader = __ffs(cgroup) - 1;
@@ -254,14 +256,26 @@ __global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, DeviceCo
 __global__ void __launch_bounds__(BIN_THREADS) scatter_perm_kernel(const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ rank_of, uint32_t n,
                                                                     const uint32_t* __restrict__ vals, const uint32_t* __restrict__ blk_first,
                                                                     const uint32_t* __restrict__ cell_off, uint32_t cap_blocks, uint32_t* __restrict__ perm) {
-    const uint32_t i = blockIdx.x * BIN_THREADS + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t slot = slot_of[i];
-    if (slot == SPK_NO_BLOCK) return;
-    const uint32_t id = vals[slot];
-    if (id >= cap_blocks) return;
-    const uint32_t cr = rank_of[i];
-    perm[blk_first[id] + cell_off[(size_t)slot * SPK_CELLS_PER_BLOCK + (cr >> SPK_RANK_BITS)] + (cr & SPK_RANK_MASK)] = i;
+    // SPK_PERM_ITEMS particles per thread, every level of the dependent chain (slot -> id -> first particle, cell offset) loaded for all
+    // of them before the next level is touched: the kernel is pure memory latency
+    const uint32_t i0 = blockIdx.x * (BIN_THREADS * SPK_PERM_ITEMS) + threadIdx.x;
+    uint32_t slot[SPK_PERM_ITEMS], cr[SPK_PERM_ITEMS], id[SPK_PERM_ITEMS], first[SPK_PERM_ITEMS], off[SPK_PERM_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SPK_PERM_ITEMS; ++k) {
+        const uint32_t i = i0 + k * BIN_THREADS;
+        slot[k] = i < n ? slot_of[i] : SPK_NO_BLOCK;
+        cr[k] = i < n ? rank_of[i] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < SPK_PERM_ITEMS; ++k) {
+        id[k] = slot[k] != SPK_NO_BLOCK ? vals[slot[k]] : 0xffffffffu;
+        off[k] = slot[k] != SPK_NO_BLOCK ? cell_off[(size_t)slot[k] * SPK_CELLS_PER_BLOCK + (cr[k] >> SPK_RANK_BITS)] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < SPK_PERM_ITEMS; ++k) first[k] = id[k] < cap_blocks ? blk_first[id[k]] : 0u;
+#pragma unroll
+    for (int k = 0; k < SPK_PERM_ITEMS; ++k)
+        if (id[k] < cap_blocks) perm[first[k] + off[k] + (cr[k] & SPK_RANK_MASK)] = i0 + k * BIN_THREADS;
 }
 
 } // namespace
@@ -277,7 +291,7 @@ cudaError_t spk_launch_sort_bin(spk_ctx* c) {
     c->counters_fresh = false;
     const uint32_t n = (uint32_t)c->n;
     if (n) {
-        bin_particles_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->pb[c->cur].a0, n, c->cell_width, g.keys, g.cap_hash, c->cell_cnt,
+        bin_particles_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->pb[c->cur].a0, n, c->cell_width, 1.0f / c->cell_width, g.keys, g.cap_hash, c->cell_cnt,
                                                                                         c->slot_of, c->rank_of, c->d_counters);
         cell_scan_kernel<<<(g.cap_hash + 8 * CELL_SCAN_SLOTS - 1) / (8 * CELL_SCAN_SLOTS), 256, 0, s>>>(g.keys, g.cap_hash, c->cell_cnt, c->slot_cnt, c->d_counters);
         c->launches += 2;
@@ -308,7 +322,7 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c) {
         }
     }
     if (n) {
-        scatter_perm_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->slot_of, c->rank_of, n, g.vals, g.blk_first, c->cell_cnt, g.cap_blocks, c->perm);
+        scatter_perm_kernel<<<(n + BIN_THREADS * SPK_PERM_ITEMS - 1) / (BIN_THREADS * SPK_PERM_ITEMS), BIN_THREADS, 0, s>>>(c->slot_of, c->rank_of, n, g.vals, g.blk_first, c->cell_cnt, g.cap_blocks, c->perm);
         c->launches += 1;
     }
     return cudaGetLastError();
