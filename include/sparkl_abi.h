@@ -503,6 +503,12 @@ int spk_grid_num_active_blocks(spk_ctx* ctx, int which_grid, uint32_t* out);
 int spk_grid_read_headers(spk_ctx* ctx, int which_grid, SpkActiveBlockHeader* dst, uint32_t n);
 int spk_grid_read_nodes(spk_ctx* ctx, int which_grid, SpkGpuGridNode* dst, uint32_t n_blocks); /* 64 (dim2: 16) nodes per block */
 int spk_grid_read_dispatch(spk_ctx* ctx, SpkDispatchBlock2ActiveBlock* dst, uint32_t n);
+/* The box the LAST particle sort ranked its blocks in (block ids follow the Morton curve of the block coordinate relative to this box;
+ * encoding of src_core/utils/morton3.rs:3-15 generalised to one bit count per axis: for l = 0, 1, ...: bit l of x, of y, of z — each
+ * only while l < its bit count — appended from the least significant end).  out[0..2]: origin (raw BlockVirtualId coordinates),
+ * out[3..5]: bits per axis, out[6]: 1 when the sort had a box at all, out[7]: 1 when a block fell outside it; with out[6] == 0 or
+ * out[7] == 1 that sort ranked the blocks by hash slot (valid ids, no spatial order).  dim2: entries [2] and [5] are 0. */
+int spk_grid_morton_box(spk_ctx* ctx, uint32_t out[8]);
 /* raw device pointers for zero-copy wrappers (torch / NCCL plumbing); valid until the next upload/append */
 int spk_device_ptr(spk_ctx* ctx, int which /* SPK_ATTR_* */, void** out);
 /* Kernel timing without perturbing the run (≙ the g2p2g field of CudaDeviceTimings, cuda_mpm_pipeline.rs:56-85, which the

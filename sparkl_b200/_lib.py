@@ -22,7 +22,7 @@ EXPORTS = [
     "spk_models_upload", "spk_colliders_upload", "spk_step", "spk_frame_begin", "spk_stage_sort", "spk_stage_reset_grid",
     "spk_stage_estimate_dt", "spk_dt_acc_get", "spk_dt_acc_set", "spk_stage_g2p2g", "spk_stage_grid_update", "spk_stage_recompute_fluids_volume",
     "spk_halo_begin", "spk_halo_active_keys", "spk_halo_tag", "spk_halo_count", "spk_halo_pack", "spk_halo_merge", "spk_grid_num_active_blocks",
-    "spk_grid_read_headers", "spk_grid_read_nodes", "spk_grid_read_dispatch", "spk_device_ptr", "spk_g2p2g_time",
+    "spk_grid_read_headers", "spk_grid_read_nodes", "spk_grid_read_dispatch", "spk_grid_morton_box", "spk_device_ptr", "spk_g2p2g_time",
     "spk_dist_export", "spk_dist_attach", "spk_dist_detach", "spk_dist_info",
     "spk_particles_truncate", "spk_particles_capacity", "spk_particles_set_gids", "spk_particles_read_gids", "spk_particles_migrate_out", "spk_particles_migrate_in",
     "spk_set_particle_kernels_launcher", "spk_default_launch_estimate_particle_timestep_length", "spk_default_launch_g2p2g",

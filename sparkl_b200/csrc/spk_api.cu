@@ -90,8 +90,11 @@ cudaError_t ensure_slot_scratch(spk_ctx* c, uint32_t cap_hash) {
     if (c->slot_cnt_cap >= cap_hash) return cudaSuccess;
     dev_free(c->slot_cnt);
     dev_free(c->cell_cnt);
+    dev_free(c->mslot);
     cudaError_t e = dev_alloc(c->slot_cnt, cap_hash);
     if (e == cudaSuccess) e = dev_alloc(c->cell_cnt, (size_t)cap_hash * SPK_CELLS_PER_BLOCK);
+    if (e == cudaSuccess) e = dev_alloc(c->mslot, (size_t)cap_hash * 4); // SPK_MORTON_FACTOR entries per hash slot (spk_sort.cu)
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->dist_bbox, 0, 16 * sizeof(uint32_t), c->stream); // no Morton box yet
     c->slot_cnt_cap = e == cudaSuccess ? cap_hash : 0;
     return e;
 }
@@ -446,6 +449,8 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
     CK(cudaEventCreateWithFlags(&c->ev_counters, cudaEventDisableTiming));
     CK(cudaMalloc((void**)&c->d_counters, sizeof(DeviceCounters)));
     CK(cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)));
+    CK(cudaMalloc((void**)&c->dist_bbox, 24 * sizeof(uint32_t))); // bounding box of the active blocks + Morton boxes (spk_sort.cu)
+    CK(cudaMemset(c->dist_bbox, 0, 24 * sizeof(uint32_t)));
     CK(cudaHostAlloc((void**)&c->h_counters, sizeof(DeviceCounters), cudaHostAllocMapped));
     std::memset(c->h_counters, 0, sizeof(DeviceCounters));
     CK(cudaHostGetDevicePointer((void**)&c->h_counters_dev, c->h_counters, 0));
@@ -472,7 +477,7 @@ int spk_ctx_destroy(spk_ctx* c) {
     if (c->dist_arena) { c->grid[0].external_hash = c->grid[1].external_hash = 1; }
     free_particles(c);
     free_grid(c->grid[0]); free_grid(c->grid[1]);
-    dev_free(c->slot_cnt); dev_free(c->cell_cnt); dev_free(c->dispatch); dev_free(c->dispatch_nbr); dev_free(c->models); dev_free(c->colliders); dev_free(c->collider_data); dev_free(c->d_counters);
+    dev_free(c->slot_cnt); dev_free(c->cell_cnt); dev_free(c->mslot); dev_free(c->dispatch); dev_free(c->dispatch_nbr); dev_free(c->models); dev_free(c->colliders); dev_free(c->collider_data); dev_free(c->d_counters);
     if (c->staging) cudaFree(c->staging);
     cudaStreamSynchronize(c->halo_stream);
     for (int k = 0; k < 8; ++k) {
@@ -920,7 +925,7 @@ int spk_stage_sort(spk_ctx* c, SpkSortInfo* info) {
     if (c->n && !c->models) return SPK_ESTATE;
     for (int attempt = 0; attempt < 16; ++attempt) {
         GridBuffers& g = c->grid[1 - c->gcur];
-        CK(ensure_staging(c, ((size_t)g.cap_hash / 256 + 1) * 12)); // the scan partials of spk_launch_sort_bin: 12 bytes per scan tile (>= 256 hash slots)
+        CK(ensure_staging(c, ((size_t)g.cap_hash * 4 / 256 + 1) * 12)); // the scan partials of spk_launch_sort_bin: 12 bytes per scan tile (>= 256 entries of the Morton table, 4 per hash slot)
         CK(spk_launch_sort_bin(c));
         // The counter record (block / dispatch counts, overflow flag, dt candidate) is published to mapped host memory, then
         // the two kernels that finish the sort are enqueued for the grid's CAPACITY (they read the true block count on the
@@ -1351,6 +1356,14 @@ int spk_grid_read_nodes(spk_ctx* c, int which_grid, SpkGpuGridNode* dst, uint32_
     CK(cudaStreamSynchronize(c->stream));
     return SPK_OK;
 }
+int spk_grid_morton_box(spk_ctx* c, uint32_t out[8]) {
+    if (!c || !out) return SPK_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out, c->dist_bbox + 16, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SPK_OK;
+}
+
 // dispatch table in the reference's format: multiplicity = ceil(num_particles / 128) entries per block
 // (write_blocks_multiplicity_to_scan_value + init_gpu_dispatch_blocks_mapping, sort.rs:226-280), derived from the headers
 int spk_grid_read_dispatch(spk_ctx* c, SpkDispatchBlock2ActiveBlock* dst, uint32_t n) {

@@ -286,7 +286,6 @@ int spk_dist_export(spk_ctx* c, SpkDistDescriptor* out) {
     CK(cudaMalloc((void**)&c->dist_peer_ids, (size_t)(cap / 2) * SPK_MAX_RANKS * sizeof(int32_t)));
     CK(cudaMalloc((void**)&c->dist_push_ptrs, SPK_MAX_RANKS * sizeof(float*)));
     CK(cudaMemset(c->dist_push_ptrs, 0, SPK_MAX_RANKS * sizeof(float*)));
-    CK(cudaMalloc((void**)&c->dist_bbox, 6 * sizeof(uint32_t)));
     c->dist_push_wait = getenv("SPK_DIST_PUSH_WAIT") ? 1 : 0;
     c->dist_merge_in_update = 1;
     if (const char* m = getenv("SPK_DIST_MERGE")) c->dist_merge_in_update = std::strcmp(m, "kernel") != 0;

@@ -185,6 +185,7 @@ struct spk_ctx {
     int gcur;             // grid[gcur] = curr (read only), grid[1-gcur] = next
     uint32_t* slot_cnt;   // [cap_hash of next] particles per hash slot
     uint32_t* cell_cnt;   // [cap_hash of next][cells per block] particles per (hash slot, cell); after cell_scan_kernel: exclusive offsets inside the block
+    uint32_t* mslot;      // [4 x cap_hash of next] Morton table of the current sort: Morton code of a block -> hash slot + 1 (spk_sort.cu)
     uint32_t slot_cnt_cap;
     DispatchEntry* dispatch; uint32_t dispatch_cap;
     int32_t* dispatch_nbr; // [dispatch_cap][2 * SPK_NBR]: nbr_self | nbr_prev of the entry's block, so that a g2p2g CTA finds its tile with ONE load
@@ -208,7 +209,9 @@ struct spk_ctx {
     // multi-GPU (all zero / null in single-GPU runs)
     DistState dist;
     char* dist_arena; size_t dist_arena_bytes; uint32_t dist_cap_hash;
-    uint32_t* dist_bbox;                 // [6] device: bounding box of this rank's active blocks of the current sort (build_tables_kernel)
+    uint32_t* dist_bbox;                 // [24] device: [0..5] bounding box of this context's active blocks of the current sort (assign_ids_kernel; sent to the
+                                         // peers of a multi-GPU run), [8..15] the Morton box the current sort ranks its blocks in (spk_sort.cu: mstate),
+                                         // [16..23] the box the last completed sort used (spk_grid_morton_box)
     int dist_merge_in_update;            // 1 (default): grid_update folds the peers' halo sums itself; 0: separate merge kernel (A/B: SPK_DIST_MERGE=kernel)
     int dist_push_wait;                  // 1: a CTA that pushed halo sums waits for their remote completion (A/B: SPK_DIST_PUSH_WAIT=1); 0 (default): the
                                          // kernel boundary + the barrier's system fence order them before the flag

@@ -15,6 +15,9 @@
 #ifndef SPK_CELL_SCAN_SLOTS
 #define SPK_CELL_SCAN_SLOTS 2
 #endif
+#ifndef SPK_MORTON_FACTOR
+#define SPK_MORTON_FACTOR 4 /* Morton-table entries per hash slot (power of two) */
+#endif
 #ifndef SPK_PERM_ITEMS
 #define SPK_PERM_ITEMS 4
 #endif
@@ -29,6 +32,50 @@ constexpr int SCAN_ITEMS = SPK_SCAN_ITEMS; // slots per thread (few: the table h
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr int SPK_RANK_BITS = 32 - SPK_CELL_SHIFT; // rank_of = cell << SPK_RANK_BITS | rank inside the cell
 constexpr uint32_t SPK_RANK_MASK = (1u << SPK_RANK_BITS) - 1u;
+
+// ---- Morton-ordered block ids.  Block ids are ranks in a scan (no atomic counter); the scan runs over a dense table indexed by the
+// Morton code of the block coordinate relative to the bounding box of the active blocks (`mslot`: code -> hash slot + 1), so ids —
+// and with them the particle order, the per-block grid chunks and the dispatch order of g2p2g — follow a Z-curve through space
+// (the interleave of src_core/utils/morton3.rs:3-15, generalised to per-axis bit counts so a flat or elongated domain still fits).
+// The box is the one of the PREVIOUS sort, grown by the one block per substep a particle can travel (+1 for the {0,1}^3 activation);
+// a block outside it (first sort, upload in between, ...) raises `fail` and this sort ranks the hash slots instead: ids are then valid
+// but unordered, and the next sort has a fresh box.  mstate: [0..2] origin, [3..5] bits per axis, [6] valid, [7] fail.
+__device__ __forceinline__ uint32_t spk_morton_index(unsigned long long key, const uint32_t* ms) {
+#if SPK_DIM == 3
+    unsigned long long k[3];
+    spk_unpack_key(key, k[0], k[1], k[2]);
+#else
+    unsigned long long k[2];
+    spk_unpack_key(key, k[0], k[1]);
+#endif
+    uint32_t d[SPK_DIM], bits[SPK_DIM];
+    uint32_t maxbits = 0;
+#pragma unroll
+    for (int a = 0; a < SPK_DIM; ++a) {
+        d[a] = (uint32_t)k[a] - ms[a];
+        bits[a] = ms[3 + a];
+        if (k[a] < ms[a] || (k[a] - ms[a]) >> bits[a]) return 0xffffffffu;
+        maxbits = max(maxbits, bits[a]);
+    }
+    uint32_t out = 0, pos = 0;
+    for (uint32_t l = 0; l < maxbits; ++l)
+#pragma unroll
+        for (int a = 0; a < SPK_DIM; ++a)
+            if (l < bits[a]) out |= ((d[a] >> l) & 1u) << pos++;
+    return out;
+}
+__device__ __forceinline__ void spk_morton_register(uint32_t* mslot, uint32_t* ms, unsigned long long key, uint32_t slot) {
+    if (!ms[6] || slot == SPK_NO_BLOCK) return;
+    const uint32_t m = spk_morton_index(key, ms);
+    if (m == 0xffffffffu) ms[7] = 1u;
+    else mslot[m] = slot + 1u;
+}
+// the hash slot behind entry i of the scan domain (Morton table, or the hash table itself when there is no usable box)
+__device__ __forceinline__ uint32_t spk_scan_slot(uint32_t i, bool morton, const uint32_t* __restrict__ mslot, const unsigned long long* __restrict__ keys,
+                                                  uint32_t cap_hash) {
+    if (morton) return mslot[i] - 1u; // 0 -> SPK_NO_BLOCK
+    return (i < cap_hash && keys[i] != SPK_EMPTY_KEY) ? i : SPK_NO_BLOCK;
+}
 
 // K1: one pass over the positions.  Per particle: block key + cell inside the block; per (warp, block) one hash insert; per
 // (warp, block, cell) one atomicAdd on the cell counter of the block's hash slot, which also hands out the particle's rank inside
@@ -76,8 +123,10 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4
 // (gpu_grid.rs:307-321).  Slots created here own no particles: their counters are all zero whether or not their warp sees the key.
 constexpr int CELL_SCAN_SLOTS = SPK_CELL_SCAN_SLOTS; // hash slots per warp (most are empty: the table is at most half full)
 __global__ void __launch_bounds__(256) cell_scan_kernel(unsigned long long* keys, uint32_t cap_hash, uint32_t* cell_cnt, uint32_t* __restrict__ slot_cnt,
-                                                          DeviceCounters* counters) {
+                                                          DeviceCounters* counters, uint32_t* bbox, uint32_t* mslot) {
     const int lane = threadIdx.x & 31;
+    uint32_t* ms = bbox + 8;
+    if (blockIdx.x == 0 && threadIdx.x < 6) bbox[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u; // empty box for assign_ids_kernel's min / max
     const uint32_t s0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * CELL_SCAN_SLOTS;
     for (uint32_t s = s0; s < s0 + CELL_SCAN_SLOTS && s < cap_hash; ++s) {
         // lane 0's view of the slot decides for the warp: the lanes that activated neighbours in the previous iteration arrive here
@@ -106,9 +155,13 @@ __global__ void __launch_bounds__(256) cell_scan_kernel(unsigned long long* keys
 #else
         if (lane < SPK_CELLS_PER_BLOCK) cc[lane] = inc - mine;
 #endif
-        if (lane == 0) slot_cnt[s] = total;
-        if (lane >= 1 && lane < SPK_NBR)
-            if (spk_hash_insert(keys, cap_hash, spk_key_offset(key, lane)) == SPK_NO_BLOCK) counters->overflow = 1;
+        if (lane == 0) { slot_cnt[s] = total; spk_morton_register(mslot, ms, key, s); }
+        if (lane >= 1 && lane < SPK_NBR) {
+            const unsigned long long nkey = spk_key_offset(key, lane);
+            const uint32_t ns = spk_hash_insert(keys, cap_hash, nkey);
+            if (ns == SPK_NO_BLOCK) counters->overflow = 1;
+            spk_morton_register(mslot, ms, nkey, ns);
+        }
     }
 }
 
@@ -137,9 +190,9 @@ __device__ __forceinline__ Triple block_exclusive_scan(Triple v, Triple& total) 
     return Triple{base.occ + inc.occ - v.occ, base.cnt + inc.cnt - v.cnt, base.mult + inc.mult - v.mult};
 }
 
-__device__ __forceinline__ Triple slot_triple(const unsigned long long* keys, const uint32_t* slot_cnt, uint32_t s, uint32_t cap_hash, uint32_t chunk) {
+__device__ __forceinline__ Triple slot_triple(const uint32_t* slot_cnt, uint32_t s, uint32_t chunk) { // s: hash slot or SPK_NO_BLOCK
     Triple t{0, 0, 0};
-    if (s < cap_hash && keys[s] != SPK_EMPTY_KEY) {
+    if (s != SPK_NO_BLOCK) {
         t.occ = 1;
         t.cnt = slot_cnt[s];
         t.mult = (t.cnt + chunk - 1) / chunk;
@@ -149,11 +202,13 @@ __device__ __forceinline__ Triple slot_triple(const unsigned long long* keys, co
 
 // pass 1 of reduce-then-scan: per-CTA totals of (occupied slots, particles, dispatch entries)
 __global__ void __launch_bounds__(SCAN_THREADS) slot_totals_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ slot_cnt,
-                                                                    uint32_t cap_hash, uint32_t chunk, Triple* partials) {
+                                                                    uint32_t cap_hash, uint32_t chunk, Triple* partials, const uint32_t* __restrict__ mslot,
+                                                                    const uint32_t* __restrict__ ms) {
     Triple acc{0, 0, 0};
+    const bool morton = ms[6] && !ms[7];
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) acc = acc + slot_triple(keys, slot_cnt, base + k, cap_hash, chunk);
+    for (int k = 0; k < SCAN_ITEMS; ++k) acc = acc + slot_triple(slot_cnt, spk_scan_slot(base + k, morton, mslot, keys, cap_hash), chunk);
     Triple total;
     block_exclusive_scan(acc, total);
     if (threadIdx.x == 0) partials[blockIdx.x] = total;
@@ -162,8 +217,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) slot_totals_kernel(const unsigne
 // pass 2: ids = rank of the slot, first_particle / dispatch base = exclusive prefix sums (replaces K6-K9, K11, K12)
 __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ slot_cnt,
                                                                    uint32_t cap_hash, uint32_t chunk, const Triple* __restrict__ partials, uint32_t* vals,
-                                                                   GridBuffers g, DispatchEntry* dispatch, uint32_t dispatch_cap, DeviceCounters* counters, uint32_t* bbox) {
+                                                                   GridBuffers g, DispatchEntry* dispatch, uint32_t dispatch_cap, DeviceCounters* counters, uint32_t* bbox,
+                                                                   const uint32_t* __restrict__ mslot) {
     __shared__ Triple s_base;
+    const uint32_t* ms = bbox + 8;
+    const bool morton = ms[6] && !ms[7];
     // redundant reduction of the partials of all previous CTAs (at most a few hundred values)
     Triple pre{0, 0, 0};
     for (uint32_t j = threadIdx.x; j < blockIdx.x; j += SCAN_THREADS) pre = pre + partials[j];
@@ -174,16 +232,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned
     const Triple cta_base = s_base;
 
     Triple item[SCAN_ITEMS];
+    uint32_t slot_of_item[SCAN_ITEMS];
     Triple acc{0, 0, 0};
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) { item[k] = slot_triple(keys, slot_cnt, base + k, cap_hash, chunk); acc = acc + item[k]; }
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        slot_of_item[k] = spk_scan_slot(base + k, morton, mslot, keys, cap_hash);
+        item[k] = slot_triple(slot_cnt, slot_of_item[k], chunk);
+        acc = acc + item[k];
+    }
     Triple total;
     Triple run = block_exclusive_scan(acc, total) + cta_base;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
         if (item[k].occ) {
-            const uint32_t s = base + k, id = run.occ;
+            const uint32_t s = slot_of_item[k], id = run.occ;
             vals[s] = id;
             if (id < g.cap_blocks) {
                 g.blk_key[id] = keys[s];
@@ -206,9 +269,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned
         counters->nab = run.occ;
         counters->ndispatch = run.mult;
         counters->nparticles_binned = run.cnt;
-        if (bbox) { // multi-GPU: empty bounding box for build_tables_kernel's min / max (no memsets)
-            bbox[0] = bbox[1] = bbox[2] = 0xffffffffu;
-            bbox[3] = bbox[4] = bbox[5] = 0u;
+    }
+    { // bounding box of the active blocks (raw key coordinates; the next sort's Morton box, and what the peers of a multi-GPU run are told):
+      // thread -> warp -> CTA, then six atomics per CTA
+        __shared__ uint32_t s_box[SCAN_THREADS / 32][6];
+        uint32_t lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (item[k].occ) {
+                unsigned long long kx, ky, kz = 0;
+#if SPK_DIM == 3
+                spk_unpack_key(keys[slot_of_item[k]], kx, ky, kz);
+#else
+                spk_unpack_key(keys[slot_of_item[k]], kx, ky);
+#endif
+                lo[0] = min(lo[0], (uint32_t)kx); lo[1] = min(lo[1], (uint32_t)ky); lo[2] = min(lo[2], (uint32_t)kz);
+                hi[0] = max(hi[0], (uint32_t)kx); hi[1] = max(hi[1], (uint32_t)ky); hi[2] = max(hi[2], (uint32_t)kz);
+            }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = __reduce_min_sync(0xffffffffu, lo[a]); hi[a] = __reduce_max_sync(0xffffffffu, hi[a]); }
+        if ((threadIdx.x & 31) == 0)
+            for (int a = 0; a < 3; ++a) { s_box[threadIdx.x >> 5][a] = lo[a]; s_box[threadIdx.x >> 5][3 + a] = hi[a]; }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            uint32_t v = s_box[0][threadIdx.x];
+            for (int w = 1; w < SCAN_THREADS / 32; ++w) v = threadIdx.x < 3 ? min(v, s_box[w][threadIdx.x]) : max(v, s_box[w][threadIdx.x]);
+            // (a CTA without blocks holds the neutral elements; the plain read first skips the atomic once the box already covers this CTA's)
+            const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&bbox[threadIdx.x]);
+            if (threadIdx.x < 3) { if (v < cur) atomicMin(&bbox[threadIdx.x], v); }
+            else if (v > cur) atomicMax(&bbox[threadIdx.x], v);
         }
     }
 }
@@ -217,27 +306,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) assign_ids_kernel(const unsigned
 // (launched for the grid's block CAPACITY before the host has read the block count back, so that the read-back overlaps this
 // kernel and scatter_perm_kernel; the true count comes from the device-side record)
 __global__ void build_tables_kernel(GridBuffers next, GridBuffers prev, DeviceCounters* counters, int32_t* __restrict__ dispatch_nbr,
-                                    uint32_t dispatch_cap, uint32_t chunk, uint32_t* bbox) {
+                                    uint32_t dispatch_cap, uint32_t chunk, uint32_t* bbox, uint32_t mcap) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) { // the counter record of this sort has been published: reset the words the rest of the substep accumulates into (no memsets)
         counters->dt_raw_bits = SPK_DT_RAW_NONE; // g2p2g's fused CFL candidate (atomicMin)
         counters->num_halo = 0;                  // multi-GPU halo detection (atomicAdd)
+        // the Morton box of the NEXT sort: this sort's bounding box grown by one block towards the origin and two away from it
+        uint32_t* ms = bbox + 8;
+        for (int k = 0; k < 8; ++k) bbox[16 + k] = ms[k]; // the box THIS sort used, for spk_grid_morton_box
+        uint32_t total_bits = 0;
+        bool ok = counters->nab > 0 && !counters->overflow;
+        for (int a = 0; a < SPK_DIM; ++a) {
+            ok = ok && bbox[a] >= 1u && bbox[3 + a] >= bbox[a];
+            const uint32_t ext = bbox[3 + a] - bbox[a] + 3u;
+            uint32_t b = 0;
+            while (b < 31u && (1u << b) < ext) ++b;
+            ms[a] = bbox[a] - 1u;
+            ms[3 + a] = b;
+            total_bits += b;
+        }
+        ms[6] = (ok && total_bits < 32u && (1u << total_bits) <= mcap) ? 1u : 0u;
+        ms[7] = 0u;
     }
     const uint32_t b = t >> SPK_NBR_SHIFT, o = t & (SPK_NBR - 1);
     const bool live = b < counters->nab && b < next.cap_blocks;
-#if SPK_DIM == 3
-    if (bbox) { // multi-GPU: bounding box of the active blocks (raw key coordinates), one atomic per warp and bound
-        unsigned long long kx = 0, ky = 0, kz = 0;
-        if (live) spk_unpack_key(next.blk_key[b], kx, ky, kz);
-        const uint32_t lo[3] = {live ? (uint32_t)kx : 0xffffffffu, live ? (uint32_t)ky : 0xffffffffu, live ? (uint32_t)kz : 0xffffffffu};
-        const uint32_t hi[3] = {live ? (uint32_t)kx : 0u, live ? (uint32_t)ky : 0u, live ? (uint32_t)kz : 0u};
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const uint32_t mn = __reduce_min_sync(0xffffffffu, lo[a]), mx = __reduce_max_sync(0xffffffffu, hi[a]);
-            if ((threadIdx.x & 31) == 0 && mn <= mx) { atomicMin(&bbox[a], mn); atomicMax(&bbox[3 + a], mx); }
-        }
-    }
-#endif
     if (!live) return;
     const unsigned long long key = spk_key_offset(next.blk_key[b], (int)o);
     const int32_t ns = spk_hash_get(next, key), np = spk_hash_get(prev, key);
@@ -288,19 +380,22 @@ cudaError_t spk_launch_sort_bin(spk_ctx* c) {
     if ((e = cudaMemsetAsync(c->slot_cnt, 0, (size_t)g.cap_hash * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(c->cell_cnt, 0, (size_t)g.cap_hash * SPK_CELLS_PER_BLOCK * 4, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(c->d_counters, 0, 16, s)) != cudaSuccess) return e; // nab, ndispatch, overflow, nparticles_binned
+    const uint32_t mcap = g.cap_hash * SPK_MORTON_FACTOR; // entries of the Morton table (= of the scan domain)
+    if ((e = cudaMemsetAsync(c->mslot, 0, (size_t)mcap * 4, s)) != cudaSuccess) return e;
     c->counters_fresh = false;
     const uint32_t n = (uint32_t)c->n;
     if (n) {
         bin_particles_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->pb[c->cur].a0, n, c->cell_width, 1.0f / c->cell_width, g.keys, g.cap_hash, c->cell_cnt,
                                                                                         c->slot_of, c->rank_of, c->d_counters);
-        cell_scan_kernel<<<(g.cap_hash + 8 * CELL_SCAN_SLOTS - 1) / (8 * CELL_SCAN_SLOTS), 256, 0, s>>>(g.keys, g.cap_hash, c->cell_cnt, c->slot_cnt, c->d_counters);
+        cell_scan_kernel<<<(g.cap_hash + 8 * CELL_SCAN_SLOTS - 1) / (8 * CELL_SCAN_SLOTS), 256, 0, s>>>(g.keys, g.cap_hash, c->cell_cnt, c->slot_cnt, c->d_counters, c->dist_bbox, c->mslot);
         c->launches += 2;
     }
-    const uint32_t ntiles = (g.cap_hash + SCAN_TILE - 1) / SCAN_TILE;
+    const uint32_t ntiles = (mcap + SCAN_TILE - 1) / SCAN_TILE;
     if ((size_t)ntiles * sizeof(Triple) > c->staging_bytes) return cudaErrorInvalidValue; // sized by spk_stage_sort (ensure_staging) before the launch
     Triple* partials = (Triple*)c->staging;
-    slot_totals_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials);
-    assign_ids_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials, g.vals, g, c->dispatch, c->dispatch_cap, c->d_counters, c->dist_bbox);
+    slot_totals_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials, c->mslot, c->dist_bbox + 8);
+    assign_ids_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(g.keys, c->slot_cnt, g.cap_hash, c->chunk, partials, g.vals, g, c->dispatch, c->dispatch_cap, c->d_counters, c->dist_bbox,
+                                                      c->mslot);
     c->launches += 2;
     return cudaGetLastError();
 }
@@ -311,7 +406,8 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c) {
     cudaStream_t s = c->stream;
     const uint32_t n = (uint32_t)c->n;
     {
-        build_tables_kernel<<<(g.cap_blocks * SPK_NBR + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters, c->dispatch_nbr, c->dispatch_cap, c->chunk, c->dist_bbox);
+        build_tables_kernel<<<(g.cap_blocks * SPK_NBR + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters, c->dispatch_nbr, c->dispatch_cap, c->chunk, c->dist_bbox,
+                                                                                 g.cap_hash * SPK_MORTON_FACTOR);
         c->launches += 1;
         // multi-GPU: this rank's hash table and bounding box are final -> tell the peers now (the arrive half of the barrier that precedes the
         // halo detection); its wait half runs ~60 us of independent work later (permutation, grid reset), when the peers' flags have landed

@@ -39,7 +39,8 @@ def declare(lib, prefix: str):
         "grid_read_nodes": [_vp, C.c_int, _vp, C.c_uint32],
         "grid_read_dispatch": [_vp, _vp, C.c_uint32],
     }
-    optional = {"stage_recompute_fluids_volume": [_vp]}  # not part of the reference's compiled module: absent from the `ref_` harness
+    # not part of the reference's compiled module (absent from the `ref_` harness) / a property of this library's sort only (absent from the oracle too)
+    optional = {"stage_recompute_fluids_volume": [_vp], "grid_morton_box": [_vp, _vp]}
     for name, args in list(sig.items()) + [(k, v) for k, v in optional.items() if hasattr(lib, prefix + k)]:
         fn = getattr(lib, prefix + name)
         fn.argtypes = args
@@ -171,6 +172,12 @@ class Engine:
         out = np.zeros((n, getattr(self.T, "CELLS_PER_BLOCK", 64)), self.T.GRID_NODE)
         if n:
             self._call("grid_read_nodes", which_grid, _ptr(out), n)
+        return out
+
+    def morton_box(self) -> np.ndarray:
+        """spk_grid_morton_box: origin[3], bits[3], had-a-box, a-block-fell-outside of the last sort"""
+        out = np.zeros(8, np.uint32)
+        self._call("grid_morton_box", _ptr(out))
         return out
 
     def dispatch(self, n: int) -> np.ndarray:

@@ -66,7 +66,8 @@ def test_dim3_api_bodies_on_the_emulation(emulated, name):
     getattr(T, name)()
 
 
-@pytest.mark.parametrize("name", ["test_negative_far_and_nan_coordinates", "test_failed_and_static_particles", "test_model_table_with_unused_entries"])
+@pytest.mark.parametrize("name", ["test_negative_far_and_nan_coordinates", "test_failed_and_static_particles", "test_model_table_with_unused_entries",
+                                  "test_block_ids_follow_the_morton_curve"])
 # (test_hash_map_grows_when_blocks_outnumber_the_estimate also passes on the emulation but takes a minute there: GPU suite only)
 def test_dim3_edge_cases_on_the_emulation(emulated, oracle, name):
     import tests.test_edge_gpu as T
