@@ -40,7 +40,7 @@ CONFIGS = {
     "C16M": {"scene": "cube_through_sand3", "dims": (400, 200, 200, 100), "scaling": "strong", "what": "examples3d/cube_through_sand3.rs scaled: kinematic block through Drucker-Prager sand"},
     "N32M": {"scene": "neo_hookean_block", "dims": (400, 400, 200), "scaling": "weak", "what": "synthetic uniform-density Neo-Hookean block, 32 M particles per GPU (256 M on 8)"},
 }
-MIGRATE_EVERY = 10
+MIGRATE_EVERY = 20
 CPU_SAMPLES = {"S4M": (100, 50, 50), "F1M": (80, 40, 40), "C16M": (100, 50, 50, 25), "N32M": (100, 100, 50)}  # bounded CPU samples of the same scenes
 
 
@@ -156,7 +156,7 @@ def build_scene(rank, world, dims, config="S4M"):
     if world == 1:
         return sc, None
     x = sc.particles.position["point"][:, 0]
-    part = SlabPartition.uniform(float(x.min()), float(x.max()), world, sc.cell_width)
+    part = SlabPartition.balanced(x, world, sc.cell_width)  # equal particle counts per slab (the kinematic block starts beside the sand: equal widths would not be)
     mine = np.nonzero(part.owner(x, sc.cell_width) == rank)[0]
     sub = scenes.Scene(sc.name, sc.cell_width, sc.particles.take(mine), sc.models, sc.colliders, sc.gravity, sc.params)
     sub.global_ids = mine.astype(np.uint32)

@@ -212,6 +212,18 @@ class SlabPartition:
             edges[r] = max(edges[r], edges[r - 1] + 1)
         return cls(edges)
 
+    @classmethod
+    def balanced(cls, x: np.ndarray, world: int, cell_width: float):
+        """`world` slabs holding (nearly) equal particle counts: the edges are the quantiles of the particles' block-x coordinates"""
+        bx = np.sort(cls.block_x(x, cell_width))
+        edges = np.empty(world + 1, np.int64)
+        edges[0], edges[world] = bx[0], bx[-1] + 1
+        for r in range(1, world):
+            edges[r] = bx[min(len(bx) - 1, (len(bx) * r) // world)]
+        for r in range(1, world + 1):
+            edges[r] = max(edges[r], edges[r - 1] + 1)
+        return cls(edges)
+
     @staticmethod
     def block_x(x: np.ndarray, cell_width: float) -> np.ndarray:
         q = np.asarray(x, np.float32) / np.float32(cell_width)
