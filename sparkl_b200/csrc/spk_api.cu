@@ -436,12 +436,20 @@ int spk_ctx_create(int device, float cell_width, uint32_t block_capacity, spk_ct
 #else
     c->g2p2g_mode = 1;
 #endif
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // the main stream outranks the side stream (grid update, grid reset, multi-GPU exchange): where both have CTAs ready — the side
+        // stream's bandwidth-bound kernels next to the sort's binning pass — the block scheduler serves the critical path first and the
+        // side work fills what the sort's small latency-bound kernels leave idle (SPK_STREAM_PRIORITY=0: all streams equal, A/B)
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        const bool prio = !(getenv("SPK_STREAM_PRIORITY") && atoi(getenv("SPK_STREAM_PRIORITY")) == 0);
+        CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio ? greatest : least));
+    }
     CK(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->gu_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_transfer_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_gu_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_tables, cudaEventDisableTiming));
     c->overlap_grid_update = getenv("SPK_NO_GU_OVERLAP") ? 0 : 1;
     CK(cudaEventCreateWithFlags(&c->up_ready, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->up_consumed, cudaEventDisableTiming));
@@ -497,7 +505,7 @@ int spk_ctx_destroy(spk_ctx* c) {
     if (c->up_staging) cudaFree(c->up_staging);
     cudaEventDestroy(c->up_ready); cudaEventDestroy(c->up_consumed);
     cudaStreamDestroy(c->stream); cudaStreamDestroy(c->halo_stream); cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->gu_stream);
-    cudaEventDestroy(c->ev_transfer_done); cudaEventDestroy(c->ev_gu_done);
+    cudaEventDestroy(c->ev_transfer_done); cudaEventDestroy(c->ev_gu_done); cudaEventDestroy(c->ev_tables);
     delete c;
     return SPK_OK;
 }
@@ -1231,12 +1239,25 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
         SpkSortInfo info;
         if ((rc = spk_stage_sort(c, &info))) return rc;
         if (timings) CK(cudaEventRecord(ev[1], c->stream));
-        if ((rc = spk_join_grid_update(c))) return rc; // reset / g2p2g read what the last grid update wrote
-        CK(spk_launch_reset_grid(c));
+        const bool side = !timings && c->overlap_grid_update && (!dist || c->dist_split_barriers);
+        if (side) {
+            // the grid reset goes to the side stream: there it follows the last grid update by stream order, needs only this sort's block
+            // tables (ev_tables, recorded before the permutation scatter) and runs next to the scatter; g2p2g joins the side stream below
+            CK(cudaStreamWaitEvent(c->gu_stream, c->ev_tables, 0));
+            cudaStream_t main_stream = c->stream;
+            c->stream = c->gu_stream;
+            const cudaError_t re = spk_launch_reset_grid(c);
+            c->stream = main_stream;
+            CK(re);
+            CK(cudaEventRecord(c->ev_gu_done, c->gu_stream));
+            c->gu_pending = true;
+        } else {
+            if ((rc = spk_join_grid_update(c))) return rc; // reset / g2p2g read what the last grid update wrote
+            CK(spk_launch_reset_grid(c));
+        }
         if (timings) CK(cudaEventRecord(ev[2], c->stream));
         float dt;
         if ((rc = spk_stage_estimate_dt(c, min_dt, std::fmin(remaining, params->max_substep_dt), &dt))) return rc;
-        const bool side = !timings && c->overlap_grid_update && (!dist || c->dist_split_barriers);
         if (dist) { // every rank has built its hash table: find the blocks shared with the peers
             // With the push kernel (the default) only the side-stream work after g2p2g reads what the detection writes (halo bits, the peers'
             // block ids): the wait for the peers and the probes of their hash tables over NVLink then run on the side stream, next to this
@@ -1255,6 +1276,7 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
             CK(de);
         }
         if (timings) CK(cudaEventRecord(ev[3], c->stream));
+        if ((rc = spk_join_grid_update(c))) return rc; // (side: the grid reset; the detection queued behind it is not waited for)
         if ((rc = launch_g2p2g_hooked(c, dt))) return rc;
         if (timings) CK(cudaEventRecord(ev[4], c->stream));
         if (dist && !side) { // NVLink red.add of the shared blocks into the peers, barrier (+ global dt minimum), fold what arrived

@@ -157,7 +157,7 @@ struct spk_ctx {
     cudaStream_t stream, halo_stream;
     // spk_step runs the grid update of substep n on its own stream, next to the particle sort of substep n + 1 (both only depend on
     // g2p2g of substep n); `gu_pending`: the main stream has not yet been ordered behind the last grid update
-    cudaStream_t gu_stream; cudaEvent_t ev_transfer_done, ev_gu_done; bool gu_pending; int overlap_grid_update;
+    cudaStream_t gu_stream; cudaEvent_t ev_transfer_done, ev_gu_done, ev_tables; bool gu_pending; int overlap_grid_update;
     // particles
     size_t n, cap;
     int cur; // index of the current particle buffer

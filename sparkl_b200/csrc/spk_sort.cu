@@ -409,6 +409,7 @@ cudaError_t spk_launch_sort_finish(spk_ctx* c) {
         build_tables_kernel<<<(g.cap_blocks * SPK_NBR + 255) / 256, 256, 0, s>>>(g, prev, c->d_counters, c->dispatch_nbr, c->dispatch_cap, c->chunk, c->dist_bbox,
                                                                                  g.cap_hash * SPK_MORTON_FACTOR);
         c->launches += 1;
+        { cudaError_t e = cudaEventRecord(c->ev_tables, s); if (e != cudaSuccess) return e; } // spk_step: the grid reset may start (side stream)
         // multi-GPU: this rank's hash table and bounding box are final -> tell the peers now (the arrive half of the barrier that precedes the
         // halo detection); its wait half runs ~60 us of independent work later (permutation, grid reset), when the peers' flags have landed
         if (spk_dist_active(c) && c->dist_split_barriers) {
