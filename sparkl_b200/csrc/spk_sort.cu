@@ -12,6 +12,14 @@
 //    g2p2g / reset never probe the hash map.
 #include "spk_device.cuh"
 
+#ifdef SPK_EMU // the CUDA emulation of the CPU test suite pays per emulated thread, not per unit of latency: coarse work items there
+#ifndef SPK_CELL_SCAN_SLOTS
+#define SPK_CELL_SCAN_SLOTS 16
+#endif
+#ifndef SPK_SCAN_ITEMS
+#define SPK_SCAN_ITEMS 16
+#endif
+#endif
 #ifndef SPK_CELL_SCAN_SLOTS
 #define SPK_CELL_SCAN_SLOTS 2
 #endif
@@ -64,10 +72,10 @@ __device__ __forceinline__ uint32_t spk_morton_index(unsigned long long key, con
             if (l < bits[a]) out |= ((d[a] >> l) & 1u) << pos++;
     return out;
 }
-__device__ __forceinline__ void spk_morton_register(uint32_t* mslot, uint32_t* ms, unsigned long long key, uint32_t slot) {
+__device__ __forceinline__ void spk_morton_register(uint32_t* mslot, uint32_t mcap, uint32_t* ms, unsigned long long key, uint32_t slot) {
     if (!ms[6] || slot == SPK_NO_BLOCK) return;
     const uint32_t m = spk_morton_index(key, ms);
-    if (m == 0xffffffffu) ms[7] = 1u;
+    if (m >= mcap) ms[7] = 1u; // outside the box (0xffffffff), or a box sized for the other grid buffer's larger table
     else mslot[m] = slot + 1u;
 }
 // the hash slot behind entry i of the scan domain (Morton table, or the hash table itself when there is no usable box)
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_particles_kernel(const float4
 // (gpu_grid.rs:307-321).  Slots created here own no particles: their counters are all zero whether or not their warp sees the key.
 constexpr int CELL_SCAN_SLOTS = SPK_CELL_SCAN_SLOTS; // hash slots per warp (most are empty: the table is at most half full)
 __global__ void __launch_bounds__(256) cell_scan_kernel(unsigned long long* keys, uint32_t cap_hash, uint32_t* cell_cnt, uint32_t* __restrict__ slot_cnt,
-                                                          DeviceCounters* counters, uint32_t* bbox, uint32_t* mslot) {
+                                                          DeviceCounters* counters, uint32_t* bbox, uint32_t* mslot, uint32_t mcap) {
     const int lane = threadIdx.x & 31;
     uint32_t* ms = bbox + 8;
     if (blockIdx.x == 0 && threadIdx.x < 6) bbox[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u; // empty box for assign_ids_kernel's min / max
@@ -155,12 +163,12 @@ __global__ void __launch_bounds__(256) cell_scan_kernel(unsigned long long* keys
 #else
         if (lane < SPK_CELLS_PER_BLOCK) cc[lane] = inc - mine;
 #endif
-        if (lane == 0) { slot_cnt[s] = total; spk_morton_register(mslot, ms, key, s); }
+        if (lane == 0) { slot_cnt[s] = total; spk_morton_register(mslot, mcap, ms, key, s); }
         if (lane >= 1 && lane < SPK_NBR) {
             const unsigned long long nkey = spk_key_offset(key, lane);
             const uint32_t ns = spk_hash_insert(keys, cap_hash, nkey);
             if (ns == SPK_NO_BLOCK) counters->overflow = 1;
-            spk_morton_register(mslot, ms, nkey, ns);
+            spk_morton_register(mslot, mcap, ms, nkey, ns);
         }
     }
 }
@@ -387,7 +395,7 @@ cudaError_t spk_launch_sort_bin(spk_ctx* c) {
     if (n) {
         bin_particles_kernel<<<(n + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(c->pb[c->cur].a0, n, c->cell_width, 1.0f / c->cell_width, g.keys, g.cap_hash, c->cell_cnt,
                                                                                         c->slot_of, c->rank_of, c->d_counters);
-        cell_scan_kernel<<<(g.cap_hash + 8 * CELL_SCAN_SLOTS - 1) / (8 * CELL_SCAN_SLOTS), 256, 0, s>>>(g.keys, g.cap_hash, c->cell_cnt, c->slot_cnt, c->d_counters, c->dist_bbox, c->mslot);
+        cell_scan_kernel<<<(g.cap_hash + 8 * CELL_SCAN_SLOTS - 1) / (8 * CELL_SCAN_SLOTS), 256, 0, s>>>(g.keys, g.cap_hash, c->cell_cnt, c->slot_cnt, c->d_counters, c->dist_bbox, c->mslot, mcap);
         c->launches += 2;
     }
     const uint32_t ntiles = (mcap + SCAN_TILE - 1) / SCAN_TILE;

@@ -150,3 +150,22 @@ def test_migration_keeps_results_and_rehomes_particles(tmp_path, oracle):
     assert util.rel_err(pos["point"], ref.position["point"]) < 2e-5
     assert util.rel_err(vel["vector"], ref.velocity["vector"], floor=1e-2) < 2e-3
     assert util.rel_err(vol["deformation_gradient"], ref.volume["deformation_gradient"], floor=1.0) < 2e-4
+
+
+def test_balanced_slab_partition_splits_by_particle_count():
+    """`SlabPartition.balanced` (bench.py --config C16M): slab edges at the quantiles of the particles' block columns — every rank owns
+    about the same number of particles even when the cloud is lopsided, edges strictly increase, ownership covers every particle"""
+    from sparkl_b200.distributed import SlabPartition
+    rng = np.random.Generator(np.random.PCG64(3))
+    x = np.concatenate([rng.uniform(-9.0, -8.0, 2000), rng.uniform(0.0, 40.0, 98000)]).astype(np.float32)  # a small far cluster + the bulk
+    for world in (2, 4, 8):
+        part = SlabPartition.balanced(x, world, 0.2)
+        assert part.world == world and (np.diff(part.bounds) > 0).all()
+        owner = part.owner(x, 0.2)
+        counts = np.bincount(owner, minlength=world)
+        assert counts.sum() == len(x) and counts.min() > 0.7 * len(x) / world and counts.max() < 1.3 * len(x) / world, counts
+        uni = SlabPartition.uniform(float(x.min()), float(x.max()), world, 0.2)
+        assert np.bincount(uni.owner(x, 0.2), minlength=world).max() >= counts.max()
+    # degenerate: fewer occupied block columns than ranks still yields strictly increasing edges
+    part = SlabPartition.balanced(np.full(100, 1.0, np.float32), 4, 0.2)
+    assert (np.diff(part.bounds) > 0).all() and (part.owner(np.full(100, 1.0, np.float32), 0.2) < 4).all()
