@@ -40,7 +40,7 @@ CONFIGS = {
     "C16M": {"scene": "cube_through_sand3", "dims": (400, 200, 200, 100), "scaling": "strong", "what": "examples3d/cube_through_sand3.rs scaled: kinematic block through Drucker-Prager sand"},
     "N32M": {"scene": "neo_hookean_block", "dims": (400, 400, 200), "scaling": "weak", "what": "synthetic uniform-density Neo-Hookean block, 32 M particles per GPU (256 M on 8)"},
 }
-MIGRATE_EVERY = 20
+MIGRATE_EVERY = int(os.environ.get("SPK_BENCH_MIGRATE_EVERY", "20"))
 CPU_SAMPLES = {"S4M": (100, 50, 50), "F1M": (80, 40, 40), "C16M": (100, 50, 50, 25), "N32M": (100, 100, 50)}  # bounded CPU samples of the same scenes
 
 
@@ -330,6 +330,11 @@ def run_ours(args):
     ctx = context_from_scene(sc, device=local)
     if partition is not None:
         ctx.set_gids(sc.global_ids)
+        # NCCL opens its point-to-point connections lazily, ~100 ms the first time a PAIR of ranks talks; the migration of a block that
+        # crosses the slabs reaches new pairs one after the other: open all of them once, outside the timed region
+        warm = torch.zeros(world, dtype=torch.uint8, device=torch.device("cuda", local))
+        dist.all_to_all_single(torch.empty_like(warm), warm)
+        torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=torch.device("cuda", local))
     params = abi.SolverParameters(stop_after_one_substep=1)
     pipe = None

@@ -496,6 +496,7 @@ int spk_ctx_destroy(spk_ctx* c) {
     if (c->dist_peer_ids) cudaFree(c->dist_peer_ids);
     if (c->dist_push_ptrs) cudaFree(c->dist_push_ptrs);
     if (c->dist_bbox) cudaFree(c->dist_bbox);
+    if (c->mg_scratch) cudaFree(c->mg_scratch);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_upload) cudaFreeHost(c->h_upload);
     for (auto& e : c->ev) cudaEventDestroy(e);

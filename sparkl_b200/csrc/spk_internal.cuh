@@ -185,6 +185,7 @@ struct spk_ctx {
     int gcur;             // grid[gcur] = curr (read only), grid[1-gcur] = next
     uint32_t* slot_cnt;   // [cap_hash of next] particles per hash slot
     uint32_t* cell_cnt;   // [cap_hash of next][cells per block] particles per (hash slot, cell); after cell_scan_kernel: exclusive offsets inside the block
+    char* mg_scratch; size_t mg_scratch_bytes; // grow-only scratch of the particle-migration passes (spk_migrate.cu)
     uint32_t* mslot;      // [4 x cap_hash of next] Morton table of the current sort: Morton code of a block -> hash slot + 1 (spk_sort.cu)
     uint32_t slot_cnt_cap;
     DispatchEntry* dispatch; uint32_t dispatch_cap;

@@ -321,18 +321,28 @@ def migrate_device(ctx, partition: SlabPartition, dist=None, device=None, wire=N
             bounds[rank] = max(bounds[rank] - hysteresis, bounds[rank - 1] + 1)
         if rank < world - 1:
             bounds[rank + 1] = min(bounds[rank + 1] + hysteresis, bounds[rank + 2] - 1)
+    import os as _os, time as _time
+    _dbg = _os.environ.get("SPK_MIGRATE_DEBUG")
+    _t = [_time.perf_counter()]
+    def _mark():
+        if _dbg:
+            torch.cuda.synchronize()
+            _t.append(_time.perf_counter())
     counts = ctx.migrate_out(bounds, rank)  # count only
+    _mark()
     mine = torch.tensor(counts.astype(np.int64), dtype=torch.int64, device=device)
     table = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(table, mine)
     table = torch.stack(table).cpu().numpy()  # table[src, dst]
     n_sent, n_recv = int(table[rank].sum()), int(table[:, rank].sum())
+    _mark()
     if table.sum() == 0:
         return 0, 0
     send = torch.empty(max(n_sent, 1) * row, dtype=torch.uint8, device=device)
     if n_sent:
         again = ctx.migrate_out(bounds, rank, send.data_ptr(), n_sent)
         assert np.array_equal(again, counts)
+    _mark()
     offs = np.concatenate([[0], np.cumsum(table[rank])]) * row  # rows are grouped by destination rank
     recv = torch.empty(max(n_recv, 1) * row, dtype=torch.uint8, device=device)
     roffs = np.concatenate([[0], np.cumsum(table[:, rank])]) * row
@@ -355,5 +365,10 @@ def migrate_device(ctx, partition: SlabPartition, dist=None, device=None, wire=N
         recv.copy_(wrecv)
     if device.type == "cuda":
         torch.cuda.current_stream(device).synchronize()  # the rows have landed before the context's stream reads them
+    _mark()
     ctx.migrate_in(recv.data_ptr() if n_recv else 0, n_recv)  # n_recv == 0: marks the set as edited (same path on every rank)
+    _mark()
+    if _dbg and rank == 0:
+        print("migrate_device ms: count %.2f gather %.2f out %.2f exchange %.2f in %.2f (sent %d recv %d)" % tuple(
+            [1e3 * (_t[i + 1] - _t[i]) for i in range(5)] + [n_sent, n_recv]), flush=True)
     return n_sent, n_recv
