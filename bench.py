@@ -509,7 +509,7 @@ def run_ours(args):
     if world == 1 and g2p2g_live_n > 0:
         g2p2g_ms_pass2, g2p2g_ms = g2p2g_ms, g2p2g_live_ms * args.steps / g2p2g_live_n  # the roofline uses the timed region's own launches
         achieved = A_G2P2G_SAND * npart * args.steps / (g2p2g_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "g2p2g_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        roof = {"bound": "hbm", "kernel": "g2p2g_cell_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": _ncu_traffic(), "peak_source": peak_src, "bytes_per_particle_substep": A_G2P2G_SAND,
                 "kernel_ms_per_launch": g2p2g_ms / args.steps,
                 "stage_ms_per_substep": dict(zip(["sort", "reset_grid", "estimate_dt", "g2p2g", "grid_update"], (stage_ms / args.steps).round(4).tolist()))}
