@@ -533,18 +533,27 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+G2P2G_SOURCES = ["spk_g2p2g.cu", "spk_g2p2g_kernel.cuh", "spk_updater.cuh", "spk_math.cuh", "spk_device.cuh", "spk_internal.cuh"]
+
+
 def _lib_sha16():
+    """identity of the benched G2P2G build: sha256 over the sources the kernel is compiled from (stable across rebuilds of the same
+    tree, unlike the bytes of the .so) and the nvcc flags"""
     import hashlib
-    from sparkl_b200 import _lib
+    from sparkl_b200 import build as b
     try:
-        return hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:16]
+        h = hashlib.sha256()
+        for f in G2P2G_SOURCES:
+            h.update(open(os.path.join(b.CSRC, f), "rb").read())
+        h.update(" ".join(b.FLAGS).encode())
+        return h.hexdigest()[:16]
     except Exception:
         return None
 
 
 def _ncu_traffic():
     """dram bytes per g2p2g launch from the committed `ncu --set full` summary (profiles/g2p2g_ncu_summary.json) — only when that
-    capture was taken with THIS build of the library (the summary records the library's sha256)"""
+    capture was taken with THIS build of the kernel (the summary records the sha256 of the kernel's sources and flags)"""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "g2p2g_ncu_summary.json")))
         if d.get("lib_sha16") and d["lib_sha16"] != _lib_sha16():

@@ -20,11 +20,10 @@ KEY = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
 
 
 def _lib_sha16():
-    import hashlib, os
-    try:
-        return hashlib.sha256(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sparkl_b200", "libsparkl_b200.so"), "rb").read()).hexdigest()[:16]
-    except Exception:
-        return None
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    return bench._lib_sha16()
 
 
 def launches(src, dst):
@@ -103,7 +102,7 @@ def kernel(src, dst, json_out=None):
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
         json.dump({"kernel": m.get("Kernel Name", ("?",))[0], "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
                    "duration_us": float(m["gpu__time_duration.sum"][0]), "source": dst + ".md", "lib_sha16": _lib_sha16(),
-                   "note": "lib_sha16 = sha256 of sparkl_b200/libsparkl_b200.so at capture time; bench.py reports `traffic` only for the same build"},
+                   "note": "lib_sha16 = sha256 over the G2P2G kernel's sources and nvcc flags at capture time (bench.py: _lib_sha16); bench.py reports `traffic` only for the same build"},
                   open(json_out, "w"), indent=1)
 
 
