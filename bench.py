@@ -107,6 +107,22 @@ class ClockSampler:
     def __init__(self, index):
         self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         self.t0 = self.t1 = self.t_load0 = None
+        self.head = []
+
+    def wait_ready(self, timeout=20.0):
+        """blocks until the sampler has delivered its first sample (interpreter start + NVML initialisation take a second or two on a fresh
+        box; the loaded phases of the default run are shorter than that)"""
+        import select
+        t_end = time.time() + timeout
+        while time.time() < t_end and self.proc.poll() is None:
+            r, _, _ = select.select([self.proc.stdout], [], [], 0.25)
+            if r:
+                line = self.proc.stdout.readline()
+                if not line:
+                    break
+                self.head.append(line)
+                if len(line.split()) == 3 or line.startswith("err"):
+                    break
 
     def load_begins(self):
         self.t_load0 = time.time()
@@ -128,7 +144,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        return summarize_clock_samples(out.splitlines(), self.t0, self.t1, self.t_load0 if self.t_load0 is not None else self.t0, t_load1, self.REASONS)
+        return summarize_clock_samples([l.rstrip("\n") for l in self.head] + out.splitlines(), self.t0, self.t1, self.t_load0 if self.t_load0 is not None else self.t0, t_load1, self.REASONS)
 
 
 def build_scene(rank, world, dims, config="S4M"):
@@ -373,6 +389,7 @@ def run_ours(args):
     # bring the scene into a loaded state first (material compressing under gravity, F != I): the rest lattice makes the
     # per-particle SVD converge in one sweep and would flatter the kernel.  Untimed, not part of the warm-up contract.
     if sampler:
+        sampler.wait_ready()
         sampler.load_begins()
     for _ in range(args.settle):
         one_substep()
