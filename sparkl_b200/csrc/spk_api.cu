@@ -1012,7 +1012,7 @@ int spk_stage_estimate_dt(spk_ctx* c, float min_dt, float max_dt, float* dt_out)
         if (spk_dist_active(c)) CK(spk_dist_launch_barrier(c, 2)); // dt_acc <- min over the ranks
         int rc = read_counters(c);
         if (rc) return rc;
-        if (c->n) c->dt_acc_host = c->h_counters->dt_acc;
+        if (c->n || spk_dist_active(c)) c->dt_acc_host = c->h_counters->dt_acc; // (multi-GPU: the minimum over the ranks, also for a rank without particles)
     }
     if (dt_out) *dt_out = host_dt_into_sec(c->dt_acc_host);
     return SPK_OK;
@@ -1221,10 +1221,11 @@ int spk_step(spk_ctx** ctxs, size_t nctx, const SpkSolverParameters* params, con
     int rc;
     if ((rc = spk_frame_begin(c, params))) return rc;
     const bool dist = spk_dist_active(c);
-    if (dist && c->n == 0) return SPK_ESTATE; // every rank takes part in the device-side barriers
     if (dist && c->h_counters->pad[1]) return SPK_EPEER; // a peer was given up on during an earlier call: the ranks have diverged
     if (c->launcher.timestep_started && (rc = c->launcher.timestep_started(c->launcher.user))) return rc; // :299-302
-    if (params->dt == 0.0f || c->n == 0) { // nothing to simulate (:305-309)
+    // nothing to simulate (:305-309) — except that a rank of a multi-GPU run that owns no particle (yet) still walks through the substeps:
+    // it takes part in the device-side barriers and in the dt minimum, with an empty grid
+    if (params->dt == 0.0f || (c->n == 0 && !dist)) {
         if (simulated_time_out) *simulated_time_out = params->dt;
         return SPK_OK;
     }

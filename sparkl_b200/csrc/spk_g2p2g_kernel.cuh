@@ -1185,7 +1185,12 @@ inline cudaError_t spk_launch_g2p2g_with(spk_ctx* c, float dt, const void* user 
     GridBuffers& next = c->grid[1 - c->gcur];
     GridBuffers& prev = c->grid[c->gcur];
     const uint32_t nd = c->h_counters->ndispatch;
-    if (nd == 0) return cudaSuccess; // never launch with 0 CTAs (cuda_mpm_pipeline.rs:485-486)
+    if (nd == 0) { // never launch with 0 CTAs (cuda_mpm_pipeline.rs:485-486)
+        // a rank of a multi-GPU run without particles: it still follows the same path as its peers in the next substep (fused dt
+        // candidate — it contributes "no bound" — rather than the stand-alone dt kernel, which ends in a barrier of its own)
+        if (c->dist.world > 1) { c->sorted_valid = false; c->dt_cache_valid = true; c->dt_raw_host_valid = false; c->counters_fresh = false; }
+        return cudaSuccess;
+    }
     G2P2GParams P;
     P.src = c->pb[c->cur];
     P.dst = c->pb[1 - c->cur];
@@ -1299,7 +1304,7 @@ template <class Updater>
 inline cudaError_t spk_launch_estimate_dt_with(spk_ctx* c, float min_dt, float max_dt, const void* user = nullptr) {
     using namespace spk_g2p2g_detail;
     const uint32_t n = (uint32_t)c->n;
-    if (!n) return cudaSuccess;
+    if (!n && !(c->dist.world > 1)) return cudaSuccess;
     const ParticleBuffers& pb = c->pb[c->cur];
     int blocks = (int)((n + DT_THREADS - 1) / DT_THREADS);
     const int maxb = c->sm_count * 8;
@@ -1307,6 +1312,7 @@ inline cudaError_t spk_launch_estimate_dt_with(spk_ctx* c, float min_dt, float m
     *c->h_upload = c->dt_acc_host;
     { cudaError_t e = cudaMemcpyAsync(&c->d_counters->dt_acc, c->h_upload, 8, cudaMemcpyHostToDevice, c->stream); if (e != cudaSuccess) return e; }
     c->counters_fresh = false;
+    if (!n) return cudaSuccess; // (multi-GPU rank without particles: the frame's dt is its entry in the minimum over the ranks)
     estimate_dt_kernel<Updater><<<blocks, DT_THREADS, 0, c->stream>>>(pb.a0, pb.a1, pb.a3, pb.a4, c->vel, n, c->models, c->cell_width, min_dt, max_dt, c->d_counters, user);
     c->launches += 1;
     return cudaGetLastError();

@@ -397,6 +397,9 @@ cudaError_t spk_launch_sort_bin(spk_ctx* c) {
                                                                                         c->slot_of, c->rank_of, c->d_counters);
         cell_scan_kernel<<<(g.cap_hash + 8 * CELL_SCAN_SLOTS - 1) / (8 * CELL_SCAN_SLOTS), 256, 0, s>>>(g.keys, g.cap_hash, c->cell_cnt, c->slot_cnt, c->d_counters, c->dist_bbox, c->mslot, mcap);
         c->launches += 2;
+    } else { // no particles (a rank of a multi-GPU run may own none): the empty bounding box cell_scan_kernel would have written
+        if ((e = cudaMemsetAsync(c->dist_bbox, 0xff, 12, s)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(c->dist_bbox + 3, 0, 12, s)) != cudaSuccess) return e;
     }
     const uint32_t ntiles = (mcap + SCAN_TILE - 1) / SCAN_TILE;
     if ((size_t)ntiles * sizeof(Triple) > c->staging_bytes) return cudaErrorInvalidValue; // sized by spk_stage_sort (ensure_staging) before the launch

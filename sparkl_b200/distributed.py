@@ -253,8 +253,8 @@ def unpack_records(rec: np.ndarray):
 def migrate(engine, gids: np.ndarray, partition: SlabPartition, dist=None, device=None):
     """Collective.  Moves every particle of `engine` (a SingleGpuMpmContext, or the oracle in CPU tests) whose block left this
     rank's slab to the rank that owns it, and re-uploads the local set.  `gids` are the global ids of the local particles (in
-    local particle-id order).  Returns (new_gids, number sent, number received).  Every rank must keep at least one particle when
-    the NVLink path is attached (its device-side barriers need every rank)."""
+    local particle-id order).  Returns (new_gids, number sent, number received).  (A rank may end up without particles:
+    the NVLink path keeps it in its device-side barriers.)"""
     import torch
     import torch.distributed as tdist
     dist = dist or tdist
