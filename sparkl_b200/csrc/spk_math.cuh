@@ -455,7 +455,6 @@ __device__ __forceinline__ Mat3 neo_hookean_stress(const DevModel& m, float phas
 template <uint32_t MM = SPK_MM_ALL>
 __device__ __forceinline__ float particle_dt_candidate(const DevModel& m, float h, float mass, float volume0, float f00, float elastic_hardening, float vx, float vy, float vz) {
     const float vn2 = vx * vx + vy * vy + vz * vz;
-    const float vn = sqrtf(vn2);
     float cand = FLT_MAX;
     bool velocity_bound = false;
     constexpr uint32_t solids = SPK_MM_C(SPK_CONSTITUTIVE_COROTATED) | SPK_MM_C(SPK_CONSTITUTIVE_NEO_HOOKEAN);
@@ -469,9 +468,13 @@ __device__ __forceinline__ float particle_dt_candidate(const DevModel& m, float 
         const float lambda = m.c[1], mu = m.c[2];
         const float bulk = (lambda + 2.f * mu / 3.f) * hard, shear = mu * hard;
         const float density0 = mass / volume0;
-        const float c_dir = sqrtf((bulk + 4.f / 3.f * shear) * 1.f / density0);
-        cand = m.c[0] * cw / fmaxf(vn, c_dir);
-        velocity_bound = true;
+        // max(|v|, c_dir) = sqrt(max(v^2, c_dir^2)) bit for bit (sqrtf is monotone and correctly rounded; a NaN operand drops out of
+        // fmaxf on either side of the identity): one square root instead of two
+        const float denom = sqrtf(fmaxf(vn2, (bulk + 4.f / 3.f * shear) * 1.f / density0));
+        cand = m.c[0] * cw / denom;
+        // the velocity bound h / |v| below cannot be the smaller one when the numerator is at most h and the denominator at least |v|
+        // (correctly rounded * and / are monotone): skipped, with its square root and division, for the usual CFL coefficient <= 1
+        velocity_bound = !(!nh && m.c[0] <= 1.f);
         }
     } else if (model_is_fluid<MM>(m)) { // eos_monaghan_sph.rs:72-99
         {
@@ -484,6 +487,6 @@ __device__ __forceinline__ float particle_dt_candidate(const DevModel& m, float 
         velocity_bound = true;
         }
     } // Custom: ActiveTimestepBounds::NONE
-    if (velocity_bound) cand = fminf(cand, h / vn);
+    if (velocity_bound) cand = fminf(cand, h / sqrtf(vn2));
     return cand;
 }
