@@ -46,6 +46,8 @@ extern "C" {
     pub fn spk_particles_migrate_in(ctx: *mut SpkCtx, dev_records: *const SpkParticleRecord, n: usize) -> c_int;
     // MlsSolver::recompute_fluids_volumes as an explicit stage (sparkl_b200/csrc/spk_fluids.cu)
     pub fn spk_stage_recompute_fluids_volume(ctx: *mut SpkCtx) -> c_int;
+    /// box / per-axis bit counts of the Morton curve the last particle sort ranked the active blocks along (diagnostic; out: [u32; 8])
+    pub fn spk_grid_morton_box(ctx: *mut SpkCtx, out: *mut u32) -> c_int;
 }
 
 /// Wire format of one migrating particle (128 bytes in dim3): the six per-particle structs + a global id.
