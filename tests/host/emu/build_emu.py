@@ -64,7 +64,7 @@ def build(dim: int = 3, force: bool = False, tag: str = "", extra_flags=()) -> s
             with open(os.path.join(src_dir, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w") as fh:
                 fh.write(text)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-DSPK_EMU", f"-DSPK_DIM={dim}", "-I" + cuda_inc, "-I" + HERE, "-include", "cuda_emu.h"]
+    flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-U_FORTIFY_SOURCE", "-DSPK_EMU", f"-DSPK_DIM={dim}", "-I" + cuda_inc, "-I" + HERE, "-include", "cuda_emu.h"]
     flags += extra_flags
     objs = []
     for s in list(sources) + ["cuda_emu"]:
@@ -94,7 +94,7 @@ def build_example() -> str:
     with open(cpp, "w") as fh:
         fh.write(text)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-DSPK_EMU", "-DSPK_DIM=3", "-I" + cuda_inc, "-I" + HERE, "-I" + src_dir, "-include", "cuda_emu.h"]
+    flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-U_FORTIFY_SOURCE", "-DSPK_EMU", "-DSPK_DIM=3", "-I" + cuda_inc, "-I" + HERE, "-I" + src_dir, "-include", "cuda_emu.h"]
     # like the CUDA build of the example (its own .so with its own CUDA runtime), the emulated one carries its own copy of the CUDA
     # stand-ins, bound with -Bsymbolic: a real libcudart that some other module (torch) loaded into the process must not capture them
     subprocess.check_call(["g++"] + flags + ["-shared", "-Wl,-Bsymbolic", "-o", out, cpp, os.path.join(HERE, "cuda_emu.cpp")])

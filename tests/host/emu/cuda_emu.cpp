@@ -2,6 +2,7 @@
 // TEST INFRASTRUCTURE ONLY.
 #include "cuda_emu.h"
 
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <chrono>
@@ -15,12 +16,24 @@ Idx tid{0, 0, 0}, bid{0, 0, 0}, bdim{1, 1, 1}, gdim{1, 1, 1};
 
 namespace {
 enum State { READY, WAIT_BLOCK, WAIT_WARP, DONE };
+// Context switches: a fiber is ENTERED once with swapcontext (which installs its stack) and from then on switched with _setjmp / _longjmp:
+// glibc's swapcontext saves and restores the signal mask with two system calls per switch, and a kernel with a few CTA barriers switches
+// every one of its threads several times (the suite spent a third of its time in rt_sigprocmask).  Sanitizer builds keep swapcontext
+// (AddressSanitizer follows it, but not a longjmp onto another stack).
+#if defined(__SANITIZE_ADDRESS__) || defined(SPK_EMU_UCONTEXT_ONLY)
+#define EMU_FAST_SWITCH 0
+#else
+#define EMU_FAST_SWITCH 1
+#endif
 struct Fiber {
     ucontext_t ctx;
+    jmp_buf jb;
+    bool entered = false;
     char* stack = nullptr;
     State state = DONE;
     unsigned wait_mask = 0;
 };
+jmp_buf sched_jb;
 constexpr size_t STACK_BYTES = 512 * 1024;
 std::vector<Fiber> fibers;
 ucontext_t sched_ctx;
@@ -29,16 +42,34 @@ const std::function<void()>* body_fn = nullptr;
 unsigned long long scratch[32][32];
 alignas(128) unsigned char dyn_smem[232448];
 
+void to_scheduler(Fiber& f) {
+#if EMU_FAST_SWITCH
+    if (_setjmp(f.jb) == 0) _longjmp(sched_jb, 1);
+#else
+    swapcontext(&f.ctx, &sched_ctx);
+#endif
+}
+void to_fiber(Fiber& f) {
+#if EMU_FAST_SWITCH
+    if (_setjmp(sched_jb) == 0) {
+        if (f.entered) _longjmp(f.jb, 1);
+        f.entered = true;
+        swapcontext(&sched_ctx, &f.ctx); // first entry: onto the fiber's own stack (it comes back through sched_jb)
+    }
+#else
+    swapcontext(&sched_ctx, &f.ctx);
+#endif
+}
 void trampoline() {
     (*body_fn)();
     fibers[cur].state = DONE;
-    swapcontext(&fibers[cur].ctx, &sched_ctx);
+    to_scheduler(fibers[cur]);
 }
 void park(State s, unsigned mask) {
     Fiber& f = fibers[cur];
     f.state = s;
     f.wait_mask = mask;
-    swapcontext(&f.ctx, &sched_ctx);
+    to_scheduler(f);
 }
 void run_cta(unsigned nthreads) {
     if (fibers.size() < nthreads) fibers.resize(nthreads);
@@ -50,6 +81,7 @@ void run_cta(unsigned nthreads) {
         f.ctx.uc_stack.ss_size = STACK_BYTES;
         f.ctx.uc_link = &sched_ctx;
         makecontext(&f.ctx, trampoline, 0);
+        f.entered = false;
         f.state = READY;
     }
     // SPK_EMU_SCHEDULE=reverse runs the ready threads of a CTA (and the CTAs of a grid) in descending order: a read that is missing a
@@ -62,7 +94,7 @@ void run_cta(unsigned nthreads) {
             if (fibers[t].state != READY) continue;
             cur = (int)t;
             tid = Idx{t, 0, 0};
-            swapcontext(&sched_ctx, &fibers[t].ctx);
+            to_fiber(fibers[t]);
             ran = true;
         }
         // release warp-level waits: every live lane named by the mask has arrived with the same mask
