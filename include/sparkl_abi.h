@@ -457,7 +457,9 @@ int spk_halo_merge(spk_ctx* ctx, const uint64_t* dev_keys, const float* dev_payl
  * and the host dt minimum, src/cuda/cuda_mpm_pipeline.rs:393-398,458-472,512-532).  Every rank exports one descriptor,
  * the caller all-gathers them with whatever transport it has (MPI, torch.distributed, a file) and attaches; from then on
  * spk_step() runs the exchange itself with device-initiated NVLink loads / atomics and two device-side barriers per
- * substep.  Collective: every rank must make the same sequence of spk_step / upload calls; each rank must own particles. */
+ * substep.  Collective: every rank must make the same sequence of spk_step / upload calls.  A rank may own no
+ * particle (it takes part in the barriers and in the dt minimum with an empty grid); the shared arena does not grow, so a context that is to
+ * receive migrants later must be created with a block capacity for them. */
 typedef struct SpkDistDescriptor { unsigned char opaque[128]; } SpkDistDescriptor;
 int spk_dist_export(spk_ctx* ctx, SpkDistDescriptor* out);   /* after the particle upload, before the first step */
 int spk_dist_attach(spk_ctx* ctx, uint32_t rank, uint32_t world, const SpkDistDescriptor* all_ranks /* [world] */);
