@@ -26,6 +26,8 @@
 #ifndef SPK_MORTON_FACTOR
 #define SPK_MORTON_FACTOR 4 /* Morton-table entries per hash slot (power of two) */
 #endif
+static_assert(SPK_MORTON_FACTOR == 1 || SPK_MORTON_FACTOR == 2 || SPK_MORTON_FACTOR == 4,
+              "ensure_slot_scratch / ensure_staging (spk_api.cu) size the Morton table and the scan partials for at most 4 entries per hash slot");
 #ifndef SPK_PERM_ITEMS
 #define SPK_PERM_ITEMS 4
 #endif
